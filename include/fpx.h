@@ -1,0 +1,240 @@
+/*
+ * fpx.h -- C ABI of the B200 quorum-vote engine (libfpx.so).
+ *
+ * This is the drop-in boundary for the FrankenPaxos quorum-vote hot path.  The
+ * reference (mwhittaker/frankenpaxos, Scala) has no FFI; its extension surface
+ * is the Actor/Transport/Chan traits.  A JVM actor (GpuProxyLeader/GpuAcceptor,
+ * see INTEGRATION.md) batches the messages the transport delivers to it and
+ * hands each batch, in delivery order, to one of the entry points below.  Every
+ * entry point cites the reference handler it replaces.  Paths are relative to
+ * the reference root; S/ = shared/src/main/scala/frankenpaxos/.
+ *
+ * Conventions
+ *   - plain C, no CUDA / torch types in any signature;
+ *   - all integers are int32 little-endian (the JVM's Int), records are 16-byte
+ *     (or 8-byte) PODs that map 1:1 onto the protobuf fields of the reference;
+ *   - host entry points (`fpx_x`) take HOST pointers, copy in, run, copy out
+ *     and return when the results are in the caller's buffers;
+ *   - device entry points (`fpx_x_dev`) take DEVICE pointers, enqueue on the
+ *     engine's stream and return immediately; call fpx_sync() to collect the
+ *     error status and the output counts;
+ *   - a handle is not thread safe: the reference's contract is one
+ *     single-threaded event loop per actor (S/Transport.scala:37-39);
+ *   - return value 0 = ok, negative = fpx_status.  The reference has no error
+ *     codes: handlers call logger.fatal (process exit / AssertionError under
+ *     FakeLogger, S/FakeLogger.scala:11-14) or `require` (IllegalArgument).  A
+ *     negative status is that event; *err_index receives the index, within the
+ *     batch, of the FIRST offending record in delivery order (or -1).
+ */
+#ifndef FPX_H_
+#define FPX_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FPX_ABI_VERSION 1
+
+/* ---- records ------------------------------------------------------------ */
+
+/* Phase2a as delivered to a proxy leader (arm) or to an acceptor (vote).
+ * S/multipaxos/MultiPaxos.proto:273-280 {slot, round, command_batch_or_noop}.
+ * value_id is a caller-owned 32-bit handle for the command batch bytes (the
+ * bytes themselves never influence the path).  dst = group<<16 | acceptor is
+ * the recipient the transport delivered this copy to; it is ignored by
+ * fpx_proxyleader_arm. */
+typedef struct { int32_t slot, round, value_id, dst; } fpx_p2a;
+
+/* Phase2b == the four required int32 fields of
+ * S/multipaxos/MultiPaxos.proto:282-290, in field order. */
+typedef struct { int32_t group, acceptor, slot, round; } fpx_p2b;
+
+/* Chosen{slot, value} S/multipaxos/MultiPaxos.proto (Chosen).  One record per
+ * chosen (slot, round); the reference sends it to every replica in config
+ * order (S/multipaxos/ProxyLeader.scala:246-253) -- that fan-out is the
+ * caller's. */
+typedef struct { int32_t slot, value_id; } fpx_chosen;
+
+/* Nack{round} to leaders(phase2a.round % numLeaders)
+ * (S/multipaxos/Acceptor.scala:192-199). */
+typedef struct { int32_t leader, round; } fpx_nack;
+
+/* ---- status ------------------------------------------------------------- */
+
+typedef enum {
+  FPX_OK = 0,
+  FPX_ERR_INVALID_ARG = -1,        /* null pointer, n < 0, n > max_batch ...           */
+  FPX_ERR_CONFIG = -2,             /* Config.checkValid() would `require`-fail          */
+  FPX_ERR_CUDA = -3,               /* CUDA runtime error (fpx_last_error has the text)  */
+  FPX_ERR_UNKNOWN_SLOT_ROUND = -4, /* Phase2b for a (slot,round) never armed:
+                                      logger.fatal, S/multipaxos/ProxyLeader.scala:220-225 */
+  FPX_ERR_BAD_ACCEPTOR = -5,       /* (group,acceptor) not a member of the quorum system:
+                                      Grid.isWriteQuorum `require`, S/quorums/Grid.scala:44-47;
+                                      also: group != slot % numAcceptorGroups (non-flexible)  */
+  FPX_ERR_SLOT_RANGE = -6,         /* slot < 0, >= capacity, or not in this shard       */
+  FPX_ERR_ROUND_RANGE = -7,        /* round < 0 or > FPX_MAX_ROUND                      */
+  FPX_ERR_OVERFLOW_FULL = -8,      /* more concurrent secondary (slot,round) keys than
+                                      config.overflow_capacity                           */
+  FPX_ERR_CONFLICT = -9,           /* same key delivered twice with different values, and
+                                      the in-batch order could not be resolved exactly   */
+  FPX_ERR_NO_DEVICE = -10,
+  FPX_ERR_UNSUPPORTED = -11
+} fpx_status;
+
+#define FPX_MAX_ROUND 0x7ffffffe
+#define FPX_MAX_ACCEPTORS 32       /* total acceptors (groups*per_group) per engine     */
+#define FPX_MAX_VOTERS_PER_SLOT 30 /* acceptors that can vote on one slot               */
+
+/* ---- configuration ------------------------------------------------------ */
+
+typedef enum {
+  FPX_MULTIPAXOS = 0,       /* S/multipaxos: ProxyLeader + Acceptor                      */
+  FPX_MENCIUS = 1,          /* S/mencius: same handlers, quorum f+1 of the slot's group  */
+  FPX_VANILLA_MENCIUS = 2   /* S/vanillamencius/Server.scala: per-slot round, self vote  */
+} fpx_protocol;
+
+/* Mirrors the fields of S/multipaxos/Config.scala:6-31 that the path reads.
+ * Validity rules are those of Config.checkValid (S/multipaxos/Config.scala:32-147):
+ *   f >= 1; num_leaders >= f+1; num_replicas >= f+1;
+ *   !flexible: every group has exactly 2f+1 acceptors;
+ *    flexible: groups = grid rows, acceptors_per_group = grid columns,
+ *              min(rows, cols) - 1 >= f. */
+typedef struct {
+  int32_t struct_size;          /* = sizeof(fpx_config), ABI guard                      */
+  int32_t protocol;             /* fpx_protocol                                          */
+  int32_t f;
+  int32_t num_acceptor_groups;  /* non-flexible: G; flexible: grid rows                  */
+  int32_t acceptors_per_group;  /* non-flexible: 2f+1; flexible: grid columns            */
+  int32_t flexible;             /* 0 / 1                                                 */
+  int32_t num_leaders;
+  int32_t num_replicas;
+  int32_t slot_capacity;        /* GLOBAL slots [0, slot_capacity) the log can hold      */
+  int32_t overflow_capacity;    /* secondary (slot, round) keys (two live rounds of one
+                                   slot after a leader change); power of two or 0        */
+  int32_t max_batch;            /* largest n of any one call                             */
+  int32_t device;               /* CUDA ordinal                                          */
+  int32_t shard_index;          /* this engine owns slots with slot % shard_count ==     */
+  int32_t shard_count;          /*   shard_index (1 GPU: 0 / 1)                          */
+} fpx_config;
+
+typedef struct fpx_engine fpx_engine; /* opaque */
+
+/* ---- life cycle --------------------------------------------------------- */
+
+int fpx_abi_version(void);
+const char* fpx_strerror(int status);
+const char* fpx_last_error(const fpx_engine* e); /* text of the last CUDA failure     */
+
+/* Actor constructors of the reference: `new ProxyLeader(address, transport,
+ * logger, config, ...)` S/multipaxos/ProxyLeader.scala:67-75 and `new
+ * Acceptor(...)` S/multipaxos/Acceptor.scala:59-66 both start with
+ * config.checkValid(); so does this.  One engine holds the state of every
+ * acceptor of the config plus one proxy leader plus one replica log. */
+int fpx_create(fpx_engine** out, const fpx_config* cfg);
+void fpx_destroy(fpx_engine* e);
+int fpx_reset(fpx_engine* e); /* back to the freshly constructed state */
+
+/* ---- host-pointer entry points (the reference-facing calls) ------------- */
+
+/* ProxyLeader.handlePhase2a, S/multipaxos/ProxyLeader.scala:175-215.
+ * For each record in delivery order: if (slot, round) is unknown create
+ * Pending(value, {}) (:213); a duplicate (slot, round) is ignored (:177-183).
+ * Recipient choice (:190-196) uses the JVM's global RNG and is NOT reproduced:
+ * the caller forwards the Phase2a copies and the acceptor batch carries the
+ * recipients actually chosen. */
+int fpx_proxyleader_arm(fpx_engine* e, const fpx_p2a* in, int32_t n, int64_t* err_index);
+
+/* Acceptor.handlePhase2a, S/multipaxos/Acceptor.scala:184-220, for the
+ * interleaved delivery stream of ALL acceptors of the config (record i goes to
+ * acceptor in[i].dst).  Per acceptor, in delivery order: round_msg < round ->
+ * Nack(round) to leaders(round_msg % numLeaders) (:192-199); else round =
+ * round_msg, states(slot) = (round, value), maxVotedSlot = max(..) (:204-209),
+ * reply Phase2b(group, index, slot, round) (:211-219).
+ * out_p2b / out_nack receive the replies in delivery order of the messages
+ * that caused them; capacity n each. */
+int fpx_acceptor_phase2a(fpx_engine* e, const fpx_p2a* in, int32_t n,
+                         fpx_p2b* out_p2b, int32_t* n_p2b,
+                         fpx_nack* out_nack, int32_t* n_nack, int64_t* err_index);
+
+/* ProxyLeader.handlePhase2b, S/multipaxos/ProxyLeader.scala:217-258, with the
+ * quorum test of :238-243: non-flexible `phase2bs.size < f+1`, flexible
+ * Grid.isWriteQuorum (S/quorums/Grid.scala:43-50).  Unknown (slot, round) is
+ * fatal (:220-225) -> FPX_ERR_UNKNOWN_SLOT_ROUND; Done is ignored (:227-232);
+ * the vote map assignment is idempotent per acceptor (:237).  out receives one
+ * Chosen per (slot, round) whose quorum completes in this batch, ORDERED BY THE
+ * INDEX OF THE COMPLETING VOTE (the order the reference's sends happen in);
+ * capacity n. */
+int fpx_proxyleader_phase2b(fpx_engine* e, const fpx_p2b* in, int32_t n,
+                            fpx_chosen* out, int32_t* n_out, int64_t* err_index);
+
+/* Replica.handleChosen, S/multipaxos/Replica.scala:572-627: first Chosen per
+ * slot wins (:580-588); later ones are redundant.  Then the executable prefix
+ * (executeLog stops at the first hole, :394-402). */
+int fpx_replica_chosen(fpx_engine* e, const fpx_chosen* in, int32_t n, int64_t* err_index);
+
+/* First GLOBAL slot of this shard's residue class that is not yet chosen, as
+ * a global slot number (shard_count==1: the replica's executedWatermark had it
+ * executed everything it could). */
+int fpx_chosen_watermark(fpx_engine* e, int32_t* out);
+
+/* Batched quorum predicates over member bitmasks (bit g*per_group+a set <=>
+ * acceptor (g,a) in the set; bit 31 set <=> the set contains a non-member):
+ * which: 0 isReadQuorum 1 isWriteQuorum 2 isSuperSetOfReadQuorum
+ * 3 isSuperSetOfWriteQuorum; flexible -> Grid (S/quorums/Grid.scala:35-56),
+ * else SimpleMajority over all acceptors of group 0
+ * (S/quorums/SimpleMajority.scala:41-55).  out[i] = 0/1, or 2 where the
+ * reference `require` would throw (non-member passed to is{Read,Write}Quorum). */
+int fpx_quorum_eval(fpx_engine* e, int32_t which, const uint32_t* masks, int32_t n, uint8_t* out);
+
+/* ---- state read-back (Phase1b / parity) --------------------------------- */
+
+/* Acceptor (group, acceptor): scalars `round` (S/multipaxos/Acceptor.scala:95)
+ * and `maxVotedSlot` (:104), and for the n_slots GLOBAL slots starting at
+ * first_slot (only slots of this shard are written; others get -1) the vote
+ * (voteRound, voteValue) of `states` (:98); voteRound = -1 where no vote. */
+int fpx_snapshot_acceptor(fpx_engine* e, int32_t group, int32_t acceptor,
+                          int32_t* round, int32_t* max_voted_slot,
+                          int32_t first_slot, int32_t n_slots,
+                          int32_t* vote_round, int32_t* vote_value);
+
+/* Replica log read-back: value_id per global slot, -1 = hole. */
+int fpx_snapshot_log(fpx_engine* e, int32_t first_slot, int32_t n_slots, int32_t* value_id);
+
+/* ---- device-pointer entry points (inputs already resident in HBM) ------- */
+
+/* Same semantics, DEVICE pointers, asynchronous on fpx_stream(e).  Output
+ * counts and the error status are collected by fpx_sync. */
+int fpx_proxyleader_arm_dev(fpx_engine* e, const fpx_p2a* d_in, int32_t n);
+int fpx_acceptor_phase2a_dev(fpx_engine* e, const fpx_p2a* d_in, int32_t n,
+                             fpx_p2b* d_out_p2b, fpx_nack* d_out_nack);
+int fpx_proxyleader_phase2b_dev(fpx_engine* e, const fpx_p2b* d_in, int32_t n,
+                                fpx_chosen* d_out);
+int fpx_replica_chosen_dev(fpx_engine* e, const fpx_chosen* d_in, int32_t n);
+/* as fpx_replica_chosen_dev, but n is read on the device from the count the
+ * last fpx_proxyleader_phase2b_dev produced (no host round trip) */
+int fpx_replica_chosen_last_dev(fpx_engine* e, const fpx_chosen* d_in);
+int fpx_chosen_watermark_dev(fpx_engine* e, int32_t* d_out);
+
+typedef struct {
+  int32_t status;        /* first (lowest record index) error of any call since last sync */
+  int32_t reserved;
+  int64_t err_index;
+  int32_t n_p2b, n_nack; /* of the last fpx_acceptor_phase2a_dev                         */
+  int32_t n_chosen;      /* of the last fpx_proxyleader_phase2b_dev                      */
+  int32_t watermark;     /* of the last fpx_chosen_watermark_dev                         */
+} fpx_sync_result;
+
+int fpx_sync(fpx_engine* e, fpx_sync_result* out);
+
+/* The engine's CUDA stream (a cudaStream_t) so a caller can order its own work
+ * (events, NCCL collectives) with the engine's. */
+void* fpx_stream(fpx_engine* e);
+/* Kernels launched by this handle since creation (bench.py's gpu_launches). */
+int64_t fpx_launch_count(const fpx_engine* e);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FPX_H_ */

@@ -1,0 +1,700 @@
+// fpx_oracle.cc -- CPU ORACLE.  TEST INFRASTRUCTURE ONLY.
+//
+// A deliberately naive, single-threaded restatement of the FrankenPaxos
+// quorum-vote path with the reference's own data structures (ordered/hash maps
+// keyed the way the Scala code keys them, sets of node ids for the quorum
+// systems, watermark + overflow set for IntPrefixSet).  Nothing in the product
+// (frankenpaxos_b200/, libfpx.so) links, imports or calls this file; only
+// tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl
+// reference legs do.
+//
+// Pinning: the reference is Scala and cannot be built or run here (no JVM, no
+// sbt, no network), so this restatement is pinned by the known-answer tests the
+// reference ships for the helpers on the path, transcribed as data into
+// tests/golden/ by tests/golden/make_golden.py:
+//   quorums (GridTest, SimpleMajorityTest, UnanimousWrites), IntPrefixSetTest,
+//   RoundSystemTest (ClassicRoundRobin), TopOneTest, QuorumWatermarkTest,
+//   BufferMapTest.
+// The HANDLERS (Acceptor.handlePhase2a, ProxyLeader.handlePhase2b, epaxos
+// Replica handlers) have no known-answer test in the reference -- they are only
+// exercised by randomized simulation with invariant checks -- so handler-level
+// parity is "parity unpinned" by the reference's own tests; it is anchored on
+// the worked micro-trace of SURVEY.md 8(g) and on the reference's invariants
+// (tests/test_invariants.py).
+//
+// Citations: S/ = shared/src/main/scala/frankenpaxos/ in the reference tree.
+
+#include <algorithm>
+#include <cstdint>
+#include <cstring>
+#include <map>
+#include <set>
+#include <unordered_map>
+#include <vector>
+
+namespace fpo {
+
+// ---------------------------------------------------------------------------
+// quorums  (S/quorums/QuorumSystem.scala:16-24)
+// ---------------------------------------------------------------------------
+using NodeSet = std::set<int>;
+
+static bool subset_of(const NodeSet& a, const NodeSet& b) {
+  for (int x : a)
+    if (!b.count(x)) return false;
+  return true;
+}
+
+// Result of a predicate that may `require`-throw.
+enum Tri { kFalse = 0, kTrue = 1, kThrows = 2 };
+
+// S/quorums/Grid.scala:5-57
+struct Grid {
+  std::vector<NodeSet> rows;  // gridSeqSet
+  NodeSet nodes;              // gridSetSet.flatten
+  bool valid = true;
+  explicit Grid(const std::vector<std::vector<int>>& grid) {
+    if (grid.empty()) { valid = false; return; }              // :9-12
+    for (auto& r : grid) {
+      if (r.size() != grid[0].size()) valid = false;          // :14-17
+      rows.emplace_back(r.begin(), r.end());
+      nodes.insert(r.begin(), r.end());
+    }
+  }
+  bool superset_read(const NodeSet& xs) const {               // :52-53
+    for (auto& row : rows)
+      if (subset_of(row, xs)) return true;
+    return false;
+  }
+  bool superset_write(const NodeSet& xs) const {              // :55-56
+    for (auto& row : rows) {
+      bool any = false;
+      for (int x : row)
+        if (xs.count(x)) { any = true; break; }
+      if (!any) return false;
+    }
+    return true;
+  }
+  Tri is_read(const NodeSet& xs) const {                      // :35-41
+    if (!subset_of(xs, nodes)) return kThrows;
+    return superset_read(xs) ? kTrue : kFalse;
+  }
+  Tri is_write(const NodeSet& xs) const {                     // :43-50
+    if (!subset_of(xs, nodes)) return kThrows;
+    return superset_write(xs) ? kTrue : kFalse;
+  }
+};
+
+// S/quorums/SimpleMajority.scala:19-56
+struct SimpleMajority {
+  NodeSet members;
+  int quorum_size;                                            // :30
+  explicit SimpleMajority(const NodeSet& m) : members(m), quorum_size((int)m.size() / 2 + 1) {}
+  Tri is_read(const NodeSet& xs) const {                      // :41-47
+    if (!subset_of(xs, members)) return kThrows;
+    return (int)xs.size() >= quorum_size ? kTrue : kFalse;
+  }
+  Tri is_write(const NodeSet& xs) const { return is_read(xs); }  // :49
+  bool superset_read(const NodeSet& xs) const {               // :51-52
+    int c = 0;
+    for (int x : xs) c += members.count(x) ? 1 : 0;
+    return c >= quorum_size;
+  }
+  bool superset_write(const NodeSet& xs) const { return superset_read(xs); }  // :54-55
+};
+
+// S/quorums/UnanimousWrites.scala: any single member is a read quorum, all
+// members are the only write quorum.
+struct UnanimousWrites {
+  NodeSet members;
+  explicit UnanimousWrites(const NodeSet& m) : members(m) {}
+  Tri is_read(const NodeSet& xs) const {
+    if (!subset_of(xs, members)) return kThrows;
+    return xs.size() >= 1 ? kTrue : kFalse;
+  }
+  Tri is_write(const NodeSet& xs) const {
+    if (!subset_of(xs, members)) return kThrows;
+    return xs.size() >= members.size() ? kTrue : kFalse;
+  }
+  bool superset_read(const NodeSet& xs) const {
+    for (int x : xs)
+      if (members.count(x)) return true;
+    return false;
+  }
+  bool superset_write(const NodeSet& xs) const { return subset_of(members, xs); }
+};
+
+// ---------------------------------------------------------------------------
+// roundsystem  (S/roundsystem/RoundSystem.scala:60-87)
+// ---------------------------------------------------------------------------
+struct ClassicRoundRobin {
+  int n;
+  int leader(int round) const { return round % n; }           // :63
+  int next_classic_round(int leader_index, int round) const { // :66-81
+    if (round < 0) return leader_index;
+    int smallest = n * (round / n);
+    int offset = leader_index % n;
+    if (smallest + offset > round) return smallest + offset;
+    return smallest + n + offset;
+  }
+};
+
+// ---------------------------------------------------------------------------
+// compact.IntPrefixSet  (S/compact/IntPrefixSet.scala:206-432)
+// ---------------------------------------------------------------------------
+struct IntPrefixSet {
+  int watermark = 0;
+  std::set<int> values;
+
+  IntPrefixSet() {}
+  IntPrefixSet(int w, std::set<int> v) : watermark(w), values(std::move(v)) { compact(); }  // :212
+  static IntPrefixSet from_set(const std::set<int>& xs) { return IntPrefixSet(0, xs); }
+
+  void compact() {                                            // :426-431
+    while (values.count(watermark)) {
+      values.erase(watermark);
+      watermark += 1;
+    }
+  }
+  bool operator==(const IntPrefixSet& o) const {              // :214-221
+    return watermark == o.watermark && values == o.values;
+  }
+  bool add(int x) {                                           // :236-246
+    if (x < watermark) return false;
+    bool fresh = values.insert(x).second;
+    compact();
+    return fresh;
+  }
+  bool contains(int x) const { return x < watermark || values.count(x); }  // :248-251
+  IntPrefixSet set_union(const IntPrefixSet& o) const {       // :253-259
+    int w = std::max(watermark, o.watermark);
+    std::set<int> v;
+    for (int x : values) if (x >= w) v.insert(x);
+    for (int x : o.values) if (x >= w) v.insert(x);
+    return IntPrefixSet(w, v);
+  }
+  IntPrefixSet diff(const IntPrefixSet& o) const {            // :261-288
+    std::set<int> v;
+    if (o.watermark == 0 && o.values.empty()) {
+      return IntPrefixSet(watermark, values);
+    } else if (o.watermark == 0) {
+      int mn = *o.values.begin();
+      if (mn >= watermark) {
+        v = values;
+        for (int x : o.values) v.erase(x);
+        return IntPrefixSet(watermark, v);
+      }
+      v = values;
+      for (int x = mn; x < watermark; ++x) v.insert(x);
+      for (int x : o.values) v.erase(x);
+      return IntPrefixSet(mn, v);
+    } else if (o.watermark <= watermark) {
+      v = values;
+      for (int x = o.watermark; x < watermark; ++x) v.insert(x);
+      for (int x : o.values) v.erase(x);
+      return IntPrefixSet(0, v);
+    } else {
+      for (int x : values) if (x >= o.watermark) v.insert(x);
+      for (int x : o.values) v.erase(x);
+      return IntPrefixSet(0, v);
+    }
+  }
+  void retain_ge(int w) {
+    for (auto it = values.begin(); it != values.end();)
+      it = (*it >= w) ? std::next(it) : values.erase(it);
+  }
+  void add_all(const IntPrefixSet& o) {                       // :317-351, the four-way branch
+    if (values.empty() && o.values.empty()) {
+      watermark = std::max(watermark, o.watermark);
+    } else if (!values.empty() && o.values.empty()) {
+      if (watermark >= o.watermark) {
+      } else {
+        watermark = o.watermark;
+        retain_ge(watermark);
+        compact();
+      }
+    } else if (values.empty() && !o.values.empty()) {
+      values = o.values;
+      if (o.watermark >= watermark) {
+        watermark = o.watermark;
+      } else {
+        retain_ge(watermark);
+        compact();
+      }
+    } else {
+      if (watermark >= o.watermark) {
+        for (int x : o.values) if (x >= watermark) values.insert(x);
+        compact();
+      } else {
+        watermark = o.watermark;
+        retain_ge(o.watermark);
+        values.insert(o.values.begin(), o.values.end());
+        compact();
+      }
+    }
+  }
+  void subtract_all(const IntPrefixSet& o) {                  // :353-386
+    if ((watermark == 0 && values.empty()) || (o.watermark == 0 && o.values.empty())) return;
+    if (o.watermark == 0) {
+      int mn = *o.values.begin();
+      if (mn >= watermark) {
+        for (int x : o.values) values.erase(x);
+      } else {
+        for (int i = mn + 1; i < watermark; ++i) values.insert(i);
+        for (int x : o.values) values.erase(x);
+        watermark = mn;
+      }
+    } else if (watermark == 0) {
+      retain_ge(o.watermark);
+      for (int x : o.values) values.erase(x);
+    } else if (o.watermark <= watermark) {
+      for (int i = o.watermark; i < watermark; ++i) values.insert(i);
+      for (int x : o.values) values.erase(x);
+      watermark = 0;
+    } else {
+      retain_ge(o.watermark);
+      for (int x : o.values) values.erase(x);
+      watermark = 0;
+    }
+  }
+  void subtract_one(int x) {                                  // :388-398
+    if (x >= watermark) {
+      values.erase(x);
+    } else {
+      for (int i = x + 1; i < watermark; ++i) values.insert(i);
+      watermark = x;
+    }
+  }
+  int size() const { return watermark + (int)values.size(); } // :400
+  std::set<int> materialize() const {                         // :409
+    std::set<int> s = values;
+    for (int i = 0; i < watermark; ++i) s.insert(i);
+    return s;
+  }
+};
+
+// IntPrefixSet.DiffIterator (S/compact/IntPrefixSet.scala:53-186): a LAZY iterator
+// over me \ other that observes later mutations of `other` (the watermark
+// iterator re-reads other.watermark / other.values on every step).
+struct DiffIterator {
+  const IntPrefixSet* me;
+  const IntPrefixSet* other;
+  int x = 0;                       // WatermarkIterator cursor (:118)
+  bool in_values = false;
+  std::vector<int> vals;           // snapshot of me.values.iterator
+  size_t vi = 0;
+  bool cached = false;             // OptionIterator.cached (:69)
+  bool cached_has = false;
+  int cached_val = 0;
+
+  DiffIterator(const IntPrefixSet* m, const IntPrefixSet* o)
+      : me(m), other(o), vals(m->values.begin(), m->values.end()) {}
+
+  bool watermark_next(int* out) {  // WatermarkIterator.getNext (:131-186)
+    int from = x, to = me->watermark;
+    if (from >= to) return false;
+    if (to <= other->watermark) return false;
+    int start = std::max(from, other->watermark);
+    if (!other->values.empty()) {
+      while (other->values.count(start)) {
+        start += 1;
+        if (start >= to) return false;
+      }
+    }
+    *out = start;
+    x = start + 1;
+    return true;
+  }
+  bool values_next(int* out) {     // ValuesIterator.getNext (:96-111)
+    while (vi < vals.size()) {
+      int v = vals[vi++];
+      if (v < other->watermark || other->values.count(v)) continue;
+      *out = v;
+      return true;
+    }
+    return false;
+  }
+  bool get_next(int* out) {
+    if (!in_values) {
+      if (watermark_next(out)) return true;
+      in_values = true;
+    }
+    return values_next(out);
+  }
+  bool has_next() {
+    if (!cached) {
+      cached_has = get_next(&cached_val);
+      cached = true;
+    }
+    return cached_has;
+  }
+  int next() {
+    if (!cached) {
+      int v = 0;
+      get_next(&v);
+      return v;
+    }
+    cached = false;
+    return cached_val;
+  }
+};
+
+// util.TopOne (S/util/TopOne.scala:6-24), keyed by (leaderIndex, id).
+struct TopOne {
+  std::vector<int> top;
+  explicit TopOne(int n) : top(n, 0) {}
+  void put(int leader, int id) { top[leader] = std::max(top[leader], id + 1); }  // :12-15
+  void merge_equals(const TopOne& o) {                                           // :19-23
+    for (size_t i = 0; i < top.size(); ++i) top[i] = std::max(top[i], o.top[i]);
+  }
+};
+
+// util.QuorumWatermark (S/util/QuorumWatermark.scala:31-48)
+struct QuorumWatermark {
+  std::vector<int> w;
+  explicit QuorumWatermark(int n) : w(n, 0) {}
+  void update(int i, int x) { w[i] = std::max(w[i], x); }     // :39-40
+  int watermark(int quorum_size) const {                      // :42-47
+    std::vector<int> s = w;
+    std::sort(s.begin(), s.end());
+    return s[s.size() - quorum_size];
+  }
+};
+
+// util.BufferMap[Int] (S/util/BufferMap.scala:8-115); value -1 == None.
+struct BufferMap {
+  int grow_size;
+  std::vector<int> buffer;  // -1 = None
+  int watermark = 0;
+  int largest_key = -1;
+  explicit BufferMap(int grow) : grow_size(grow), buffer(grow, -1) {}
+  int normalize(int key) const { return key - watermark; }
+  int get(int key) const {                                    // :29-35
+    int k = normalize(key);
+    if (k < 0 || k >= (int)buffer.size()) return -1;
+    return buffer[k];
+  }
+  void put(int key, int value) {                              // :37-51
+    largest_key = std::max(largest_key, key);
+    int k = normalize(key);
+    if (k < 0) return;
+    if (k < (int)buffer.size()) { buffer[k] = value; return; }
+    buffer.resize(k + 1 + grow_size, -1);
+    buffer[k] = value;
+  }
+  void garbage_collect(int wm) {                              // :55-62
+    if (wm <= watermark) return;
+    size_t cut = std::min<size_t>(wm - watermark, buffer.size());
+    buffer.erase(buffer.begin(), buffer.begin() + cut);
+    watermark = wm;
+  }
+};
+
+// ---------------------------------------------------------------------------
+// MultiPaxos quorum-vote path
+// ---------------------------------------------------------------------------
+struct P2a { int32_t slot, round, value_id, dst; };
+struct P2b { int32_t group, acceptor, slot, round; };
+struct Chosen { int32_t slot, value_id; };
+struct Nack { int32_t leader, round; };
+
+enum Status {
+  kOk = 0, kInvalidArg = -1, kConfig = -2, kUnknownSlotRound = -4, kBadAcceptor = -5,
+  kSlotRange = -6, kRoundRange = -7
+};
+
+struct Config {
+  int f, groups, per_group, flexible, num_leaders, num_replicas;
+  // S/multipaxos/Config.scala:32-147 (the clauses the path depends on)
+  bool valid() const {
+    if (f < 1) return false;                                  // :33
+    if (num_leaders < f + 1) return false;                    // :65-67
+    if (groups < 1) return false;                             // :92-95 / :108-111
+    if (!flexible) {
+      if (per_group != 2 * f + 1) return false;               // :96-102
+    } else {
+      if (std::min(groups, per_group) - 1 < f) return false;  // :117-125
+    }
+    if (num_replicas < f + 1) return false;                   // :129-132
+    return true;
+  }
+};
+
+// S/multipaxos/Acceptor.scala:73-104
+struct Acceptor {
+  int round = -1;                                             // :95
+  std::map<int, std::pair<int, int>> states;                  // :98  slot -> (voteRound, voteValue)
+  int max_voted_slot = -1;                                    // :104
+};
+
+struct MultiPaxos {
+  Config cfg;
+  std::vector<std::vector<Acceptor>> acceptors;  // [group][index]
+  ClassicRoundRobin round_system;                // Acceptor.scala:92
+  Grid grid;                                     // ProxyLeader.scala:118-124, node id = row*cols+col
+  // ProxyLeader.scala:135  states: Map[SlotRound, State]
+  struct PLState {
+    bool done = false;
+    int value = 0;
+    std::set<std::pair<int, int>> phase2bs;  // keys of Pending.phase2bs
+  };
+  std::map<std::pair<int, int>, PLState> pl_states;
+  // Replica.scala: log (BufferMap) + executedWatermark
+  std::map<int, int> log;
+  int executed_watermark = 0;
+
+  static std::vector<std::vector<int>> make_grid(const Config& c) {
+    std::vector<std::vector<int>> g(c.groups);
+    for (int r = 0; r < c.groups; ++r)
+      for (int col = 0; col < c.per_group; ++col) g[r].push_back(r * c.per_group + col);
+    return g;
+  }
+  explicit MultiPaxos(const Config& c)
+      : cfg(c), acceptors(c.groups, std::vector<Acceptor>(c.per_group)),
+        round_system{c.num_leaders}, grid(make_grid(c)) {}
+
+  // ProxyLeader.handlePhase2a, S/multipaxos/ProxyLeader.scala:175-215
+  int arm(const P2a* in, int n, int64_t* err) {
+    for (int i = 0; i < n; ++i) {
+      auto key = std::make_pair(in[i].slot, in[i].round);
+      if (pl_states.count(key)) continue;                     // :177-183
+      PLState s;
+      s.value = in[i].value_id;
+      pl_states[key] = s;                                     // :213
+    }
+    (void)err;
+    return kOk;
+  }
+
+  // Acceptor.handlePhase2a, S/multipaxos/Acceptor.scala:184-220
+  int acceptor_phase2a(const P2a* in, int n, P2b* out_p2b, int* n_p2b, Nack* out_nack,
+                       int* n_nack, int64_t* err) {
+    int np = 0, nn = 0;
+    for (int i = 0; i < n; ++i) {
+      int g = in[i].dst >> 16, a = in[i].dst & 0xffff;
+      if (g < 0 || g >= cfg.groups || a < 0 || a >= cfg.per_group) {
+        *err = i;
+        *n_p2b = np; *n_nack = nn;
+        return kBadAcceptor;
+      }
+      Acceptor& acc = acceptors[g][a];
+      if (in[i].round < acc.round) {                          // :192
+        out_nack[nn++] = Nack{round_system.leader(in[i].round), acc.round};  // :197-198
+        continue;
+      }
+      acc.round = in[i].round;                                // :204
+      acc.states[in[i].slot] = {acc.round, in[i].value_id};   // :205-208
+      acc.max_voted_slot = std::max(acc.max_voted_slot, in[i].slot);  // :209
+      out_p2b[np++] = P2b{g, a, in[i].slot, acc.round};       // :211-219
+    }
+    *n_p2b = np; *n_nack = nn;
+    return kOk;
+  }
+
+  // ProxyLeader.handlePhase2b, S/multipaxos/ProxyLeader.scala:217-258
+  int proxyleader_phase2b(const P2b* in, int n, Chosen* out, int* n_out, int64_t* err) {
+    int nc = 0;
+    for (int i = 0; i < n; ++i) {
+      auto it = pl_states.find({in[i].slot, in[i].round});
+      if (it == pl_states.end()) {                            // :220-225 logger.fatal
+        *err = i; *n_out = nc;
+        return kUnknownSlotRound;
+      }
+      PLState& st = it->second;
+      if (st.done) continue;                                  // :227-232
+      st.phase2bs.insert({in[i].group, in[i].acceptor});      // :237
+      if (!cfg.flexible) {
+        if ((int)st.phase2bs.size() < cfg.f + 1) continue;    // :238-240
+      } else {
+        NodeSet xs;
+        bool member = true;
+        for (auto& ga : st.phase2bs) {
+          if (ga.first < 0 || ga.first >= cfg.groups || ga.second < 0 || ga.second >= cfg.per_group) {
+            member = false;
+            xs.insert(1 << 30);
+          } else {
+            xs.insert(ga.first * cfg.per_group + ga.second);
+          }
+        }
+        Tri q = grid.is_write(xs);                            // :241-243 -> Grid.scala:43-50
+        if (q == kThrows || !member) {                        // `require` throws
+          *err = i; *n_out = nc;
+          return kBadAcceptor;
+        }
+        if (q == kFalse) continue;
+      }
+      out[nc++] = Chosen{in[i].slot, st.value};               // :246-253
+      st.done = true;                                         // :256
+      st.phase2bs.clear();
+    }
+    *n_out = nc;
+    return kOk;
+  }
+
+  // Replica.handleChosen + executeLog, S/multipaxos/Replica.scala:572-588, 394-402
+  int replica_chosen(const Chosen* in, int n) {
+    for (int i = 0; i < n; ++i) {
+      if (log.count(in[i].slot)) continue;                    // :580-586 redundantlyChosen
+      log[in[i].slot] = in[i].value_id;                       // :587
+      while (log.count(executed_watermark)) executed_watermark++;  // :397-418
+    }
+    return kOk;
+  }
+};
+
+}  // namespace fpo
+
+// ---------------------------------------------------------------------------
+// C interface (ctypes)
+// ---------------------------------------------------------------------------
+using namespace fpo;
+
+static NodeSet to_set(const int* xs, int n) { return NodeSet(xs, xs + n); }
+
+extern "C" {
+
+// which: 0 isReadQuorum 1 isWriteQuorum 2 isSuperSetOfReadQuorum 3 isSuperSetOfWriteQuorum
+// kind: 0 Grid (members row-major, rows x cols) 1 SimpleMajority 2 UnanimousWrites
+int fpo_quorum_eval(int kind, const int* members, int rows, int cols, int which, const int* xs,
+                    int nxs) {
+  NodeSet s = to_set(xs, nxs);
+  if (kind == 0) {
+    std::vector<std::vector<int>> g(rows);
+    for (int r = 0; r < rows; ++r) g[r].assign(members + r * cols, members + (r + 1) * cols);
+    Grid q(g);
+    switch (which) {
+      case 0: return q.is_read(s);
+      case 1: return q.is_write(s);
+      case 2: return q.superset_read(s);
+      default: return q.superset_write(s);
+    }
+  } else if (kind == 1) {
+    SimpleMajority q(to_set(members, rows * cols));
+    switch (which) {
+      case 0: return q.is_read(s);
+      case 1: return q.is_write(s);
+      case 2: return q.superset_read(s);
+      default: return q.superset_write(s);
+    }
+  } else {
+    UnanimousWrites q(to_set(members, rows * cols));
+    switch (which) {
+      case 0: return q.is_read(s);
+      case 1: return q.is_write(s);
+      case 2: return q.superset_read(s);
+      default: return q.superset_write(s);
+    }
+  }
+}
+
+int fpo_rr_leader(int n, int round) { return ClassicRoundRobin{n}.leader(round); }
+int fpo_rr_next_classic_round(int n, int leader, int round) {
+  return ClassicRoundRobin{n}.next_classic_round(leader, round);
+}
+
+// ---- IntPrefixSet handles
+void* fpo_ips_new() { return new IntPrefixSet(); }
+void* fpo_ips_from_set(const int* xs, int n) {
+  return new IntPrefixSet(IntPrefixSet::from_set(std::set<int>(xs, xs + n)));
+}
+void* fpo_ips_from_watermark_values(int w, const int* xs, int n) {
+  return new IntPrefixSet(w, std::set<int>(xs, xs + n));
+}
+void fpo_ips_free(void* p) { delete (IntPrefixSet*)p; }
+void* fpo_ips_clone(void* p) { return new IntPrefixSet(*(IntPrefixSet*)p); }
+int fpo_ips_add(void* p, int x) { return ((IntPrefixSet*)p)->add(x); }
+int fpo_ips_contains(void* p, int x) { return ((IntPrefixSet*)p)->contains(x); }
+int fpo_ips_watermark(void* p) { return ((IntPrefixSet*)p)->watermark; }
+int fpo_ips_num_values(void* p) { return (int)((IntPrefixSet*)p)->values.size(); }
+int fpo_ips_values(void* p, int* out, int cap) {
+  int n = 0;
+  for (int x : ((IntPrefixSet*)p)->values) { if (n < cap) out[n] = x; ++n; }
+  return n;
+}
+int fpo_ips_size(void* p) { return ((IntPrefixSet*)p)->size(); }
+int fpo_ips_equals(void* a, void* b) { return *(IntPrefixSet*)a == *(IntPrefixSet*)b; }
+void* fpo_ips_union(void* a, void* b) {
+  return new IntPrefixSet(((IntPrefixSet*)a)->set_union(*(IntPrefixSet*)b));
+}
+void* fpo_ips_diff(void* a, void* b) {
+  return new IntPrefixSet(((IntPrefixSet*)a)->diff(*(IntPrefixSet*)b));
+}
+void fpo_ips_add_all(void* a, void* b) { ((IntPrefixSet*)a)->add_all(*(IntPrefixSet*)b); }
+void fpo_ips_subtract_all(void* a, void* b) { ((IntPrefixSet*)a)->subtract_all(*(IntPrefixSet*)b); }
+void fpo_ips_subtract_one(void* a, int x) { ((IntPrefixSet*)a)->subtract_one(x); }
+int fpo_ips_materialize(void* p, int* out, int cap) {
+  int n = 0;
+  for (int x : ((IntPrefixSet*)p)->materialize()) { if (n < cap) out[n] = x; ++n; }
+  return n;
+}
+
+void* fpo_ips_diff_iterator(void* a, void* b) {
+  return new DiffIterator((IntPrefixSet*)a, (IntPrefixSet*)b);
+}
+void fpo_ips_diff_iterator_free(void* it) { delete (DiffIterator*)it; }
+int fpo_ips_diff_iterator_has_next(void* it) { return ((DiffIterator*)it)->has_next(); }
+int fpo_ips_diff_iterator_next(void* it) { return ((DiffIterator*)it)->next(); }
+
+// ---- TopOne / QuorumWatermark / BufferMap
+void* fpo_topone_new(int n) { return new TopOne(n); }
+void fpo_topone_free(void* p) { delete (TopOne*)p; }
+void fpo_topone_put(void* p, int leader, int id) { ((TopOne*)p)->put(leader, id); }
+void fpo_topone_merge(void* a, void* b) { ((TopOne*)a)->merge_equals(*(TopOne*)b); }
+void fpo_topone_get(void* p, int* out) {
+  auto& t = ((TopOne*)p)->top;
+  std::copy(t.begin(), t.end(), out);
+}
+void* fpo_qw_new(int n) { return new QuorumWatermark(n); }
+void fpo_qw_free(void* p) { delete (QuorumWatermark*)p; }
+void fpo_qw_update(void* p, int i, int w) { ((QuorumWatermark*)p)->update(i, w); }
+int fpo_qw_watermark(void* p, int q) { return ((QuorumWatermark*)p)->watermark(q); }
+void* fpo_bm_new(int grow) { return new BufferMap(grow); }
+void fpo_bm_free(void* p) { delete (BufferMap*)p; }
+int fpo_bm_get(void* p, int k) { return ((BufferMap*)p)->get(k); }
+void fpo_bm_put(void* p, int k, int v) { ((BufferMap*)p)->put(k, v); }
+void fpo_bm_gc(void* p, int w) { ((BufferMap*)p)->garbage_collect(w); }
+
+// ---- MultiPaxos
+void* fpo_mp_new(int f, int groups, int per_group, int flexible, int num_leaders, int num_replicas) {
+  Config c{f, groups, per_group, flexible, num_leaders, num_replicas};
+  if (!c.valid()) return nullptr;
+  return new MultiPaxos(c);
+}
+void fpo_mp_free(void* p) { delete (MultiPaxos*)p; }
+int fpo_mp_arm(void* p, const P2a* in, int n, int64_t* err) {
+  *err = -1;
+  return ((MultiPaxos*)p)->arm(in, n, err);
+}
+int fpo_mp_acceptor_phase2a(void* p, const P2a* in, int n, P2b* out_p2b, int* n_p2b, Nack* out_nack,
+                            int* n_nack, int64_t* err) {
+  *err = -1;
+  return ((MultiPaxos*)p)->acceptor_phase2a(in, n, out_p2b, n_p2b, out_nack, n_nack, err);
+}
+int fpo_mp_proxyleader_phase2b(void* p, const P2b* in, int n, Chosen* out, int* n_out, int64_t* err) {
+  *err = -1;
+  return ((MultiPaxos*)p)->proxyleader_phase2b(in, n, out, n_out, err);
+}
+int fpo_mp_replica_chosen(void* p, const Chosen* in, int n) {
+  return ((MultiPaxos*)p)->replica_chosen(in, n);
+}
+int fpo_mp_executed_watermark(void* p) { return ((MultiPaxos*)p)->executed_watermark; }
+void fpo_mp_snapshot_acceptor(void* p, int g, int a, int* round, int* max_voted_slot, int first_slot,
+                              int n_slots, int* vote_round, int* vote_value) {
+  Acceptor& acc = ((MultiPaxos*)p)->acceptors[g][a];
+  *round = acc.round;
+  *max_voted_slot = acc.max_voted_slot;
+  for (int i = 0; i < n_slots; ++i) {
+    auto it = acc.states.find(first_slot + i);
+    vote_round[i] = it == acc.states.end() ? -1 : it->second.first;
+    vote_value[i] = it == acc.states.end() ? -1 : it->second.second;
+  }
+}
+void fpo_mp_snapshot_log(void* p, int first_slot, int n_slots, int* value_id) {
+  auto& log = ((MultiPaxos*)p)->log;
+  for (int i = 0; i < n_slots; ++i) {
+    auto it = log.find(first_slot + i);
+    value_id[i] = it == log.end() ? -1 : it->second;
+  }
+}
+
+}  // extern "C"

@@ -1,0 +1,242 @@
+"""ctypes binding of the CPU oracle (oracle/fpx_oracle.cc).  TEST INFRASTRUCTURE.
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl
+reference legs may import this module; the product package never does.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_SO = os.path.join(_HERE, "libfpx_oracle.so")
+
+P2A = np.dtype([("slot", "<i4"), ("round", "<i4"), ("value_id", "<i4"), ("dst", "<i4")])
+P2B = np.dtype([("group", "<i4"), ("acceptor", "<i4"), ("slot", "<i4"), ("round", "<i4")])
+CHOSEN = np.dtype([("slot", "<i4"), ("value_id", "<i4")])
+NACK = np.dtype([("leader", "<i4"), ("round", "<i4")])
+
+
+def build(force=False):
+    src = os.path.join(_HERE, "fpx_oracle.cc")
+    if force or not os.path.exists(_SO) or os.path.getmtime(_SO) < os.path.getmtime(src):
+        subprocess.check_call(["make", "-C", _HERE, "-s", "libfpx_oracle.so"])
+    return _SO
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        build()
+        L = C.CDLL(_SO)
+        vp, i32, i64p = C.c_void_p, C.c_int, C.POINTER(C.c_int64)
+        ip = C.POINTER(C.c_int)
+        L.fpo_quorum_eval.argtypes = [i32, ip, i32, i32, i32, ip, i32]
+        L.fpo_quorum_eval.restype = i32
+        for name in ["fpo_ips_new"]:
+            getattr(L, name).restype = vp
+        L.fpo_ips_from_set.argtypes = [ip, i32]; L.fpo_ips_from_set.restype = vp
+        L.fpo_ips_from_watermark_values.argtypes = [i32, ip, i32]; L.fpo_ips_from_watermark_values.restype = vp
+        L.fpo_ips_free.argtypes = [vp]
+        L.fpo_ips_clone.argtypes = [vp]; L.fpo_ips_clone.restype = vp
+        for name in ["fpo_ips_add", "fpo_ips_contains"]:
+            getattr(L, name).argtypes = [vp, i32]; getattr(L, name).restype = i32
+        for name in ["fpo_ips_watermark", "fpo_ips_num_values", "fpo_ips_size"]:
+            getattr(L, name).argtypes = [vp]; getattr(L, name).restype = i32
+        for name in ["fpo_ips_values", "fpo_ips_materialize"]:
+            getattr(L, name).argtypes = [vp, ip, i32]; getattr(L, name).restype = i32
+        L.fpo_ips_equals.argtypes = [vp, vp]; L.fpo_ips_equals.restype = i32
+        for name in ["fpo_ips_union", "fpo_ips_diff", "fpo_ips_diff_iterator"]:
+            getattr(L, name).argtypes = [vp, vp]; getattr(L, name).restype = vp
+        for name in ["fpo_ips_add_all", "fpo_ips_subtract_all"]:
+            getattr(L, name).argtypes = [vp, vp]; getattr(L, name).restype = None
+        L.fpo_ips_subtract_one.argtypes = [vp, i32]; L.fpo_ips_subtract_one.restype = None
+        L.fpo_ips_diff_iterator_free.argtypes = [vp]
+        L.fpo_ips_diff_iterator_has_next.argtypes = [vp]; L.fpo_ips_diff_iterator_has_next.restype = i32
+        L.fpo_ips_diff_iterator_next.argtypes = [vp]; L.fpo_ips_diff_iterator_next.restype = i32
+        L.fpo_topone_new.argtypes = [i32]; L.fpo_topone_new.restype = vp
+        L.fpo_topone_free.argtypes = [vp]
+        L.fpo_topone_put.argtypes = [vp, i32, i32]
+        L.fpo_topone_merge.argtypes = [vp, vp]
+        L.fpo_topone_get.argtypes = [vp, ip]
+        L.fpo_qw_new.argtypes = [i32]; L.fpo_qw_new.restype = vp
+        L.fpo_qw_free.argtypes = [vp]
+        L.fpo_qw_update.argtypes = [vp, i32, i32]
+        L.fpo_qw_watermark.argtypes = [vp, i32]; L.fpo_qw_watermark.restype = i32
+        L.fpo_bm_new.argtypes = [i32]; L.fpo_bm_new.restype = vp
+        L.fpo_bm_free.argtypes = [vp]
+        L.fpo_bm_get.argtypes = [vp, i32]; L.fpo_bm_get.restype = i32
+        L.fpo_bm_put.argtypes = [vp, i32, i32]
+        L.fpo_bm_gc.argtypes = [vp, i32]
+        L.fpo_rr_leader.argtypes = [i32, i32]; L.fpo_rr_leader.restype = i32
+        L.fpo_rr_next_classic_round.argtypes = [i32, i32, i32]; L.fpo_rr_next_classic_round.restype = i32
+        L.fpo_mp_new.argtypes = [i32] * 6; L.fpo_mp_new.restype = vp
+        L.fpo_mp_free.argtypes = [vp]
+        L.fpo_mp_arm.argtypes = [vp, vp, i32, i64p]; L.fpo_mp_arm.restype = i32
+        L.fpo_mp_acceptor_phase2a.argtypes = [vp, vp, i32, vp, ip, vp, ip, i64p]
+        L.fpo_mp_acceptor_phase2a.restype = i32
+        L.fpo_mp_proxyleader_phase2b.argtypes = [vp, vp, i32, vp, ip, i64p]
+        L.fpo_mp_proxyleader_phase2b.restype = i32
+        L.fpo_mp_replica_chosen.argtypes = [vp, vp, i32]; L.fpo_mp_replica_chosen.restype = i32
+        L.fpo_mp_executed_watermark.argtypes = [vp]; L.fpo_mp_executed_watermark.restype = i32
+        L.fpo_mp_snapshot_acceptor.argtypes = [vp, i32, i32, ip, ip, i32, i32, vp, vp]
+        L.fpo_mp_snapshot_log.argtypes = [vp, i32, i32, vp]
+        _lib = L
+    return _lib
+
+
+def _iarr(xs):
+    xs = list(xs)
+    return (C.c_int * max(1, len(xs)))(*xs), len(xs)
+
+
+QUORUM_PREDS = {"isReadQuorum": 0, "isWriteQuorum": 1, "isSuperSetOfReadQuorum": 2,
+                "isSuperSetOfWriteQuorum": 3}
+
+
+def quorum_eval(kind, members, which, xs):
+    """kind: 'grid' (members = list of rows) | 'simple_majority' | 'unanimous_writes'.
+    Returns 0/1, or 2 where the reference `require` throws."""
+    if kind == "grid":
+        rows, cols = len(members), len(members[0])
+        flat = [x for r in members for x in r]
+        k = 0
+    else:
+        rows, cols = 1, len(members)
+        flat = list(members)
+        k = 1 if kind == "simple_majority" else 2
+    m, _ = _iarr(flat)
+    x, n = _iarr(xs)
+    return lib().fpo_quorum_eval(k, m, rows, cols, QUORUM_PREDS[which] if isinstance(which, str) else which, x, n)
+
+
+class IntPrefixSet:
+    def __init__(self, handle=None):
+        self.h = handle if handle is not None else lib().fpo_ips_new()
+
+    @classmethod
+    def from_set(cls, xs):
+        a, n = _iarr(sorted(xs))
+        return cls(lib().fpo_ips_from_set(a, n))
+
+    @classmethod
+    def from_watermark_values(cls, w, xs):
+        a, n = _iarr(sorted(xs))
+        return cls(lib().fpo_ips_from_watermark_values(w, a, n))
+
+    def __del__(self):
+        try:
+            lib().fpo_ips_free(self.h)
+        except Exception:
+            pass
+
+    def clone(self): return IntPrefixSet(lib().fpo_ips_clone(self.h))
+    def add(self, x): return bool(lib().fpo_ips_add(self.h, x))
+    def contains(self, x): return bool(lib().fpo_ips_contains(self.h, x))
+    def watermark(self): return lib().fpo_ips_watermark(self.h)
+    def size(self): return lib().fpo_ips_size(self.h)
+
+    def values(self):
+        n = lib().fpo_ips_num_values(self.h)
+        buf = (C.c_int * max(1, n))()
+        lib().fpo_ips_values(self.h, buf, n)
+        return set(buf[:n])
+
+    def materialize(self):
+        n = lib().fpo_ips_size(self.h)
+        buf = (C.c_int * max(1, n))()
+        lib().fpo_ips_materialize(self.h, buf, n)
+        return set(buf[:n])
+
+    def __eq__(self, o): return bool(lib().fpo_ips_equals(self.h, o.h))
+    def union(self, o): return IntPrefixSet(lib().fpo_ips_union(self.h, o.h))
+    def diff(self, o): return IntPrefixSet(lib().fpo_ips_diff(self.h, o.h))
+    def add_all(self, o): lib().fpo_ips_add_all(self.h, o.h); return self
+    def subtract_all(self, o): lib().fpo_ips_subtract_all(self.h, o.h); return self
+    def subtract_one(self, x): lib().fpo_ips_subtract_one(self.h, x); return self
+
+    def diff_iterator(self, o):
+        return DiffIterator(self, o)
+
+
+class DiffIterator:
+    def __init__(self, me, other):
+        self._keep = (me, other)
+        self.h = lib().fpo_ips_diff_iterator(me.h, other.h)
+
+    def __del__(self):
+        try:
+            lib().fpo_ips_diff_iterator_free(self.h)
+        except Exception:
+            pass
+
+    def has_next(self): return bool(lib().fpo_ips_diff_iterator_has_next(self.h))
+    def next(self): return lib().fpo_ips_diff_iterator_next(self.h)
+
+
+class MultiPaxos:
+    """Sequential restatement of the multipaxos Acceptor / ProxyLeader / Replica
+    handlers on the quorum-vote path; same call shapes as frankenpaxos_b200.Engine."""
+
+    def __init__(self, f, groups, per_group, flexible=False, num_leaders=None, num_replicas=None):
+        num_leaders = f + 1 if num_leaders is None else num_leaders
+        num_replicas = f + 1 if num_replicas is None else num_replicas
+        self.h = lib().fpo_mp_new(f, groups, per_group, int(flexible), num_leaders, num_replicas)
+        if not self.h:
+            raise ValueError("Config.checkValid failed")
+
+    def __del__(self):
+        try:
+            if self.h:
+                lib().fpo_mp_free(self.h)
+        except Exception:
+            pass
+
+    def arm(self, p2a):
+        p2a = np.ascontiguousarray(p2a, dtype=P2A)
+        err = C.c_int64(-1)
+        st = lib().fpo_mp_arm(self.h, p2a.ctypes.data, len(p2a), C.byref(err))
+        return st, err.value
+
+    def acceptor_phase2a(self, p2a):
+        p2a = np.ascontiguousarray(p2a, dtype=P2A)
+        n = len(p2a)
+        out = np.zeros(max(n, 1), dtype=P2B)
+        nack = np.zeros(max(n, 1), dtype=NACK)
+        n1, n2, err = C.c_int(0), C.c_int(0), C.c_int64(-1)
+        st = lib().fpo_mp_acceptor_phase2a(self.h, p2a.ctypes.data, n, out.ctypes.data, C.byref(n1),
+                                           nack.ctypes.data, C.byref(n2), C.byref(err))
+        return st, err.value, out[:n1.value].copy(), nack[:n2.value].copy()
+
+    def proxyleader_phase2b(self, p2b):
+        p2b = np.ascontiguousarray(p2b, dtype=P2B)
+        n = len(p2b)
+        out = np.zeros(max(n, 1), dtype=CHOSEN)
+        n1, err = C.c_int(0), C.c_int64(-1)
+        st = lib().fpo_mp_proxyleader_phase2b(self.h, p2b.ctypes.data, n, out.ctypes.data, C.byref(n1),
+                                              C.byref(err))
+        return st, err.value, out[:n1.value].copy()
+
+    def replica_chosen(self, chosen):
+        chosen = np.ascontiguousarray(chosen, dtype=CHOSEN)
+        return lib().fpo_mp_replica_chosen(self.h, chosen.ctypes.data, len(chosen))
+
+    def executed_watermark(self):
+        return lib().fpo_mp_executed_watermark(self.h)
+
+    def snapshot_acceptor(self, group, acceptor, first_slot, n_slots):
+        vr = np.zeros(max(n_slots, 1), dtype=np.int32)
+        vv = np.zeros(max(n_slots, 1), dtype=np.int32)
+        r, m = C.c_int(0), C.c_int(0)
+        lib().fpo_mp_snapshot_acceptor(self.h, group, acceptor, C.byref(r), C.byref(m), first_slot, n_slots,
+                                       vr.ctypes.data, vv.ctypes.data)
+        return r.value, m.value, vr[:n_slots], vv[:n_slots]
+
+    def snapshot_log(self, first_slot, n_slots):
+        v = np.zeros(max(n_slots, 1), dtype=np.int32)
+        lib().fpo_mp_snapshot_log(self.h, first_slot, n_slots, v.ctypes.data)
+        return v[:n_slots]

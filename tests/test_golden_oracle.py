@@ -1,0 +1,142 @@
+"""Pin the CPU oracle against every known-answer vector the reference's own
+tests hold for the helper classes on the quorum-vote path (tests/golden/*.json,
+transcribed by tests/golden/make_golden.py from shared/src/test/scala/...)."""
+import ctypes as C
+import json
+import os
+
+import pytest
+
+from oracle import fpx_oracle_py as O
+
+
+def load(golden_dir, name):
+    with open(os.path.join(golden_dir, name)) as f:
+        return json.load(f)
+
+
+@pytest.mark.parametrize("kind", ["grid", "simple_majority", "unanimous_writes"])
+def test_quorum_known_answers(golden_dir, kind):
+    g = load(golden_dir, "quorums.json")[kind]
+    assert len(g["cases"]) >= 36
+    for c in g["cases"]:
+        got = O.quorum_eval(kind, g["members"], c["pred"], c["set"])
+        assert got == int(c["expect"]), (g["source"], c["line"], c)
+
+
+def test_quorum_require_throws():
+    # Grid.scala:36-39 / SimpleMajority.scala:42-45: non-member input to
+    # is{Read,Write}Quorum is an IllegalArgumentException -> oracle returns 2.
+    assert O.quorum_eval("grid", [[1, 2, 3], [4, 5, 6]], "isWriteQuorum", [9001, 1, 4]) == 2
+    assert O.quorum_eval("grid", [[1, 2, 3], [4, 5, 6]], "isReadQuorum", [9001]) == 2
+    assert O.quorum_eval("simple_majority", [0, 1, 2, 3, 4], "isReadQuorum", [0, 1, 5]) == 2
+
+
+def test_int_prefix_set_known_answers(golden_dir):
+    g = load(golden_dir, "int_prefix_set.json")
+    assert len(g["tests"]) == 12
+    for t in g["tests"]:
+        env = {}
+        for op in t["ops"]:
+            k = op[0]
+            where = (g["source"], t["name"], op)
+            if k == "new":
+                env[op[1]] = O.IntPrefixSet()
+            elif k == "from_set":
+                env[op[1]] = O.IntPrefixSet.from_set(op[2])
+            elif k == "union":
+                env[op[1]] = env[op[2]].union(env[op[3]])
+            elif k == "diff":
+                env[op[1]] = env[op[2]].diff(env[op[3]])
+            elif k == "clone":
+                env[op[1]] = env[op[2]].clone()
+            elif k == "diff_iterator":
+                env[op[1]] = env[op[2]].diff_iterator(env[op[3]])
+            elif k == "add":
+                env[op[1]].add(op[2])
+            elif k == "subtractOne":
+                env[op[1]].subtract_one(op[2])
+            elif k == "add_all_set":
+                env[op[1]].add_all(O.IntPrefixSet.from_set(op[2]))
+            elif k == "expect_contains":
+                assert env[op[1]].contains(op[2]) == op[3], where
+            elif k == "expect_materialize":
+                assert env[op[1]].materialize() == set(op[2]), where
+            elif k == "expect_watermark":
+                assert env[op[1]].watermark() == op[2], where
+            elif k == "expect_equals_set":
+                assert env[op[1]] == O.IntPrefixSet.from_set(op[2]), where
+            elif k == "expect_has_next":
+                assert env[op[1]].has_next() == op[2], where
+            elif k == "expect_next":
+                assert env[op[1]].next() == op[2], where
+            else:
+                raise AssertionError(f"unknown op {op}")
+
+
+def test_round_system_known_answers(golden_dir):
+    g = load(golden_dir, "round_system.json")
+    assert len(g["cases"]) == 33
+    L = O.lib()
+    for c in g["cases"]:
+        if c["op"] == "leader":
+            assert L.fpo_rr_leader(c["n"], c["round"]) == c["expect"], c
+        else:
+            assert L.fpo_rr_next_classic_round(c["n"], c["leader"], c["round"]) == c["expect"], c
+
+
+def test_top_one_known_answers(golden_dir):
+    g = load(golden_dir, "top_one.json")
+    L = O.lib()
+    assert len(g["tests"]) == 8
+    for t in g["tests"]:
+        env, size = {}, {}
+        for op in t["ops"]:
+            if op[0] == "new":
+                env[op[1]] = L.fpo_topone_new(op[2]); size[op[1]] = op[2]
+            elif op[0] == "put":
+                L.fpo_topone_put(env[op[1]], op[2], op[3])
+            elif op[0] == "merge":
+                L.fpo_topone_merge(env[op[1]], env[op[2]])
+            elif op[0] == "expect_get":
+                buf = (C.c_int * size[op[1]])()
+                L.fpo_topone_get(env[op[1]], buf)
+                assert list(buf) == op[2], (t["name"], op)
+        for h in env.values():
+            L.fpo_topone_free(h)
+
+
+def test_quorum_watermark_known_answers(golden_dir):
+    g = load(golden_dir, "quorum_watermark.json")
+    L = O.lib()
+    n_expect = 0
+    for t in g["tests"]:
+        h = None
+        for op in t["ops"]:
+            if op[0] == "new":
+                h = L.fpo_qw_new(op[1])
+            elif op[0] == "update":
+                L.fpo_qw_update(h, op[1], op[2])
+            else:
+                assert L.fpo_qw_watermark(h, op[1]) == op[2], op
+                n_expect += 1
+        L.fpo_qw_free(h)
+    assert n_expect == 15
+
+
+def test_buffer_map_known_answers(golden_dir):
+    g = load(golden_dir, "buffer_map.json")
+    L = O.lib()
+    assert len(g["tests"]) == 10
+    for t in g["tests"]:
+        h = None
+        for op in t["ops"]:
+            if op[0] == "new":
+                h = L.fpo_bm_new(op[1])
+            elif op[0] == "put":
+                L.fpo_bm_put(h, op[1], op[2])
+            elif op[0] == "gc":
+                L.fpo_bm_gc(h, op[1])
+            else:
+                assert L.fpo_bm_get(h, op[1]) == op[2], (t["name"], op)
+        L.fpo_bm_free(h)
