@@ -1,0 +1,81 @@
+"""ctypes loader for libfpx.so (the C ABI of include/fpx.h).
+
+There is no CPU fallback: if the shared library is missing it is built with
+nvcc; if that fails, or a symbol declared in include/fpx.h is missing, import
+of the product raises.
+"""
+import ctypes as C
+import os
+
+from . import build as _build
+
+_lib = None
+
+SYMBOLS = [
+    "fpx_abi_version", "fpx_strerror", "fpx_last_error", "fpx_create", "fpx_destroy", "fpx_reset",
+    "fpx_proxyleader_arm", "fpx_acceptor_phase2a", "fpx_proxyleader_phase2b", "fpx_replica_chosen",
+    "fpx_chosen_watermark", "fpx_quorum_eval", "fpx_snapshot_acceptor", "fpx_snapshot_log",
+    "fpx_proxyleader_arm_dev", "fpx_acceptor_phase2a_dev", "fpx_proxyleader_phase2b_dev",
+    "fpx_replica_chosen_dev", "fpx_replica_chosen_last_dev", "fpx_chosen_watermark_dev", "fpx_sync",
+    "fpx_stream", "fpx_launch_count",
+]
+
+
+class Config(C.Structure):
+    """struct fpx_config (include/fpx.h)."""
+    _fields_ = [(n, C.c_int32) for n in (
+        "struct_size", "protocol", "f", "num_acceptor_groups", "acceptors_per_group", "flexible",
+        "num_leaders", "num_replicas", "slot_capacity", "overflow_capacity", "max_batch", "device",
+        "shard_index", "shard_count")]
+
+
+class SyncResult(C.Structure):
+    """struct fpx_sync_result (include/fpx.h)."""
+    _fields_ = [("status", C.c_int32), ("reserved", C.c_int32), ("err_index", C.c_int64),
+                ("n_p2b", C.c_int32), ("n_nack", C.c_int32), ("n_chosen", C.c_int32),
+                ("watermark", C.c_int32)]
+
+
+def lib():
+    global _lib
+    if _lib is not None:
+        return _lib
+    path = _build.LIB
+    if not os.path.exists(path):
+        path = _build.build()
+    L = C.CDLL(path)
+    missing = [s for s in SYMBOLS if not hasattr(L, s)]
+    if missing:
+        raise ImportError(f"libfpx.so lacks symbols declared in include/fpx.h: {missing}")
+    vp, i32, i64 = C.c_void_p, C.c_int32, C.c_int64
+    p = C.POINTER
+    L.fpx_abi_version.restype = i32
+    L.fpx_strerror.argtypes = [i32]; L.fpx_strerror.restype = C.c_char_p
+    L.fpx_last_error.argtypes = [vp]; L.fpx_last_error.restype = C.c_char_p
+    L.fpx_create.argtypes = [p(vp), p(Config)]; L.fpx_create.restype = i32
+    L.fpx_destroy.argtypes = [vp]; L.fpx_destroy.restype = None
+    L.fpx_reset.argtypes = [vp]; L.fpx_reset.restype = i32
+    L.fpx_proxyleader_arm.argtypes = [vp, vp, i32, p(i64)]; L.fpx_proxyleader_arm.restype = i32
+    L.fpx_acceptor_phase2a.argtypes = [vp, vp, i32, vp, p(i32), vp, p(i32), p(i64)]
+    L.fpx_acceptor_phase2a.restype = i32
+    L.fpx_proxyleader_phase2b.argtypes = [vp, vp, i32, vp, p(i32), p(i64)]
+    L.fpx_proxyleader_phase2b.restype = i32
+    L.fpx_replica_chosen.argtypes = [vp, vp, i32, p(i64)]; L.fpx_replica_chosen.restype = i32
+    L.fpx_chosen_watermark.argtypes = [vp, p(i32)]; L.fpx_chosen_watermark.restype = i32
+    L.fpx_quorum_eval.argtypes = [vp, i32, vp, i32, vp]; L.fpx_quorum_eval.restype = i32
+    L.fpx_snapshot_acceptor.argtypes = [vp, i32, i32, p(i32), p(i32), i32, i32, vp, vp]
+    L.fpx_snapshot_acceptor.restype = i32
+    L.fpx_snapshot_log.argtypes = [vp, i32, i32, vp]; L.fpx_snapshot_log.restype = i32
+    L.fpx_proxyleader_arm_dev.argtypes = [vp, vp, i32]; L.fpx_proxyleader_arm_dev.restype = i32
+    L.fpx_acceptor_phase2a_dev.argtypes = [vp, vp, i32, vp, vp]; L.fpx_acceptor_phase2a_dev.restype = i32
+    L.fpx_proxyleader_phase2b_dev.argtypes = [vp, vp, i32, vp]; L.fpx_proxyleader_phase2b_dev.restype = i32
+    L.fpx_replica_chosen_dev.argtypes = [vp, vp, i32]; L.fpx_replica_chosen_dev.restype = i32
+    L.fpx_replica_chosen_last_dev.argtypes = [vp, vp]; L.fpx_replica_chosen_last_dev.restype = i32
+    L.fpx_chosen_watermark_dev.argtypes = [vp, vp]; L.fpx_chosen_watermark_dev.restype = i32
+    L.fpx_sync.argtypes = [vp, p(SyncResult)]; L.fpx_sync.restype = i32
+    L.fpx_stream.argtypes = [vp]; L.fpx_stream.restype = vp
+    L.fpx_launch_count.argtypes = [vp]; L.fpx_launch_count.restype = i64
+    if L.fpx_abi_version() != 1:
+        raise ImportError("libfpx.so ABI version mismatch")
+    _lib = L
+    return L

@@ -1,0 +1,546 @@
+// fpx_engine.cu -- host side of libfpx.so: the C ABI of include/fpx.h.
+//
+// One fpx_engine owns, on one B200: the vote cells of every acceptor of the
+// config (flat slot x voter array of 64-bit {round, value} cells), the proxy
+// leader's per-(slot, round) rows, the overflow table for secondary rounds, the
+// replica log, one CUDA stream, and pinned/device staging for the host-pointer
+// entry points.  No CPU fallback exists: without a CUDA device fpx_create fails
+// with FPX_ERR_NO_DEVICE.
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <algorithm>
+#include <new>
+#include <string>
+
+#include "fpx_kernels.cuh"
+
+using namespace fpx;
+
+struct fpx_engine {
+  fpx_config cfg;
+  Geometry g;
+  cudaStream_t stream = nullptr;
+  // device state
+  uint32_t* rows = nullptr;
+  unsigned long long* ovf_keys = nullptr;
+  uint32_t* ovf_rows = nullptr;
+  unsigned long long* votes = nullptr;
+  int32_t* acc_round = nullptr;
+  int32_t* acc_max_voted = nullptr;
+  unsigned long long* rlog = nullptr;
+  DevStatus* st = nullptr;
+  // scratch
+  uint32_t* bits = nullptr;            // accept / win bitmask, max_batch/32 words
+  unsigned long long* desc_max = nullptr;
+  unsigned long long* desc_cnt = nullptr;
+  void* conflicts = nullptr;           // kMaxConflicts * 8 bytes
+  // staging for host-pointer calls
+  void* d_in = nullptr;                // max_batch * 16
+  void* d_out_a = nullptr;             // max_batch * 16 (p2b)
+  void* d_out_b = nullptr;             // max_batch * 8  (nack / chosen)
+  DevStatus* h_st = nullptr;           // pinned mirror
+  // host bookkeeping
+  uint32_t epoch = 0;
+  uint32_t seq_base = 1;               // Phase2b delivery sequence numbers
+  uint32_t rseq_base = 1;              // Chosen delivery sequence numbers
+  int32_t last_p2b_n = 0;
+  int64_t launches = 0;
+  int max_tiles = 0;
+  std::string last_error;
+};
+
+#define CK(e, call)                                                              \
+  do {                                                                           \
+    cudaError_t _err = (call);                                                   \
+    if (_err != cudaSuccess) {                                                   \
+      (e)->last_error = std::string(#call) + ": " + cudaGetErrorString(_err);   \
+      return FPX_ERR_CUDA;                                                       \
+    }                                                                            \
+  } while (0)
+
+static int validate(const fpx_config* c) {
+  // Config.checkValid, S/multipaxos/Config.scala:32-147 (clauses the path reads)
+  if (c->f < 1) return FPX_ERR_CONFIG;
+  if (c->num_leaders < c->f + 1) return FPX_ERR_CONFIG;
+  if (c->num_replicas < c->f + 1) return FPX_ERR_CONFIG;
+  if (c->num_acceptor_groups < 1 || c->acceptors_per_group < 1) return FPX_ERR_CONFIG;
+  if (!c->flexible) {
+    if (c->acceptors_per_group != 2 * c->f + 1) return FPX_ERR_CONFIG;
+  } else {
+    if (std::min(c->num_acceptor_groups, c->acceptors_per_group) - 1 < c->f) return FPX_ERR_CONFIG;
+  }
+  // engine limits
+  if (c->protocol != FPX_MULTIPAXOS) return FPX_ERR_UNSUPPORTED;
+  long long total = (long long)c->num_acceptor_groups * c->acceptors_per_group;
+  if (total > FPX_MAX_ACCEPTORS) return FPX_ERR_UNSUPPORTED;
+  int voters = c->flexible ? (int)total : c->acceptors_per_group;
+  if (voters > FPX_MAX_VOTERS_PER_SLOT) return FPX_ERR_UNSUPPORTED;
+  if (c->slot_capacity < 1 || c->max_batch < 1) return FPX_ERR_INVALID_ARG;
+  if (c->shard_count < 1 || c->shard_index < 0 || c->shard_index >= c->shard_count) return FPX_ERR_INVALID_ARG;
+  if (c->overflow_capacity < 0 || (c->overflow_capacity & (c->overflow_capacity - 1)) != 0)
+    return FPX_ERR_INVALID_ARG;
+  return FPX_OK;
+}
+
+static int reset_state(fpx_engine* e) {
+  const Geometry& g = e->g;
+  size_t row_bytes = (size_t)g.local_slots * g.row_words * 4;
+  CK(e, cudaMemsetAsync(e->rows, 0xff, row_bytes, e->stream));
+  if (g.ovf_cap) {
+    CK(e, cudaMemsetAsync(e->ovf_keys, 0xff, (size_t)g.ovf_cap * 8, e->stream));
+    CK(e, cudaMemsetAsync(e->ovf_rows, 0xff, (size_t)g.ovf_cap * g.row_words * 4, e->stream));
+  }
+  CK(e, cudaMemsetAsync(e->votes, 0, (size_t)g.local_slots * g.voters * 8, e->stream));
+  CK(e, cudaMemsetAsync(e->acc_round, 0xff, kMaxKeys * 4, e->stream));      // round = -1 (Acceptor.scala:95)
+  CK(e, cudaMemsetAsync(e->acc_max_voted, 0xff, kMaxKeys * 4, e->stream));  // maxVotedSlot = -1 (:104)
+  CK(e, cudaMemsetAsync(e->rlog, 0xff, (size_t)g.local_slots * 8, e->stream));
+  CK(e, cudaMemsetAsync(e->desc_max, 0, (size_t)e->max_tiles * kMaxKeys * 8, e->stream));
+  CK(e, cudaMemsetAsync(e->desc_cnt, 0, (size_t)e->max_tiles * 8, e->stream));
+  DevStatus init;
+  memset(&init, 0, sizeof(init));
+  init.err_word = ~0ull;
+  init.max_chosen_local = -1;
+  init.wm_found = INT_MAX;
+  init.watermark = g.shard_index;
+  *e->h_st = init;
+  CK(e, cudaMemcpyAsync(e->st, e->h_st, sizeof(DevStatus), cudaMemcpyHostToDevice, e->stream));
+  CK(e, cudaStreamSynchronize(e->stream));
+  e->epoch = 0;
+  e->seq_base = 1;
+  e->rseq_base = 1;
+  e->last_p2b_n = 0;
+  return FPX_OK;
+}
+
+extern "C" {
+
+int fpx_abi_version(void) { return FPX_ABI_VERSION; }
+
+const char* fpx_strerror(int s) {
+  switch (s) {
+    case FPX_OK: return "ok";
+    case FPX_ERR_INVALID_ARG: return "invalid argument";
+    case FPX_ERR_CONFIG: return "Config.checkValid failed";
+    case FPX_ERR_CUDA: return "CUDA error";
+    case FPX_ERR_UNKNOWN_SLOT_ROUND: return "Phase2b for a (slot, round) that was never armed (logger.fatal)";
+    case FPX_ERR_BAD_ACCEPTOR: return "acceptor is not a member of the quorum system (require)";
+    case FPX_ERR_SLOT_RANGE: return "slot out of range for this engine/shard";
+    case FPX_ERR_ROUND_RANGE: return "round out of range";
+    case FPX_ERR_OVERFLOW_FULL: return "secondary (slot, round) overflow table full";
+    case FPX_ERR_CONFLICT: return "too many same-key/different-value conflicts in one batch";
+    case FPX_ERR_NO_DEVICE: return "no CUDA device";
+    case FPX_ERR_UNSUPPORTED: return "configuration not supported by this engine build";
+    default: return "unknown status";
+  }
+}
+
+const char* fpx_last_error(const fpx_engine* e) { return e ? e->last_error.c_str() : ""; }
+
+int fpx_create(fpx_engine** out, const fpx_config* cfg) {
+  if (!out || !cfg || cfg->struct_size != (int32_t)sizeof(fpx_config)) return FPX_ERR_INVALID_ARG;
+  *out = nullptr;
+  int v = validate(cfg);
+  if (v != FPX_OK) return v;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return FPX_ERR_NO_DEVICE;
+  if (cfg->device < 0 || cfg->device >= ndev) return FPX_ERR_NO_DEVICE;
+  fpx_engine* e = new (std::nothrow) fpx_engine();
+  if (!e) return FPX_ERR_INVALID_ARG;
+  e->cfg = *cfg;
+  Geometry& g = e->g;
+  g.protocol = cfg->protocol;
+  g.f = cfg->f;
+  g.groups = cfg->num_acceptor_groups;
+  g.per_group = cfg->acceptors_per_group;
+  g.flexible = cfg->flexible ? 1 : 0;
+  g.num_leaders = cfg->num_leaders;
+  g.num_keys = g.groups * g.per_group;
+  g.voters = g.flexible ? g.num_keys : g.per_group;
+  g.quorum = g.f + 1;
+  g.row_words = g.voters <= 6 ? 8 : (g.voters <= 14 ? 16 : 32);
+  g.slot_capacity = cfg->slot_capacity;
+  g.shard_index = cfg->shard_index;
+  g.shard_count = cfg->shard_count;
+  g.local_slots = (cfg->slot_capacity - cfg->shard_index + cfg->shard_count - 1) / cfg->shard_count;
+  if (g.local_slots < 1) g.local_slots = 1;
+  g.ovf_cap = cfg->overflow_capacity;
+  g.ovf_mask = g.ovf_cap ? (uint32_t)g.ovf_cap - 1u : 0u;
+  e->max_tiles = (cfg->max_batch + kTile - 1) / kTile;
+
+  auto fail = [&](int code) { fpx_destroy(e); return code; };
+#define CKC(call)                                                                \
+  do {                                                                           \
+    cudaError_t _err = (call);                                                   \
+    if (_err != cudaSuccess) {                                                   \
+      fprintf(stderr, "fpx_create: %s: %s\n", #call, cudaGetErrorString(_err)); \
+      return fail(FPX_ERR_CUDA);                                                 \
+    }                                                                            \
+  } while (0)
+  CKC(cudaSetDevice(cfg->device));
+  CKC(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
+  size_t mb = (size_t)cfg->max_batch;
+  CKC(cudaMalloc(&e->rows, (size_t)g.local_slots * g.row_words * 4));
+  if (g.ovf_cap) {
+    CKC(cudaMalloc(&e->ovf_keys, (size_t)g.ovf_cap * 8));
+    CKC(cudaMalloc(&e->ovf_rows, (size_t)g.ovf_cap * g.row_words * 4));
+  }
+  CKC(cudaMalloc(&e->votes, (size_t)g.local_slots * g.voters * 8));
+  CKC(cudaMalloc(&e->acc_round, kMaxKeys * 4));
+  CKC(cudaMalloc(&e->acc_max_voted, kMaxKeys * 4));
+  CKC(cudaMalloc(&e->rlog, (size_t)g.local_slots * 8));
+  CKC(cudaMalloc(&e->st, sizeof(DevStatus)));
+  CKC(cudaMalloc(&e->bits, (mb / 32 + 2) * 4));
+  CKC(cudaMalloc(&e->desc_max, (size_t)e->max_tiles * kMaxKeys * 8));
+  CKC(cudaMalloc(&e->desc_cnt, (size_t)e->max_tiles * 8));
+  CKC(cudaMalloc(&e->conflicts, kMaxConflicts * 8));
+  CKC(cudaMalloc(&e->d_in, mb * 16));
+  CKC(cudaMalloc(&e->d_out_a, mb * 16));
+  CKC(cudaMalloc(&e->d_out_b, mb * 8));
+  CKC(cudaMallocHost(&e->h_st, sizeof(DevStatus)));
+#undef CKC
+  int r = reset_state(e);
+  if (r != FPX_OK) { fprintf(stderr, "fpx_create: %s\n", e->last_error.c_str()); return fail(r); }
+  *out = e;
+  return FPX_OK;
+}
+
+void fpx_destroy(fpx_engine* e) {
+  if (!e) return;
+  cudaSetDevice(e->cfg.device);
+  if (e->stream) cudaStreamSynchronize(e->stream);
+  cudaFree(e->rows); cudaFree(e->ovf_keys); cudaFree(e->ovf_rows); cudaFree(e->votes);
+  cudaFree(e->acc_round); cudaFree(e->acc_max_voted); cudaFree(e->rlog); cudaFree(e->st);
+  cudaFree(e->bits); cudaFree(e->desc_max); cudaFree(e->desc_cnt); cudaFree(e->conflicts);
+  cudaFree(e->d_in); cudaFree(e->d_out_a); cudaFree(e->d_out_b);
+  if (e->h_st) cudaFreeHost(e->h_st);
+  if (e->stream) cudaStreamDestroy(e->stream);
+  delete e;
+}
+
+int fpx_reset(fpx_engine* e) {
+  if (!e) return FPX_ERR_INVALID_ARG;
+  CK(e, cudaSetDevice(e->cfg.device));
+  return reset_state(e);
+}
+
+void* fpx_stream(fpx_engine* e) { return e ? (void*)e->stream : nullptr; }
+int64_t fpx_launch_count(const fpx_engine* e) { return e ? e->launches : 0; }
+
+// --------------------------------------------------------------------------- device entry points
+
+static int check_n(fpx_engine* e, const void* p, int32_t n) {
+  if (!e || n < 0 || n > e->cfg.max_batch || (n > 0 && !p)) return FPX_ERR_INVALID_ARG;
+  return FPX_OK;
+}
+
+int fpx_proxyleader_arm_dev(fpx_engine* e, const fpx_p2a* d_in, int32_t n) {
+  int c = check_n(e, d_in, n);
+  if (c != FPX_OK || n == 0) return c;
+  ArmParams P;
+  P.g = e->g;
+  P.pl = PLState{e->rows, e->ovf_keys, e->ovf_rows};
+  P.in = (const int4*)d_in;
+  P.n = n;
+  P.st = e->st;
+  P.conflicts = (ArmConflict*)e->conflicts;
+  P.win_bits = e->bits;
+  arm_kernel<<<(n + 255) / 256, 256, 0, e->stream>>>(P);
+  e->launches++;
+  CK(e, cudaGetLastError());
+  return FPX_OK;
+}
+
+int fpx_acceptor_phase2a_dev(fpx_engine* e, const fpx_p2a* d_in, int32_t n, fpx_p2b* d_out_p2b,
+                             fpx_nack* d_out_nack) {
+  int c = check_n(e, d_in, n);
+  if (c != FPX_OK) return c;
+  if (n > 0 && (!d_out_p2b || !d_out_nack)) return FPX_ERR_INVALID_ARG;
+  if (n == 0) {
+    e->h_st->n_p2b = e->h_st->n_nack = 0;
+    CK(e, cudaMemsetAsync(&e->st->n_p2b, 0, 8, e->stream));
+    return FPX_OK;
+  }
+  AcceptorParams P;
+  P.g = e->g;
+  P.in = (const int4*)d_in;
+  P.n = n;
+  P.out_p2b = (int4*)d_out_p2b;
+  P.out_nack = (int2*)d_out_nack;
+  P.votes = e->votes;
+  P.acc_round = e->acc_round;
+  P.acc_max_voted = e->acc_max_voted;
+  P.accept_bits = e->bits;
+  P.desc_max = e->desc_max;
+  P.desc_cnt = e->desc_cnt;
+  P.epoch = ++e->epoch & 0x3fffffffu;
+  if (P.epoch == 0) P.epoch = e->epoch = 1;
+  P.st = e->st;
+  P.conflicts = (VoteConflict*)e->conflicts;
+  acceptor_phase2a_kernel<<<(n + kTile - 1) / kTile, kTileThreads, 0, e->stream>>>(P);
+  e->launches++;
+  CK(e, cudaGetLastError());
+  return FPX_OK;
+}
+
+int fpx_proxyleader_phase2b_dev(fpx_engine* e, const fpx_p2b* d_in, int32_t n, fpx_chosen* d_out) {
+  int c = check_n(e, d_in, n);
+  if (c != FPX_OK) return c;
+  if (n > 0 && !d_out) return FPX_ERR_INVALID_ARG;
+  e->last_p2b_n = n;
+  if (n == 0) {
+    CK(e, cudaMemsetAsync(&e->st->n_chosen, 0, 4, e->stream));
+    return FPX_OK;
+  }
+  if (e->seq_base > 0xffffffffu - (uint32_t)n - 16u) {
+    size_t nrows = (size_t)e->g.local_slots;
+    renormalize_stamps_kernel<<<(unsigned)((nrows + 255) / 256), 256, 0, e->stream>>>(e->g, e->rows, nrows);
+    if (e->g.ovf_cap)
+      renormalize_stamps_kernel<<<(e->g.ovf_cap + 255) / 256, 256, 0, e->stream>>>(e->g, e->ovf_rows,
+                                                                                   (size_t)e->g.ovf_cap);
+    e->launches += 2;
+    e->seq_base = 1;
+  }
+  TallyParams P;
+  P.g = e->g;
+  P.pl = PLState{e->rows, e->ovf_keys, e->ovf_rows};
+  P.in = (const int4*)d_in;
+  P.n = n;
+  P.seq_base = e->seq_base;
+  P.out_chosen = (int2*)d_out;
+  P.desc_cnt = e->desc_cnt;
+  P.epoch = ++e->epoch & 0x3fffffffu;
+  if (P.epoch == 0) P.epoch = e->epoch = 1;
+  P.st = e->st;
+  e->seq_base += (uint32_t)n;
+  tally_stamp_kernel<<<(n + 255) / 256, 256, 0, e->stream>>>(P);
+  int tiles = (n + kTile - 1) / kTile;
+  switch (e->g.row_words) {
+    case 8: tally_complete_kernel<8><<<tiles, kTileThreads, 0, e->stream>>>(P); break;
+    case 16: tally_complete_kernel<16><<<tiles, kTileThreads, 0, e->stream>>>(P); break;
+    default: tally_complete_kernel<32><<<tiles, kTileThreads, 0, e->stream>>>(P); break;
+  }
+  e->launches += 2;
+  CK(e, cudaGetLastError());
+  return FPX_OK;
+}
+
+static int replica_launch(fpx_engine* e, const fpx_chosen* d_in, int32_t n, int32_t bound) {
+  if (bound == 0) return FPX_OK;
+  if (e->rseq_base > 0xffffffffu - (uint32_t)bound - 16u) {
+    size_t nl = (size_t)e->g.local_slots;
+    renormalize_rlog_kernel<<<(unsigned)((nl + 255) / 256), 256, 0, e->stream>>>(e->rlog, nl);
+    e->launches++;
+    e->rseq_base = 1;
+  }
+  ReplicaParams P;
+  P.g = e->g;
+  P.in = (const int2*)d_in;
+  P.n = n;
+  P.seq_base = e->rseq_base;
+  P.rlog = e->rlog;
+  P.st = e->st;
+  e->rseq_base += (uint32_t)bound;
+  int blocks = std::min((bound + 255) / 256, 148 * 8);
+  replica_chosen_kernel<<<blocks, 256, 0, e->stream>>>(P);
+  e->launches++;
+  CK(e, cudaGetLastError());
+  return FPX_OK;
+}
+
+int fpx_replica_chosen_dev(fpx_engine* e, const fpx_chosen* d_in, int32_t n) {
+  int c = check_n(e, d_in, n);
+  if (c != FPX_OK) return c;
+  return replica_launch(e, d_in, n, n);
+}
+
+int fpx_replica_chosen_last_dev(fpx_engine* e, const fpx_chosen* d_in) {
+  if (!e || (!d_in && e->last_p2b_n > 0)) return FPX_ERR_INVALID_ARG;
+  return replica_launch(e, d_in, -1, e->last_p2b_n);
+}
+
+int fpx_chosen_watermark_dev(fpx_engine* e, int32_t* d_out) {
+  if (!e) return FPX_ERR_INVALID_ARG;
+  watermark_scan_kernel<<<148 * 4, 256, 0, e->stream>>>(e->g, e->rlog, e->st);
+  watermark_finish_kernel<<<1, 1, 0, e->stream>>>(e->g, e->st, d_out);
+  e->launches += 2;
+  CK(e, cudaGetLastError());
+  return FPX_OK;
+}
+
+int fpx_sync(fpx_engine* e, fpx_sync_result* out) {
+  if (!e) return FPX_ERR_INVALID_ARG;
+  CK(e, cudaMemcpyAsync(e->h_st, e->st, sizeof(DevStatus), cudaMemcpyDeviceToHost, e->stream));
+  CK(e, cudaStreamSynchronize(e->stream));
+  int status = FPX_OK;
+  long long idx = -1;
+  if (e->h_st->err_word != ~0ull) {
+    status = -(int)(e->h_st->err_word & 0xff);
+    idx = (long long)(e->h_st->err_word >> 8);
+    unsigned long long none = ~0ull;
+    CK(e, cudaMemcpyAsync(&e->st->err_word, &none, 8, cudaMemcpyHostToDevice, e->stream));
+    CK(e, cudaStreamSynchronize(e->stream));
+  }
+  if (out) {
+    out->status = status;
+    out->reserved = 0;
+    out->err_index = idx;
+    out->n_p2b = e->h_st->n_p2b;
+    out->n_nack = e->h_st->n_nack;
+    out->n_chosen = e->h_st->n_chosen;
+    out->watermark = e->h_st->watermark;
+  }
+  return status;
+}
+
+// --------------------------------------------------------------------------- host entry points
+
+int fpx_proxyleader_arm(fpx_engine* e, const fpx_p2a* in, int32_t n, int64_t* err_index) {
+  if (err_index) *err_index = -1;
+  int c = check_n(e, in, n);
+  if (c != FPX_OK || n == 0) return c;
+  CK(e, cudaSetDevice(e->cfg.device));
+  CK(e, cudaMemcpyAsync(e->d_in, in, (size_t)n * 16, cudaMemcpyHostToDevice, e->stream));
+  c = fpx_proxyleader_arm_dev(e, (const fpx_p2a*)e->d_in, n);
+  if (c != FPX_OK) return c;
+  fpx_sync_result r;
+  c = fpx_sync(e, &r);
+  if (err_index) *err_index = r.err_index;
+  return c;
+}
+
+int fpx_acceptor_phase2a(fpx_engine* e, const fpx_p2a* in, int32_t n, fpx_p2b* out_p2b, int32_t* n_p2b,
+                         fpx_nack* out_nack, int32_t* n_nack, int64_t* err_index) {
+  if (err_index) *err_index = -1;
+  if (n_p2b) *n_p2b = 0;
+  if (n_nack) *n_nack = 0;
+  int c = check_n(e, in, n);
+  if (c != FPX_OK || n == 0) return c;
+  if (!out_p2b || !out_nack || !n_p2b || !n_nack) return FPX_ERR_INVALID_ARG;
+  CK(e, cudaSetDevice(e->cfg.device));
+  CK(e, cudaMemcpyAsync(e->d_in, in, (size_t)n * 16, cudaMemcpyHostToDevice, e->stream));
+  c = fpx_acceptor_phase2a_dev(e, (const fpx_p2a*)e->d_in, n, (fpx_p2b*)e->d_out_a, (fpx_nack*)e->d_out_b);
+  if (c != FPX_OK) return c;
+  fpx_sync_result r;
+  c = fpx_sync(e, &r);
+  if (err_index) *err_index = r.err_index;
+  if (c != FPX_OK) return c;
+  *n_p2b = r.n_p2b;
+  *n_nack = r.n_nack;
+  if (r.n_p2b) CK(e, cudaMemcpyAsync(out_p2b, e->d_out_a, (size_t)r.n_p2b * 16, cudaMemcpyDeviceToHost, e->stream));
+  if (r.n_nack) CK(e, cudaMemcpyAsync(out_nack, e->d_out_b, (size_t)r.n_nack * 8, cudaMemcpyDeviceToHost, e->stream));
+  CK(e, cudaStreamSynchronize(e->stream));
+  return FPX_OK;
+}
+
+int fpx_proxyleader_phase2b(fpx_engine* e, const fpx_p2b* in, int32_t n, fpx_chosen* out, int32_t* n_out,
+                            int64_t* err_index) {
+  if (err_index) *err_index = -1;
+  if (n_out) *n_out = 0;
+  int c = check_n(e, in, n);
+  if (c != FPX_OK || n == 0) return c;
+  if (!out || !n_out) return FPX_ERR_INVALID_ARG;
+  CK(e, cudaSetDevice(e->cfg.device));
+  CK(e, cudaMemcpyAsync(e->d_in, in, (size_t)n * 16, cudaMemcpyHostToDevice, e->stream));
+  c = fpx_proxyleader_phase2b_dev(e, (const fpx_p2b*)e->d_in, n, (fpx_chosen*)e->d_out_b);
+  if (c != FPX_OK) return c;
+  fpx_sync_result r;
+  c = fpx_sync(e, &r);
+  if (err_index) *err_index = r.err_index;
+  if (c != FPX_OK) return c;
+  *n_out = r.n_chosen;
+  if (r.n_chosen) {
+    CK(e, cudaMemcpyAsync(out, e->d_out_b, (size_t)r.n_chosen * 8, cudaMemcpyDeviceToHost, e->stream));
+    CK(e, cudaStreamSynchronize(e->stream));
+  }
+  return FPX_OK;
+}
+
+int fpx_replica_chosen(fpx_engine* e, const fpx_chosen* in, int32_t n, int64_t* err_index) {
+  if (err_index) *err_index = -1;
+  int c = check_n(e, in, n);
+  if (c != FPX_OK || n == 0) return c;
+  CK(e, cudaSetDevice(e->cfg.device));
+  CK(e, cudaMemcpyAsync(e->d_in, in, (size_t)n * 8, cudaMemcpyHostToDevice, e->stream));
+  c = fpx_replica_chosen_dev(e, (const fpx_chosen*)e->d_in, n);
+  if (c != FPX_OK) return c;
+  fpx_sync_result r;
+  c = fpx_sync(e, &r);
+  if (err_index) *err_index = r.err_index;
+  return c;
+}
+
+int fpx_chosen_watermark(fpx_engine* e, int32_t* out) {
+  if (!e || !out) return FPX_ERR_INVALID_ARG;
+  CK(e, cudaSetDevice(e->cfg.device));
+  int c = fpx_chosen_watermark_dev(e, nullptr);
+  if (c != FPX_OK) return c;
+  fpx_sync_result r;
+  c = fpx_sync(e, &r);
+  *out = r.watermark;
+  return c;
+}
+
+int fpx_quorum_eval(fpx_engine* e, int32_t which, const uint32_t* masks, int32_t n, uint8_t* out) {
+  if (!e || which < 0 || which > 3 || n < 0 || (n > 0 && (!masks || !out))) return FPX_ERR_INVALID_ARG;
+  if (n == 0) return FPX_OK;
+  CK(e, cudaSetDevice(e->cfg.device));
+  uint32_t* d_m = nullptr;
+  uint8_t* d_o = nullptr;
+  CK(e, cudaMalloc(&d_m, (size_t)n * 4));
+  CK(e, cudaMalloc(&d_o, (size_t)n));
+  CK(e, cudaMemcpyAsync(d_m, masks, (size_t)n * 4, cudaMemcpyHostToDevice, e->stream));
+  quorum_eval_kernel<<<(n + 255) / 256, 256, 0, e->stream>>>(e->g, which, d_m, n, d_o);
+  e->launches++;
+  CK(e, cudaMemcpyAsync(out, d_o, (size_t)n, cudaMemcpyDeviceToHost, e->stream));
+  CK(e, cudaStreamSynchronize(e->stream));
+  cudaFree(d_m);
+  cudaFree(d_o);
+  return FPX_OK;
+}
+
+int fpx_snapshot_acceptor(fpx_engine* e, int32_t group, int32_t acceptor, int32_t* round,
+                          int32_t* max_voted_slot, int32_t first_slot, int32_t n_slots, int32_t* vote_round,
+                          int32_t* vote_value) {
+  if (!e || group < 0 || group >= e->g.groups || acceptor < 0 || acceptor >= e->g.per_group || n_slots < 0)
+    return FPX_ERR_INVALID_ARG;
+  CK(e, cudaSetDevice(e->cfg.device));
+  int key = group * e->g.per_group + acceptor;
+  if (round) CK(e, cudaMemcpyAsync(round, e->acc_round + key, 4, cudaMemcpyDeviceToHost, e->stream));
+  if (max_voted_slot)
+    CK(e, cudaMemcpyAsync(max_voted_slot, e->acc_max_voted + key, 4, cudaMemcpyDeviceToHost, e->stream));
+  if (n_slots > 0) {
+    if (!vote_round || !vote_value) return FPX_ERR_INVALID_ARG;
+    int32_t *d_r = nullptr, *d_v = nullptr;
+    CK(e, cudaMalloc(&d_r, (size_t)n_slots * 4));
+    CK(e, cudaMalloc(&d_v, (size_t)n_slots * 4));
+    snapshot_votes_kernel<<<(n_slots + 255) / 256, 256, 0, e->stream>>>(e->g, e->votes, group, acceptor,
+                                                                         first_slot, n_slots, d_r, d_v);
+    e->launches++;
+    CK(e, cudaMemcpyAsync(vote_round, d_r, (size_t)n_slots * 4, cudaMemcpyDeviceToHost, e->stream));
+    CK(e, cudaMemcpyAsync(vote_value, d_v, (size_t)n_slots * 4, cudaMemcpyDeviceToHost, e->stream));
+    CK(e, cudaStreamSynchronize(e->stream));
+    cudaFree(d_r);
+    cudaFree(d_v);
+  }
+  CK(e, cudaStreamSynchronize(e->stream));
+  return FPX_OK;
+}
+
+int fpx_snapshot_log(fpx_engine* e, int32_t first_slot, int32_t n_slots, int32_t* value_id) {
+  if (!e || n_slots < 0 || (n_slots > 0 && !value_id)) return FPX_ERR_INVALID_ARG;
+  if (n_slots == 0) return FPX_OK;
+  CK(e, cudaSetDevice(e->cfg.device));
+  int32_t* d_v = nullptr;
+  CK(e, cudaMalloc(&d_v, (size_t)n_slots * 4));
+  snapshot_log_kernel<<<(n_slots + 255) / 256, 256, 0, e->stream>>>(e->g, e->rlog, first_slot, n_slots, d_v);
+  e->launches++;
+  CK(e, cudaMemcpyAsync(value_id, d_v, (size_t)n_slots * 4, cudaMemcpyDeviceToHost, e->stream));
+  CK(e, cudaStreamSynchronize(e->stream));
+  cudaFree(d_v);
+  return FPX_OK;
+}
+
+}  // extern "C"

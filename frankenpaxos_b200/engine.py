@@ -1,0 +1,184 @@
+"""Thin Python handle over the C ABI (include/fpx.h).  Arrays in, arrays out.
+
+Record dtypes mirror the protobuf messages of the reference's hot path
+(shared/src/main/scala/frankenpaxos/multipaxos/MultiPaxos.proto:273-290).
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+
+P2A = np.dtype([("slot", "<i4"), ("round", "<i4"), ("value_id", "<i4"), ("dst", "<i4")])
+P2B = np.dtype([("group", "<i4"), ("acceptor", "<i4"), ("slot", "<i4"), ("round", "<i4")])
+CHOSEN = np.dtype([("slot", "<i4"), ("value_id", "<i4")])
+NACK = np.dtype([("leader", "<i4"), ("round", "<i4")])
+
+MULTIPAXOS, MENCIUS, VANILLA_MENCIUS = 0, 1, 2
+
+OK = 0
+ERR_INVALID_ARG, ERR_CONFIG, ERR_CUDA, ERR_UNKNOWN_SLOT_ROUND, ERR_BAD_ACCEPTOR = -1, -2, -3, -4, -5
+ERR_SLOT_RANGE, ERR_ROUND_RANGE, ERR_OVERFLOW_FULL, ERR_CONFLICT, ERR_NO_DEVICE, ERR_UNSUPPORTED = \
+    -6, -7, -8, -9, -10, -11
+
+
+class FpxError(RuntimeError):
+    """A negative fpx_status: the reference's logger.fatal / require at `index`."""
+
+    def __init__(self, status, index=-1, detail=""):
+        self.status, self.index = status, index
+        msg = _lib.lib().fpx_strerror(status).decode()
+        super().__init__(f"fpx status {status} ({msg}) at record {index}{(': ' + detail) if detail else ''}")
+
+
+def dst(group, acceptor):
+    """fpx_p2a.dst encoding."""
+    return (np.asarray(group, dtype=np.int32) << 16) | np.asarray(acceptor, dtype=np.int32)
+
+
+class Engine:
+    """One GPU-resident {acceptors, proxy leader, replica log} for one config."""
+
+    def __init__(self, f, num_acceptor_groups, acceptors_per_group, flexible=False, num_leaders=None,
+                 num_replicas=None, slot_capacity=1 << 20, overflow_capacity=1 << 10, max_batch=1 << 20,
+                 device=0, shard_index=0, shard_count=1, protocol=MULTIPAXOS):
+        L = _lib.lib()
+        cfg = _lib.Config()
+        cfg.struct_size = C.sizeof(_lib.Config)
+        cfg.protocol = protocol
+        cfg.f = f
+        cfg.num_acceptor_groups = num_acceptor_groups
+        cfg.acceptors_per_group = acceptors_per_group
+        cfg.flexible = int(bool(flexible))
+        cfg.num_leaders = f + 1 if num_leaders is None else num_leaders
+        cfg.num_replicas = f + 1 if num_replicas is None else num_replicas
+        cfg.slot_capacity = slot_capacity
+        cfg.overflow_capacity = overflow_capacity
+        cfg.max_batch = max_batch
+        cfg.device = device
+        cfg.shard_index, cfg.shard_count = shard_index, shard_count
+        self.cfg = cfg
+        self._L = L
+        self.h = C.c_void_p()
+        st = L.fpx_create(C.byref(self.h), C.byref(cfg))
+        if st != OK:
+            self.h = None
+            raise FpxError(st)
+
+    # -- life cycle
+    def close(self):
+        if getattr(self, "h", None):
+            self._L.fpx_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def reset(self):
+        self._check(self._L.fpx_reset(self.h))
+
+    def _check(self, st, idx=-1):
+        if st != OK:
+            detail = self._L.fpx_last_error(self.h).decode() if st == ERR_CUDA else ""
+            raise FpxError(st, idx, detail)
+
+    @property
+    def stream(self):
+        return self._L.fpx_stream(self.h)
+
+    @property
+    def launch_count(self):
+        return self._L.fpx_launch_count(self.h)
+
+    # -- host-pointer calls (numpy in / numpy out)
+    def proxyleader_arm(self, p2a):
+        p2a = np.ascontiguousarray(p2a, dtype=P2A)
+        err = C.c_int64(-1)
+        st = self._L.fpx_proxyleader_arm(self.h, p2a.ctypes.data, len(p2a), C.byref(err))
+        self._check(st, err.value)
+
+    def acceptor_phase2a(self, p2a):
+        p2a = np.ascontiguousarray(p2a, dtype=P2A)
+        n = len(p2a)
+        out = np.empty(max(n, 1), dtype=P2B)
+        nack = np.empty(max(n, 1), dtype=NACK)
+        n1, n2, err = C.c_int32(0), C.c_int32(0), C.c_int64(-1)
+        st = self._L.fpx_acceptor_phase2a(self.h, p2a.ctypes.data, n, out.ctypes.data, C.byref(n1),
+                                          nack.ctypes.data, C.byref(n2), C.byref(err))
+        self._check(st, err.value)
+        return out[:n1.value], nack[:n2.value]
+
+    def proxyleader_phase2b(self, p2b):
+        p2b = np.ascontiguousarray(p2b, dtype=P2B)
+        n = len(p2b)
+        out = np.empty(max(n, 1), dtype=CHOSEN)
+        n1, err = C.c_int32(0), C.c_int64(-1)
+        st = self._L.fpx_proxyleader_phase2b(self.h, p2b.ctypes.data, n, out.ctypes.data, C.byref(n1),
+                                             C.byref(err))
+        self._check(st, err.value)
+        return out[:n1.value]
+
+    def replica_chosen(self, chosen):
+        chosen = np.ascontiguousarray(chosen, dtype=CHOSEN)
+        err = C.c_int64(-1)
+        st = self._L.fpx_replica_chosen(self.h, chosen.ctypes.data, len(chosen), C.byref(err))
+        self._check(st, err.value)
+
+    def chosen_watermark(self):
+        out = C.c_int32(0)
+        self._check(self._L.fpx_chosen_watermark(self.h, C.byref(out)))
+        return out.value
+
+    def quorum_eval(self, which, masks):
+        masks = np.ascontiguousarray(masks, dtype=np.uint32)
+        out = np.empty(max(len(masks), 1), dtype=np.uint8)
+        self._check(self._L.fpx_quorum_eval(self.h, which, masks.ctypes.data, len(masks), out.ctypes.data))
+        return out[:len(masks)]
+
+    def snapshot_acceptor(self, group, acceptor, first_slot=0, n_slots=0):
+        vr = np.empty(max(n_slots, 1), dtype=np.int32)
+        vv = np.empty(max(n_slots, 1), dtype=np.int32)
+        r, m = C.c_int32(0), C.c_int32(0)
+        self._check(self._L.fpx_snapshot_acceptor(self.h, group, acceptor, C.byref(r), C.byref(m), first_slot,
+                                                  n_slots, vr.ctypes.data, vv.ctypes.data))
+        return r.value, m.value, vr[:n_slots], vv[:n_slots]
+
+    def snapshot_log(self, first_slot, n_slots):
+        v = np.empty(max(n_slots, 1), dtype=np.int32)
+        self._check(self._L.fpx_snapshot_log(self.h, first_slot, n_slots, v.ctypes.data))
+        return v[:n_slots]
+
+    # -- device-pointer calls (raw device addresses, asynchronous on self.stream)
+    def proxyleader_arm_dev(self, d_in, n):
+        self._check(self._L.fpx_proxyleader_arm_dev(self.h, d_in, n))
+
+    def acceptor_phase2a_dev(self, d_in, n, d_out_p2b, d_out_nack):
+        self._check(self._L.fpx_acceptor_phase2a_dev(self.h, d_in, n, d_out_p2b, d_out_nack))
+
+    def proxyleader_phase2b_dev(self, d_in, n, d_out):
+        self._check(self._L.fpx_proxyleader_phase2b_dev(self.h, d_in, n, d_out))
+
+    def replica_chosen_dev(self, d_in, n):
+        self._check(self._L.fpx_replica_chosen_dev(self.h, d_in, n))
+
+    def replica_chosen_last_dev(self, d_in):
+        self._check(self._L.fpx_replica_chosen_last_dev(self.h, d_in))
+
+    def chosen_watermark_dev(self, d_out=None):
+        self._check(self._L.fpx_chosen_watermark_dev(self.h, d_out))
+
+    def sync(self, check=True):
+        r = _lib.SyncResult()
+        st = self._L.fpx_sync(self.h, C.byref(r))
+        if check:
+            self._check(st, r.err_index)
+        return r

@@ -1,0 +1,110 @@
+"""Synthetic delivery traces for the quorum-vote path.
+
+A trace is what the reference's transport would deliver: arrays of fixed-size
+records in delivery order.  Recipient choice and delivery interleaving are
+INPUTS (the reference draws them from an unseeded global RNG,
+shared/src/main/scala/frankenpaxos/multipaxos/ProxyLeader.scala:190-196), here
+drawn from numpy's PCG64 so that oracle and engine see identical traces.
+"""
+import numpy as np
+
+from .engine import P2A, P2B, dst
+
+
+def rng(seed):
+    return np.random.Generator(np.random.PCG64(seed))
+
+
+def arms(slots, round_=0, values=None):
+    """Phase2a records as a leader sends them to a proxy leader (slot order)."""
+    slots = np.asarray(slots, dtype=np.int32)
+    a = np.zeros(len(slots), dtype=P2A)
+    a["slot"] = slots
+    a["round"] = round_
+    a["value_id"] = slots if values is None else values
+    a["dst"] = -1
+    return a
+
+
+def _choose_k_of_n(g, n_rows, n, k):
+    """n_rows independent uniform k-subsets of range(n), each in random order."""
+    keys = g.random((n_rows, n))
+    return np.argsort(keys, axis=1)[:, :k].astype(np.int32)
+
+
+def phase2as(g, slots, f, groups, per_group, flexible, round_=0, values=None, thrifty=True):
+    """The copies a proxy leader forwards to acceptors (ProxyLeader.handlePhase2a,
+    ProxyLeader.scala:186-197): non-flexible -> f+1 random members of group
+    slot % groups; flexible -> one random grid column, i.e. one acceptor per row.
+    thrifty=False sends to every acceptor that may vote on the slot."""
+    slots = np.asarray(slots, dtype=np.int32)
+    n = len(slots)
+    vals = slots if values is None else np.asarray(values, dtype=np.int32)
+    if not flexible:
+        q = f + 1 if thrifty else per_group
+        acc = _choose_k_of_n(g, n, per_group, q)
+        grp = np.repeat((slots % groups)[:, None], q, axis=1)
+    else:
+        if thrifty:
+            q = groups
+            col = g.integers(0, per_group, size=n, dtype=np.int32)
+            acc = np.repeat(col[:, None], groups, axis=1)
+            grp = np.repeat(np.arange(groups, dtype=np.int32)[None, :], n, axis=0)
+        else:
+            q = groups * per_group
+            acc = np.tile(np.tile(np.arange(per_group, dtype=np.int32), groups), (n, 1))
+            grp = np.tile(np.repeat(np.arange(groups, dtype=np.int32), per_group), (n, 1))
+    out = np.zeros(n * q, dtype=P2A)
+    out["slot"] = np.repeat(slots, q)
+    out["round"] = round_ if np.isscalar(round_) else np.repeat(np.asarray(round_, dtype=np.int32), q)
+    out["value_id"] = np.repeat(vals, q)
+    out["dst"] = dst(grp.reshape(-1), acc.reshape(-1))
+    return out
+
+
+def votes_of(p2a):
+    """Phase2b each accepted Phase2a produces (Acceptor.scala:211-219)."""
+    b = np.zeros(len(p2a), dtype=P2B)
+    b["group"] = p2a["dst"] >> 16
+    b["acceptor"] = p2a["dst"] & 0xffff
+    b["slot"] = p2a["slot"]
+    b["round"] = p2a["round"]
+    return b
+
+
+def shuffled(g, recs, partitions=None, key=None):
+    """A uniformly random delivery order; with `partitions`, records are shuffled
+    within each partition (key % partitions) and partitions are concatenated."""
+    if partitions is None:
+        return recs[g.permutation(len(recs))]
+    k = (recs["slot"] if key is None else key) % partitions
+    order = np.lexsort((g.random(len(recs)), k))
+    return recs[order]
+
+
+def config_by_name(name):
+    """BASELINE.json configs -> engine constructor kwargs + workload shape."""
+    if name == "cfg1":   # MultiPaxos f=1, 3 acceptors, 128 slots
+        return dict(f=1, num_acceptor_groups=1, acceptors_per_group=3, flexible=False, num_leaders=2,
+                    num_replicas=2), 128
+    if name == "cfg2":   # MultiPaxos 5 acceptors SimpleMajority, 1M slots
+        return dict(f=2, num_acceptor_groups=1, acceptors_per_group=5, flexible=False, num_leaders=3,
+                    num_replicas=3), 1 << 20
+    if name == "cfg3":   # Compartmentalized 2x3 grid, 10 proxy leaders, 4M slots
+        return dict(f=1, num_acceptor_groups=2, acceptors_per_group=3, flexible=True, num_leaders=2,
+                    num_replicas=2), 1 << 22
+    raise KeyError(name)
+
+
+def workload(seed, cfg, n_slots, slot0=0, round_=0, slot_stride=1, slot_offset=0, partitions=None):
+    """One step of the benchmark workload: every slot of the window is armed,
+    forwarded to a thrifty quorum, voted, and the votes arrive shuffled.
+    Returns (arm, p2a, p2b) record arrays; slots = slot_offset + slot_stride *
+    (slot0 + arange(n_slots)) (stride/offset = shard_count/shard_index)."""
+    g = rng(seed)
+    slots = (slot_offset + slot_stride * (slot0 + np.arange(n_slots, dtype=np.int64))).astype(np.int32)
+    a = arms(slots, round_)
+    p = phase2as(g, slots, cfg["f"], cfg["num_acceptor_groups"], cfg["acceptors_per_group"], cfg["flexible"],
+                 round_)
+    b = shuffled(g, votes_of(p), partitions)
+    return a, p, b

@@ -1,0 +1,347 @@
+"""Parity of the CUDA path (through the C ABI) against the CPU oracle, bit-exact:
+Phase2b / Nack / Chosen streams INCLUDING ORDER, error status + first offending
+index, final acceptor state (round, maxVotedSlot, voteRound[], voteValue[]) and
+replica log / watermark.  Marked gpu: needs a B200."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+import harness as H
+from frankenpaxos_b200 import CHOSEN, P2A, P2B, Engine, FpxError, dst
+from frankenpaxos_b200 import traces as T
+from oracle import fpx_oracle_py as O
+
+pytestmark = pytest.mark.gpu
+
+
+def D(g, a):
+    return (g << 16) | a
+
+
+def recs(dtype, *rows):
+    return np.array(list(rows), dtype=dtype)
+
+
+# --------------------------------------------------------------------------- golden vectors on the GPU
+@pytest.mark.parametrize("kind", ["grid", "simple_majority"])
+def test_quorum_predicates_golden(golden_dir, kind):
+    """GridTest.scala:11-102 / SimpleMajorityTest.scala:11-63 replayed on the CUDA
+    predicate kernel (fpx_quorum_eval)."""
+    g = json.load(open(os.path.join(golden_dir, "quorums.json")))[kind]
+    if kind == "grid":
+        members = [x for row in g["members"] for x in row]
+        eng = Engine(1, 2, 3, flexible=True, slot_capacity=8, max_batch=1024)
+    else:
+        members = g["members"]
+        eng = Engine(2, 1, 5, slot_capacity=8, max_batch=1024)
+    index = {m: i for i, m in enumerate(members)}
+    for which, pred in enumerate(["isReadQuorum", "isWriteQuorum", "isSuperSetOfReadQuorum",
+                                  "isSuperSetOfWriteQuorum"]):
+        cases = [c for c in g["cases"] if c["pred"] == pred]
+        masks = []
+        for c in cases:
+            m = 0
+            for x in c["set"]:
+                m |= (1 << index[x]) if x in index else (1 << 31)
+            masks.append(m)
+        got = eng.quorum_eval(which, np.array(masks, dtype=np.uint32))
+        for c, r in zip(cases, got):
+            assert int(r) == int(c["expect"]), (g["source"], c["line"], c)
+    # `require` on non-members (Grid.scala:36-39)
+    assert eng.quorum_eval(1, np.array([(1 << 31) | 0b001001], dtype=np.uint32))[0] == 2
+    eng.close()
+
+
+# --------------------------------------------------------------------------- hand-derived micro traces
+def test_micro_trace_survey_8g():
+    cfg = dict(f=1, num_acceptor_groups=1, acceptors_per_group=3, flexible=False, num_leaders=2, num_replicas=2)
+    eng, ora = H.make_pair(cfg, 64)
+    H.arm(eng, ora, recs(P2A, (0, 0, 100, -1)))
+    b, _ = H.phase2a(eng, ora, recs(P2A, (0, 0, 100, D(0, 0))))
+    H.phase2b(eng, ora, b)
+    H.phase2b(eng, ora, b)                      # duplicate vote
+    b2, _ = H.phase2a(eng, ora, recs(P2A, (0, 0, 100, D(0, 2))))
+    st, c = H.phase2b(eng, ora, b2)
+    assert c.tolist() == [(0, 100)]
+    H.phase2b(eng, ora, recs(P2B, (0, 1, 0, 0)))  # late vote, Done
+    H.phase2a(eng, ora, recs(P2A, (1, 3, 101, D(0, 0))))
+    b, n = H.phase2a(eng, ora, recs(P2A, (2, 0, 102, D(0, 0))))
+    assert n.tolist() == [(0, 3)]
+    H.phase2a(eng, ora, recs(P2A, (0, 3, 109, D(0, 0))))
+    H.compare_acceptors(eng, ora, cfg, 0, 8)
+    st, _ = H.phase2b(eng, ora, recs(P2B, (0, 1, 0, 0), (0, 0, 5, 0)))
+    assert st == -4
+    eng.close()
+
+
+def test_whole_micro_trace_in_single_batches():
+    """Same deliveries as above but batched: order semantics inside one launch."""
+    cfg = dict(f=1, num_acceptor_groups=1, acceptors_per_group=3, flexible=False, num_leaders=2, num_replicas=2)
+    eng, ora = H.make_pair(cfg, 64)
+    H.arm(eng, ora, recs(P2A, (0, 0, 100, -1), (1, 3, 101, -1), (0, 3, 109, -1), (0, 0, 555, -1)))
+    b, n = H.phase2a(eng, ora, recs(P2A, (0, 0, 100, D(0, 0)), (0, 0, 100, D(0, 2)), (1, 3, 101, D(0, 0)),
+                                    (2, 0, 102, D(0, 0)), (0, 3, 109, D(0, 0)), (0, 3, 777, D(0, 0)),
+                                    (0, 3, 3, D(0, 0))))
+    H.compare_acceptors(eng, ora, cfg, 0, 8)
+    votes = recs(P2B, (0, 0, 0, 0), (0, 0, 0, 0), (0, 2, 0, 0), (0, 1, 0, 0), (0, 0, 1, 3), (0, 0, 0, 3),
+                 (0, 1, 0, 3), (0, 1, 1, 3))
+    st, c = H.phase2b(eng, ora, votes)
+    assert c.tolist() == [(0, 100), (0, 109), (1, 101)]
+    H.replica(eng, ora, c)
+    H.compare_log(eng, ora, 0, 8)
+    eng.close()
+
+
+def test_grid_and_bad_acceptor():
+    cfg = dict(f=1, num_acceptor_groups=2, acceptors_per_group=3, flexible=True, num_leaders=2, num_replicas=2)
+    eng, ora = H.make_pair(cfg, 64)
+    H.arm(eng, ora, recs(P2A, (0, 0, 7, -1), (1, 0, 8, -1), (2, 0, 9, -1)))
+    st, c = H.phase2b(eng, ora, recs(P2B, (0, 1, 0, 0), (0, 2, 0, 0), (1, 0, 0, 0), (1, 1, 0, 0)))
+    assert c.tolist() == [(0, 7)]
+    # foreign acceptor on a Done key is ignored; on a Pending key it is `require`
+    st, c = H.phase2b(eng, ora, recs(P2B, (5, 0, 0, 0), (0, 0, 1, 0)))
+    assert st == 0
+    st, c = H.phase2b(eng, ora, recs(P2B, (1, 1, 1, 0), (0, 0, 2, 0), (5, 0, 2, 0), (9, 9, 2, 0)))
+    assert st == -5
+    eng.close()
+
+
+def test_bad_acceptor_after_completion_in_same_batch_is_ignored():
+    cfg = dict(f=1, num_acceptor_groups=2, acceptors_per_group=3, flexible=True, num_leaders=2, num_replicas=2)
+    eng, ora = H.make_pair(cfg, 64)
+    H.arm(eng, ora, recs(P2A, (3, 0, 7, -1)))
+    st, c = H.phase2b(eng, ora, recs(P2B, (0, 1, 3, 0), (1, 1, 3, 0), (7, 7, 3, 0)))
+    assert st == 0 and c.tolist() == [(3, 7)]
+    eng.close()
+
+
+def test_two_live_rounds_and_overflow_table():
+    cfg = dict(f=1, num_acceptor_groups=1, acceptors_per_group=3, flexible=False, num_leaders=2, num_replicas=2)
+    eng, ora = H.make_pair(cfg, 64)
+    H.arm(eng, ora, recs(P2A, (4, 0, 40, -1), (4, 1, 41, -1), (4, 2, 42, -1), (5, 7, 50, -1)))
+    st, c = H.phase2b(eng, ora, recs(P2B, (0, 0, 4, 1), (0, 0, 4, 0), (0, 1, 4, 1), (0, 2, 4, 0), (0, 2, 4, 2)))
+    assert c.tolist() == [(4, 41), (4, 40)]
+    H.replica(eng, ora, c)
+    st, c = H.phase2b(eng, ora, recs(P2B, (0, 1, 4, 2), (0, 1, 5, 7), (0, 0, 5, 7)))
+    assert c.tolist() == [(4, 42), (5, 50)]
+    H.replica(eng, ora, c)
+    H.compare_log(eng, ora, 0, 8)
+    # unknown round of a known slot is fatal too
+    st, _ = H.phase2b(eng, ora, recs(P2B, (0, 1, 4, 9)))
+    assert st == -4
+    eng.close()
+
+
+def test_duplicate_arm_different_value_keeps_first_in_order():
+    cfg = dict(f=1, num_acceptor_groups=1, acceptors_per_group=3, flexible=False, num_leaders=2, num_replicas=2)
+    eng, ora = H.make_pair(cfg, 4096)
+    n = 3000
+    a = np.zeros(2 * n, dtype=P2A)
+    a["slot"] = np.concatenate([np.arange(n), np.arange(n)[::-1]])
+    a["value_id"] = np.arange(2 * n) + 10
+    a["dst"] = -1
+    H.arm(eng, ora, a[:50])             # some keys exist before the conflicting batch
+    H.arm(eng, ora, a)                  # every key armed twice with different values
+    votes = T.votes_of(T.phase2as(T.rng(0), np.arange(n), 1, 1, 3, False))
+    st, c = H.phase2b(eng, ora, votes)
+    assert len(c) == n
+    eng.close()
+
+
+def test_same_cell_same_round_different_value_last_wins():
+    cfg = dict(f=1, num_acceptor_groups=1, acceptors_per_group=3, flexible=False, num_leaders=2, num_replicas=2)
+    eng, ora = H.make_pair(cfg, 4096)
+    n = 2500
+    p = np.zeros(3 * n, dtype=P2A)
+    p["slot"] = np.tile(np.arange(n), 3)
+    p["round"] = 2
+    p["value_id"] = T.rng(1).integers(0, 1 << 30, size=3 * n)
+    p["dst"] = D(0, 1)
+    H.phase2a(eng, ora, p[:100])
+    H.phase2a(eng, ora, p)
+    H.compare_acceptors(eng, ora, cfg, 0, n)
+    eng.close()
+
+
+# --------------------------------------------------------------------------- BASELINE configs, seeded
+@pytest.mark.parametrize("name,n_slots", [("cfg1", 128), ("cfg2", 20000), ("cfg3", 30000)])
+@pytest.mark.parametrize("seed", [0, 1, 2])
+def test_baseline_configs(name, n_slots, seed):
+    cfg, _ = T.config_by_name(name)
+    eng, ora = H.make_pair(cfg, n_slots, max_batch=1 << 17)
+    a, p, b = T.workload(seed, cfg, n_slots, partitions=10 if name == "cfg3" else None)
+    H.arm(eng, ora, a)
+    ob, on = H.phase2a(eng, ora, p)
+    assert len(on) == 0
+    H.compare_acceptors(eng, ora, cfg, 0, n_slots)
+    total = 0
+    for chunk in np.array_split(b, 5):
+        st, c = H.phase2b(eng, ora, chunk)
+        total += len(c)
+        H.replica(eng, ora, c)
+    assert total == n_slots
+    assert eng.chosen_watermark() == n_slots
+    H.compare_log(eng, ora, 0, n_slots)
+    eng.close()
+
+
+def test_cfg1_round_bump_nacks():
+    """cfg1 variant: a mid-trace round bump (leader 1, round 1) makes later round-0
+    Phase2as stale at the acceptors that saw it."""
+    cfg, n_slots = T.config_by_name("cfg1")
+    for seed in range(3):
+        g = T.rng(100 + seed)
+        eng, ora = H.make_pair(cfg, n_slots)
+        slots = np.arange(n_slots)
+        p0 = T.phase2as(g, slots, 1, 1, 3, False, 0)
+        p1 = T.phase2as(g, slots[: n_slots // 2], 1, 1, 3, False, 1, values=slots[: n_slots // 2] + 1000)
+        mix = np.concatenate([p0, p1])[g.permutation(len(p0) + len(p1))]
+        H.arm(eng, ora, np.concatenate([T.arms(slots, 0), T.arms(slots[: n_slots // 2], 1,
+                                                                 slots[: n_slots // 2] + 1000)]))
+        ob, on = H.phase2a(eng, ora, mix)
+        assert len(on) > 0
+        H.compare_acceptors(eng, ora, cfg, 0, n_slots)
+        st, c = H.phase2b(eng, ora, ob[g.permutation(len(ob))])
+        H.replica(eng, ora, c)
+        H.compare_log(eng, ora, 0, n_slots)
+        eng.close()
+
+
+# --------------------------------------------------------------------------- adversarial differential
+@pytest.mark.parametrize("seed", range(6))
+@pytest.mark.parametrize("shape", ["majority5", "grid2x3", "groups3x3"])
+def test_adversarial_random_traces(seed, shape):
+    """Random rounds (stale and fresh), duplicate deliveries, late votes, several
+    live rounds per slot, non-thrifty fan-out, many small and large batches."""
+    if shape == "majority5":
+        cfg = dict(f=2, num_acceptor_groups=1, acceptors_per_group=5, flexible=False, num_leaders=3,
+                   num_replicas=3)
+    elif shape == "grid2x3":
+        cfg = dict(f=1, num_acceptor_groups=2, acceptors_per_group=3, flexible=True, num_leaders=2,
+                   num_replicas=2)
+    else:
+        cfg = dict(f=1, num_acceptor_groups=3, acceptors_per_group=3, flexible=False, num_leaders=2,
+                   num_replicas=2)
+    g = T.rng(1000 * seed + len(shape))
+    n_slots = 3000
+    eng, ora = H.make_pair(cfg, n_slots, max_batch=1 << 16, overflow_capacity=1 << 13)
+    for phase in range(4):
+        k = int(g.integers(1, 2500))
+        slots = g.integers(0, n_slots, size=k).astype(np.int32)
+        rounds = g.integers(0, 4, size=k).astype(np.int32) if phase else np.zeros(k, dtype=np.int32)
+        values = (slots * 8 + rounds).astype(np.int32)   # one value per (slot, round)
+        a = T.arms(slots, 0, values)
+        a["round"] = rounds
+        H.arm(eng, ora, a)
+        p = T.phase2as(g, slots, cfg["f"], cfg["num_acceptor_groups"], cfg["acceptors_per_group"],
+                       cfg["flexible"], rounds, values, thrifty=bool(g.integers(0, 2)))
+        p = p[g.permutation(len(p))]
+        dup = p[g.integers(0, len(p), size=len(p) // 10)]
+        p = np.concatenate([p, dup])[g.permutation(len(p) + len(dup))]
+        votes = []
+        for chunk in np.array_split(p, int(g.integers(1, 4))):
+            ob, on = H.phase2a(eng, ora, chunk)
+            votes.append(ob)
+        H.compare_acceptors(eng, ora, cfg, 0, n_slots)
+        v = np.concatenate(votes)
+        v = np.concatenate([v, v[g.integers(0, max(len(v), 1), size=len(v) // 5)]]) if len(v) else v
+        v = v[g.permutation(len(v))]
+        for chunk in np.array_split(v, int(g.integers(1, 6))):
+            st, c = H.phase2b(eng, ora, chunk)
+            assert st == 0
+            H.replica(eng, ora, c)
+    H.compare_log(eng, ora, 0, n_slots)
+    eng.close()
+
+
+def test_unknown_key_error_index_is_first_in_order():
+    cfg, _ = T.config_by_name("cfg2")
+    eng, ora = H.make_pair(cfg, 5000)
+    a, p, b = T.workload(3, cfg, 4000)
+    H.arm(eng, ora, a[:3990])              # slots 3990.. never armed
+    st, _ = H.phase2b(eng, ora, b)
+    assert st == -4
+    eng.close()
+
+
+def test_empty_and_ragged_batches():
+    cfg, _ = T.config_by_name("cfg2")
+    eng, ora = H.make_pair(cfg, 5000)
+    z2a, z2b = np.zeros(0, dtype=P2A), np.zeros(0, dtype=P2B)
+    H.arm(eng, ora, z2a)
+    H.phase2a(eng, ora, z2a)
+    H.phase2b(eng, ora, z2b)
+    for n in (1, 31, 32, 33, 255, 1023, 1024, 1025, 2049):
+        eng.reset()
+        ora = O.MultiPaxos(2, 1, 5, False, 3, 3)
+        a, p, b = T.workload(n, cfg, n)
+        H.arm(eng, ora, a)
+        H.phase2a(eng, ora, p)
+        st, c = H.phase2b(eng, ora, b)
+        assert len(c) == n
+    eng.close()
+
+
+def test_sharded_engines_cover_the_log():
+    """Slot-residue sharding: P engines, slot % P == g; the union of
+    their Chosen streams is the unsharded one and the global watermark is
+    min_g(local frontier)."""
+    cfg, _ = T.config_by_name("cfg2")
+    n_slots, P = 6000, 4
+    ora = O.MultiPaxos(2, 1, 5, False, 3, 3)
+    a, p, b = T.workload(11, cfg, n_slots)
+    ora.arm(a)
+    ora.acceptor_phase2a(p)
+    _, _, oc = ora.proxyleader_phase2b(b)
+    ora.replica_chosen(oc)
+    got = []
+    wms = []
+    for gi in range(P):
+        eng = Engine(slot_capacity=n_slots, max_batch=1 << 16, shard_index=gi, shard_count=P, **cfg)
+        eng.proxyleader_arm(a[a["slot"] % P == gi])
+        pb, nk = eng.acceptor_phase2a(p[p["slot"] % P == gi])
+        assert len(nk) == 0
+        c = eng.proxyleader_phase2b(b[b["slot"] % P == gi])
+        eng.replica_chosen(c)
+        wms.append(eng.chosen_watermark())
+        got.append(c)
+        with pytest.raises(FpxError) as ei:
+            eng.proxyleader_arm(a[a["slot"] % P == (gi + 1) % P][:5])
+        assert ei.value.status == -6
+        eng.close()
+    allc = np.concatenate(got)
+    assert sorted(allc.tolist()) == sorted(oc.tolist())
+    assert min(wms) >= n_slots and ora.executed_watermark() == n_slots
+
+
+def test_full_size_properties_cfg2():
+    """BASELINE cfg2 at full size (2^20 slots, 3*2^20 votes): size-independent
+    properties instead of the (slow) oracle: every slot chosen exactly once with
+    value == slot, Chosen order == order of completing votes, watermark == n."""
+    cfg, n_slots = T.config_by_name("cfg2")
+    eng = Engine(slot_capacity=n_slots, max_batch=3 << 20, **cfg)
+    a, p, b = T.workload(0, cfg, n_slots)
+    eng.proxyleader_arm(a)
+    pb, nk = eng.acceptor_phase2a(p)
+    assert len(nk) == 0 and len(pb) == len(p)
+    assert np.array_equal(pb, T.votes_of(p))
+    c = eng.proxyleader_phase2b(b)
+    assert len(c) == n_slots
+    assert np.array_equal(np.sort(c["slot"]), np.arange(n_slots))
+    assert np.array_equal(c["slot"], c["value_id"])
+    # completing vote of a slot = the LAST of its 3 votes in delivery order
+    last = np.zeros(n_slots, dtype=np.int64)
+    np.maximum.at(last, b["slot"], np.arange(len(b)))
+    assert np.array_equal(c["slot"], b["slot"][np.sort(last)])
+    eng.replica_chosen(c)
+    assert eng.chosen_watermark() == n_slots
+    for g_, a_ in [(0, 0), (0, 4)]:
+        r, m, vr, vv = eng.snapshot_acceptor(g_, a_, 0, n_slots)
+        mine = p[(p["dst"] & 0xffff) == a_]
+        assert r == 0 and m == mine["slot"].max()
+        exp = np.full(n_slots, -1, dtype=np.int32)
+        exp[mine["slot"]] = 0
+        assert np.array_equal(vr, exp)
+    eng.close()
