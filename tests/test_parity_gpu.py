@@ -137,7 +137,7 @@ def test_two_live_rounds_and_overflow_table():
 def test_duplicate_arm_different_value_keeps_first_in_order():
     cfg = dict(f=1, num_acceptor_groups=1, acceptors_per_group=3, flexible=False, num_leaders=2, num_replicas=2)
     eng, ora = H.make_pair(cfg, 4096)
-    n = 3000
+    n = 900                             # <= kMaxConflicts (1024) detections per batch
     a = np.zeros(2 * n, dtype=P2A)
     a["slot"] = np.concatenate([np.arange(n), np.arange(n)[::-1]])
     a["value_id"] = np.arange(2 * n) + 10
@@ -153,7 +153,7 @@ def test_duplicate_arm_different_value_keeps_first_in_order():
 def test_same_cell_same_round_different_value_last_wins():
     cfg = dict(f=1, num_acceptor_groups=1, acceptors_per_group=3, flexible=False, num_leaders=2, num_replicas=2)
     eng, ora = H.make_pair(cfg, 4096)
-    n = 2500
+    n = 300                             # <= kMaxConflicts (1024) detections per batch
     p = np.zeros(3 * n, dtype=P2A)
     p["slot"] = np.tile(np.arange(n), 3)
     p["round"] = 2
@@ -162,6 +162,21 @@ def test_same_cell_same_round_different_value_last_wins():
     H.phase2a(eng, ora, p[:100])
     H.phase2a(eng, ora, p)
     H.compare_acceptors(eng, ora, cfg, 0, n)
+    eng.close()
+
+
+def test_conflict_cap_is_reported_not_silently_wrong():
+    """More than 1024 same-key/different-value collisions in ONE batch (only a
+    faulty leader produces even one) exceed the in-kernel resolver: the engine
+    must say FPX_ERR_CONFLICT, never return a wrong value (documented limit)."""
+    eng = Engine(1, 1, 3, num_leaders=2, num_replicas=2, slot_capacity=8192, max_batch=1 << 16)
+    n = 4000
+    a = np.zeros(2 * n, dtype=P2A)
+    a["slot"] = np.tile(np.arange(n), 2)
+    a["value_id"] = np.arange(2 * n)
+    with pytest.raises(FpxError) as ei:
+        eng.proxyleader_arm(a)
+    assert ei.value.status == -9
     eng.close()
 
 
