@@ -1,0 +1,392 @@
+#!/usr/bin/env python3
+"""bench.py -- committed slots/sec of the quorum-vote hot path on B200.
+
+Workload (BASELINE.json configs[1], "cfg2"): MultiPaxos, 5 acceptors (f=2),
+thrifty quorum of 3, 2^20 slots in flight per GPU per step.  One STEP is one
+pass of the hot path over one window of 2^20 fresh slots:
+    arm 2^20 (slot, round)  ->  3*2^20 Phase2a at the acceptors (ballot CAS +
+    vote cells + Phase2b stream)  ->  3*2^20 shuffled Phase2b at the proxy leader
+    (tally + quorum check + ordered Chosen stream)  ->  replica log + chosen
+    watermark (+ NCCL all-gather of the per-GPU watermark when N > 1).
+`value` times K steps with every input already resident in HBM (distinct
+buffers per step, > L2 in total, fresh state region per step);
+`e2e` times the same K steps through the host-pointer C ABI from pinned host
+buffers (H2D of every input, D2H of the Phase2b and Chosen replies).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+  python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...
+"""
+import argparse
+import ctypes
+import json
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+SLOTS_PER_STEP = 1 << 20
+CFG = dict(f=2, num_acceptor_groups=1, acceptors_per_group=5, flexible=False, num_leaders=3, num_replicas=3)
+Q = CFG["f"] + 1
+# Algorithmic bytes per committed slot (SURVEY.md 8(d) / DESIGN.md):
+#   acceptor kernel  40*Q  = read 16Q (Phase2a) + write 8Q (vote cell) + write 16Q (Phase2b)
+#   tally kernels    16Q+24 = read 16Q (Phase2b) + 8+8 slot state RMW + write 8 (Chosen)
+B_ACCEPTOR = 40 * Q
+B_TALLY = 16 * Q + 24
+B_SLOT = B_ACCEPTOR + B_TALLY
+N_BASE = 4  # distinct base traces; step s uses base s % N_BASE re-based onto its own slot window
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--cpu-sample-slots", type=int, default=1 << 18)
+    ap.add_argument("--no-e2e", action="store_true")
+    return ap.parse_args()
+
+
+def peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+# --------------------------------------------------------------------------- CPU arms (oracle port)
+def cpu_run(sample_slots, threads):
+    """The reference's path restated on the CPU (oracle/fpx_oracle.cc, std::map /
+    std::set like the Scala collections), `threads` proxy-leader/acceptor
+    partitions by slot % threads (the reference's own scale-out), one pass over a
+    bounded sample of the cfg2 workload.  Returns slots/s."""
+    from frankenpaxos_b200 import traces as T
+    from oracle import fpx_oracle_py as O
+    a, p, b = T.workload(12345, CFG, sample_slots)
+    parts = []
+    for t in range(threads):
+        parts.append((a[a["slot"] % threads == t], p[p["slot"] % threads == t], b[b["slot"] % threads == t]))
+    oras = [O.MultiPaxos(CFG["f"], 1, 5, False, 3, 3) for _ in range(threads)]
+    done = [0] * threads
+
+    def work(t):
+        o, (aa, pp, bb) = oras[t], parts[t]
+        o.arm(aa)
+        st, _, pb, nk = o.acceptor_phase2a(pp)
+        st, _, c = o.proxyleader_phase2b(bb)
+        o.replica_chosen(c)
+        done[t] = len(c)
+
+    t0 = time.perf_counter()
+    if threads == 1:
+        work(0)
+    else:
+        th = [threading.Thread(target=work, args=(t,)) for t in range(threads)]
+        [x.start() for x in th]
+        [x.join() for x in th]
+    dt = time.perf_counter() - t0
+    assert sum(done) == sample_slots
+    return sample_slots / dt, dt
+
+
+def reference_arm(args, rank):
+    """--impl reference: the reference's own CPU path.  The Scala/JVM reference
+    cannot run (no JVM on the box, no offline build), so this is the C++ oracle
+    PORT of the same handlers with the reference's data structures, on all host
+    cores via the reference's own partitioning (slot % P)."""
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    threads = max(1, min(cores, 64))
+    sample = args.cpu_sample_slots
+    vals = []
+    for _ in range(args.warmup if args.warmup < 2 else 1):
+        cpu_run(min(sample, 1 << 15), threads)
+    t_total = 0.0
+    for _ in range(args.steps):
+        v, dt = cpu_run(sample, threads)
+        vals.append(v)
+        t_total += dt
+        if t_total > 120:
+            break
+    value = float(np.mean(vals))
+    line = {
+        "impl": "reference", "metric": "committed slots/sec (simulated) at 1M in-flight slots",
+        "value": value, "unit": "slots/s", "n_gpus": args.gpus, "steps": len(vals), "warmup": args.warmup,
+        "ms_per_step": 1e3 * sample / value, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "int32", "data": "synthetic",
+        "config": {"workload": "cfg2: MultiPaxos f=2, 5 acceptors, thrifty quorum 3, shuffled Phase2b",
+                   "slots_per_step": sample, "note": "each step = a bounded sample of the 2^20-slot window"},
+        "cpu_baseline": {"value": value, "unit": "slots/s", "cores": threads, "kind": "port",
+                         "sample": f"{sample} slots x {len(vals)} passes, slot % {threads} partitions, "
+                                   "C++ oracle port (JVM reference not runnable offline)"},
+        "e2e": {"value": value, "unit": "slots/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+# --------------------------------------------------------------------------- clocks
+class ClockSampler(threading.Thread):
+    """Polls NVML while the timed region runs (it is far shorter than nvidia-smi's
+    sampling period)."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.stop_flag, self.active = index, [], False, False
+        self.max_mhz, self.ok = 0, False
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+            self.ok = True
+        except Exception:
+            self.ok = False
+
+    def run(self):
+        if not self.ok:
+            return
+        nv = self.nv
+        while not self.stop_flag:
+            try:
+                mhz = nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)
+                reasons = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h) \
+                    if hasattr(nv, "nvmlDeviceGetCurrentClocksEventReasons") \
+                    else nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                if self.active:
+                    self.samples.append((mhz, reasons))
+            except Exception:
+                pass
+            time.sleep(0.0005)
+
+    def summary(self):
+        if not self.ok or not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz or None, "reasons": ["unsampled"]}
+        nv = self.nv
+        names = {
+            getattr(nv, "nvmlClocksThrottleReasonHwSlowdown", 0x8): "hw_slowdown",
+            getattr(nv, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40): "hw_thermal_slowdown",
+            getattr(nv, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20): "sw_thermal_slowdown",
+            getattr(nv, "nvmlClocksThrottleReasonSwPowerCap", 0x4): "sw_power_cap",
+            getattr(nv, "nvmlClocksThrottleReasonHwPowerBrakeSlowdown", 0x80): "hw_power_brake",
+        }
+        seen = set()
+        for _, r in self.samples:
+            for bit, nm in names.items():
+                if r & bit:
+                    seen.add(nm)
+        mhz = sorted(m for m, _ in self.samples)
+        return {"sm_mhz": mhz[len(mhz) // 2], "sm_max_mhz": self.max_mhz, "reasons": sorted(seen),
+                "samples": len(mhz)}
+
+
+# --------------------------------------------------------------------------- our arm
+def main():
+    args = parse()
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        reference_arm(args, rank)
+        return
+
+    import torch
+    import torch.distributed as dist
+    from frankenpaxos_b200 import P2A, P2B, CHOSEN, NACK, Engine
+    from frankenpaxos_b200 import traces as T
+
+    if not torch.cuda.is_available():
+        sys.exit("bench.py: no CUDA device; the product has no CPU path")
+    N = world
+    if args.gpus != N and world == 1 and args.gpus > 1:
+        sys.exit("bench.py: launch N>1 with torch.distributed.run (one rank per GPU)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if N > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    K, W = args.steps, max(args.warmup, 3)
+    S = K + W
+    total_windows = S + (0 if args.no_e2e else S)
+    if total_windows * SLOTS_PER_STEP * N >= (1 << 31):
+        sys.exit(f"bench.py: (steps+warmup)*2^20*N must stay below 2^31 slots (int32 slot numbers)")
+    n_slots_local = total_windows * SLOTS_PER_STEP
+    eng = Engine(slot_capacity=n_slots_local * N, max_batch=Q * SLOTS_PER_STEP, overflow_capacity=1 << 10,
+                 device=local_rank, shard_index=rank, shard_count=N, **CFG)
+    ext = torch.cuda.ExternalStream(eng.stream, device=dev)
+
+    # ---- traces: N_BASE distinct seeded base traces on window 0; step s re-bases onto window s
+    base = [T.workload(1000 * rank + b, CFG, SLOTS_PER_STEP) for b in range(N_BASE)]
+
+    def rebase(rec, field, window):
+        out = rec.copy()
+        local = out[field].astype(np.int64) + window * SLOTS_PER_STEP
+        out[field] = (local * N + rank).astype(np.int32)
+        return out
+
+    def step_inputs(window):
+        a, p, b = base[window % N_BASE]
+        return rebase(a, "slot", window), rebase(p, "slot", window), rebase(b, "slot", window)
+
+    def to_dev(rec):
+        t = torch.from_numpy(rec.view(np.int32).reshape(len(rec), -1))
+        return t.to(dev, non_blocking=False)
+
+    d_arm, d_p2a, d_p2b = [], [], []
+    for s in range(S):
+        a, p, b = step_inputs(s)
+        d_arm.append(to_dev(a)); d_p2a.append(to_dev(p)); d_p2b.append(to_dev(b))
+    nrec = Q * SLOTS_PER_STEP
+    d_out_p2b = torch.empty((nrec, 4), dtype=torch.int32, device=dev)
+    d_out_nack = torch.empty((nrec, 2), dtype=torch.int32, device=dev)
+    d_out_chosen = torch.empty((nrec, 2), dtype=torch.int32, device=dev)
+    d_wm = torch.zeros(1, dtype=torch.int32, device=dev)
+    d_wm_all = torch.zeros(N, dtype=torch.int32, device=dev)
+    torch.cuda.synchronize()
+
+    def step(s, ev=None):
+        eng.proxyleader_arm_dev(d_arm[s].data_ptr(), SLOTS_PER_STEP)
+        if ev: ev[0].record(ext)
+        eng.acceptor_phase2a_dev(d_p2a[s].data_ptr(), nrec, d_out_p2b.data_ptr(), d_out_nack.data_ptr())
+        if ev: ev[1].record(ext)
+        eng.proxyleader_phase2b_dev(d_p2b[s].data_ptr(), nrec, d_out_chosen.data_ptr())
+        if ev: ev[2].record(ext)
+        eng.replica_chosen_last_dev(d_out_chosen.data_ptr())
+        eng.chosen_watermark_dev(d_wm.data_ptr())
+        if N > 1:
+            with torch.cuda.stream(ext):
+                dist.all_gather_into_tensor(d_wm_all, d_wm)
+
+    def barrier():
+        if N > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for s in range(W):
+        step(s)
+    r = eng.sync()
+    assert r.n_chosen == SLOTS_PER_STEP and r.n_nack == 0, (r.n_chosen, r.n_nack)
+
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    evs = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(K)]
+    e_begin, e_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    launches0 = eng.launch_count
+    barrier()
+    sampler.active = True
+    e_begin.record(ext)
+    for k in range(K):
+        step(W + k, evs[k])
+    e_end.record(ext)
+    barrier()
+    sampler.active = False
+    launches = eng.launch_count - launches0
+    ms = e_begin.elapsed_time(e_end)
+    r = eng.sync()
+    assert r.status == 0 and r.n_chosen == SLOTS_PER_STEP and r.n_nack == 0
+    exp_wm = (S * SLOTS_PER_STEP) * N + rank
+    assert r.watermark == exp_wm, (r.watermark, exp_wm)
+
+    t = torch.tensor([ms], dtype=torch.float64, device=dev)
+    if N > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_max = float(t.item())
+    value = N * K * SLOTS_PER_STEP / (ms_max * 1e-3)
+
+    acc_ms = float(np.mean([evs[k][0].elapsed_time(evs[k][1]) for k in range(K)]))
+    tally_ms = float(np.mean([evs[k][1].elapsed_time(evs[k][2]) for k in range(K)]))
+    peak, peak_src = peaks()
+    acc_gbs = B_ACCEPTOR * SLOTS_PER_STEP / (acc_ms * 1e-3) / 1e9
+    tally_gbs = B_TALLY * SLOTS_PER_STEP / (tally_ms * 1e-3) / 1e9
+
+    # ---- e2e: host-pointer C ABI, pinned host buffers, copies inside the timed region
+    e2e = None
+    if not args.no_e2e:
+        h_in = []
+        for s in range(S):
+            a, p, b = step_inputs(S + s)
+            h_in.append(tuple(torch.from_numpy(x.view(np.int32).reshape(len(x), -1)).pin_memory() for x in (a, p, b)))
+        h_p2b = torch.empty((nrec, 4), dtype=torch.int32).pin_memory()
+        h_nack = torch.empty((nrec, 2), dtype=torch.int32).pin_memory()
+        h_chosen = torch.empty((nrec, 2), dtype=torch.int32).pin_memory()
+        L = eng._L
+        n1, n2, n3, err = ctypes.c_int32(), ctypes.c_int32(), ctypes.c_int32(), ctypes.c_int64()
+        wm = ctypes.c_int32()
+
+        def e2e_step(s):
+            a, p, b = h_in[s]
+            st = L.fpx_proxyleader_arm(eng.h, a.data_ptr(), SLOTS_PER_STEP, ctypes.byref(err))
+            st |= L.fpx_acceptor_phase2a(eng.h, p.data_ptr(), nrec, h_p2b.data_ptr(), ctypes.byref(n1),
+                                         h_nack.data_ptr(), ctypes.byref(n2), ctypes.byref(err))
+            st |= L.fpx_proxyleader_phase2b(eng.h, b.data_ptr(), nrec, h_chosen.data_ptr(), ctypes.byref(n3),
+                                            ctypes.byref(err))
+            st |= L.fpx_replica_chosen(eng.h, h_chosen.data_ptr(), n3.value, ctypes.byref(err))
+            st |= L.fpx_chosen_watermark(eng.h, ctypes.byref(wm))
+            assert st == 0 and n3.value == SLOTS_PER_STEP and n1.value == nrec, (st, n1.value, n3.value)
+            if N > 1:
+                d_wm.fill_(wm.value)
+                dist.all_gather_into_tensor(d_wm_all, d_wm)
+
+        for s in range(W):
+            e2e_step(s)
+        barrier()
+        t0 = time.perf_counter()
+        for k in range(K):
+            e2e_step(W + k)
+        barrier()
+        dt = time.perf_counter() - t0
+        t = torch.tensor([dt], dtype=torch.float64, device=dev)
+        if N > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e = {"value": N * K * SLOTS_PER_STEP / float(t.item()), "unit": "slots/s",
+               "h2d_bytes_per_step": 16 * SLOTS_PER_STEP + 2 * 16 * nrec + 8 * SLOTS_PER_STEP,
+               "d2h_bytes_per_step": 16 * nrec + 8 * SLOTS_PER_STEP + 4,
+               "ms_per_step": 1e3 * float(t.item()) / K,
+               "api": "fpx_proxyleader_arm + fpx_acceptor_phase2a + fpx_proxyleader_phase2b + "
+                      "fpx_replica_chosen + fpx_chosen_watermark (host pointers, pinned)"}
+    sampler.stop_flag = True
+    clocks = sampler.summary()
+
+    cpu = None
+    if rank == 0 and N == 1:
+        v, dt = cpu_run(args.cpu_sample_slots, 1)
+        cpu = {"value": v, "unit": "slots/s", "cores": 1, "kind": "port",
+               "sample": f"{args.cpu_sample_slots} slots of the cfg2 workload, one pass ({dt:.1f} s), "
+                         "single-threaded C++ oracle port of the Scala handlers (JVM reference not runnable offline)"}
+
+    if rank == 0:
+        line = {
+            "metric": "committed slots/sec (simulated) at 1M in-flight slots",
+            "value": value, "unit": "slots/s", "n_gpus": N, "steps": K, "warmup": W,
+            "ms_per_step": ms_max / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "int32", "data": "synthetic",
+            "config": {"workload": "cfg2: MultiPaxos f=2, 5 acceptors, thrifty quorum 3, 2^20 slots in flight "
+                                   "per GPU per step, Phase2b globally shuffled",
+                       "slots_per_step_per_gpu": SLOTS_PER_STEP, "records_per_step_per_gpu": 2 * nrec + SLOTS_PER_STEP,
+                       "sharding": f"slot % {N}", "l2": "distinct input buffers and a fresh state window every "
+                                                        "step (inputs+state touched per step 196 MB > L2)",
+                       "bytes_per_slot_algorithmic": B_SLOT},
+            "roofline": {"bound": "hbm", "kernel": "acceptor_phase2a_kernel", "achieved": acc_gbs, "peak": peak,
+                         "unit": "GB/s", "frac": acc_gbs / peak, "traffic": None,
+                         "algorithmic_bytes_per_launch": B_ACCEPTOR * SLOTS_PER_STEP, "ms_per_launch": acc_ms,
+                         "peak_source": peak_src},
+            "kernels": {"acceptor_phase2a": {"ms": acc_ms, "GB/s": acc_gbs, "frac": acc_gbs / peak},
+                        "tally_stamp+complete": {"ms": tally_ms, "GB/s": tally_gbs, "frac": tally_gbs / peak},
+                        "whole_step_GB/s": B_SLOT * SLOTS_PER_STEP / (ms_max / K * 1e-3) / 1e9},
+            "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
+        }
+        print(json.dumps(line), flush=True)
+    eng.close()
+    if N > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
