@@ -1,0 +1,320 @@
+// fpx_acceptor.cuh -- K2: Acceptor.handlePhase2a for the interleaved delivery
+// stream of all acceptors of the config.   S/multipaxos/Acceptor.scala:184-220
+//
+//   `round` is ONE scalar per acceptor (:95), so for record i addressed to
+//   acceptor k the handler's test (:192) is
+//        msg.round < max(round_k at batch start, max_{j<i, dst_j==k} msg_j.round)
+//   (rejected messages are below the running max, so including them is
+//   harmless): an exclusive keyed prefix-max in delivery order.
+//
+//   Persistent cooperative kernel, every warp owns a contiguous range:
+//     pass 1  stream the range once, lane k of the warp accumulates the max round
+//             addressed to acceptor k (warp redux; one instruction when the whole
+//             chunk carries one round -- the steady state);
+//     barrier CTA aggregates -> global; every CTA takes the max over the CTAs
+//             before it (+ the acceptors' rounds at batch start) = its carry-in;
+//     pass 2  stream the range again (now an L2 hit): accept test, vote cell,
+//             Phase2b reply, maxVotedSlot.  Replies are written at index i
+//             (dense = correct whenever the batch produces no Nack);
+//     barrier if any Nack was produced (leader change): pass 3 rewrites both
+//             reply streams compacted in delivery order from exact prefix counts.
+//   Vote cell: states(slot) = State(round, value) (:205-208) is one 64-bit
+//   atomicMax of (round+1 : value_id): accepted rounds never decrease in
+//   delivery order, so max == last writer, except "same round, different value"
+//   which is flagged and resolved to last-in-order by the last block.
+#pragma once
+#include "fpx_common.cuh"
+
+namespace fpx {
+
+struct VoteConflict { int32_t dst, slot; };
+
+struct AcceptorParams {
+  Geometry g;
+  const int4* in;
+  int32_t n;
+  int4* out_p2b;
+  int2* out_nack;
+  unsigned long long* votes;       // local_slots * voters cells
+  int32_t* acc_round;              // num_keys
+  int32_t* acc_max_voted;          // num_keys
+  uint32_t* accept_bits;           // ceil(n/32)
+  int32_t* g_agg;                  // [grid][kMaxKeys] per-CTA max round per acceptor
+  uint32_t* g_wacc;                // [grid*kWarps] accepted records per warp range
+  uint32_t bar_base;               // st->barrier when this launch starts
+  uint32_t parity;                 // which nack counter this launch uses
+  DevStatus* st;
+  VoteConflict* conflicts;
+};
+
+constexpr int kAccUnroll = 4;
+
+// decode + validate one Phase2a record; key = global acceptor id or -1
+__device__ __forceinline__ int decode_p2a(const Geometry& g, const int4& rec, int& key, int& loc, int& vix) {
+  key = -1; loc = -1; vix = -1;
+  int grp = rec.w >> 16, acc = rec.w & 0xffff;
+  if (grp < 0 || grp >= g.groups || acc >= g.per_group) return FPX_ERR_BAD_ACCEPTOR;
+  if (rec.y < 0 || rec.y > FPX_MAX_ROUND) return FPX_ERR_ROUND_RANGE;
+  int l = local_slot(g, rec.x);
+  if (l < 0) return FPX_ERR_SLOT_RANGE;
+  int v = voter_index(g, grp, acc, rec.x);
+  if (v < 0) return FPX_ERR_BAD_ACCEPTOR;
+  key = grp * g.per_group + acc; loc = l; vix = v;
+  return 0;
+}
+
+// Pass 2 (kExact = false: effects + dense replies) and pass 3 (kExact = true:
+// compacted replies only).  `run` is lane-indexed: lane k holds acceptor k's
+// round as of the start of the warp's range.
+template <bool kExact>
+__device__ __forceinline__ void acceptor_apply(const AcceptorParams& P, long long wlo, long long whi, int lane,
+                                               int run, uint32_t pos_base, int& mvs, uint32_t& wacc,
+                                               uint32_t& wnack) {
+  const Geometry& g = P.g;
+  const unsigned full = 0xffffffffu;
+  for (long long base = wlo; base < whi; base += 32 * kAccUnroll) {
+    int4 rec[kAccUnroll];
+#pragma unroll
+    for (int u = 0; u < kAccUnroll; ++u) {
+      long long i = base + u * 32 + lane;
+      rec[u] = (i < whi) ? ld_cg(P.in + i) : make_int4(0, -1, 0, -1);
+    }
+#pragma unroll
+    for (int u = 0; u < kAccUnroll; ++u) {
+      const long long i0 = base + u * 32;
+      if (i0 >= whi) break;
+      const long long i = i0 + lane;
+      int key, loc, vix;
+      bool valid = (i < whi) && decode_p2a(g, rec[u], key, loc, vix) == 0;
+      const int r = rec[u].y;
+      int mn = __reduce_min_sync(full, valid ? r : INT_MAX);
+      int mx = __reduce_max_sync(full, valid ? r : INT_MIN);
+      if (mx == INT_MIN) {
+        if (!kExact && lane == 0) P.accept_bits[i0 >> 5] = 0;
+        continue;
+      }
+      int my_run = __shfl_sync(full, run, key & 31);
+      int cur;
+      if (mn == mx) {  // one round in the whole chunk: no in-chunk dependency
+        cur = my_run;
+        unsigned present = __reduce_or_sync(full, valid ? (1u << key) : 0u);
+        if ((present >> lane) & 1u) run = max(run, mx);
+      } else {
+        int pin = INT_MIN, chunk_agg = INT_MIN;
+        unsigned remaining = __ballot_sync(full, valid);
+        while (remaining) {
+          int leader = __ffs(remaining) - 1;
+          int kk = __shfl_sync(full, key, leader);
+          bool mine = valid && key == kk;
+          int incl = warp_incl_scan_max(mine ? r : INT_MIN, lane);
+          int ex = __shfl_up_sync(full, incl, 1);
+          if (lane == 0) ex = INT_MIN;
+          if (mine) pin = ex;
+          int tot = __shfl_sync(full, incl, 31);
+          if (lane == kk) chunk_agg = tot;
+          remaining &= ~__ballot_sync(full, mine);
+        }
+        cur = max(my_run, pin);
+        run = max(run, chunk_agg);
+      }
+      const bool accept = valid && r >= cur;   // Acceptor.scala:192
+      const unsigned b = __ballot_sync(full, accept);
+      const unsigned nb = __ballot_sync(full, valid && !accept);
+      if (!kExact) {
+        if (lane == 0) P.accept_bits[i0 >> 5] = b;
+        if (accept) {
+          // Phase2b(groupIndex, acceptorIndex, slot, round) (:211-219)
+          st_stream(P.out_p2b + i, make_int4(rec[u].w >> 16, rec[u].w & 0xffff, rec[u].x, r));
+          // states(slot) = State(voteRound = round, voteValue) (:205-208)
+          unsigned long long cell = ((unsigned long long)(uint32_t)(r + 1) << 32) | (uint32_t)rec[u].z;
+          unsigned long long old = atomicMax(&P.votes[(size_t)loc * g.voters + vix], cell);
+          if ((old >> 32) == (cell >> 32) && old != cell) {
+            uint32_t cidx = atomicAdd(&P.st->n_conflicts, 1u);
+            if (cidx < (uint32_t)kMaxConflicts) P.conflicts[cidx] = VoteConflict{rec[u].w, rec[u].x};
+          }
+        }
+        // maxVotedSlot = max(maxVotedSlot, slot) (:209), lane kk keeps acceptor kk's
+        unsigned rem = b;
+        while (rem) {
+          int leader = __ffs(rem) - 1;
+          int kk = __shfl_sync(full, key, leader);
+          bool mine = accept && key == kk;
+          int m = __reduce_max_sync(full, mine ? rec[u].x : INT_MIN);
+          if (lane == kk) mvs = max(mvs, m);
+          rem &= ~__ballot_sync(full, mine);
+        }
+      } else {
+        uint32_t before = pos_base + wacc + __popc(b & lanemask_lt());
+        if (accept) {
+          st_stream(P.out_p2b + before, make_int4(rec[u].w >> 16, rec[u].w & 0xffff, rec[u].x, r));
+        } else if (valid) {
+          // Nack(round) to leaders(roundSystem.leader(phase2a.round)) (:197-198)
+          st_stream2(P.out_nack + ((uint32_t)i - before), make_int2(r % g.num_leaders, cur));
+        }
+      }
+      wacc += __popc(b);
+      wnack += __popc(nb);
+    }
+  }
+}
+
+__global__ void __launch_bounds__(kThreads) acceptor_phase2a_kernel(AcceptorParams P) {
+  const Geometry& g = P.g;
+  __shared__ int s_wagg[kWarps][kMaxKeys];
+  __shared__ int s_tmp[kWarps][kMaxKeys];
+  __shared__ int s_mvs[kWarps][kMaxKeys];
+  __shared__ bool s_last;
+  __shared__ int s_win;
+
+  const unsigned full = 0xffffffffu;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int per = warp_range_len(P.n);
+  const long long gw = (long long)blockIdx.x * kWarps + warp;
+  const long long wlo = min((long long)P.n, gw * per);
+  const long long whi = min((long long)P.n, wlo + per);
+  uint32_t* nack_ctr = P.parity ? &P.st->nack_total : &P.st->pad[0];
+  uint32_t* nack_other = P.parity ? &P.st->pad[0] : &P.st->nack_total;
+  if (blockIdx.x == 0 && tid == 0) *nack_other = 0;  // the counter the NEXT launch uses
+
+  // ---- pass 1: per-acceptor max round of the warp's range (lane = acceptor)
+  int wagg = INT_MIN;
+  for (long long base = wlo; base < whi; base += 32 * kAccUnroll) {
+    int4 rec[kAccUnroll];
+#pragma unroll
+    for (int u = 0; u < kAccUnroll; ++u) {
+      long long i = base + u * 32 + lane;
+      rec[u] = (i < whi) ? ld_stream(P.in + i) : make_int4(0, -1, 0, -1);
+    }
+#pragma unroll
+    for (int u = 0; u < kAccUnroll; ++u) {
+      const long long i = base + u * 32 + lane;
+      if (base + u * 32 >= whi) break;
+      int key, loc, vix;
+      bool valid = false;
+      if (i < whi) {
+        int err = decode_p2a(g, rec[u], key, loc, vix);
+        if (err) report_error(P.st, err, i);
+        valid = err == 0;
+      }
+      const int r = rec[u].y;
+      int mn = __reduce_min_sync(full, valid ? r : INT_MAX);
+      int mx = __reduce_max_sync(full, valid ? r : INT_MIN);
+      if (mx == INT_MIN) continue;
+      if (mn == mx) {
+        unsigned present = __reduce_or_sync(full, valid ? (1u << key) : 0u);
+        if ((present >> lane) & 1u) wagg = max(wagg, mx);
+      } else {
+        unsigned remaining = __ballot_sync(full, valid);
+        while (remaining) {
+          int leader = __ffs(remaining) - 1;
+          int kk = __shfl_sync(full, key, leader);
+          bool mine = valid && key == kk;
+          int m = __reduce_max_sync(full, mine ? r : INT_MIN);
+          if (lane == kk) wagg = max(wagg, m);
+          remaining &= ~__ballot_sync(full, mine);
+        }
+      }
+    }
+  }
+  s_wagg[warp][lane] = wagg;
+  __syncthreads();
+  int cta_agg = INT_MIN;
+  if (warp == 0) {
+#pragma unroll
+    for (int w = 0; w < kWarps; ++w) cta_agg = max(cta_agg, s_wagg[w][lane]);
+    __stcg(&P.g_agg[blockIdx.x * kMaxKeys + lane], cta_agg);
+  }
+  grid_barrier(&P.st->barrier, P.bar_base + gridDim.x);
+
+  // ---- carry-in: acceptor rounds at batch start + every CTA before this one
+  {
+    int v = INT_MIN;
+    for (int c = warp; c < (int)blockIdx.x; c += kWarps) v = max(v, __ldcg(&P.g_agg[c * kMaxKeys + lane]));
+    s_tmp[warp][lane] = v;
+  }
+  __syncthreads();
+  int cta_carry = lane < g.num_keys ? __ldcg(&P.acc_round[lane]) : INT_MIN;
+#pragma unroll
+  for (int w = 0; w < kWarps; ++w) cta_carry = max(cta_carry, s_tmp[w][lane]);
+  int run = cta_carry;
+  for (int w = 0; w < warp; ++w) run = max(run, s_wagg[w][lane]);
+
+  // ---- pass 2: decisions + effects, replies at dense positions
+  int mvs = INT_MIN;
+  uint32_t wacc = 0, wnack = 0;
+  acceptor_apply<false>(P, wlo, whi, lane, run, 0u, mvs, wacc, wnack);
+  if (lane == 0) {
+    __stcg(&P.g_wacc[gw], wacc);
+    if (wnack) atomicAdd(nack_ctr, wnack);
+  }
+  s_mvs[warp][lane] = mvs;
+  __syncthreads();
+  if (warp == 0 && lane < g.num_keys) {
+    int m = INT_MIN;
+#pragma unroll
+    for (int w = 0; w < kWarps; ++w) m = max(m, s_mvs[w][lane]);
+    if (m != INT_MIN) atomicMax(&P.acc_max_voted[lane], m);
+  }
+  grid_barrier(&P.st->barrier, P.bar_base + 2 * gridDim.x);
+
+  // round after the batch = max over everything (:204); only now is it safe to
+  // overwrite the batch-start value every CTA read above
+  if (blockIdx.x == gridDim.x - 1 && warp == 0 && lane < g.num_keys) {
+    int tot = cta_carry;
+#pragma unroll
+    for (int w = 0; w < kWarps; ++w) tot = max(tot, s_wagg[w][lane]);
+    P.acc_round[lane] = tot;
+  }
+  const uint32_t total_nacks = __ldcg(nack_ctr);
+  if (total_nacks == 0) {
+    if (blockIdx.x == 0 && tid == 0) { P.st->n_p2b = P.n; P.st->n_nack = 0; }
+  } else {
+    // ---- pass 3 (leader change only): exact, compacted reply streams
+    uint32_t before = 0;
+    for (long long j = lane; j < gw; j += 32) before += __ldcg(&P.g_wacc[j]);
+    before = __reduce_add_sync(full, before);
+    int mvs2 = INT_MIN;
+    uint32_t wacc2 = 0, wnack2 = 0;
+    acceptor_apply<true>(P, wlo, whi, lane, run, before, mvs2, wacc2, wnack2);
+    if (gw == (long long)gridDim.x * kWarps - 1 && lane == 0) {
+      P.st->n_p2b = (int)(before + wacc2);
+      P.st->n_nack = P.n - (int)(before + wacc2);
+    }
+  }
+
+  // ---- last block: same (acceptor, slot, round) voted twice with different
+  // values in one batch -> the later delivery must win (map overwrite, :205)
+  __threadfence();
+  __syncthreads();
+  if (tid == 0) s_last = (atomicAdd(&P.st->ticket, 1u) == gridDim.x - 1);
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  uint32_t nc = *(volatile uint32_t*)&P.st->n_conflicts;
+  if (tid == 0) P.st->ticket = 0;
+  if (nc == 0) return;
+  if (nc > (uint32_t)kMaxConflicts) {
+    if (tid == 0) { report_error(P.st, FPX_ERR_CONFLICT, 0); P.st->n_conflicts = 0; }
+    return;
+  }
+  for (uint32_t cix = 0; cix < nc; ++cix) {
+    int dst = P.conflicts[cix].dst, slot = P.conflicts[cix].slot;
+    if (tid == 0) s_win = -1;
+    __syncthreads();
+    for (int j = tid; j < P.n; j += kThreads) {
+      int4 rr = P.in[j];
+      if (rr.w == dst && rr.x == slot && ((__ldcg(&P.accept_bits[j >> 5]) >> (j & 31)) & 1u)) atomicMax(&s_win, j);
+    }
+    __syncthreads();
+    if (tid == 0 && s_win >= 0) {
+      int4 rr = P.in[s_win];
+      int l = local_slot(g, slot);
+      int v = voter_index(g, dst >> 16, dst & 0xffff, slot);
+      P.votes[(size_t)l * g.voters + v] = ((unsigned long long)(uint32_t)(rr.y + 1) << 32) | (uint32_t)rr.z;
+    }
+    __syncthreads();
+  }
+  if (tid == 0) P.st->n_conflicts = 0;
+}
+
+}  // namespace fpx

@@ -1,0 +1,138 @@
+#pragma once
+#include "fpx_common.cuh"
+
+namespace fpx {
+
+// ===========================================================================
+// K1  ProxyLeader.handlePhase2a  -- "arm"   S/multipaxos/ProxyLeader.scala:175-215
+//   states.get((slot, round)): Some -> ignore (:177-183); None -> Pending(phase2a,
+//   {}) (:213).  One thread per record; the key's header {round_word, value_id}
+//   is claimed with ONE 64-bit CAS.  A second round for a slot whose primary row
+//   is taken goes to the overflow table.  Two arms of one key with DIFFERENT
+//   values inside one batch (never produced by a correct leader) are resolved to
+//   "first in delivery order wins" by the last block (resolve_arm_conflicts).
+// ===========================================================================
+struct ArmConflict { int32_t slot, round; };
+
+struct ArmParams {
+  Geometry g;
+  PLState pl;
+  const int4* in;
+  int32_t n;
+  DevStatus* st;
+  ArmConflict* conflicts;
+  uint32_t* win_bits;  // ceil(n/32): record i created its key's entry
+};
+
+__device__ __forceinline__ void note_arm_conflict(const ArmParams& P, int slot, int round) {
+  uint32_t c = atomicAdd(&P.st->n_conflicts, 1u);
+  if (c < (uint32_t)kMaxConflicts) P.conflicts[c] = ArmConflict{slot, round};
+}
+
+// returns true if this record installed the header
+__device__ __forceinline__ bool claim_header(const ArmParams& P, RowRef r, int slot, int round, int value,
+                                             bool* other_round) {
+  unsigned long long want = ((unsigned long long)(uint32_t)value << 32) | (uint32_t)round;
+  unsigned long long old = atomicCAS(r.hdr64(), kU64Empty, want);
+  *other_round = false;
+  if (old == kU64Empty) return true;
+  uint32_t orw = (uint32_t)old;
+  if ((int)(orw & ~kDoneBit) != round) { *other_round = true; return false; }
+  if ((uint32_t)(old >> 32) != (uint32_t)value) note_arm_conflict(P, slot, round);
+  return false;
+}
+
+__device__ __forceinline__ bool arm_one(const ArmParams& P, const int4& rec, long long i) {
+  const Geometry& g = P.g;
+  int slot = rec.x, round = rec.y, value = rec.z;
+  int local = local_slot(g, slot);
+  if (local < 0) { report_error(P.st, FPX_ERR_SLOT_RANGE, i); return false; }
+  if (round < 0 || round > FPX_MAX_ROUND) { report_error(P.st, FPX_ERR_ROUND_RANGE, i); return false; }
+  RowRef r{P.pl.rows + (size_t)local * g.row_words};
+  bool other;
+  bool won = claim_header(P, r, slot, round, value, &other);
+  if (!other) return won;
+  // secondary round of this slot -> overflow table (SURVEY 8(g) rule 3)
+  if (g.ovf_cap == 0) { report_error(P.st, FPX_ERR_OVERFLOW_FULL, i); return false; }
+  unsigned long long key = ((unsigned long long)(uint32_t)slot << 32) | (uint32_t)round;
+  uint32_t h = (uint32_t)mix64(key) & g.ovf_mask;
+  for (int probe = 0; probe < g.ovf_cap; ++probe) {
+    unsigned long long k = atomicCAS(&P.pl.ovf_keys[h], kU64Empty, key);
+    if (k == kU64Empty || k == key) {
+      RowRef o{P.pl.ovf_rows + (size_t)h * g.row_words};
+      bool dummy;
+      return claim_header(P, o, slot, round, value, &dummy);
+    }
+    h = (h + 1) & g.ovf_mask;
+  }
+  report_error(P.st, FPX_ERR_OVERFLOW_FULL, i);
+  return false;
+}
+
+constexpr int kArmUnroll = 4;
+
+__global__ void __launch_bounds__(256) arm_kernel(ArmParams P) {
+  const Geometry& g = P.g;
+  const int lane = threadIdx.x & 31;
+  const long long total_warps = (long long)gridDim.x * (blockDim.x >> 5);
+  const long long gwarp = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const long long n_chunks = ((long long)P.n + 31) >> 5;
+  // warp-strided 32-record chunks, kArmUnroll independent records in flight per lane
+  for (long long c0 = gwarp * kArmUnroll; c0 < n_chunks; c0 += total_warps * kArmUnroll) {
+    int4 rec[kArmUnroll];
+#pragma unroll
+    for (int u = 0; u < kArmUnroll; ++u) {
+      long long i = (c0 + u) * 32 + lane;
+      rec[u] = (i < P.n) ? ld_stream(P.in + i) : make_int4(0, 0, 0, 0);  // {slot, round, value_id, dst}
+    }
+#pragma unroll
+    for (int u = 0; u < kArmUnroll; ++u) {
+      long long i = (c0 + u) * 32 + lane;
+      if (c0 + u >= n_chunks) break;
+      bool won = (i < P.n) && arm_one(P, rec[u], i);  // created the key's Pending entry (:213)
+      unsigned wb = __ballot_sync(0xffffffffu, won);
+      if (lane == 0) P.win_bits[c0 + u] = wb;
+    }
+  }
+
+  // ---- last block: two arms of one key with different values.  If the key was
+  // created by a record of THIS batch, the lowest-index arm is the one the
+  // reference would have kept (later ones hit `case Some(_)`, :177-183); if it
+  // existed before the batch, the stored value stands.
+  __shared__ bool s_last;
+  __shared__ int s_min, s_any;
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) s_last = (atomicAdd(&P.st->ticket, 1u) == gridDim.x - 1);
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  uint32_t nc = *(volatile uint32_t*)&P.st->n_conflicts;
+  if (threadIdx.x == 0) P.st->ticket = 0;
+  if (nc == 0) return;
+  if (nc > (uint32_t)kMaxConflicts) {
+    if (threadIdx.x == 0) { report_error(P.st, FPX_ERR_CONFLICT, 0); P.st->n_conflicts = 0; }
+    return;
+  }
+  for (uint32_t c = 0; c < nc; ++c) {
+    int slot = P.conflicts[c].slot, round = P.conflicts[c].round;
+    if (threadIdx.x == 0) { s_min = INT_MAX; s_any = 0; }
+    __syncthreads();
+    for (int j = threadIdx.x; j < P.n; j += blockDim.x) {
+      int4 rec = P.in[j];
+      if (rec.x == slot && rec.y == round) {
+        atomicMin(&s_min, j);
+        if ((__ldcg(&P.win_bits[j >> 5]) >> (j & 31)) & 1u) s_any = 1;
+      }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0 && s_any && s_min != INT_MAX) {
+      RowRef r = find_row(g, P.pl, local_slot(g, slot), slot, round);
+      if (r.p != nullptr) r.p[1] = (uint32_t)P.in[s_min].z;
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) P.st->n_conflicts = 0;
+}
+
+}  // namespace fpx

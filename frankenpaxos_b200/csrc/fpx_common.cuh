@@ -1,0 +1,209 @@
+// fpx_common.cuh -- shared layouts and device helpers of the sm_100a kernels.
+//
+// Everything here is integer scatter/gather + order-preserving prefix logic
+// bounded by HBM/L2 bandwidth; there is no GEMM-shaped work, hence no
+// tcgen05/TMEM.  What matters (DESIGN.md "kernels"): one 128-bit load per
+// message record, fully coalesced warp chunks, at most one 32-byte sector per
+// random state access (a proxy-leader row IS one sector for <= 6 voters),
+// warp ballots/shuffles/redux for the in-order logic, and PERSISTENT
+// cooperative kernels (one wave, grid = SMs x resident CTAs) in which every
+// warp owns a contiguous range of the delivery stream: cross-range
+// dependencies are resolved by "reduce, grid barrier, apply" instead of a
+// per-tile look-back chain.
+//
+// Reference semantics each kernel reproduces are cited at the kernel.
+// S/ = shared/src/main/scala/frankenpaxos/ in mwhittaker/frankenpaxos.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/fpx.h"
+
+namespace fpx {
+
+// ---------------------------------------------------------------------------
+// constants / layouts
+// ---------------------------------------------------------------------------
+constexpr uint32_t kUnarmed = 0xffffffffu;      // row.round_word of a never-armed key
+constexpr uint32_t kDoneBit = 0x80000000u;      // row.round_word bit: ProxyLeader `Done`
+constexpr uint32_t kStampEmpty = 0xffffffffu;   // no Phase2b from this voter yet
+constexpr uint64_t kU64Empty = ~0ull;
+constexpr int kThreads = 256;                     // threads per CTA of the range kernels
+constexpr int kWarps = kThreads / 32;
+constexpr int kMaxKeys = FPX_MAX_ACCEPTORS;       // acceptors tracked by the round scan (lane = key)
+constexpr int kMaxConflicts = 1024;
+constexpr int kMaxGrid = 148 * 8;                 // upper bound on CTAs of a cooperative launch
+
+// Device-resident status block (one per engine).
+struct DevStatus {
+  unsigned long long err_word;  // min over errors of (index << 8 | -code); ~0 = none
+  int32_t n_p2b, n_nack, n_chosen, watermark;
+  uint32_t n_conflicts;         // entries in the conflict list of the running call
+  uint32_t ticket;              // last-block-done ticket
+  int32_t wm_local;             // replica: first local index not yet chosen
+  int32_t max_chosen_local;     // replica: largest local index ever chosen
+  int32_t wm_found;             // scratch of the watermark scan
+  uint32_t barrier;             // monotone arrival counter of the grid barriers
+  uint32_t nack_total;          // acceptor kernel: Nacks of the running call
+  uint32_t pad[3];
+};
+
+struct Geometry {
+  int32_t protocol, f, groups, per_group, flexible, num_leaders;
+  int32_t voters;          // acceptors that can vote on one slot (row width)
+  int32_t num_keys;        // total acceptors = groups * per_group
+  int32_t quorum;          // f + 1 (count predicate)
+  int32_t row_words;       // 8 / 16 / 32 uint32 per proxy-leader row
+  int32_t slot_capacity;   // global
+  int32_t local_slots;     // rows held by this shard
+  int32_t shard_index, shard_count;
+  uint32_t ovf_mask;       // overflow_capacity - 1, or 0 with ovf_cap == 0
+  int32_t ovf_cap;
+};
+
+// ---------------------------------------------------------------------------
+// small helpers
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ int4 ld_stream(const int4* p) {
+  // streaming 128-bit load: message records are read exactly once
+  int4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.s32 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+               : "l"(p));
+  return r;
+}
+__device__ __forceinline__ void st_stream(int4* p, int4 v) {
+  asm volatile("st.global.L1::no_allocate.v4.s32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(v.x), "r"(v.y),
+               "r"(v.z), "r"(v.w));
+}
+__device__ __forceinline__ void st_stream2(int2* p, int2 v) {
+  asm volatile("st.global.L1::no_allocate.v2.s32 [%0], {%1,%2};" ::"l"(p), "r"(v.x), "r"(v.y));
+}
+__device__ __forceinline__ unsigned lanemask_lt() {
+  unsigned m;
+  asm("mov.u32 %0, %%lanemask_lt;" : "=r"(m));
+  return m;
+}
+
+__device__ __forceinline__ void report_error(DevStatus* st, int code, long long index) {
+  unsigned long long w = ((unsigned long long)index << 8) | (unsigned long long)(unsigned)(-code);
+  atomicMin(&st->err_word, w);
+}
+
+// global slot -> local row index of this shard, or -1
+__device__ __forceinline__ int local_slot(const Geometry& g, int slot) {
+  if (slot < 0 || slot >= g.slot_capacity) return -1;
+  if (g.shard_count == 1) return slot;
+  if (slot % g.shard_count != g.shard_index) return -1;
+  return slot / g.shard_count;
+}
+
+// (group, acceptor) -> voter index within the slot's row, or -1.
+// non-flexible: the slot's group is slot % numAcceptorGroups
+// (S/multipaxos/ProxyLeader.scala:190); flexible: every (row, col) of the grid
+// (S/multipaxos/ProxyLeader.scala:118-124).
+__device__ __forceinline__ int voter_index(const Geometry& g, int group, int acceptor, int slot) {
+  if (group < 0 || group >= g.groups || acceptor < 0 || acceptor >= g.per_group) return -1;
+  if (g.flexible) return group * g.per_group + acceptor;
+  if (g.protocol == FPX_MULTIPAXOS && group != slot % g.groups) return -1;
+  return acceptor;
+}
+
+// Quorum predicate over a voter bitmask: non-flexible `size >= f+1`
+// (S/multipaxos/ProxyLeader.scala:238-240); flexible Grid.isWriteQuorum, one
+// member of every row (S/quorums/Grid.scala:49).
+__device__ __forceinline__ bool write_quorum(const Geometry& g, uint32_t mask) {
+  if (!g.flexible) return __popc(mask) >= g.quorum;
+  uint32_t rowmask = (1u << g.per_group) - 1u;
+  for (int r = 0; r < g.groups; ++r) {
+    if (((mask >> (r * g.per_group)) & rowmask) == 0) return false;
+  }
+  return true;
+}
+__device__ __forceinline__ bool read_quorum(const Geometry& g, uint32_t mask) {
+  // Grid.isReadQuorum: some row entirely inside (S/quorums/Grid.scala:40)
+  uint32_t rowmask = (1u << g.per_group) - 1u;
+  for (int r = 0; r < g.groups; ++r) {
+    if (((mask >> (r * g.per_group)) & rowmask) == rowmask) return true;
+  }
+  return false;
+}
+
+__device__ __forceinline__ uint64_t mix64(uint64_t x) {
+  x ^= x >> 33; x *= 0xff51afd7ed558ccdull; x ^= x >> 33; x *= 0xc4ceb9fe1a85ec53ull; x ^= x >> 33;
+  return x;
+}
+
+// Proxy-leader row: {u32 round_word; i32 value_id; u32 stamp[voters]; pad}.
+// round_word = kUnarmed | round | kDoneBit.  stamp[v] = global sequence number
+// of the FIRST Phase2b delivery from voter v for this (slot, round).
+struct RowRef {
+  uint32_t* p;
+  __device__ __forceinline__ uint32_t round_word() const { return p[0]; }
+  __device__ __forceinline__ int value_id() const { return (int)p[1]; }
+  __device__ __forceinline__ uint32_t* stamps() const { return p + 2; }
+  __device__ __forceinline__ unsigned long long* hdr64() const { return (unsigned long long*)p; }
+};
+
+struct PLState {
+  uint32_t* rows;               // local_slots * row_words
+  unsigned long long* ovf_keys; // ovf_cap
+  uint32_t* ovf_rows;           // ovf_cap * row_words
+};
+
+// Find the row of key (slot, round): the primary row when its armed round
+// matches, else the overflow table.  Returns p == nullptr when the key was never
+// armed (ProxyLeader.scala:220-225 `case None`).
+__device__ __forceinline__ RowRef find_row(const Geometry& g, const PLState& s, int local, int slot, int round) {
+  RowRef r{s.rows + (size_t)local * g.row_words};
+  uint32_t rw = r.round_word();
+  if (rw != kUnarmed && (int)(rw & ~kDoneBit) == round) return r;
+  if (rw == kUnarmed || g.ovf_cap == 0) return RowRef{nullptr};
+  unsigned long long key = ((unsigned long long)(uint32_t)slot << 32) | (uint32_t)round;
+  uint32_t h = (uint32_t)mix64(key) & g.ovf_mask;
+  for (int probe = 0; probe < g.ovf_cap; ++probe) {
+    unsigned long long k = s.ovf_keys[h];
+    if (k == key) return RowRef{s.ovf_rows + (size_t)h * g.row_words};
+    if (k == kU64Empty) break;
+    h = (h + 1) & g.ovf_mask;
+  }
+  return RowRef{nullptr};
+}
+
+// ---------------------------------------------------------------------------
+// Grid barrier for cooperative (co-resident) launches.  `st->barrier` only ever
+// grows; the host passes the value it will have when every CTA has arrived.
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ void grid_barrier(uint32_t* bar, uint32_t target) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(bar) : "memory");
+    uint32_t v;
+    do {
+      asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(bar) : "memory");
+    } while ((int32_t)(v - target) < 0);
+    __threadfence();
+  }
+  __syncthreads();
+}
+
+// Contiguous range of the delivery stream owned by the calling warp: warp gw of
+// the grid owns [gw*per, (gw+1)*per), per a multiple of 32, so a CTA owns a
+// contiguous range too and ranges are ordered by (blockIdx, warp).
+__device__ __forceinline__ int warp_range_len(int n) {
+  int total_warps = gridDim.x * kWarps;
+  return (((n + total_warps - 1) / total_warps) + 31) & ~31;
+}
+__device__ __forceinline__ int4 ld_cg(const int4* p) { return __ldcg(p); }
+
+__device__ __forceinline__ int warp_incl_scan_max(int v, int lane) {
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    int o = __shfl_up_sync(0xffffffffu, v, d);
+    if (lane >= d) v = max(v, o);
+  }
+  return v;
+}
+
+}  // namespace fpx

@@ -15,7 +15,11 @@
 #include <new>
 #include <string>
 
-#include "fpx_kernels.cuh"
+#include "fpx_acceptor.cuh"
+#include "fpx_arm.cuh"
+#include "fpx_common.cuh"
+#include "fpx_replica_misc.cuh"
+#include "fpx_tally.cuh"
 
 using namespace fpx;
 
@@ -34,8 +38,9 @@ struct fpx_engine {
   DevStatus* st = nullptr;
   // scratch
   uint32_t* bits = nullptr;            // accept / win bitmask, max_batch/32 words
-  unsigned long long* desc_max = nullptr;
-  unsigned long long* desc_cnt = nullptr;
+  int32_t* g_agg = nullptr;            // [kMaxGrid][kMaxKeys] acceptor kernel CTA aggregates
+  uint32_t* g_wacc = nullptr;          // [kMaxGrid*kWarps] accepted per warp range
+  uint32_t* g_ccnt = nullptr;          // [kMaxGrid] Chosen per CTA
   void* conflicts = nullptr;           // kMaxConflicts * 8 bytes
   // staging for host-pointer calls
   void* d_in = nullptr;                // max_batch * 16
@@ -43,12 +48,16 @@ struct fpx_engine {
   void* d_out_b = nullptr;             // max_batch * 8  (nack / chosen)
   DevStatus* h_st = nullptr;           // pinned mirror
   // host bookkeeping
-  uint32_t epoch = 0;
+  uint32_t bar = 0;                    // value of st->barrier when the next launch starts
+  uint32_t parity = 0;                 // nack counter the next acceptor launch uses
+  int grid_acceptor = 0;               // co-resident CTAs of the cooperative kernels
+  int grid_tally = 0;
+  int tally_per_cap = 0;               // max records per warp range (shared-memory buffer)
+  int num_sms = 0;
   uint32_t seq_base = 1;               // Phase2b delivery sequence numbers
   uint32_t rseq_base = 1;              // Chosen delivery sequence numbers
   int32_t last_p2b_n = 0;
   int64_t launches = 0;
-  int max_tiles = 0;
   std::string last_error;
 };
 
@@ -85,6 +94,14 @@ static int validate(const fpx_config* c) {
   return FPX_OK;
 }
 
+static const void* tally_kernel_ptr(int row_words) {
+  switch (row_words) {
+    case 8: return (const void*)tally_kernel<8>;
+    case 16: return (const void*)tally_kernel<16>;
+    default: return (const void*)tally_kernel<32>;
+  }
+}
+
 static int reset_state(fpx_engine* e) {
   const Geometry& g = e->g;
   size_t row_bytes = (size_t)g.local_slots * g.row_words * 4;
@@ -97,8 +114,6 @@ static int reset_state(fpx_engine* e) {
   CK(e, cudaMemsetAsync(e->acc_round, 0xff, kMaxKeys * 4, e->stream));      // round = -1 (Acceptor.scala:95)
   CK(e, cudaMemsetAsync(e->acc_max_voted, 0xff, kMaxKeys * 4, e->stream));  // maxVotedSlot = -1 (:104)
   CK(e, cudaMemsetAsync(e->rlog, 0xff, (size_t)g.local_slots * 8, e->stream));
-  CK(e, cudaMemsetAsync(e->desc_max, 0, (size_t)e->max_tiles * kMaxKeys * 8, e->stream));
-  CK(e, cudaMemsetAsync(e->desc_cnt, 0, (size_t)e->max_tiles * 8, e->stream));
   DevStatus init;
   memset(&init, 0, sizeof(init));
   init.err_word = ~0ull;
@@ -108,7 +123,8 @@ static int reset_state(fpx_engine* e) {
   *e->h_st = init;
   CK(e, cudaMemcpyAsync(e->st, e->h_st, sizeof(DevStatus), cudaMemcpyHostToDevice, e->stream));
   CK(e, cudaStreamSynchronize(e->stream));
-  e->epoch = 0;
+  e->bar = 0;
+  e->parity = 0;
   e->seq_base = 1;
   e->rseq_base = 1;
   e->last_p2b_n = 0;
@@ -168,7 +184,6 @@ int fpx_create(fpx_engine** out, const fpx_config* cfg) {
   if (g.local_slots < 1) g.local_slots = 1;
   g.ovf_cap = cfg->overflow_capacity;
   g.ovf_mask = g.ovf_cap ? (uint32_t)g.ovf_cap - 1u : 0u;
-  e->max_tiles = (cfg->max_batch + kTile - 1) / kTile;
 
   auto fail = [&](int code) { fpx_destroy(e); return code; };
 #define CKC(call)                                                                \
@@ -193,8 +208,25 @@ int fpx_create(fpx_engine** out, const fpx_config* cfg) {
   CKC(cudaMalloc(&e->rlog, (size_t)g.local_slots * 8));
   CKC(cudaMalloc(&e->st, sizeof(DevStatus)));
   CKC(cudaMalloc(&e->bits, (mb / 32 + 2) * 4));
-  CKC(cudaMalloc(&e->desc_max, (size_t)e->max_tiles * kMaxKeys * 8));
-  CKC(cudaMalloc(&e->desc_cnt, (size_t)e->max_tiles * 8));
+  CKC(cudaMalloc(&e->g_agg, (size_t)kMaxGrid * kMaxKeys * 4));
+  CKC(cudaMalloc(&e->g_wacc, (size_t)kMaxGrid * kWarps * 4));
+  CKC(cudaMalloc(&e->g_ccnt, (size_t)kMaxGrid * 4));
+  {
+    // cooperative (co-resident) grids: SMs x resident CTAs per SM
+    cudaDeviceProp prop;
+    CKC(cudaGetDeviceProperties(&prop, cfg->device));
+    if (!prop.cooperativeLaunch) return fail(FPX_ERR_UNSUPPORTED);
+    e->num_sms = prop.multiProcessorCount;
+    int occ = 0;
+    CKC(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, acceptor_phase2a_kernel, kThreads, 0));
+    e->grid_acceptor = std::min(std::max(occ, 1) * e->num_sms, kMaxGrid);
+    const int smem_cap = 56 * 1024;  // Chosen buffer: kWarps * per * 8 bytes
+    e->tally_per_cap = smem_cap / (kWarps * 8);
+    const void* tk = tally_kernel_ptr(g.row_words);
+    CKC(cudaFuncSetAttribute(tk, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_cap));
+    CKC(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, tk, kThreads, smem_cap));
+    e->grid_tally = std::min(std::max(occ, 1) * e->num_sms, kMaxGrid);
+  }
   CKC(cudaMalloc(&e->conflicts, kMaxConflicts * 8));
   CKC(cudaMalloc(&e->d_in, mb * 16));
   CKC(cudaMalloc(&e->d_out_a, mb * 16));
@@ -213,7 +245,7 @@ void fpx_destroy(fpx_engine* e) {
   if (e->stream) cudaStreamSynchronize(e->stream);
   cudaFree(e->rows); cudaFree(e->ovf_keys); cudaFree(e->ovf_rows); cudaFree(e->votes);
   cudaFree(e->acc_round); cudaFree(e->acc_max_voted); cudaFree(e->rlog); cudaFree(e->st);
-  cudaFree(e->bits); cudaFree(e->desc_max); cudaFree(e->desc_cnt); cudaFree(e->conflicts);
+  cudaFree(e->bits); cudaFree(e->g_agg); cudaFree(e->g_wacc); cudaFree(e->g_ccnt); cudaFree(e->conflicts);
   cudaFree(e->d_in); cudaFree(e->d_out_a); cudaFree(e->d_out_b);
   if (e->h_st) cudaFreeHost(e->h_st);
   if (e->stream) cudaStreamDestroy(e->stream);
@@ -247,7 +279,8 @@ int fpx_proxyleader_arm_dev(fpx_engine* e, const fpx_p2a* d_in, int32_t n) {
   P.st = e->st;
   P.conflicts = (ArmConflict*)e->conflicts;
   P.win_bits = e->bits;
-  arm_kernel<<<(n + 255) / 256, 256, 0, e->stream>>>(P);
+  int arm_blocks = std::min((n + 256 * kArmUnroll - 1) / (256 * kArmUnroll), e->num_sms * 8);
+  arm_kernel<<<arm_blocks, 256, 0, e->stream>>>(P);
   e->launches++;
   CK(e, cudaGetLastError());
   return FPX_OK;
@@ -273,13 +306,18 @@ int fpx_acceptor_phase2a_dev(fpx_engine* e, const fpx_p2a* d_in, int32_t n, fpx_
   P.acc_round = e->acc_round;
   P.acc_max_voted = e->acc_max_voted;
   P.accept_bits = e->bits;
-  P.desc_max = e->desc_max;
-  P.desc_cnt = e->desc_cnt;
-  P.epoch = ++e->epoch & 0x3fffffffu;
-  if (P.epoch == 0) P.epoch = e->epoch = 1;
+  P.g_agg = e->g_agg;
+  P.g_wacc = e->g_wacc;
   P.st = e->st;
   P.conflicts = (VoteConflict*)e->conflicts;
-  acceptor_phase2a_kernel<<<(n + kTile - 1) / kTile, kTileThreads, 0, e->stream>>>(P);
+  int grid = std::max(1, std::min(e->grid_acceptor, (n + kThreads - 1) / kThreads));
+  P.bar_base = e->bar;
+  P.parity = e->parity;
+  e->bar += 2u * (uint32_t)grid;
+  e->parity ^= 1u;
+  void* args[] = {&P};
+  CK(e, cudaLaunchCooperativeKernel((const void*)acceptor_phase2a_kernel, dim3(grid), dim3(kThreads), args, 0,
+                                    e->stream));
   e->launches++;
   CK(e, cudaGetLastError());
   return FPX_OK;
@@ -303,26 +341,32 @@ int fpx_proxyleader_phase2b_dev(fpx_engine* e, const fpx_p2b* d_in, int32_t n, f
     e->launches += 2;
     e->seq_base = 1;
   }
-  TallyParams P;
-  P.g = e->g;
-  P.pl = PLState{e->rows, e->ovf_keys, e->ovf_rows};
-  P.in = (const int4*)d_in;
-  P.n = n;
-  P.seq_base = e->seq_base;
-  P.out_chosen = (int2*)d_out;
-  P.desc_cnt = e->desc_cnt;
-  P.epoch = ++e->epoch & 0x3fffffffu;
-  if (P.epoch == 0) P.epoch = e->epoch = 1;
-  P.st = e->st;
-  e->seq_base += (uint32_t)n;
-  tally_stamp_kernel<<<(n + 255) / 256, 256, 0, e->stream>>>(P);
-  int tiles = (n + kTile - 1) / kTile;
-  switch (e->g.row_words) {
-    case 8: tally_complete_kernel<8><<<tiles, kTileThreads, 0, e->stream>>>(P); break;
-    case 16: tally_complete_kernel<16><<<tiles, kTileThreads, 0, e->stream>>>(P); break;
-    default: tally_complete_kernel<32><<<tiles, kTileThreads, 0, e->stream>>>(P); break;
+  const int grid_cap = e->grid_tally;
+  const int max_sub = grid_cap * kWarps * e->tally_per_cap;  // records one launch can buffer
+  const void* tk = tally_kernel_ptr(e->g.row_words);
+  for (int32_t done = 0; done < n;) {
+    int32_t sub = std::min(n - done, max_sub);
+    int grid = std::max(1, std::min(grid_cap, (sub + kThreads - 1) / kThreads));
+    int per = (((sub + grid * kWarps - 1) / (grid * kWarps)) + 31) & ~31;
+    TallyParams P;
+    P.g = e->g;
+    P.pl = PLState{e->rows, e->ovf_keys, e->ovf_rows};
+    P.in = (const int4*)d_in + done;
+    P.n = sub;
+    P.seq_base = e->seq_base;
+    P.out_chosen = (int2*)d_out;
+    P.g_ccnt = e->g_ccnt;
+    P.bar_base = e->bar;
+    P.first = done == 0;
+    P.per = per;
+    P.st = e->st;
+    e->bar += 3u * (uint32_t)grid;
+    e->seq_base += (uint32_t)sub;
+    void* args[] = {&P};
+    CK(e, cudaLaunchCooperativeKernel(tk, dim3(grid), dim3(kThreads), args, (size_t)kWarps * per * 8, e->stream));
+    e->launches++;
+    done += sub;
   }
-  e->launches += 2;
   CK(e, cudaGetLastError());
   return FPX_OK;
 }

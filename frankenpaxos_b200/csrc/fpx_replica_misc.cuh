@@ -1,0 +1,125 @@
+#pragma once
+#include "fpx_common.cuh"
+
+namespace fpx {
+
+// Sequence numbers are 32-bit; before they wrap, every recorded first-delivery
+// stamp is collapsed to 0 ("before everything"): a key that is still pending
+// has fewer old stamps than a quorum, so their relative order can never decide
+// a completing vote again.
+__global__ void renormalize_stamps_kernel(Geometry g, uint32_t* rows, size_t n_rows) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_rows) return;
+  uint32_t* r = rows + i * g.row_words;
+  for (int v = 0; v < g.voters; ++v)
+    if (r[2 + v] != kStampEmpty) r[2 + v] = 0;
+}
+
+// ===========================================================================
+// K5  Replica.handleChosen   S/multipaxos/Replica.scala:572-588
+//   log.get(slot): Some -> redundant, ignore; None -> log.put.  First Chosen in
+//   delivery order wins: 64-bit atomicMin of (seq : value_id).
+// K6  executeLog's prefix rule (:394-402): first hole at or after the watermark.
+// ===========================================================================
+struct ReplicaParams {
+  Geometry g;
+  const int2* in;
+  int32_t n;               // < 0: read the count from st->n_chosen
+  uint32_t seq_base;
+  unsigned long long* rlog;
+  DevStatus* st;
+};
+
+__global__ void __launch_bounds__(256) replica_chosen_kernel(ReplicaParams P) {
+  const Geometry& g = P.g;
+  int n = P.n >= 0 ? P.n : P.st->n_chosen;
+  int mx = INT_MIN;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    int2 rec = P.in[i];
+    int local = local_slot(g, rec.x);
+    if (local < 0) { report_error(P.st, FPX_ERR_SLOT_RANGE, i); continue; }
+    unsigned long long w = ((unsigned long long)(P.seq_base + (uint32_t)i) << 32) | (uint32_t)rec.y;
+    atomicMin(&P.rlog[local], w);
+    mx = max(mx, local);
+  }
+  mx = __reduce_max_sync(0xffffffffu, mx);
+  if ((threadIdx.x & 31) == 0 && mx != INT_MIN) atomicMax(&P.st->max_chosen_local, mx);
+}
+
+__global__ void __launch_bounds__(256) watermark_scan_kernel(Geometry g, const unsigned long long* rlog,
+                                                            DevStatus* st) {
+  int lo = st->wm_local;
+  int hi = min(st->max_chosen_local + 2, g.local_slots);  // one past the last candidate hole
+  for (int i = lo + blockIdx.x * blockDim.x + threadIdx.x; i < hi; i += gridDim.x * blockDim.x) {
+    if (i >= *(volatile int*)&st->wm_found) break;
+    if (rlog[i] == kU64Empty) { atomicMin(&st->wm_found, i); break; }
+  }
+}
+__global__ void watermark_finish_kernel(Geometry g, DevStatus* st, int32_t* d_out) {
+  int hi = min(st->max_chosen_local + 2, g.local_slots);
+  int found = min(st->wm_found, hi);
+  found = max(found, st->wm_local);
+  if (found > g.local_slots) found = g.local_slots;
+  st->wm_local = found;
+  st->wm_found = INT_MAX;
+  int global = found * g.shard_count + g.shard_index;
+  st->watermark = global;
+  if (d_out) *d_out = global;
+}
+__global__ void renormalize_rlog_kernel(unsigned long long* rlog, size_t n) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n && rlog[i] != kU64Empty) rlog[i] &= 0xffffffffull;
+}
+
+// ===========================================================================
+// K7  batched quorum predicates  S/quorums/Grid.scala:35-56,
+//     S/quorums/SimpleMajority.scala:41-55
+// ===========================================================================
+__global__ void quorum_eval_kernel(Geometry g, int which, const uint32_t* masks, int n, uint8_t* out) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  uint32_t m = masks[i];
+  bool foreign = (m >> 31) & 1u;
+  int members = g.flexible ? g.groups * g.per_group : g.per_group;
+  uint32_t member_mask = members >= 31 ? 0x7fffffffu : ((1u << members) - 1u);
+  if (m & ~member_mask & 0x7fffffffu) foreign = true;
+  m &= member_mask;
+  uint8_t r;
+  if (g.flexible) {
+    bool rd = read_quorum(g, m), wr = write_quorum(g, m);
+    r = (which == 0 || which == 2) ? rd : wr;
+  } else {
+    int q = members / 2 + 1;  // SimpleMajority.scala:30
+    r = __popc(m) >= q;
+  }
+  if (foreign && which < 2) r = 2;  // `require(nodes.subsetOf(members))` throws
+  out[i] = r;
+}
+
+// ---- snapshots (Phase1b / parity read-back; not on the hot path)
+__global__ void snapshot_votes_kernel(Geometry g, const unsigned long long* votes, int group, int acceptor,
+                                      int first_slot, int n_slots, int32_t* vote_round, int32_t* vote_value) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_slots) return;
+  int slot = first_slot + i;
+  int l = local_slot(g, slot);
+  int v = l >= 0 ? voter_index(g, group, acceptor, slot) : -1;
+  int vr = -1, vv = -1;
+  if (v >= 0) {
+    unsigned long long c = votes[(size_t)l * g.voters + v];
+    if ((c >> 32) != 0) { vr = (int)(c >> 32) - 1; vv = (int)(uint32_t)c; }
+  }
+  vote_round[i] = vr;
+  vote_value[i] = vv;
+}
+__global__ void snapshot_log_kernel(Geometry g, const unsigned long long* rlog, int first_slot, int n_slots,
+                                    int32_t* value) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_slots) return;
+  int l = local_slot(g, first_slot + i);
+  int v = -1;
+  if (l >= 0 && rlog[l] != kU64Empty) v = (int)(uint32_t)rlog[l];
+  value[i] = v;
+}
+
+}  // namespace fpx

@@ -1,0 +1,219 @@
+// fpx_tally.cuh -- K3: ProxyLeader.handlePhase2b   S/multipaxos/ProxyLeader.scala:217-258
+//
+//   The reference applies votes one at a time: phase2bs((g,a)) = msg (:237,
+//   idempotent per acceptor), then the quorum test (:238-243); the FIRST vote
+//   that makes the test pass sends Chosen (:246-253) and flips the key to Done
+//   (:256); later votes see Done (:227-232).  Which vote completes depends on
+//   delivery order, and the order of Chosen records in the output is the order
+//   of their completing votes.  One persistent cooperative kernel, every warp
+//   owns a contiguous range of the delivery stream, no sort:
+//     phase A  stamp[key][voter] = min(stamp, seq_i)          one RED per record
+//     barrier
+//     phase B  record i is the completing vote of its key iff it is the first
+//              delivery of its voter (stamp == seq_i), the voters with
+//              stamp < seq_i are NOT a quorum, and with voter i they ARE.  The
+//              warp appends its completing records, in order, to its slice of a
+//              shared-memory buffer;
+//     barrier  CTA counts -> global, each CTA sums the CTAs before it
+//     phase C  coalesced copy of the buffered Chosen records to their exact
+//              positions: the output is the Chosen stream in delivery order.
+//   seq_i = seq_base + i is a per-engine running sequence number, so first
+//   deliveries of earlier batches order before this batch.  A proxy-leader row
+//   {round|done, value, stamp[voters]} is ONE 32-byte sector for <= 6 voters.
+#pragma once
+#include "fpx_common.cuh"
+
+namespace fpx {
+
+struct TallyParams {
+  Geometry g;
+  PLState pl;
+  const int4* in;
+  int32_t n;
+  uint32_t seq_base;
+  int2* out_chosen;
+  uint32_t* g_ccnt;        // [grid] Chosen records produced per CTA
+  uint32_t bar_base;
+  int32_t first;           // 1: first launch of a call (output offset 0), else append at st->n_chosen
+  int32_t per;             // records per warp range == shared buffer entries per warp
+  DevStatus* st;
+};
+
+constexpr int kTallyUnroll = 4;  // chunks in flight per warp (phase B: 32 / ROWW)
+
+template <int ROWW>
+__device__ __forceinline__ void load_row(const uint32_t* p, uint32_t (&w)[ROWW]) {
+  const int4* rp = (const int4*)p;
+#pragma unroll
+  for (int q = 0; q < ROWW / 4; ++q) {
+    int4 t = __ldcg(rp + q);
+    w[4 * q] = t.x; w[4 * q + 1] = t.y; w[4 * q + 2] = t.z; w[4 * q + 3] = t.w;
+  }
+}
+
+template <int ROWW>
+__global__ void __launch_bounds__(kThreads) tally_kernel(TallyParams P) {
+  const Geometry& g = P.g;
+  extern __shared__ int2 s_buf[];  // kWarps * P.per Chosen records
+  __shared__ uint32_t s_wcnt[kWarps];
+  __shared__ uint32_t s_woff[kWarps];
+  __shared__ uint32_t s_cta_off;
+
+  const unsigned full = 0xffffffffu;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int per = P.per;
+  const long long gw = (long long)blockIdx.x * kWarps + warp;
+  const long long wlo = min((long long)P.n, gw * per);
+  const long long whi = min((long long)P.n, wlo + per);
+
+  // ---- phase A: first-delivery stamps
+  for (long long base = wlo; base < whi; base += 32 * kTallyUnroll) {
+    int4 rec[kTallyUnroll];
+    uint32_t* row[kTallyUnroll];
+    uint32_t rw[kTallyUnroll];
+#pragma unroll
+    for (int u = 0; u < kTallyUnroll; ++u) {
+      long long i = base + u * 32 + lane;
+      rec[u] = (i < whi) ? ld_stream(P.in + i) : make_int4(-1, -1, -1, -1);  // {group, acceptor, slot, round}
+    }
+#pragma unroll
+    for (int u = 0; u < kTallyUnroll; ++u) {
+      long long i = base + u * 32 + lane;
+      row[u] = nullptr;
+      rw[u] = kUnarmed;
+      if (i < whi) {
+        int local = local_slot(g, rec[u].z);
+        if (local < 0) {
+          report_error(P.st, FPX_ERR_SLOT_RANGE, i);
+        } else {
+          row[u] = P.pl.rows + (size_t)local * g.row_words;
+          rw[u] = __ldcg(row[u]);
+        }
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < kTallyUnroll; ++u) {
+      long long i = base + u * 32 + lane;
+      if (row[u] == nullptr) continue;
+      uint32_t* r = row[u];
+      uint32_t w = rw[u];
+      if (w == kUnarmed || (int)(w & ~kDoneBit) != rec[u].w) {
+        // not the slot's primary round: overflow table, or never armed (:220-225)
+        RowRef rr = find_row(g, P.pl, local_slot(g, rec[u].z), rec[u].z, rec[u].w);
+        if (rr.p == nullptr) { report_error(P.st, FPX_ERR_UNKNOWN_SLOT_ROUND, i); continue; }
+        r = rr.p;
+        w = __ldcg(r);
+      }
+      if (w & kDoneBit) continue;                      // Done before this batch (:227-232)
+      int v = voter_index(g, rec[u].x, rec[u].y, rec[u].z);
+      if (v < 0) continue;                             // judged in phase B (needs Done-ness at i)
+      atomicMin(&r[2 + v], P.seq_base + (uint32_t)i);  // phase2bs((g,a)) = msg (:237)
+    }
+  }
+  grid_barrier(&P.st->barrier, P.bar_base + gridDim.x);
+
+  // ---- phase B: completing votes, buffered in delivery order per warp
+  constexpr int kUB = ROWW == 8 ? 4 : (ROWW == 16 ? 2 : 1);
+  uint32_t wcnt = 0;
+  int2* my_buf = s_buf + (size_t)warp * per;
+  for (long long base = wlo; base < whi; base += 32 * kUB) {
+    int4 rec[kUB];
+#pragma unroll
+    for (int u = 0; u < kUB; ++u) {
+      long long i = base + u * 32 + lane;
+      rec[u] = (i < whi) ? ld_cg(P.in + i) : make_int4(-1, -1, -1, -1);
+    }
+    uint32_t w[kUB][ROWW];
+    uint32_t* row[kUB];
+#pragma unroll
+    for (int u = 0; u < kUB; ++u) {
+      long long i = base + u * 32 + lane;
+      row[u] = nullptr;
+      if (i < whi) {
+        int local = local_slot(g, rec[u].z);
+        if (local >= 0) {
+          row[u] = P.pl.rows + (size_t)local * g.row_words;
+          load_row<ROWW>(row[u], w[u]);
+        }
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < kUB; ++u) {
+      if (base + u * 32 >= whi) break;
+      long long i = base + u * 32 + lane;
+      bool complete = false;
+      int2 out = make_int2(0, 0);
+      if (row[u] != nullptr) {
+        uint32_t* r = row[u];
+        bool ok = true;
+        if (w[u][0] == kUnarmed || (int)(w[u][0] & ~kDoneBit) != rec[u].w) {
+          RowRef rr = find_row(g, P.pl, local_slot(g, rec[u].z), rec[u].z, rec[u].w);
+          ok = rr.p != nullptr;
+          if (ok) { r = rr.p; load_row<ROWW>(r, w[u]); }
+        }
+        if (ok) {
+          const uint32_t seq = P.seq_base + (uint32_t)i;
+          uint32_t before = 0;
+#pragma unroll
+          for (int v = 0; v < ROWW - 2; ++v)
+            if (v < g.voters && w[u][2 + v] < seq) before |= 1u << v;
+          if (!write_quorum(g, before)) {  // key still Pending when vote i is delivered
+            const int v = voter_index(g, rec[u].x, rec[u].y, rec[u].z);
+            if (v < 0) {
+              // Grid.isWriteQuorum `require(xs subsetOf nodes)` (Grid.scala:44-47)
+              report_error(P.st, FPX_ERR_BAD_ACCEPTOR, i);
+            } else {
+              uint32_t mine = 0;
+#pragma unroll
+              for (int q = 0; q < ROWW - 2; ++q)
+                if (q == v) mine = w[u][2 + q];
+              if (mine == seq && write_quorum(g, before | (1u << v))) {
+                complete = true;
+                out = make_int2(rec[u].z, (int)w[u][1]);  // Chosen(slot, pending.phase2a.value) (:249-251)
+                atomicOr(r, kDoneBit);                    // states(slotround) = Done (:256)
+              }
+            }
+          }
+        }
+      }
+      unsigned b = __ballot_sync(full, complete);
+      if (complete) my_buf[wcnt + __popc(b & lanemask_lt())] = out;
+      wcnt += __popc(b);
+    }
+  }
+  if (lane == 0) s_wcnt[warp] = wcnt;
+  __syncthreads();
+  if (tid == 0) {
+    uint32_t run = 0;
+#pragma unroll
+    for (int wv = 0; wv < kWarps; ++wv) { s_woff[wv] = run; run += s_wcnt[wv]; }
+    __stcg(&P.g_ccnt[blockIdx.x], run);
+  }
+  grid_barrier(&P.st->barrier, P.bar_base + 2 * gridDim.x);
+
+  // ---- phase C: exact output positions, coalesced copy-out
+  if (warp == 0) {
+    uint32_t off = 0;
+    for (int c = lane; c < (int)blockIdx.x; c += 32) off += __ldcg(&P.g_ccnt[c]);
+    off = __reduce_add_sync(full, off);
+    uint32_t out_base = P.first ? 0u : (uint32_t)__ldcg(&P.st->n_chosen);
+    if (lane == 0) s_cta_off = out_base + off;
+  }
+  __syncthreads();
+  {
+    const uint32_t dst0 = s_cta_off + s_woff[warp];
+    for (uint32_t j = lane; j < wcnt; j += 32) st_stream2(P.out_chosen + dst0 + j, my_buf[j]);
+  }
+  if (blockIdx.x == gridDim.x - 1) {
+    // every CTA has read the old n_chosen before this one may overwrite it
+    grid_barrier(&P.st->barrier, P.bar_base + 3 * gridDim.x);
+    if (tid == 0) P.st->n_chosen = (int)(s_cta_off + s_woff[kWarps - 1] + s_wcnt[kWarps - 1]);
+  } else {
+    if (tid == 0) {
+      __threadfence();
+      asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(&P.st->barrier) : "memory");
+    }
+  }
+}
+
+}  // namespace fpx
