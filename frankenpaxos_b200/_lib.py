@@ -41,8 +41,8 @@ def lib():
     if _lib is not None:
         return _lib
     path = _build.LIB
-    if not os.path.exists(path):
-        path = _build.build()
+    if not os.path.exists(path) or (_build.stale() and _build.have_nvcc()):
+        path = _build.build(force=True)
     L = C.CDLL(path)
     missing = [s for s in SYMBOLS if not hasattr(L, s)]
     if missing:

@@ -26,6 +26,10 @@ def deps():
     return d
 
 
+def have_nvcc():
+    return os.path.exists(os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc"))
+
+
 def stale():
     if not os.path.exists(LIB):
         return True

@@ -53,8 +53,8 @@ constexpr int kAccUnroll = 4;
 __device__ __forceinline__ int decode_p2a(const Geometry& g, const int4& rec, int& key, int& loc, int& vix) {
   key = -1; loc = -1; vix = -1;
   int grp = rec.w >> 16, acc = rec.w & 0xffff;
-  if (grp < 0 || grp >= g.groups || acc >= g.per_group) return FPX_ERR_BAD_ACCEPTOR;
-  if (rec.y < 0 || rec.y > FPX_MAX_ROUND) return FPX_ERR_ROUND_RANGE;
+  if ((uint32_t)grp >= (uint32_t)g.groups || acc >= g.per_group) return FPX_ERR_BAD_ACCEPTOR;
+  if ((uint32_t)rec.y > (uint32_t)FPX_MAX_ROUND) return FPX_ERR_ROUND_RANGE;
   int l = local_slot(g, rec.x);
   if (l < 0) return FPX_ERR_SLOT_RANGE;
   int v = voter_index(g, grp, acc, rec.x);
@@ -62,30 +62,46 @@ __device__ __forceinline__ int decode_p2a(const Geometry& g, const int4& rec, in
   key = grp * g.per_group + acc; loc = l; vix = v;
   return 0;
 }
+// pass 1 only needs the acceptor id and the round; slot-level validity is judged
+// (and reported) in pass 2
+__device__ __forceinline__ int decode_key(const Geometry& g, const int4& rec) {
+  int grp = rec.w >> 16, acc = rec.w & 0xffff;
+  if ((uint32_t)grp >= (uint32_t)g.groups || acc >= g.per_group) return -1;
+  if ((uint32_t)rec.y > (uint32_t)FPX_MAX_ROUND) return -1;
+  return grp * g.per_group + acc;
+}
+__device__ __noinline__ void acceptor_error(DevStatus* st, int code, int index) { report_error(st, code, index); }
 
 // Pass 2 (kExact = false: effects + dense replies) and pass 3 (kExact = true:
 // compacted replies only).  `run` is lane-indexed: lane k holds acceptor k's
-// round as of the start of the warp's range.
+// round as of the start of the warp's range.  s_mv is a [num_keys][kThreads]
+// table of per-thread private maxima of accepted slots (maxVotedSlot, :209).
 template <bool kExact>
-__device__ __forceinline__ void acceptor_apply(const AcceptorParams& P, long long wlo, long long whi, int lane,
-                                               int run, uint32_t pos_base, int& mvs, uint32_t& wacc,
-                                               uint32_t& wnack) {
+__device__ __forceinline__ void acceptor_apply(const AcceptorParams& P, int wlo, int whi, int lane, int run,
+                                               uint32_t pos_base, int* s_mv, uint32_t& wacc, uint32_t& wnack) {
   const Geometry& g = P.g;
   const unsigned full = 0xffffffffu;
-  for (long long base = wlo; base < whi; base += 32 * kAccUnroll) {
+  for (int base = wlo; base < whi; base += 32 * kAccUnroll) {
     int4 rec[kAccUnroll];
+    unsigned long long cell[kAccUnroll], old[kAccUnroll];
 #pragma unroll
     for (int u = 0; u < kAccUnroll; ++u) {
-      long long i = base + u * 32 + lane;
+      int i = base + u * 32 + lane;
       rec[u] = (i < whi) ? ld_cg(P.in + i) : make_int4(0, -1, 0, -1);
+      cell[u] = 0; old[u] = 0;
     }
 #pragma unroll
     for (int u = 0; u < kAccUnroll; ++u) {
-      const long long i0 = base + u * 32;
+      const int i0 = base + u * 32;
       if (i0 >= whi) break;
-      const long long i = i0 + lane;
+      const int i = i0 + lane;
       int key, loc, vix;
-      bool valid = (i < whi) && decode_p2a(g, rec[u], key, loc, vix) == 0;
+      bool valid = false;
+      if (i < whi) {
+        int err = decode_p2a(g, rec[u], key, loc, vix);
+        if (err && !kExact) acceptor_error(P.st, err, i);
+        valid = err == 0;
+      }
       const int r = rec[u].y;
       int mn = __reduce_min_sync(full, valid ? r : INT_MAX);
       int mx = __reduce_max_sync(full, valid ? r : INT_MIN);
@@ -119,30 +135,18 @@ __device__ __forceinline__ void acceptor_apply(const AcceptorParams& P, long lon
       }
       const bool accept = valid && r >= cur;   // Acceptor.scala:192
       const unsigned b = __ballot_sync(full, accept);
-      const unsigned nb = __ballot_sync(full, valid && !accept);
       if (!kExact) {
         if (lane == 0) P.accept_bits[i0 >> 5] = b;
         if (accept) {
           // Phase2b(groupIndex, acceptorIndex, slot, round) (:211-219)
           st_stream(P.out_p2b + i, make_int4(rec[u].w >> 16, rec[u].w & 0xffff, rec[u].x, r));
           // states(slot) = State(voteRound = round, voteValue) (:205-208)
-          unsigned long long cell = ((unsigned long long)(uint32_t)(r + 1) << 32) | (uint32_t)rec[u].z;
-          unsigned long long old = atomicMax(&P.votes[(size_t)loc * g.voters + vix], cell);
-          if ((old >> 32) == (cell >> 32) && old != cell) {
-            uint32_t cidx = atomicAdd(&P.st->n_conflicts, 1u);
-            if (cidx < (uint32_t)kMaxConflicts) P.conflicts[cidx] = VoteConflict{rec[u].w, rec[u].x};
-          }
+          cell[u] = ((unsigned long long)(uint32_t)(r + 1) << 32) | (uint32_t)rec[u].z;
+          old[u] = atomicMax(&P.votes[(size_t)loc * g.voters + vix], cell[u]);
+          // maxVotedSlot = max(maxVotedSlot, slot) (:209): thread-private column
+          atomicMax(&s_mv[key * kThreads + threadIdx.x], rec[u].x);
         }
-        // maxVotedSlot = max(maxVotedSlot, slot) (:209), lane kk keeps acceptor kk's
-        unsigned rem = b;
-        while (rem) {
-          int leader = __ffs(rem) - 1;
-          int kk = __shfl_sync(full, key, leader);
-          bool mine = accept && key == kk;
-          int m = __reduce_max_sync(full, mine ? rec[u].x : INT_MIN);
-          if (lane == kk) mvs = max(mvs, m);
-          rem &= ~__ballot_sync(full, mine);
-        }
+        wnack += __popc(__ballot_sync(full, valid && !accept));
       } else {
         uint32_t before = pos_base + wacc + __popc(b & lanemask_lt());
         if (accept) {
@@ -153,49 +157,54 @@ __device__ __forceinline__ void acceptor_apply(const AcceptorParams& P, long lon
         }
       }
       wacc += __popc(b);
-      wnack += __popc(nb);
+    }
+    if (!kExact) {
+      // the atomics' return values are only consumed here, after all of the
+      // group's loads/atomics are in flight
+#pragma unroll
+      for (int u = 0; u < kAccUnroll; ++u) {
+        if ((old[u] >> 32) == (cell[u] >> 32) && old[u] != cell[u]) {
+          uint32_t cidx = atomicAdd(&P.st->n_conflicts, 1u);
+          if (cidx < (uint32_t)kMaxConflicts) P.conflicts[cidx] = VoteConflict{rec[u].w, rec[u].x};
+        }
+      }
     }
   }
 }
 
 __global__ void __launch_bounds__(kThreads) acceptor_phase2a_kernel(AcceptorParams P) {
   const Geometry& g = P.g;
+  extern __shared__ int s_mv[];  // [num_keys][kThreads] private maxVotedSlot columns
   __shared__ int s_wagg[kWarps][kMaxKeys];
   __shared__ int s_tmp[kWarps][kMaxKeys];
-  __shared__ int s_mvs[kWarps][kMaxKeys];
   __shared__ bool s_last;
   __shared__ int s_win;
 
   const unsigned full = 0xffffffffu;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int per = warp_range_len(P.n);
-  const long long gw = (long long)blockIdx.x * kWarps + warp;
-  const long long wlo = min((long long)P.n, gw * per);
-  const long long whi = min((long long)P.n, wlo + per);
+  const int gw = blockIdx.x * kWarps + warp;
+  const int wlo = (int)min((long long)P.n, (long long)gw * per);
+  const int whi = (int)min((long long)P.n, (long long)wlo + per);
   uint32_t* nack_ctr = P.parity ? &P.st->nack_total : &P.st->pad[0];
   uint32_t* nack_other = P.parity ? &P.st->pad[0] : &P.st->nack_total;
   if (blockIdx.x == 0 && tid == 0) *nack_other = 0;  // the counter the NEXT launch uses
+  for (int k = 0; k < g.num_keys; ++k) s_mv[k * kThreads + tid] = INT_MIN;
 
   // ---- pass 1: per-acceptor max round of the warp's range (lane = acceptor)
   int wagg = INT_MIN;
-  for (long long base = wlo; base < whi; base += 32 * kAccUnroll) {
+  for (int base = wlo; base < whi; base += 32 * kAccUnroll) {
     int4 rec[kAccUnroll];
 #pragma unroll
     for (int u = 0; u < kAccUnroll; ++u) {
-      long long i = base + u * 32 + lane;
+      int i = base + u * 32 + lane;
       rec[u] = (i < whi) ? ld_stream(P.in + i) : make_int4(0, -1, 0, -1);
     }
 #pragma unroll
     for (int u = 0; u < kAccUnroll; ++u) {
-      const long long i = base + u * 32 + lane;
       if (base + u * 32 >= whi) break;
-      int key, loc, vix;
-      bool valid = false;
-      if (i < whi) {
-        int err = decode_p2a(g, rec[u], key, loc, vix);
-        if (err) report_error(P.st, err, i);
-        valid = err == 0;
-      }
+      const int key = decode_key(g, rec[u]);  // -1 for padding lanes too (round -1)
+      const bool valid = key >= 0;
       const int r = rec[u].y;
       int mn = __reduce_min_sync(full, valid ? r : INT_MAX);
       int mx = __reduce_max_sync(full, valid ? r : INT_MIN);
@@ -240,20 +249,19 @@ __global__ void __launch_bounds__(kThreads) acceptor_phase2a_kernel(AcceptorPara
   for (int w = 0; w < warp; ++w) run = max(run, s_wagg[w][lane]);
 
   // ---- pass 2: decisions + effects, replies at dense positions
-  int mvs = INT_MIN;
   uint32_t wacc = 0, wnack = 0;
-  acceptor_apply<false>(P, wlo, whi, lane, run, 0u, mvs, wacc, wnack);
+  acceptor_apply<false>(P, wlo, whi, lane, run, 0u, s_mv, wacc, wnack);
   if (lane == 0) {
     __stcg(&P.g_wacc[gw], wacc);
     if (wnack) atomicAdd(nack_ctr, wnack);
   }
-  s_mvs[warp][lane] = mvs;
   __syncthreads();
-  if (warp == 0 && lane < g.num_keys) {
+  for (int k = warp; k < g.num_keys; k += kWarps) {
     int m = INT_MIN;
 #pragma unroll
-    for (int w = 0; w < kWarps; ++w) m = max(m, s_mvs[w][lane]);
-    if (m != INT_MIN) atomicMax(&P.acc_max_voted[lane], m);
+    for (int t = lane; t < kThreads; t += 32) m = max(m, s_mv[k * kThreads + t]);
+    m = __reduce_max_sync(full, m);
+    if (lane == 0 && m != INT_MIN) atomicMax(&P.acc_max_voted[k], m);
   }
   grid_barrier(&P.st->barrier, P.bar_base + 2 * gridDim.x);
 
@@ -271,12 +279,11 @@ __global__ void __launch_bounds__(kThreads) acceptor_phase2a_kernel(AcceptorPara
   } else {
     // ---- pass 3 (leader change only): exact, compacted reply streams
     uint32_t before = 0;
-    for (long long j = lane; j < gw; j += 32) before += __ldcg(&P.g_wacc[j]);
+    for (int j = lane; j < gw; j += 32) before += __ldcg(&P.g_wacc[j]);
     before = __reduce_add_sync(full, before);
-    int mvs2 = INT_MIN;
     uint32_t wacc2 = 0, wnack2 = 0;
-    acceptor_apply<true>(P, wlo, whi, lane, run, before, mvs2, wacc2, wnack2);
-    if (gw == (long long)gridDim.x * kWarps - 1 && lane == 0) {
+    acceptor_apply<true>(P, wlo, whi, lane, run, before, s_mv, wacc2, wnack2);
+    if (gw == (int)gridDim.x * kWarps - 1 && lane == 0) {
       P.st->n_p2b = (int)(before + wacc2);
       P.st->n_nack = P.n - (int)(before + wacc2);
     }

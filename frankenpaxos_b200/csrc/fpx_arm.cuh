@@ -42,16 +42,16 @@ __device__ __forceinline__ bool claim_header(const ArmParams& P, RowRef r, int s
   return false;
 }
 
-__device__ __forceinline__ bool arm_one(const ArmParams& P, const int4& rec, long long i) {
+// second stage of one arm: `old` is what the 64-bit CAS on the primary row's
+// header returned.  Returns true if this record created the key's entry.
+__device__ __forceinline__ bool arm_finish(const ArmParams& P, const int4& rec, unsigned long long old, int i) {
   const Geometry& g = P.g;
-  int slot = rec.x, round = rec.y, value = rec.z;
-  int local = local_slot(g, slot);
-  if (local < 0) { report_error(P.st, FPX_ERR_SLOT_RANGE, i); return false; }
-  if (round < 0 || round > FPX_MAX_ROUND) { report_error(P.st, FPX_ERR_ROUND_RANGE, i); return false; }
-  RowRef r{P.pl.rows + (size_t)local * g.row_words};
-  bool other;
-  bool won = claim_header(P, r, slot, round, value, &other);
-  if (!other) return won;
+  const int slot = rec.x, round = rec.y, value = rec.z;
+  if (old == kU64Empty) return true;                       // Pending(phase2a, {}) created (:213)
+  if ((int)((uint32_t)old & ~kDoneBit) == round) {         // `case Some(_)`: ignore (:177-183)
+    if ((uint32_t)(old >> 32) != (uint32_t)value) note_arm_conflict(P, slot, round);
+    return false;
+  }
   // secondary round of this slot -> overflow table (SURVEY 8(g) rule 3)
   if (g.ovf_cap == 0) { report_error(P.st, FPX_ERR_OVERFLOW_FULL, i); return false; }
   unsigned long long key = ((unsigned long long)(uint32_t)slot << 32) | (uint32_t)round;
@@ -74,22 +74,43 @@ constexpr int kArmUnroll = 4;
 __global__ void __launch_bounds__(256) arm_kernel(ArmParams P) {
   const Geometry& g = P.g;
   const int lane = threadIdx.x & 31;
-  const long long total_warps = (long long)gridDim.x * (blockDim.x >> 5);
-  const long long gwarp = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  const long long n_chunks = ((long long)P.n + 31) >> 5;
-  // warp-strided 32-record chunks, kArmUnroll independent records in flight per lane
-  for (long long c0 = gwarp * kArmUnroll; c0 < n_chunks; c0 += total_warps * kArmUnroll) {
+  const int total_warps = gridDim.x * (blockDim.x >> 5);
+  const int gwarp = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int n_chunks = (P.n + 31) >> 5;
+  // warp-strided 32-record chunks; per lane kArmUnroll independent record loads,
+  // then kArmUnroll independent header CASes, are in flight before any is used
+  for (int c0 = gwarp * kArmUnroll; c0 < n_chunks; c0 += total_warps * kArmUnroll) {
     int4 rec[kArmUnroll];
+    unsigned long long old[kArmUnroll];
+    bool ok[kArmUnroll];
 #pragma unroll
     for (int u = 0; u < kArmUnroll; ++u) {
-      long long i = (c0 + u) * 32 + lane;
-      rec[u] = (i < P.n) ? ld_stream(P.in + i) : make_int4(0, 0, 0, 0);  // {slot, round, value_id, dst}
+      int i = (c0 + u) * 32 + lane;
+      rec[u] = (c0 + u < n_chunks && i < P.n) ? ld_stream(P.in + i) : make_int4(-1, 0, 0, 0);  // {slot, round, value_id, dst}
     }
 #pragma unroll
     for (int u = 0; u < kArmUnroll; ++u) {
-      long long i = (c0 + u) * 32 + lane;
+      int i = (c0 + u) * 32 + lane;
+      ok[u] = false;
+      old[u] = 0;
+      if (c0 + u < n_chunks && i < P.n) {
+        int local = local_slot(g, rec[u].x);
+        if (local < 0) {
+          report_error(P.st, FPX_ERR_SLOT_RANGE, i);
+        } else if ((uint32_t)rec[u].y > (uint32_t)FPX_MAX_ROUND) {
+          report_error(P.st, FPX_ERR_ROUND_RANGE, i);
+        } else {
+          ok[u] = true;
+          unsigned long long want = ((unsigned long long)(uint32_t)rec[u].z << 32) | (uint32_t)rec[u].y;
+          old[u] = atomicCAS((unsigned long long*)(P.pl.rows + (size_t)local * g.row_words), kU64Empty, want);
+        }
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < kArmUnroll; ++u) {
       if (c0 + u >= n_chunks) break;
-      bool won = (i < P.n) && arm_one(P, rec[u], i);  // created the key's Pending entry (:213)
+      int i = (c0 + u) * 32 + lane;
+      bool won = ok[u] && arm_finish(P, rec[u], old[u], i);
       unsigned wb = __ballot_sync(0xffffffffu, won);
       if (lane == 0) P.win_bits[c0 + u] = wb;
     }

@@ -59,7 +59,20 @@ struct Geometry {
   int32_t shard_index, shard_count;
   uint32_t ovf_mask;       // overflow_capacity - 1, or 0 with ovf_cap == 0
   int32_t ovf_cap;
+  // Lemire fastmod/fastdiv constants (M = ceil(2^64 / d)) for the two runtime
+  // divisors on the hot path: numAcceptorGroups and shard_count
+  unsigned long long m_groups, m_shards;
 };
+
+// a % d and a / d for 0 <= a < 2^31, 1 <= d < 2^31, M = 2^64 / d + 1
+// (Lemire, Kaser, Kurz: "Faster remainder by direct computation", 2019)
+__device__ __forceinline__ uint32_t fastmod_u32(uint32_t a, unsigned long long M, uint32_t d) {
+  unsigned long long low = M * a;
+  return (uint32_t)__umul64hi(low, d);
+}
+__device__ __forceinline__ uint32_t fastdiv_u32(uint32_t a, unsigned long long M) {
+  return (uint32_t)__umul64hi(M, a);
+}
 
 // ---------------------------------------------------------------------------
 // small helpers
@@ -92,10 +105,11 @@ __device__ __forceinline__ void report_error(DevStatus* st, int code, long long 
 
 // global slot -> local row index of this shard, or -1
 __device__ __forceinline__ int local_slot(const Geometry& g, int slot) {
-  if (slot < 0 || slot >= g.slot_capacity) return -1;
+  if ((uint32_t)slot >= (uint32_t)g.slot_capacity) return -1;
   if (g.shard_count == 1) return slot;
-  if (slot % g.shard_count != g.shard_index) return -1;
-  return slot / g.shard_count;
+  uint32_t q = fastdiv_u32((uint32_t)slot, g.m_shards);
+  if ((int)((uint32_t)slot - q * (uint32_t)g.shard_count) != g.shard_index) return -1;
+  return (int)q;
 }
 
 // (group, acceptor) -> voter index within the slot's row, or -1.
@@ -103,9 +117,11 @@ __device__ __forceinline__ int local_slot(const Geometry& g, int slot) {
 // (S/multipaxos/ProxyLeader.scala:190); flexible: every (row, col) of the grid
 // (S/multipaxos/ProxyLeader.scala:118-124).
 __device__ __forceinline__ int voter_index(const Geometry& g, int group, int acceptor, int slot) {
-  if (group < 0 || group >= g.groups || acceptor < 0 || acceptor >= g.per_group) return -1;
+  if ((uint32_t)group >= (uint32_t)g.groups || (uint32_t)acceptor >= (uint32_t)g.per_group) return -1;
   if (g.flexible) return group * g.per_group + acceptor;
-  if (g.protocol == FPX_MULTIPAXOS && group != slot % g.groups) return -1;
+  if (g.groups > 1 && g.protocol == FPX_MULTIPAXOS &&
+      group != (int)fastmod_u32((uint32_t)slot, g.m_groups, (uint32_t)g.groups))
+    return -1;
   return acceptor;
 }
 

@@ -184,6 +184,8 @@ int fpx_create(fpx_engine** out, const fpx_config* cfg) {
   if (g.local_slots < 1) g.local_slots = 1;
   g.ovf_cap = cfg->overflow_capacity;
   g.ovf_mask = g.ovf_cap ? (uint32_t)g.ovf_cap - 1u : 0u;
+  g.m_groups = ~0ull / (unsigned long long)g.groups + 1ull;
+  g.m_shards = ~0ull / (unsigned long long)g.shard_count + 1ull;
 
   auto fail = [&](int code) { fpx_destroy(e); return code; };
 #define CKC(call)                                                                \
@@ -218,7 +220,8 @@ int fpx_create(fpx_engine** out, const fpx_config* cfg) {
     if (!prop.cooperativeLaunch) return fail(FPX_ERR_UNSUPPORTED);
     e->num_sms = prop.multiProcessorCount;
     int occ = 0;
-    CKC(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, acceptor_phase2a_kernel, kThreads, 0));
+    CKC(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, acceptor_phase2a_kernel, kThreads,
+                                                      (size_t)g.num_keys * kThreads * 4));
     e->grid_acceptor = std::min(std::max(occ, 1) * e->num_sms, kMaxGrid);
     const int smem_cap = 56 * 1024;  // Chosen buffer: kWarps * per * 8 bytes
     e->tally_per_cap = smem_cap / (kWarps * 8);
@@ -316,8 +319,8 @@ int fpx_acceptor_phase2a_dev(fpx_engine* e, const fpx_p2a* d_in, int32_t n, fpx_
   e->bar += 2u * (uint32_t)grid;
   e->parity ^= 1u;
   void* args[] = {&P};
-  CK(e, cudaLaunchCooperativeKernel((const void*)acceptor_phase2a_kernel, dim3(grid), dim3(kThreads), args, 0,
-                                    e->stream));
+  CK(e, cudaLaunchCooperativeKernel((const void*)acceptor_phase2a_kernel, dim3(grid), dim3(kThreads), args,
+                                    (size_t)e->g.num_keys * kThreads * 4, e->stream));
   e->launches++;
   CK(e, cudaGetLastError());
   return FPX_OK;

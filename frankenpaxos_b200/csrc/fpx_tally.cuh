@@ -18,7 +18,10 @@
 //     phase C  coalesced copy of the buffered Chosen records to their exact
 //              positions: the output is the Chosen stream in delivery order.
 //   seq_i = seq_base + i is a per-engine running sequence number, so first
-//   deliveries of earlier batches order before this batch.  A proxy-leader row
+//   deliveries of earlier batches order before this batch.  `Done` (:256) is not
+//   stored: a key is Done at delivery i iff the stamps below seq_i already form
+//   a quorum, which is exactly what phase B evaluates (later votes of a Done key
+//   only add larger stamps, which never change that).  A proxy-leader row
 //   {round|done, value, stamp[voters]} is ONE 32-byte sector for <= 6 voters.
 #pragma once
 #include "fpx_common.cuh"
@@ -41,13 +44,17 @@ struct TallyParams {
 
 constexpr int kTallyUnroll = 4;  // chunks in flight per warp (phase B: 32 / ROWW)
 
+// One proxy-leader row from L2.  A fully divergent warp load costs L1TEX one
+// wavefront per lane PER INSTRUCTION, so the 32-byte row is fetched with a
+// single 256-bit load (LDG.E.256, sm_100+) instead of two 128-bit ones.
 template <int ROWW>
 __device__ __forceinline__ void load_row(const uint32_t* p, uint32_t (&w)[ROWW]) {
-  const int4* rp = (const int4*)p;
 #pragma unroll
-  for (int q = 0; q < ROWW / 4; ++q) {
-    int4 t = __ldcg(rp + q);
-    w[4 * q] = t.x; w[4 * q + 1] = t.y; w[4 * q + 2] = t.z; w[4 * q + 3] = t.w;
+  for (int q = 0; q < ROWW / 8; ++q) {
+    asm volatile("ld.global.cg.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(w[8 * q]), "=r"(w[8 * q + 1]), "=r"(w[8 * q + 2]), "=r"(w[8 * q + 3]),
+                   "=r"(w[8 * q + 4]), "=r"(w[8 * q + 5]), "=r"(w[8 * q + 6]), "=r"(w[8 * q + 7])
+                 : "l"(p + 8 * q));
   }
 }
 
@@ -96,15 +103,13 @@ __global__ void __launch_bounds__(kThreads) tally_kernel(TallyParams P) {
       long long i = base + u * 32 + lane;
       if (row[u] == nullptr) continue;
       uint32_t* r = row[u];
-      uint32_t w = rw[u];
+      const uint32_t w = rw[u];
       if (w == kUnarmed || (int)(w & ~kDoneBit) != rec[u].w) {
         // not the slot's primary round: overflow table, or never armed (:220-225)
         RowRef rr = find_row(g, P.pl, local_slot(g, rec[u].z), rec[u].z, rec[u].w);
         if (rr.p == nullptr) { report_error(P.st, FPX_ERR_UNKNOWN_SLOT_ROUND, i); continue; }
         r = rr.p;
-        w = __ldcg(r);
       }
-      if (w & kDoneBit) continue;                      // Done before this batch (:227-232)
       int v = voter_index(g, rec[u].x, rec[u].y, rec[u].z);
       if (v < 0) continue;                             // judged in phase B (needs Done-ness at i)
       atomicMin(&r[2 + v], P.seq_base + (uint32_t)i);  // phase2bs((g,a)) = msg (:237)
@@ -170,7 +175,6 @@ __global__ void __launch_bounds__(kThreads) tally_kernel(TallyParams P) {
               if (mine == seq && write_quorum(g, before | (1u << v))) {
                 complete = true;
                 out = make_int2(rec[u].z, (int)w[u][1]);  // Chosen(slot, pending.phase2a.value) (:249-251)
-                atomicOr(r, kDoneBit);                    // states(slotround) = Done (:256)
               }
             }
           }
