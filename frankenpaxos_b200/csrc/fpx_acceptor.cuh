@@ -190,15 +190,19 @@ __global__ void __launch_bounds__(kThreads) acceptor_phase2a_kernel(AcceptorPara
   uint32_t* nack_other = P.parity ? &P.st->pad[0] : &P.st->nack_total;
   if (blockIdx.x == 0 && tid == 0) *nack_other = 0;  // the counter the NEXT launch uses
   for (int k = 0; k < g.num_keys; ++k) s_mv[k * kThreads + tid] = INT_MIN;
+  FPX_MARK(P.st->t_acceptor, 0);
 
-  // ---- pass 1: per-acceptor max round of the warp's range (lane = acceptor)
+  // ---- pass 1: per-acceptor max round of the warp's range (lane = acceptor).
+  // The stream is tagged evict_last in L2 so that pass 2 (which also writes
+  // 88 B/record of replies and vote cells through L2) still finds it there.
+  const unsigned long long pol_keep = l2_policy_evict_last();
   int wagg = INT_MIN;
   for (int base = wlo; base < whi; base += 32 * kAccUnroll) {
     int4 rec[kAccUnroll];
 #pragma unroll
     for (int u = 0; u < kAccUnroll; ++u) {
       int i = base + u * 32 + lane;
-      rec[u] = (i < whi) ? ld_stream(P.in + i) : make_int4(0, -1, 0, -1);
+      rec[u] = (i < whi) ? ld_keep(P.in + i, pol_keep) : make_int4(0, -1, 0, -1);
     }
 #pragma unroll
     for (int u = 0; u < kAccUnroll; ++u) {
@@ -233,21 +237,29 @@ __global__ void __launch_bounds__(kThreads) acceptor_phase2a_kernel(AcceptorPara
     for (int w = 0; w < kWarps; ++w) cta_agg = max(cta_agg, s_wagg[w][lane]);
     __stcg(&P.g_agg[blockIdx.x * kMaxKeys + lane], cta_agg);
   }
+  FPX_MARK(P.st->t_acceptor, 1);
   grid_barrier(&P.st->barrier, P.bar_base + gridDim.x);
+  FPX_MARK(P.st->t_acceptor, 2);
 
-  // ---- carry-in: acceptor rounds at batch start + every CTA before this one
-  {
+  // ---- carry-in: acceptor rounds at batch start + every CTA before this one.
+  // thread t covers CTAs t, t+256, ... for every acceptor: all loads independent.
+  for (int k = 0; k < g.num_keys; ++k) {
     int v = INT_MIN;
-    for (int c = warp; c < (int)blockIdx.x; c += kWarps) v = max(v, __ldcg(&P.g_agg[c * kMaxKeys + lane]));
-    s_tmp[warp][lane] = v;
+    for (int c = tid; c < (int)blockIdx.x; c += kThreads) v = max(v, __ldcg(&P.g_agg[c * kMaxKeys + k]));
+    v = __reduce_max_sync(full, v);
+    if (lane == 0) s_tmp[warp][k] = v;
   }
   __syncthreads();
-  int cta_carry = lane < g.num_keys ? __ldcg(&P.acc_round[lane]) : INT_MIN;
+  int cta_carry = INT_MIN;
+  if (lane < g.num_keys) {
+    cta_carry = __ldcg(&P.acc_round[lane]);
 #pragma unroll
-  for (int w = 0; w < kWarps; ++w) cta_carry = max(cta_carry, s_tmp[w][lane]);
+    for (int w = 0; w < kWarps; ++w) cta_carry = max(cta_carry, s_tmp[w][lane]);
+  }
   int run = cta_carry;
   for (int w = 0; w < warp; ++w) run = max(run, s_wagg[w][lane]);
 
+  FPX_MARK(P.st->t_acceptor, 3);
   // ---- pass 2: decisions + effects, replies at dense positions
   uint32_t wacc = 0, wnack = 0;
   acceptor_apply<false>(P, wlo, whi, lane, run, 0u, s_mv, wacc, wnack);
@@ -263,7 +275,9 @@ __global__ void __launch_bounds__(kThreads) acceptor_phase2a_kernel(AcceptorPara
     m = __reduce_max_sync(full, m);
     if (lane == 0 && m != INT_MIN) atomicMax(&P.acc_max_voted[k], m);
   }
+  FPX_MARK(P.st->t_acceptor, 4);
   grid_barrier(&P.st->barrier, P.bar_base + 2 * gridDim.x);
+  FPX_MARK(P.st->t_acceptor, 5);
 
   // round after the batch = max over everything (:204); only now is it safe to
   // overwrite the batch-start value every CTA read above

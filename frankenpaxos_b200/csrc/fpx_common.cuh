@@ -46,7 +46,16 @@ struct DevStatus {
   uint32_t barrier;             // monotone arrival counter of the grid barriers
   uint32_t nack_total;          // acceptor kernel: Nacks of the running call
   uint32_t pad[3];
+  unsigned long long t_acceptor[8];  // %globaltimer at the phase boundaries of CTA 0 (profiling aid)
+  unsigned long long t_tally[8];
 };
+
+__device__ __forceinline__ unsigned long long global_timer_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+#define FPX_MARK(arr, k) do { if (blockIdx.x == 0 && threadIdx.x == 0) (arr)[k] = global_timer_ns(); } while (0)
 
 struct Geometry {
   int32_t protocol, f, groups, per_group, flexible, num_leaders;
@@ -83,6 +92,19 @@ __device__ __forceinline__ int4 ld_stream(const int4* p) {
   asm volatile("ld.global.nc.L1::no_allocate.v4.s32 {%0,%1,%2,%3}, [%4];"
                : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
                : "l"(p));
+  return r;
+}
+// L2 eviction-priority policies (createpolicy + .L2::cache_hint)
+__device__ __forceinline__ unsigned long long l2_policy_evict_last() {
+  unsigned long long pol;
+  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
+__device__ __forceinline__ int4 ld_keep(const int4* p, unsigned long long pol) {
+  int4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v4.s32 {%0,%1,%2,%3}, [%4], %5;"
+               : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+               : "l"(p), "l"(pol));
   return r;
 }
 __device__ __forceinline__ void st_stream(int4* p, int4 v) {

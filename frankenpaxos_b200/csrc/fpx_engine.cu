@@ -262,6 +262,16 @@ int fpx_reset(fpx_engine* e) {
 }
 
 void* fpx_stream(fpx_engine* e) { return e ? (void*)e->stream : nullptr; }
+
+// Undocumented profiling aid (not part of include/fpx.h): phase-boundary
+// timestamps (ns) CTA 0 of the last acceptor / tally launch recorded.
+int fpx_debug_phase_times(fpx_engine* e, unsigned long long* acceptor8, unsigned long long* tally8) {
+  if (!e) return FPX_ERR_INVALID_ARG;
+  CK(e, cudaStreamSynchronize(e->stream));
+  CK(e, cudaMemcpy(acceptor8, e->st->t_acceptor, 64, cudaMemcpyDeviceToHost));
+  CK(e, cudaMemcpy(tally8, e->st->t_tally, 64, cudaMemcpyDeviceToHost));
+  return FPX_OK;
+}
 int64_t fpx_launch_count(const fpx_engine* e) { return e ? e->launches : 0; }
 
 // --------------------------------------------------------------------------- device entry points

@@ -73,7 +73,9 @@ __global__ void __launch_bounds__(kThreads) tally_kernel(TallyParams P) {
   const long long wlo = min((long long)P.n, gw * per);
   const long long whi = min((long long)P.n, wlo + per);
 
-  // ---- phase A: first-delivery stamps
+  // ---- phase A: first-delivery stamps (stream tagged evict_last: phase B re-reads it from L2)
+  const unsigned long long pol_keep = l2_policy_evict_last();
+  FPX_MARK(P.st->t_tally, 0);
   for (long long base = wlo; base < whi; base += 32 * kTallyUnroll) {
     int4 rec[kTallyUnroll];
     uint32_t* row[kTallyUnroll];
@@ -81,7 +83,7 @@ __global__ void __launch_bounds__(kThreads) tally_kernel(TallyParams P) {
 #pragma unroll
     for (int u = 0; u < kTallyUnroll; ++u) {
       long long i = base + u * 32 + lane;
-      rec[u] = (i < whi) ? ld_stream(P.in + i) : make_int4(-1, -1, -1, -1);  // {group, acceptor, slot, round}
+      rec[u] = (i < whi) ? ld_keep(P.in + i, pol_keep) : make_int4(-1, -1, -1, -1);  // {group, acceptor, slot, round}
     }
 #pragma unroll
     for (int u = 0; u < kTallyUnroll; ++u) {
@@ -115,7 +117,9 @@ __global__ void __launch_bounds__(kThreads) tally_kernel(TallyParams P) {
       atomicMin(&r[2 + v], P.seq_base + (uint32_t)i);  // phase2bs((g,a)) = msg (:237)
     }
   }
+  FPX_MARK(P.st->t_tally, 1);
   grid_barrier(&P.st->barrier, P.bar_base + gridDim.x);
+  FPX_MARK(P.st->t_tally, 2);
 
   // ---- phase B: completing votes, buffered in delivery order per warp
   constexpr int kUB = ROWW == 8 ? 4 : (ROWW == 16 ? 2 : 1);
@@ -193,7 +197,9 @@ __global__ void __launch_bounds__(kThreads) tally_kernel(TallyParams P) {
     for (int wv = 0; wv < kWarps; ++wv) { s_woff[wv] = run; run += s_wcnt[wv]; }
     __stcg(&P.g_ccnt[blockIdx.x], run);
   }
+  FPX_MARK(P.st->t_tally, 3);
   grid_barrier(&P.st->barrier, P.bar_base + 2 * gridDim.x);
+  FPX_MARK(P.st->t_tally, 4);
 
   // ---- phase C: exact output positions, coalesced copy-out
   if (warp == 0) {
@@ -208,6 +214,7 @@ __global__ void __launch_bounds__(kThreads) tally_kernel(TallyParams P) {
     const uint32_t dst0 = s_cta_off + s_woff[warp];
     for (uint32_t j = lane; j < wcnt; j += 32) st_stream2(P.out_chosen + dst0 + j, my_buf[j]);
   }
+  FPX_MARK(P.st->t_tally, 5);
   if (blockIdx.x == gridDim.x - 1) {
     // every CTA has read the old n_chosen before this one may overwrite it
     grid_barrier(&P.st->barrier, P.bar_base + 3 * gridDim.x);
