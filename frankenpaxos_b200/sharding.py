@@ -1,0 +1,45 @@
+"""Slot-residue sharding across the GPUs of one box.
+
+Rank g of P owns the slots with slot % P == g -- the reference's own way of
+partitioning a log (`slot % numAcceptorGroups`,
+shared/src/main/scala/frankenpaxos/multipaxos/ProxyLeader.scala:190) -- and runs
+its own engine on them with no data-path collective.  The one exchange a single
+global log needs is the executable prefix: replicas execute in slot order and
+stop at the first hole (multipaxos/Replica.scala:397-402), so every rank
+contributes its first not-yet-chosen GLOBAL slot and the global watermark is the
+minimum.  Pure torch / numpy: runs under gloo on CPU and nccl on GPU.
+"""
+import numpy as np
+
+
+def owner(slot, world):
+    return np.asarray(slot) % world
+
+
+def split(records, world, field="slot"):
+    """Records of each rank, delivery order preserved within a rank."""
+    k = records[field] % world
+    return [records[k == g] for g in range(world)]
+
+
+def local_to_global(local_index, rank, world):
+    return np.asarray(local_index, dtype=np.int64) * world + rank
+
+
+def global_watermark(first_unchosen_global_slot, group=None):
+    """all_gather one integer per rank, return (min over ranks, gathered tensor).
+    `first_unchosen_global_slot` is a 1-element int32 tensor on the rank's device."""
+    import torch
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return int(first_unchosen_global_slot.item()), first_unchosen_global_slot.clone()
+    world = dist.get_world_size(group)
+    out = torch.empty(world, dtype=first_unchosen_global_slot.dtype, device=first_unchosen_global_slot.device)
+    dist.all_gather_into_tensor(out, first_unchosen_global_slot.reshape(1), group=group)
+    return int(out.min().item()), out
+
+
+def merge_chosen_in_slot_order(per_rank_chosen):
+    """A replica's view of the sharded log: Chosen records of all ranks by slot."""
+    allc = np.concatenate(per_rank_chosen)
+    return allc[np.argsort(allc["slot"], kind="stable")]

@@ -60,3 +60,13 @@ def test_config_validation_is_checked_before_device():
         with pytest.raises(FpxError) as ei:
             Engine(**kw)
         assert ei.value.status == -2, kw
+
+
+def test_jni_symbols_exported():
+    """frankenpaxos_b200/csrc/fpx_jni.c: every Native method of INTEGRATION.md is an
+    exported Java_frankenpaxos_gpu_Native_* symbol."""
+    from frankenpaxos_b200 import build
+    L = ctypes.CDLL(build.build())
+    for m in ["create", "destroy", "proxyLeaderArm", "acceptorPhase2a", "proxyLeaderPhase2b", "replicaChosen",
+              "chosenWatermark", "snapshotAcceptor"]:
+        assert hasattr(L, "Java_frankenpaxos_gpu_Native_" + m), m

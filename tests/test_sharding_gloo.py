@@ -1,0 +1,67 @@
+"""world_size-2 gloo test (CPU) of the N>1 host logic: slot-residue split of a
+trace and the all-gathered global chosen watermark, with the CPU oracle standing
+in for the per-rank engines (the GPU engines are exercised by -m gpu tests)."""
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, n_slots, hole, q):
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from frankenpaxos_b200 import sharding as S
+    from frankenpaxos_b200 import traces as T
+    from oracle import fpx_oracle_py as O
+    cfg, _ = T.config_by_name("cfg2")
+    a, p, b = T.workload(5, cfg, n_slots)          # every rank regenerates the same global trace
+    b = b[b["slot"] != hole]                        # slot `hole` never gets its votes
+    mine = lambda recs: S.split(recs, world)[rank]
+    o = O.MultiPaxos(2, 1, 5, False, 3, 3)
+    o.arm(mine(a))
+    o.acceptor_phase2a(mine(p))
+    _, _, c = o.proxyleader_phase2b(mine(b))
+    assert np.all(c["slot"] % world == rank)
+    # local frontier = first local index of this residue class that is not chosen
+    chosen = np.zeros(n_slots // world + 1, dtype=bool)
+    chosen[c["slot"] // world] = True
+    first_hole_local = int(np.argmin(chosen))
+    wm = torch.tensor([int(S.local_to_global(first_hole_local, rank, world))], dtype=torch.int32)
+    g, allw = S.global_watermark(wm)
+    q.put((rank, g, allw.tolist(), len(c)))
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("hole", [777, 1000])
+def test_global_watermark_two_ranks(hole):
+    world, n_slots = 2, 4000
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, n_slots, hole, q)) for r in range(world)]
+    [p.start() for p in procs]
+    res = sorted(q.get(timeout=120) for _ in range(world))
+    [p.join(timeout=60) for p in procs]
+    assert all(p.exitcode == 0 for p in procs)
+    # both ranks agree; the global executable prefix stops exactly at the hole
+    assert res[0][1] == res[1][1] == hole
+    assert sum(r[3] for r in res) == n_slots - 1
+    owner = hole % world
+    assert res[0][2][owner] == hole and res[0][2][1 - owner] >= n_slots
