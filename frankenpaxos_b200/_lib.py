@@ -18,6 +18,8 @@ SYMBOLS = [
     "fpx_proxyleader_arm_dev", "fpx_acceptor_phase2a_dev", "fpx_proxyleader_phase2b_dev",
     "fpx_replica_chosen_dev", "fpx_replica_chosen_last_dev", "fpx_chosen_watermark_dev", "fpx_sync",
     "fpx_stream", "fpx_launch_count",
+    "fpx_epaxos_create", "fpx_epaxos_destroy", "fpx_epaxos_lead", "fpx_epaxos_preaccept", "fpx_epaxos_accept",
+    "fpx_epaxos_preacceptok", "fpx_epaxos_acceptok", "fpx_epaxos_entry", "fpx_depset_union",
 ]
 
 

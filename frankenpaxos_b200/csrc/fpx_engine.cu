@@ -18,6 +18,7 @@
 #include "fpx_acceptor.cuh"
 #include "fpx_arm.cuh"
 #include "fpx_common.cuh"
+#include "fpx_epaxos.cuh"
 #include "fpx_replica_misc.cuh"
 #include "fpx_tally.cuh"
 
@@ -149,6 +150,8 @@ const char* fpx_strerror(int s) {
     case FPX_ERR_CONFLICT: return "too many same-key/different-value conflicts in one batch";
     case FPX_ERR_NO_DEVICE: return "no CUDA device";
     case FPX_ERR_UNSUPPORTED: return "configuration not supported by this engine build";
+    case FPX_ERR_BATCH_ORDER: return "EPaxos batch contract violated: split the batch at err_index";
+    case FPX_ERR_EPAXOS_STATE: return "transitionToPreAcceptPhase on a committed instance / regressing ballot";
     default: return "unknown status";
   }
 }
@@ -598,6 +601,221 @@ int fpx_snapshot_log(fpx_engine* e, int32_t first_slot, int32_t n_slots, int32_t
   CK(e, cudaStreamSynchronize(e->stream));
   cudaFree(d_v);
   return FPX_OK;
+}
+
+}  // extern "C"
+
+// --------------------------------------------------------------------------- EPaxos
+
+struct fpx_epaxos {
+  fpx_epaxos_config cfg;
+  EpGeometry g;
+  EpState s;
+  cudaStream_t stream = nullptr;
+  int32_t* d_in = nullptr;
+  int32_t* d_out = nullptr;
+  DevStatus* h_st = nullptr;
+  uint32_t tag = 1;
+  uint32_t seq_base = 1;
+  std::string last_error;
+};
+
+#define CKE(e, call)                                                             \
+  do {                                                                           \
+    cudaError_t _err = (call);                                                   \
+    if (_err != cudaSuccess) {                                                   \
+      (e)->last_error = std::string(#call) + ": " + cudaGetErrorString(_err);   \
+      fprintf(stderr, "fpx_epaxos: %s\n", (e)->last_error.c_str());            \
+      return FPX_ERR_CUDA;                                                       \
+    }                                                                            \
+  } while (0)
+
+static int ep_finish(fpx_epaxos* e, int64_t* err_index) {
+  CKE(e, cudaMemcpyAsync(e->h_st, e->s.st, sizeof(DevStatus), cudaMemcpyDeviceToHost, e->stream));
+  CKE(e, cudaStreamSynchronize(e->stream));
+  if (err_index) *err_index = -1;
+  if (e->h_st->err_word == ~0ull) return FPX_OK;
+  int status = -(int)(e->h_st->err_word & 0xff);
+  if (err_index) *err_index = (long long)(e->h_st->err_word >> 8);
+  unsigned long long none = ~0ull;
+  CKE(e, cudaMemcpyAsync(&e->s.st->err_word, &none, 8, cudaMemcpyHostToDevice, e->stream));
+  CKE(e, cudaStreamSynchronize(e->stream));
+  return status;
+}
+
+extern "C" {
+
+int fpx_epaxos_create(fpx_epaxos** out, const fpx_epaxos_config* cfg) {
+  if (!out || !cfg || cfg->struct_size != (int32_t)sizeof(fpx_epaxos_config)) return FPX_ERR_INVALID_ARG;
+  *out = nullptr;
+  if (cfg->f < 1) return FPX_ERR_CONFIG;
+  int n = 2 * cfg->f + 1;
+  if (n > kEpMaxN - 1) return FPX_ERR_UNSUPPORTED;
+  if (cfg->replica_index < 0 || cfg->replica_index >= n || cfg->instances_per_replica < 1 || cfg->max_batch < 1)
+    return FPX_ERR_INVALID_ARG;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0 || cfg->device < 0 || cfg->device >= ndev)
+    return FPX_ERR_NO_DEVICE;
+  fpx_epaxos* e = new (std::nothrow) fpx_epaxos();
+  if (!e) return FPX_ERR_INVALID_ARG;
+  e->cfg = *cfg;
+  e->g = EpGeometry{cfg->f, n, cfg->replica_index, n - 1, cfg->f + 1, cfg->instances_per_replica};
+  size_t ninst = (size_t)n * cfg->instances_per_replica;
+  size_t mb = (size_t)cfg->max_batch;
+  auto fail = [&](int code) { fpx_epaxos_destroy(e); return code; };
+#define CKC(call) do { if ((call) != cudaSuccess) return fail(FPX_ERR_CUDA); } while (0)
+  CKC(cudaSetDevice(cfg->device));
+  CKC(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
+  CKC(cudaMalloc(&e->s.cmd, ninst * kEpCmdWords * 4));
+  CKC(cudaMalloc(&e->s.lead, ninst * kEpLeadWords * 4));
+  CKC(cudaMalloc(&e->s.claim, ninst * 8));
+  CKC(cudaMalloc(&e->s.count, ninst * 8));
+  CKC(cudaMalloc(&e->s.largest, 16));
+  CKC(cudaMalloc(&e->s.proc_ballot, mb * 8));
+  CKC(cudaMalloc(&e->s.st, sizeof(DevStatus)));
+  CKC(cudaMalloc(&e->d_in, mb * (6 + 2 * kEpMaxN) * 4));
+  CKC(cudaMalloc(&e->d_out, mb * (4 + kEpMaxN) * 4));
+  CKC(cudaMallocHost(&e->h_st, sizeof(DevStatus)));
+  CKC(cudaMemsetAsync(e->s.cmd, 0, ninst * kEpCmdWords * 4, e->stream));
+  CKC(cudaMemsetAsync(e->s.lead, 0, ninst * kEpLeadWords * 4, e->stream));
+  CKC(cudaMemsetAsync(e->s.claim, 0xff, ninst * 8, e->stream));
+  CKC(cudaMemsetAsync(e->s.count, 0, ninst * 8, e->stream));
+  CKC(cudaMemsetAsync(e->s.largest, 0, 16, e->stream));
+  memset(e->h_st, 0, sizeof(DevStatus));
+  e->h_st->err_word = ~0ull;
+  CKC(cudaMemcpyAsync(e->s.st, e->h_st, sizeof(DevStatus), cudaMemcpyHostToDevice, e->stream));
+  CKC(cudaStreamSynchronize(e->stream));
+#undef CKC
+  *out = e;
+  return FPX_OK;
+}
+
+void fpx_epaxos_destroy(fpx_epaxos* e) {
+  if (!e) return;
+  cudaSetDevice(e->cfg.device);
+  if (e->stream) cudaStreamSynchronize(e->stream);
+  cudaFree(e->s.cmd); cudaFree(e->s.lead); cudaFree(e->s.claim); cudaFree(e->s.count); cudaFree(e->s.largest);
+  cudaFree(e->s.proc_ballot); cudaFree(e->s.st); cudaFree(e->d_in); cudaFree(e->d_out);
+  if (e->h_st) cudaFreeHost(e->h_st);
+  if (e->stream) cudaStreamDestroy(e->stream);
+  delete e;
+}
+
+static int ep_call(fpx_epaxos* e, const int32_t* in, int32_t n_rec, int w_in, int32_t* out, int w_out, int which,
+                   int64_t* err_index) {
+  if (err_index) *err_index = -1;
+  if (!e || n_rec < 0 || n_rec > e->cfg.max_batch || (n_rec > 0 && (!in || (w_out && !out)))) return FPX_ERR_INVALID_ARG;
+  if (n_rec == 0) return FPX_OK;
+  CKE(e, cudaSetDevice(e->cfg.device));
+  CKE(e, cudaMemcpyAsync(e->d_in, in, (size_t)n_rec * w_in * 4, cudaMemcpyHostToDevice, e->stream));
+  EpParams P;
+  P.g = e->g; P.s = e->s; P.in = e->d_in; P.out = e->d_out; P.n_rec = n_rec;
+  P.tag = e->tag++;
+  if (e->tag == 0xffffffffu) e->tag = 1;
+  P.seq_base = e->seq_base;
+  int blocks = (n_rec + 255) / 256;
+  switch (which) {
+    case 0: ep_lead_kernel<<<blocks, 256, 0, e->stream>>>(P); break;
+    case 1:
+    case 2:
+      if (which == 1) ep_acceptor_kernel<false><<<blocks, 256, 0, e->stream>>>(P);
+      else ep_acceptor_kernel<true><<<blocks, 256, 0, e->stream>>>(P);
+      ep_nack_fixup_kernel<<<std::min(n_rec, 1024), 256, 0, e->stream>>>(P, w_out);
+      ep_largest_commit_kernel<<<1, 1, 0, e->stream>>>(e->s);
+      break;
+    case 3:
+      if (e->seq_base > 0xffffffffu - (uint32_t)n_rec - 16u) return FPX_ERR_UNSUPPORTED;
+      e->seq_base += (uint32_t)n_rec;
+      ep_response_stamp_kernel<false><<<blocks, 256, 0, e->stream>>>(P);
+      ep_response_decide_kernel<false><<<blocks, 256, 0, e->stream>>>(P);
+      break;
+    default:
+      if (e->seq_base > 0xffffffffu - (uint32_t)n_rec - 16u) return FPX_ERR_UNSUPPORTED;
+      e->seq_base += (uint32_t)n_rec;
+      ep_response_stamp_kernel<true><<<blocks, 256, 0, e->stream>>>(P);
+      ep_response_decide_kernel<true><<<blocks, 256, 0, e->stream>>>(P);
+      break;
+  }
+  CKE(e, cudaGetLastError());
+  if (w_out) CKE(e, cudaMemcpyAsync(out, e->d_out, (size_t)n_rec * w_out * 4, cudaMemcpyDeviceToHost, e->stream));
+  return ep_finish(e, err_index);
+}
+
+int fpx_epaxos_lead(fpx_epaxos* e, const int32_t* in, int32_t n_rec, int64_t* err_index) {
+  return ep_call(e, in, n_rec, e ? 8 + e->g.n : 0, nullptr, 0, 0, err_index);
+}
+int fpx_epaxos_preaccept(fpx_epaxos* e, const int32_t* in, int32_t n_rec, int32_t* reply, int64_t* err_index) {
+  return ep_call(e, in, n_rec, e ? 6 + 2 * e->g.n : 0, reply, e ? 4 + e->g.n : 0, 1, err_index);
+}
+int fpx_epaxos_accept(fpx_epaxos* e, const int32_t* in, int32_t n_rec, int32_t* reply, int64_t* err_index) {
+  return ep_call(e, in, n_rec, e ? 6 + e->g.n : 0, reply, e ? 4 + e->g.n : 0, 2, err_index);
+}
+int fpx_epaxos_preacceptok(fpx_epaxos* e, const int32_t* in, int32_t n_rec, int32_t* event, int64_t* err_index) {
+  return ep_call(e, in, n_rec, e ? 6 + e->g.n : 0, event, e ? 2 + e->g.n : 0, 3, err_index);
+}
+int fpx_epaxos_acceptok(fpx_epaxos* e, const int32_t* in, int32_t n_rec, int32_t* event, int64_t* err_index) {
+  return ep_call(e, in, n_rec, 6, event, e ? 2 + e->g.n : 0, 4, err_index);
+}
+
+int fpx_epaxos_entry(fpx_epaxos* e, int32_t rep, int32_t num, int32_t* out, int32_t* leader_kind,
+                     int32_t* largest_ballot) {
+  if (!e || !out || rep < 0 || rep >= e->g.n || num < 0 || num >= e->g.per_replica) return FPX_ERR_INVALID_ARG;
+  CKE(e, cudaSetDevice(e->cfg.device));
+  size_t inst = (size_t)num * e->g.n + rep;
+  int32_t row[kEpCmdWords];
+  CKE(e, cudaMemcpyAsync(row, e->s.cmd + inst * kEpCmdWords, sizeof(row), cudaMemcpyDeviceToHost, e->stream));
+  int32_t lk = 0;
+  CKE(e, cudaMemcpyAsync(&lk, e->s.lead + inst * kEpLeadWords, 4, cudaMemcpyDeviceToHost, e->stream));
+  unsigned long long lb = 0;
+  CKE(e, cudaMemcpyAsync(&lb, e->s.largest, 8, cudaMemcpyDeviceToHost, e->stream));
+  CKE(e, cudaStreamSynchronize(e->stream));
+  out[0] = row[C_KIND]; out[1] = row[C_BORD]; out[2] = row[C_BREP]; out[3] = row[C_VBORD]; out[4] = row[C_VBREP];
+  out[5] = row[C_VALUE]; out[6] = row[C_SEQ];
+  if (row[C_KIND] == EK_NONE) { out[1] = out[2] = out[3] = out[4] = -1; }
+  if (row[C_KIND] == EK_COMMITTED) { out[1] = out[2] = out[3] = out[4] = -1; }
+  for (int k = 0; k < e->g.n; ++k) out[7 + k] = row[C_DEPS + k];
+  if (leader_kind) *leader_kind = lk;
+  if (largest_ballot) {
+    largest_ballot[0] = (int)(uint32_t)(lb >> 32) - 1;
+    largest_ballot[1] = (int)(uint32_t)lb - 1;
+  }
+  return FPX_OK;
+}
+
+int fpx_depset_union(int32_t device, const int32_t* watermark, const int32_t* off, const int32_t* values,
+                     int32_t n_sets, const int32_t* group_off, int32_t n_groups, int32_t* out_watermark,
+                     int32_t* out_count, int32_t* out_values) {
+  if (n_sets < 0 || n_groups < 0 || (n_groups > 0 && (!watermark || !off || !group_off || !out_watermark || !out_count)))
+    return FPX_ERR_INVALID_ARG;
+  if (n_groups == 0) return FPX_OK;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0 || device < 0 || device >= ndev) return FPX_ERR_NO_DEVICE;
+  if (cudaSetDevice(device) != cudaSuccess) return FPX_ERR_CUDA;
+  int32_t nv = off[n_sets];
+  if (nv > 0 && (!values || !out_values)) return FPX_ERR_INVALID_ARG;
+  int32_t *d_w = nullptr, *d_off = nullptr, *d_v = nullptr, *d_g = nullptr, *d_ow = nullptr, *d_on = nullptr, *d_ov = nullptr;
+  int rc = FPX_OK;
+#define CKU(call) do { if ((call) != cudaSuccess) { rc = FPX_ERR_CUDA; goto done; } } while (0)
+  CKU(cudaMalloc(&d_w, (size_t)std::max(n_sets, 1) * 4));
+  CKU(cudaMalloc(&d_off, (size_t)(n_sets + 1) * 4));
+  CKU(cudaMalloc(&d_v, (size_t)std::max(nv, 1) * 4));
+  CKU(cudaMalloc(&d_g, (size_t)(n_groups + 1) * 4));
+  CKU(cudaMalloc(&d_ow, (size_t)n_groups * 4));
+  CKU(cudaMalloc(&d_on, (size_t)n_groups * 4));
+  CKU(cudaMalloc(&d_ov, (size_t)std::max(nv, 1) * 4));
+  CKU(cudaMemcpy(d_w, watermark, (size_t)n_sets * 4, cudaMemcpyHostToDevice));
+  CKU(cudaMemcpy(d_off, off, (size_t)(n_sets + 1) * 4, cudaMemcpyHostToDevice));
+  if (nv) CKU(cudaMemcpy(d_v, values, (size_t)nv * 4, cudaMemcpyHostToDevice));
+  CKU(cudaMemcpy(d_g, group_off, (size_t)(n_groups + 1) * 4, cudaMemcpyHostToDevice));
+  depset_union_kernel<<<(n_groups + 127) / 128, 128>>>(d_w, d_off, d_v, d_g, n_groups, d_ow, d_on, d_ov);
+  CKU(cudaGetLastError());
+  CKU(cudaMemcpy(out_watermark, d_ow, (size_t)n_groups * 4, cudaMemcpyDeviceToHost));
+  CKU(cudaMemcpy(out_count, d_on, (size_t)n_groups * 4, cudaMemcpyDeviceToHost));
+  if (nv) CKU(cudaMemcpy(out_values, d_ov, (size_t)nv * 4, cudaMemcpyDeviceToHost));
+#undef CKU
+done:
+  cudaFree(d_w); cudaFree(d_off); cudaFree(d_v); cudaFree(d_g); cudaFree(d_ow); cudaFree(d_on); cudaFree(d_ov);
+  return rc;
 }
 
 }  // extern "C"

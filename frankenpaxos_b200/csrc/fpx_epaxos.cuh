@@ -1,0 +1,414 @@
+// fpx_epaxos.cuh -- EPaxos replica hot path.
+//   S/epaxos/Replica.scala: handlePreAccept :1159-1289, handlePreAcceptOk :1291-1419,
+//   preAcceptingSlowPath :796-813, handleAccept :1421-1512, handleAcceptOk :1514-1565,
+//   transitionToPreAcceptPhase :633-729, transitionToAcceptPhase :732-793, commit :815-829.
+//   S/epaxos/InstancePrefixSet.scala:121-126 -> S/compact/IntPrefixSet.scala:317-351 (dep-set union).
+//
+// One thread per message.  Batch contract (checked on the device, violations are
+// FPX_ERR_BATCH_ORDER with the offending index, never a wrong answer):
+//   E1  PreAccept / Accept / lead batches hold at most one message per instance;
+//   E2  PreAcceptOk / AcceptOk batches hold at most one message per (instance,
+//       replica); a response that REPLACES an earlier one with different content
+//       (`responses(replicaIndex) = ok`, :1340) must be alone for its instance.
+// Under E1/E2 handlers of different messages only interact through (a) the
+// per-instance response count, resolved exactly like the MultiPaxos tally with
+// first-delivery stamps, and (b) `largestBallot`, a running max that is only
+// read when a Nack is built (resolved by a prefix pass over the batch).
+// Dep sets are dense watermark vectors (topKDependencies = 1, Replica.scala:95);
+// their union is the elementwise max (IntPrefixSet.addAll's values-empty branch,
+// IntPrefixSet.scala:320-321).  General sets go through depset_union_kernel.
+#pragma once
+#include "fpx_common.cuh"
+
+namespace fpx {
+
+constexpr int kEpMaxN = 8;          // replicas (n = 2f+1 <= 7)
+constexpr int kEpCmdWords = 16;     // cmdLog row: 8 header + 8 deps
+constexpr int kEpLeadWords = 128;   // leader row
+// cmdLog row words
+enum { C_KIND = 0, C_VALUE, C_BORD, C_BREP, C_VBORD, C_VBREP, C_SEQ, C_PAD, C_DEPS = 8 };
+enum { EK_NONE = 0, EK_NOCOMMAND = 1, EK_PREACCEPTED = 2, EK_ACCEPTED = 3, EK_COMMITTED = 4 };
+// leader row words
+enum { L_KIND = 0, L_VALUE, L_BORD, L_BREP, L_FLAGS, L_ASEQ, L_PAD0, L_PAD1, L_ADEPS = 8, L_ASTAMP = 16, L_RESP = 24 };
+enum { LK_NONE = 0, LK_PREACCEPTING = 1, LK_ACCEPTING = 2 };
+constexpr int kEpRespWords = 10;    // {stamp, seq, deps[8]}
+enum { LF_AVOID = 1, LF_TIMER = 2 };
+enum { REPLY_NONE = 0, REPLY_OK = 1, REPLY_NACK = 2, REPLY_COMMIT = 3 };
+enum { EV_NONE = 0, EV_FAST_COMMIT = 1, EV_SLOW_ACCEPT = 2, EV_TIMER = 3, EV_COMMIT = 4 };
+
+struct EpGeometry {
+  int32_t f, n, index, fast_quorum, slow_quorum;
+  int32_t per_replica;   // instance numbers [0, per_replica)
+};
+
+struct EpState {
+  int32_t* cmd;                    // [n*per_replica][kEpCmdWords]
+  int32_t* lead;                   // [n*per_replica][kEpLeadWords]
+  unsigned long long* claim;       // [n*per_replica]  (~batch_tag : min index) of the running batch
+  unsigned long long* count;       // [n*per_replica]  (batch_tag : #records) of the running batch
+  unsigned long long* largest;     // largestBallot as an order-preserving key
+  unsigned long long* proc_ballot; // [max_batch] ballot key of record i if it "proceeded", else 0
+  DevStatus* st;
+};
+
+// (ordering, replicaIndex) -> key with tuple order (BallotHelpers.scala:11-21); both >= -1
+__device__ __forceinline__ unsigned long long ballot_key(int ord, int rep) {
+  return ((unsigned long long)(uint32_t)(ord + 1) << 32) | (uint32_t)(rep + 1);
+}
+__device__ __forceinline__ void key_ballot(unsigned long long k, int& ord, int& rep) {
+  ord = (int)(uint32_t)(k >> 32) - 1;
+  rep = (int)(uint32_t)k - 1;
+}
+__device__ __forceinline__ long long ep_instance(const EpGeometry& g, int rep, int num) {
+  if ((uint32_t)rep >= (uint32_t)g.n || (uint32_t)num >= (uint32_t)g.per_replica) return -1;
+  return (long long)num * g.n + rep;
+}
+// contract E1/E2: min index of this batch per instance; returns true if another
+// record of this batch already claimed the instance with a smaller/larger index
+__device__ __forceinline__ bool ep_claim(const EpState& s, long long inst, uint32_t tag, int i) {
+  unsigned long long mine = ((unsigned long long)(~tag) << 32) | (uint32_t)i;
+  unsigned long long old = atomicMin(&s.claim[inst], mine);
+  if ((uint32_t)(old >> 32) == ~tag) {
+    report_error(s.st, FPX_ERR_BATCH_ORDER, max((long long)i, (long long)(uint32_t)old));
+    return true;
+  }
+  return false;
+}
+__device__ __forceinline__ uint32_t ep_count(const EpState& s, long long inst, uint32_t tag) {
+  unsigned long long* p = &s.count[inst];
+  unsigned long long old = *p, assumed;
+  do {
+    assumed = old;
+    unsigned long long nw = ((uint32_t)(assumed >> 32) == tag) ? assumed + 1 : (((unsigned long long)tag << 32) | 1u);
+    old = atomicCAS(p, assumed, nw);
+  } while (old != assumed);
+  return 0;
+}
+
+struct EpParams {
+  EpGeometry g;
+  EpState s;
+  const int32_t* in;
+  int32_t* out;
+  int32_t n_rec;
+  uint32_t tag;        // batch tag
+  uint32_t seq_base;   // response stamps
+};
+
+// ---- transitionToPreAcceptPhase (:633-729).  in row: {rep, num, b_ord, b_rep, value, seq, avoid, pad, deps[n]}
+__global__ void ep_lead_kernel(EpParams P) {
+  const EpGeometry& g = P.g;
+  const int W = 8 + g.n;
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= P.n_rec) return;
+  const int32_t* r = P.in + (size_t)i * W;
+  long long inst = ep_instance(g, r[0], r[1]);
+  if (inst < 0) { report_error(P.s.st, FPX_ERR_SLOT_RANGE, i); return; }
+  if (ep_claim(P.s, inst, P.tag, i)) return;
+  int32_t* c = P.s.cmd + inst * kEpCmdWords;
+  unsigned long long b = ballot_key(r[2], r[3]);
+  int kind = c[C_KIND];
+  if (kind == EK_COMMITTED) { report_error(P.s.st, FPX_ERR_EPAXOS_STATE, i); return; }   // logger.fatal :663-667
+  if (kind != EK_NONE) {
+    if (b < ballot_key(c[C_BORD], c[C_BREP])) { report_error(P.s.st, FPX_ERR_EPAXOS_STATE, i); return; }  // checkLe
+    if (kind != EK_NOCOMMAND && b < ballot_key(c[C_VBORD], c[C_VBREP])) { report_error(P.s.st, FPX_ERR_EPAXOS_STATE, i); return; }
+  }
+  c[C_KIND] = EK_PREACCEPTED; c[C_VALUE] = r[4]; c[C_BORD] = r[2]; c[C_BREP] = r[3];
+  c[C_VBORD] = r[2]; c[C_VBREP] = r[3]; c[C_SEQ] = r[5];
+  for (int k = 0; k < g.n; ++k) c[C_DEPS + k] = r[8 + k];                       // :684-693
+  int32_t* l = P.s.lead + inst * kEpLeadWords;
+  l[L_KIND] = LK_PREACCEPTING; l[L_VALUE] = r[4]; l[L_BORD] = r[2]; l[L_BREP] = r[3];
+  l[L_FLAGS] = r[6] ? LF_AVOID : 0;
+  for (int k = 0; k < kEpMaxN; ++k) {
+    l[L_ASTAMP + k] = (int32_t)kStampEmpty;
+    l[L_RESP + k * kEpRespWords] = (int32_t)kStampEmpty;
+  }
+  int32_t* self = l + L_RESP + g.index * kEpRespWords;                          // :716-724 own PreAcceptOk
+  self[0] = 0;
+  self[1] = r[5];
+  for (int k = 0; k < g.n; ++k) self[2 + k] = r[8 + k];
+}
+
+// ---- handlePreAccept (:1159-1289) / handleAccept (:1421-1512)
+// in row preaccept: {rep, num, b_ord, b_rep, value, seq, local_deps[n], msg_deps[n]}
+// in row accept:    {rep, num, b_ord, b_rep, value, seq, deps[n]}
+// out row: {kind, b_ord, b_rep, seq, deps[n]}
+template <bool kAccept>
+__global__ void ep_acceptor_kernel(EpParams P) {
+  const EpGeometry& g = P.g;
+  const int W = kAccept ? 6 + g.n : 6 + 2 * g.n;
+  const int WO = 4 + g.n;
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= P.n_rec) return;
+  const int32_t* r = P.in + (size_t)i * W;
+  int32_t* o = P.out + (size_t)i * WO;
+  P.s.proc_ballot[i] = 0;
+  o[0] = REPLY_NONE; o[1] = -1; o[2] = -1; o[3] = 0;
+  for (int k = 0; k < g.n; ++k) o[4 + k] = 0;
+  long long inst = ep_instance(g, r[0], r[1]);
+  if (inst < 0) { report_error(P.s.st, FPX_ERR_SLOT_RANGE, i); return; }
+  if (ep_claim(P.s, inst, P.tag, i)) return;
+  int32_t* c = P.s.cmd + inst * kEpCmdWords;
+  const unsigned long long b = ballot_key(r[2], r[3]);
+  const int kind = c[C_KIND];
+  if (kind == EK_COMMITTED) {                                   // :1223-1234 / :1466-1477 reply Commit
+    o[0] = REPLY_COMMIT; o[3] = c[C_SEQ];
+    for (int k = 0; k < g.n; ++k) o[4 + k] = c[C_DEPS + k];
+    return;
+  }
+  if (kind != EK_NONE) {
+    if (b < ballot_key(c[C_BORD], c[C_BREP])) {                 // stale ballot: Nack(largestBallot)
+      o[0] = REPLY_NACK;                                         // ballot filled by ep_nack_fixup_kernel
+      return;
+    }
+    unsigned long long vb = ballot_key(c[C_VBORD], c[C_VBREP]);
+    if (!kAccept) {
+      if (kind == EK_PREACCEPTED && b == vb) {                  // :1195-1208 re-send the stored answer
+        o[0] = REPLY_OK; o[1] = r[2]; o[2] = r[3]; o[3] = c[C_SEQ];
+        for (int k = 0; k < g.n; ++k) o[4 + k] = c[C_DEPS + k];
+        return;
+      }
+      if (kind == EK_ACCEPTED && b == vb) { o[1] = r[2]; o[2] = r[3]; return; }  // :1219-1221 drop
+    } else {
+      if (kind == EK_ACCEPTED && b == vb) {                     // :1455-1464 re-send AcceptOk
+        o[0] = REPLY_OK; o[1] = r[2]; o[2] = r[3];
+        return;
+      }
+    }
+  }
+  // yield leadership to a higher ballot (:1240-1244 / :1482-1486)
+  int32_t* l = P.s.lead + inst * kEpLeadWords;
+  if (l[L_KIND] != LK_NONE && b > ballot_key(l[L_BORD], l[L_BREP])) l[L_KIND] = LK_NONE;
+  P.s.proc_ballot[i] = b;                                       // largestBallot = max(..) (:1246 / :1489)
+  atomicMax(P.s.largest + 1, b);
+  int seq = r[5];
+  o[0] = REPLY_OK; o[1] = r[2]; o[2] = r[3];
+  if (!kAccept) {
+    seq = max(0, seq);                                          // :1256 (local sequence number is 0, :599)
+    for (int k = 0; k < g.n; ++k) {
+      int d = max(r[6 + k], r[6 + g.n + k]);                    // deps.addAll(msg.deps) (:1257), dense
+      c[C_DEPS + k] = d;
+      o[4 + k] = d;
+    }
+    o[3] = seq;
+    c[C_KIND] = EK_PREACCEPTED;
+  } else {
+    for (int k = 0; k < g.n; ++k) c[C_DEPS + k] = r[6 + k];
+    c[C_KIND] = EK_ACCEPTED;
+  }
+  c[C_VALUE] = r[4]; c[C_BORD] = r[2]; c[C_BREP] = r[3]; c[C_VBORD] = r[2]; c[C_VBREP] = r[3]; c[C_SEQ] = seq;
+}
+
+// Nack(instance, largestBallot) carries largestBallot AS OF that delivery (:1166-1167):
+// the max over the handle's value at batch start and the ballots of the records
+// that proceeded before it.  One CTA per 256 records; each Nack scans its prefix.
+__global__ void ep_nack_fixup_kernel(EpParams P, int WO) {
+  __shared__ unsigned long long s_red[256];
+  const unsigned long long start = P.s.largest[0];
+  for (int i = blockIdx.x; i < P.n_rec; i += gridDim.x) {
+    int32_t* o = P.out + (size_t)i * WO;
+    if (o[0] != REPLY_NACK) continue;                           // uniform per block
+    unsigned long long m = start;
+    for (int j = threadIdx.x; j < i; j += blockDim.x) m = max(m, P.s.proc_ballot[j]);
+    s_red[threadIdx.x] = m;
+    __syncthreads();
+    for (int d = 128; d > 0; d >>= 1) {
+      if ((int)threadIdx.x < d) s_red[threadIdx.x] = max(s_red[threadIdx.x], s_red[threadIdx.x + d]);
+      __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+      int ord, rep;
+      key_ballot(s_red[0], ord, rep);
+      o[1] = ord; o[2] = rep;
+    }
+    __syncthreads();
+  }
+}
+__global__ void ep_largest_commit_kernel(EpState s) {
+  // largest[1] accumulated this batch's proceeding ballots; fold into largest[0]
+  s.largest[0] = max(s.largest[0], s.largest[1]);
+  s.largest[1] = 0;
+}
+
+// ---- handlePreAcceptOk (:1291-1419) / handleAcceptOk (:1514-1565), stamp pass
+// in row preacceptok: {rep, num, b_ord, b_rep, from, seq, deps[n]};  acceptok: {rep, num, b_ord, b_rep, from, pad}
+// scratch out row word 0: 0 inactive, 1 first delivery of its replica, 2 replacing response
+template <bool kAccept>
+__global__ void ep_response_stamp_kernel(EpParams P) {
+  const EpGeometry& g = P.g;
+  const int W = kAccept ? 6 : 6 + g.n;
+  const int WO = 2 + g.n;
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= P.n_rec) return;
+  const int32_t* r = P.in + (size_t)i * W;
+  int32_t* o = P.out + (size_t)i * WO;
+  o[0] = 0; o[1] = 0;
+  for (int k = 0; k < g.n; ++k) o[2 + k] = 0;
+  long long inst = ep_instance(g, r[0], r[1]);
+  if (inst < 0 || (uint32_t)r[4] >= (uint32_t)g.n) { report_error(P.s.st, FPX_ERR_SLOT_RANGE, i); return; }
+  int32_t* l = P.s.lead + inst * kEpLeadWords;
+  if (l[L_KIND] != (kAccept ? LK_ACCEPTING : LK_PREACCEPTING)) return;          // :1295-1315 / :1518-1535
+  if (ballot_key(r[2], r[3]) != ballot_key(l[L_BORD], l[L_BREP])) return;       // :1325-1335 / :1543-1552
+  ep_count(P.s, inst, P.tag);
+  const uint32_t seq = P.seq_base + (uint32_t)i;
+  if (kAccept) {
+    uint32_t old = atomicMin((uint32_t*)&l[L_ASTAMP + r[4]], seq);
+    if (old == kStampEmpty) o[0] = 1;
+    else if (old >= P.seq_base) report_error(P.s.st, FPX_ERR_BATCH_ORDER, max((uint32_t)i, old - P.seq_base));
+    return;
+  }
+  int32_t* resp = l + L_RESP + r[4] * kEpRespWords;
+  uint32_t old = atomicMin((uint32_t*)&resp[0], seq);
+  if (old == kStampEmpty) {                                     // responses(replicaIndex) = ok (:1340), new key
+    resp[1] = r[5];
+    for (int k = 0; k < g.n; ++k) resp[2 + k] = r[6 + k];
+    o[0] = 1;
+  } else if (old >= P.seq_base) {                               // two responses of one replica in one batch (E2)
+    report_error(P.s.st, FPX_ERR_BATCH_ORDER, max((uint32_t)i, old - P.seq_base));
+  } else {
+    bool same = resp[1] == r[5];
+    for (int k = 0; k < g.n; ++k) same = same && resp[2 + k] == r[6 + k];
+    if (!same) o[0] = 2;                                        // replaces content; judged in the decide pass
+  }
+}
+
+// decide pass: events at the first crossing of the quorum thresholds
+template <bool kAccept>
+__global__ void ep_response_decide_kernel(EpParams P) {
+  const EpGeometry& g = P.g;
+  const int W = kAccept ? 6 : 6 + g.n;
+  const int WO = 2 + g.n;
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= P.n_rec) return;
+  const int32_t* r = P.in + (size_t)i * W;
+  int32_t* o = P.out + (size_t)i * WO;
+  const int mode = o[0];
+  o[0] = EV_NONE;
+  if (mode == 0) return;
+  long long inst = ep_instance(g, r[0], r[1]);
+  int32_t* l = P.s.lead + inst * kEpLeadWords;
+  int32_t* c = P.s.cmd + inst * kEpCmdWords;
+  const uint32_t seq = P.seq_base + (uint32_t)i;
+  if (mode == 2) {
+    // a replacing response must be alone for its instance in the batch (E2)
+    unsigned long long cnt = P.s.count[inst];
+    if ((uint32_t)(cnt >> 32) == P.tag && (uint32_t)cnt > 1) { report_error(P.s.st, FPX_ERR_BATCH_ORDER, i); return; }
+    int32_t* resp = l + L_RESP + r[4] * kEpRespWords;
+    resp[1] = r[5];
+    for (int k = 0; k < g.n; ++k) resp[2 + k] = r[6 + k];
+    return;                                                     // size unchanged: no threshold can be crossed
+  }
+  int before = 0;
+  for (int k = 0; k < g.n; ++k) {
+    uint32_t st = (uint32_t)(kAccept ? l[L_ASTAMP + k] : l[L_RESP + k * kEpRespWords]);
+    if (st < seq) ++before;
+  }
+  const int after = before + 1;
+  if (kAccept) {
+    if (!(before < g.slow_quorum && after >= g.slow_quorum)) return;           // :1558-1560
+    o[0] = EV_COMMIT; o[1] = l[L_ASEQ];
+    c[C_KIND] = EK_COMMITTED; c[C_VALUE] = l[L_VALUE]; c[C_SEQ] = l[L_ASEQ];    // commit (:815-829)
+    for (int k = 0; k < g.n; ++k) { o[2 + k] = l[L_ADEPS + k]; c[C_DEPS + k] = l[L_ADEPS + k]; }
+    l[L_KIND] = LK_NONE;
+    return;
+  }
+  const bool avoid = l[L_FLAGS] & LF_AVOID;
+  if (after < g.slow_quorum) return;                                           // :1345-1347
+  bool slow = false, decide = false;
+  if (!avoid && before < g.slow_quorum && after >= g.slow_quorum && g.slow_quorum < g.fast_quorum) {
+    atomicOr((int*)&l[L_FLAGS], LF_TIMER);                                     // :1353-1364
+    o[0] = EV_TIMER;
+    return;
+  }
+  if (avoid) { if (before < g.slow_quorum) slow = true; else return; }         // :1369-1372
+  else if (after >= g.fast_quorum && before < g.fast_quorum) decide = true;    // :1376
+  else return;
+  int fseq = 0, fdeps[kEpMaxN];
+  bool fast = false;
+  if (decide) {
+    // popularItems over the non-leader (seq, deps) pairs, threshold fastQuorumSize - 1 (:1382-1396)
+    for (int a = 0; a < g.n && !fast; ++a) {
+      if (a == g.index) continue;
+      const int32_t* ra = l + L_RESP + a * kEpRespWords;
+      if ((uint32_t)ra[0] > seq) continue;
+      int cnt = 0;
+      for (int b2 = 0; b2 < g.n; ++b2) {
+        if (b2 == g.index) continue;
+        const int32_t* rb = l + L_RESP + b2 * kEpRespWords;
+        if ((uint32_t)rb[0] > seq) continue;
+        bool eq = ra[1] == rb[1];
+        for (int k = 0; k < g.n; ++k) eq = eq && ra[2 + k] == rb[2 + k];
+        cnt += eq;
+      }
+      if (cnt >= g.fast_quorum - 1) {
+        fast = true; fseq = ra[1];
+        for (int k = 0; k < g.n; ++k) fdeps[k] = ra[2 + k];
+      }
+    }
+    if (!fast) slow = true;
+  }
+  if (fast) {                                                                  // :1401-1410 commit
+    o[0] = EV_FAST_COMMIT; o[1] = fseq;
+    c[C_KIND] = EK_COMMITTED; c[C_VALUE] = l[L_VALUE]; c[C_SEQ] = fseq;
+    for (int k = 0; k < g.n; ++k) { o[2 + k] = fdeps[k]; c[C_DEPS + k] = fdeps[k]; }
+    l[L_KIND] = LK_NONE;
+    return;
+  }
+  if (slow) {                                                                  // preAcceptingSlowPath :796-813
+    int sseq = INT_MIN;
+    int sdeps[kEpMaxN];
+    for (int k = 0; k < g.n; ++k) sdeps[k] = 0;
+    for (int a = 0; a < g.n; ++a) {
+      const int32_t* ra = l + L_RESP + a * kEpRespWords;
+      if ((uint32_t)ra[0] > seq) continue;
+      sseq = max(sseq, ra[1]);
+      for (int k = 0; k < g.n; ++k) sdeps[k] = max(sdeps[k], ra[2 + k]);       // dependencies.addAll (:804-807)
+    }
+    o[0] = EV_SLOW_ACCEPT; o[1] = sseq;
+    // transitionToAcceptPhase (:732-793)
+    c[C_KIND] = EK_ACCEPTED; c[C_VALUE] = l[L_VALUE]; c[C_BORD] = l[L_BORD]; c[C_BREP] = l[L_BREP];
+    c[C_VBORD] = l[L_BORD]; c[C_VBREP] = l[L_BREP]; c[C_SEQ] = sseq;
+    l[L_ASEQ] = sseq;
+    for (int k = 0; k < g.n; ++k) { o[2 + k] = sdeps[k]; c[C_DEPS + k] = sdeps[k]; l[L_ADEPS + k] = sdeps[k]; }
+    for (int k = 0; k < kEpMaxN; ++k) l[L_ASTAMP + k] = (int32_t)kStampEmpty;
+    l[L_ASTAMP + g.index] = 0;                                                 // own AcceptOk (:781-789)
+    l[L_KIND] = LK_ACCEPTING;
+  }
+}
+
+// ---- general IntPrefixSet union (S/compact/IntPrefixSet.scala:253-259, 317-351, 426-431)
+// Sets are CSR: watermark[j], values[off[j] .. off[j+1]) (canonical: every value >
+// watermark).  Group q unions sets [goff[q], goff[q+1]).  Output: out_w[q],
+// out_values[ooff[q] .. ooff[q] + out_n[q]) sorted ascending, ooff[q] = off[goff[q]].
+// One thread per group; value lists on this path are tiny (the overflow of a
+// prefix set), so an in-place insertion sort beats anything cooperative.
+__global__ void depset_union_kernel(const int32_t* wm, const int32_t* off, const int32_t* values, const int32_t* goff,
+                                    int n_groups, int32_t* out_w, int32_t* out_n, int32_t* out_values) {
+  int q = blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= n_groups) return;
+  int s0 = goff[q], s1 = goff[q + 1];
+  int w = 0;
+  for (int j = s0; j < s1; ++j) w = max(w, wm[j]);                           // maxWatermark
+  int32_t* dst = out_values + off[s0];
+  int m = 0;
+  for (int j = s0; j < s1; ++j) {
+    for (int t = off[j]; t < off[j + 1]; ++t) {
+      int v = values[t];
+      if (v < w) continue;                                                  // .filter(_ >= maxWatermark)
+      int pos = m;                                                          // sorted insert, dedup (a Set)
+      while (pos > 0 && dst[pos - 1] > v) --pos;
+      if (pos > 0 && dst[pos - 1] == v) continue;
+      for (int u = m; u > pos; --u) dst[u] = dst[u - 1];
+      dst[pos] = v;
+      ++m;
+    }
+  }
+  int lo = 0;
+  while (lo < m && dst[lo] == w) { ++lo; ++w; }                             // compact() (:426-431)
+  if (lo)
+    for (int u = lo; u < m; ++u) dst[u - lo] = dst[u];
+  out_w[q] = w;
+  out_n[q] = m - lo;
+}
+
+}  // namespace fpx

@@ -1,0 +1,121 @@
+"""Python handle over the EPaxos entry points of include/fpx.h (one replica's cmdLog +
+leaderStates; shared/src/main/scala/frankenpaxos/epaxos/Replica.scala).  Messages are
+int32 matrices, one row per message, dependency sets dense watermark vectors."""
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from .engine import FpxError
+
+REPLY_NONE, REPLY_OK, REPLY_NACK, REPLY_COMMIT = 0, 1, 2, 3
+EV_NONE, EV_FAST_COMMIT, EV_SLOW_ACCEPT, EV_TIMER, EV_COMMIT = 0, 1, 2, 3, 4
+
+
+class EpaxosConfig(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in ("struct_size", "f", "replica_index", "instances_per_replica",
+                                         "max_batch", "device")]
+
+
+def _bind(L):
+    if getattr(L, "_ep_bound", False):
+        return
+    vp, i32, p = C.c_void_p, C.c_int32, C.POINTER
+    L.fpx_epaxos_create.argtypes = [p(vp), p(EpaxosConfig)]; L.fpx_epaxos_create.restype = i32
+    L.fpx_epaxos_destroy.argtypes = [vp]; L.fpx_epaxos_destroy.restype = None
+    L.fpx_epaxos_lead.argtypes = [vp, vp, i32, p(C.c_int64)]; L.fpx_epaxos_lead.restype = i32
+    for nm in ("fpx_epaxos_preaccept", "fpx_epaxos_accept", "fpx_epaxos_preacceptok", "fpx_epaxos_acceptok"):
+        f = getattr(L, nm)
+        f.argtypes = [vp, vp, i32, vp, p(C.c_int64)]; f.restype = i32
+    L.fpx_epaxos_entry.argtypes = [vp, i32, i32, vp, p(i32), vp]; L.fpx_epaxos_entry.restype = i32
+    L.fpx_depset_union.argtypes = [i32, vp, vp, vp, i32, vp, i32, vp, vp, vp]; L.fpx_depset_union.restype = i32
+    L._ep_bound = True
+
+
+class EpaxosReplica:
+    def __init__(self, f, replica_index, instances_per_replica, max_batch=1 << 16, device=0):
+        self._L = _lib.lib()
+        _bind(self._L)
+        cfg = EpaxosConfig(C.sizeof(EpaxosConfig), f, replica_index, instances_per_replica, max_batch, device)
+        self.f, self.n, self.index = f, 2 * f + 1, replica_index
+        self.h = C.c_void_p()
+        st = self._L.fpx_epaxos_create(C.byref(self.h), C.byref(cfg))
+        if st != 0:
+            self.h = None
+            raise FpxError(st)
+
+    def close(self):
+        if getattr(self, "h", None):
+            self._L.fpx_epaxos_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _call(self, fn, rows, width, out_width):
+        rows = np.ascontiguousarray(rows, dtype=np.int32).reshape(-1, width)
+        out = np.zeros((max(len(rows), 1), max(out_width, 1)), dtype=np.int32)
+        err = C.c_int64(-1)
+        if out_width:
+            st = fn(self.h, rows.ctypes.data, len(rows), out.ctypes.data, C.byref(err))
+        else:
+            st = fn(self.h, rows.ctypes.data, len(rows), C.byref(err))
+        if st != 0:
+            raise FpxError(st, err.value)
+        return out[:len(rows)]
+
+    def lead(self, rows):
+        """rows: {inst_replica, inst_number, b_ord, b_rep, value_id, seq, avoid_fast_path, 0, deps[n]}"""
+        self._call(self._L.fpx_epaxos_lead, rows, 8 + self.n, 0)
+
+    def preaccept(self, rows):
+        """rows: {inst_replica, inst_number, b_ord, b_rep, value_id, seq, local_deps[n], msg_deps[n]}
+        -> replies {kind, b_ord, b_rep, seq, deps[n]}"""
+        return self._call(self._L.fpx_epaxos_preaccept, rows, 6 + 2 * self.n, 4 + self.n)
+
+    def accept(self, rows):
+        return self._call(self._L.fpx_epaxos_accept, rows, 6 + self.n, 4 + self.n)
+
+    def preacceptok(self, rows):
+        """rows: {inst_replica, inst_number, b_ord, b_rep, from, seq, deps[n]} -> events {kind, seq, deps[n]}"""
+        return self._call(self._L.fpx_epaxos_preacceptok, rows, 6 + self.n, 2 + self.n)
+
+    def acceptok(self, rows):
+        return self._call(self._L.fpx_epaxos_acceptok, rows, 6, 2 + self.n)
+
+    def entry(self, rep, num):
+        out = np.zeros(7 + self.n, dtype=np.int32)
+        lk = C.c_int32(0)
+        lb = np.zeros(2, dtype=np.int32)
+        st = self._L.fpx_epaxos_entry(self.h, rep, num, out.ctypes.data, C.byref(lk), lb.ctypes.data)
+        if st != 0:
+            raise FpxError(st)
+        return out, lk.value, lb
+
+
+def depset_union(watermarks, value_lists, group_off, device=0):
+    """Batched IntPrefixSet union on the GPU.  watermarks[j], value_lists[j] (iterable of
+    ints > watermark); group q unions sets group_off[q]..group_off[q+1].  Returns a list of
+    (watermark, sorted values)."""
+    L = _lib.lib()
+    _bind(L)
+    wm = np.ascontiguousarray(watermarks, dtype=np.int32)
+    off = np.zeros(len(wm) + 1, dtype=np.int32)
+    off[1:] = np.cumsum([len(v) for v in value_lists])
+    vals = np.ascontiguousarray([x for v in value_lists for x in v], dtype=np.int32) if off[-1] else np.zeros(1, np.int32)
+    goff = np.ascontiguousarray(group_off, dtype=np.int32)
+    ng = len(goff) - 1
+    ow, on = np.zeros(max(ng, 1), np.int32), np.zeros(max(ng, 1), np.int32)
+    ov = np.zeros(max(int(off[-1]), 1), np.int32)
+    st = L.fpx_depset_union(device, wm.ctypes.data, off.ctypes.data, vals.ctypes.data, len(wm), goff.ctypes.data, ng,
+                            ow.ctypes.data, on.ctypes.data, ov.ctypes.data)
+    if st != 0:
+        raise FpxError(st)
+    res = []
+    for q in range(ng):
+        o = off[goff[q]]
+        res.append((int(ow[q]), ov[o:o + on[q]].tolist()))
+    return res

@@ -108,3 +108,56 @@ def workload(seed, cfg, n_slots, slot0=0, round_=0, slot_stride=1, slot_offset=0
                  round_)
     b = shuffled(g, votes_of(p), partitions)
     return a, p, b
+
+
+# --------------------------------------------------------------------------- EPaxos (BASELINE cfg4)
+def epaxos_cfg4(seed, f=2, n_instances=1 << 14, conflict_rate=0.2, me=0, lag=8):
+    """One EPaxos PreAccept round as seen by replica `me` (n = 2f+1 replicas,
+    instances round-robin over the leaders, BernoulliSingleKeyWorkload(conflict_rate):
+    with probability conflict_rate a command is set(x) -- these conflict with each
+    other -- else get(y), which conflicts with nothing;
+    jvm/src/main/scala/frankenpaxos/Workload.scala:75-103).  Dependency vectors are
+    what a TopOne conflict index (shared/src/main/scala/frankenpaxos/util/TopOne.scala)
+    would return in each replica's own delivery order; every replica sees the
+    proposals with a random lag of up to `lag` instances, which is what makes some
+    PreAcceptOk answers differ (slow path).  Returns
+      lead        rows for the instances `me` leads          (8+n ints)
+      preaccept   rows for the instances the others lead      (6+2n ints), delivery order
+      preacceptok rows answering `me`'s instances, shuffled    (6+n ints)
+    """
+    g = rng(seed)
+    n = 2 * f + 1
+    is_set = g.random(n_instances) < conflict_rate
+    leader = np.arange(n_instances) % n
+    number = np.arange(n_instances) // n
+
+    def view(k, who_lag):
+        """TopOne(x) of a replica that has indexed the set(x) instances < k - who_lag."""
+        hi = max(0, k - who_lag)
+        v = np.zeros(n, dtype=np.int32)
+        idx = np.nonzero(is_set[:hi])[0]
+        if len(idx):
+            np.maximum.at(v, leader[idx], number[idx] + 1)
+        return v
+
+    lags = g.integers(0, lag + 1, size=(n_instances, n))
+    lead_rows, pa_rows, ok_rows = [], [], []
+    for k in range(n_instances):
+        L, num = int(leader[k]), int(number[k])
+        zeros = np.zeros(n, dtype=np.int32)
+        ldeps = view(k, int(lags[k, L])) if is_set[k] else zeros
+        if L == me:
+            lead_rows.append(np.concatenate([[L, num, 0, L, k, 0, 0, 0], ldeps]))
+            for r in range(n):
+                if r == me:
+                    continue
+                rdeps = np.maximum(ldeps, view(k, int(lags[k, r]))) if is_set[k] else zeros
+                ok_rows.append(np.concatenate([[L, num, 0, L, r, 0], rdeps]))
+        else:
+            mine = view(k, int(lags[k, me])) if is_set[k] else zeros
+            pa_rows.append(np.concatenate([[L, num, 0, L, k, 0], mine, ldeps]))
+    lead_rows = np.array(lead_rows, dtype=np.int32).reshape(-1, 8 + n)
+    pa_rows = np.array(pa_rows, dtype=np.int32).reshape(-1, 6 + 2 * n)
+    ok_rows = np.array(ok_rows, dtype=np.int32).reshape(-1, 6 + n)
+    ok_rows = ok_rows[g.permutation(len(ok_rows))]
+    return lead_rows, pa_rows, ok_rows

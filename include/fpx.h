@@ -80,7 +80,13 @@ typedef enum {
   FPX_ERR_CONFLICT = -9,           /* same key delivered twice with different values, and
                                       the in-batch order could not be resolved exactly   */
   FPX_ERR_NO_DEVICE = -10,
-  FPX_ERR_UNSUPPORTED = -11
+  FPX_ERR_UNSUPPORTED = -11,
+  FPX_ERR_BATCH_ORDER = -12,       /* EPaxos batch contract E1/E2 violated (two messages of
+                                      one instance / one (instance, replica) in one call):
+                                      split the batch at err_index and resubmit           */
+  FPX_ERR_EPAXOS_STATE = -13       /* transitionToPreAcceptPhase on a committed instance or
+                                      with a regressing ballot: logger.fatal / checkLe,
+                                      S/epaxos/Replica.scala:663-681                       */
 } fpx_status;
 
 #define FPX_MAX_ROUND 0x7ffffffe
@@ -201,6 +207,77 @@ int fpx_snapshot_acceptor(fpx_engine* e, int32_t group, int32_t acceptor,
 
 /* Replica log read-back: value_id per global slot, -1 = hole. */
 int fpx_snapshot_log(fpx_engine* e, int32_t first_slot, int32_t n_slots, int32_t* value_id);
+
+
+/* ---- EPaxos replica (S/epaxos/Replica.scala) ------------------------------
+ * One fpx_epaxos handle = one replica's cmdLog (:298-330) and leaderStates
+ * (:347-386) for n = 2f+1 replicas, instances (replicaIndex, instanceNumber <
+ * instances_per_replica).  Messages are rows of int32 of fixed width (n = 2f+1);
+ * dependency sets are DENSE watermark vectors of n ints (InstancePrefixSet with
+ * empty `values`, the topKDependencies = 1 default, Replica.scala:95); general
+ * sets go through fpx_depset_union.  Ballot = (ordering, replicaIndex), tuple
+ * order (S/epaxos/BallotHelpers.scala:11-21).  Replies / events are DENSE: row i
+ * of the output belongs to message i of the input (kind 0 = nothing to send).
+ * Batch contract, checked on the device (FPX_ERR_BATCH_ORDER + first index):
+ *   E1 lead / preaccept / accept: at most one message per instance per call;
+ *   E2 preacceptok / acceptok: at most one message per (instance, replica) per
+ *      call; a PreAcceptOk that replaces an earlier response of its replica with
+ *      DIFFERENT content must be the only message of its instance in the call.
+ * What the conflict index would compute (computeSequenceNumberAndDependencies,
+ * :569-600) is an INPUT: `local_deps` of a PreAccept, `deps` of lead.        */
+typedef struct fpx_epaxos fpx_epaxos;
+typedef struct {
+  int32_t struct_size;
+  int32_t f;                      /* n = 2f+1 <= 7; fast quorum n-1, slow f+1 (S/epaxos/Config.scala:8-9) */
+  int32_t replica_index;          /* this replica                                                       */
+  int32_t instances_per_replica;
+  int32_t max_batch;
+  int32_t device;
+} fpx_epaxos_config;
+
+enum { FPX_EP_REPLY_NONE = 0, FPX_EP_REPLY_OK = 1, FPX_EP_REPLY_NACK = 2, FPX_EP_REPLY_COMMIT = 3 };
+enum { FPX_EP_EV_NONE = 0, FPX_EP_EV_FAST_COMMIT = 1, FPX_EP_EV_SLOW_ACCEPT = 2, FPX_EP_EV_TIMER = 3,
+       FPX_EP_EV_COMMIT = 4 };
+
+int fpx_epaxos_create(fpx_epaxos** out, const fpx_epaxos_config* cfg);
+void fpx_epaxos_destroy(fpx_epaxos* e);
+
+/* transitionToPreAcceptPhase, Replica.scala:633-729 (the leader's own cmdLog entry
+ * + PreAccepting state with its own response).  in rows of 8+n ints:
+ * {inst_replica, inst_number, ballot_ord, ballot_rep, value_id, seq, avoid_fast_path, 0, deps[n]} */
+int fpx_epaxos_lead(fpx_epaxos* e, const int32_t* in, int32_t n_rec, int64_t* err_index);
+/* handlePreAccept, Replica.scala:1159-1289.  in rows of 6+2n ints: {inst_replica,
+ * inst_number, ballot_ord, ballot_rep, value_id, seq, local_deps[n], msg_deps[n]};
+ * reply rows of 4+n ints: {kind, ballot_ord, ballot_rep, seq, deps[n]} -- PreAcceptOk
+ * (kind OK), Nack(largestBallot) (kind NACK), Commit resend (kind COMMIT). */
+int fpx_epaxos_preaccept(fpx_epaxos* e, const int32_t* in, int32_t n_rec, int32_t* reply, int64_t* err_index);
+/* handleAccept, Replica.scala:1421-1512.  in rows of 6+n ints: {inst_replica,
+ * inst_number, ballot_ord, ballot_rep, value_id, seq, deps[n]}; reply as above (OK = AcceptOk). */
+int fpx_epaxos_accept(fpx_epaxos* e, const int32_t* in, int32_t n_rec, int32_t* reply, int64_t* err_index);
+/* handlePreAcceptOk, Replica.scala:1291-1419 incl. the fast-path equality vote
+ * (Util.popularItems, S/Util.scala:19-21, threshold n-2) and preAcceptingSlowPath
+ * (:796-813, dep-set union of all responses).  in rows of 6+n ints: {inst_replica,
+ * inst_number, ballot_ord, ballot_rep, from_replica, seq, deps[n]}; event rows of
+ * 2+n ints: {kind, seq, deps[n]}. */
+int fpx_epaxos_preacceptok(fpx_epaxos* e, const int32_t* in, int32_t n_rec, int32_t* event, int64_t* err_index);
+/* handleAcceptOk, Replica.scala:1514-1565.  in rows of 6 ints: {inst_replica,
+ * inst_number, ballot_ord, ballot_rep, from_replica, 0}; event rows as above (COMMIT). */
+int fpx_epaxos_acceptok(fpx_epaxos* e, const int32_t* in, int32_t n_rec, int32_t* event, int64_t* err_index);
+/* read-back: out[7+n] = {kind, b_ord, b_rep, vb_ord, vb_rep, value_id, seq, deps[n]},
+ * kind 0 none 1 NoCommand 2 PreAccepted 3 Accepted 4 Committed; *leader_kind 0 none 1
+ * PreAccepting 2 Accepting; largest_ballot[2] */
+int fpx_epaxos_entry(fpx_epaxos* e, int32_t inst_replica, int32_t inst_number, int32_t* out,
+                     int32_t* leader_kind, int32_t* largest_ballot);
+
+/* Batched IntPrefixSet union (S/compact/IntPrefixSet.scala:253-259 == repeated
+ * addAll :317-351, then compact :426-431).  Sets in CSR form: watermark[j] and
+ * values[off[j] .. off[j+1]) (canonical: every value > its watermark); group q
+ * unions sets [group_off[q], group_off[q+1]).  Output: out_watermark[q],
+ * out_count[q] and the sorted overflow values at out_values[off[group_off[q]] ..).
+ * `device` = CUDA ordinal. */
+int fpx_depset_union(int32_t device, const int32_t* watermark, const int32_t* off, const int32_t* values,
+                     int32_t n_sets, const int32_t* group_off, int32_t n_groups, int32_t* out_watermark,
+                     int32_t* out_count, int32_t* out_values);
 
 /* ---- device-pointer entry points (inputs already resident in HBM) ------- */
 

@@ -25,6 +25,7 @@
 // Citations: S/ = shared/src/main/scala/frankenpaxos/ in the reference tree.
 
 #include <algorithm>
+#include <climits>
 #include <cstdint>
 #include <cstring>
 #include <map>
@@ -542,6 +543,236 @@ struct MultiPaxos {
   }
 };
 
+
+// ---------------------------------------------------------------------------
+// EPaxos replica: PreAccept / PreAcceptOk / Accept / AcceptOk
+// S/epaxos/Replica.scala:247-387 (types), 633-813 (transitions), 1159-1565 (handlers)
+// ---------------------------------------------------------------------------
+// InstancePrefixSet = one IntPrefixSet per replica column (S/epaxos/InstancePrefixSet.scala:58-61)
+struct InstancePrefixSet {
+  std::vector<IntPrefixSet> cols;
+  explicit InstancePrefixSet(int n = 0) : cols(n) {}
+  static InstancePrefixSet from_watermarks(const int* w, int n) {  // fromWatermarks (:19-25)
+    InstancePrefixSet s(n);
+    for (int i = 0; i < n; ++i) s.cols[i] = IntPrefixSet(w[i], {});
+    return s;
+  }
+  void add_all(const InstancePrefixSet& o) {                        // addAll (:121-126)
+    for (size_t i = 0; i < cols.size(); ++i) cols[i].add_all(o.cols[i]);
+  }
+  bool operator==(const InstancePrefixSet& o) const { return cols == o.cols; }
+  bool operator<(const InstancePrefixSet& o) const {                // only for std::map keys
+    for (size_t i = 0; i < cols.size(); ++i) {
+      if (cols[i].watermark != o.cols[i].watermark) return cols[i].watermark < o.cols[i].watermark;
+      if (cols[i].values != o.cols[i].values) return cols[i].values < o.cols[i].values;
+    }
+    return false;
+  }
+};
+
+using Ballot = std::pair<int, int>;  // (ordering, replicaIndex), tuple order (BallotHelpers.scala:11-21)
+static const Ballot kNullBallot(-1, -1);  // Replica.scala:256
+
+struct EPaxos {
+  int f, n, index;             // this replica's index
+  int fast_quorum, slow_quorum;  // Config.scala:8-9
+  enum Kind { kNone = 0, kNoCommand = 1, kPreAccepted = 2, kAccepted = 3, kCommitted = 4 };
+  struct Entry {               // CmdLogEntry variants, Replica.scala:298-330
+    Kind kind = kNone;
+    Ballot ballot = kNullBallot, vote_ballot = kNullBallot;
+    int value = 0, seq = 0;
+    InstancePrefixSet deps;
+  };
+  struct Response { int seq; InstancePrefixSet deps; };
+  enum LKind { kLNone = 0, kPreAccepting = 1, kAccepting = 2 };
+  struct Leader {              // LeaderState, Replica.scala:347-386
+    LKind kind = kLNone;
+    Ballot ballot;
+    int value = 0;
+    bool avoid_fast_path = false, timer_armed = false;
+    std::map<int, Response> responses;     // PreAccepting.responses
+    int seq = 0;                           // Accepting.triple
+    InstancePrefixSet deps;
+    std::set<int> accept_responses;        // Accepting.responses (keys)
+  };
+  using Instance = std::pair<int, int>;    // (replicaIndex, instanceNumber)
+  std::map<Instance, Entry> cmd_log;
+  std::map<Instance, Leader> leader_states;
+  Ballot largest_ballot = kNullBallot;
+
+  EPaxos(int f_, int index_) : f(f_), n(2 * f_ + 1), index(index_), fast_quorum(n - 1), slow_quorum(f_ + 1) {}
+
+  // reply kinds / event kinds shared with the engine
+  enum { kReplyNone = 0, kReplyOk = 1, kReplyNack = 2, kReplyCommit = 3 };
+  enum { kEvNone = 0, kEvFastCommit = 1, kEvSlowAccept = 2, kEvTimer = 3, kEvCommit = 4 };
+
+  // transitionToPreAcceptPhase, Replica.scala:633-729 (deps = the conflict index's answer, an input)
+  int lead(Instance I, Ballot ballot, int value, int seq, const InstancePrefixSet& deps, bool avoid) {
+    auto it = cmd_log.find(I);
+    if (it != cmd_log.end()) {
+      if (it->second.kind == kCommitted) return -1;          // logger.fatal (:663-667)
+      if (ballot < it->second.ballot) return -1;              // checkLe (:672-681)
+      if (it->second.kind != kNoCommand && ballot < it->second.vote_ballot) return -1;
+    }
+    Entry e;
+    e.kind = kPreAccepted; e.ballot = ballot; e.vote_ballot = ballot; e.value = value; e.seq = seq; e.deps = deps;
+    cmd_log[I] = e;                                           // :684-693
+    Leader l;
+    l.kind = kPreAccepting; l.ballot = ballot; l.value = value; l.avoid_fast_path = avoid;
+    l.responses[index] = Response{seq, deps};                 // :716-724 self response
+    leader_states[I] = l;                                     // :713-728
+    return 0;
+  }
+
+  struct Reply { int kind; Ballot ballot; int seq; InstancePrefixSet deps; };
+
+  // handlePreAccept, Replica.scala:1159-1289.  local_deps = computeSequenceNumberAndDependencies
+  // (:1248-1251), an input (SURVEY 8(g) rule 5); local seq is always 0 (:599).
+  Reply pre_accept(Instance I, Ballot b, int value, int seq, const InstancePrefixSet& local_deps,
+                   const InstancePrefixSet& msg_deps) {
+    Reply nack{kReplyNack, largest_ballot, 0, InstancePrefixSet(n)};   // :1166-1167 (built before the match)
+    auto it = cmd_log.find(I);
+    if (it != cmd_log.end()) {
+      Entry& e = it->second;
+      switch (e.kind) {
+        case kNoCommand:
+          if (b < e.ballot) return nack;                      // :1181-1184
+          break;
+        case kPreAccepted:
+          if (b < e.ballot) return nack;                      // :1188-1191
+          if (b == e.vote_ballot) return Reply{kReplyOk, b, e.seq, e.deps};  // :1195-1208 resend
+          break;
+        case kAccepted:
+          if (b < e.ballot) return nack;                      // :1212-1215
+          if (b == e.vote_ballot) return Reply{kReplyNone, b, 0, InstancePrefixSet(n)};  // :1219-1221
+          break;
+        case kCommitted:
+          return Reply{kReplyCommit, kNullBallot, e.seq, e.deps};  // :1223-1234
+        default: break;
+      }
+    }
+    auto ls = leader_states.find(I);                          // :1240-1244 yield leadership
+    if (ls != leader_states.end() && ls->second.kind != kLNone && b > ls->second.ballot) leader_states.erase(ls);
+    largest_ballot = std::max(largest_ballot, b);             // :1246
+    int s = std::max(0, seq);                                 // :1256
+    InstancePrefixSet deps = local_deps;
+    deps.add_all(msg_deps);                                   // :1257
+    Entry e;
+    e.kind = kPreAccepted; e.ballot = b; e.vote_ballot = b; e.value = value; e.seq = s; e.deps = deps;
+    cmd_log[I] = e;                                           // :1260-1271
+    return Reply{kReplyOk, b, s, deps};                       // :1278-1288
+  }
+
+  // handleAccept, Replica.scala:1421-1512
+  Reply accept(Instance I, Ballot b, int value, int seq, const InstancePrefixSet& deps) {
+    Reply nack{kReplyNack, largest_ballot, 0, InstancePrefixSet(n)};
+    auto it = cmd_log.find(I);
+    if (it != cmd_log.end()) {
+      Entry& e = it->second;
+      switch (e.kind) {
+        case kNoCommand:
+        case kPreAccepted:
+          if (b < e.ballot) return nack;                      // :1433-1444
+          break;
+        case kAccepted:
+          if (b < e.ballot) return nack;                      // :1448-1451
+          if (b == e.vote_ballot) return Reply{kReplyOk, b, 0, InstancePrefixSet(n)};  // :1455-1464 resend AcceptOk
+          break;
+        case kCommitted:
+          return Reply{kReplyCommit, kNullBallot, e.seq, e.deps};  // :1466-1477
+        default: break;
+      }
+    }
+    auto ls = leader_states.find(I);                          // :1482-1486
+    if (ls != leader_states.end() && ls->second.kind != kLNone && b > ls->second.ballot) leader_states.erase(ls);
+    largest_ballot = std::max(largest_ballot, b);             // :1489
+    Entry e;
+    e.kind = kAccepted; e.ballot = b; e.vote_ballot = b; e.value = value; e.seq = seq; e.deps = deps;
+    cmd_log[I] = e;                                           // :1495-1504
+    return Reply{kReplyOk, b, 0, InstancePrefixSet(n)};       // :1506-1511 AcceptOk
+  }
+
+  struct Event { int kind; int seq; InstancePrefixSet deps; };
+
+  void commit(Instance I, int value, int seq, const InstancePrefixSet& deps) {  // :815-829
+    Entry e;
+    e.kind = kCommitted; e.value = value; e.seq = seq; e.deps = deps;
+    cmd_log[I] = e;
+    leader_states.erase(I);
+  }
+  void to_accept_phase(Instance I, Ballot b, int value, int seq, const InstancePrefixSet& deps) {  // :732-793
+    Entry e;
+    e.kind = kAccepted; e.ballot = b; e.vote_ballot = b; e.value = value; e.seq = seq; e.deps = deps;
+    cmd_log[I] = e;
+    Leader l;
+    l.kind = kAccepting; l.ballot = b; l.value = value; l.seq = seq; l.deps = deps;
+    l.accept_responses.insert(index);                         // :781-789 self AcceptOk
+    leader_states[I] = l;
+  }
+
+  // handlePreAcceptOk, Replica.scala:1291-1419
+  Event pre_accept_ok(Instance I, Ballot b, int from, int seq, const InstancePrefixSet& deps) {
+    Event none{kEvNone, 0, InstancePrefixSet(n)};
+    auto it = leader_states.find(I);
+    if (it == leader_states.end() || it->second.kind != kPreAccepting) return none;  // :1295-1315
+    Leader& l = it->second;
+    if (b != l.ballot) return none;                           // :1325-1335
+    int old_n = (int)l.responses.size();
+    l.responses[from] = Response{seq, deps};                  // :1339-1341
+    int new_n = (int)l.responses.size();
+    if (new_n < slow_quorum) return none;                     // :1345-1347
+    if (!l.avoid_fast_path && old_n < slow_quorum && new_n >= slow_quorum && slow_quorum < fast_quorum) {
+      l.timer_armed = true;                                   // :1353-1364
+      return Event{kEvTimer, 0, InstancePrefixSet(n)};
+    }
+    if (l.avoid_fast_path && new_n >= slow_quorum) {          // :1369-1372
+      return slow_path(I, l);
+    }
+    if (new_n >= fast_quorum) {                               // :1376-1417
+      // popularItems over the non-leader (seq, deps) pairs with threshold fastQuorumSize - 1 (:1382-1396)
+      std::map<std::pair<int, InstancePrefixSet>, int> hist;
+      for (auto& kv : l.responses)
+        if (kv.first != index) hist[{kv.second.seq, kv.second.deps}]++;
+      for (auto& kv : hist) {
+        if (kv.second >= fast_quorum - 1) {
+          Event ev{kEvFastCommit, kv.first.first, kv.first.second};
+          commit(I, l.value, ev.seq, ev.deps);                // :1401-1410
+          return ev;
+        }
+      }
+      return slow_path(I, l);                                 // :1412-1415
+    }
+    return none;
+  }
+  Event slow_path(Instance I, Leader& l) {                    // preAcceptingSlowPath, :796-813
+    int seq = INT32_MIN;
+    InstancePrefixSet deps(n);
+    for (auto& kv : l.responses) {
+      seq = std::max(seq, kv.second.seq);
+      deps.add_all(kv.second.deps);
+    }
+    Ballot b = l.ballot;
+    int value = l.value;
+    Event ev{kEvSlowAccept, seq, deps};
+    to_accept_phase(I, b, value, seq, deps);
+    return ev;
+  }
+
+  // handleAcceptOk, Replica.scala:1514-1565
+  Event accept_ok(Instance I, Ballot b, int from) {
+    Event none{kEvNone, 0, InstancePrefixSet(n)};
+    auto it = leader_states.find(I);
+    if (it == leader_states.end() || it->second.kind != kAccepting) return none;
+    Leader& l = it->second;
+    if (b != l.ballot) return none;                           // :1543-1552
+    l.accept_responses.insert(from);                          // :1554-1555
+    if ((int)l.accept_responses.size() < slow_quorum) return none;  // :1558-1560
+    Event ev{kEvCommit, l.seq, l.deps};
+    commit(I, l.value, l.seq, l.deps);                        // :1563
+    return ev;
+  }
+};
+
 }  // namespace fpo
 
 // ---------------------------------------------------------------------------
@@ -695,6 +926,77 @@ void fpo_mp_snapshot_log(void* p, int first_slot, int n_slots, int* value_id) {
     auto it = log.find(first_slot + i);
     value_id[i] = it == log.end() ? -1 : it->second;
   }
+}
+
+
+// ---- EPaxos.  Dep sets cross this interface as DENSE watermark vectors (n ints);
+// an output set whose overflow `values` is non-empty is flagged in `sparse_out`.
+void* fpo_ep_new(int f, int index) { return new EPaxos(f, index); }
+void fpo_ep_free(void* p) { delete (EPaxos*)p; }
+static void put_deps(const InstancePrefixSet& d, int n, int* out, int* sparse) {
+  for (int i = 0; i < n; ++i) {
+    out[i] = i < (int)d.cols.size() ? d.cols[i].watermark : 0;
+    if (i < (int)d.cols.size() && !d.cols[i].values.empty()) *sparse = 1;
+  }
+}
+int fpo_ep_lead(void* p, int rep, int num, int b_ord, int b_rep, int value, int seq, const int* deps, int avoid) {
+  EPaxos* e = (EPaxos*)p;
+  return e->lead({rep, num}, {b_ord, b_rep}, value, seq, InstancePrefixSet::from_watermarks(deps, e->n), avoid != 0);
+}
+// reply: {kind, b_ord, b_rep, seq, deps[n]}
+void fpo_ep_pre_accept(void* p, int rep, int num, int b_ord, int b_rep, int value, int seq, const int* local_deps,
+                       const int* msg_deps, int* reply, int* sparse) {
+  EPaxos* e = (EPaxos*)p;
+  auto r = e->pre_accept({rep, num}, {b_ord, b_rep}, value, seq, InstancePrefixSet::from_watermarks(local_deps, e->n),
+                         InstancePrefixSet::from_watermarks(msg_deps, e->n));
+  reply[0] = r.kind; reply[1] = r.ballot.first; reply[2] = r.ballot.second; reply[3] = r.seq;
+  *sparse = 0;
+  put_deps(r.deps, e->n, reply + 4, sparse);
+}
+void fpo_ep_accept(void* p, int rep, int num, int b_ord, int b_rep, int value, int seq, const int* deps, int* reply,
+                   int* sparse) {
+  EPaxos* e = (EPaxos*)p;
+  auto r = e->accept({rep, num}, {b_ord, b_rep}, value, seq, InstancePrefixSet::from_watermarks(deps, e->n));
+  reply[0] = r.kind; reply[1] = r.ballot.first; reply[2] = r.ballot.second; reply[3] = r.seq;
+  *sparse = 0;
+  put_deps(r.deps, e->n, reply + 4, sparse);
+}
+// event: {kind, seq, deps[n]}
+void fpo_ep_pre_accept_ok(void* p, int rep, int num, int b_ord, int b_rep, int from, int seq, const int* deps,
+                          int* event, int* sparse) {
+  EPaxos* e = (EPaxos*)p;
+  auto ev = e->pre_accept_ok({rep, num}, {b_ord, b_rep}, from, seq, InstancePrefixSet::from_watermarks(deps, e->n));
+  event[0] = ev.kind; event[1] = ev.seq;
+  *sparse = 0;
+  put_deps(ev.deps, e->n, event + 2, sparse);
+}
+void fpo_ep_accept_ok(void* p, int rep, int num, int b_ord, int b_rep, int from, int* event, int* sparse) {
+  EPaxos* e = (EPaxos*)p;
+  auto ev = e->accept_ok({rep, num}, {b_ord, b_rep}, from);
+  event[0] = ev.kind; event[1] = ev.seq;
+  *sparse = 0;
+  put_deps(ev.deps, e->n, event + 2, sparse);
+}
+// cmdLog entry read-back: {kind, b_ord, b_rep, vb_ord, vb_rep, value, seq, deps[n]}; returns 0 if absent
+int fpo_ep_entry(void* p, int rep, int num, int* out) {
+  EPaxos* e = (EPaxos*)p;
+  auto it = e->cmd_log.find({rep, num});
+  if (it == e->cmd_log.end()) return 0;
+  auto& en = it->second;
+  out[0] = en.kind; out[1] = en.ballot.first; out[2] = en.ballot.second; out[3] = en.vote_ballot.first;
+  out[4] = en.vote_ballot.second; out[5] = en.value; out[6] = en.seq;
+  int sp = 0;
+  put_deps(en.deps, e->n, out + 7, &sp);
+  return 1;
+}
+int fpo_ep_leader_kind(void* p, int rep, int num) {
+  EPaxos* e = (EPaxos*)p;
+  auto it = e->leader_states.find({rep, num});
+  return it == e->leader_states.end() ? 0 : (int)it->second.kind;
+}
+void fpo_ep_largest_ballot(void* p, int* out) {
+  EPaxos* e = (EPaxos*)p;
+  out[0] = e->largest_ballot.first; out[1] = e->largest_ballot.second;
 }
 
 }  // extern "C"

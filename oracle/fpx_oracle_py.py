@@ -85,6 +85,16 @@ def lib():
         L.fpo_mp_executed_watermark.argtypes = [vp]; L.fpo_mp_executed_watermark.restype = i32
         L.fpo_mp_snapshot_acceptor.argtypes = [vp, i32, i32, ip, ip, i32, i32, vp, vp]
         L.fpo_mp_snapshot_log.argtypes = [vp, i32, i32, vp]
+        L.fpo_ep_new.argtypes = [i32, i32]; L.fpo_ep_new.restype = vp
+        L.fpo_ep_free.argtypes = [vp]
+        L.fpo_ep_lead.argtypes = [vp, i32, i32, i32, i32, i32, i32, vp, i32]; L.fpo_ep_lead.restype = i32
+        L.fpo_ep_pre_accept.argtypes = [vp, i32, i32, i32, i32, i32, i32, vp, vp, vp, ip]
+        L.fpo_ep_accept.argtypes = [vp, i32, i32, i32, i32, i32, i32, vp, vp, ip]
+        L.fpo_ep_pre_accept_ok.argtypes = [vp, i32, i32, i32, i32, i32, i32, vp, vp, ip]
+        L.fpo_ep_accept_ok.argtypes = [vp, i32, i32, i32, i32, i32, vp, ip]
+        L.fpo_ep_entry.argtypes = [vp, i32, i32, vp]; L.fpo_ep_entry.restype = i32
+        L.fpo_ep_leader_kind.argtypes = [vp, i32, i32]; L.fpo_ep_leader_kind.restype = i32
+        L.fpo_ep_largest_ballot.argtypes = [vp, vp]
         _lib = L
     return _lib
 
@@ -240,3 +250,85 @@ class MultiPaxos:
         v = np.zeros(max(n_slots, 1), dtype=np.int32)
         lib().fpo_mp_snapshot_log(self.h, first_slot, n_slots, v.ctypes.data)
         return v[:n_slots]
+
+
+class EPaxos:
+    """Sequential restatement of one epaxos.Replica's handlers on the path (dense deps).
+    Same row formats as frankenpaxos_b200.epaxos.EpaxosReplica, one message at a time."""
+
+    def __init__(self, f, index):
+        self.f, self.n, self.index = f, 2 * f + 1, index
+        self.h = lib().fpo_ep_new(f, index)
+        self.saw_sparse = False
+
+    def __del__(self):
+        try:
+            lib().fpo_ep_free(self.h)
+        except Exception:
+            pass
+
+    def lead(self, rows):
+        n = self.n
+        rows = np.ascontiguousarray(rows, dtype=np.int32).reshape(-1, 8 + n)
+        for i, r in enumerate(rows):
+            d = np.ascontiguousarray(r[8:8 + n])
+            if lib().fpo_ep_lead(self.h, int(r[0]), int(r[1]), int(r[2]), int(r[3]), int(r[4]), int(r[5]),
+                                 d.ctypes.data, int(r[6])) != 0:
+                return -13, i
+        return 0, -1
+
+    def preaccept(self, rows):
+        n = self.n
+        rows = np.ascontiguousarray(rows, dtype=np.int32).reshape(-1, 6 + 2 * n)
+        out = np.zeros((len(rows), 4 + n), dtype=np.int32)
+        sp = C.c_int(0)
+        for i, r in enumerate(rows):
+            a = np.ascontiguousarray(r[6:6 + n]); b = np.ascontiguousarray(r[6 + n:6 + 2 * n])
+            lib().fpo_ep_pre_accept(self.h, int(r[0]), int(r[1]), int(r[2]), int(r[3]), int(r[4]), int(r[5]),
+                                    a.ctypes.data, b.ctypes.data, out[i].ctypes.data, C.byref(sp))
+            self.saw_sparse |= bool(sp.value)
+        return out
+
+    def accept(self, rows):
+        n = self.n
+        rows = np.ascontiguousarray(rows, dtype=np.int32).reshape(-1, 6 + n)
+        out = np.zeros((len(rows), 4 + n), dtype=np.int32)
+        sp = C.c_int(0)
+        for i, r in enumerate(rows):
+            a = np.ascontiguousarray(r[6:6 + n])
+            lib().fpo_ep_accept(self.h, int(r[0]), int(r[1]), int(r[2]), int(r[3]), int(r[4]), int(r[5]),
+                                a.ctypes.data, out[i].ctypes.data, C.byref(sp))
+        return out
+
+    def preacceptok(self, rows):
+        n = self.n
+        rows = np.ascontiguousarray(rows, dtype=np.int32).reshape(-1, 6 + n)
+        out = np.zeros((len(rows), 2 + n), dtype=np.int32)
+        sp = C.c_int(0)
+        for i, r in enumerate(rows):
+            a = np.ascontiguousarray(r[6:6 + n])
+            lib().fpo_ep_pre_accept_ok(self.h, int(r[0]), int(r[1]), int(r[2]), int(r[3]), int(r[4]), int(r[5]),
+                                       a.ctypes.data, out[i].ctypes.data, C.byref(sp))
+            self.saw_sparse |= bool(sp.value)
+        return out
+
+    def acceptok(self, rows):
+        n = self.n
+        rows = np.ascontiguousarray(rows, dtype=np.int32).reshape(-1, 6)
+        out = np.zeros((len(rows), 2 + n), dtype=np.int32)
+        sp = C.c_int(0)
+        for i, r in enumerate(rows):
+            lib().fpo_ep_accept_ok(self.h, int(r[0]), int(r[1]), int(r[2]), int(r[3]), int(r[4]),
+                                   out[i].ctypes.data, C.byref(sp))
+        return out
+
+    def entry(self, rep, num):
+        out = np.zeros(7 + self.n, dtype=np.int32)
+        if not lib().fpo_ep_entry(self.h, rep, num, out.ctypes.data):
+            out[:] = 0
+            out[1:5] = -1
+        elif out[0] == 4:
+            out[1:5] = -1
+        lb = np.zeros(2, dtype=np.int32)
+        lib().fpo_ep_largest_ballot(self.h, lb.ctypes.data)
+        return out, lib().fpo_ep_leader_kind(self.h, rep, num), lb
