@@ -28,7 +28,7 @@ class Config(C.Structure):
     _fields_ = [(n, C.c_int32) for n in (
         "struct_size", "protocol", "f", "num_acceptor_groups", "acceptors_per_group", "flexible",
         "num_leaders", "num_replicas", "slot_capacity", "overflow_capacity", "max_batch", "device",
-        "shard_index", "shard_count")]
+        "shard_index", "shard_count", "num_leader_groups")]
 
 
 class SyncResult(C.Structure):

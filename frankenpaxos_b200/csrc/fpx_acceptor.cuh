@@ -48,6 +48,7 @@ struct AcceptorParams {
 };
 
 constexpr int kAccUnroll = 4;
+__device__ __forceinline__ int grp_of(int dst) { return dst >> 16; }
 
 // decode + validate one Phase2a record; key = global acceptor id or -1
 __device__ __forceinline__ int decode_p2a(const Geometry& g, const int4& rec, int& key, int& loc, int& vix) {
@@ -58,7 +59,7 @@ __device__ __forceinline__ int decode_p2a(const Geometry& g, const int4& rec, in
   int l = local_slot(g, rec.x);
   if (l < 0) return FPX_ERR_SLOT_RANGE;
   int v = voter_index(g, grp, acc, rec.x);
-  if (v < 0) return FPX_ERR_BAD_ACCEPTOR;
+  if (v < 0 || (g.protocol == FPX_MENCIUS && grp != expected_group(g, rec.x))) return FPX_ERR_BAD_ACCEPTOR;
   key = grp * g.per_group + acc; loc = l; vix = v;
   return 0;
 }
@@ -153,7 +154,9 @@ __device__ __forceinline__ void acceptor_apply(const AcceptorParams& P, int wlo,
           st_stream(P.out_p2b + before, make_int4(rec[u].w >> 16, rec[u].w & 0xffff, rec[u].x, r));
         } else if (valid) {
           // Nack(round) to leaders(roundSystem.leader(phase2a.round)) (:197-198)
-          st_stream2(P.out_nack + ((uint32_t)i - before), make_int2(r % g.num_leaders, cur));
+          int ldr = r % g.num_leaders;
+          if (g.protocol == FPX_MENCIUS) ldr += (grp_of(rec[u].w) / g.agroups) * g.num_leaders;
+          st_stream2(P.out_nack + ((uint32_t)i - before), make_int2(ldr, cur));
         }
       }
       wacc += __popc(b);

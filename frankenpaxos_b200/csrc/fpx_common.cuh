@@ -71,6 +71,8 @@ struct Geometry {
   // Lemire fastmod/fastdiv constants (M = ceil(2^64 / d)) for the two runtime
   // divisors on the hot path: numAcceptorGroups and shard_count
   unsigned long long m_groups, m_shards;
+  int32_t lgroups, agroups;   // FPX_MENCIUS: leader groups, acceptor groups per leader group
+  unsigned long long m_lgroups, m_agroups;
 };
 
 // a % d and a / d for 0 <= a < 2^31, 1 <= d < 2^31, M = 2^64 / d + 1
@@ -138,12 +140,26 @@ __device__ __forceinline__ int local_slot(const Geometry& g, int slot) {
 // non-flexible: the slot's group is slot % numAcceptorGroups
 // (S/multipaxos/ProxyLeader.scala:190); flexible: every (row, col) of the grid
 // (S/multipaxos/ProxyLeader.scala:118-124).
+// The acceptor group a slot's Phase2a goes to, or -1 when any group may see it
+// (flexible grid).  multipaxos: slot % numAcceptorGroups (ProxyLeader.scala:190);
+// mencius: leader group slot % LG, acceptor group (slot / LG) % AG
+// (S/mencius/ProxyLeader.scala:169-176,231-234).
+__device__ __forceinline__ int expected_group(const Geometry& g, int slot) {
+  if (g.flexible) return -1;
+  if (g.protocol == FPX_MENCIUS) {
+    uint32_t q = g.lgroups > 1 ? fastdiv_u32((uint32_t)slot, g.m_lgroups) : (uint32_t)slot;
+    uint32_t lg = (uint32_t)slot - q * (uint32_t)g.lgroups;
+    uint32_t ag = g.agroups > 1 ? fastmod_u32(q, g.m_agroups, (uint32_t)g.agroups) : 0u;
+    return (int)(lg * (uint32_t)g.agroups + ag);
+  }
+  return g.groups > 1 ? (int)fastmod_u32((uint32_t)slot, g.m_groups, (uint32_t)g.groups) : 0;
+}
 __device__ __forceinline__ int voter_index(const Geometry& g, int group, int acceptor, int slot) {
-  if ((uint32_t)group >= (uint32_t)g.groups || (uint32_t)acceptor >= (uint32_t)g.per_group) return -1;
-  if (g.flexible) return group * g.per_group + acceptor;
-  if (g.groups > 1 && g.protocol == FPX_MULTIPAXOS &&
-      group != (int)fastmod_u32((uint32_t)slot, g.m_groups, (uint32_t)g.groups))
-    return -1;
+  if ((uint32_t)acceptor >= (uint32_t)g.per_group) return -1;
+  if (g.flexible) return (uint32_t)group < (uint32_t)g.groups ? group * g.per_group + acceptor : -1;
+  // mencius' Phase2b carries no group (S/mencius/Mencius.proto): only the index counts
+  if (g.protocol == FPX_MENCIUS) return acceptor;
+  if ((uint32_t)group >= (uint32_t)g.groups || group != expected_group(g, slot)) return -1;
   return acceptor;
 }
 

@@ -83,8 +83,16 @@ static int validate(const fpx_config* c) {
     if (std::min(c->num_acceptor_groups, c->acceptors_per_group) - 1 < c->f) return FPX_ERR_CONFIG;
   }
   // engine limits
-  if (c->protocol != FPX_MULTIPAXOS) return FPX_ERR_UNSUPPORTED;
-  long long total = (long long)c->num_acceptor_groups * c->acceptors_per_group;
+  if (c->protocol != FPX_MULTIPAXOS && c->protocol != FPX_MENCIUS) return FPX_ERR_UNSUPPORTED;
+  int lgroups = 1;
+  if (c->protocol == FPX_MENCIUS) {
+    // S/mencius/Config.scala:40-100: >= 1 leader group of >= f+1 leaders, groups of 2f+1 acceptors
+    if (c->flexible || c->num_leader_groups < 1) return FPX_ERR_CONFIG;
+    lgroups = c->num_leader_groups;
+  } else if (c->num_leader_groups > 1) {
+    return FPX_ERR_CONFIG;
+  }
+  long long total = (long long)lgroups * c->num_acceptor_groups * c->acceptors_per_group;
   if (total > FPX_MAX_ACCEPTORS) return FPX_ERR_UNSUPPORTED;
   int voters = c->flexible ? (int)total : c->acceptors_per_group;
   if (voters > FPX_MAX_VOTERS_PER_SLOT) return FPX_ERR_UNSUPPORTED;
@@ -172,7 +180,9 @@ int fpx_create(fpx_engine** out, const fpx_config* cfg) {
   Geometry& g = e->g;
   g.protocol = cfg->protocol;
   g.f = cfg->f;
-  g.groups = cfg->num_acceptor_groups;
+  g.lgroups = cfg->protocol == FPX_MENCIUS ? cfg->num_leader_groups : 1;
+  g.agroups = cfg->num_acceptor_groups;
+  g.groups = g.lgroups * g.agroups;
   g.per_group = cfg->acceptors_per_group;
   g.flexible = cfg->flexible ? 1 : 0;
   g.num_leaders = cfg->num_leaders;
@@ -189,6 +199,8 @@ int fpx_create(fpx_engine** out, const fpx_config* cfg) {
   g.ovf_mask = g.ovf_cap ? (uint32_t)g.ovf_cap - 1u : 0u;
   g.m_groups = ~0ull / (unsigned long long)g.groups + 1ull;
   g.m_shards = ~0ull / (unsigned long long)g.shard_count + 1ull;
+  g.m_lgroups = ~0ull / (unsigned long long)g.lgroups + 1ull;
+  g.m_agroups = ~0ull / (unsigned long long)g.agroups + 1ull;
 
   auto fail = [&](int code) { fpx_destroy(e); return code; };
 #define CKC(call)                                                                \

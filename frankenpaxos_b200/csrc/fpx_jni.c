@@ -20,12 +20,12 @@ typedef int32_t jint_;   /* JNI jint   */
 
 /* long create(int protocol, int f, int groups, int perGroup, int flexible, int numLeaders,
  *             int numReplicas, int slotCapacity, int overflowCapacity, int maxBatch, int device,
- *             int shardIndex, int shardCount)  -> handle, or the negative fpx_status */
+ *             int shardIndex, int shardCount, int numLeaderGroups)  -> handle, or the negative fpx_status */
 JNIEXPORT_ jlong_ Java_frankenpaxos_gpu_Native_create(JNIEnv_* env, jclass_ cls, jint_ protocol, jint_ f,
                                                       jint_ groups, jint_ per_group, jint_ flexible,
                                                       jint_ num_leaders, jint_ num_replicas, jint_ slot_capacity,
                                                       jint_ overflow_capacity, jint_ max_batch, jint_ device,
-                                                      jint_ shard_index, jint_ shard_count) {
+                                                      jint_ shard_index, jint_ shard_count, jint_ num_leader_groups) {
   (void)env; (void)cls;
   fpx_config c;
   c.struct_size = (int32_t)sizeof(c);
@@ -33,6 +33,7 @@ JNIEXPORT_ jlong_ Java_frankenpaxos_gpu_Native_create(JNIEnv_* env, jclass_ cls,
   c.flexible = flexible; c.num_leaders = num_leaders; c.num_replicas = num_replicas;
   c.slot_capacity = slot_capacity; c.overflow_capacity = overflow_capacity; c.max_batch = max_batch;
   c.device = device; c.shard_index = shard_index; c.shard_count = shard_count;
+  c.num_leader_groups = num_leader_groups;
   fpx_engine* e = 0;
   int st = fpx_create(&e, &c);
   return st == FPX_OK ? (jlong_)(intptr_t)e : (jlong_)st;

@@ -104,6 +104,7 @@ __global__ void snapshot_votes_kernel(Geometry g, const unsigned long long* vote
   int slot = first_slot + i;
   int l = local_slot(g, slot);
   int v = l >= 0 ? voter_index(g, group, acceptor, slot) : -1;
+  if (!g.flexible && v >= 0 && group != expected_group(g, slot)) v = -1;  // this acceptor never sees that slot
   int vr = -1, vv = -1;
   if (v >= 0) {
     unsigned long long c = votes[(size_t)l * g.voters + v];

@@ -41,7 +41,7 @@ class Engine:
 
     def __init__(self, f, num_acceptor_groups, acceptors_per_group, flexible=False, num_leaders=None,
                  num_replicas=None, slot_capacity=1 << 20, overflow_capacity=1 << 10, max_batch=1 << 20,
-                 device=0, shard_index=0, shard_count=1, protocol=MULTIPAXOS):
+                 device=0, shard_index=0, shard_count=1, protocol=MULTIPAXOS, num_leader_groups=0):
         L = _lib.lib()
         cfg = _lib.Config()
         cfg.struct_size = C.sizeof(_lib.Config)
@@ -57,6 +57,7 @@ class Engine:
         cfg.max_batch = max_batch
         cfg.device = device
         cfg.shard_index, cfg.shard_count = shard_index, shard_count
+        cfg.num_leader_groups = num_leader_groups
         self.cfg = cfg
         self._L = L
         self.h = C.c_void_p()

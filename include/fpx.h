@@ -123,6 +123,16 @@ typedef struct {
   int32_t device;               /* CUDA ordinal                                          */
   int32_t shard_index;          /* this engine owns slots with slot % shard_count ==     */
   int32_t shard_count;          /*   shard_index (1 GPU: 0 / 1)                          */
+  int32_t num_leader_groups;    /* FPX_MENCIUS: leader groups; slot s belongs to leader
+                                   group s % num_leader_groups and, inside it, to acceptor
+                                   group (s / num_leader_groups) % num_acceptor_groups
+                                   (S/mencius/ProxyLeader.scala:169-176,231-234);
+                                   num_acceptor_groups is then PER LEADER GROUP, num_leaders
+                                   the leaders per group, and a record's group id is
+                                   leader_group * num_acceptor_groups + acceptor_group.
+                                   Nack.leader = leader_group * num_leaders + round %
+                                   num_leaders (S/mencius/Acceptor.scala:215-219).  Other
+                                   protocols: 0 or 1.                                    */
 } fpx_config;
 
 typedef struct fpx_engine fpx_engine; /* opaque */

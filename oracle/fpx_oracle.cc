@@ -406,6 +406,8 @@ enum Status {
 
 struct Config {
   int f, groups, per_group, flexible, num_leaders, num_replicas;
+  int mencius = 0;   // S/mencius: `groups` = lgroups * agroups, num_leaders per leader group
+  int lgroups = 1;
   // S/multipaxos/Config.scala:32-147 (the clauses the path depends on)
   bool valid() const {
     if (f < 1) return false;                                  // :33
@@ -480,7 +482,10 @@ struct MultiPaxos {
       }
       Acceptor& acc = acceptors[g][a];
       if (in[i].round < acc.round) {                          // :192
-        out_nack[nn++] = Nack{round_system.leader(in[i].round), acc.round};  // :197-198
+        int ldr = round_system.leader(in[i].round);                         // :197-198
+        if (cfg.mencius)  // leaders(slotSystem.leader(slot))(roundSystem.leader(round)), mencius/Acceptor.scala:215-219
+          ldr += (in[i].slot % cfg.lgroups) * cfg.num_leaders;
+        out_nack[nn++] = Nack{ldr, acc.round};
         continue;
       }
       acc.round = in[i].round;                                // :204
@@ -503,7 +508,8 @@ struct MultiPaxos {
       }
       PLState& st = it->second;
       if (st.done) continue;                                  // :227-232
-      st.phase2bs.insert({in[i].group, in[i].acceptor});      // :237
+      if (cfg.mencius) st.phase2bs.insert({0, in[i].acceptor});  // phase2bs(acceptorIndex), mencius/ProxyLeader.scala:334
+      else st.phase2bs.insert({in[i].group, in[i].acceptor});  // :237
       if (!cfg.flexible) {
         if ((int)st.phase2bs.size() < cfg.f + 1) continue;    // :238-240
       } else {
@@ -889,6 +895,14 @@ void fpo_bm_gc(void* p, int w) { ((BufferMap*)p)->garbage_collect(w); }
 void* fpo_mp_new(int f, int groups, int per_group, int flexible, int num_leaders, int num_replicas) {
   Config c{f, groups, per_group, flexible, num_leaders, num_replicas};
   if (!c.valid()) return nullptr;
+  return new MultiPaxos(c);
+}
+// S/mencius: lgroups leader groups, each with agroups acceptor groups of 2f+1
+void* fpo_mencius_new(int f, int lgroups, int agroups, int per_group, int num_leaders, int num_replicas) {
+  Config c{f, lgroups * agroups, per_group, 0, num_leaders, num_replicas};
+  c.mencius = 1;
+  c.lgroups = lgroups;
+  if (!c.valid() || lgroups < 1) return nullptr;
   return new MultiPaxos(c);
 }
 void fpo_mp_free(void* p) { delete (MultiPaxos*)p; }

@@ -75,6 +75,7 @@ def lib():
         L.fpo_rr_leader.argtypes = [i32, i32]; L.fpo_rr_leader.restype = i32
         L.fpo_rr_next_classic_round.argtypes = [i32, i32, i32]; L.fpo_rr_next_classic_round.restype = i32
         L.fpo_mp_new.argtypes = [i32] * 6; L.fpo_mp_new.restype = vp
+        L.fpo_mencius_new.argtypes = [i32] * 6; L.fpo_mencius_new.restype = vp
         L.fpo_mp_free.argtypes = [vp]
         L.fpo_mp_arm.argtypes = [vp, vp, i32, i64p]; L.fpo_mp_arm.restype = i32
         L.fpo_mp_acceptor_phase2a.argtypes = [vp, vp, i32, vp, ip, vp, ip, i64p]
@@ -192,10 +193,14 @@ class MultiPaxos:
     """Sequential restatement of the multipaxos Acceptor / ProxyLeader / Replica
     handlers on the quorum-vote path; same call shapes as frankenpaxos_b200.Engine."""
 
-    def __init__(self, f, groups, per_group, flexible=False, num_leaders=None, num_replicas=None):
+    def __init__(self, f, groups, per_group, flexible=False, num_leaders=None, num_replicas=None,
+                 mencius_leader_groups=0):
         num_leaders = f + 1 if num_leaders is None else num_leaders
         num_replicas = f + 1 if num_replicas is None else num_replicas
-        self.h = lib().fpo_mp_new(f, groups, per_group, int(flexible), num_leaders, num_replicas)
+        if mencius_leader_groups:
+            self.h = lib().fpo_mencius_new(f, mencius_leader_groups, groups, per_group, num_leaders, num_replicas)
+        else:
+            self.h = lib().fpo_mp_new(f, groups, per_group, int(flexible), num_leaders, num_replicas)
         if not self.h:
             raise ValueError("Config.checkValid failed")
 

@@ -27,7 +27,7 @@ def test_header_symbols_exported():
 
 def test_struct_layouts_match_header():
     from frankenpaxos_b200 import _lib, engine
-    assert ctypes.sizeof(_lib.Config) == 14 * 4
+    assert ctypes.sizeof(_lib.Config) == 15 * 4
     assert ctypes.sizeof(_lib.SyncResult) == 32
     assert engine.P2A.itemsize == 16 and engine.P2B.itemsize == 16
     assert engine.CHOSEN.itemsize == 8 and engine.NACK.itemsize == 8

@@ -360,3 +360,55 @@ def test_full_size_properties_cfg2():
         exp[mine["slot"]] = 0
         assert np.array_equal(vr, exp)
     eng.close()
+
+
+# --------------------------------------------------------------------------- compartmentalized Mencius (a9)
+@pytest.mark.parametrize("seed", [0, 1])
+def test_mencius_index_math_and_tally(seed):
+    """S/mencius: slot s -> leader group s % LG, acceptor group (s / LG) % AG
+    (mencius/ProxyLeader.scala:169-176,231-234), quorum f+1 keyed by acceptor index
+    (:334-336), Nack to leaders(s % LG)(round % leadersPerGroup) (mencius/Acceptor.scala:215-219)."""
+    from frankenpaxos_b200 import MENCIUS
+    f, LG, AG, per = 1, 3, 2, 3
+    n_slots = 5000
+    g = T.rng(70 + seed)
+    eng = Engine(f, AG, per, num_leaders=2, num_replicas=2, slot_capacity=n_slots, max_batch=1 << 16,
+                 protocol=MENCIUS, num_leader_groups=LG)
+    ora = O.MultiPaxos(f, AG, per, False, 2, 2, mencius_leader_groups=LG)
+    slots = np.arange(n_slots, dtype=np.int32)
+    grp = (slots % LG) * AG + (slots // LG) % AG
+    def p2as(sl, rnd, thrifty=True):
+        q = f + 1 if thrifty else per
+        keys = g.random((len(sl), per))
+        acc = np.argsort(keys, axis=1)[:, :q].astype(np.int32)
+        out = np.zeros(len(sl) * q, dtype=P2A)
+        out["slot"] = np.repeat(sl, q); out["round"] = rnd; out["value_id"] = np.repeat(sl, q) * 4 + rnd
+        out["dst"] = (np.repeat(grp[sl], q) << 16) | acc.reshape(-1)
+        return out
+    a0 = T.arms(slots, 0, slots * 4)
+    H.arm(eng, ora, a0)
+    bump = slots[::7]
+    a1 = T.arms(bump, 1, bump * 4 + 1)
+    H.arm(eng, ora, a1)
+    mix = np.concatenate([p2as(slots, 0), p2as(bump, 1, thrifty=False)])
+    mix = mix[g.permutation(len(mix))]
+    votes = []
+    for chunk in np.array_split(mix, 3):
+        ob, on = H.phase2a(eng, ora, chunk)
+        votes.append(ob)
+    assert sum(len(v) for v in votes) < len(mix)          # some Nacks happened
+    cfg = dict(num_acceptor_groups=LG * AG, acceptors_per_group=per)
+    H.compare_acceptors(eng, ora, cfg, 0, n_slots)
+    v = np.concatenate(votes)
+    v = v[g.permutation(len(v))]
+    for chunk in np.array_split(v, 4):
+        st, c = H.phase2b(eng, ora, chunk)
+        assert st == 0
+        H.replica(eng, ora, c)
+    H.compare_log(eng, ora, 0, n_slots)
+    # a Phase2a delivered to the wrong acceptor group is a precondition violation
+    bad = np.array([(0, 0, 0, (1 << 16) | 0)], dtype=P2A)
+    with pytest.raises(FpxError) as ei:
+        eng.acceptor_phase2a(bad)
+    assert ei.value.status == -5
+    eng.close()
