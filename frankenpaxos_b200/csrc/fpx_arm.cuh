@@ -22,6 +22,8 @@ struct ArmParams {
   DevStatus* st;
   ArmConflict* conflicts;
   uint32_t* win_bits;  // ceil(n/32): record i created its key's entry
+  unsigned long long* votes;  // vanilla Mencius (vanilla != 0): the coordinator votes for itself
+  int32_t vanilla;
 };
 
 __device__ __forceinline__ void note_arm_conflict(const ArmParams& P, int slot, int round) {
@@ -99,6 +101,9 @@ __global__ void __launch_bounds__(256) arm_kernel(ArmParams P) {
           report_error(P.st, FPX_ERR_SLOT_RANGE, i);
         } else if ((uint32_t)rec[u].y > (uint32_t)FPX_MAX_ROUND) {
           report_error(P.st, FPX_ERR_ROUND_RANGE, i);
+        } else if (P.vanilla && ((rec[u].w >> 16) != 0 || (rec[u].w & 0xffff) >= g.per_group ||
+                                 rec[u].x % g.per_group != (rec[u].w & 0xffff))) {
+          report_error(P.st, FPX_ERR_BAD_ACCEPTOR, i);   // only the slot's owner coordinates it (:773, slotSystem)
         } else {
           ok[u] = true;
           unsigned long long want = ((unsigned long long)(uint32_t)rec[u].z << 32) | (uint32_t)rec[u].y;
@@ -110,7 +115,16 @@ __global__ void __launch_bounds__(256) arm_kernel(ArmParams P) {
     for (int u = 0; u < kArmUnroll; ++u) {
       if (c0 + u >= n_chunks) break;
       int i = (c0 + u) * 32 + lane;
-      bool won = ok[u] && arm_finish(P, rec[u], old[u], i);
+      bool won = ok[u] && arm_finish(P, rec[u], old[u], i);  // created the key's Pending entry (:213)
+      if (won && P.vanilla) {
+        // Server.handleClientRequest: log.put(slot, PendingEntry(0, 0, value)) (:779) and
+        // phase2s(slot).phase2bs = {index -> Phase2b} (:818-825): own vote, stamped "before everything"
+        int local = local_slot(g, rec[u].x);
+        int self = rec[u].w & 0xffff;
+        P.pl.rows[(size_t)local * g.row_words + 2 + self] = 0;
+        atomicMax(&P.votes[(size_t)local * g.voters + self],
+                  ((unsigned long long)(uint32_t)(rec[u].y + 1) << 32) | (uint32_t)rec[u].z);
+      }
       unsigned wb = __ballot_sync(0xffffffffu, won);
       if (lane == 0) P.win_bits[c0 + u] = wb;
     }

@@ -28,6 +28,7 @@ constexpr uint32_t kUnarmed = 0xffffffffu;      // row.round_word of a never-arm
 constexpr uint32_t kDoneBit = 0x80000000u;      // row.round_word bit: ProxyLeader `Done`
 constexpr uint32_t kStampEmpty = 0xffffffffu;   // no Phase2b from this voter yet
 constexpr uint64_t kU64Empty = ~0ull;
+constexpr uint64_t kCellChosen = 0x8000000000000000ull;  // vanilla Mencius: the server's entry is a ChosenEntry
 constexpr int kThreads = 256;                     // threads per CTA of the range kernels
 constexpr int kWarps = kThreads / 32;
 constexpr int kMaxKeys = FPX_MAX_ACCEPTORS;       // acceptors tracked by the round scan (lane = key)
@@ -158,7 +159,7 @@ __device__ __forceinline__ int voter_index(const Geometry& g, int group, int acc
   if ((uint32_t)acceptor >= (uint32_t)g.per_group) return -1;
   if (g.flexible) return (uint32_t)group < (uint32_t)g.groups ? group * g.per_group + acceptor : -1;
   // mencius' Phase2b carries no group (S/mencius/Mencius.proto): only the index counts
-  if (g.protocol == FPX_MENCIUS) return acceptor;
+  if (g.protocol == FPX_MENCIUS || g.protocol == FPX_VANILLA_MENCIUS) return acceptor;
   if ((uint32_t)group >= (uint32_t)g.groups || group != expected_group(g, slot)) return -1;
   return acceptor;
 }

@@ -21,6 +21,7 @@
 #include "fpx_epaxos.cuh"
 #include "fpx_replica_misc.cuh"
 #include "fpx_tally.cuh"
+#include "fpx_vanilla.cuh"
 
 using namespace fpx;
 
@@ -36,6 +37,8 @@ struct fpx_engine {
   int32_t* acc_round = nullptr;
   int32_t* acc_max_voted = nullptr;
   unsigned long long* rlog = nullptr;
+  unsigned long long* vm_claim = nullptr;  // vanilla Mencius: per-cell batch claims
+  uint32_t vm_tag = 1;
   DevStatus* st = nullptr;
   // scratch
   uint32_t* bits = nullptr;            // accept / win bitmask, max_batch/32 words
@@ -83,7 +86,10 @@ static int validate(const fpx_config* c) {
     if (std::min(c->num_acceptor_groups, c->acceptors_per_group) - 1 < c->f) return FPX_ERR_CONFIG;
   }
   // engine limits
-  if (c->protocol != FPX_MULTIPAXOS && c->protocol != FPX_MENCIUS) return FPX_ERR_UNSUPPORTED;
+  if (c->protocol != FPX_MULTIPAXOS && c->protocol != FPX_MENCIUS && c->protocol != FPX_VANILLA_MENCIUS)
+    return FPX_ERR_UNSUPPORTED;
+  // S/vanillamencius/Config.scala:13-17: 2f+1 servers, no grid, one "group"
+  if (c->protocol == FPX_VANILLA_MENCIUS && (c->flexible || c->num_acceptor_groups != 1)) return FPX_ERR_CONFIG;
   int lgroups = 1;
   if (c->protocol == FPX_MENCIUS) {
     // S/mencius/Config.scala:40-100: >= 1 leader group of >= f+1 leaders, groups of 2f+1 acceptors
@@ -123,6 +129,7 @@ static int reset_state(fpx_engine* e) {
   CK(e, cudaMemsetAsync(e->acc_round, 0xff, kMaxKeys * 4, e->stream));      // round = -1 (Acceptor.scala:95)
   CK(e, cudaMemsetAsync(e->acc_max_voted, 0xff, kMaxKeys * 4, e->stream));  // maxVotedSlot = -1 (:104)
   CK(e, cudaMemsetAsync(e->rlog, 0xff, (size_t)g.local_slots * 8, e->stream));
+  if (e->vm_claim) CK(e, cudaMemsetAsync(e->vm_claim, 0xff, (size_t)g.local_slots * g.voters * 8, e->stream));
   DevStatus init;
   memset(&init, 0, sizeof(init));
   init.err_word = ~0ull;
@@ -223,6 +230,7 @@ int fpx_create(fpx_engine** out, const fpx_config* cfg) {
   CKC(cudaMalloc(&e->acc_round, kMaxKeys * 4));
   CKC(cudaMalloc(&e->acc_max_voted, kMaxKeys * 4));
   CKC(cudaMalloc(&e->rlog, (size_t)g.local_slots * 8));
+  if (cfg->protocol == FPX_VANILLA_MENCIUS) CKC(cudaMalloc(&e->vm_claim, (size_t)g.local_slots * g.voters * 8));
   CKC(cudaMalloc(&e->st, sizeof(DevStatus)));
   CKC(cudaMalloc(&e->bits, (mb / 32 + 2) * 4));
   CKC(cudaMalloc(&e->g_agg, (size_t)kMaxGrid * kMaxKeys * 4));
@@ -262,7 +270,7 @@ void fpx_destroy(fpx_engine* e) {
   cudaSetDevice(e->cfg.device);
   if (e->stream) cudaStreamSynchronize(e->stream);
   cudaFree(e->rows); cudaFree(e->ovf_keys); cudaFree(e->ovf_rows); cudaFree(e->votes);
-  cudaFree(e->acc_round); cudaFree(e->acc_max_voted); cudaFree(e->rlog); cudaFree(e->st);
+  cudaFree(e->acc_round); cudaFree(e->acc_max_voted); cudaFree(e->rlog); cudaFree(e->vm_claim); cudaFree(e->st);
   cudaFree(e->bits); cudaFree(e->g_agg); cudaFree(e->g_wacc); cudaFree(e->g_ccnt); cudaFree(e->conflicts);
   cudaFree(e->d_in); cudaFree(e->d_out_a); cudaFree(e->d_out_b);
   if (e->h_st) cudaFreeHost(e->h_st);
@@ -296,7 +304,7 @@ static int check_n(fpx_engine* e, const void* p, int32_t n) {
   return FPX_OK;
 }
 
-int fpx_proxyleader_arm_dev(fpx_engine* e, const fpx_p2a* d_in, int32_t n) {
+static int arm_launch(fpx_engine* e, const fpx_p2a* d_in, int32_t n, int vanilla) {
   int c = check_n(e, d_in, n);
   if (c != FPX_OK || n == 0) return c;
   ArmParams P;
@@ -307,6 +315,8 @@ int fpx_proxyleader_arm_dev(fpx_engine* e, const fpx_p2a* d_in, int32_t n) {
   P.st = e->st;
   P.conflicts = (ArmConflict*)e->conflicts;
   P.win_bits = e->bits;
+  P.votes = e->votes;
+  P.vanilla = vanilla;
   int arm_blocks = std::min((n + 256 * kArmUnroll - 1) / (256 * kArmUnroll), e->num_sms * 8);
   arm_kernel<<<arm_blocks, 256, 0, e->stream>>>(P);
   e->launches++;
@@ -314,11 +324,17 @@ int fpx_proxyleader_arm_dev(fpx_engine* e, const fpx_p2a* d_in, int32_t n) {
   return FPX_OK;
 }
 
+int fpx_proxyleader_arm_dev(fpx_engine* e, const fpx_p2a* d_in, int32_t n) {
+  if (e && e->g.protocol == FPX_VANILLA_MENCIUS) return FPX_ERR_UNSUPPORTED;  // use fpx_vm_client_request
+  return arm_launch(e, d_in, n, 0);
+}
+
 int fpx_acceptor_phase2a_dev(fpx_engine* e, const fpx_p2a* d_in, int32_t n, fpx_p2b* d_out_p2b,
                              fpx_nack* d_out_nack) {
   int c = check_n(e, d_in, n);
   if (c != FPX_OK) return c;
   if (n > 0 && (!d_out_p2b || !d_out_nack)) return FPX_ERR_INVALID_ARG;
+  if (e->g.protocol == FPX_VANILLA_MENCIUS) return FPX_ERR_UNSUPPORTED;  // use fpx_vm_phase2a
   if (n == 0) {
     e->h_st->n_p2b = e->h_st->n_nack = 0;
     CK(e, cudaMemsetAsync(&e->st->n_p2b, 0, 8, e->stream));
@@ -387,6 +403,7 @@ int fpx_proxyleader_phase2b_dev(fpx_engine* e, const fpx_p2b* d_in, int32_t n, f
     P.bar_base = e->bar;
     P.first = done == 0;
     P.per = per;
+    P.votes = e->votes;
     P.st = e->st;
     e->bar += 3u * (uint32_t)grid;
     e->seq_base += (uint32_t)sub;
@@ -528,6 +545,55 @@ int fpx_proxyleader_phase2b(fpx_engine* e, const fpx_p2b* in, int32_t n, fpx_cho
     CK(e, cudaStreamSynchronize(e->stream));
   }
   return FPX_OK;
+}
+
+
+// --------------------------------------------------------------------------- vanilla Mencius
+
+int fpx_vm_client_request(fpx_engine* e, const fpx_p2a* in, int32_t n, int64_t* err_index) {
+  if (err_index) *err_index = -1;
+  int c = check_n(e, in, n);
+  if (c != FPX_OK || n == 0) return c;
+  if (e->g.protocol != FPX_VANILLA_MENCIUS) return FPX_ERR_UNSUPPORTED;
+  CK(e, cudaSetDevice(e->cfg.device));
+  CK(e, cudaMemcpyAsync(e->d_in, in, (size_t)n * 16, cudaMemcpyHostToDevice, e->stream));
+  c = arm_launch(e, (const fpx_p2a*)e->d_in, n, 1);
+  if (c != FPX_OK) return c;
+  fpx_sync_result r;
+  c = fpx_sync(e, &r);
+  if (err_index) *err_index = r.err_index;
+  return c;
+}
+
+static int vm_call(fpx_engine* e, const void* in, int32_t n, fpx_p2b* reply, int64_t* err_index, int which) {
+  if (err_index) *err_index = -1;
+  int c = check_n(e, in, n);
+  if (c != FPX_OK || n == 0) return c;
+  if (e->g.protocol != FPX_VANILLA_MENCIUS) return FPX_ERR_UNSUPPORTED;
+  if (which == 0 && !reply) return FPX_ERR_INVALID_ARG;
+  CK(e, cudaSetDevice(e->cfg.device));
+  CK(e, cudaMemcpyAsync(e->d_in, in, (size_t)n * 16, cudaMemcpyHostToDevice, e->stream));
+  VmParams P;
+  P.g = e->g; P.in = (const int4*)e->d_in; P.out = (int4*)e->d_out_a; P.n = n; P.votes = e->votes;
+  P.claim = e->vm_claim; P.rows = e->rows; P.st = e->st;
+  P.tag = e->vm_tag++;
+  if (e->vm_tag == 0xffffffffu) e->vm_tag = 1;
+  if (which == 0) vm_phase2a_kernel<<<(n + 255) / 256, 256, 0, e->stream>>>(P);
+  else vm_learn_chosen_kernel<<<(n + 255) / 256, 256, 0, e->stream>>>(P);
+  e->launches++;
+  CK(e, cudaGetLastError());
+  if (which == 0) CK(e, cudaMemcpyAsync(reply, e->d_out_a, (size_t)n * 16, cudaMemcpyDeviceToHost, e->stream));
+  fpx_sync_result r;
+  c = fpx_sync(e, &r);
+  if (err_index) *err_index = r.err_index;
+  return c;
+}
+
+int fpx_vm_phase2a(fpx_engine* e, const fpx_p2a* in, int32_t n, fpx_p2b* reply, int64_t* err_index) {
+  return vm_call(e, in, n, reply, err_index, 0);
+}
+int fpx_vm_learn_chosen(fpx_engine* e, const fpx_p2b* in, int32_t n, int64_t* err_index) {
+  return vm_call(e, in, n, nullptr, err_index, 1);
 }
 
 int fpx_replica_chosen(fpx_engine* e, const fpx_chosen* in, int32_t n, int64_t* err_index) {

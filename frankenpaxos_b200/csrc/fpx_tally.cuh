@@ -39,6 +39,7 @@ struct TallyParams {
   uint32_t bar_base;
   int32_t first;           // 1: first launch of a call (output offset 0), else append at st->n_chosen
   int32_t per;             // records per warp range == shared buffer entries per warp
+  unsigned long long* votes;  // vanilla Mencius: the coordinator's log entry turns ChosenEntry on completion
   DevStatus* st;
 };
 
@@ -106,7 +107,12 @@ __global__ void __launch_bounds__(kThreads) tally_kernel(TallyParams P) {
       if (row[u] == nullptr) continue;
       uint32_t* r = row[u];
       const uint32_t w = rw[u];
-      if (w == kUnarmed || (int)(w & ~kDoneBit) != rec[u].w) {
+      if (g.protocol == FPX_VANILLA_MENCIUS) {
+        // Server.handlePhase2b: no Phase 2 for the slot / already chosen -> ignore
+        // (:1088-1106); stale round -> ignore (:1109-1112); a larger round fails checkEq (:1116)
+        if (w == kUnarmed || (w & kDoneBit) || rec[u].w < (int)w) continue;
+        if (rec[u].w > (int)w) { report_error(P.st, FPX_ERR_UNKNOWN_SLOT_ROUND, i); continue; }
+      } else if (w == kUnarmed || (int)(w & ~kDoneBit) != rec[u].w) {
         // not the slot's primary round: overflow table, or never armed (:220-225)
         RowRef rr = find_row(g, P.pl, local_slot(g, rec[u].z), rec[u].z, rec[u].w);
         if (rr.p == nullptr) { report_error(P.st, FPX_ERR_UNKNOWN_SLOT_ROUND, i); continue; }
@@ -155,7 +161,9 @@ __global__ void __launch_bounds__(kThreads) tally_kernel(TallyParams P) {
       if (row[u] != nullptr) {
         uint32_t* r = row[u];
         bool ok = true;
-        if (w[u][0] == kUnarmed || (int)(w[u][0] & ~kDoneBit) != rec[u].w) {
+        if (g.protocol == FPX_VANILLA_MENCIUS) {
+          ok = w[u][0] != kUnarmed && !(w[u][0] & kDoneBit) && rec[u].w == (int)w[u][0];
+        } else if (w[u][0] == kUnarmed || (int)(w[u][0] & ~kDoneBit) != rec[u].w) {
           RowRef rr = find_row(g, P.pl, local_slot(g, rec[u].z), rec[u].z, rec[u].w);
           ok = rr.p != nullptr;
           if (ok) { r = rr.p; load_row<ROWW>(r, w[u]); }
@@ -179,6 +187,12 @@ __global__ void __launch_bounds__(kThreads) tally_kernel(TallyParams P) {
               if (mine == seq && write_quorum(g, before | (1u << v))) {
                 complete = true;
                 out = make_int2(rec[u].z, (int)w[u][1]);  // Chosen(slot, pending.phase2a.value) (:249-251)
+                if (g.protocol == FPX_VANILLA_MENCIUS) {
+                  // choose(): the coordinator's own entry becomes ChosenEntry, phase2s.remove (:622-625)
+                  int owner = rec[u].z % g.per_group;
+                  atomicMax(&P.votes[(size_t)local_slot(g, rec[u].z) * g.voters + owner], kCellChosen | w[u][1]);
+                  atomicOr(r, kDoneBit);
+                }
               }
             }
           }

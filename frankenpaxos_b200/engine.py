@@ -158,6 +158,25 @@ class Engine:
         self._check(self._L.fpx_snapshot_log(self.h, first_slot, n_slots, v.ctypes.data))
         return v[:n_slots]
 
+    # -- vanilla Mencius (protocol=VANILLA_MENCIUS)
+    def vm_client_request(self, p2a):
+        p2a = np.ascontiguousarray(p2a, dtype=P2A)
+        err = C.c_int64(-1)
+        self._check(self._L.fpx_vm_client_request(self.h, p2a.ctypes.data, len(p2a), C.byref(err)), err.value)
+
+    def vm_phase2a(self, p2a):
+        """dense replies {group = kind (0 Phase2b, 1 Phase2Nack, 2 Chosen), acceptor = server, slot, round|value}"""
+        p2a = np.ascontiguousarray(p2a, dtype=P2A)
+        out = np.empty(max(len(p2a), 1), dtype=P2B)
+        err = C.c_int64(-1)
+        self._check(self._L.fpx_vm_phase2a(self.h, p2a.ctypes.data, len(p2a), out.ctypes.data, C.byref(err)), err.value)
+        return out[:len(p2a)]
+
+    def vm_learn_chosen(self, recs):
+        recs = np.ascontiguousarray(recs, dtype=P2B)
+        err = C.c_int64(-1)
+        self._check(self._L.fpx_vm_learn_chosen(self.h, recs.ctypes.data, len(recs), C.byref(err)), err.value)
+
     # -- device-pointer calls (raw device addresses, asynchronous on self.stream)
     def proxyleader_arm_dev(self, d_in, n):
         self._check(self._L.fpx_proxyleader_arm_dev(self.h, d_in, n))

@@ -219,6 +219,39 @@ int fpx_snapshot_acceptor(fpx_engine* e, int32_t group, int32_t acceptor,
 int fpx_snapshot_log(fpx_engine* e, int32_t first_slot, int32_t n_slots, int32_t* value_id);
 
 
+
+/* ---- Vanilla Mencius (S/vanillamencius/Server.scala), protocol FPX_VANILLA_MENCIUS ----
+ * n = 2f+1 servers (acceptors_per_group = n, num_acceptor_groups = 1), every
+ * server is proposer + acceptor, server s coordinates the slots with slot % n ==
+ * s.  One engine holds the log entries of all n servers (vote cells [slot][server])
+ * and the coordinators' `phase2s`.  Skips, revocation and Phase 1 are control
+ * path and out of scope.  Batch contract (checked, ->
+ * FPX_ERR_BATCH_ORDER): at most one Phase2a per (slot, server) per call, because
+ * the round compare is per log entry (:1016-1042), not per acceptor.          */
+
+/* Server.handleClientRequest, state part (:767-829): the coordinator in.dst (which
+ * must own in.slot) votes for its own command -- log(slot) = PendingEntry(0, 0,
+ * value) (:779) -- and opens phase2s(slot) with its own Phase2b (:818-825). */
+int fpx_vm_client_request(fpx_engine* e, const fpx_p2a* in, int32_t n, int64_t* err_index);
+
+/* Server.handlePhase2a (:1001-1082) at server in.dst.  DENSE replies, reply[i]
+ * answers in[i]: {group = kind, acceptor = server, slot, round}:
+ *   kind 0  Phase2b(server, slot, round)                 (:1077-1081)
+ *   kind 1  Phase2Nack(slot, round = the entry's round)  (:1044-1051)
+ *   kind 2  Chosen(slot, value in `round`)               (:1018-1027, entry already chosen) */
+int fpx_vm_phase2a(fpx_engine* e, const fpx_p2a* in, int32_t n, fpx_p2b* reply, int64_t* err_index);
+
+/* Server.handlePhase2b (:1084-1142) is fpx_proxyleader_phase2b with this protocol's
+ * rules: no Phase 2 running for the slot -> ignored (:1099-1106), stale round ->
+ * ignored (:1109-1112), larger round -> checkEq fails (FPX_ERR_UNKNOWN_SLOT_ROUND,
+ * :1116), quorum f+1 INCLUDING the coordinator's own vote (:1119-1122); on completion
+ * the coordinator's own entry becomes ChosenEntry (choose, :622-625). */
+
+/* Server.handleChosen -> choose (:1170-1197, :622-640): server in.acceptor learns
+ * that in.slot is chosen with value in.round: its entry becomes ChosenEntry; if it
+ * coordinates the slot, phase2s(slot) is dropped. */
+int fpx_vm_learn_chosen(fpx_engine* e, const fpx_p2b* in, int32_t n, int64_t* err_index);
+
 /* ---- EPaxos replica (S/epaxos/Replica.scala) ------------------------------
  * One fpx_epaxos handle = one replica's cmdLog (:298-330) and leaderStates
  * (:347-386) for n = 2f+1 replicas, instances (replicaIndex, instanceNumber <

@@ -779,6 +779,74 @@ struct EPaxos {
   }
 };
 
+
+// ---------------------------------------------------------------------------
+// Vanilla Mencius server (S/vanillamencius/Server.scala), normal case only: the
+// state parts of handleClientRequest :767-829, handlePhase2a :1001-1082 (without
+// skips), handlePhase2b :1084-1142, handleChosen/choose :1170-1197, :622-640.
+// All n servers are co-located here: logs[s] is server s's log.
+// ---------------------------------------------------------------------------
+struct VanillaMencius {
+  int f, n;
+  struct LogEntry { int kind = 0; int round = -1, vote_round = -1, value = 0; };  // 0 none 2 Pending 3 Chosen (:208-226)
+  struct Phase2 { int round, value; std::set<int> phase2bs; };                      // :198-204
+  std::vector<std::map<int, LogEntry>> logs;
+  std::map<int, Phase2> phase2s;  // the coordinator of a slot is slot % n (slotSystem, :252-257)
+  explicit VanillaMencius(int f_) : f(f_), n(2 * f_ + 1), logs(2 * f_ + 1) {}
+
+  int client_request(const P2a* in, int cnt, int64_t* err) {
+    for (int i = 0; i < cnt; ++i) {
+      int self = in[i].dst & 0xffff;
+      if ((in[i].dst >> 16) != 0 || self >= n || in[i].slot % n != self) { *err = i; return kBadAcceptor; }
+      if (phase2s.count(in[i].slot) || logs[self].count(in[i].slot)) continue;  // check(!contains) (:773-774): duplicate ignored
+      logs[self][in[i].slot] = LogEntry{2, in[i].round, in[i].round, in[i].value_id};  // :779
+      phase2s[in[i].slot] = Phase2{in[i].round, in[i].value_id, {self}};             // :818-825
+    }
+    return kOk;
+  }
+  // reply {kind, server, slot, round|value}
+  int phase2a(const P2a* in, int cnt, P2b* reply, int64_t* err) {
+    for (int i = 0; i < cnt; ++i) {
+      int s = in[i].dst & 0xffff;
+      if ((in[i].dst >> 16) != 0 || s >= n) { *err = i; return kBadAcceptor; }
+      LogEntry& e = logs[s][in[i].slot];
+      if (e.kind == 3) { reply[i] = P2b{2, s, in[i].slot, e.value}; continue; }     // :1017-1027
+      int round = e.kind == 0 ? -1 : e.round;                                          // :1029-1034
+      if (in[i].round < round) { reply[i] = P2b{1, s, in[i].slot, round}; continue; }  // :1037-1045
+      e = LogEntry{2, in[i].round, in[i].round, in[i].value_id};                       // :1048-1052
+      reply[i] = P2b{0, s, in[i].slot, in[i].round};                                   // :1077-1081
+    }
+    return kOk;
+  }
+  int phase2b(const P2b* in, int cnt, Chosen* out, int* n_out, int64_t* err) {
+    int nc = 0;
+    for (int i = 0; i < cnt; ++i) {
+      int coord = in[i].slot % n;
+      auto le = logs[coord].find(in[i].slot);
+      if (le != logs[coord].end() && le->second.kind == 3) continue;                   // :1088-1092
+      auto it = phase2s.find(in[i].slot);
+      if (it == phase2s.end()) continue;                                               // :1099-1106
+      Phase2& p = it->second;
+      if (in[i].round < p.round) continue;                                             // :1109-1112
+      if (in[i].round != p.round) { *err = i; *n_out = nc; return kUnknownSlotRound; } // checkEq :1116
+      if (in[i].acceptor < 0 || in[i].acceptor >= n) { *err = i; *n_out = nc; return kBadAcceptor; }
+      p.phase2bs.insert(in[i].acceptor);                                               // :1119
+      if ((int)p.phase2bs.size() < f + 1) continue;                                    // :1120-1122
+      out[nc++] = Chosen{in[i].slot, p.value};                                         // :1127-1136
+      logs[coord][in[i].slot] = LogEntry{3, -1, -1, p.value};                          // choose (:624)
+      phase2s.erase(it);                                                               // :625
+    }
+    *n_out = nc;
+    return kOk;
+  }
+  void learn_chosen(const P2b* in, int cnt) {                                          // handleChosen -> choose
+    for (int i = 0; i < cnt; ++i) {
+      logs[in[i].acceptor][in[i].slot] = LogEntry{3, -1, -1, in[i].round};
+      if (in[i].slot % n == in[i].acceptor) phase2s.erase(in[i].slot);
+    }
+  }
+};
+
 }  // namespace fpo
 
 // ---------------------------------------------------------------------------
@@ -1011,6 +1079,34 @@ int fpo_ep_leader_kind(void* p, int rep, int num) {
 void fpo_ep_largest_ballot(void* p, int* out) {
   EPaxos* e = (EPaxos*)p;
   out[0] = e->largest_ballot.first; out[1] = e->largest_ballot.second;
+}
+
+
+// ---- vanilla Mencius
+void* fpo_vm_new(int f) { return new VanillaMencius(f); }
+void fpo_vm_free(void* p) { delete (VanillaMencius*)p; }
+int fpo_vm_client_request(void* p, const P2a* in, int n, int64_t* err) {
+  *err = -1;
+  return ((VanillaMencius*)p)->client_request(in, n, err);
+}
+int fpo_vm_phase2a(void* p, const P2a* in, int n, P2b* reply, int64_t* err) {
+  *err = -1;
+  return ((VanillaMencius*)p)->phase2a(in, n, reply, err);
+}
+int fpo_vm_phase2b(void* p, const P2b* in, int n, Chosen* out, int* n_out, int64_t* err) {
+  *err = -1;
+  return ((VanillaMencius*)p)->phase2b(in, n, out, n_out, err);
+}
+void fpo_vm_learn_chosen(void* p, const P2b* in, int n) { ((VanillaMencius*)p)->learn_chosen(in, n); }
+// server's log entry for n_slots slots: kind (0 none, 2 pending, 3 chosen), round, value
+void fpo_vm_snapshot(void* p, int server, int first_slot, int n_slots, int* kind, int* round, int* value) {
+  auto& log = ((VanillaMencius*)p)->logs[server];
+  for (int i = 0; i < n_slots; ++i) {
+    auto it = log.find(first_slot + i);
+    kind[i] = it == log.end() ? 0 : it->second.kind;
+    round[i] = it == log.end() ? -1 : it->second.round;
+    value[i] = it == log.end() ? -1 : it->second.value;
+  }
 }
 
 }  // extern "C"

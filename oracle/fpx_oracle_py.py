@@ -96,6 +96,13 @@ def lib():
         L.fpo_ep_entry.argtypes = [vp, i32, i32, vp]; L.fpo_ep_entry.restype = i32
         L.fpo_ep_leader_kind.argtypes = [vp, i32, i32]; L.fpo_ep_leader_kind.restype = i32
         L.fpo_ep_largest_ballot.argtypes = [vp, vp]
+        L.fpo_vm_new.argtypes = [i32]; L.fpo_vm_new.restype = vp
+        L.fpo_vm_free.argtypes = [vp]
+        L.fpo_vm_client_request.argtypes = [vp, vp, i32, i64p]; L.fpo_vm_client_request.restype = i32
+        L.fpo_vm_phase2a.argtypes = [vp, vp, i32, vp, i64p]; L.fpo_vm_phase2a.restype = i32
+        L.fpo_vm_phase2b.argtypes = [vp, vp, i32, vp, ip, i64p]; L.fpo_vm_phase2b.restype = i32
+        L.fpo_vm_learn_chosen.argtypes = [vp, vp, i32]
+        L.fpo_vm_snapshot.argtypes = [vp, i32, i32, i32, vp, vp, vp]
         _lib = L
     return _lib
 
@@ -337,3 +344,48 @@ class EPaxos:
         lb = np.zeros(2, dtype=np.int32)
         lib().fpo_ep_largest_ballot(self.h, lb.ctypes.data)
         return out, lib().fpo_ep_leader_kind(self.h, rep, num), lb
+
+
+class VanillaMencius:
+    """Sequential restatement of vanillamencius.Server's normal-case handlers, all n
+    servers co-located; same call shapes as Engine(protocol=VANILLA_MENCIUS)."""
+
+    def __init__(self, f):
+        self.f, self.n = f, 2 * f + 1
+        self.h = lib().fpo_vm_new(f)
+
+    def __del__(self):
+        try:
+            lib().fpo_vm_free(self.h)
+        except Exception:
+            pass
+
+    def client_request(self, recs):
+        recs = np.ascontiguousarray(recs, dtype=P2A)
+        err = C.c_int64(-1)
+        return lib().fpo_vm_client_request(self.h, recs.ctypes.data, len(recs), C.byref(err)), err.value
+
+    def phase2a(self, recs):
+        recs = np.ascontiguousarray(recs, dtype=P2A)
+        out = np.zeros(max(len(recs), 1), dtype=P2B)
+        err = C.c_int64(-1)
+        st = lib().fpo_vm_phase2a(self.h, recs.ctypes.data, len(recs), out.ctypes.data, C.byref(err))
+        return st, err.value, out[:len(recs)]
+
+    def phase2b(self, recs):
+        recs = np.ascontiguousarray(recs, dtype=P2B)
+        out = np.zeros(max(len(recs), 1), dtype=CHOSEN)
+        n1, err = C.c_int(0), C.c_int64(-1)
+        st = lib().fpo_vm_phase2b(self.h, recs.ctypes.data, len(recs), out.ctypes.data, C.byref(n1), C.byref(err))
+        return st, err.value, out[:n1.value].copy()
+
+    proxyleader_phase2b = phase2b
+
+    def learn_chosen(self, recs):
+        recs = np.ascontiguousarray(recs, dtype=P2B)
+        lib().fpo_vm_learn_chosen(self.h, recs.ctypes.data, len(recs))
+
+    def snapshot(self, server, first_slot, n_slots):
+        k = np.zeros(max(n_slots, 1), np.int32); r = np.zeros(max(n_slots, 1), np.int32); v = np.zeros(max(n_slots, 1), np.int32)
+        lib().fpo_vm_snapshot(self.h, server, first_slot, n_slots, k.ctypes.data, r.ctypes.data, v.ctypes.data)
+        return k[:n_slots], r[:n_slots], v[:n_slots]

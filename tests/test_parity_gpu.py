@@ -412,3 +412,79 @@ def test_mencius_index_math_and_tally(seed):
         eng.acceptor_phase2a(bad)
     assert ei.value.status == -5
     eng.close()
+
+
+# --------------------------------------------------------------------------- vanilla Mencius (a9, BASELINE cfg5 shape)
+@pytest.mark.parametrize("f", [1, 3])
+def test_vanilla_mencius_matches_oracle(f):
+    """cfg5: n = 2f+1 servers, owner = slot % n, the coordinator's own vote is
+    pre-seeded, up to n-1 Phase2bs per slot, quorum f+1 (Server.scala:767-829,
+    1001-1142).  Also: per-slot round compare (Phase2Nack), Phase2a for an entry that
+    is already chosen, stale / unknown Phase2bs, learn-chosen at other servers."""
+    from frankenpaxos_b200 import VANILLA_MENCIUS
+    n = 2 * f + 1
+    n_slots = 4000
+    g = T.rng(90 + f)
+    eng = Engine(f, 1, n, num_leaders=f + 1, num_replicas=f + 1, slot_capacity=n_slots, max_batch=1 << 16,
+                 protocol=VANILLA_MENCIUS)
+    ora = O.VanillaMencius(f)
+    slots = np.arange(n_slots, dtype=np.int32)
+    req = np.zeros(n_slots, dtype=P2A)
+    req["slot"] = slots; req["round"] = 0; req["value_id"] = slots * 3 + 1; req["dst"] = slots % n
+    eng.vm_client_request(req)
+    assert ora.client_request(req) == (0, -1)
+    # Phase2a from each coordinator to all other servers (:806-815), shuffled delivery
+    others = np.array([[s for s in range(n) if s != o] for o in range(n)], dtype=np.int32)
+    p = np.zeros(n_slots * (n - 1), dtype=P2A)
+    p["slot"] = np.repeat(slots, n - 1); p["round"] = 0; p["value_id"] = np.repeat(req["value_id"], n - 1)
+    p["dst"] = others[slots % n].reshape(-1)
+    p = p[g.permutation(len(p))]
+    votes = []
+    for chunk in np.array_split(p, 3):
+        st, _, orep = ora.phase2a(chunk)
+        erep = eng.vm_phase2a(chunk)
+        H.same(erep, orep, "vanilla Phase2a replies")
+        votes.append(erep[erep["group"] == 0])
+    v = np.concatenate(votes)
+    v["group"] = 0
+    v = v[g.permutation(len(v))]
+    # a stale-round vote and a vote for a slot without Phase 2 are ignored
+    junk = np.array([(0, 1, n_slots - 1, 0)], dtype=P2B)
+    total = 0
+    for chunk in np.array_split(v, 5):
+        st, c = H.phase2b(eng, ora, chunk)
+        assert st == 0
+        total += len(c)
+        H.replica(eng, ora, c) if False else None
+    assert total == n_slots
+    st, c = H.phase2b(eng, ora, junk)
+    assert st == 0 and len(c) == 0
+    # higher-round Phase2a at a non-coordinator: accepted; lower round afterwards: Phase2Nack
+    hi = np.array([(10, 5, 777, 1 if 10 % n != 1 else 2), (11, 5, 778, 0 if 11 % n != 0 else 2)], dtype=P2A)
+    H.same(eng.vm_phase2a(hi), ora.phase2a(hi)[2], "higher round")
+    lo = np.array([(10, 2, 779, hi[0]["dst"]), (11, 5, 780, hi[1]["dst"])], dtype=P2A)
+    er = eng.vm_phase2a(lo)
+    H.same(er, ora.phase2a(lo)[2], "lower/equal round")
+    assert er["group"].tolist() == [1, 0] and er["round"][0] == 5
+    # Phase2a for a slot the coordinator already chose: reply Chosen(value) (:1017-1027)
+    ch = np.array([(20, 0, 1, 20 % n)], dtype=P2A)
+    er = eng.vm_phase2a(ch)
+    H.same(er, ora.phase2a(ch)[2], "Phase2a on a chosen entry")
+    assert er["group"][0] == 2 and er["round"][0] == 20 * 3 + 1
+    # learn-chosen at another server, then a Phase2a there
+    lc = np.array([(0, (30 % n + 1) % n, 30, 91)], dtype=P2B)
+    eng.vm_learn_chosen(lc); ora.learn_chosen(lc)
+    q = np.array([(30, 9, 5, lc[0]["acceptor"])], dtype=P2A)
+    H.same(eng.vm_phase2a(q), ora.phase2a(q)[2], "Phase2a after learn-chosen")
+    # batch contract: two Phase2as for one (slot, server) in one call
+    with pytest.raises(FpxError) as ei:
+        eng.vm_phase2a(np.array([(40, 1, 1, (40 % n + 1) % n), (41, 1, 1, (41 % n + 1) % n), (40, 2, 2, (40 % n + 1) % n)], dtype=P2A))
+    assert (ei.value.status, ei.value.index) == (-12, 2)
+    # a Phase2b in a LARGER round than the one proposed fails checkEq (:1116)
+    eng2 = Engine(f, 1, n, num_leaders=f + 1, num_replicas=f + 1, slot_capacity=64, max_batch=1024, protocol=VANILLA_MENCIUS)
+    ora2 = O.VanillaMencius(f)
+    r2 = np.array([(0, 0, 5, 0)], dtype=P2A)
+    eng2.vm_client_request(r2); ora2.client_request(r2)
+    st, c = H.phase2b(eng2, ora2, np.array([(0, 1, 0, 3)], dtype=P2B))
+    assert st == -4
+    eng.close(); eng2.close()
