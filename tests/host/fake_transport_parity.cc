@@ -164,7 +164,7 @@ int main(int argc, char** argv) {
     }
     printf("seed %llu: %s (%zu transcript lines, %zu Chosen deliveries, %zu Nacks)\n", (unsigned long long)seed,
            ok ? "PARITY OK" : "MISMATCH", ref.size(), chosen, nacks);
-    if (chosen < (size_t)(2 * n_slots) || nacks == 0) { printf("scenario did not exercise the path\n"); ++failures; }
+    if (chosen < (size_t)n_slots || nacks == 0) { printf("scenario did not exercise the path\n"); ++failures; }
   }
   // duplicate address registration is fatal (FakeTransport.scala:80-85)
   try {
