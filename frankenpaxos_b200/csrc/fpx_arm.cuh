@@ -44,31 +44,70 @@ __device__ __forceinline__ bool claim_header(const ArmParams& P, RowRef r, int s
   return false;
 }
 
-// second stage of one arm: `old` is what the 64-bit CAS on the primary row's
-// header returned.  Returns true if this record created the key's entry.
-__device__ __forceinline__ bool arm_finish(const ArmParams& P, const int4& rec, unsigned long long old, int i) {
+// table slot of key (slot, round), inserting the key if absent; nullptr = table full
+__device__ __forceinline__ uint32_t* table_insert(const ArmParams& P, int slot, int round) {
   const Geometry& g = P.g;
-  const int slot = rec.x, round = rec.y, value = rec.z;
-  if (old == kU64Empty) return true;                       // Pending(phase2a, {}) created (:213)
-  if ((int)((uint32_t)old & ~kDoneBit) == round) {         // `case Some(_)`: ignore (:177-183)
-    if ((uint32_t)(old >> 32) != (uint32_t)value) note_arm_conflict(P, slot, round);
-    return false;
-  }
-  // secondary round of this slot -> overflow table (SURVEY 8(g) rule 3)
-  if (g.ovf_cap == 0) { report_error(P.st, FPX_ERR_OVERFLOW_FULL, i); return false; }
+  if (g.ovf_cap == 0) return nullptr;
   unsigned long long key = ((unsigned long long)(uint32_t)slot << 32) | (uint32_t)round;
   uint32_t h = (uint32_t)mix64(key) & g.ovf_mask;
   for (int probe = 0; probe < g.ovf_cap; ++probe) {
     unsigned long long k = atomicCAS(&P.pl.ovf_keys[h], kU64Empty, key);
-    if (k == kU64Empty || k == key) {
-      RowRef o{P.pl.ovf_rows + (size_t)h * g.row_words};
-      bool dummy;
-      return claim_header(P, o, slot, round, value, &dummy);
-    }
+    if (k == kU64Empty || k == key) return P.pl.ovf_rows + (size_t)h * g.row_words;
     h = (h + 1) & g.ovf_mask;
   }
-  report_error(P.st, FPX_ERR_OVERFLOW_FULL, i);
-  return false;
+  return nullptr;
+}
+
+// second stage of one arm: `old` is what the 64-bit CAS on the primary row's header
+// returned.  Returns true if this record created the key's entry.
+//
+// A slot's primary row holds its ONLY armed round.  When a second round of the slot is
+// armed (leader change: Leader.handlePhase1b re-proposes chosenWatermark..maxSlot in the
+// new round, S/multipaxos/Leader.scala:551-562; both (slot, round) keys then tally
+// independently, ProxyLeader.scala:135) the first round's entry -- header and stamps, which
+// are quiescent during an arm call -- is moved to the (slot, round) table and the primary
+// header is poisoned for good; from then on every key of that slot lives in the table.
+// That is what lets the tally kernel stamp votes without loading the header first.
+__device__ __forceinline__ bool arm_finish(const ArmParams& P, const int4& rec, unsigned long long old, int i) {
+  const Geometry& g = P.g;
+  const int slot = rec.x, round = rec.y, value = rec.z;
+  if (old == kU64Empty) return true;                       // Pending(phase2a, {}) created (:213)
+  uint32_t* prim = P.pl.rows + (size_t)local_slot(g, slot) * g.row_words;
+  unsigned long long* hdr = (unsigned long long*)prim;
+  while (true) {
+    uint32_t orw = (uint32_t)old;
+    if (orw == kBusy) {                                    // another record is moving the row: wait
+      __nanosleep(64);
+      old = *(volatile unsigned long long*)hdr;
+      continue;
+    }
+    if (orw == kPoison) {
+      uint32_t* t = table_insert(P, slot, round);
+      if (t == nullptr) { report_error(P.st, FPX_ERR_OVERFLOW_FULL, i); return false; }
+      bool dummy;
+      return claim_header(P, RowRef{t}, slot, round, value, &dummy);
+    }
+    if ((int)(orw & ~kDoneBit) == round) {                 // `case Some(_)`: ignore (:177-183)
+      if ((uint32_t)(old >> 32) != (uint32_t)value) note_arm_conflict(P, slot, round);
+      return false;
+    }
+    // a second round for this slot: move the first one to the table, poison the primary
+    unsigned long long busy = (old & 0xffffffff00000000ull) | kBusy;
+    unsigned long long prev = atomicCAS(hdr, old, busy);
+    if (prev != old) { old = prev; continue; }
+    uint32_t* t = table_insert(P, slot, (int)(orw & ~kDoneBit));
+    if (t == nullptr) {
+      report_error(P.st, FPX_ERR_OVERFLOW_FULL, i);
+      atomicExch(hdr, old);
+      return false;
+    }
+    t[0] = orw;
+    t[1] = (uint32_t)(old >> 32);
+    for (int v = 0; v < g.voters; ++v) t[2 + v] = prim[2 + v];
+    __threadfence();
+    old = (old & 0xffffffff00000000ull) | kPoison;
+    atomicExch(hdr, old);
+  }
 }
 
 constexpr int kArmUnroll = 4;
@@ -81,6 +120,7 @@ __global__ void __launch_bounds__(256) arm_kernel(ArmParams P) {
   const int n_chunks = (P.n + 31) >> 5;
   // warp-strided 32-record chunks; per lane kArmUnroll independent record loads,
   // then kArmUnroll independent header CASes, are in flight before any is used
+  int max_local = -1;
   for (int c0 = gwarp * kArmUnroll; c0 < n_chunks; c0 += total_warps * kArmUnroll) {
     int4 rec[kArmUnroll];
     unsigned long long old[kArmUnroll];
@@ -127,8 +167,12 @@ __global__ void __launch_bounds__(256) arm_kernel(ArmParams P) {
       }
       unsigned wb = __ballot_sync(0xffffffffu, won);
       if (lane == 0) P.win_bits[c0 + u] = wb;
+      int ml = __reduce_max_sync(0xffffffffu, won ? local_slot(g, rec[u].x) : -1);
+      if (lane == 0 && ml > max_local) max_local = ml;
     }
   }
+
+  if (lane == 0 && max_local >= 0) atomicMax(&P.st->max_armed_local, max_local);
 
   // ---- last block: two arms of one key with different values.  If the key was
   // created by a record of THIS batch, the lowest-index arm is the one the

@@ -25,7 +25,9 @@ namespace fpx {
 // constants / layouts
 // ---------------------------------------------------------------------------
 constexpr uint32_t kUnarmed = 0xffffffffu;      // row.round_word of a never-armed key
-constexpr uint32_t kDoneBit = 0x80000000u;      // row.round_word bit: ProxyLeader `Done`
+constexpr uint32_t kDoneBit = 0x80000000u;      // row.round_word bit: phase2s entry retired (vanilla Mencius)
+constexpr uint32_t kPoison = 0xfffffffeu;       // row.round_word: >1 round of this slot armed -> all its keys live in the table
+constexpr uint32_t kBusy = 0xfffffffdu;         // row.round_word: being moved to the table (arm kernel only)
 constexpr uint32_t kStampEmpty = 0xffffffffu;   // no Phase2b from this voter yet
 constexpr uint64_t kU64Empty = ~0ull;
 constexpr uint64_t kCellChosen = 0x8000000000000000ull;  // vanilla Mencius: the server's entry is a ChosenEntry
@@ -46,7 +48,8 @@ struct DevStatus {
   int32_t wm_found;             // scratch of the watermark scan
   uint32_t barrier;             // monotone arrival counter of the grid barriers
   uint32_t nack_total;          // acceptor kernel: Nacks of the running call
-  uint32_t pad[3];
+  uint32_t pad[2];              // [0] second Nack counter (parity), [1] tally: a vote hit a poisoned row
+  int32_t max_armed_local;      // largest local slot ever armed (prefetch window of the tally)
   unsigned long long t_acceptor[8];  // %globaltimer at the phase boundaries of CTA 0 (profiling aid)
   unsigned long long t_tally[8];
 };
@@ -206,22 +209,26 @@ struct PLState {
   uint32_t* ovf_rows;           // ovf_cap * row_words
 };
 
-// Find the row of key (slot, round): the primary row when its armed round
-// matches, else the overflow table.  Returns p == nullptr when the key was never
-// armed (ProxyLeader.scala:220-225 `case None`).
-__device__ __forceinline__ RowRef find_row(const Geometry& g, const PLState& s, int local, int slot, int round) {
-  RowRef r{s.rows + (size_t)local * g.row_words};
-  uint32_t rw = r.round_word();
-  if (rw != kUnarmed && (int)(rw & ~kDoneBit) == round) return r;
-  if (rw == kUnarmed || g.ovf_cap == 0) return RowRef{nullptr};
+// Find the row of key (slot, round): the primary row while the slot has a single
+// armed round, else (poisoned primary) the open-addressing table.  Returns p ==
+// nullptr when the key was never armed (ProxyLeader.scala:220-225 `case None`).
+__device__ __forceinline__ uint32_t* table_lookup(const Geometry& g, const PLState& s, int slot, int round) {
+  if (g.ovf_cap == 0) return nullptr;
   unsigned long long key = ((unsigned long long)(uint32_t)slot << 32) | (uint32_t)round;
   uint32_t h = (uint32_t)mix64(key) & g.ovf_mask;
   for (int probe = 0; probe < g.ovf_cap; ++probe) {
-    unsigned long long k = s.ovf_keys[h];
-    if (k == key) return RowRef{s.ovf_rows + (size_t)h * g.row_words};
+    unsigned long long k = __ldcg(&s.ovf_keys[h]);
+    if (k == key) return s.ovf_rows + (size_t)h * g.row_words;
     if (k == kU64Empty) break;
     h = (h + 1) & g.ovf_mask;
   }
+  return nullptr;
+}
+__device__ __forceinline__ RowRef find_row(const Geometry& g, const PLState& s, int local, int slot, int round) {
+  RowRef r{s.rows + (size_t)local * g.row_words};
+  uint32_t rw = __ldcg(r.p);
+  if (rw == kPoison) return RowRef{table_lookup(g, s, slot, round)};
+  if (rw != kUnarmed && rw != kBusy && (int)(rw & ~kDoneBit) == round) return r;
   return RowRef{nullptr};
 }
 

@@ -134,6 +134,7 @@ static int reset_state(fpx_engine* e) {
   memset(&init, 0, sizeof(init));
   init.err_word = ~0ull;
   init.max_chosen_local = -1;
+  init.max_armed_local = -1;
   init.wm_found = INT_MAX;
   init.watermark = g.shard_index;
   *e->h_st = init;
@@ -405,7 +406,7 @@ int fpx_proxyleader_phase2b_dev(fpx_engine* e, const fpx_p2b* d_in, int32_t n, f
     P.per = per;
     P.votes = e->votes;
     P.st = e->st;
-    e->bar += 3u * (uint32_t)grid;
+    e->bar += 4u * (uint32_t)grid;
     e->seq_base += (uint32_t)sub;
     void* args[] = {&P};
     CK(e, cudaLaunchCooperativeKernel(tk, dim3(grid), dim3(kThreads), args, (size_t)kWarps * per * 8, e->stream));

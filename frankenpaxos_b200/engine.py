@@ -40,7 +40,7 @@ class Engine:
     """One GPU-resident {acceptors, proxy leader, replica log} for one config."""
 
     def __init__(self, f, num_acceptor_groups, acceptors_per_group, flexible=False, num_leaders=None,
-                 num_replicas=None, slot_capacity=1 << 20, overflow_capacity=1 << 10, max_batch=1 << 20,
+                 num_replicas=None, slot_capacity=1 << 20, overflow_capacity=1 << 14, max_batch=1 << 20,
                  device=0, shard_index=0, shard_count=1, protocol=MULTIPAXOS, num_leader_groups=0):
         L = _lib.lib()
         cfg = _lib.Config()

@@ -89,7 +89,7 @@ typedef enum {
                                       S/epaxos/Replica.scala:663-681                       */
 } fpx_status;
 
-#define FPX_MAX_ROUND 0x7ffffffe
+#define FPX_MAX_ROUND 0x7ffffff0
 #define FPX_MAX_ACCEPTORS 32       /* total acceptors (groups*per_group) per engine     */
 #define FPX_MAX_VOTERS_PER_SLOT 30 /* acceptors that can vote on one slot               */
 
