@@ -433,7 +433,7 @@ static int replica_launch(fpx_engine* e, const fpx_chosen* d_in, int32_t n, int3
   P.rlog = e->rlog;
   P.st = e->st;
   e->rseq_base += (uint32_t)bound;
-  int blocks = std::min((bound + 255) / 256, 148 * 8);
+  int blocks = std::max(1, std::min((bound + 256 * kReplicaUnroll - 1) / (256 * kReplicaUnroll), e->num_sms * 8));
   replica_chosen_kernel<<<blocks, 256, 0, e->stream>>>(P);
   e->launches++;
   CK(e, cudaGetLastError());
@@ -453,9 +453,8 @@ int fpx_replica_chosen_last_dev(fpx_engine* e, const fpx_chosen* d_in) {
 
 int fpx_chosen_watermark_dev(fpx_engine* e, int32_t* d_out) {
   if (!e) return FPX_ERR_INVALID_ARG;
-  watermark_scan_kernel<<<148 * 4, 256, 0, e->stream>>>(e->g, e->rlog, e->st);
-  watermark_finish_kernel<<<1, 1, 0, e->stream>>>(e->g, e->st, d_out);
-  e->launches += 2;
+  watermark_scan_kernel<<<e->num_sms * 4, 256, 0, e->stream>>>(e->g, e->rlog, e->st, d_out);
+  e->launches += 1;
   CK(e, cudaGetLastError());
   return FPX_OK;
 }

@@ -30,39 +30,75 @@ struct ReplicaParams {
   DevStatus* st;
 };
 
+constexpr int kReplicaUnroll = 4;
+
 __global__ void __launch_bounds__(256) replica_chosen_kernel(ReplicaParams P) {
   const Geometry& g = P.g;
-  int n = P.n >= 0 ? P.n : P.st->n_chosen;
+  __shared__ int s_mx[8];
+  const int n = P.n >= 0 ? P.n : __ldcg(&P.st->n_chosen);
+  const int stride = gridDim.x * blockDim.x;
   int mx = INT_MIN;
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-    int2 rec = P.in[i];
-    int local = local_slot(g, rec.x);
-    if (local < 0) { report_error(P.st, FPX_ERR_SLOT_RANGE, i); continue; }
-    unsigned long long w = ((unsigned long long)(P.seq_base + (uint32_t)i) << 32) | (uint32_t)rec.y;
-    atomicMin(&P.rlog[local], w);
-    mx = max(mx, local);
+  // kReplicaUnroll independent records (and their atomics) in flight per thread
+  for (int i0 = blockIdx.x * blockDim.x + threadIdx.x; i0 < n; i0 += stride * kReplicaUnroll) {
+    int2 rec[kReplicaUnroll];
+#pragma unroll
+    for (int u = 0; u < kReplicaUnroll; ++u) {
+      int i = i0 + u * stride;
+      rec[u] = i < n ? __ldcg(P.in + i) : make_int2(-1, 0);
+    }
+#pragma unroll
+    for (int u = 0; u < kReplicaUnroll; ++u) {
+      int i = i0 + u * stride;
+      if (i >= n) break;
+      int local = local_slot(g, rec[u].x);
+      if (local < 0) { report_error(P.st, FPX_ERR_SLOT_RANGE, i); continue; }
+      // first Chosen per slot wins (Replica.scala:580-588): min over (delivery seq : value)
+      atomicMin(&P.rlog[local], ((unsigned long long)(P.seq_base + (uint32_t)i) << 32) | (uint32_t)rec[u].y);
+      mx = max(mx, local);
+    }
   }
   mx = __reduce_max_sync(0xffffffffu, mx);
-  if ((threadIdx.x & 31) == 0 && mx != INT_MIN) atomicMax(&P.st->max_chosen_local, mx);
-}
-
-__global__ void __launch_bounds__(256) watermark_scan_kernel(Geometry g, const unsigned long long* rlog,
-                                                            DevStatus* st) {
-  int lo = st->wm_local;
-  int hi = min(st->max_chosen_local + 2, g.local_slots);  // one past the last candidate hole
-  for (int i = lo + blockIdx.x * blockDim.x + threadIdx.x; i < hi; i += gridDim.x * blockDim.x) {
-    if (i >= *(volatile int*)&st->wm_found) break;
-    if (rlog[i] == kU64Empty) { atomicMin(&st->wm_found, i); break; }
+  if ((threadIdx.x & 31) == 0) s_mx[threadIdx.x >> 5] = mx;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int w = 1; w < 8; ++w) mx = max(mx, s_mx[w]);
+    if (mx != INT_MIN) atomicMax(&P.st->max_chosen_local, mx);   // one same-address atomic per CTA
   }
 }
-__global__ void watermark_finish_kernel(Geometry g, DevStatus* st, int32_t* d_out) {
-  int hi = min(st->max_chosen_local + 2, g.local_slots);
-  int found = min(st->wm_found, hi);
-  found = max(found, st->wm_local);
-  if (found > g.local_slots) found = g.local_slots;
-  st->wm_local = found;
+
+// executeLog's prefix rule (Replica.scala:394-402): the first hole at or after the
+// watermark.  Coalesced scan of the replica log over [watermark, last chosen + 2); the
+// last CTA to finish publishes the result.
+__global__ void __launch_bounds__(256) watermark_scan_kernel(Geometry g, const unsigned long long* rlog,
+                                                            DevStatus* st, int32_t* d_out) {
+  __shared__ int s_found[8];
+  __shared__ bool s_last;
+  const int lo = __ldcg(&st->wm_local);
+  const int hi = min(__ldcg(&st->max_chosen_local) + 2, g.local_slots);  // one past the last candidate hole
+  int found = INT_MAX;
+  for (int i = lo + blockIdx.x * blockDim.x + threadIdx.x; i < hi && found == INT_MAX; i += gridDim.x * blockDim.x)
+    if (__ldcg(&rlog[i]) == kU64Empty) found = i;
+  found = __reduce_min_sync(0xffffffffu, found);
+  if ((threadIdx.x & 31) == 0) s_found[threadIdx.x >> 5] = found;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int w = 1; w < 8; ++w) found = min(found, s_found[w]);
+    if (found != INT_MAX) atomicMin(&st->wm_found, found);
+    __threadfence();
+    s_last = (atomicAdd(&st->ticket, 1u) == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (!s_last || threadIdx.x != 0) return;
+  __threadfence();
+  int f = min(*(volatile int*)&st->wm_found, hi);
+  f = max(f, lo);
+  if (f > g.local_slots) f = g.local_slots;
+  st->wm_local = f;
   st->wm_found = INT_MAX;
-  int global = found * g.shard_count + g.shard_index;
+  st->ticket = 0;
+  int global = f * g.shard_count + g.shard_index;
   st->watermark = global;
   if (d_out) *d_out = global;
 }
