@@ -52,6 +52,17 @@ def parse():
     return ap.parse_args()
 
 
+def ncu_traffic(kernel):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of `kernel`, from the
+    committed ncu --set full capture (profiles/r1_traffic.json); None if absent."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "r1_traffic.json")) as f:
+            k = json.load(f)[kernel]
+        return int(k["dram_bytes_read"] + k["dram_bytes_write"])
+    except Exception:
+        return None
+
+
 def peaks():
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
@@ -374,11 +385,13 @@ def main():
                                                         "step (inputs+state touched per step 196 MB > L2)",
                        "bytes_per_slot_algorithmic": B_SLOT},
             "roofline": {"bound": "hbm", "kernel": "acceptor_phase2a_kernel", "achieved": acc_gbs, "peak": peak,
-                         "unit": "GB/s", "frac": acc_gbs / peak, "traffic": None,
+                         "unit": "GB/s", "frac": acc_gbs / peak, "traffic": ncu_traffic("acceptor_phase2a_kernel"),
                          "algorithmic_bytes_per_launch": B_ACCEPTOR * SLOTS_PER_STEP, "ms_per_launch": acc_ms,
                          "peak_source": peak_src},
             "kernels": {"acceptor_phase2a": {"ms": acc_ms, "GB/s": acc_gbs, "frac": acc_gbs / peak},
-                        "tally_stamp+complete": {"ms": tally_ms, "GB/s": tally_gbs, "frac": tally_gbs / peak},
+                        "tally_kernel": {"ms": tally_ms, "GB/s": tally_gbs, "frac": tally_gbs / peak,
+                                         "algorithmic_bytes_per_launch": B_TALLY * SLOTS_PER_STEP,
+                                         "traffic": ncu_traffic("tally_kernel")},
                         "whole_step_GB/s": B_SLOT * SLOTS_PER_STEP / (ms_max / K * 1e-3) / 1e9},
             "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
         }
