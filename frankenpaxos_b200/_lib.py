@@ -18,6 +18,7 @@ SYMBOLS = [
     "fpx_proxyleader_arm_dev", "fpx_acceptor_phase2a_dev", "fpx_proxyleader_phase2b_dev",
     "fpx_replica_chosen_dev", "fpx_replica_chosen_last_dev", "fpx_chosen_watermark_dev", "fpx_sync",
     "fpx_stream", "fpx_launch_count",
+    "fpx_acceptor_phase1a", "fpx_leader_safe_values",
     "fpx_vm_client_request", "fpx_vm_phase2a", "fpx_vm_learn_chosen",
     "fpx_epaxos_create", "fpx_epaxos_destroy", "fpx_epaxos_lead", "fpx_epaxos_preaccept", "fpx_epaxos_accept",
     "fpx_epaxos_preacceptok", "fpx_epaxos_acceptok", "fpx_epaxos_entry", "fpx_depset_union",
@@ -75,6 +76,8 @@ def lib():
     L.fpx_replica_chosen_dev.argtypes = [vp, vp, i32]; L.fpx_replica_chosen_dev.restype = i32
     L.fpx_replica_chosen_last_dev.argtypes = [vp, vp]; L.fpx_replica_chosen_last_dev.restype = i32
     L.fpx_chosen_watermark_dev.argtypes = [vp, vp]; L.fpx_chosen_watermark_dev.restype = i32
+    L.fpx_acceptor_phase1a.argtypes = [vp, i32, i32, i32, p(i32)]; L.fpx_acceptor_phase1a.restype = i32
+    L.fpx_leader_safe_values.argtypes = [vp, C.c_uint32, i32, i32, vp, vp, p(i32)]; L.fpx_leader_safe_values.restype = i32
     L.fpx_vm_client_request.argtypes = [vp, vp, i32, p(i64)]; L.fpx_vm_client_request.restype = i32
     L.fpx_vm_phase2a.argtypes = [vp, vp, i32, vp, p(i64)]; L.fpx_vm_phase2a.restype = i32
     L.fpx_vm_learn_chosen.argtypes = [vp, vp, i32, p(i64)]; L.fpx_vm_learn_chosen.restype = i32

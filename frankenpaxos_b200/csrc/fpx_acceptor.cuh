@@ -43,6 +43,7 @@ struct AcceptorParams {
   uint32_t* g_wacc;                // [grid*kWarps] accepted records per warp range
   uint32_t bar_base;               // st->barrier when this launch starts
   uint32_t parity;                 // which nack counter this launch uses
+  int32_t append;                  // 1: continue the reply streams of the previous launch (chunked host call)
   DevStatus* st;
   VoteConflict* conflicts;
 };
@@ -78,8 +79,9 @@ __device__ __noinline__ void acceptor_error(DevStatus* st, int code, int index) 
 // round as of the start of the warp's range.  s_mv is a [num_keys][kThreads]
 // table of per-thread private maxima of accepted slots (maxVotedSlot, :209).
 template <bool kExact>
-__device__ __forceinline__ void acceptor_apply(const AcceptorParams& P, int wlo, int whi, int lane, int run,
-                                               uint32_t pos_base, int* s_mv, uint32_t& wacc, uint32_t& wnack) {
+__device__ __forceinline__ void acceptor_apply(const AcceptorParams& P, int4* out_p2b, int2* out_nack, int wlo, int whi,
+                                               int lane, int run, uint32_t pos_base, int* s_mv, uint32_t& wacc,
+                                               uint32_t& wnack) {
   const Geometry& g = P.g;
   const unsigned full = 0xffffffffu;
   for (int base = wlo; base < whi; base += 32 * kAccUnroll) {
@@ -140,7 +142,7 @@ __device__ __forceinline__ void acceptor_apply(const AcceptorParams& P, int wlo,
         if (lane == 0) P.accept_bits[i0 >> 5] = b;
         if (accept) {
           // Phase2b(groupIndex, acceptorIndex, slot, round) (:211-219)
-          st_stream(P.out_p2b + i, make_int4(rec[u].w >> 16, rec[u].w & 0xffff, rec[u].x, r));
+          st_stream(out_p2b + i, make_int4(rec[u].w >> 16, rec[u].w & 0xffff, rec[u].x, r));
           // states(slot) = State(voteRound = round, voteValue) (:205-208)
           cell[u] = ((unsigned long long)(uint32_t)(r + 1) << 32) | (uint32_t)rec[u].z;
           old[u] = atomicMax(&P.votes[(size_t)loc * g.voters + vix], cell[u]);
@@ -151,12 +153,12 @@ __device__ __forceinline__ void acceptor_apply(const AcceptorParams& P, int wlo,
       } else {
         uint32_t before = pos_base + wacc + __popc(b & lanemask_lt());
         if (accept) {
-          st_stream(P.out_p2b + before, make_int4(rec[u].w >> 16, rec[u].w & 0xffff, rec[u].x, r));
+          st_stream(out_p2b + before, make_int4(rec[u].w >> 16, rec[u].w & 0xffff, rec[u].x, r));
         } else if (valid) {
           // Nack(round) to leaders(roundSystem.leader(phase2a.round)) (:197-198)
           int ldr = r % g.num_leaders;
           if (g.protocol == FPX_MENCIUS) ldr += (grp_of(rec[u].w) / g.agroups) * g.num_leaders;
-          st_stream2(P.out_nack + ((uint32_t)i - before), make_int2(ldr, cur));
+          st_stream2(out_nack + ((uint32_t)i - before), make_int2(ldr, cur));
         }
       }
       wacc += __popc(b);
@@ -192,6 +194,12 @@ __global__ void __launch_bounds__(kThreads) acceptor_phase2a_kernel(AcceptorPara
   uint32_t* nack_ctr = P.parity ? &P.st->nack_total : &P.st->pad[0];
   uint32_t* nack_other = P.parity ? &P.st->pad[0] : &P.st->nack_total;
   if (blockIdx.x == 0 && tid == 0) *nack_other = 0;  // the counter the NEXT launch uses
+  // reply-stream bases: 0, or where the previous launch of a chunked call stopped (read by
+  // every CTA before the first grid barrier; rewritten only after the second)
+  const uint32_t base_p2b = P.append ? (uint32_t)__ldcg(&P.st->n_p2b) : 0u;
+  const uint32_t base_nack = P.append ? (uint32_t)__ldcg(&P.st->n_nack) : 0u;
+  int4* const out_p2b = P.out_p2b + base_p2b;
+  int2* const out_nack = P.out_nack + base_nack;
   for (int k = 0; k < g.num_keys; ++k) s_mv[k * kThreads + tid] = INT_MIN;
   FPX_MARK(P.st->t_acceptor, 0);
 
@@ -265,7 +273,7 @@ __global__ void __launch_bounds__(kThreads) acceptor_phase2a_kernel(AcceptorPara
   FPX_MARK(P.st->t_acceptor, 3);
   // ---- pass 2: decisions + effects, replies at dense positions
   uint32_t wacc = 0, wnack = 0;
-  acceptor_apply<false>(P, wlo, whi, lane, run, 0u, s_mv, wacc, wnack);
+  acceptor_apply<false>(P, out_p2b, out_nack, wlo, whi, lane, run, 0u, s_mv, wacc, wnack);
   if (lane == 0) {
     __stcg(&P.g_wacc[gw], wacc);
     if (wnack) atomicAdd(nack_ctr, wnack);
@@ -292,17 +300,17 @@ __global__ void __launch_bounds__(kThreads) acceptor_phase2a_kernel(AcceptorPara
   }
   const uint32_t total_nacks = __ldcg(nack_ctr);
   if (total_nacks == 0) {
-    if (blockIdx.x == 0 && tid == 0) { P.st->n_p2b = P.n; P.st->n_nack = 0; }
+    if (blockIdx.x == 0 && tid == 0) { P.st->n_p2b = (int)base_p2b + P.n; P.st->n_nack = (int)base_nack; }
   } else {
     // ---- pass 3 (leader change only): exact, compacted reply streams
     uint32_t before = 0;
     for (int j = lane; j < gw; j += 32) before += __ldcg(&P.g_wacc[j]);
     before = __reduce_add_sync(full, before);
     uint32_t wacc2 = 0, wnack2 = 0;
-    acceptor_apply<true>(P, wlo, whi, lane, run, before, s_mv, wacc2, wnack2);
+    acceptor_apply<true>(P, out_p2b, out_nack, wlo, whi, lane, run, before, s_mv, wacc2, wnack2);
     if (gw == (int)gridDim.x * kWarps - 1 && lane == 0) {
-      P.st->n_p2b = (int)(before + wacc2);
-      P.st->n_nack = P.n - (int)(before + wacc2);
+      P.st->n_p2b = (int)(base_p2b + before + wacc2);
+      P.st->n_nack = (int)base_nack + P.n - (int)(before + wacc2);
     }
   }
 

@@ -25,10 +25,14 @@
 
 using namespace fpx;
 
+constexpr int kMaxEvents = 16;
+
 struct fpx_engine {
   fpx_config cfg;
   Geometry g;
   cudaStream_t stream = nullptr;
+  cudaStream_t h2d_stream = nullptr, d2h_stream = nullptr;  // copy engines of the chunk-pipelined host calls
+  cudaEvent_t ev[16] = {};
   // device state
   uint32_t* rows = nullptr;
   unsigned long long* ovf_keys = nullptr;
@@ -221,6 +225,9 @@ int fpx_create(fpx_engine** out, const fpx_config* cfg) {
   } while (0)
   CKC(cudaSetDevice(cfg->device));
   CKC(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
+  CKC(cudaStreamCreateWithFlags(&e->h2d_stream, cudaStreamNonBlocking));
+  CKC(cudaStreamCreateWithFlags(&e->d2h_stream, cudaStreamNonBlocking));
+  for (int i = 0; i < kMaxEvents; ++i) CKC(cudaEventCreateWithFlags(&e->ev[i], cudaEventDisableTiming));
   size_t mb = (size_t)cfg->max_batch;
   CKC(cudaMalloc(&e->rows, (size_t)g.local_slots * g.row_words * 4));
   if (g.ovf_cap) {
@@ -275,6 +282,9 @@ void fpx_destroy(fpx_engine* e) {
   cudaFree(e->bits); cudaFree(e->g_agg); cudaFree(e->g_wacc); cudaFree(e->g_ccnt); cudaFree(e->conflicts);
   cudaFree(e->d_in); cudaFree(e->d_out_a); cudaFree(e->d_out_b);
   if (e->h_st) cudaFreeHost(e->h_st);
+  for (int i = 0; i < kMaxEvents; ++i) if (e->ev[i]) cudaEventDestroy(e->ev[i]);
+  if (e->h2d_stream) cudaStreamDestroy(e->h2d_stream);
+  if (e->d2h_stream) cudaStreamDestroy(e->d2h_stream);
   if (e->stream) cudaStreamDestroy(e->stream);
   delete e;
 }
@@ -330,15 +340,22 @@ int fpx_proxyleader_arm_dev(fpx_engine* e, const fpx_p2a* d_in, int32_t n) {
   return arm_launch(e, d_in, n, 0);
 }
 
+static int acceptor_launch(fpx_engine* e, const fpx_p2a* d_in, int32_t n, fpx_p2b* d_out_p2b, fpx_nack* d_out_nack,
+                           int append, cudaStream_t stream);
+
 int fpx_acceptor_phase2a_dev(fpx_engine* e, const fpx_p2a* d_in, int32_t n, fpx_p2b* d_out_p2b,
                              fpx_nack* d_out_nack) {
+  return acceptor_launch(e, d_in, n, d_out_p2b, d_out_nack, 0, e ? e->stream : nullptr);
+}
+
+static int acceptor_launch(fpx_engine* e, const fpx_p2a* d_in, int32_t n, fpx_p2b* d_out_p2b, fpx_nack* d_out_nack,
+                           int append, cudaStream_t stream) {
   int c = check_n(e, d_in, n);
   if (c != FPX_OK) return c;
   if (n > 0 && (!d_out_p2b || !d_out_nack)) return FPX_ERR_INVALID_ARG;
   if (e->g.protocol == FPX_VANILLA_MENCIUS) return FPX_ERR_UNSUPPORTED;  // use fpx_vm_phase2a
   if (n == 0) {
-    e->h_st->n_p2b = e->h_st->n_nack = 0;
-    CK(e, cudaMemsetAsync(&e->st->n_p2b, 0, 8, e->stream));
+    if (!append) CK(e, cudaMemsetAsync(&e->st->n_p2b, 0, 8, stream));
     return FPX_OK;
   }
   AcceptorParams P;
@@ -358,11 +375,12 @@ int fpx_acceptor_phase2a_dev(fpx_engine* e, const fpx_p2a* d_in, int32_t n, fpx_
   int grid = std::max(1, std::min(e->grid_acceptor, (n + kThreads - 1) / kThreads));
   P.bar_base = e->bar;
   P.parity = e->parity;
+  P.append = append;
   e->bar += 2u * (uint32_t)grid;
   e->parity ^= 1u;
   void* args[] = {&P};
   CK(e, cudaLaunchCooperativeKernel((const void*)acceptor_phase2a_kernel, dim3(grid), dim3(kThreads), args,
-                                    (size_t)e->g.num_keys * kThreads * 4, e->stream));
+                                    (size_t)e->g.num_keys * kThreads * 4, stream));
   e->launches++;
   CK(e, cudaGetLastError());
   return FPX_OK;
@@ -509,18 +527,41 @@ int fpx_acceptor_phase2a(fpx_engine* e, const fpx_p2a* in, int32_t n, fpx_p2b* o
   if (c != FPX_OK || n == 0) return c;
   if (!out_p2b || !out_nack || !n_p2b || !n_nack) return FPX_ERR_INVALID_ARG;
   CK(e, cudaSetDevice(e->cfg.device));
-  CK(e, cudaMemcpyAsync(e->d_in, in, (size_t)n * 16, cudaMemcpyHostToDevice, e->stream));
-  c = fpx_acceptor_phase2a_dev(e, (const fpx_p2a*)e->d_in, n, (fpx_p2b*)e->d_out_a, (fpx_nack*)e->d_out_b);
-  if (c != FPX_OK) return c;
+  // A batch may be cut at any index without changing its meaning (each piece is a
+  // batch in delivery order), so the call is chunk-pipelined: H2D of chunk c+1 and
+  // D2H of chunk c-1's replies overlap the kernel of chunk c on three streams.  The
+  // replies of a chunk are copied back from their dense positions, which is where they
+  // are as long as no Nack has been produced; otherwise the exact streams are copied
+  // again at the end.
+  const int32_t chunk = 1 << 19;
+  int k = 0;
+  for (int32_t off = 0; off < n; off += chunk, ++k) {
+    int32_t len = std::min(chunk, n - off);
+    cudaEvent_t ev_in = e->ev[(2 * k) % kMaxEvents], ev_k = e->ev[(2 * k + 1) % kMaxEvents];
+    CK(e, cudaMemcpyAsync((char*)e->d_in + (size_t)off * 16, in + off, (size_t)len * 16, cudaMemcpyHostToDevice,
+                          e->h2d_stream));
+    CK(e, cudaEventRecord(ev_in, e->h2d_stream));
+    CK(e, cudaStreamWaitEvent(e->stream, ev_in, 0));
+    c = acceptor_launch(e, (const fpx_p2a*)e->d_in + off, len, (fpx_p2b*)e->d_out_a, (fpx_nack*)e->d_out_b, off > 0,
+                        e->stream);
+    if (c != FPX_OK) return c;
+    CK(e, cudaEventRecord(ev_k, e->stream));
+    CK(e, cudaStreamWaitEvent(e->d2h_stream, ev_k, 0));
+    CK(e, cudaMemcpyAsync(out_p2b + off, (char*)e->d_out_a + (size_t)off * 16, (size_t)len * 16, cudaMemcpyDeviceToHost,
+                          e->d2h_stream));
+  }
   fpx_sync_result r;
   c = fpx_sync(e, &r);
   if (err_index) *err_index = r.err_index;
+  CK(e, cudaStreamSynchronize(e->d2h_stream));
   if (c != FPX_OK) return c;
   *n_p2b = r.n_p2b;
   *n_nack = r.n_nack;
-  if (r.n_p2b) CK(e, cudaMemcpyAsync(out_p2b, e->d_out_a, (size_t)r.n_p2b * 16, cudaMemcpyDeviceToHost, e->stream));
-  if (r.n_nack) CK(e, cudaMemcpyAsync(out_nack, e->d_out_b, (size_t)r.n_nack * 8, cudaMemcpyDeviceToHost, e->stream));
-  CK(e, cudaStreamSynchronize(e->stream));
+  if (r.n_nack) {  // leader change in this batch: the dense copies are not the streams
+    if (r.n_p2b) CK(e, cudaMemcpyAsync(out_p2b, e->d_out_a, (size_t)r.n_p2b * 16, cudaMemcpyDeviceToHost, e->stream));
+    CK(e, cudaMemcpyAsync(out_nack, e->d_out_b, (size_t)r.n_nack * 8, cudaMemcpyDeviceToHost, e->stream));
+    CK(e, cudaStreamSynchronize(e->stream));
+  }
   return FPX_OK;
 }
 
@@ -664,6 +705,48 @@ int fpx_snapshot_acceptor(fpx_engine* e, int32_t group, int32_t acceptor, int32_
     cudaFree(d_v);
   }
   CK(e, cudaStreamSynchronize(e->stream));
+  return FPX_OK;
+}
+
+
+int fpx_acceptor_phase1a(fpx_engine* e, int32_t group, int32_t acceptor, int32_t round, int32_t* nack_round) {
+  if (!e || !nack_round || group < 0 || group >= e->g.groups || acceptor < 0 || acceptor >= e->g.per_group)
+    return FPX_ERR_INVALID_ARG;
+  if (round < 0 || round > FPX_MAX_ROUND) return FPX_ERR_ROUND_RANGE;
+  CK(e, cudaSetDevice(e->cfg.device));
+  int key = group * e->g.per_group + acceptor;
+  int32_t cur = 0;
+  CK(e, cudaMemcpyAsync(&cur, e->acc_round + key, 4, cudaMemcpyDeviceToHost, e->stream));
+  CK(e, cudaStreamSynchronize(e->stream));
+  if (round < cur) {            // Nack(round = round), Acceptor.scala:156-163
+    *nack_round = cur;
+    return FPX_OK;
+  }
+  *nack_round = -1;             // round = phase1a.round (:166)
+  CK(e, cudaMemcpyAsync(e->acc_round + key, &round, 4, cudaMemcpyHostToDevice, e->stream));
+  CK(e, cudaStreamSynchronize(e->stream));
+  return FPX_OK;
+}
+
+int fpx_leader_safe_values(fpx_engine* e, uint32_t responders, int32_t first_slot, int32_t n_slots,
+                           int32_t* vote_round, int32_t* value_id, int32_t* max_slot) {
+  if (!e || n_slots < 0 || (n_slots > 0 && (!vote_round || !value_id)) || !max_slot) return FPX_ERR_INVALID_ARG;
+  *max_slot = -1;
+  if (n_slots == 0) return FPX_OK;
+  CK(e, cudaSetDevice(e->cfg.device));
+  int32_t *d_r = nullptr, *d_v = nullptr, *d_m = nullptr;
+  CK(e, cudaMalloc(&d_r, (size_t)n_slots * 4));
+  CK(e, cudaMalloc(&d_v, (size_t)n_slots * 4));
+  CK(e, cudaMalloc(&d_m, 4));
+  CK(e, cudaMemsetAsync(d_m, 0xff, 4, e->stream));
+  safe_values_kernel<<<(n_slots + 255) / 256, 256, 0, e->stream>>>(e->g, e->votes, responders, first_slot, n_slots,
+                                                                    d_r, d_v, d_m);
+  e->launches++;
+  CK(e, cudaMemcpyAsync(vote_round, d_r, (size_t)n_slots * 4, cudaMemcpyDeviceToHost, e->stream));
+  CK(e, cudaMemcpyAsync(value_id, d_v, (size_t)n_slots * 4, cudaMemcpyDeviceToHost, e->stream));
+  CK(e, cudaMemcpyAsync(max_slot, d_m, 4, cudaMemcpyDeviceToHost, e->stream));
+  CK(e, cudaStreamSynchronize(e->stream));
+  cudaFree(d_r); cudaFree(d_v); cudaFree(d_m);
   return FPX_OK;
 }
 

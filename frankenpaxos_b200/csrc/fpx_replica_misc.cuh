@@ -149,6 +149,37 @@ __global__ void snapshot_votes_kernel(Geometry g, const unsigned long long* vote
   vote_round[i] = vr;
   vote_value[i] = vv;
 }
+// Leader.safeValue over a Phase-1 quorum (S/multipaxos/Leader.scala:318-329): coalesced
+// sweep of the flat slot x voter cell array, arg-max of voteRound per slot over the
+// responders' cells (64-bit max of {voteRound+1, value}); warp redux for maxPhase1bSlot.
+__global__ void __launch_bounds__(256) safe_values_kernel(Geometry g, const unsigned long long* votes,
+                                                         uint32_t responders, int first_slot, int n_slots,
+                                                         int32_t* vote_round, int32_t* value, int32_t* d_max_slot) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  int best_slot = -1;
+  if (i < n_slots) {
+    int slot = first_slot + i;
+    int l = local_slot(g, slot);
+    unsigned long long m = 0;
+    if (l >= 0) {
+      int grp = expected_group(g, slot);
+      for (int v = 0; v < g.voters; ++v) {
+        int gid = g.flexible ? v : grp * g.per_group + v;   // global acceptor id of voter v of this slot
+        if (!((responders >> gid) & 1u)) continue;
+        unsigned long long c = __ldcg(&votes[(size_t)l * g.voters + v]);
+        if (c & kCellChosen) continue;
+        m = max(m, c);
+      }
+    }
+    bool any = (m >> 32) != 0;
+    vote_round[i] = any ? (int)(m >> 32) - 1 : -1;
+    value[i] = any ? (int)(uint32_t)m : -1;                // else Noop (:325)
+    if (any) best_slot = slot;
+  }
+  best_slot = __reduce_max_sync(0xffffffffu, best_slot);
+  if ((threadIdx.x & 31) == 0 && best_slot >= 0) atomicMax(d_max_slot, best_slot);
+}
+
 __global__ void snapshot_log_kernel(Geometry g, const unsigned long long* rlog, int first_slot, int n_slots,
                                     int32_t* value) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;

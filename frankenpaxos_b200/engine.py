@@ -158,6 +158,26 @@ class Engine:
         self._check(self._L.fpx_snapshot_log(self.h, first_slot, n_slots, v.ctypes.data))
         return v[:n_slots]
 
+    # -- Phase 1 reads
+    def acceptor_phase1a(self, group, acceptor, round_, chosen_watermark=0):
+        """Acceptor.handlePhase1a: returns ('nack', acceptor_round) or ('phase1b', info) with info =
+        [(slot, voteRound, voteValue)] from chosen_watermark on, ascending slots."""
+        nack = C.c_int32(0)
+        self._check(self._L.fpx_acceptor_phase1a(self.h, group, acceptor, round_, C.byref(nack)))
+        if nack.value >= 0:
+            return "nack", nack.value
+        r, m, vr, vv = self.snapshot_acceptor(group, acceptor, chosen_watermark, max(0, self.snapshot_acceptor(group, acceptor)[1] + 1 - chosen_watermark))
+        keep = np.nonzero(vr >= 0)[0]
+        return "phase1b", [(int(chosen_watermark + i), int(vr[i]), int(vv[i])) for i in keep]
+
+    def leader_safe_values(self, responders, first_slot, n_slots):
+        vr = np.empty(max(n_slots, 1), dtype=np.int32)
+        vv = np.empty(max(n_slots, 1), dtype=np.int32)
+        mx = C.c_int32(-1)
+        self._check(self._L.fpx_leader_safe_values(self.h, responders, first_slot, n_slots, vr.ctypes.data,
+                                                   vv.ctypes.data, C.byref(mx)))
+        return vr[:n_slots], vv[:n_slots], mx.value
+
     # -- vanilla Mencius (protocol=VANILLA_MENCIUS)
     def vm_client_request(self, p2a):
         p2a = np.ascontiguousarray(p2a, dtype=P2A)

@@ -220,6 +220,25 @@ int fpx_snapshot_log(fpx_engine* e, int32_t first_slot, int32_t n_slots, int32_t
 
 
 
+
+/* ---- Phase 1 reads of the same state --------------
+ * Acceptor.handlePhase1a, S/multipaxos/Acceptor.scala:148-182: phase1a.round <
+ * round -> Nack(round): *nack_round = the acceptor's round, state unchanged;
+ * else round = phase1a.round, *nack_round = -1, and the Phase1b's `info` is the
+ * acceptor's votes from chosenWatermark on (:171-179), i.e. fpx_snapshot_acceptor
+ * over [chosen_watermark, maxVotedSlot] with the voteRound = -1 slots dropped.
+ * Not batched with Phase2a traffic: SURVEY 8(g) rule 2 makes it a batch boundary. */
+int fpx_acceptor_phase1a(fpx_engine* e, int32_t group, int32_t acceptor, int32_t round, int32_t* nack_round);
+
+/* Leader.handlePhase1b's fill-in, S/multipaxos/Leader.scala:318-329,536-562: for the
+ * n_slots slots from first_slot, the vote with the highest voteRound among the
+ * acceptors that answered Phase 1 (responders: bit group*acceptors_per_group+index)
+ * and may vote on the slot -- safeValue -- or vote_round = -1 / value_id = -1 where
+ * none voted (Noop is safe).  *max_slot = the largest slot with a vote among the
+ * responders (maxPhase1bSlot, :303-312), -1 if none. */
+int fpx_leader_safe_values(fpx_engine* e, uint32_t responders, int32_t first_slot, int32_t n_slots,
+                           int32_t* vote_round, int32_t* value_id, int32_t* max_slot);
+
 /* ---- Vanilla Mencius (S/vanillamencius/Server.scala), protocol FPX_VANILLA_MENCIUS ----
  * n = 2f+1 servers (acceptors_per_group = n, num_acceptor_groups = 1), every
  * server is proposer + acceptor, server s coordinates the slots with slot % n ==

@@ -538,6 +538,34 @@ struct MultiPaxos {
     return kOk;
   }
 
+  // Acceptor.handlePhase1a, S/multipaxos/Acceptor.scala:148-182.  Returns the Nack round or -1.
+  int phase1a(int g, int a, int round) {
+    Acceptor& acc = acceptors[g][a];
+    if (round < acc.round) return acc.round;                  // :156-163
+    acc.round = round;                                        // :166
+    return -1;
+  }
+  // Leader.safeValue over the responders' Phase1b infos (Leader.scala:318-329); ties in
+  // voteRound (impossible between correct acceptors) resolve to the larger value id.
+  void safe_values(uint32_t responders, int first_slot, int n_slots, int* vote_round, int* value, int* max_slot) {
+    *max_slot = -1;
+    for (int i = 0; i < n_slots; ++i) {
+      int slot = first_slot + i;
+      std::pair<int, int> best(-1, -1);
+      for (int g = 0; g < cfg.groups; ++g) {
+        if (!cfg.flexible && g != slot % cfg.groups) continue;  // phase1bs(slot % numAcceptorGroups) (:553)
+        for (int a = 0; a < cfg.per_group; ++a) {
+          if (!((responders >> (g * cfg.per_group + a)) & 1u)) continue;
+          auto it = acceptors[g][a].states.find(slot);
+          if (it != acceptors[g][a].states.end()) best = std::max(best, it->second);
+        }
+      }
+      vote_round[i] = best.first;
+      value[i] = best.first < 0 ? -1 : best.second;
+      if (best.first >= 0) *max_slot = std::max(*max_slot, slot);
+    }
+  }
+
   // Replica.handleChosen + executeLog, S/multipaxos/Replica.scala:572-588, 394-402
   int replica_chosen(const Chosen* in, int n) {
     for (int i = 0; i < n; ++i) {
@@ -1001,6 +1029,10 @@ void fpo_mp_snapshot_acceptor(void* p, int g, int a, int* round, int* max_voted_
     vote_round[i] = it == acc.states.end() ? -1 : it->second.first;
     vote_value[i] = it == acc.states.end() ? -1 : it->second.second;
   }
+}
+int fpo_mp_phase1a(void* p, int g, int a, int round) { return ((MultiPaxos*)p)->phase1a(g, a, round); }
+void fpo_mp_safe_values(void* p, unsigned responders, int first_slot, int n_slots, int* vote_round, int* value, int* max_slot) {
+  ((MultiPaxos*)p)->safe_values(responders, first_slot, n_slots, vote_round, value, max_slot);
 }
 void fpo_mp_snapshot_log(void* p, int first_slot, int n_slots, int* value_id) {
   auto& log = ((MultiPaxos*)p)->log;

@@ -86,6 +86,8 @@ def lib():
         L.fpo_mp_executed_watermark.argtypes = [vp]; L.fpo_mp_executed_watermark.restype = i32
         L.fpo_mp_snapshot_acceptor.argtypes = [vp, i32, i32, ip, ip, i32, i32, vp, vp]
         L.fpo_mp_snapshot_log.argtypes = [vp, i32, i32, vp]
+        L.fpo_mp_phase1a.argtypes = [vp, i32, i32, i32]; L.fpo_mp_phase1a.restype = i32
+        L.fpo_mp_safe_values.argtypes = [vp, C.c_uint, i32, i32, vp, vp, ip]
         L.fpo_ep_new.argtypes = [i32, i32]; L.fpo_ep_new.restype = vp
         L.fpo_ep_free.argtypes = [vp]
         L.fpo_ep_lead.argtypes = [vp, i32, i32, i32, i32, i32, i32, vp, i32]; L.fpo_ep_lead.restype = i32
@@ -257,6 +259,15 @@ class MultiPaxos:
         lib().fpo_mp_snapshot_acceptor(self.h, group, acceptor, C.byref(r), C.byref(m), first_slot, n_slots,
                                        vr.ctypes.data, vv.ctypes.data)
         return r.value, m.value, vr[:n_slots], vv[:n_slots]
+
+    def phase1a(self, group, acceptor, round_):
+        return lib().fpo_mp_phase1a(self.h, group, acceptor, round_)
+
+    def safe_values(self, responders, first_slot, n_slots):
+        vr = np.zeros(max(n_slots, 1), dtype=np.int32); vv = np.zeros(max(n_slots, 1), dtype=np.int32)
+        mx = C.c_int(-1)
+        lib().fpo_mp_safe_values(self.h, responders, first_slot, n_slots, vr.ctypes.data, vv.ctypes.data, C.byref(mx))
+        return vr[:n_slots], vv[:n_slots], mx.value
 
     def snapshot_log(self, first_slot, n_slots):
         v = np.zeros(max(n_slots, 1), dtype=np.int32)

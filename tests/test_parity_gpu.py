@@ -488,3 +488,42 @@ def test_vanilla_mencius_matches_oracle(f):
     st, c = H.phase2b(eng2, ora2, np.array([(0, 1, 0, 3)], dtype=P2B))
     assert st == -4
     eng.close(); eng2.close()
+
+
+# --------------------------------------------------------------------------- Phase 1 reads
+@pytest.mark.parametrize("shape", ["majority5", "grid2x3", "groups3x3"])
+def test_phase1a_and_safe_values(shape):
+    """Acceptor.handlePhase1a (Acceptor.scala:148-182) and Leader.safeValue
+    (Leader.scala:318-329) over the same vote cells, after traffic in several rounds."""
+    if shape == "majority5":
+        cfg = dict(f=2, num_acceptor_groups=1, acceptors_per_group=5, flexible=False, num_leaders=3, num_replicas=3)
+    elif shape == "grid2x3":
+        cfg = dict(f=1, num_acceptor_groups=2, acceptors_per_group=3, flexible=True, num_leaders=2, num_replicas=2)
+    else:
+        cfg = dict(f=1, num_acceptor_groups=3, acceptors_per_group=3, flexible=False, num_leaders=2, num_replicas=2)
+    g = T.rng(len(shape))
+    n_slots = 3000
+    eng, ora = H.make_pair(cfg, n_slots, overflow_capacity=1 << 13)
+    for rnd in (0, 1, 3):
+        slots = np.sort(g.choice(n_slots, size=1200, replace=False)).astype(np.int32)
+        p = T.phase2as(g, slots, cfg["f"], cfg["num_acceptor_groups"], cfg["acceptors_per_group"], cfg["flexible"],
+                       rnd, slots * 4 + rnd)
+        H.phase2a(eng, ora, p[g.permutation(len(p))])
+    G, A = cfg["num_acceptor_groups"], cfg["acceptors_per_group"]
+    # a stale Phase1a is nacked with the acceptor's round; a fresh one raises it and reads the votes
+    kind, val = eng.acceptor_phase1a(0, 0, 1)
+    assert (kind, val) == ("nack", 3) and ora.phase1a(0, 0, 1) == 3
+    for gi in range(G):
+        for a in range(A):
+            assert ora.phase1a(gi, a, 7) == -1
+            kind, info = eng.acceptor_phase1a(gi, a, 7, chosen_watermark=100)
+            assert kind == "phase1b"
+            r, m, vr, vv = ora.snapshot_acceptor(gi, a, 100, max(0, m_ := ora.snapshot_acceptor(gi, a, 0, 0)[1]) + 1 - 100)
+            exp = [(100 + i, int(vr[i]), int(vv[i])) for i in range(len(vr)) if vr[i] >= 0]
+            assert info == exp and r == 7
+    H.compare_acceptors(eng, ora, cfg, 0, n_slots)
+    for responders in (0b1, (1 << (G * A)) - 1, 0b101011 & ((1 << (G * A)) - 1), 0):
+        ev, evv, em = eng.leader_safe_values(responders, 50, 2500)
+        ov, ovv, om = ora.safe_values(responders, 50, 2500)
+        H.same(ev, ov, "safeValue voteRound"); H.same(evv, ovv, "safeValue value"); assert em == om
+    eng.close()
