@@ -69,46 +69,6 @@ def test_blocks(lines):
 
 
 # --------------------------------------------------------------------------- quorums
-def quorum_vectors(rel, ctor_re, kind):
-    lines = read(rel)
-    out = []
-    for name, lineno, body in test_blocks(lines):
-        members = None
-        loops = []  # stack of (vars, ranges, depth)
-        depth = 0
-        for ln, line in body:
-            m = re.search(ctor_re, line)
-            if m:
-                members = m.group(1)
-                continue
-            m = re.match(r"\s*for\s*\((.*)\)\s*\{", line)
-            if m:
-                gens = [g.strip() for g in m.group(1).split(";")]
-                vars_, ranges = [], []
-                for g in gens:
-                    mm = re.match(r"(\w+)\s*<-\s*(-?\d+)\s+to\s+(-?\d+)", g)
-                    vars_.append(mm.group(1))
-                    ranges.append(range(int(mm.group(2)), int(mm.group(3)) + 1))
-                loops.append((vars_, ranges))
-                continue
-            if line.strip() == "}" and loops:
-                loops.pop()
-                continue
-            m = re.search(r"qs\.(\w+)\(Set\((.*?)\)\)\s+shouldBe\s+(true|false)", line)
-            if m:
-                pred, elems, exp = m.group(1), m.group(2), m.group(3) == "true"
-                all_vars = [v for vs, _ in loops for v in vs]
-                all_ranges = [r for _, rs in loops for r in rs]
-                for combo in itertools.product(*all_ranges) if all_vars else [()]:
-                    env = dict(zip(all_vars, combo))
-                    xs = sorted(set(int(eval(e, {}, env)) for e in elems.split(",") if e.strip()))
-                    out.append({"pred": pred, "set": xs, "expect": exp, "line": ln})
-        out_members = members
-        if out:
-            yield name, out_members
-    return
-
-
 def parse_quorums():
     res = {}
     specs = [

@@ -527,3 +527,49 @@ def test_phase1a_and_safe_values(shape):
         ov, ovv, om = ora.safe_values(responders, 50, 2500)
         H.same(ev, ov, "safeValue voteRound"); H.same(evv, ovv, "safeValue value"); assert em == om
     eng.close()
+
+
+def test_full_size_properties_cfg3():
+    """BASELINE cfg3 at full size: 2x3 grid, 2^22 slots, thrifty write quorum = one grid
+    column (2 votes per slot), 10 proxy-leader partitions (slot % 10) shuffled within a
+    partition; 8.4M-record batches (two tally launches).  Size-independent properties."""
+    cfg, n_slots = T.config_by_name("cfg3")
+    eng = Engine(slot_capacity=n_slots, max_batch=2 * n_slots, **cfg)
+    a, p, b = T.workload(1, cfg, n_slots, partitions=10)
+    eng.proxyleader_arm(a)
+    pb, nk = eng.acceptor_phase2a(p)
+    assert len(nk) == 0 and np.array_equal(pb, T.votes_of(p))
+    c = eng.proxyleader_phase2b(b)
+    assert len(c) == n_slots
+    assert np.array_equal(np.sort(c["slot"]), np.arange(n_slots)) and np.array_equal(c["slot"], c["value_id"])
+    last = np.zeros(n_slots, dtype=np.int64)
+    np.maximum.at(last, b["slot"], np.arange(len(b)))
+    assert np.array_equal(c["slot"], b["slot"][np.sort(last)])   # Chosen order == order of the completing votes
+    eng.replica_chosen(c)
+    assert eng.chosen_watermark() == n_slots
+    # votes of one grid row only are never a write quorum (Grid.scala:49): re-run with row-0 votes only
+    eng.reset()
+    eng.proxyleader_arm(a[:100000])
+    row0 = b[(b["group"] == 0) & (b["slot"] < 100000)]
+    assert len(eng.proxyleader_phase2b(row0)) == 0
+    eng.close()
+
+
+def test_full_size_properties_cfg4_epaxos():
+    """BASELINE cfg4 shape at 2^18 instances per replica view (the generator is O(N) host
+    work): every led instance produces exactly one decision event; fast commits carry the
+    leader's deps when all answers agree; entries end Committed or Accepted."""
+    from frankenpaxos_b200.epaxos import EpaxosReplica
+    f, n, N = 2, 5, 1 << 15
+    lead, pa, ok = T.epaxos_cfg4(3, f=f, n_instances=N, me=0)
+    eng = EpaxosReplica(f, 0, N // n + 2, max_batch=1 << 17)
+    eng.lead(lead)
+    rep = eng.preaccept(pa)
+    assert (rep[:, 0] == 1).all()
+    # reply deps = elementwise max(local, msg)
+    assert np.array_equal(rep[:, 4:], np.maximum(pa[:, 6:6 + n], pa[:, 6 + n:]))
+    ev = eng.preacceptok(ok)
+    decided = ev[(ev[:, 0] == 1) | (ev[:, 0] == 2)]
+    assert len(decided) == len(lead)
+    assert (ev[:, 0] == 3).sum() == len(lead)          # one timer event per instance (f+1 < n-1)
+    eng.close()
