@@ -84,6 +84,9 @@ __device__ __forceinline__ void acceptor_apply(const AcceptorParams& P, int4* ou
                                                uint32_t& wnack) {
   const Geometry& g = P.g;
   const unsigned full = 0xffffffffu;
+  // the reply stream is write-once: evict_first gets it written back while this kernel
+  // still runs instead of during the next kernel's reads
+  const unsigned long long pol_out = l2_policy_evict_first();
   for (int base = wlo; base < whi; base += 32 * kAccUnroll) {
     int4 rec[kAccUnroll];
     unsigned long long cell[kAccUnroll], old[kAccUnroll];
@@ -142,7 +145,7 @@ __device__ __forceinline__ void acceptor_apply(const AcceptorParams& P, int4* ou
         if (lane == 0) P.accept_bits[i0 >> 5] = b;
         if (accept) {
           // Phase2b(groupIndex, acceptorIndex, slot, round) (:211-219)
-          st_stream(out_p2b + i, make_int4(rec[u].w >> 16, rec[u].w & 0xffff, rec[u].x, r));
+          st_evict_first(out_p2b + i, make_int4(rec[u].w >> 16, rec[u].w & 0xffff, rec[u].x, r), pol_out);
           // states(slot) = State(voteRound = round, voteValue) (:205-208)
           cell[u] = ((unsigned long long)(uint32_t)(r + 1) << 32) | (uint32_t)rec[u].z;
           old[u] = atomicMax(&P.votes[(size_t)loc * g.voters + vix], cell[u]);

@@ -106,6 +106,16 @@ __device__ __forceinline__ unsigned long long l2_policy_evict_last() {
   asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
   return pol;
 }
+__device__ __forceinline__ unsigned long long l2_policy_evict_first() {
+  unsigned long long pol;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
+// streaming 128-bit store whose line is the first candidate for eviction (written back early)
+__device__ __forceinline__ void st_evict_first(int4* p, int4 v, unsigned long long pol) {
+  asm volatile("st.global.L1::no_allocate.L2::cache_hint.v4.s32 [%0], {%1,%2,%3,%4}, %5;" ::"l"(p), "r"(v.x), "r"(v.y),
+               "r"(v.z), "r"(v.w), "l"(pol));
+}
 __device__ __forceinline__ int4 ld_keep(const int4* p, unsigned long long pol) {
   int4 r;
   asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v4.s32 {%0,%1,%2,%3}, [%4], %5;"

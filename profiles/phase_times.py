@@ -12,7 +12,9 @@ outp=torch.empty((3*n,4),dtype=torch.int32,device=dev); outn=torch.empty((3*n,2)
 for s in range(6):
     a,p,b=T.workload(s,cfg,n,slot0=s*n)
     da,dp,db=td(a),td(p),td(b)
-    eng.proxyleader_arm_dev(da.data_ptr(),n); eng.acceptor_phase2a_dev(dp.data_ptr(),3*n,outp.data_ptr(),outn.data_ptr()); eng.proxyleader_phase2b_dev(db.data_ptr(),3*n,outc.data_ptr())
+    eng.proxyleader_arm_dev(da.data_ptr(),n)
+    if '--no-acceptor' not in sys.argv: eng.acceptor_phase2a_dev(dp.data_ptr(),3*n,outp.data_ptr(),outn.data_ptr())
+    eng.proxyleader_phase2b_dev(db.data_ptr(),3*n,outc.data_ptr())
     eng.replica_chosen_last_dev(outc.data_ptr()); eng.chosen_watermark_dev()
     r=eng.sync(check=False)
     ta=(ctypes.c_ulonglong*8)(); tt=(ctypes.c_ulonglong*8)()
