@@ -6,11 +6,12 @@ namespace fpx {
 // ===========================================================================
 // K1  ProxyLeader.handlePhase2a  -- "arm"   S/multipaxos/ProxyLeader.scala:175-215
 //   states.get((slot, round)): Some -> ignore (:177-183); None -> Pending(phase2a,
-//   {}) (:213).  One thread per record; the key's header {round_word, value_id}
-//   is claimed with ONE 64-bit CAS.  A second round for a slot whose primary row
-//   is taken goes to the overflow table.  Two arms of one key with DIFFERENT
+//   {}) (:213).  Warp-strided 32-record chunks; the key's header {round_word,
+//   value_id} is claimed with ONE 64-bit CAS, four of them in flight per lane.  A
+//   second round for a slot moves the slot's keys to the (slot, round) table and
+//   poisons the primary row (arm_finish).  Two arms of one key with DIFFERENT
 //   values inside one batch (never produced by a correct leader) are resolved to
-//   "first in delivery order wins" by the last block (resolve_arm_conflicts).
+//   "first in delivery order wins" by the last block of the launch.
 // ===========================================================================
 struct ArmConflict { int32_t slot, round; };
 
