@@ -1,0 +1,30 @@
+"""bench.py's JSON-line contract, checked on the CPU through the reference arm
+(`--impl reference` times the C++ oracle port on the host cores; no GPU involved)."""
+import json
+import os
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_reference_arm_json_line():
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "2",
+                        "--warmup", "1", "--cpu-sample-slots", "16384"], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr
+    line = json.loads(r.stdout.strip().splitlines()[-1])
+    assert line["impl"] == "reference" and line["unit"] == "slots/s" and line["higher_is_better"] is True
+    assert line["metric"].startswith("committed slots/sec")
+    assert line["value"] > 0 and line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
+    assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["d2h_bytes_per_step"] == 0
+    assert "workload" in line["config"]
+
+
+def test_product_paths_never_import_the_oracle():
+    """Only tests/, __graft_entry__.smoke() and bench.py's cpu legs may touch oracle/."""
+    pkg = os.path.join(ROOT, "frankenpaxos_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".c", ".h", ".hpp")):
+                text = open(os.path.join(dirpath, f), errors="ignore").read()
+                assert "fpx_oracle" not in text and "from oracle" not in text and "import oracle" not in text, f
