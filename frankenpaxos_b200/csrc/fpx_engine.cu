@@ -943,6 +943,19 @@ int fpx_epaxos_entry(fpx_epaxos* e, int32_t rep, int32_t num, int32_t* out, int3
   return FPX_OK;
 }
 
+int fpx_depset_union_dense_dev(int32_t device, const int32_t* d_in, int32_t n_groups, int32_t sets_per_group,
+                               int32_t n_replicas, int32_t* d_out, void* stream) {
+  if (n_groups < 0 || sets_per_group < 1 || n_replicas < 1 || (n_groups > 0 && (!d_in || !d_out))) return FPX_ERR_INVALID_ARG;
+  if (n_groups == 0) return FPX_OK;
+  if (cudaSetDevice(device) != cudaSuccess) return FPX_ERR_NO_DEVICE;
+  size_t smem = (size_t)kUnionTile * (sets_per_group + 1) * n_replicas * 4;
+  if (smem > 48 * 1024) return FPX_ERR_UNSUPPORTED;   // (R+1)*n <= 48
+  int blocks = (int)std::min<long long>(((long long)n_groups + kUnionTile - 1) / kUnionTile, 148 * 8);
+  depset_union_dense_kernel<<<blocks, kUnionTile, smem, (cudaStream_t)stream>>>(d_in, n_groups, sets_per_group,
+                                                                               n_replicas, d_out);
+  return cudaGetLastError() == cudaSuccess ? FPX_OK : FPX_ERR_CUDA;
+}
+
 int fpx_depset_union(int32_t device, const int32_t* watermark, const int32_t* off, const int32_t* values,
                      int32_t n_sets, const int32_t* group_off, int32_t n_groups, int32_t* out_watermark,
                      int32_t* out_count, int32_t* out_values) {

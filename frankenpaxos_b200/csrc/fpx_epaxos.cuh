@@ -376,6 +376,42 @@ __global__ void ep_response_decide_kernel(EpParams P) {
   }
 }
 
+// ---- dense dep-set union (all `values` empty): elementwise max over the R sets of a group.
+// Pure streaming, 4n(R+1) bytes per group.  A CTA stages a tile of 256 groups of the flat
+// [group][set][replica] int32 array in shared memory with fully coalesced 128-bit loads,
+// then thread t reduces group t (conflict-free when R*n is odd, 2-way otherwise) and the
+// tile's outputs go out coalesced.
+constexpr int kUnionTile = 256;
+__global__ void __launch_bounds__(kUnionTile) depset_union_dense_kernel(const int32_t* __restrict__ in, int n_groups,
+                                                                        int R, int n, int32_t* __restrict__ out) {
+  extern __shared__ int32_t s_tile[];             // kUnionTile * R * n  (+ kUnionTile * n outputs)
+  const int W = R * n;
+  int32_t* s_out = s_tile + kUnionTile * W;
+  for (long long g0 = (long long)blockIdx.x * kUnionTile; g0 < n_groups; g0 += (long long)gridDim.x * kUnionTile) {
+    const int groups = (int)min((long long)kUnionTile, n_groups - g0);
+    const long long base = g0 * W;                // multiple of 4 ints: 16-byte aligned
+    const int words = groups * W;
+    const int4* src = (const int4*)(in + base);
+    for (int v = threadIdx.x; v < words / 4; v += kUnionTile) {
+      int4 x = ld_stream(src + v);
+      *(int4*)(s_tile + 4 * v) = x;
+    }
+    for (int v = (words & ~3) + threadIdx.x; v < words; v += kUnionTile) s_tile[v] = in[base + v];
+    __syncthreads();
+    if ((int)threadIdx.x < groups) {
+      const int32_t* p = s_tile + threadIdx.x * W;
+      for (int k = 0; k < n; ++k) {
+        int m = p[k];
+        for (int r = 1; r < R; ++r) m = max(m, p[r * n + k]);   // dependencies.addAll (Replica.scala:804-807)
+        s_out[threadIdx.x * n + k] = m;
+      }
+    }
+    __syncthreads();
+    for (int v = threadIdx.x; v < groups * n; v += kUnionTile) __stcs(out + g0 * n + v, s_out[v]);
+    __syncthreads();
+  }
+}
+
 // ---- general IntPrefixSet union (S/compact/IntPrefixSet.scala:253-259, 317-351, 426-431)
 // Sets are CSR: watermark[j], values[off[j] .. off[j+1]) (canonical: every value >
 // watermark).  Group q unions sets [goff[q], goff[q+1]).  Output: out_w[q],

@@ -29,6 +29,7 @@ def _bind(L):
         f.argtypes = [vp, vp, i32, vp, p(C.c_int64)]; f.restype = i32
     L.fpx_epaxos_entry.argtypes = [vp, i32, i32, vp, p(i32), vp]; L.fpx_epaxos_entry.restype = i32
     L.fpx_depset_union.argtypes = [i32, vp, vp, vp, i32, vp, i32, vp, vp, vp]; L.fpx_depset_union.restype = i32
+    L.fpx_depset_union_dense_dev.argtypes = [i32, vp, i32, i32, i32, vp, vp]; L.fpx_depset_union_dense_dev.restype = i32
     L._ep_bound = True
 
 
@@ -119,3 +120,12 @@ def depset_union(watermarks, value_lists, group_off, device=0):
         o = off[goff[q]]
         res.append((int(ow[q]), ov[o:o + on[q]].tolist()))
     return res
+
+
+def depset_union_dense_dev(d_in, n_groups, sets_per_group, n_replicas, d_out, stream=None, device=0):
+    """Dense batched union on device pointers: out[q][k] = max_r in[q][r][k] (asynchronous)."""
+    L = _lib.lib()
+    _bind(L)
+    st = L.fpx_depset_union_dense_dev(device, d_in, n_groups, sets_per_group, n_replicas, d_out, stream)
+    if st != 0:
+        raise FpxError(st)

@@ -341,6 +341,14 @@ int fpx_depset_union(int32_t device, const int32_t* watermark, const int32_t* of
                      int32_t n_sets, const int32_t* group_off, int32_t n_groups, int32_t* out_watermark,
                      int32_t* out_count, int32_t* out_values);
 
+/* Dense batched dep-set union, DEVICE pointers (BASELINE cfg4's "dep-set union kernel"):
+ * out[q][k] = max_r in[q][r][k] for q < n_groups, r < sets_per_group, k < n_replicas --
+ * InstancePrefixSet.addAll over sets whose `values` are empty (IntPrefixSet.scala:320-321),
+ * e.g. preAcceptingSlowPath's union of the R responses of an instance (Replica.scala:804-807).
+ * Asynchronous on `stream` (a cudaStream_t, 0 = default stream). */
+int fpx_depset_union_dense_dev(int32_t device, const int32_t* d_in, int32_t n_groups, int32_t sets_per_group,
+                               int32_t n_replicas, int32_t* d_out, void* stream);
+
 /* ---- device-pointer entry points (inputs already resident in HBM) ------- */
 
 /* Same semantics, DEVICE pointers, asynchronous on fpx_stream(e).  Output

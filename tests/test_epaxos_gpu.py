@@ -189,3 +189,26 @@ def test_union_random_vs_oracle():
         expect.append((acc.watermark(), sorted(acc.values())))
     got = depset_union(wms, vals, goff)
     assert got == expect
+
+
+def test_dense_union_kernel_matches_numpy_and_oracle():
+    """BASELINE cfg4's dep-set union kernel (n=5, R=4 sets per instance): elementwise max,
+    checked against numpy at 2^20 instances and against IntPrefixSet.addAll on a sample."""
+    import torch
+    from frankenpaxos_b200.epaxos import depset_union_dense_dev
+    g = T.rng(4)
+    G, R, n = 1 << 20, 4, 5
+    x = g.integers(0, 1 << 20, size=(G, R, n), dtype=np.int32)
+    d_in = torch.from_numpy(x).cuda()
+    d_out = torch.empty((G, n), dtype=torch.int32, device="cuda")
+    torch.cuda.synchronize()
+    depset_union_dense_dev(d_in.data_ptr(), G, R, n, d_out.data_ptr())
+    torch.cuda.synchronize()
+    out = d_out.cpu().numpy()
+    assert np.array_equal(out, x.max(axis=1))
+    for q in range(0, G, G // 50):
+        for k in range(n):
+            acc = O.IntPrefixSet()
+            for r in range(R):
+                acc.add_all(O.IntPrefixSet.from_watermark_values(int(x[q, r, k]), []))
+            assert acc.watermark() == out[q, k] and not acc.values()
