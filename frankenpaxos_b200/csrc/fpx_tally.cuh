@@ -80,7 +80,7 @@ __device__ __forceinline__ uint32_t tally_phase_b(const TallyParams& P, int wlo,
   const Geometry& g = P.g;
   const unsigned full = 0xffffffffu;
   const bool vanilla = g.protocol == FPX_VANILLA_MENCIUS;
-  constexpr int kUB = ROWW == 8 ? 4 : (ROWW == 16 ? 2 : 1);
+  constexpr int kUB = ROWW <= 16 ? 2 : 1;
   uint32_t wcnt = 0;
   for (int base = wlo; base < whi; base += 32 * kUB) {
     int4 rec[kUB];
@@ -176,7 +176,7 @@ __device__ __forceinline__ uint32_t tally_phase_b(const TallyParams& P, int wlo,
 }
 
 template <int ROWW>
-__global__ void __launch_bounds__(kThreads) tally_kernel(TallyParams P) {
+__global__ void __launch_bounds__(kThreads, ROWW == 8 ? 4 : 1) tally_kernel(TallyParams P) {
   const Geometry& g = P.g;
   extern __shared__ int2 s_buf[];  // kWarps * P.per Chosen records
   __shared__ uint32_t s_wcnt[kWarps];
