@@ -19,8 +19,9 @@
 // Replica handlers) have no known-answer test in the reference -- they are only
 // exercised by randomized simulation with invariant checks -- so handler-level
 // parity is "parity unpinned" by the reference's own tests; it is anchored on
-// the worked micro-trace of SURVEY.md 8(g) and on the reference's invariants
-// (tests/test_invariants.py).
+// the worked micro-trace of SURVEY.md 8(g), on the reference's invariants
+// (tests/test_oracle_handlers.py) and on an independent Python transcription of the
+// same Scala handlers (tests/scala_transcription.py, tests/test_oracle_cross_check.py).
 //
 // Citations: S/ = shared/src/main/scala/frankenpaxos/ in the reference tree.
 
