@@ -21,7 +21,7 @@ SYMBOLS = [
     "fpx_acceptor_phase1a", "fpx_leader_safe_values",
     "fpx_vm_client_request", "fpx_vm_phase2a", "fpx_vm_learn_chosen",
     "fpx_epaxos_create", "fpx_epaxos_destroy", "fpx_epaxos_lead", "fpx_epaxos_preaccept", "fpx_epaxos_accept",
-    "fpx_epaxos_preacceptok", "fpx_epaxos_acceptok", "fpx_epaxos_entry", "fpx_depset_union", "fpx_depset_union_dense_dev",
+    "fpx_epaxos_preacceptok", "fpx_epaxos_acceptok", "fpx_epaxos_entry", "fpx_epaxos_last_kernel_ms", "fpx_depset_union", "fpx_depset_union_dense_dev",
 ]
 
 

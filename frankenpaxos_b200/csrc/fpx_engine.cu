@@ -778,6 +778,7 @@ struct fpx_epaxos {
   DevStatus* h_st = nullptr;
   uint32_t tag = 1;
   uint32_t seq_base = 1;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   std::string last_error;
 };
 
@@ -837,6 +838,8 @@ int fpx_epaxos_create(fpx_epaxos** out, const fpx_epaxos_config* cfg) {
   CKC(cudaMalloc(&e->d_in, mb * (6 + 2 * kEpMaxN) * 4));
   CKC(cudaMalloc(&e->d_out, mb * (4 + kEpMaxN) * 4));
   CKC(cudaMallocHost(&e->h_st, sizeof(DevStatus)));
+  CKC(cudaEventCreate(&e->ev0));
+  CKC(cudaEventCreate(&e->ev1));
   CKC(cudaMemsetAsync(e->s.cmd, 0, ninst * kEpCmdWords * 4, e->stream));
   CKC(cudaMemsetAsync(e->s.lead, 0, ninst * kEpLeadWords * 4, e->stream));
   CKC(cudaMemsetAsync(e->s.claim, 0xff, ninst * 8, e->stream));
@@ -858,8 +861,16 @@ void fpx_epaxos_destroy(fpx_epaxos* e) {
   cudaFree(e->s.cmd); cudaFree(e->s.lead); cudaFree(e->s.claim); cudaFree(e->s.count); cudaFree(e->s.largest);
   cudaFree(e->s.proc_ballot); cudaFree(e->s.st); cudaFree(e->d_in); cudaFree(e->d_out);
   if (e->h_st) cudaFreeHost(e->h_st);
+  if (e->ev0) cudaEventDestroy(e->ev0);
+  if (e->ev1) cudaEventDestroy(e->ev1);
   if (e->stream) cudaStreamDestroy(e->stream);
   delete e;
+}
+
+float fpx_epaxos_last_kernel_ms(fpx_epaxos* e) {
+  float ms = 0.f;
+  if (!e || cudaEventElapsedTime(&ms, e->ev0, e->ev1) != cudaSuccess) return -1.f;
+  return ms;
 }
 
 static int ep_call(fpx_epaxos* e, const int32_t* in, int32_t n_rec, int w_in, int32_t* out, int w_out, int which,
@@ -875,6 +886,7 @@ static int ep_call(fpx_epaxos* e, const int32_t* in, int32_t n_rec, int w_in, in
   if (e->tag == 0xffffffffu) e->tag = 1;
   P.seq_base = e->seq_base;
   int blocks = (n_rec + 255) / 256;
+  CKE(e, cudaEventRecord(e->ev0, e->stream));
   switch (which) {
     case 0: ep_lead_kernel<<<blocks, 256, 0, e->stream>>>(P); break;
     case 1:
@@ -897,6 +909,7 @@ static int ep_call(fpx_epaxos* e, const int32_t* in, int32_t n_rec, int w_in, in
       ep_response_decide_kernel<true><<<blocks, 256, 0, e->stream>>>(P);
       break;
   }
+  CKE(e, cudaEventRecord(e->ev1, e->stream));
   CKE(e, cudaGetLastError());
   if (w_out) CKE(e, cudaMemcpyAsync(out, e->d_out, (size_t)n_rec * w_out * 4, cudaMemcpyDeviceToHost, e->stream));
   return ep_finish(e, err_index);

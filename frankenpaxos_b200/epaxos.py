@@ -29,6 +29,7 @@ def _bind(L):
         f.argtypes = [vp, vp, i32, vp, p(C.c_int64)]; f.restype = i32
     L.fpx_epaxos_entry.argtypes = [vp, i32, i32, vp, p(i32), vp]; L.fpx_epaxos_entry.restype = i32
     L.fpx_depset_union.argtypes = [i32, vp, vp, vp, i32, vp, i32, vp, vp, vp]; L.fpx_depset_union.restype = i32
+    L.fpx_epaxos_last_kernel_ms.argtypes = [vp]; L.fpx_epaxos_last_kernel_ms.restype = C.c_float
     L.fpx_depset_union_dense_dev.argtypes = [i32, vp, i32, i32, i32, vp, vp]; L.fpx_depset_union_dense_dev.restype = i32
     L._ep_bound = True
 
@@ -86,6 +87,9 @@ class EpaxosReplica:
 
     def acceptok(self, rows):
         return self._call(self._L.fpx_epaxos_acceptok, rows, 6, 2 + self.n)
+
+    def last_kernel_ms(self):
+        return float(self._L.fpx_epaxos_last_kernel_ms(self.h))
 
     def entry(self, rep, num):
         out = np.zeros(7 + self.n, dtype=np.int32)

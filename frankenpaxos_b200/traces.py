@@ -127,37 +127,45 @@ def epaxos_cfg4(seed, f=2, n_instances=1 << 14, conflict_rate=0.2, me=0, lag=8):
     """
     g = rng(seed)
     n = 2 * f + 1
-    is_set = g.random(n_instances) < conflict_rate
-    leader = np.arange(n_instances) % n
-    number = np.arange(n_instances) // n
+    N = n_instances
+    is_set = g.random(N) < conflict_rate
+    leader = (np.arange(N) % n).astype(np.int32)
+    number = (np.arange(N) // n).astype(np.int32)
+    # pm[L][j] = TopOne column L after indexing the set(x) instances < j  (vectorised prefix max)
+    pm = np.zeros((n, N + 1), dtype=np.int32)
+    for L in range(n):
+        contrib = np.where(is_set & (leader == L), number + 1, 0)
+        pm[L, 1:] = np.maximum.accumulate(contrib)
+    lags = g.integers(0, lag + 1, size=(N, n))
+    k = np.arange(N)
 
-    def view(k, who_lag):
-        """TopOne(x) of a replica that has indexed the set(x) instances < k - who_lag."""
-        hi = max(0, k - who_lag)
-        v = np.zeros(n, dtype=np.int32)
-        idx = np.nonzero(is_set[:hi])[0]
-        if len(idx):
-            np.maximum.at(v, leader[idx], number[idx] + 1)
+    def views(who):
+        """TopOne(x) of replica `who` when it handles instance k: all set(x) instances < k - lag."""
+        hi = np.maximum(0, k - lags[:, who] if np.isscalar(who) else k - lags[np.arange(N), who])
+        v = pm[:, hi].T.copy()
+        v[~is_set] = 0                       # get(y) conflicts with nothing
         return v
 
-    lags = g.integers(0, lag + 1, size=(n_instances, n))
-    lead_rows, pa_rows, ok_rows = [], [], []
-    for k in range(n_instances):
-        L, num = int(leader[k]), int(number[k])
-        zeros = np.zeros(n, dtype=np.int32)
-        ldeps = view(k, int(lags[k, L])) if is_set[k] else zeros
-        if L == me:
-            lead_rows.append(np.concatenate([[L, num, 0, L, k, 0, 0, 0], ldeps]))
-            for r in range(n):
-                if r == me:
-                    continue
-                rdeps = np.maximum(ldeps, view(k, int(lags[k, r]))) if is_set[k] else zeros
-                ok_rows.append(np.concatenate([[L, num, 0, L, r, 0], rdeps]))
-        else:
-            mine = view(k, int(lags[k, me])) if is_set[k] else zeros
-            pa_rows.append(np.concatenate([[L, num, 0, L, k, 0], mine, ldeps]))
-    lead_rows = np.array(lead_rows, dtype=np.int32).reshape(-1, 8 + n)
-    pa_rows = np.array(pa_rows, dtype=np.int32).reshape(-1, 6 + 2 * n)
-    ok_rows = np.array(ok_rows, dtype=np.int32).reshape(-1, 6 + n)
+    ldeps = views(leader)                    # the leader's own answer
+    mine = leader == me
+    lead_rows = np.zeros((int(mine.sum()), 8 + n), dtype=np.int32)
+    lead_rows[:, 0] = me; lead_rows[:, 1] = number[mine]; lead_rows[:, 3] = me; lead_rows[:, 4] = k[mine]
+    lead_rows[:, 8:] = ldeps[mine]
+    ok_parts = []
+    for r in range(n):
+        if r == me:
+            continue
+        rdeps = np.maximum(ldeps[mine], views(r)[mine])
+        rows = np.zeros((int(mine.sum()), 6 + n), dtype=np.int32)
+        rows[:, 0] = me; rows[:, 1] = number[mine]; rows[:, 3] = me; rows[:, 4] = r
+        rows[:, 6:] = rdeps
+        ok_parts.append(rows)
+    ok_rows = np.concatenate(ok_parts) if ok_parts else np.zeros((0, 6 + n), dtype=np.int32)
     ok_rows = ok_rows[g.permutation(len(ok_rows))]
+    others = ~mine
+    pa_rows = np.zeros((int(others.sum()), 6 + 2 * n), dtype=np.int32)
+    pa_rows[:, 0] = leader[others]; pa_rows[:, 1] = number[others]; pa_rows[:, 3] = leader[others]
+    pa_rows[:, 4] = k[others]
+    pa_rows[:, 6:6 + n] = views(me)[others]
+    pa_rows[:, 6 + n:] = ldeps[others]
     return lead_rows, pa_rows, ok_rows

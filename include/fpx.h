@@ -328,6 +328,9 @@ int fpx_epaxos_acceptok(fpx_epaxos* e, const int32_t* in, int32_t n_rec, int32_t
 /* read-back: out[7+n] = {kind, b_ord, b_rep, vb_ord, vb_rep, value_id, seq, deps[n]},
  * kind 0 none 1 NoCommand 2 PreAccepted 3 Accepted 4 Committed; *leader_kind 0 none 1
  * PreAccepting 2 Accepting; largest_ballot[2] */
+/* device time (ms, CUDA events on the handle's stream) of the kernels of the last
+ * fpx_epaxos_* call, without its host<->device copies */
+float fpx_epaxos_last_kernel_ms(fpx_epaxos* e);
 int fpx_epaxos_entry(fpx_epaxos* e, int32_t inst_replica, int32_t inst_number, int32_t* out,
                      int32_t* leader_kind, int32_t* largest_ballot);
 
