@@ -7,6 +7,6 @@ Acceptor).  Importing the package does not need a GPU; constructing an Engine
 does -- there is no CPU fallback.
 """
 from .engine import (CHOSEN, NACK, P2A, P2B, Engine, FpxError, dst,  # noqa: F401
-                     MULTIPAXOS, MENCIUS, VANILLA_MENCIUS)
+                     MULTIPAXOS, MENCIUS, VANILLA_MENCIUS, P2A_RANGE, P2B_RANGE, CHOSEN_RANGE, VM_SKIP, VALUE_NOOP)
 
 __all__ = ["Engine", "FpxError", "P2A", "P2B", "CHOSEN", "NACK", "dst"]

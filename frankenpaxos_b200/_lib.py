@@ -19,7 +19,9 @@ SYMBOLS = [
     "fpx_replica_chosen_dev", "fpx_replica_chosen_last_dev", "fpx_chosen_watermark_dev", "fpx_sync",
     "fpx_stream", "fpx_launch_count",
     "fpx_acceptor_phase1a", "fpx_leader_safe_values",
-    "fpx_vm_client_request", "fpx_vm_phase2a", "fpx_vm_learn_chosen",
+    "fpx_vm_client_request", "fpx_vm_phase2a", "fpx_vm_learn_chosen", "fpx_vm_skip",
+    "fpx_mencius_arm_range", "fpx_mencius_acceptor_noop_range", "fpx_mencius_range_phase2b",
+    "fpx_mencius_replica_chosen_range",
     "fpx_epaxos_create", "fpx_epaxos_destroy", "fpx_epaxos_lead", "fpx_epaxos_preaccept", "fpx_epaxos_accept",
     "fpx_epaxos_preacceptok", "fpx_epaxos_acceptok", "fpx_epaxos_entry", "fpx_epaxos_last_kernel_ms", "fpx_depset_union", "fpx_depset_union_dense_dev",
 ]
@@ -81,6 +83,13 @@ def lib():
     L.fpx_vm_client_request.argtypes = [vp, vp, i32, p(i64)]; L.fpx_vm_client_request.restype = i32
     L.fpx_vm_phase2a.argtypes = [vp, vp, i32, vp, p(i64)]; L.fpx_vm_phase2a.restype = i32
     L.fpx_vm_learn_chosen.argtypes = [vp, vp, i32, p(i64)]; L.fpx_vm_learn_chosen.restype = i32
+    L.fpx_vm_skip.argtypes = [vp, vp, i32, p(i64)]; L.fpx_vm_skip.restype = i32
+    L.fpx_mencius_arm_range.argtypes = [vp, vp, i32, p(i64)]; L.fpx_mencius_arm_range.restype = i32
+    L.fpx_mencius_acceptor_noop_range.argtypes = [vp, vp, i32, vp, p(i32), vp, p(i32), p(i64)]
+    L.fpx_mencius_acceptor_noop_range.restype = i32
+    L.fpx_mencius_range_phase2b.argtypes = [vp, vp, i32, vp, p(i32), p(i64)]; L.fpx_mencius_range_phase2b.restype = i32
+    L.fpx_mencius_replica_chosen_range.argtypes = [vp, vp, i32, p(i64)]
+    L.fpx_mencius_replica_chosen_range.restype = i32
     L.fpx_sync.argtypes = [vp, p(SyncResult)]; L.fpx_sync.restype = i32
     L.fpx_stream.argtypes = [vp]; L.fpx_stream.restype = vp
     L.fpx_launch_count.argtypes = [vp]; L.fpx_launch_count.restype = i64

@@ -1,5 +1,6 @@
 #pragma once
 #include "fpx_common.cuh"
+#include "fpx_ranges.cuh"
 
 namespace fpx {
 
@@ -25,6 +26,8 @@ struct ArmParams {
   uint32_t* win_bits;  // ceil(n/32): record i created its key's entry
   unsigned long long* votes;  // vanilla Mencius (vanilla != 0): the coordinator votes for itself
   int32_t vanilla;
+  RangeTable rng;      // mencius: one-slot Phase2aNoopRange keys share the key space (check_rng != 0)
+  int32_t check_rng;
 };
 
 __device__ __forceinline__ void note_arm_conflict(const ArmParams& P, int slot, int round) {
@@ -145,6 +148,9 @@ __global__ void __launch_bounds__(256) arm_kernel(ArmParams P) {
         } else if (P.vanilla && ((rec[u].w >> 16) != 0 || (rec[u].w & 0xffff) >= g.per_group ||
                                  rec[u].x % g.per_group != (rec[u].w & 0xffff))) {
           report_error(P.st, FPX_ERR_BAD_ACCEPTOR, i);   // only the slot's owner coordinates it (:773, slotSystem)
+        } else if (P.check_rng && range_find(P.rng, rec[u].x, rec[u].x + 1, rec[u].y) != nullptr) {
+          // S/mencius: SlotRound(slot, slot+1, round) is held by a one-slot Phase2aNoopRange:
+          // `case Some(_)` -> ignored (mencius/ProxyLeader.scala:220-226)
         } else {
           ok[u] = true;
           unsigned long long want = ((unsigned long long)(uint32_t)rec[u].z << 32) | (uint32_t)rec[u].y;

@@ -19,6 +19,7 @@
 #include "fpx_arm.cuh"
 #include "fpx_common.cuh"
 #include "fpx_epaxos.cuh"
+#include "fpx_ranges.cuh"
 #include "fpx_replica_misc.cuh"
 #include "fpx_tally.cuh"
 #include "fpx_vanilla.cuh"
@@ -43,6 +44,11 @@ struct fpx_engine {
   unsigned long long* rlog = nullptr;
   unsigned long long* vm_claim = nullptr;  // vanilla Mencius: per-cell batch claims
   uint32_t vm_tag = 1;
+  uint32_t* rng_tab = nullptr;             // mencius: (start, end, round) key table of the NoopRange path
+  int32_t rng_cap = 0;
+  int32_t* rng_dec = nullptr;              // per-record scratch of the range kernels (FPX_MAX_RANGE_BATCH)
+  uint32_t rng_seq_base = 1;               // Phase2bNoopRange delivery sequence numbers
+  int unit_ranges = 0;                     // a one-slot range was ever armed: arms must look at the range keys
   DevStatus* st = nullptr;
   // scratch
   uint32_t* bits = nullptr;            // accept / win bitmask, max_batch/32 words
@@ -134,6 +140,9 @@ static int reset_state(fpx_engine* e) {
   CK(e, cudaMemsetAsync(e->acc_max_voted, 0xff, kMaxKeys * 4, e->stream));  // maxVotedSlot = -1 (:104)
   CK(e, cudaMemsetAsync(e->rlog, 0xff, (size_t)g.local_slots * 8, e->stream));
   if (e->vm_claim) CK(e, cudaMemsetAsync(e->vm_claim, 0xff, (size_t)g.local_slots * g.voters * 8, e->stream));
+  if (e->rng_tab) CK(e, cudaMemsetAsync(e->rng_tab, 0xff, (size_t)e->rng_cap * kRangeWords * 4, e->stream));
+  e->rng_seq_base = 1;
+  e->unit_ranges = 0;
   DevStatus init;
   memset(&init, 0, sizeof(init));
   init.err_word = ~0ull;
@@ -171,6 +180,7 @@ const char* fpx_strerror(int s) {
     case FPX_ERR_NO_DEVICE: return "no CUDA device";
     case FPX_ERR_UNSUPPORTED: return "configuration not supported by this engine build";
     case FPX_ERR_BATCH_ORDER: return "EPaxos batch contract violated: split the batch at err_index";
+    case FPX_ERR_CHECK_FAILED: return "a logger.check of the reference failed";
     case FPX_ERR_EPAXOS_STATE: return "transitionToPreAcceptPhase on a committed instance / regressing ballot";
     default: return "unknown status";
   }
@@ -239,6 +249,11 @@ int fpx_create(fpx_engine** out, const fpx_config* cfg) {
   CKC(cudaMalloc(&e->acc_max_voted, kMaxKeys * 4));
   CKC(cudaMalloc(&e->rlog, (size_t)g.local_slots * 8));
   if (cfg->protocol == FPX_VANILLA_MENCIUS) CKC(cudaMalloc(&e->vm_claim, (size_t)g.local_slots * g.voters * 8));
+  if (cfg->protocol == FPX_MENCIUS) {
+    e->rng_cap = std::max(1024, g.ovf_cap);
+    CKC(cudaMalloc(&e->rng_tab, (size_t)e->rng_cap * kRangeWords * 4));
+  }
+  if (cfg->protocol != FPX_MULTIPAXOS) CKC(cudaMalloc(&e->rng_dec, (size_t)(FPX_MAX_RANGE_BATCH + 1) * 4));
   CKC(cudaMalloc(&e->st, sizeof(DevStatus)));
   CKC(cudaMalloc(&e->bits, (mb / 32 + 2) * 4));
   CKC(cudaMalloc(&e->g_agg, (size_t)kMaxGrid * kMaxKeys * 4));
@@ -279,6 +294,7 @@ void fpx_destroy(fpx_engine* e) {
   if (e->stream) cudaStreamSynchronize(e->stream);
   cudaFree(e->rows); cudaFree(e->ovf_keys); cudaFree(e->ovf_rows); cudaFree(e->votes);
   cudaFree(e->acc_round); cudaFree(e->acc_max_voted); cudaFree(e->rlog); cudaFree(e->vm_claim); cudaFree(e->st);
+  cudaFree(e->rng_tab); cudaFree(e->rng_dec);
   cudaFree(e->bits); cudaFree(e->g_agg); cudaFree(e->g_wacc); cudaFree(e->g_ccnt); cudaFree(e->conflicts);
   cudaFree(e->d_in); cudaFree(e->d_out_a); cudaFree(e->d_out_b);
   if (e->h_st) cudaFreeHost(e->h_st);
@@ -328,6 +344,8 @@ static int arm_launch(fpx_engine* e, const fpx_p2a* d_in, int32_t n, int vanilla
   P.win_bits = e->bits;
   P.votes = e->votes;
   P.vanilla = vanilla;
+  P.rng = RangeTable{e->rng_tab, (uint32_t)e->rng_cap - 1u, e->rng_cap};
+  P.check_rng = e->unit_ranges;
   int arm_blocks = std::min((n + 256 * kArmUnroll - 1) / (256 * kArmUnroll), e->num_sms * 8);
   arm_kernel<<<arm_blocks, 256, 0, e->stream>>>(P);
   e->launches++;
@@ -635,6 +653,142 @@ int fpx_vm_phase2a(fpx_engine* e, const fpx_p2a* in, int32_t n, fpx_p2b* reply, 
 }
 int fpx_vm_learn_chosen(fpx_engine* e, const fpx_p2b* in, int32_t n, int64_t* err_index) {
   return vm_call(e, in, n, nullptr, err_index, 1);
+}
+
+// --------------------------------------------------------------------------- range fills
+
+static int range_call_begin(fpx_engine* e, const void* in, int32_t n, int64_t* err_index, int protocol) {
+  if (err_index) *err_index = -1;
+  if (!e || n < 0 || n > FPX_MAX_RANGE_BATCH || n > e->cfg.max_batch || (n > 0 && !in)) return FPX_ERR_INVALID_ARG;
+  if (e->g.protocol != protocol) return FPX_ERR_UNSUPPORTED;
+  return FPX_OK;
+}
+static int range_call_end(fpx_engine* e, fpx_sync_result* r, int64_t* err_index) {
+  int c = fpx_sync(e, r);
+  if (err_index) *err_index = r->err_index;
+  return c;
+}
+// CTAs along x for strided fills of at most `max_count` elements per record (grid = (x, n))
+static unsigned fill_grid_x(const fpx_engine* e, long long max_count, int32_t n) {
+  long long want = (max_count + 255) / 256;
+  long long cap = std::max(1LL, (long long)e->num_sms * 8 / std::max(1, n));
+  return (unsigned)std::max(1LL, std::min(want, std::max(cap, 1LL)));
+}
+
+int fpx_vm_skip(fpx_engine* e, const fpx_vm_skip_rec* in, int32_t n, int64_t* err_index) {
+  int c = range_call_begin(e, in, n, err_index, FPX_VANILLA_MENCIUS);
+  if (c != FPX_OK || n == 0) return c;
+  CK(e, cudaSetDevice(e->cfg.device));
+  long long mx = 0;
+  for (int32_t i = 0; i < n; ++i) mx = std::max(mx, ((long long)in[i].slot_stop - in[i].slot_start) / e->g.per_group + 1);
+  CK(e, cudaMemcpyAsync(e->d_in, in, (size_t)n * 16, cudaMemcpyHostToDevice, e->stream));
+  VmSkipParams P{e->g, (const int4*)e->d_in, e->votes, e->rows, e->st};
+  vm_skip_kernel<<<dim3(fill_grid_x(e, mx, n), n), 256, 0, e->stream>>>(P);
+  e->launches++;
+  CK(e, cudaGetLastError());
+  fpx_sync_result r;
+  return range_call_end(e, &r, err_index);
+}
+
+int fpx_mencius_arm_range(fpx_engine* e, const fpx_p2a_range* in, int32_t n, int64_t* err_index) {
+  int c = range_call_begin(e, in, n, err_index, FPX_MENCIUS);
+  if (c != FPX_OK || n == 0) return c;
+  CK(e, cudaSetDevice(e->cfg.device));
+  for (int32_t i = 0; i < n; ++i)
+    if (in[i].slot_end == in[i].slot_start + 1) e->unit_ranges = 1;
+  CK(e, cudaMemcpyAsync(e->d_in, in, (size_t)n * 16, cudaMemcpyHostToDevice, e->stream));
+  RangeArmParams P{e->g, PLState{e->rows, e->ovf_keys, e->ovf_rows},
+                   RangeTable{e->rng_tab, (uint32_t)e->rng_cap - 1u, e->rng_cap}, (const int4*)e->d_in, n, e->st};
+  range_arm_kernel<<<(n + 255) / 256, 256, 0, e->stream>>>(P);
+  e->launches++;
+  CK(e, cudaGetLastError());
+  fpx_sync_result r;
+  return range_call_end(e, &r, err_index);
+}
+
+int fpx_mencius_acceptor_noop_range(fpx_engine* e, const fpx_p2a_range* in, int32_t n, fpx_p2b_range* out,
+                                    int32_t* n_out, fpx_nack* out_nack, int32_t* n_nack, int64_t* err_index) {
+  if (n_out) *n_out = 0;
+  if (n_nack) *n_nack = 0;
+  int c = range_call_begin(e, in, n, err_index, FPX_MENCIUS);
+  if (c != FPX_OK || n == 0) return c;
+  if (!out || !n_out || !out_nack || !n_nack) return FPX_ERR_INVALID_ARG;
+  CK(e, cudaSetDevice(e->cfg.device));
+  long long mx = 0;
+  for (int32_t i = 0; i < n; ++i) mx = std::max(mx, ((long long)in[i].slot_end - in[i].slot_start) / e->g.groups + 1);
+  CK(e, cudaMemcpyAsync(e->d_in, in, (size_t)n * 16, cudaMemcpyHostToDevice, e->stream));
+  RangeAcceptorParams P{e->g, (const int4*)e->d_in, n, (int4*)e->d_out_a, (int2*)e->d_out_b, e->rng_dec,
+                        e->acc_round, e->st};
+  range_acceptor_kernel<<<1, kRangeCtaThreads, 0, e->stream>>>(P);
+  RangeFillParams F{e->g, (const int4*)e->d_in, e->rng_dec, e->votes};
+  range_fill_kernel<<<dim3(fill_grid_x(e, mx, n), n), 256, 0, e->stream>>>(F);
+  e->launches += 2;
+  CK(e, cudaGetLastError());
+  fpx_sync_result r;
+  c = range_call_end(e, &r, err_index);
+  if (c != FPX_OK) return c;
+  *n_out = r.n_p2b;
+  *n_nack = r.n_nack;
+  if (r.n_p2b) CK(e, cudaMemcpyAsync(out, e->d_out_a, (size_t)r.n_p2b * 16, cudaMemcpyDeviceToHost, e->stream));
+  if (r.n_nack) CK(e, cudaMemcpyAsync(out_nack, e->d_out_b, (size_t)r.n_nack * 8, cudaMemcpyDeviceToHost, e->stream));
+  CK(e, cudaStreamSynchronize(e->stream));
+  return FPX_OK;
+}
+
+int fpx_mencius_range_phase2b(fpx_engine* e, const fpx_p2b_range* in, int32_t n, fpx_chosen_range* out,
+                              int32_t* n_out, int64_t* err_index) {
+  if (n_out) *n_out = 0;
+  int c = range_call_begin(e, in, n, err_index, FPX_MENCIUS);
+  if (c != FPX_OK || n == 0) return c;
+  if (!out || !n_out) return FPX_ERR_INVALID_ARG;
+  CK(e, cudaSetDevice(e->cfg.device));
+  RangeTable tab{e->rng_tab, (uint32_t)e->rng_cap - 1u, e->rng_cap};
+  if (e->rng_seq_base > 0xffffffffu - (uint32_t)n - 16u) {
+    renormalize_range_stamps_kernel<<<(e->rng_cap + 255) / 256, 256, 0, e->stream>>>(tab);
+    e->launches++;
+    e->rng_seq_base = 1;
+  }
+  CK(e, cudaMemcpyAsync(e->d_in, in, (size_t)n * 16, cudaMemcpyHostToDevice, e->stream));
+  RangeTallyParams P{e->g, PLState{e->rows, e->ovf_keys, e->ovf_rows}, tab, (const int4*)e->d_in, n,
+                     e->rng_seq_base, (int2*)e->d_out_b, e->rng_dec, e->st};
+  e->rng_seq_base += (uint32_t)n;
+  range_tally_kernel<<<1, kRangeCtaThreads, 0, e->stream>>>(P);
+  e->launches++;
+  CK(e, cudaGetLastError());
+  fpx_sync_result r;
+  c = range_call_end(e, &r, err_index);
+  if (c != FPX_OK) return c;
+  *n_out = r.n_chosen;
+  if (r.n_chosen) {
+    CK(e, cudaMemcpyAsync(out, e->d_out_b, (size_t)r.n_chosen * 8, cudaMemcpyDeviceToHost, e->stream));
+    CK(e, cudaStreamSynchronize(e->stream));
+  }
+  return FPX_OK;
+}
+
+int fpx_mencius_replica_chosen_range(fpx_engine* e, const fpx_chosen_range* in, int32_t n, int64_t* err_index) {
+  int c = range_call_begin(e, in, n, err_index, FPX_MENCIUS);
+  if (c != FPX_OK || n == 0) return c;
+  CK(e, cudaSetDevice(e->cfg.device));
+  if (e->rseq_base > 0xffffffffu - (uint32_t)n - 16u) {
+    size_t nl = (size_t)e->g.local_slots;
+    renormalize_rlog_kernel<<<(unsigned)((nl + 255) / 256), 256, 0, e->stream>>>(e->rlog, nl);
+    e->launches++;
+    e->rseq_base = 1;
+  }
+  long long mx = 0;
+  for (int32_t i = 0; i < n; ++i) mx = std::max(mx, ((long long)in[i].slot_end - in[i].slot_start) / e->g.lgroups + 1);
+  CK(e, cudaMemcpyAsync(e->d_in, in, (size_t)n * 8, cudaMemcpyHostToDevice, e->stream));
+  CK(e, cudaMemsetAsync(e->rng_dec, 0x7f, (size_t)n * 4, e->stream));
+  ReplicaRangeParams P{e->g, (const int2*)e->d_in, n, e->rseq_base, e->rlog, e->rng_dec, e->st};
+  e->rseq_base += (uint32_t)n;
+  dim3 grid(fill_grid_x(e, mx, n), n);
+  replica_range_first_kernel<<<grid, 256, 0, e->stream>>>(P);
+  replica_range_fill_kernel<<<grid, 256, 0, e->stream>>>(P);
+  e->launches += 2;
+  CK(e, cudaGetLastError());
+  fpx_sync_result r;
+  return range_call_end(e, &r, err_index);
 }
 
 int fpx_replica_chosen(fpx_engine* e, const fpx_chosen* in, int32_t n, int64_t* err_index) {

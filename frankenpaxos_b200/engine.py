@@ -13,6 +13,12 @@ P2A = np.dtype([("slot", "<i4"), ("round", "<i4"), ("value_id", "<i4"), ("dst", 
 P2B = np.dtype([("group", "<i4"), ("acceptor", "<i4"), ("slot", "<i4"), ("round", "<i4")])
 CHOSEN = np.dtype([("slot", "<i4"), ("value_id", "<i4")])
 NACK = np.dtype([("leader", "<i4"), ("round", "<i4")])
+# S/mencius Phase2aNoopRange / Phase2bNoopRange / ChosenNoopRange, S/vanillamencius Skip (include/fpx.h)
+P2A_RANGE = np.dtype([("slot_start", "<i4"), ("slot_end", "<i4"), ("round", "<i4"), ("dst", "<i4")])
+P2B_RANGE = np.dtype([("dst", "<i4"), ("slot_start", "<i4"), ("slot_end", "<i4"), ("round", "<i4")])
+CHOSEN_RANGE = np.dtype([("slot_start", "<i4"), ("slot_end", "<i4")])
+VM_SKIP = np.dtype([("server", "<i4"), ("slot_start", "<i4"), ("slot_stop", "<i4"), ("own", "<i4")])
+VALUE_NOOP = -(1 << 31)
 
 MULTIPAXOS, MENCIUS, VANILLA_MENCIUS = 0, 1, 2
 
@@ -196,6 +202,43 @@ class Engine:
         recs = np.ascontiguousarray(recs, dtype=P2B)
         err = C.c_int64(-1)
         self._check(self._L.fpx_vm_learn_chosen(self.h, recs.ctypes.data, len(recs), C.byref(err)), err.value)
+
+    def vm_skip(self, recs):
+        """Server.advanceWithSkips' log fill (own=1) / Server.handleSkip (own=0)."""
+        recs = np.ascontiguousarray(recs, dtype=VM_SKIP)
+        err = C.c_int64(-1)
+        self._check(self._L.fpx_vm_skip(self.h, recs.ctypes.data, len(recs), C.byref(err)), err.value)
+
+    # -- S/mencius Phase2aNoopRange path
+    def mencius_arm_range(self, recs):
+        recs = np.ascontiguousarray(recs, dtype=P2A_RANGE)
+        err = C.c_int64(-1)
+        self._check(self._L.fpx_mencius_arm_range(self.h, recs.ctypes.data, len(recs), C.byref(err)), err.value)
+
+    def mencius_acceptor_noop_range(self, recs):
+        recs = np.ascontiguousarray(recs, dtype=P2A_RANGE)
+        n = len(recs)
+        out = np.zeros(max(n, 1), dtype=P2B_RANGE)
+        nack = np.zeros(max(n, 1), dtype=NACK)
+        n1, n2, err = C.c_int32(0), C.c_int32(0), C.c_int64(-1)
+        self._check(self._L.fpx_mencius_acceptor_noop_range(self.h, recs.ctypes.data, n, out.ctypes.data, C.byref(n1),
+                                                            nack.ctypes.data, C.byref(n2), C.byref(err)), err.value)
+        return out[:n1.value].copy(), nack[:n2.value].copy()
+
+    def mencius_range_phase2b(self, recs):
+        recs = np.ascontiguousarray(recs, dtype=P2B_RANGE)
+        n = len(recs)
+        out = np.zeros(max(n, 1), dtype=CHOSEN_RANGE)
+        n1, err = C.c_int32(0), C.c_int64(-1)
+        self._check(self._L.fpx_mencius_range_phase2b(self.h, recs.ctypes.data, n, out.ctypes.data, C.byref(n1),
+                                                      C.byref(err)), err.value)
+        return out[:n1.value].copy()
+
+    def mencius_replica_chosen_range(self, recs):
+        recs = np.ascontiguousarray(recs, dtype=CHOSEN_RANGE)
+        err = C.c_int64(-1)
+        self._check(self._L.fpx_mencius_replica_chosen_range(self.h, recs.ctypes.data, len(recs), C.byref(err)),
+                    err.value)
 
     # -- device-pointer calls (raw device addresses, asynchronous on self.stream)
     def proxyleader_arm_dev(self, d_in, n):

@@ -93,7 +93,33 @@ def config_by_name(name):
     if name == "cfg3":   # Compartmentalized 2x3 grid, 10 proxy leaders, 4M slots
         return dict(f=1, num_acceptor_groups=2, acceptors_per_group=3, flexible=True, num_leaders=2,
                     num_replicas=2), 1 << 22
+    if name == "cfg5":   # vanilla Mencius n=7, f=3, 1M slots (single group of n servers)
+        return dict(f=3, num_acceptor_groups=1, acceptors_per_group=7, flexible=False, num_leaders=4,
+                    num_replicas=4), 1 << 20
     raise KeyError(name)
+
+
+def vanilla_cfg5(seed, f=3, n_slots=1 << 20, slot_stride=1, slot_offset=0):
+    """BASELINE cfg5: vanilla Mencius with n = 2f+1 servers, owner(slot) = slot % n
+    (S/vanillamencius/Server.scala:773, slotSystem).  Returns
+      req   one client request per slot at its owner (dst = owner)        -- Server.handleClientRequest :767-829
+      p2a   the owner's Phase2a to the n-1 other servers (:806-815), shuffled delivery
+      p2b   the Phase2b every such Phase2a produces in a fresh log (:1077-1081), shuffled
+    value_id = 3*slot+1."""
+    g = rng(seed)
+    n = 2 * f + 1
+    slots = (slot_offset + slot_stride * np.arange(n_slots, dtype=np.int64)).astype(np.int32)
+    req = np.zeros(n_slots, dtype=P2A)
+    req["slot"] = slots; req["round"] = 0; req["value_id"] = slots * 3 + 1; req["dst"] = slots % n
+    others = np.array([[s for s in range(n) if s != o] for o in range(n)], dtype=np.int32)
+    p = np.zeros(n_slots * (n - 1), dtype=P2A)
+    p["slot"] = np.repeat(slots, n - 1); p["round"] = 0; p["value_id"] = np.repeat(req["value_id"], n - 1)
+    p["dst"] = others[slots % n].reshape(-1)
+    p = p[g.permutation(len(p))]
+    b = np.zeros(len(p), dtype=P2B)
+    b["group"] = 0; b["acceptor"] = p["dst"]; b["slot"] = p["slot"]; b["round"] = 0
+    b = b[g.permutation(len(b))]
+    return req, p, b
 
 
 def workload(seed, cfg, n_slots, slot0=0, round_=0, slot_stride=1, slot_offset=0, partitions=None):

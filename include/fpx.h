@@ -61,6 +61,23 @@ typedef struct { int32_t slot, value_id; } fpx_chosen;
  * (S/multipaxos/Acceptor.scala:192-199). */
 typedef struct { int32_t leader, round; } fpx_nack;
 
+/* value_id of CommandBatchOrNoop().withNoop(Noop()): what the range fills below write. */
+#define FPX_VALUE_NOOP INT32_MIN
+
+/* S/mencius/Mencius.proto Phase2aNoopRange{slotStartInclusive, slotEndExclusive, round}
+ * as delivered to a proxy leader (dst ignored) or to acceptor dst = group<<16 | acceptor,
+ * group = leader_group * num_acceptor_groups + acceptor_group. */
+typedef struct { int32_t slot_start, slot_end, round, dst; } fpx_p2a_range;
+/* Phase2bNoopRange{acceptorGroupIndex, acceptorIndex, slotStartInclusive,
+ * slotEndExclusive, round}; the voter is packed in dst like above. */
+typedef struct { int32_t dst, slot_start, slot_end, round; } fpx_p2b_range;
+/* ChosenNoopRange{slotStartInclusive, slotEndExclusive}. */
+typedef struct { int32_t slot_start, slot_end; } fpx_chosen_range;
+/* S/vanillamencius Skip{serverIndex, startSlotInclusive, stopSlotExclusive} applied to
+ * server `server`'s log; own = 1: the fill advanceWithSkips does at the skipping server. */
+typedef struct { int32_t server, slot_start, slot_stop, own; } fpx_vm_skip_rec;
+#define FPX_MAX_RANGE_BATCH 65535   /* records per range call */
+
 /* ---- status ------------------------------------------------------------- */
 
 typedef enum {
@@ -84,6 +101,8 @@ typedef enum {
   FPX_ERR_BATCH_ORDER = -12,       /* EPaxos batch contract E1/E2 violated (two messages of
                                       one instance / one (instance, replica) in one call):
                                       split the batch at err_index and resubmit           */
+  FPX_ERR_CHECK_FAILED = -14,      /* a logger.check of the reference failed (vanilla Mencius
+                                      advanceWithSkips: a slot to skip is not vacant)   */
   FPX_ERR_EPAXOS_STATE = -13       /* transitionToPreAcceptPhase on a committed instance or
                                       with a regressing ballot: logger.fatal / checkLe,
                                       S/epaxos/Replica.scala:663-681                       */
@@ -270,6 +289,55 @@ int fpx_vm_phase2a(fpx_engine* e, const fpx_p2a* in, int32_t n, fpx_p2b* reply, 
  * that in.slot is chosen with value in.round: its entry becomes ChosenEntry; if it
  * coordinates the slot, phase2s(slot) is dropped. */
 int fpx_vm_learn_chosen(fpx_engine* e, const fpx_p2b* in, int32_t n, int64_t* err_index);
+
+/* Skips.  own = 1: the log fill of advanceWithSkips (:577-620) at the skipping server --
+ * its own slots slot_start, slot_start + n, ... < slot_stop become ChosenEntry(Noop); each
+ * must be vacant (logger.check(!log.contains) / check(!phase2s.contains), :613-614 ->
+ * FPX_ERR_CHECK_FAILED); nextSlot and skipSlots stay the caller's scalars.  own = 0:
+ * handleSkip (:1144-1168) at `server`: choose(slot, Noop) for the coordinator's slots of
+ * the range (log.put unconditionally, phase2s.remove, :622-625).  n <= FPX_MAX_RANGE_BATCH. */
+int fpx_vm_skip(fpx_engine* e, const fpx_vm_skip_rec* in, int32_t n, int64_t* err_index);
+
+/* ---- Mencius Phase2aNoopRange path (S/mencius), protocol FPX_MENCIUS ---------------
+ * A lagging leader group closes its gap with ONE message standing for the strided run
+ * of Noop slots {s in [start, end) : s = start (mod numLeaderGroups)} (Leader.scala:
+ * 742-764).  The four handlers below are the range forms of arm / acceptor_phase2a /
+ * proxyleader_phase2b / replica_chosen and share their state (the acceptors' rounds and
+ * vote cells, the replica log).  Deliver ranges and single-slot messages in separate
+ * calls, each a batch in delivery order; n <= FPX_MAX_RANGE_BATCH.  Preconditions the
+ * reference does not state (it would loop or index out of bounds): 0 <= start <= end <=
+ * slot_capacity (FPX_ERR_SLOT_RANGE), round as for Phase2a, dst an acceptor of leader
+ * group start % numLeaderGroups (FPX_ERR_BAD_ACCEPTOR).
+ *
+ * ProxyLeader.handlePhase2aNoopRange (S/mencius/ProxyLeader.scala:255-303): key
+ * SlotRound(start, end, round) present -> ignored, else PendingPhase2aNoopRange.  The
+ * key space is shared with Phase2a (slot, slot+1, round) (:217-219): a one-slot range and
+ * that slot's Phase2a exclude each other, first one wins (both directions checked here
+ * and in fpx_proxyleader_arm).  Table of overflow_capacity (>= 1024) keys
+ * (FPX_ERR_OVERFLOW_FULL).  [A Phase2b for a key held by a one-slot RANGE would be
+ * ignored by the reference (:319-332) and is FPX_ERR_UNKNOWN_SLOT_ROUND here; no
+ * execution produces it, the proxy leader never forwarded that Phase2a.] */
+int fpx_mencius_arm_range(fpx_engine* e, const fpx_p2a_range* in, int32_t n, int64_t* err_index);
+/* Acceptor.handlePhase2aNoopRange (S/mencius/Acceptor.scala:237-291): round < the
+ * acceptor's round -> Nack(round) to leaders(start % LG)(round % leadersPerGroup); else
+ * round = msg.round, the acceptor group's slots of the range get State(round, Noop)
+ * (first such slot, then stride numLeaderGroups * numAcceptorGroups, :263-277), reply
+ * Phase2bNoopRange.  Outputs compacted in delivery order like fpx_acceptor_phase2a. */
+int fpx_mencius_acceptor_noop_range(fpx_engine* e, const fpx_p2a_range* in, int32_t n, fpx_p2b_range* out,
+                                    int32_t* n_out, fpx_nack* out_nack, int32_t* n_nack, int64_t* err_index);
+/* ProxyLeader.handlePhase2bNoopRange (S/mencius/ProxyLeader.scala:355-412): unknown key ->
+ * logger.fatal (FPX_ERR_UNKNOWN_SLOT_ROUND), Done -> ignored, else record the vote and wait
+ * until EVERY acceptor group of the leader group has f+1 votes (:394-396); the completing
+ * delivery emits ChosenNoopRange(start, end), in delivery order. */
+int fpx_mencius_range_phase2b(fpx_engine* e, const fpx_p2b_range* in, int32_t n, fpx_chosen_range* out,
+                              int32_t* n_out, int64_t* err_index);
+/* Replica.handleChosenNoopRange (S/mencius/Replica.scala:464-486): slots start, start+LG,
+ * ... < end are put as Noop UNTIL THE FIRST ONE ALREADY IN THE LOG, where the reference's
+ * handler returns (:476-480).  Batch contract (FPX_ERR_BATCH_ORDER): two records of one
+ * call must not cover a common slot.  With shard_count > 1 "already in the log" is judged
+ * on this shard's slots only.  fpx_chosen_watermark afterwards is the first hole, i.e.
+ * where executeLog stops when it next runs. */
+int fpx_mencius_replica_chosen_range(fpx_engine* e, const fpx_chosen_range* in, int32_t n, int64_t* err_index);
 
 /* ---- EPaxos replica (S/epaxos/Replica.scala) ------------------------------
  * One fpx_epaxos handle = one replica's cmdLog (:298-330) and leaderStates

@@ -31,6 +31,7 @@
 #include <cstring>
 #include <map>
 #include <set>
+#include <tuple>
 #include <unordered_map>
 #include <vector>
 
@@ -399,10 +400,15 @@ struct P2a { int32_t slot, round, value_id, dst; };
 struct P2b { int32_t group, acceptor, slot, round; };
 struct Chosen { int32_t slot, value_id; };
 struct Nack { int32_t leader, round; };
+// S/mencius/Mencius.proto Phase2aNoopRange / Phase2bNoopRange / ChosenNoopRange (+ the recipient / voter in dst)
+struct P2aRange { int32_t slot_start, slot_end, round, dst; };
+struct P2bRange { int32_t dst, slot_start, slot_end, round; };
+struct ChosenRange { int32_t slot_start, slot_end; };
+constexpr int32_t kNoopValue = INT32_MIN;   // value id of CommandBatchOrNoop().withNoop(Noop())
 
 enum Status {
   kOk = 0, kInvalidArg = -1, kConfig = -2, kUnknownSlotRound = -4, kBadAcceptor = -5,
-  kSlotRange = -6, kRoundRange = -7
+  kSlotRange = -6, kRoundRange = -7, kCheckFailed = -14
 };
 
 struct Config {
@@ -443,6 +449,15 @@ struct MultiPaxos {
     std::set<std::pair<int, int>> phase2bs;  // keys of Pending.phase2bs
   };
   std::map<std::pair<int, int>, PLState> pl_states;
+  // S/mencius/ProxyLeader.scala:86-113: states are keyed SlotRound(slotStartInclusive,
+  // slotEndExclusive, round); a Phase2a of slot s lives under (s, s+1, round) (:217-219) and
+  // shares the key space with PendingPhase2aNoopRange entries.  pl_states holds the
+  // (s, s+1, round) keys as (s, round); pl_range_states the NoopRange ones.
+  struct RangeState {
+    bool done = false;
+    std::vector<std::set<int>> phase2bs;   // one map per acceptor group of the leader group (:101-106)
+  };
+  std::map<std::tuple<int, int, int>, RangeState> pl_range_states;
   // Replica.scala: log (BufferMap) + executedWatermark
   std::map<int, int> log;
   int executed_watermark = 0;
@@ -462,6 +477,8 @@ struct MultiPaxos {
     for (int i = 0; i < n; ++i) {
       auto key = std::make_pair(in[i].slot, in[i].round);
       if (pl_states.count(key)) continue;                     // :177-183
+      if (cfg.mencius && pl_range_states.count(std::make_tuple(in[i].slot, in[i].slot + 1, in[i].round)))
+        continue;                                             // mencius/ProxyLeader.scala:223 `case Some(_)`
       PLState s;
       s.value = in[i].value_id;
       pl_states[key] = s;                                     // :213
@@ -503,6 +520,9 @@ struct MultiPaxos {
     int nc = 0;
     for (int i = 0; i < n; ++i) {
       auto it = pl_states.find({in[i].slot, in[i].round});
+      if (it == pl_states.end() && cfg.mencius &&
+          pl_range_states.count(std::make_tuple(in[i].slot, in[i].slot + 1, in[i].round)))
+        continue;            // Some(Done) / Some(_: PendingPhase2aNoopRange): ignored (mencius/ProxyLeader.scala:319-332)
       if (it == pl_states.end()) {                            // :220-225 logger.fatal
         *err = i; *n_out = nc;
         return kUnknownSlotRound;
@@ -536,6 +556,103 @@ struct MultiPaxos {
       st.phase2bs.clear();
     }
     *n_out = nc;
+    return kOk;
+  }
+
+  // ---- S/mencius Phase2aNoopRange path --------------------------
+  int agroups() const { return cfg.groups / cfg.lgroups; }
+  // the engine's preconditions on a range record (the reference has none: it would loop / index
+  // out of bounds); same codes as the engine
+  int check_range(int start, int end, int round, int capacity) const {
+    if (start < 0 || end < start || end > capacity) return kSlotRange;
+    if (round < 0 || round > 0x7ffffff0) return kRoundRange;
+    return kOk;
+  }
+  // ProxyLeader.handlePhase2aNoopRange, S/mencius/ProxyLeader.scala:255-303
+  int arm_range(const P2aRange* in, int n, int capacity, int64_t* err) {
+    for (int i = 0; i < n; ++i) {
+      int c = check_range(in[i].slot_start, in[i].slot_end, in[i].round, capacity);
+      if (c != kOk) { *err = i; return c; }
+      auto key = std::make_tuple(in[i].slot_start, in[i].slot_end, in[i].round);
+      if (pl_range_states.count(key)) continue;                                  // :262-269 `case Some(_)`
+      if (in[i].slot_end == in[i].slot_start + 1 && pl_states.count({in[i].slot_start, in[i].round})) continue;
+      RangeState st;
+      st.phase2bs.resize(agroups());                                             // :297-301
+      pl_range_states[key] = st;
+    }
+    return kOk;
+  }
+  // Acceptor.handlePhase2aNoopRange, S/mencius/Acceptor.scala:237-291
+  int acceptor_noop_range(const P2aRange* in, int n, int capacity, P2bRange* out, int* n_out, Nack* out_nack,
+                          int* n_nack, int64_t* err) {
+    int np = 0, nn = 0;
+    const int LG = cfg.lgroups, AG = agroups();
+    for (int i = 0; i < n; ++i) {
+      int g = in[i].dst >> 16, a = in[i].dst & 0xffff;
+      int c = check_range(in[i].slot_start, in[i].slot_end, in[i].round, capacity);
+      if (c == kOk && (g < 0 || g >= cfg.groups || a >= cfg.per_group || g / AG != in[i].slot_start % LG))
+        c = kBadAcceptor;     // the acceptor belongs to another leader group than the range's slots
+      if (c != kOk) { *err = i; *n_out = np; *n_nack = nn; return c; }
+      Acceptor& acc = acceptors[g][a];
+      if (in[i].round < acc.round) {                                             // :245
+        int ldr = round_system.leader(in[i].round) + (in[i].slot_start % LG) * cfg.num_leaders;  // :250-252
+        out_nack[nn++] = Nack{ldr, acc.round};                                   // :253
+        continue;
+      }
+      acc.round = in[i].round;                                                   // :259
+      int start_slot = in[i].slot_start;                                         // :263-266
+      while ((start_slot / LG) % AG != g % AG) start_slot += LG;
+      for (int slot = start_slot; slot < in[i].slot_end; slot += LG * AG)        // :268-277
+        acc.states[slot] = {acc.round, kNoopValue};
+      out[np++] = P2bRange{in[i].dst, in[i].slot_start, in[i].slot_end, acc.round};  // :279-290
+    }
+    *n_out = np; *n_nack = nn;
+    return kOk;
+  }
+  // ProxyLeader.handlePhase2bNoopRange, S/mencius/ProxyLeader.scala:355-412
+  int range_phase2b(const P2bRange* in, int n, ChosenRange* out, int* n_out, int64_t* err) {
+    int nc = 0;
+    const int LG = cfg.lgroups, AG = agroups();
+    for (int i = 0; i < n; ++i) {
+      auto it = pl_range_states.find(std::make_tuple(in[i].slot_start, in[i].slot_end, in[i].round));
+      if (it == pl_range_states.end()) {
+        if (in[i].slot_end == in[i].slot_start + 1 && pl_states.count({in[i].slot_start, in[i].round}))
+          continue;                                    // Some(Done) / Some(_: PendingPhase2a): ignored (:372-388)
+        *err = i; *n_out = nc;
+        return kUnknownSlotRound;                      // :364-370 logger.fatal
+      }
+      RangeState& st = it->second;
+      if (st.done) continue;                           // :372-378
+      int g = in[i].dst >> 16, a = in[i].dst & 0xffff;
+      if (g < 0 || g >= cfg.groups || a >= cfg.per_group || g / AG != in[i].slot_start % LG) {
+        *err = i; *n_out = nc;
+        return kBadAcceptor;                           // phase2bs(acceptorGroupIndex): index out of bounds
+      }
+      st.phase2bs[g % AG].insert(a);                   // :392-393
+      bool wait = false;
+      for (auto& grp : st.phase2bs) wait |= (int)grp.size() < cfg.f + 1;   // :394-396
+      if (wait) continue;
+      out[nc++] = ChosenRange{in[i].slot_start, in[i].slot_end};          // :399-409
+      st.done = true;                                                       // :412
+    }
+    *n_out = nc;
+    return kOk;
+  }
+  // Replica.handleChosenNoopRange, S/mencius/Replica.scala:464-486: slots start, start+LG, ...
+  // are filled with Noop UNTIL THE FIRST ONE ALREADY IN THE LOG, where the handler returns
+  // (:476-480 -- the `return` leaves the whole handler, not just the iteration).
+  int replica_chosen_range(const ChosenRange* in, int n, int capacity, int64_t* err) {
+    for (int i = 0; i < n; ++i) {
+      int c = check_range(in[i].slot_start, in[i].slot_end, 0, capacity);
+      if (c != kOk) { *err = i; return c; }
+      bool returned = false;
+      for (int slot = in[i].slot_start; slot < in[i].slot_end; slot += cfg.lgroups) {
+        if (log.count(slot)) { returned = true; break; }
+        log[slot] = kNoopValue;                                                  // :481-483
+      }
+      if (!returned)
+        while (log.count(executed_watermark)) executed_watermark++;              // executeLog() (:487)
+    }
     return kOk;
   }
 
@@ -868,6 +985,30 @@ struct VanillaMencius {
     *n_out = nc;
     return kOk;
   }
+  // Skips.  rec {server, start, stop, own}:
+  //  own = 1  the log fill of advanceWithSkips at the skipping server itself (:610-620): its own
+  //           slots start, start+n, ... < stop become ChosenEntry(Noop); each must be vacant
+  //           (logger.check(!log.contains), check(!phase2s.contains)).  nextSlot / skipSlots are
+  //           the caller's scalars.
+  //  own = 0  handleSkip at `server` (:1144-1168): choose(slot, Noop) for the coordinator's slots
+  //           start, start+n, ... < stop (log.put is unconditional, phase2s.remove, :622-625).
+  struct VmSkip { int32_t server, slot_start, slot_stop, own; };
+  int skip(const VmSkip* in, int cnt, int capacity, int64_t* err) {
+    for (int i = 0; i < cnt; ++i) {
+      int s = in[i].server;
+      if (s < 0 || s >= n) { *err = i; return kBadAcceptor; }
+      if (in[i].slot_start < 0 || in[i].slot_stop < in[i].slot_start || in[i].slot_stop > capacity) { *err = i; return kSlotRange; }
+      if (in[i].own && in[i].slot_start % n != s) { *err = i; return kBadAcceptor; }
+      for (int slot = in[i].slot_start; slot < in[i].slot_stop; slot += n) {       // nextClassicRound(coordinator, slot)
+        if (in[i].own) {
+          if (logs[s].count(slot) || phase2s.count(slot)) { *err = i; return kCheckFailed; }  // :613-614
+        }
+        logs[s][slot] = LogEntry{3, -1, -1, kNoopValue};                             // :615-618 / :624
+        if (slot % n == s) phase2s.erase(slot);                                      // :625
+      }
+    }
+    return kOk;
+  }
   void learn_chosen(const P2b* in, int cnt) {                                          // handleChosen -> choose
     for (int i = 0; i < cnt; ++i) {
       logs[in[i].acceptor][in[i].slot] = LogEntry{3, -1, -1, in[i].round};
@@ -1019,7 +1160,31 @@ int fpo_mp_proxyleader_phase2b(void* p, const P2b* in, int n, Chosen* out, int* 
 int fpo_mp_replica_chosen(void* p, const Chosen* in, int n) {
   return ((MultiPaxos*)p)->replica_chosen(in, n);
 }
+int fpo_mp_arm_range(void* p, const P2aRange* in, int n, int capacity, int64_t* err) {
+  *err = -1;
+  return ((MultiPaxos*)p)->arm_range(in, n, capacity, err);
+}
+int fpo_mp_acceptor_noop_range(void* p, const P2aRange* in, int n, int capacity, P2bRange* out, int* n_out,
+                               Nack* out_nack, int* n_nack, int64_t* err) {
+  *err = -1;
+  return ((MultiPaxos*)p)->acceptor_noop_range(in, n, capacity, out, n_out, out_nack, n_nack, err);
+}
+int fpo_mp_range_phase2b(void* p, const P2bRange* in, int n, ChosenRange* out, int* n_out, int64_t* err) {
+  *err = -1;
+  return ((MultiPaxos*)p)->range_phase2b(in, n, out, n_out, err);
+}
+int fpo_mp_replica_chosen_range(void* p, const ChosenRange* in, int n, int capacity, int64_t* err) {
+  *err = -1;
+  return ((MultiPaxos*)p)->replica_chosen_range(in, n, capacity, err);
+}
 int fpo_mp_executed_watermark(void* p) { return ((MultiPaxos*)p)->executed_watermark; }
+// where executeLog would stop if it ran now (the engine's fpx_chosen_watermark)
+int fpo_mp_first_hole(void* p) {
+  MultiPaxos* m = (MultiPaxos*)p;
+  int w = m->executed_watermark;
+  while (m->log.count(w)) ++w;
+  return w;
+}
 void fpo_mp_snapshot_acceptor(void* p, int g, int a, int* round, int* max_voted_slot, int first_slot,
                               int n_slots, int* vote_round, int* vote_value) {
   Acceptor& acc = ((MultiPaxos*)p)->acceptors[g][a];
@@ -1131,6 +1296,10 @@ int fpo_vm_phase2b(void* p, const P2b* in, int n, Chosen* out, int* n_out, int64
   return ((VanillaMencius*)p)->phase2b(in, n, out, n_out, err);
 }
 void fpo_vm_learn_chosen(void* p, const P2b* in, int n) { ((VanillaMencius*)p)->learn_chosen(in, n); }
+int fpo_vm_skip(void* p, const void* in, int n, int capacity, int64_t* err) {
+  *err = -1;
+  return ((VanillaMencius*)p)->skip((const VanillaMencius::VmSkip*)in, n, capacity, err);
+}
 // server's log entry for n_slots slots: kind (0 none, 2 pending, 3 chosen), round, value
 void fpo_vm_snapshot(void* p, int server, int first_slot, int n_slots, int* kind, int* round, int* value) {
   auto& log = ((VanillaMencius*)p)->logs[server];

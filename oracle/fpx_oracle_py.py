@@ -16,6 +16,11 @@ P2A = np.dtype([("slot", "<i4"), ("round", "<i4"), ("value_id", "<i4"), ("dst", 
 P2B = np.dtype([("group", "<i4"), ("acceptor", "<i4"), ("slot", "<i4"), ("round", "<i4")])
 CHOSEN = np.dtype([("slot", "<i4"), ("value_id", "<i4")])
 NACK = np.dtype([("leader", "<i4"), ("round", "<i4")])
+P2A_RANGE = np.dtype([("slot_start", "<i4"), ("slot_end", "<i4"), ("round", "<i4"), ("dst", "<i4")])
+P2B_RANGE = np.dtype([("dst", "<i4"), ("slot_start", "<i4"), ("slot_end", "<i4"), ("round", "<i4")])
+CHOSEN_RANGE = np.dtype([("slot_start", "<i4"), ("slot_end", "<i4")])
+VM_SKIP = np.dtype([("server", "<i4"), ("slot_start", "<i4"), ("slot_stop", "<i4"), ("own", "<i4")])
+NOOP = -(1 << 31)
 
 
 def build(force=False):
@@ -84,6 +89,12 @@ def lib():
         L.fpo_mp_proxyleader_phase2b.restype = i32
         L.fpo_mp_replica_chosen.argtypes = [vp, vp, i32]; L.fpo_mp_replica_chosen.restype = i32
         L.fpo_mp_executed_watermark.argtypes = [vp]; L.fpo_mp_executed_watermark.restype = i32
+        L.fpo_mp_first_hole.argtypes = [vp]; L.fpo_mp_first_hole.restype = i32
+        L.fpo_mp_arm_range.argtypes = [vp, vp, i32, i32, i64p]; L.fpo_mp_arm_range.restype = i32
+        L.fpo_mp_acceptor_noop_range.argtypes = [vp, vp, i32, i32, vp, ip, vp, ip, i64p]
+        L.fpo_mp_acceptor_noop_range.restype = i32
+        L.fpo_mp_range_phase2b.argtypes = [vp, vp, i32, vp, ip, i64p]; L.fpo_mp_range_phase2b.restype = i32
+        L.fpo_mp_replica_chosen_range.argtypes = [vp, vp, i32, i32, i64p]; L.fpo_mp_replica_chosen_range.restype = i32
         L.fpo_mp_snapshot_acceptor.argtypes = [vp, i32, i32, ip, ip, i32, i32, vp, vp]
         L.fpo_mp_snapshot_log.argtypes = [vp, i32, i32, vp]
         L.fpo_mp_phase1a.argtypes = [vp, i32, i32, i32]; L.fpo_mp_phase1a.restype = i32
@@ -104,6 +115,7 @@ def lib():
         L.fpo_vm_phase2a.argtypes = [vp, vp, i32, vp, i64p]; L.fpo_vm_phase2a.restype = i32
         L.fpo_vm_phase2b.argtypes = [vp, vp, i32, vp, ip, i64p]; L.fpo_vm_phase2b.restype = i32
         L.fpo_vm_learn_chosen.argtypes = [vp, vp, i32]
+        L.fpo_vm_skip.argtypes = [vp, vp, i32, i32, i64p]; L.fpo_vm_skip.restype = i32
         L.fpo_vm_snapshot.argtypes = [vp, i32, i32, i32, vp, vp, vp]
         _lib = L
     return _lib
@@ -252,6 +264,41 @@ class MultiPaxos:
     def executed_watermark(self):
         return lib().fpo_mp_executed_watermark(self.h)
 
+    def first_hole(self):
+        """Where executeLog would stop if it ran now (what fpx_chosen_watermark reports)."""
+        return lib().fpo_mp_first_hole(self.h)
+
+    # -- S/mencius Phase2aNoopRange path; `capacity` = the engine's slot_capacity (range precondition)
+    def arm_range(self, recs, capacity):
+        recs = np.ascontiguousarray(recs, dtype=P2A_RANGE)
+        err = C.c_int64(-1)
+        st = lib().fpo_mp_arm_range(self.h, recs.ctypes.data, len(recs), capacity, C.byref(err))
+        return st, err.value
+
+    def acceptor_noop_range(self, recs, capacity):
+        recs = np.ascontiguousarray(recs, dtype=P2A_RANGE)
+        n = len(recs)
+        out = np.zeros(max(n, 1), dtype=P2B_RANGE)
+        nack = np.zeros(max(n, 1), dtype=NACK)
+        n1, n2, err = C.c_int(0), C.c_int(0), C.c_int64(-1)
+        st = lib().fpo_mp_acceptor_noop_range(self.h, recs.ctypes.data, n, capacity, out.ctypes.data, C.byref(n1),
+                                              nack.ctypes.data, C.byref(n2), C.byref(err))
+        return st, err.value, out[:n1.value].copy(), nack[:n2.value].copy()
+
+    def range_phase2b(self, recs):
+        recs = np.ascontiguousarray(recs, dtype=P2B_RANGE)
+        n = len(recs)
+        out = np.zeros(max(n, 1), dtype=CHOSEN_RANGE)
+        n1, err = C.c_int(0), C.c_int64(-1)
+        st = lib().fpo_mp_range_phase2b(self.h, recs.ctypes.data, n, out.ctypes.data, C.byref(n1), C.byref(err))
+        return st, err.value, out[:n1.value].copy()
+
+    def replica_chosen_range(self, recs, capacity):
+        recs = np.ascontiguousarray(recs, dtype=CHOSEN_RANGE)
+        err = C.c_int64(-1)
+        st = lib().fpo_mp_replica_chosen_range(self.h, recs.ctypes.data, len(recs), capacity, C.byref(err))
+        return st, err.value
+
     def snapshot_acceptor(self, group, acceptor, first_slot, n_slots):
         vr = np.zeros(max(n_slots, 1), dtype=np.int32)
         vv = np.zeros(max(n_slots, 1), dtype=np.int32)
@@ -395,6 +442,11 @@ class VanillaMencius:
     def learn_chosen(self, recs):
         recs = np.ascontiguousarray(recs, dtype=P2B)
         lib().fpo_vm_learn_chosen(self.h, recs.ctypes.data, len(recs))
+
+    def skip(self, recs, capacity):
+        recs = np.ascontiguousarray(recs, dtype=VM_SKIP)
+        err = C.c_int64(-1)
+        return lib().fpo_vm_skip(self.h, recs.ctypes.data, len(recs), capacity, C.byref(err)), err.value
 
     def snapshot(self, server, first_slot, n_slots):
         k = np.zeros(max(n_slots, 1), np.int32); r = np.zeros(max(n_slots, 1), np.int32); v = np.zeros(max(n_slots, 1), np.int32)

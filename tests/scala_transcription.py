@@ -134,3 +134,116 @@ class System:
                 out.append(r[1:])
                 self.replica.handle_chosen(r[1], r[2])
         return 0, -1, out
+
+
+# =============================================================================
+# S/mencius: the Phase2aNoopRange path next to the single-slot one, transcribed
+# from mencius/Acceptor.scala, mencius/ProxyLeader.scala, mencius/Replica.scala.
+# One leader group's view is enough for the acceptors; the proxy leader and the
+# replica see every leader group.
+# =============================================================================
+NOOP = "Noop"
+
+
+class MenciusAcceptor:  # S/mencius/Acceptor.scala:59-139
+    def __init__(self, leader_group, acceptor_group, index, num_leader_groups, num_acceptor_groups, leaders_per_group):
+        self.leader_group_index, self.acceptor_group_index, self.index = leader_group, acceptor_group, index
+        self.LG, self.AG, self.leaders_per_group = num_leader_groups, num_acceptor_groups, leaders_per_group
+        self.round = -1            # :128
+        self.states = {}           # :131
+
+    def acceptor_group_index_by_slot(self, slot):  # :134-137
+        return (slot // self.LG) % self.AG
+
+    def _nack(self, slot, round_):
+        # leaders(slotSystem.leader(slot))(roundSystem.leader(round)) (:215-219, :250-252)
+        return ("Nack", (slot % self.LG, round_ % self.leaders_per_group), self.round)
+
+    def handle_phase2a(self, slot, round_, value):  # :202-235
+        if round_ < self.round:
+            return self._nack(slot, round_)
+        self.round = round_
+        self.states[slot] = (self.round, value)
+        return ("Phase2b", self.acceptor_group_index, self.index, slot, self.round)
+
+    def handle_phase2a_noop_range(self, start, end, round_):  # :237-291
+        if round_ < self.round:                                   # :245
+            return self._nack(start, round_)                      # :250-254
+        self.round = round_                                       # :259
+        start_slot = start                                        # :263
+        while self.acceptor_group_index_by_slot(start_slot) != self.acceptor_group_index:   # :264-266
+            start_slot += self.LG
+        for slot in range(start_slot, end, self.LG * self.AG):    # :268-272
+            self.states[slot] = (self.round, NOOP)                # :273-276
+        return ("Phase2bNoopRange", self.acceptor_group_index, self.index, start, end, self.round)  # :279-290
+
+
+class MenciusProxyLeader:  # S/mencius/ProxyLeader.scala:67-412
+    DONE = "Done"
+
+    def __init__(self, f, num_leader_groups, num_acceptor_groups):
+        self.f, self.LG, self.AG = f, num_leader_groups, num_acceptor_groups
+        self.states = {}           # :150  SlotRound(start, end, round) -> state
+
+    def handle_phase2a(self, slot, round_, value):  # :216-253
+        key = (slot, slot + 1, round_)
+        if key in self.states:
+            return
+        self.states[key] = ("PendingPhase2a", value, {})
+
+    def handle_phase2a_noop_range(self, start, end, round_):  # :255-303
+        key = (start, end, round_)
+        if key in self.states:                                    # :262-269
+            return
+        self.states[key] = ("PendingPhase2aNoopRange", [dict() for _ in range(self.AG)])   # :297-301
+
+    def handle_phase2b(self, acceptor_index, slot, round_):  # :305-353
+        key = (slot, slot + 1, round_)
+        st = self.states.get(key)
+        if st is None:
+            raise Fatal("never sent")
+        if st == self.DONE or st[0] == "PendingPhase2aNoopRange":
+            return None
+        st[2][acceptor_index] = True                              # :334
+        if len(st[2]) < self.f + 1:                               # :335-337
+            return None
+        self.states[key] = self.DONE
+        return ("Chosen", slot, st[1])
+
+    def handle_phase2b_noop_range(self, acceptor_group_index, acceptor_index, start, end, round_):  # :355-412
+        key = (start, end, round_)
+        st = self.states.get(key)
+        if st is None:                                            # :364-370
+            raise Fatal("never sent a Phase2aNoopRange")
+        if st == self.DONE or st[0] == "PendingPhase2a":         # :372-388
+            return None
+        phase2bs = st[1]
+        phase2bs[acceptor_group_index][acceptor_index] = True     # :392-393 (IndexError = out of bounds)
+        if any(len(m) < self.f + 1 for m in phase2bs):            # :394-396
+            return None
+        self.states[key] = self.DONE                              # :412
+        return ("ChosenNoopRange", start, end)                    # :399-409
+
+
+class MenciusReplica:  # S/mencius/Replica.scala:325-370, 400-486
+    def __init__(self, num_leader_groups):
+        self.LG = num_leader_groups
+        self.log = {}
+        self.executed_watermark = 0
+
+    def _execute_log(self):
+        while self.executed_watermark in self.log:
+            self.executed_watermark += 1
+
+    def handle_chosen(self, slot, value):  # :400-416
+        if slot in self.log:
+            return
+        self.log[slot] = value
+        self._execute_log()
+
+    def handle_chosen_noop_range(self, start, end):  # :464-487
+        for slot in range(start, end, self.LG):                   # :471-473
+            if slot in self.log:                                  # :474-480
+                return                                            # leaves the handler
+            self.log[slot] = NOOP                                 # :481-483
+        self._execute_log()                                       # :487

@@ -573,3 +573,55 @@ def test_full_size_properties_cfg4_epaxos():
     assert len(decided) == len(lead)
     assert (ev[:, 0] == 3).sum() == len(lead)          # one timer event per instance (f+1 < n-1)
     eng.close()
+
+
+def test_full_size_properties_cfg5_vanilla_mencius():
+    """BASELINE cfg5 at full size: n=7, f=3, 2^20 slots, owner = slot % 7, 6 Phase2as and up
+    to 6 Phase2bs per slot.  Every Phase2a in a fresh log is answered Phase2b(round 0); a slot
+    is chosen by the 3rd remote vote in delivery order (own vote pre-seeded, quorum f+1 = 4,
+    Server.scala:818-825,1122-1125); later votes hit a ChosenEntry and are dropped (:1090-1093)."""
+    from frankenpaxos_b200 import VANILLA_MENCIUS
+    cfg, n_slots = T.config_by_name("cfg5")
+    f, n = cfg["f"], cfg["acceptors_per_group"]
+    eng = Engine(slot_capacity=n_slots, max_batch=(n - 1) * n_slots, protocol=VANILLA_MENCIUS, **cfg)
+    req, p, b = T.vanilla_cfg5(2, f, n_slots)
+    eng.vm_client_request(req)
+    rep = eng.vm_phase2a(p)
+    assert (rep["group"] == 0).all()                       # kind 0 = Phase2b
+    assert np.array_equal(rep["acceptor"], p["dst"]) and np.array_equal(rep["slot"], p["slot"])
+    assert (rep["round"] == 0).all()
+    c = eng.proxyleader_phase2b(b)
+    assert len(c) == n_slots
+    assert np.array_equal(np.sort(c["slot"]), np.arange(n_slots))
+    assert np.array_equal(c["value_id"], c["slot"] * 3 + 1)
+    # completing vote of a slot = its f-th (3rd) remote vote in delivery order
+    order = np.lexsort((np.arange(len(b)), b["slot"]))
+    third = order.reshape(n_slots, n - 1)[:, f - 1]
+    assert np.array_equal(c["slot"], b["slot"][np.sort(third)])
+    # replaying every vote afterwards changes nothing (ChosenEntry is absorbing)
+    assert len(eng.proxyleader_phase2b(b[: 1 << 18])) == 0
+    eng.close()
+
+
+def test_vanilla_mencius_sharded_by_slot_residue():
+    """cfg5's multi-GPU layout: shard slot % 8; the shards' Chosen streams
+    partition the unsharded stream."""
+    from frankenpaxos_b200 import VANILLA_MENCIUS
+    cfg, _ = T.config_by_name("cfg5")
+    f, n, P, per = cfg["f"], cfg["acceptors_per_group"], 8, 1500
+    whole = []
+    for gi in range(P):
+        eng = Engine(slot_capacity=per * P, max_batch=1 << 16, protocol=VANILLA_MENCIUS, shard_index=gi,
+                     shard_count=P, **cfg)
+        req, p, b = T.vanilla_cfg5(10 + gi, f, per, slot_stride=P, slot_offset=gi)
+        eng.vm_client_request(req)
+        assert (eng.vm_phase2a(p)["group"] == 0).all()
+        c = eng.proxyleader_phase2b(b)
+        assert len(c) == per and (c["slot"] % P == gi).all()
+        whole.append(c)
+        # a slot of another shard is a range error
+        with pytest.raises(FpxError):
+            eng.vm_phase2a(np.array([((gi + 1) % P, 0, 1, ((gi + 1) % P % n + 1) % n)], dtype=P2A))
+        eng.close()
+    allc = np.concatenate(whole)
+    assert np.array_equal(np.sort(allc["slot"]), np.arange(per * P))
