@@ -93,3 +93,47 @@ JNIEXPORT_ jint_ Java_frankenpaxos_gpu_Native_snapshotAcceptor(JNIEnv_* env, jcl
   return fpx_snapshot_acceptor((fpx_engine*)P(h), group, acceptor, (int32_t*)P(round), (int32_t*)P(max_voted),
                                first_slot, n_slots, (int32_t*)P(vote_round), (int32_t*)P(vote_value));
 }
+
+/* ---- S/mencius Phase2aNoopRange path and S/vanillamencius Skip (include/fpx.h) ---- */
+
+/* int menciusArmRange(long h, long in, int n, long err) */
+JNIEXPORT_ jint_ Java_frankenpaxos_gpu_Native_menciusArmRange(JNIEnv_* env, jclass_ cls, jlong_ h, jlong_ in, jint_ n,
+                                                              jlong_ err_index) {
+  (void)env; (void)cls;
+  return fpx_mencius_arm_range((fpx_engine*)P(h), (const fpx_p2a_range*)P(in), n, (int64_t*)P(err_index));
+}
+
+/* int menciusAcceptorNoopRange(long h, long in, int n, long out, long nOut, long outNack, long nNack, long err) */
+JNIEXPORT_ jint_ Java_frankenpaxos_gpu_Native_menciusAcceptorNoopRange(JNIEnv_* env, jclass_ cls, jlong_ h, jlong_ in,
+                                                                       jint_ n, jlong_ out, jlong_ n_out,
+                                                                       jlong_ out_nack, jlong_ n_nack,
+                                                                       jlong_ err_index) {
+  (void)env; (void)cls;
+  return fpx_mencius_acceptor_noop_range((fpx_engine*)P(h), (const fpx_p2a_range*)P(in), n, (fpx_p2b_range*)P(out),
+                                         (int32_t*)P(n_out), (fpx_nack*)P(out_nack), (int32_t*)P(n_nack),
+                                         (int64_t*)P(err_index));
+}
+
+/* int menciusRangePhase2b(long h, long in, int n, long out, long nOut, long err) */
+JNIEXPORT_ jint_ Java_frankenpaxos_gpu_Native_menciusRangePhase2b(JNIEnv_* env, jclass_ cls, jlong_ h, jlong_ in,
+                                                                  jint_ n, jlong_ out, jlong_ n_out,
+                                                                  jlong_ err_index) {
+  (void)env; (void)cls;
+  return fpx_mencius_range_phase2b((fpx_engine*)P(h), (const fpx_p2b_range*)P(in), n, (fpx_chosen_range*)P(out),
+                                   (int32_t*)P(n_out), (int64_t*)P(err_index));
+}
+
+/* int menciusReplicaChosenRange(long h, long in, int n, long err) */
+JNIEXPORT_ jint_ Java_frankenpaxos_gpu_Native_menciusReplicaChosenRange(JNIEnv_* env, jclass_ cls, jlong_ h,
+                                                                        jlong_ in, jint_ n, jlong_ err_index) {
+  (void)env; (void)cls;
+  return fpx_mencius_replica_chosen_range((fpx_engine*)P(h), (const fpx_chosen_range*)P(in), n,
+                                          (int64_t*)P(err_index));
+}
+
+/* int vmSkip(long h, long in, int n, long err) */
+JNIEXPORT_ jint_ Java_frankenpaxos_gpu_Native_vmSkip(JNIEnv_* env, jclass_ cls, jlong_ h, jlong_ in, jint_ n,
+                                                     jlong_ err_index) {
+  (void)env; (void)cls;
+  return fpx_vm_skip((fpx_engine*)P(h), (const fpx_vm_skip_rec*)P(in), n, (int64_t*)P(err_index));
+}
