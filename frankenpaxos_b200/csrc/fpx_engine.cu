@@ -66,6 +66,7 @@ struct fpx_engine {
   uint32_t parity = 0;                 // nack counter the next acceptor launch uses
   int grid_acceptor = 0;               // co-resident CTAs of the cooperative kernels
   int grid_tally = 0;
+  int occ_acceptor = 0, occ_tally = 0; // resident CTAs per SM each kernel could have alone
   int tally_per_cap = 0;               // max records per warp range (shared-memory buffer)
   int num_sms = 0;
   uint32_t seq_base = 1;               // Phase2b delivery sequence numbers
@@ -268,12 +269,14 @@ int fpx_create(fpx_engine** out, const fpx_config* cfg) {
     int occ = 0;
     CKC(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, acceptor_phase2a_kernel, kThreads,
                                                       (size_t)g.num_keys * kThreads * 4));
+    e->occ_acceptor = std::max(occ, 1);
     e->grid_acceptor = std::min(std::max(occ, 1) * e->num_sms, kMaxGrid);
     const int smem_cap = 56 * 1024;  // Chosen buffer: kWarps * per * 8 bytes
     e->tally_per_cap = smem_cap / (kWarps * 8);
     const void* tk = tally_kernel_ptr(g.row_words);
     CKC(cudaFuncSetAttribute(tk, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_cap));
     CKC(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, tk, kThreads, smem_cap));
+    e->occ_tally = std::max(occ, 1);
     e->grid_tally = std::min(std::max(occ, 1) * e->num_sms, kMaxGrid);
   }
   CKC(cudaMalloc(&e->conflicts, kMaxConflicts * 8));
@@ -312,6 +315,15 @@ int fpx_reset(fpx_engine* e) {
 }
 
 void* fpx_stream(fpx_engine* e) { return e ? (void*)e->stream : nullptr; }
+
+int fpx_set_coop_ctas_per_sm(fpx_engine* e, int32_t ctas_per_sm) {
+  if (!e || ctas_per_sm < 0) return FPX_ERR_INVALID_ARG;
+  int a = ctas_per_sm == 0 ? e->occ_acceptor : std::min(e->occ_acceptor, ctas_per_sm);
+  int t = ctas_per_sm == 0 ? e->occ_tally : std::min(e->occ_tally, ctas_per_sm);
+  e->grid_acceptor = std::min(a * e->num_sms, kMaxGrid);
+  e->grid_tally = std::min(t * e->num_sms, kMaxGrid);
+  return FPX_OK;
+}
 
 // Undocumented profiling aid (not part of include/fpx.h): phase-boundary
 // timestamps (ns) CTA 0 of the last acceptor / tally launch recorded.

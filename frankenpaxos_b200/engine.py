@@ -259,6 +259,11 @@ class Engine:
     def chosen_watermark_dev(self, d_out=None):
         self._check(self._L.fpx_chosen_watermark_dev(self.h, d_out))
 
+    def set_coop_ctas_per_sm(self, k):
+        """Cap the cooperative kernels at k resident CTAs per SM (0 = full grid) so that
+        several engines can run side by side on one GPU."""
+        self._check(self._L.fpx_set_coop_ctas_per_sm(self.h, k))
+
     def sync(self, check=True):
         r = _lib.SyncResult()
         st = self._L.fpx_sync(self.h, C.byref(r))

@@ -449,6 +449,12 @@ int fpx_sync(fpx_engine* e, fpx_sync_result* out);
 /* The engine's CUDA stream (a cudaStream_t) so a caller can order its own work
  * (events, NCCL collectives) with the engine's. */
 void* fpx_stream(fpx_engine* e);
+/* Several engines (slot-residue shards) may share one GPU, each on its own stream.  The
+ * acceptor and tally kernels are persistent cooperative launches sized to fill the GPU
+ * (SMs x resident CTAs), and a cooperative launch waits until its whole grid fits; capping
+ * an engine at ctas_per_sm resident CTAs per SM lets the kernels of different engines run
+ * side by side instead of one after the other.  0 restores the full grid. */
+int fpx_set_coop_ctas_per_sm(fpx_engine* e, int32_t ctas_per_sm);
 /* Kernels launched by this handle since creation (bench.py's gpu_launches). */
 int64_t fpx_launch_count(const fpx_engine* e);
 

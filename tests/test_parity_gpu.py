@@ -239,11 +239,15 @@ def test_adversarial_random_traces(seed, shape):
     else:
         cfg = dict(f=1, num_acceptor_groups=3, acceptors_per_group=3, flexible=False, num_leaders=2,
                    num_replicas=2)
-    g = T.rng(1000 * seed + len(shape))
-    n_slots = 3000
-    eng, ora = H.make_pair(cfg, n_slots, max_batch=1 << 16, overflow_capacity=1 << 13)
+    _adversarial(cfg, 1000 * seed + len(shape), 3000, 2500)
+
+
+def _adversarial(cfg, seed, n_slots, kmax, coop_ctas_per_sm=0, max_batch=1 << 16):
+    g = T.rng(seed)
+    eng, ora = H.make_pair(cfg, n_slots, max_batch=max_batch, overflow_capacity=1 << 13 if n_slots <= 3000 else 1 << 20)
+    eng.set_coop_ctas_per_sm(coop_ctas_per_sm)
     for phase in range(4):
-        k = int(g.integers(1, 2500))
+        k = int(g.integers(1, kmax))
         slots = g.integers(0, n_slots, size=k).astype(np.int32)
         rounds = g.integers(0, 4, size=k).astype(np.int32) if phase else np.zeros(k, dtype=np.int32)
         values = (slots * 8 + rounds).astype(np.int32)   # one value per (slot, round)
@@ -269,6 +273,15 @@ def test_adversarial_random_traces(seed, shape):
             H.replica(eng, ora, c)
     H.compare_log(eng, ora, 0, n_slots)
     eng.close()
+
+
+@pytest.mark.parametrize("ctas_per_sm", [1, 2, 0])
+def test_results_do_not_depend_on_the_grid_size(ctas_per_sm):
+    """The persistent kernels split the delivery stream into per-warp ranges; the outputs must be
+    the same for any grid (fpx_set_coop_ctas_per_sm: engines sharing a GPU run smaller grids).
+    Batches of up to 6 * 10^5 records, i.e. more CTAs than one wave at 1 CTA/SM."""
+    cfg = dict(f=2, num_acceptor_groups=1, acceptors_per_group=5, flexible=False, num_leaders=3, num_replicas=3)
+    _adversarial(cfg, 4242, 150000, 120000, coop_ctas_per_sm=ctas_per_sm, max_batch=1 << 20)
 
 
 def test_unknown_key_error_index_is_first_in_order():
