@@ -275,13 +275,13 @@ def _adversarial(cfg, seed, n_slots, kmax, coop_ctas_per_sm=0, max_batch=1 << 16
     eng.close()
 
 
-@pytest.mark.parametrize("ctas_per_sm", [1, 2, 0])
+@pytest.mark.parametrize("ctas_per_sm", [1, 0])
 def test_results_do_not_depend_on_the_grid_size(ctas_per_sm):
     """The persistent kernels split the delivery stream into per-warp ranges; the outputs must be
     the same for any grid (fpx_set_coop_ctas_per_sm: engines sharing a GPU run smaller grids).
-    Batches of up to 6 * 10^5 records, i.e. more CTAs than one wave at 1 CTA/SM."""
+    Batches of up to 2 * 10^5 records, i.e. more CTAs than one wave at 1 CTA/SM."""
     cfg = dict(f=2, num_acceptor_groups=1, acceptors_per_group=5, flexible=False, num_leaders=3, num_replicas=3)
-    _adversarial(cfg, 4242, 150000, 120000, coop_ctas_per_sm=ctas_per_sm, max_batch=1 << 20)
+    _adversarial(cfg, 4242, 50000, 40000, coop_ctas_per_sm=ctas_per_sm, max_batch=1 << 18)
 
 
 def test_unknown_key_error_index_is_first_in_order():
