@@ -22,6 +22,8 @@ SYMBOLS = [
     "fpx_vm_client_request", "fpx_vm_phase2a", "fpx_vm_learn_chosen", "fpx_vm_skip",
     "fpx_mencius_arm_range", "fpx_mencius_acceptor_noop_range", "fpx_mencius_range_phase2b",
     "fpx_mencius_replica_chosen_range",
+    "fpx_wire_decode_inbound", "fpx_wire_decode_inbound_dev", "fpx_wire_encode_phase2b", "fpx_wire_encode_phase2b_dev",
+    "fpx_wire_encode_nack", "fpx_wire_encode_chosen",
     "fpx_epaxos_create", "fpx_epaxos_destroy", "fpx_epaxos_lead", "fpx_epaxos_preaccept", "fpx_epaxos_accept",
     "fpx_epaxos_preacceptok", "fpx_epaxos_acceptok", "fpx_epaxos_entry", "fpx_epaxos_last_kernel_ms", "fpx_depset_union", "fpx_depset_union_dense_dev",
 ]
@@ -90,6 +92,13 @@ def lib():
     L.fpx_mencius_range_phase2b.argtypes = [vp, vp, i32, vp, p(i32), p(i64)]; L.fpx_mencius_range_phase2b.restype = i32
     L.fpx_mencius_replica_chosen_range.argtypes = [vp, vp, i32, p(i64)]
     L.fpx_mencius_replica_chosen_range.restype = i32
+    L.fpx_wire_decode_inbound.argtypes = [vp, i32, vp, vp, i32, vp, vp, p(i64)]; L.fpx_wire_decode_inbound.restype = i32
+    L.fpx_wire_decode_inbound_dev.argtypes = [vp, i32, vp, vp, i32, vp, vp]; L.fpx_wire_decode_inbound_dev.restype = i32
+    L.fpx_wire_encode_phase2b.argtypes = [vp, vp, i32, vp, i32, vp, p(i64)]; L.fpx_wire_encode_phase2b.restype = i32
+    L.fpx_wire_encode_phase2b_dev.argtypes = [vp, vp, i32, vp, i32, vp]; L.fpx_wire_encode_phase2b_dev.restype = i32
+    L.fpx_wire_encode_nack.argtypes = [vp, vp, i32, vp, i32, vp, p(i64)]; L.fpx_wire_encode_nack.restype = i32
+    L.fpx_wire_encode_chosen.argtypes = [vp, vp, i32, vp, vp, i32, vp, i32, vp, p(i64)]
+    L.fpx_wire_encode_chosen.restype = i32
     L.fpx_sync.argtypes = [vp, p(SyncResult)]; L.fpx_sync.restype = i32
     L.fpx_set_coop_ctas_per_sm.argtypes = [vp, i32]; L.fpx_set_coop_ctas_per_sm.restype = i32
     L.fpx_stream.argtypes = [vp]; L.fpx_stream.restype = vp

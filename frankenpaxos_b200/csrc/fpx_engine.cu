@@ -23,6 +23,7 @@
 #include "fpx_replica_misc.cuh"
 #include "fpx_tally.cuh"
 #include "fpx_vanilla.cuh"
+#include "fpx_wire.cuh"
 
 using namespace fpx;
 
@@ -49,6 +50,9 @@ struct fpx_engine {
   int32_t* rng_dec = nullptr;              // per-record scratch of the range kernels (FPX_MAX_RANGE_BATCH)
   uint32_t rng_seq_base = 1;               // Phase2bNoopRange delivery sequence numbers
   int unit_ranges = 0;                     // a one-slot range was ever armed: arms must look at the range keys
+  // wire codec staging (grown on demand)
+  struct WireBuf { void* p = nullptr; size_t cap = 0; };
+  WireBuf w_bytes, w_offs, w_kind, w_rec, w_out, w_tiles, w_arena, w_voffs;
   DevStatus* st = nullptr;
   // scratch
   uint32_t* bits = nullptr;            // accept / win bitmask, max_batch/32 words
@@ -182,6 +186,7 @@ const char* fpx_strerror(int s) {
     case FPX_ERR_UNSUPPORTED: return "configuration not supported by this engine build";
     case FPX_ERR_BATCH_ORDER: return "EPaxos batch contract violated: split the batch at err_index";
     case FPX_ERR_CHECK_FAILED: return "a logger.check of the reference failed";
+    case FPX_ERR_WIRE: return "malformed protobuf message (InvalidProtocolBufferException)";
     case FPX_ERR_EPAXOS_STATE: return "transitionToPreAcceptPhase on a committed instance / regressing ballot";
     default: return "unknown status";
   }
@@ -298,6 +303,9 @@ void fpx_destroy(fpx_engine* e) {
   cudaFree(e->rows); cudaFree(e->ovf_keys); cudaFree(e->ovf_rows); cudaFree(e->votes);
   cudaFree(e->acc_round); cudaFree(e->acc_max_voted); cudaFree(e->rlog); cudaFree(e->vm_claim); cudaFree(e->st);
   cudaFree(e->rng_tab); cudaFree(e->rng_dec);
+  for (fpx_engine::WireBuf* b : {&e->w_bytes, &e->w_offs, &e->w_kind, &e->w_rec, &e->w_out, &e->w_tiles, &e->w_arena,
+                                 &e->w_voffs})
+    cudaFree(b->p);
   cudaFree(e->bits); cudaFree(e->g_agg); cudaFree(e->g_wacc); cudaFree(e->g_ccnt); cudaFree(e->conflicts);
   cudaFree(e->d_in); cudaFree(e->d_out_a); cudaFree(e->d_out_b);
   if (e->h_st) cudaFreeHost(e->h_st);
@@ -801,6 +809,149 @@ int fpx_mencius_replica_chosen_range(fpx_engine* e, const fpx_chosen_range* in, 
   CK(e, cudaGetLastError());
   fpx_sync_result r;
   return range_call_end(e, &r, err_index);
+}
+
+// --------------------------------------------------------------------------- wire codec
+
+static int wire_reserve(fpx_engine* e, fpx_engine::WireBuf* b, size_t need) {
+  need += 64;                               // the kernels may touch the last partial 16-byte chunk
+  if (b->cap >= need) return FPX_OK;
+  CK(e, cudaStreamSynchronize(e->stream));
+  cudaFree(b->p);
+  b->p = nullptr; b->cap = 0;
+  size_t cap = need + need / 2;
+  CK(e, cudaMalloc(&b->p, cap));
+  b->cap = cap;
+  return FPX_OK;
+}
+static bool aligned16(const void* p) { return ((uintptr_t)p & 15u) == 0; }
+
+int fpx_wire_decode_inbound_dev(fpx_engine* e, int32_t inbound, const uint8_t* d_bytes, const int32_t* d_offsets,
+                                int32_t n, int32_t* d_kind, fpx_wire_rec* d_out) {
+  if (!e || n < 0 || (inbound != FPX_WIRE_PROXYLEADER_INBOUND && inbound != FPX_WIRE_ACCEPTOR_INBOUND))
+    return FPX_ERR_INVALID_ARG;
+  if (n == 0) return FPX_OK;
+  if (!d_bytes || !d_offsets || !d_kind || !d_out || !aligned16(d_bytes)) return FPX_ERR_INVALID_ARG;
+  WireDecodeParams P{d_bytes, d_offsets, n, inbound, d_kind, (int4*)d_out, e->st};
+  wire_decode_kernel<<<(n + kWireDecThreads - 1) / kWireDecThreads, kWireDecThreads, 0, e->stream>>>(P);
+  e->launches++;
+  CK(e, cudaGetLastError());
+  return FPX_OK;
+}
+
+int fpx_wire_decode_inbound(fpx_engine* e, int32_t inbound, const uint8_t* bytes, const int32_t* offsets, int32_t n,
+                            int32_t* kind, fpx_wire_rec* out, int64_t* err_index) {
+  if (err_index) *err_index = -1;
+  if (!e || n < 0 || (n > 0 && (!offsets || !kind || !out))) return FPX_ERR_INVALID_ARG;
+  if (n == 0) return FPX_OK;
+  const int64_t total = offsets[n];
+  if (offsets[0] < 0 || total < offsets[0] || (total > 0 && !bytes)) return FPX_ERR_INVALID_ARG;
+  CK(e, cudaSetDevice(e->cfg.device));
+  int c;
+  if ((c = wire_reserve(e, &e->w_bytes, (size_t)total)) || (c = wire_reserve(e, &e->w_offs, ((size_t)n + 1) * 4)) ||
+      (c = wire_reserve(e, &e->w_kind, (size_t)n * 4)) || (c = wire_reserve(e, &e->w_rec, (size_t)n * 16)))
+    return c;
+  if (total) CK(e, cudaMemcpyAsync(e->w_bytes.p, bytes, (size_t)total, cudaMemcpyHostToDevice, e->stream));
+  CK(e, cudaMemcpyAsync(e->w_offs.p, offsets, ((size_t)n + 1) * 4, cudaMemcpyHostToDevice, e->stream));
+  c = fpx_wire_decode_inbound_dev(e, inbound, (const uint8_t*)e->w_bytes.p, (const int32_t*)e->w_offs.p, n,
+                                  (int32_t*)e->w_kind.p, (fpx_wire_rec*)e->w_rec.p);
+  if (c != FPX_OK) return c;
+  CK(e, cudaMemcpyAsync(kind, e->w_kind.p, (size_t)n * 4, cudaMemcpyDeviceToHost, e->stream));
+  CK(e, cudaMemcpyAsync(out, e->w_rec.p, (size_t)n * 16, cudaMemcpyDeviceToHost, e->stream));
+  fpx_sync_result r;
+  c = fpx_sync(e, &r);
+  if (err_index) *err_index = r.err_index;
+  return c;
+}
+
+}  // extern "C"
+template <int KIND>
+static int wire_encode_launch(fpx_engine* e, const void* d_in, int32_t n, uint8_t* d_out, int32_t out_capacity,
+                              int32_t* d_offs, const uint8_t* d_arena, const int32_t* d_voffs, int32_t num_values) {
+  const int tiles = (n + kWireEncTile - 1) / kWireEncTile;
+  int c = wire_reserve(e, &e->w_tiles, ((size_t)tiles + 1) * 4);
+  if (c != FPX_OK) return c;
+  WireEncodeParams P{d_in, n, d_out, out_capacity, d_offs, (uint32_t*)e->w_tiles.p, d_arena, d_voffs, num_values, e->st};
+  wire_size_kernel<KIND><<<tiles, kWireEncThreads, 0, e->stream>>>(P);
+  wire_scan_kernel<<<1, 1024, 0, e->stream>>>((uint32_t*)e->w_tiles.p, tiles, out_capacity, e->st);
+  if (KIND == kWireChosen) {
+    wire_emit_chosen_kernel<<<tiles, kWireEncThreads, 0, e->stream>>>(P);
+  } else {
+    const size_t smem = 16 + (size_t)kWireEncTile * (KIND == kWirePhase2b ? kWireMaxP2b : kWireMaxNack);
+    wire_emit_small_kernel<KIND><<<tiles, kWireEncThreads, smem, e->stream>>>(P);
+  }
+  e->launches += 3;
+  CK(e, cudaGetLastError());
+  return FPX_OK;
+}
+extern "C" {
+
+int fpx_wire_encode_phase2b_dev(fpx_engine* e, const fpx_p2b* d_in, int32_t n, uint8_t* d_out, int32_t out_capacity,
+                                int32_t* d_offsets) {
+  if (!e || n < 0 || out_capacity < 0) return FPX_ERR_INVALID_ARG;
+  if (n == 0) return FPX_OK;
+  if (!d_in || !d_out || !d_offsets || !aligned16(d_out)) return FPX_ERR_INVALID_ARG;
+  return wire_encode_launch<kWirePhase2b>(e, d_in, n, d_out, out_capacity, d_offsets, nullptr, nullptr, 0);
+}
+
+}  // extern "C"
+// host form of the three encoders: records in, (bytes, offsets) out
+template <int KIND>
+static int wire_encode_host(fpx_engine* e, const void* in, size_t rec_bytes, int32_t n, const uint8_t* arena,
+                            const int32_t* value_offsets, int32_t num_values, uint8_t* out, int32_t out_capacity,
+                            int32_t* offsets, int64_t* err_index) {
+  if (err_index) *err_index = -1;
+  if (!e || n < 0 || out_capacity < 0 || !offsets) return FPX_ERR_INVALID_ARG;
+  if (n == 0) { offsets[0] = 0; return FPX_OK; }
+  if (!in || !out) return FPX_ERR_INVALID_ARG;
+  CK(e, cudaSetDevice(e->cfg.device));
+  int c;
+  if ((c = wire_reserve(e, &e->w_rec, (size_t)n * rec_bytes)) || (c = wire_reserve(e, &e->w_offs, ((size_t)n + 1) * 4)) ||
+      (c = wire_reserve(e, &e->w_out, (size_t)out_capacity)))
+    return c;
+  CK(e, cudaMemcpyAsync(e->w_rec.p, in, (size_t)n * rec_bytes, cudaMemcpyHostToDevice, e->stream));
+  const uint8_t* d_arena = nullptr;
+  const int32_t* d_voffs = nullptr;
+  if (KIND == kWireChosen) {
+    if (num_values < 0 || !value_offsets || value_offsets[0] < 0) return FPX_ERR_INVALID_ARG;
+    const size_t alen = (size_t)value_offsets[num_values];
+    if (alen && !arena) return FPX_ERR_INVALID_ARG;
+    if ((c = wire_reserve(e, &e->w_arena, alen)) || (c = wire_reserve(e, &e->w_voffs, ((size_t)num_values + 1) * 4)))
+      return c;
+    if (alen) CK(e, cudaMemcpyAsync(e->w_arena.p, arena, alen, cudaMemcpyHostToDevice, e->stream));
+    CK(e, cudaMemcpyAsync(e->w_voffs.p, value_offsets, ((size_t)num_values + 1) * 4, cudaMemcpyHostToDevice, e->stream));
+    d_arena = (const uint8_t*)e->w_arena.p;
+    d_voffs = (const int32_t*)e->w_voffs.p;
+  }
+  c = wire_encode_launch<KIND>(e, e->w_rec.p, n, (uint8_t*)e->w_out.p, out_capacity, (int32_t*)e->w_offs.p, d_arena,
+                               d_voffs, num_values);
+  if (c != FPX_OK) return c;
+  CK(e, cudaMemcpyAsync(offsets, e->w_offs.p, ((size_t)n + 1) * 4, cudaMemcpyDeviceToHost, e->stream));
+  fpx_sync_result r;
+  c = fpx_sync(e, &r);
+  if (err_index) *err_index = r.err_index;
+  if (c != FPX_OK) return c;
+  if (offsets[n] > 0) {
+    CK(e, cudaMemcpyAsync(out, e->w_out.p, (size_t)offsets[n], cudaMemcpyDeviceToHost, e->stream));
+    CK(e, cudaStreamSynchronize(e->stream));
+  }
+  return FPX_OK;
+}
+extern "C" {
+
+int fpx_wire_encode_phase2b(fpx_engine* e, const fpx_p2b* in, int32_t n, uint8_t* out, int32_t out_capacity,
+                            int32_t* offsets, int64_t* err_index) {
+  return wire_encode_host<kWirePhase2b>(e, in, 16, n, nullptr, nullptr, 0, out, out_capacity, offsets, err_index);
+}
+int fpx_wire_encode_nack(fpx_engine* e, const fpx_nack* in, int32_t n, uint8_t* out, int32_t out_capacity,
+                         int32_t* offsets, int64_t* err_index) {
+  return wire_encode_host<kWireNack>(e, in, 8, n, nullptr, nullptr, 0, out, out_capacity, offsets, err_index);
+}
+int fpx_wire_encode_chosen(fpx_engine* e, const fpx_chosen* in, int32_t n, const uint8_t* arena,
+                           const int32_t* value_offsets, int32_t num_values, uint8_t* out, int32_t out_capacity,
+                           int32_t* offsets, int64_t* err_index) {
+  return wire_encode_host<kWireChosen>(e, in, 8, n, arena, value_offsets, num_values, out, out_capacity, offsets,
+                                       err_index);
 }
 
 int fpx_replica_chosen(fpx_engine* e, const fpx_chosen* in, int32_t n, int64_t* err_index) {

@@ -1,0 +1,399 @@
+// fpx_wire.cuh -- wire codec of the hot messages: scalapb / protobuf proto2 bytes <-> records.
+//
+// The reference spends most of a handler's time parsing the inbound protobuf and serialising
+// the reply ("where the time goes"; every *InboundSerializer is ProtoSerializer,
+// S/ProtoSerializer.scala:3-11).  The shapes are all-int32 plus one opaque value
+// (S/multipaxos/MultiPaxos.proto: Phase2a :273-280, Phase2b :282-290, Chosen :292-298, Nack
+// :455-460, LeaderInbound.nack = 6 :525-539, ProxyLeaderInbound :541-549, AcceptorInbound
+// :551-561, ReplicaInbound.chosen = 1 :563-576), so a batch of received byte strings is decoded
+// one thread per message and replies are encoded size -> scan -> emit, all HBM-bound byte work:
+//   decode  the CTA stages its messages' contiguous byte span in shared memory with 128-bit
+//           loads and parses from there (falls back to global loads for spans > kWireStage,
+//           i.e. Phase2a batches, whose value bytes are skipped by length, not read);
+//   encode  each CTA serialises 1024 replies into shared memory at the output's alignment
+//           phase and copies the span out with 128-bit stores.
+// Parsing rules restated from the published format (see oracle/fpx_oracle.cc `wire`): base-128
+// varints of at most 10 bytes, int32 = low 32 bits, unknown fields skipped by wire type, a known
+// number with another wire type is unknown, oneof = last member on the wire, a missing
+// `required` field or any malformed byte fails the message (FPX_ERR_WIRE + its index).
+#pragma once
+#include "fpx_common.cuh"
+
+namespace fpx {
+
+constexpr int kWireStage = 24 * 1024;     // bytes of one CTA's message span staged in shared memory
+constexpr int kWireDecThreads = 256;
+constexpr int kWireEncPer = 4;            // replies per thread of the encoders
+constexpr int kWireEncThreads = 256;
+constexpr int kWireEncTile = kWireEncPer * kWireEncThreads;
+constexpr int kWireMaxP2b = 46, kWireMaxNack = 13;
+
+// `mem[pos]` is byte `pos` of the batch buffer, whether the span is staged or not
+struct WireReader {
+  const uint8_t* mem;
+  long long p, end;
+  bool ok;
+  __device__ __forceinline__ bool done() const { return p >= end; }
+  __device__ __forceinline__ unsigned long long varint() {
+    unsigned long long v = 0;
+#pragma unroll 1
+    for (int i = 0; i < 10; ++i) {
+      if (p >= end) { ok = false; return 0; }
+      uint32_t b = mem[p++];
+      v |= (unsigned long long)(b & 0x7f) << (7 * i);
+      if (!(b & 0x80)) return v;
+    }
+    ok = false;
+    return 0;
+  }
+  __device__ __forceinline__ bool skip(int wt) {
+    if (wt == 0) { varint(); return ok; }
+    if (wt == 1) { if (end - p < 8) return ok = false; p += 8; return true; }
+    if (wt == 5) { if (end - p < 4) return ok = false; p += 4; return true; }
+    if (wt == 2) {
+      unsigned long long n = varint();
+      if (!ok || (unsigned long long)(end - p) < n) return ok = false;
+      p += (long long)n;
+      return true;
+    }
+    return ok = false;
+  }
+};
+
+// inbound 0 = ProxyLeaderInbound {phase2a = 1, phase2b = 2}, 1 = AcceptorInbound {phase2a = 2}
+__device__ __forceinline__ bool wire_decode_one(int inbound, const uint8_t* mem, long long lo, long long hi, int* kind,
+                                                int4* out) {
+  WireReader r{mem, lo, hi, true};
+  int which = 0;
+  long long blo = 0, bhi = 0;
+  while (!r.done()) {
+    unsigned long long tag = r.varint();
+    if (!r.ok || (tag >> 3) == 0 || (tag >> 3) > 0x1fffffffull) return false;
+    int wt = (int)(tag & 7);
+    if (wt == 2) {
+      unsigned long long n = r.varint();
+      if (!r.ok || (unsigned long long)(r.end - r.p) < n) return false;
+      which = (int)(tag >> 3); blo = r.p; bhi = r.p + (long long)n;     // oneof: last member wins
+      r.p = bhi;
+    } else if (!r.skip(wt)) {
+      return false;
+    }
+  }
+  *kind = which;
+  *out = make_int4(0, 0, 0, 0);
+  if (which == 0) return true;
+  const int f_p2a = inbound == 0 ? 1 : 2, f_p2b = inbound == 0 ? 2 : -1;
+  WireReader b{mem, blo, bhi, true};
+  if (which == f_p2b) {
+    int v0 = 0, v1 = 0, v2 = 0, v3 = 0;
+    unsigned have = 0;
+    while (!b.done()) {
+      unsigned long long tag = b.varint();
+      if (!b.ok || (tag >> 3) == 0) return false;
+      const int f = (int)(tag >> 3), wt = (int)(tag & 7);
+      if (wt == 0 && f >= 1 && f <= 4) {
+        int v = (int)(uint32_t)b.varint();
+        if (!b.ok) return false;
+        if (f == 1) v0 = v; else if (f == 2) v1 = v; else if (f == 3) v2 = v; else v3 = v;
+        have |= 1u << (f - 1);
+      } else if (!b.skip(wt)) {
+        return false;
+      }
+    }
+    if (have != 0xfu) return false;                    // "Message missing required fields."
+    *out = make_int4(v0, v1, v2, v3);
+  } else if (which == f_p2a) {
+    int slot = 0, round = 0;
+    long long off = 0, len = 0;
+    unsigned have = 0;
+    while (!b.done()) {
+      unsigned long long tag = b.varint();
+      if (!b.ok || (tag >> 3) == 0) return false;
+      const int f = (int)(tag >> 3), wt = (int)(tag & 7);
+      if (wt == 0 && f == 1) { slot = (int)(uint32_t)b.varint(); have |= 1u; if (!b.ok) return false; }
+      else if (wt == 0 && f == 2) { round = (int)(uint32_t)b.varint(); have |= 2u; if (!b.ok) return false; }
+      else if (wt == 2 && f == 3) {
+        unsigned long long n = b.varint();
+        if (!b.ok || (unsigned long long)(b.end - b.p) < n || (have & 4u)) return false;
+        off = b.p; len = (long long)n; have |= 4u; b.p += (long long)n;   // the value bytes are not read
+      } else if (!b.skip(wt)) {
+        return false;
+      }
+    }
+    if (have != 7u) return false;
+    *out = make_int4(slot, round, (int)off, (int)len);
+  } else {
+    *out = make_int4(0, 0, (int)blo, (int)(bhi - blo));
+  }
+  return true;
+}
+
+struct WireDecodeParams {
+  const uint8_t* bytes;     // 16-byte aligned
+  const int32_t* offs;      // n + 1
+  int32_t n;
+  int32_t inbound;
+  int32_t* kind;
+  int4* out;
+  DevStatus* st;
+};
+
+__global__ void __launch_bounds__(kWireDecThreads) wire_decode_kernel(WireDecodeParams P) {
+  __shared__ __align__(16) uint8_t s_buf[kWireStage + 32];
+  const int m0 = blockIdx.x * kWireDecThreads;
+  const int m1 = min(P.n, m0 + kWireDecThreads);
+  const long long lo = P.offs[m0], hi = P.offs[m1];
+  const long long total = P.offs[P.n];
+  const long long base = lo & ~15ll;
+  const bool sane = lo >= 0 && lo <= hi && hi <= total;   // garbage offsets never turn into wild reads
+  const bool staged = sane && hi - base <= kWireStage;
+  if (staged) {
+    // 128-bit loads while the chunk lies inside the buffer, bytes for the last partial chunk
+    for (long long k = (long long)threadIdx.x * 16; base + k < hi; k += (long long)kWireDecThreads * 16) {
+      if (base + k + 16 <= (total & ~15ll)) {
+        *(uint4*)(s_buf + k) = __ldg((const uint4*)(P.bytes + base + k));
+      } else {
+        for (int j = 0; j < 16 && base + k + j < total; ++j) s_buf[k + j] = __ldg(P.bytes + base + k + j);
+      }
+    }
+  }
+  __syncthreads();
+  const int i = m0 + threadIdx.x;
+  if (i >= m1) return;
+  const long long a = P.offs[i], b = P.offs[i + 1];
+  int kind = 0;
+  int4 rec = make_int4(0, 0, 0, 0);
+  bool ok = sane && a <= b && a >= lo && b <= hi;      // offsets must be monotone
+  if (ok) ok = wire_decode_one(P.inbound, staged ? s_buf - base : P.bytes, a, b, &kind, &rec);
+  if (!ok) report_error(P.st, FPX_ERR_WIRE, i);
+  P.kind[i] = kind;
+  P.out[i] = rec;
+}
+
+// ---------------------------------------------------------------------------
+// encoders
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ int wire_varint_size(unsigned long long v) {
+  int n = 1;
+  while (v >= 0x80) { v >>= 7; ++n; }
+  return n;
+}
+__device__ __forceinline__ int wire_int32_size(int v) {   // negative int32 is sign-extended: 10 bytes
+  return v < 0 ? 10 : wire_varint_size((unsigned long long)(uint32_t)v);
+}
+__device__ __forceinline__ uint8_t* wire_put_varint(uint8_t* p, unsigned long long v) {
+  while (v >= 0x80) { *p++ = (uint8_t)(v | 0x80); v >>= 7; }
+  *p++ = (uint8_t)v;
+  return p;
+}
+__device__ __forceinline__ uint8_t* wire_put_int32(uint8_t* p, int field, int v) {
+  *p++ = (uint8_t)(field << 3);
+  return wire_put_varint(p, (unsigned long long)(long long)v);
+}
+
+enum { kWirePhase2b = 0, kWireNack = 1, kWireChosen = 2 };
+
+struct WireEncodeParams {
+  const void* in;             // fpx_p2b (int4) | fpx_nack (int2) | fpx_chosen (int2)
+  int32_t n;
+  uint8_t* out;               // 16-byte aligned
+  int32_t out_capacity;
+  int32_t* offs;              // n + 1
+  uint32_t* tile_sum;         // [tiles] bytes per tile, then (after the scan) [tiles + 1] exclusive offsets
+  // Chosen only: the value bytes of value_id v are arena[value_offs[v] .. value_offs[v + 1])
+  const uint8_t* arena;
+  const int32_t* value_offs;
+  int32_t num_values;
+  DevStatus* st;
+};
+
+template <int KIND>
+__device__ __forceinline__ int wire_size_of(const WireEncodeParams& P, int i, bool* bad) {
+  if (KIND == kWirePhase2b) {
+    int4 r = ((const int4*)P.in)[i];
+    // ProxyLeaderInbound{phase2b = 2}: 0x12, len (< 128: one byte), four int32 fields
+    return 2 + 4 + wire_int32_size(r.x) + wire_int32_size(r.y) + wire_int32_size(r.z) + wire_int32_size(r.w);
+  } else if (KIND == kWireNack) {
+    int2 r = ((const int2*)P.in)[i];
+    return 2 + 1 + wire_int32_size(r.y);     // LeaderInbound{nack = 6 {round = 1}}
+  } else {
+    int2 r = ((const int2*)P.in)[i];
+    if ((uint32_t)r.y >= (uint32_t)P.num_values) { *bad = true; return 0; }
+    long long vlen = (long long)P.value_offs[r.y + 1] - P.value_offs[r.y];
+    if (vlen < 0) { *bad = true; return 0; }
+    long long body = 1 + wire_int32_size(r.x) + 1 + wire_varint_size((unsigned long long)vlen) + vlen;
+    return (int)(1 + wire_varint_size((unsigned long long)body) + body);
+  }
+}
+
+// pass 1: bytes per tile of kWireEncTile replies
+template <int KIND>
+__global__ void __launch_bounds__(kWireEncThreads) wire_size_kernel(WireEncodeParams P) {
+  __shared__ uint32_t s_w[kWireEncThreads / 32];
+  uint32_t sum = 0;
+  bool bad = false;
+  int first_bad = INT_MAX;
+  for (int u = 0; u < kWireEncPer; ++u) {
+    int i = blockIdx.x * kWireEncTile + u * kWireEncThreads + threadIdx.x;
+    if (i < P.n) {
+      bool b = false;
+      sum += (uint32_t)wire_size_of<KIND>(P, i, &b);
+      if (b) { bad = true; first_bad = min(first_bad, i); }
+    }
+  }
+  if (bad) report_error(P.st, FPX_ERR_INVALID_ARG, first_bad);
+  sum = __reduce_add_sync(0xffffffffu, sum);
+  if ((threadIdx.x & 31) == 0) s_w[threadIdx.x >> 5] = sum;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    uint32_t t = 0;
+    for (int w = 0; w < kWireEncThreads / 32; ++w) t += s_w[w];
+    P.tile_sum[blockIdx.x] = t;
+  }
+}
+
+// pass 2: exclusive scan of the tile sums (one CTA), total at [tiles]
+__global__ void __launch_bounds__(1024) wire_scan_kernel(uint32_t* tile_sum, int tiles, int32_t out_capacity,
+                                                         DevStatus* st) {
+  __shared__ uint32_t s_w[32];
+  __shared__ uint32_t s_carry;
+  if (threadIdx.x == 0) s_carry = 0;
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int base = 0; base < tiles; base += 1024) {
+    int i = base + threadIdx.x;
+    uint32_t v = i < tiles ? tile_sum[i] : 0u, x = v;
+    for (int d = 1; d < 32; d <<= 1) {
+      uint32_t o = __shfl_up_sync(0xffffffffu, x, d);
+      if (lane >= d) x += o;
+    }
+    if (lane == 31) s_w[warp] = x;
+    __syncthreads();
+    uint32_t woff = 0;
+    for (int w = 0; w < warp; ++w) woff += s_w[w];
+    uint32_t excl = s_carry + woff + x - v;
+    __syncthreads();
+    if (i < tiles) tile_sum[i] = excl;
+    if (threadIdx.x == 1023) s_carry = excl + v;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    tile_sum[tiles] = s_carry;
+    if (s_carry > (uint32_t)out_capacity) report_error(st, FPX_ERR_INVALID_ARG, 0);   // output buffer too small
+  }
+}
+
+// CTA-wide exclusive scan of kWireEncPer values per thread (thread-major order = message order
+// i = tile0 + u * threads + t is NOT contiguous per thread, so scan per u-row)
+__device__ __forceinline__ uint32_t cta_excl_scan(uint32_t v, uint32_t* s_w, uint32_t* s_total) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  uint32_t x = v;
+  for (int d = 1; d < 32; d <<= 1) {
+    uint32_t o = __shfl_up_sync(0xffffffffu, x, d);
+    if (lane >= d) x += o;
+  }
+  if (lane == 31) s_w[warp] = x;
+  __syncthreads();
+  uint32_t woff = 0, tot = 0;
+  for (int w = 0; w < kWireEncThreads / 32; ++w) { if (w < warp) woff += s_w[w]; tot += s_w[w]; }
+  __syncthreads();
+  *s_total = tot;
+  return woff + x - v;
+}
+
+// pass 3 (Phase2b / Nack): serialise the tile into shared memory, copy the span out
+template <int KIND>
+__global__ void __launch_bounds__(kWireEncThreads) wire_emit_small_kernel(WireEncodeParams P) {
+  extern __shared__ __align__(16) uint8_t s_out[];   // 16 + tile * max message size
+  __shared__ uint32_t s_w[kWireEncThreads / 32];
+  const uint32_t tiles = gridDim.x;
+  if (__ldcg(&P.tile_sum[tiles]) > (uint32_t)P.out_capacity) return;   // reported by the scan
+  const uint32_t gbase = __ldcg(&P.tile_sum[blockIdx.x]);
+  const uint32_t phase = gbase & 15u;
+  uint32_t run = 0;
+  for (int u = 0; u < kWireEncPer; ++u) {
+    const int i = blockIdx.x * kWireEncTile + u * kWireEncThreads + threadIdx.x;
+    bool bad = false;
+    const uint32_t sz = i < P.n ? (uint32_t)wire_size_of<KIND>(P, i, &bad) : 0u;
+    uint32_t tot;
+    const uint32_t off = run + cta_excl_scan(sz, s_w, &tot);
+    run += tot;
+    if (i < P.n) {
+      P.offs[i] = (int32_t)(gbase + off);
+      uint8_t* p = s_out + phase + off;
+      if (KIND == kWirePhase2b) {
+        int4 r = ((const int4*)P.in)[i];
+        *p++ = 0x12; *p++ = (uint8_t)(sz - 2);
+        p = wire_put_int32(p, 1, r.x); p = wire_put_int32(p, 2, r.y); p = wire_put_int32(p, 3, r.z);
+        p = wire_put_int32(p, 4, r.w);
+      } else {
+        int2 r = ((const int2*)P.in)[i];
+        *p++ = 0x32; *p++ = (uint8_t)(sz - 2);
+        p = wire_put_int32(p, 1, r.y);
+      }
+    }
+  }
+  if (blockIdx.x == tiles - 1 && threadIdx.x == 0) P.offs[P.n] = (int32_t)(gbase + run);
+  __syncthreads();
+  // global [gbase, gbase + run) <- shared [phase, phase + run): aligned 16-byte chunks in the middle
+  const uint32_t end = phase + run;
+  const uint32_t body_lo = phase ? 16u : 0u, body_hi = end & ~15u;
+  uint8_t* g0 = P.out + (gbase - phase);     // 16-byte aligned
+  if (body_hi > body_lo) {
+    for (uint32_t k = body_lo + threadIdx.x * 16u; k < body_hi; k += kWireEncThreads * 16u)
+      *(uint4*)(g0 + k) = *(const uint4*)(s_out + k);
+  }
+  for (uint32_t k = phase + threadIdx.x; k < min(end, body_lo); k += kWireEncThreads) g0[k] = s_out[k];
+  for (uint32_t k = max(body_hi, max(body_lo, phase)) + threadIdx.x; k < end; k += kWireEncThreads) g0[k] = s_out[k];
+}
+
+// pass 3 (Chosen): header by its thread, value bytes by the warps of the CTA (lane-strided copy)
+__global__ void __launch_bounds__(kWireEncThreads) wire_emit_chosen_kernel(WireEncodeParams P) {
+  __shared__ uint32_t s_w[kWireEncThreads / 32];
+  __shared__ uint32_t s_dst[kWireEncTile];     // where each message's value bytes go
+  __shared__ int32_t s_src[kWireEncTile], s_len[kWireEncTile];
+  const uint32_t tiles = gridDim.x;
+  if (__ldcg(&P.tile_sum[tiles]) > (uint32_t)P.out_capacity) return;
+  const uint32_t gbase = __ldcg(&P.tile_sum[blockIdx.x]);
+  uint32_t run = 0;
+  for (int u = 0; u < kWireEncPer; ++u) {
+    const int i = blockIdx.x * kWireEncTile + u * kWireEncThreads + threadIdx.x;
+    const int slotix = u * kWireEncThreads + threadIdx.x;
+    bool bad = false;
+    const uint32_t sz = i < P.n ? (uint32_t)wire_size_of<kWireChosen>(P, i, &bad) : 0u;
+    uint32_t tot;
+    const uint32_t off = run + cta_excl_scan(sz, s_w, &tot);
+    run += tot;
+    s_len[slotix] = 0;
+    if (i < P.n && !bad) {
+      P.offs[i] = (int32_t)(gbase + off);
+      int2 r = ((const int2*)P.in)[i];
+      const int src = P.value_offs[r.y], vlen = P.value_offs[r.y + 1] - src;
+      const unsigned long long body = 1ull + wire_int32_size(r.x) + 1 + wire_varint_size((unsigned long long)vlen) + vlen;
+      uint8_t hdr[24];
+      uint8_t* p = hdr;
+      *p++ = 0x0a; p = wire_put_varint(p, body);               // ReplicaInbound.chosen = 1
+      p = wire_put_int32(p, 1, r.x);                           // Chosen.slot = 1
+      *p++ = 0x12; p = wire_put_varint(p, (unsigned long long)vlen);   // Chosen.command_batch_or_noop = 2
+      const int hl = (int)(p - hdr);
+      uint8_t* g = P.out + gbase + off;
+      for (int k = 0; k < hl; ++k) g[k] = hdr[k];
+      s_dst[slotix] = gbase + off + (uint32_t)hl;
+      s_src[slotix] = src;
+      s_len[slotix] = vlen;
+    } else if (i < P.n) {
+      P.offs[i] = (int32_t)(gbase + off);
+    }
+  }
+  if (blockIdx.x == tiles - 1 && threadIdx.x == 0) P.offs[P.n] = (int32_t)(gbase + run);
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int m = warp; m < kWireEncTile; m += kWireEncThreads / 32) {
+    const int len = s_len[m];
+    const uint8_t* src = P.arena + s_src[m];
+    uint8_t* dst = P.out + s_dst[m];
+    for (int k = lane; k < len; k += 32) dst[k] = __ldg(src + k);
+  }
+}
+
+}  // namespace fpx

@@ -19,6 +19,8 @@ P2B_RANGE = np.dtype([("dst", "<i4"), ("slot_start", "<i4"), ("slot_end", "<i4")
 CHOSEN_RANGE = np.dtype([("slot_start", "<i4"), ("slot_end", "<i4")])
 VM_SKIP = np.dtype([("server", "<i4"), ("slot_start", "<i4"), ("slot_stop", "<i4"), ("own", "<i4")])
 VALUE_NOOP = -(1 << 31)
+WIRE_REC = np.dtype([("a", "<i4"), ("b", "<i4"), ("c", "<i4"), ("d", "<i4")])
+WIRE_PROXYLEADER_INBOUND, WIRE_ACCEPTOR_INBOUND = 0, 1
 
 MULTIPAXOS, MENCIUS, VANILLA_MENCIUS = 0, 1, 2
 
@@ -239,6 +241,54 @@ class Engine:
         err = C.c_int64(-1)
         self._check(self._L.fpx_mencius_replica_chosen_range(self.h, recs.ctypes.data, len(recs), C.byref(err)),
                     err.value)
+
+    # -- wire codec: protobuf bytes of a batch of messages <-> records (include/fpx.h)
+    def wire_decode_inbound(self, inbound, buf, offsets):
+        """buf: uint8 array with the messages back to back, offsets[n+1].  Returns (kind[n], rec[n])."""
+        buf = np.ascontiguousarray(buf, dtype=np.uint8)
+        offsets = np.ascontiguousarray(offsets, dtype=np.int32)
+        n = len(offsets) - 1
+        kind = np.zeros(max(n, 1), dtype=np.int32)
+        rec = np.zeros(max(n, 1), dtype=WIRE_REC)
+        err = C.c_int64(-1)
+        self._check(self._L.fpx_wire_decode_inbound(self.h, inbound, buf.ctypes.data if len(buf) else None,
+                                                    offsets.ctypes.data, n, kind.ctypes.data, rec.ctypes.data,
+                                                    C.byref(err)), err.value)
+        return kind[:n], rec[:n]
+
+    def _wire_encode(self, fn, recs, dtype, max_per, *extra):
+        recs = np.ascontiguousarray(recs, dtype=dtype)
+        n = len(recs)
+        cap = max(16, n * max_per) if not extra else extra[-1]
+        out = np.zeros(cap, dtype=np.uint8)
+        offs = np.zeros(n + 1, dtype=np.int32)
+        err = C.c_int64(-1)
+        args = [self.h, recs.ctypes.data, n] + list(extra[:-1] if extra else []) + [out.ctypes.data, cap, offs.ctypes.data,
+                                                                                     C.byref(err)]
+        self._check(fn(*args), err.value)
+        return out[:offs[n]].copy(), offs
+
+    def wire_encode_phase2b(self, recs):
+        return self._wire_encode(self._L.fpx_wire_encode_phase2b, recs, P2B, 46)
+
+    def wire_encode_nack(self, recs):
+        return self._wire_encode(self._L.fpx_wire_encode_nack, recs, NACK, 13)
+
+    def wire_encode_chosen(self, recs, arena, value_offsets):
+        arena = np.ascontiguousarray(arena, dtype=np.uint8)
+        value_offsets = np.ascontiguousarray(value_offsets, dtype=np.int32)
+        recs = np.ascontiguousarray(recs, dtype=CHOSEN)
+        lens = np.diff(value_offsets)
+        ok = (recs["value_id"] >= 0) & (recs["value_id"] < len(lens))
+        cap = int(24 * len(recs) + lens[recs["value_id"][ok]].sum()) + 16
+        return self._wire_encode(self._L.fpx_wire_encode_chosen, recs, CHOSEN, 0, arena.ctypes.data if len(arena) else None,
+                                 value_offsets.ctypes.data, len(value_offsets) - 1, cap)
+
+    def wire_decode_inbound_dev(self, inbound, d_bytes, d_offsets, n, d_kind, d_out):
+        self._check(self._L.fpx_wire_decode_inbound_dev(self.h, inbound, d_bytes, d_offsets, n, d_kind, d_out))
+
+    def wire_encode_phase2b_dev(self, d_in, n, d_out, out_capacity, d_offsets):
+        self._check(self._L.fpx_wire_encode_phase2b_dev(self.h, d_in, n, d_out, out_capacity, d_offsets))
 
     # -- device-pointer calls (raw device addresses, asynchronous on self.stream)
     def proxyleader_arm_dev(self, d_in, n):

@@ -103,6 +103,8 @@ typedef enum {
                                       split the batch at err_index and resubmit           */
   FPX_ERR_CHECK_FAILED = -14,      /* a logger.check of the reference failed (vanilla Mencius
                                       advanceWithSkips: a slot to skip is not vacant)   */
+  FPX_ERR_WIRE = -15,              /* malformed protobuf bytes: what parseFrom rejects with
+                                      InvalidProtocolBufferException                    */
   FPX_ERR_EPAXOS_STATE = -13       /* transitionToPreAcceptPhase on a committed instance or
                                       with a regressing ballot: logger.fatal / checkLe,
                                       S/epaxos/Replica.scala:663-681                       */
@@ -338,6 +340,49 @@ int fpx_mencius_range_phase2b(fpx_engine* e, const fpx_p2b_range* in, int32_t n,
  * on this shard's slots only.  fpx_chosen_watermark afterwards is the first hole, i.e.
  * where executeLog stops when it next runs. */
 int fpx_mencius_replica_chosen_range(fpx_engine* e, const fpx_chosen_range* in, int32_t n, int64_t* err_index);
+
+/* ---- Wire codec: the reference's protobuf bytes <-> the records above ---------------
+ * Every actor's inbound serializer is ProtoSerializer (S/ProtoSerializer.scala:3-11:
+ * scalapb toByteArray / parseFrom), and parsing + serialising dominate a handler's time in
+ * the reference.  These entry points take a BATCH of received messages as one byte buffer
+ * plus offsets[n+1] (message i = bytes[offsets[i] .. offsets[i+1])) and decode it on the
+ * GPU, and encode a batch of reply records into the same layout.  Shapes from
+ * S/multipaxos/MultiPaxos.proto: Phase2a :273-280, Phase2b :282-290, Chosen :292-298, Nack
+ * :455-460, LeaderInbound.nack = 6 :525-539, ProxyLeaderInbound {phase2a = 1, phase2b = 2}
+ * :541-549, AcceptorInbound {phase2a = 2} :551-561, ReplicaInbound.chosen = 1 :563-576.
+ * Parsing follows protobuf-java's CodedInputStream as scalapb drives it: varints of at most
+ * 10 bytes, int32 = low 32 bits, unknown fields skipped by wire type, oneof = last member on
+ * the wire, a missing required field or malformed bytes -> FPX_ERR_WIRE with the message's
+ * index (group wire types and a repeated command_batch_or_noop, which no serializer emits,
+ * are FPX_ERR_WIRE too).  Encoders emit the canonical form (fields in number order, minimal
+ * varints, negative int32 as 10 bytes), which is what toByteArray produces.  Buffers: bytes
+ * and out 16-byte aligned for the *_dev forms; total size below 2^31. */
+enum { FPX_WIRE_PROXYLEADER_INBOUND = 0, FPX_WIRE_ACCEPTOR_INBOUND = 1 };
+/* One decoded message.  kind[i] = field number of the `request` oneof member that is set
+ * (0: none).  Phase2b -> {group, acceptor, slot, round} (an fpx_p2b); Phase2a -> {slot,
+ * round, value_off, value_len}: the CommandBatchOrNoop is bytes[value_off .. +value_len),
+ * never read; any other member -> {0, 0, body_off, body_len} for the host to parse. */
+typedef struct { int32_t a, b, c, d; } fpx_wire_rec;
+
+int fpx_wire_decode_inbound(fpx_engine* e, int32_t inbound, const uint8_t* bytes, const int32_t* offsets, int32_t n,
+                            int32_t* kind, fpx_wire_rec* out, int64_t* err_index);
+int fpx_wire_decode_inbound_dev(fpx_engine* e, int32_t inbound, const uint8_t* d_bytes, const int32_t* d_offsets,
+                                int32_t n, int32_t* d_kind, fpx_wire_rec* d_out);
+/* ProxyLeaderInbound{phase2b}: the acceptor's replies, ready for transport.send.  offsets[n+1]
+ * is written; the bytes must fit out_capacity (FPX_ERR_INVALID_ARG otherwise). */
+int fpx_wire_encode_phase2b(fpx_engine* e, const fpx_p2b* in, int32_t n, uint8_t* out, int32_t out_capacity,
+                            int32_t* offsets, int64_t* err_index);
+int fpx_wire_encode_phase2b_dev(fpx_engine* e, const fpx_p2b* d_in, int32_t n, uint8_t* d_out, int32_t out_capacity,
+                                int32_t* d_offsets);
+/* LeaderInbound{nack{round}}; in[i].leader selects the destination and is not on the wire. */
+int fpx_wire_encode_nack(fpx_engine* e, const fpx_nack* in, int32_t n, uint8_t* out, int32_t out_capacity,
+                         int32_t* offsets, int64_t* err_index);
+/* ReplicaInbound{chosen{slot, command_batch_or_noop}}: the value bytes of value_id v are
+ * arena[value_offsets[v] .. value_offsets[v+1]) (e.g. the Phase2a payloads the proxy leader
+ * kept); value_id out of [0, num_values) -> FPX_ERR_INVALID_ARG with the record's index. */
+int fpx_wire_encode_chosen(fpx_engine* e, const fpx_chosen* in, int32_t n, const uint8_t* arena,
+                           const int32_t* value_offsets, int32_t num_values, uint8_t* out, int32_t out_capacity,
+                           int32_t* offsets, int64_t* err_index);
 
 /* ---- EPaxos replica (S/epaxos/Replica.scala) ------------------------------
  * One fpx_epaxos handle = one replica's cmdLog (:298-330) and leaderStates

@@ -1017,6 +1017,112 @@ struct VanillaMencius {
   }
 };
 
+
+// ---------------------------------------------------------------------------
+// Wire codec of the hot messages.  The algorithm lives in a THIRD-PARTY dependency that is
+// not under /root/reference: scalapb-runtime (compilerplugin-shaded 0.7.4, project/plugins.sbt:
+// 6-9) over protobuf-java's CodedInputStream / CodedOutputStream; the call sites are every
+// ProtoSerializer (S/ProtoSerializer.scala:3-11: toByteArray / parseFrom), e.g.
+// ProxyLeaderInboundSerializer (S/multipaxos/ProxyLeader.scala:18-24).  This restates the
+// published proto2 wire format (protocol-buffers "Encoding": base-128 varints, tag =
+// field << 3 | wire type, wire type 0 varint / 1 fixed64 / 2 length-delimited / 5 fixed32,
+// int32 sign-extended to 64 bits before encoding, known fields written in field-number
+// order, unknown fields skipped by wire type, a missing `required` field fails the parse)
+// for the message shapes of S/multipaxos/MultiPaxos.proto: Phase2a :273-280, Phase2b
+// :282-290, Chosen :292-298, Nack :455-460, LeaderInbound.nack = 6 :525-539,
+// ProxyLeaderInbound {phase2a = 1, phase2b = 2} :541-549, AcceptorInbound {phase2a = 2}
+// :551-561, ReplicaInbound.chosen = 1 :563-576.  Pinned by tests/golden/wire.json (bytes
+// produced by Google's Python protobuf runtime from the same shapes).
+// ---------------------------------------------------------------------------
+namespace wire {
+constexpr int kWireError = -15;
+struct Reader {
+  const uint8_t* p; const uint8_t* end;
+  bool ok = true;
+  bool done() const { return p >= end; }
+  uint64_t varint() {                       // CodedInputStream.readRawVarint64: at most 10 bytes
+    uint64_t v = 0;
+    for (int i = 0; i < 10; ++i) {
+      if (p >= end) { ok = false; return 0; }
+      uint8_t b = *p++;
+      v |= (uint64_t)(b & 0x7f) << (7 * i);
+      if (!(b & 0x80)) return v;
+    }
+    ok = false;                             // malformedVarint
+    return 0;
+  }
+  bool skip(int wt) {                       // skipField
+    switch (wt) {
+      case 0: varint(); return ok;
+      case 1: if (end - p < 8) return ok = false; p += 8; return true;
+      case 5: if (end - p < 4) return ok = false; p += 4; return true;
+      case 2: { uint64_t n = varint(); if (!ok || (uint64_t)(end - p) < n) return ok = false; p += n; return true; }
+      default: return ok = false;           // groups / invalid wire types: not produced by scalapb
+    }
+  }
+};
+struct Rec { int32_t a, b, c, d; };
+// inbound 0 = ProxyLeaderInbound (phase2a = 1, phase2b = 2), 1 = AcceptorInbound (phase2a = 2)
+inline int decode_one(int inbound, const uint8_t* base, int64_t lo, int64_t hi, int32_t* kind, Rec* out) {
+  Reader r{base + lo, base + hi};
+  int which = 0; const uint8_t* blo = nullptr; const uint8_t* bhi = nullptr;
+  while (!r.done()) {
+    uint64_t tag = r.varint();
+    if (!r.ok || (tag >> 3) == 0 || (tag >> 3) > 0x1fffffff) return kWireError;
+    int wt = (int)(tag & 7);
+    if (wt == 2) {
+      uint64_t n = r.varint();
+      if (!r.ok || (uint64_t)(r.end - r.p) < n) return kWireError;
+      which = (int)(tag >> 3); blo = r.p; bhi = r.p + n;   // a oneof: the last member on the wire wins
+      r.p += n;
+    } else if (!r.skip(wt)) {
+      return kWireError;
+    }
+  }
+  *kind = which;
+  *out = Rec{0, 0, 0, 0};
+  if (which == 0) return 0;
+  const int f_p2a = inbound == 0 ? 1 : 2, f_p2b = inbound == 0 ? 2 : -1;
+  Reader b{blo, bhi};
+  if (which == f_p2b) {
+    int32_t v[4] = {0, 0, 0, 0}; unsigned have = 0;
+    while (!b.done()) {
+      uint64_t tag = b.varint();
+      if (!b.ok || (tag >> 3) == 0) return kWireError;
+      int f = (int)(tag >> 3), wt = (int)(tag & 7);
+      if (wt == 0 && f >= 1 && f <= 4) { v[f - 1] = (int32_t)b.varint(); have |= 1u << (f - 1); if (!b.ok) return kWireError; }
+      else if (!b.skip(wt)) return kWireError;
+    }
+    if (have != 0xf) return kWireError;               // "Message missing required fields"
+    *out = Rec{v[0], v[1], v[2], v[3]};
+  } else if (which == f_p2a) {
+    int32_t slot = 0, round = 0; int64_t off = 0, len = 0; unsigned have = 0;
+    while (!b.done()) {
+      uint64_t tag = b.varint();
+      if (!b.ok || (tag >> 3) == 0) return kWireError;
+      int f = (int)(tag >> 3), wt = (int)(tag & 7);
+      if (wt == 0 && f == 1) { slot = (int32_t)b.varint(); have |= 1; if (!b.ok) return kWireError; }
+      else if (wt == 0 && f == 2) { round = (int32_t)b.varint(); have |= 2; if (!b.ok) return kWireError; }
+      else if (wt == 2 && f == 3) {
+        uint64_t n = b.varint();
+        if (!b.ok || (uint64_t)(b.end - b.p) < n) return kWireError;
+        if (have & 4) return kWireError;                // a second value would be MERGED by the parser: never emitted, not supported
+        off = b.p - base; len = (int64_t)n; have |= 4; b.p += n;
+      } else if (!b.skip(wt)) return kWireError;
+    }
+    if (have != 7) return kWireError;
+    *out = Rec{slot, round, (int32_t)off, (int32_t)len};
+  } else {
+    *out = Rec{0, 0, (int32_t)(blo - base), (int32_t)(bhi - blo)};
+  }
+  return 0;
+}
+inline int varint_size(uint64_t v) { int n = 1; while (v >= 0x80) { v >>= 7; ++n; } return n; }
+inline int int32_size(int32_t v) { return varint_size((uint64_t)(int64_t)v); }     // negative: 10 bytes
+inline uint8_t* put_varint(uint8_t* p, uint64_t v) { while (v >= 0x80) { *p++ = (uint8_t)(v | 0x80); v >>= 7; } *p++ = (uint8_t)v; return p; }
+inline uint8_t* put_int32(uint8_t* p, int field, int32_t v) { *p++ = (uint8_t)(field << 3); return put_varint(p, (uint64_t)(int64_t)v); }
+}  // namespace wire
+
 }  // namespace fpo
 
 // ---------------------------------------------------------------------------
@@ -1279,6 +1385,62 @@ void fpo_ep_largest_ballot(void* p, int* out) {
   out[0] = e->largest_ballot.first; out[1] = e->largest_ballot.second;
 }
 
+
+// ---- wire codec.  offsets[n+1] delimit the messages inside `bytes`.
+int fpo_wire_decode_inbound(int inbound, const uint8_t* bytes, const int32_t* offsets, int n, int32_t* kind,
+                            int32_t* out /* n x 4 */, int64_t* err) {
+  *err = -1;
+  for (int i = 0; i < n; ++i) {
+    int st = fpo::wire::decode_one(inbound, bytes, offsets[i], offsets[i + 1], &kind[i], (fpo::wire::Rec*)(out + 4 * i));
+    if (st != 0) { *err = i; return st; }
+  }
+  return 0;
+}
+// ProxyLeaderInbound{phase2b = 2 {group_index = 1, acceptor_index = 2, slot = 3, round = 4}}; returns total bytes
+int64_t fpo_wire_encode_phase2b(const P2b* in, int n, uint8_t* out, int32_t* offsets) {
+  using namespace fpo::wire;
+  uint8_t* p = out;
+  for (int i = 0; i < n; ++i) {
+    offsets[i] = (int32_t)(p - out);
+    int body = 4 + int32_size(in[i].group) + int32_size(in[i].acceptor) + int32_size(in[i].slot) + int32_size(in[i].round);
+    *p++ = 0x12; p = put_varint(p, (uint64_t)body);
+    p = put_int32(p, 1, in[i].group); p = put_int32(p, 2, in[i].acceptor); p = put_int32(p, 3, in[i].slot); p = put_int32(p, 4, in[i].round);
+  }
+  offsets[n] = (int32_t)(p - out);
+  return p - out;
+}
+// LeaderInbound{nack = 6 {round = 1}} (the record's `leader` picks the destination, it is not on the wire)
+int64_t fpo_wire_encode_nack(const Nack* in, int n, uint8_t* out, int32_t* offsets) {
+  using namespace fpo::wire;
+  uint8_t* p = out;
+  for (int i = 0; i < n; ++i) {
+    offsets[i] = (int32_t)(p - out);
+    *p++ = 0x32; p = put_varint(p, (uint64_t)(1 + int32_size(in[i].round)));
+    p = put_int32(p, 1, in[i].round);
+  }
+  offsets[n] = (int32_t)(p - out);
+  return p - out;
+}
+// ReplicaInbound{chosen = 1 {slot = 1, command_batch_or_noop = 2}}; the value bytes of value_id v are
+// arena[value_offsets[v] .. value_offsets[v+1])
+int64_t fpo_wire_encode_chosen(const Chosen* in, int n, const uint8_t* arena, const int32_t* value_offsets, int num_values,
+                               uint8_t* out, int32_t* offsets, int64_t* err) {
+  using namespace fpo::wire;
+  uint8_t* p = out;
+  *err = -1;
+  for (int i = 0; i < n; ++i) {
+    offsets[i] = (int32_t)(p - out);
+    if (in[i].value_id < 0 || in[i].value_id >= num_values) { *err = i; return kInvalidArg; }
+    int64_t vlen = value_offsets[in[i].value_id + 1] - value_offsets[in[i].value_id];
+    int64_t body = 1 + int32_size(in[i].slot) + 1 + varint_size((uint64_t)vlen) + vlen;
+    *p++ = 0x0a; p = put_varint(p, (uint64_t)body);
+    p = put_int32(p, 1, in[i].slot);
+    *p++ = 0x12; p = put_varint(p, (uint64_t)vlen);
+    memcpy(p, arena + value_offsets[in[i].value_id], (size_t)vlen); p += vlen;
+  }
+  offsets[n] = (int32_t)(p - out);
+  return p - out;
+}
 
 // ---- vanilla Mencius
 void* fpo_vm_new(int f) { return new VanillaMencius(f); }

@@ -109,6 +109,10 @@ def lib():
         L.fpo_ep_entry.argtypes = [vp, i32, i32, vp]; L.fpo_ep_entry.restype = i32
         L.fpo_ep_leader_kind.argtypes = [vp, i32, i32]; L.fpo_ep_leader_kind.restype = i32
         L.fpo_ep_largest_ballot.argtypes = [vp, vp]
+        L.fpo_wire_decode_inbound.argtypes = [i32, vp, vp, i32, vp, vp, i64p]; L.fpo_wire_decode_inbound.restype = i32
+        L.fpo_wire_encode_phase2b.argtypes = [vp, i32, vp, vp]; L.fpo_wire_encode_phase2b.restype = C.c_int64
+        L.fpo_wire_encode_nack.argtypes = [vp, i32, vp, vp]; L.fpo_wire_encode_nack.restype = C.c_int64
+        L.fpo_wire_encode_chosen.argtypes = [vp, i32, vp, vp, i32, vp, vp, i64p]; L.fpo_wire_encode_chosen.restype = C.c_int64
         L.fpo_vm_new.argtypes = [i32]; L.fpo_vm_new.restype = vp
         L.fpo_vm_free.argtypes = [vp]
         L.fpo_vm_client_request.argtypes = [vp, vp, i32, i64p]; L.fpo_vm_client_request.restype = i32
@@ -452,3 +456,59 @@ class VanillaMencius:
         k = np.zeros(max(n_slots, 1), np.int32); r = np.zeros(max(n_slots, 1), np.int32); v = np.zeros(max(n_slots, 1), np.int32)
         lib().fpo_vm_snapshot(self.h, server, first_slot, n_slots, k.ctypes.data, r.ctypes.data, v.ctypes.data)
         return k[:n_slots], r[:n_slots], v[:n_slots]
+
+
+# --------------------------------------------------------------------------- wire codec
+WIRE_REC = np.dtype([("a", "<i4"), ("b", "<i4"), ("c", "<i4"), ("d", "<i4")])
+WIRE_PROXYLEADER_INBOUND, WIRE_ACCEPTOR_INBOUND = 0, 1
+
+
+def pack_messages(msgs):
+    """list of bytes -> (uint8 array, int32 offsets[n+1])"""
+    offs = np.zeros(len(msgs) + 1, dtype=np.int32)
+    offs[1:] = np.cumsum([len(m) for m in msgs])
+    buf = np.frombuffer(b"".join(msgs), dtype=np.uint8).copy() if msgs else np.zeros(0, dtype=np.uint8)
+    return buf, offs
+
+
+def wire_decode_inbound(inbound, buf, offs):
+    buf = np.ascontiguousarray(buf, dtype=np.uint8); offs = np.ascontiguousarray(offs, dtype=np.int32)
+    n = len(offs) - 1
+    kind = np.zeros(max(n, 1), dtype=np.int32); out = np.zeros(max(n, 1), dtype=WIRE_REC)
+    err = C.c_int64(-1)
+    pad = buf if len(buf) else np.zeros(1, dtype=np.uint8)
+    st = lib().fpo_wire_decode_inbound(inbound, pad.ctypes.data, offs.ctypes.data, n, kind.ctypes.data, out.ctypes.data,
+                                       C.byref(err))
+    return st, err.value, kind[:n], out[:n]
+
+
+def _wire_encode(fn, recs, dtype, max_per):
+    recs = np.ascontiguousarray(recs, dtype=dtype)
+    n = len(recs)
+    out = np.zeros(max(1, n * max_per), dtype=np.uint8); offs = np.zeros(n + 1, dtype=np.int32)
+    total = fn(recs.ctypes.data, n, out.ctypes.data, offs.ctypes.data)
+    return out[:total].copy(), offs
+
+
+def wire_encode_phase2b(recs):
+    return _wire_encode(lib().fpo_wire_encode_phase2b, recs, P2B, 46)
+
+
+def wire_encode_nack(recs):
+    return _wire_encode(lib().fpo_wire_encode_nack, recs, NACK, 13)
+
+
+def wire_encode_chosen(recs, arena, value_offsets):
+    recs = np.ascontiguousarray(recs, dtype=CHOSEN)
+    arena = np.ascontiguousarray(arena, dtype=np.uint8); value_offsets = np.ascontiguousarray(value_offsets, dtype=np.int32)
+    n = len(recs)
+    lens = np.diff(value_offsets)
+    cap = int(n * 24 + (lens[np.clip(recs["value_id"], 0, len(lens) - 1)].sum() if n and len(lens) else 0))
+    out = np.zeros(max(1, cap), dtype=np.uint8); offs = np.zeros(n + 1, dtype=np.int32)
+    err = C.c_int64(-1)
+    pad = arena if len(arena) else np.zeros(1, dtype=np.uint8)
+    total = lib().fpo_wire_encode_chosen(recs.ctypes.data, n, pad.ctypes.data, value_offsets.ctypes.data,
+                                         len(value_offsets) - 1, out.ctypes.data, offs.ctypes.data, C.byref(err))
+    if total < 0:
+        return int(total), err.value, None, None
+    return 0, -1, out[:total].copy(), offs
