@@ -137,3 +137,44 @@ JNIEXPORT_ jint_ Java_frankenpaxos_gpu_Native_vmSkip(JNIEnv_* env, jclass_ cls, 
   (void)env; (void)cls;
   return fpx_vm_skip((fpx_engine*)P(h), (const fpx_vm_skip_rec*)P(in), n, (int64_t*)P(err_index));
 }
+
+/* ---- wire codec (include/fpx.h): batches of protobuf bytes <-> records ---- */
+
+/* int wireDecodeInbound(long h, int inbound, long bytes, long offsets, int n, long kind, long out, long err) */
+JNIEXPORT_ jint_ Java_frankenpaxos_gpu_Native_wireDecodeInbound(JNIEnv_* env, jclass_ cls, jlong_ h, jint_ inbound,
+                                                                jlong_ bytes, jlong_ offsets, jint_ n, jlong_ kind,
+                                                                jlong_ out, jlong_ err_index) {
+  (void)env; (void)cls;
+  return fpx_wire_decode_inbound((fpx_engine*)P(h), inbound, (const uint8_t*)P(bytes), (const int32_t*)P(offsets), n,
+                                 (int32_t*)P(kind), (fpx_wire_rec*)P(out), (int64_t*)P(err_index));
+}
+
+/* int wireEncodePhase2b(long h, long in, int n, long out, int outCapacity, long offsets, long err) */
+JNIEXPORT_ jint_ Java_frankenpaxos_gpu_Native_wireEncodePhase2b(JNIEnv_* env, jclass_ cls, jlong_ h, jlong_ in,
+                                                                jint_ n, jlong_ out, jint_ out_capacity,
+                                                                jlong_ offsets, jlong_ err_index) {
+  (void)env; (void)cls;
+  return fpx_wire_encode_phase2b((fpx_engine*)P(h), (const fpx_p2b*)P(in), n, (uint8_t*)P(out), out_capacity,
+                                 (int32_t*)P(offsets), (int64_t*)P(err_index));
+}
+
+/* int wireEncodeNack(long h, long in, int n, long out, int outCapacity, long offsets, long err) */
+JNIEXPORT_ jint_ Java_frankenpaxos_gpu_Native_wireEncodeNack(JNIEnv_* env, jclass_ cls, jlong_ h, jlong_ in, jint_ n,
+                                                             jlong_ out, jint_ out_capacity, jlong_ offsets,
+                                                             jlong_ err_index) {
+  (void)env; (void)cls;
+  return fpx_wire_encode_nack((fpx_engine*)P(h), (const fpx_nack*)P(in), n, (uint8_t*)P(out), out_capacity,
+                              (int32_t*)P(offsets), (int64_t*)P(err_index));
+}
+
+/* int wireEncodeChosen(long h, long in, int n, long arena, long valueOffsets, int numValues, long out,
+ *                      int outCapacity, long offsets, long err) */
+JNIEXPORT_ jint_ Java_frankenpaxos_gpu_Native_wireEncodeChosen(JNIEnv_* env, jclass_ cls, jlong_ h, jlong_ in, jint_ n,
+                                                               jlong_ arena, jlong_ value_offsets, jint_ num_values,
+                                                               jlong_ out, jint_ out_capacity, jlong_ offsets,
+                                                               jlong_ err_index) {
+  (void)env; (void)cls;
+  return fpx_wire_encode_chosen((fpx_engine*)P(h), (const fpx_chosen*)P(in), n, (const uint8_t*)P(arena),
+                                (const int32_t*)P(value_offsets), num_values, (uint8_t*)P(out), out_capacity,
+                                (int32_t*)P(offsets), (int64_t*)P(err_index));
+}
