@@ -12,7 +12,7 @@
 //           i.e. Phase2a batches, whose value bytes are skipped by length, not read);
 //   encode  each CTA serialises 1024 replies into shared memory at the output's alignment
 //           phase and copies the span out with 128-bit stores.
-// Parsing rules restated from the published format (see oracle/fpx_oracle.cc `wire`): base-128
+// Parsing rules restated from the published proto2 wire format (wire codec): base-128
 // varints of at most 10 bytes, int32 = low 32 bits, unknown fields skipped by wire type, a known
 // number with another wire type is unknown, oneof = last member on the wire, a missing
 // `required` field or any malformed byte fails the message (FPX_ERR_WIRE + its index).
