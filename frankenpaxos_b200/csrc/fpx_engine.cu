@@ -869,18 +869,21 @@ template <int KIND>
 static int wire_encode_launch(fpx_engine* e, const void* d_in, int32_t n, uint8_t* d_out, int32_t out_capacity,
                               int32_t* d_offs, const uint8_t* d_arena, const int32_t* d_voffs, int32_t num_values) {
   const int tiles = (n + kWireEncTile - 1) / kWireEncTile;
-  int c = wire_reserve(e, &e->w_tiles, ((size_t)tiles + 1) * 4);
+  int c = wire_reserve(e, &e->w_tiles, ((size_t)tiles + 2) * 8);
   if (c != FPX_OK) return c;
   WireEncodeParams P{d_in, n, d_out, out_capacity, d_offs, (uint32_t*)e->w_tiles.p, d_arena, d_voffs, num_values, e->st};
-  wire_size_kernel<KIND><<<tiles, kWireEncThreads, 0, e->stream>>>(P);
-  wire_scan_kernel<<<1, 1024, 0, e->stream>>>((uint32_t*)e->w_tiles.p, tiles, out_capacity, e->st);
   if (KIND == kWireChosen) {
+    wire_size_kernel<KIND><<<tiles, kWireEncThreads, 0, e->stream>>>(P);
+    wire_scan_kernel<<<1, 1024, 0, e->stream>>>((uint32_t*)e->w_tiles.p, tiles, out_capacity, e->st);
     wire_emit_chosen_kernel<<<tiles, kWireEncThreads, 0, e->stream>>>(P);
+    e->launches += 3;
   } else {
+    // two passes: bytes per tile, then emit (each CTA sums the tiles before it itself)
     const size_t smem = 16 + (size_t)kWireEncTile * (KIND == kWirePhase2b ? kWireMaxP2b : kWireMaxNack);
-    wire_emit_small_kernel<KIND><<<tiles, kWireEncThreads, smem, e->stream>>>(P);
+    wire_size_kernel<KIND><<<tiles, kWireEncThreads, 0, e->stream>>>(P);
+    wire_emit_small_kernel<KIND><<<tiles, kWireEncThreads, smem, e->stream>>>(P, tiles);
+    e->launches += 2;
   }
-  e->launches += 3;
   CK(e, cudaGetLastError());
   return FPX_OK;
 }

@@ -28,52 +28,88 @@ constexpr int kWireEncThreads = 256;
 constexpr int kWireEncTile = kWireEncPer * kWireEncThreads;
 constexpr int kWireMaxP2b = 46, kWireMaxNack = 13;
 
-// `mem[pos]` is byte `pos` of the batch buffer, whether the span is staged or not
+// Byte reader over one message.  kShared: positions index the CTA's staged window in shared memory
+// (explicit ld.shared: a generic pointer would cost a generic load per byte); else they are offsets
+// from the batch buffer in global memory.  All positions are 32-bit (the batch is < 2^31 bytes).
+template <bool kShared>
 struct WireReader {
-  const uint8_t* mem;
-  long long p, end;
+  uint32_t sbase;            // shared-window address of window byte 0
+  const uint8_t* g;          // batch buffer
+  uint32_t p, end;
   bool ok;
+  __device__ __forceinline__ uint32_t byte(uint32_t pos) const {
+    if (kShared) {
+      uint32_t v;
+      asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(sbase + pos));
+      return v;
+    }
+    return __ldg(g + pos);
+  }
   __device__ __forceinline__ bool done() const { return p >= end; }
-  __device__ __forceinline__ unsigned long long varint() {
-    unsigned long long v = 0;
+  // low 32 bits of a varint of at most 10 bytes; *hi_nonzero: bits 32.. were set (tags / lengths reject that)
+  __device__ __forceinline__ uint32_t varint32(bool* hi_nonzero) {
+    // one-byte varints (every tag, length and small field of the hot messages) without the loop
+    if (p < end) {
+      const uint32_t b0 = byte(p);
+      if (b0 < 0x80u) { ++p; *hi_nonzero = false; return b0; }
+    }
+    uint32_t v = 0;
+    bool hi = false;
 #pragma unroll 1
     for (int i = 0; i < 10; ++i) {
       if (p >= end) { ok = false; return 0; }
-      uint32_t b = mem[p++];
-      v |= (unsigned long long)(b & 0x7f) << (7 * i);
-      if (!(b & 0x80)) return v;
+      const uint32_t b = byte(p++);
+      if (i < 4) v |= (b & 0x7f) << (7 * i);
+      else if (i == 4) { v |= (b & 0x0f) << 28; hi |= (b & 0x70) != 0; }
+      else hi |= (b & 0x7f) != 0;
+      if (!(b & 0x80)) { *hi_nonzero = hi; return v; }
     }
-    ok = false;
+    ok = false;                                  // malformed varint: more than 10 bytes
     return 0;
   }
+  __device__ __forceinline__ uint32_t int32() { bool hi; return varint32(&hi); }      // (int) readRawVarint64
+  // a tag: field number 1 .. 2^29-1 in bits 3.., i.e. any non-zero-field 32-bit value
+  __device__ __forceinline__ uint32_t tag() {
+    bool hi = false;
+    uint32_t v = varint32(&hi);
+    if (hi || (v >> 3) == 0) ok = false;
+    return v;
+  }
+  // a length: anything >= 2^31 is longer than the batch
+  __device__ __forceinline__ uint32_t small() {
+    bool hi = false;
+    uint32_t v = varint32(&hi);
+    if (hi || (v >> 31)) ok = false;
+    return v;
+  }
   __device__ __forceinline__ bool skip(int wt) {
-    if (wt == 0) { varint(); return ok; }
-    if (wt == 1) { if (end - p < 8) return ok = false; p += 8; return true; }
-    if (wt == 5) { if (end - p < 4) return ok = false; p += 4; return true; }
+    if (wt == 0) { int32(); return ok; }
+    if (wt == 1) { if (end - p < 8u) return ok = false; p += 8; return true; }
+    if (wt == 5) { if (end - p < 4u) return ok = false; p += 4; return true; }
     if (wt == 2) {
-      unsigned long long n = varint();
-      if (!ok || (unsigned long long)(end - p) < n) return ok = false;
-      p += (long long)n;
+      uint32_t n = small();
+      if (!ok || end - p < n) return ok = false;
+      p += n;
       return true;
     }
     return ok = false;
   }
 };
 
-// inbound 0 = ProxyLeaderInbound {phase2a = 1, phase2b = 2}, 1 = AcceptorInbound {phase2a = 2}
-__device__ __forceinline__ bool wire_decode_one(int inbound, const uint8_t* mem, long long lo, long long hi, int* kind,
-                                                int4* out) {
-  WireReader r{mem, lo, hi, true};
+// inbound 0 = ProxyLeaderInbound {phase2a = 1, phase2b = 2}, 1 = AcceptorInbound {phase2a = 2}.
+// [lo, hi) and the offsets written to *out are reader positions; the caller rebases them.
+template <bool kShared>
+__device__ __forceinline__ bool wire_decode_one(int inbound, WireReader<kShared> r, int* kind, int4* out) {
   int which = 0;
-  long long blo = 0, bhi = 0;
+  uint32_t blo = 0, bhi = 0;
   while (!r.done()) {
-    unsigned long long tag = r.varint();
-    if (!r.ok || (tag >> 3) == 0 || (tag >> 3) > 0x1fffffffull) return false;
-    int wt = (int)(tag & 7);
+    const uint32_t tag = r.tag();
+    if (!r.ok) return false;
+    const int wt = (int)(tag & 7);
     if (wt == 2) {
-      unsigned long long n = r.varint();
-      if (!r.ok || (unsigned long long)(r.end - r.p) < n) return false;
-      which = (int)(tag >> 3); blo = r.p; bhi = r.p + (long long)n;     // oneof: last member wins
+      const uint32_t n = r.small();
+      if (!r.ok || r.end - r.p < n) return false;
+      which = (int)(tag >> 3); blo = r.p; bhi = r.p + n;       // oneof: last member wins
       r.p = bhi;
     } else if (!r.skip(wt)) {
       return false;
@@ -83,16 +119,17 @@ __device__ __forceinline__ bool wire_decode_one(int inbound, const uint8_t* mem,
   *out = make_int4(0, 0, 0, 0);
   if (which == 0) return true;
   const int f_p2a = inbound == 0 ? 1 : 2, f_p2b = inbound == 0 ? 2 : -1;
-  WireReader b{mem, blo, bhi, true};
+  WireReader<kShared> b = r;
+  b.p = blo; b.end = bhi; b.ok = true;
   if (which == f_p2b) {
     int v0 = 0, v1 = 0, v2 = 0, v3 = 0;
     unsigned have = 0;
     while (!b.done()) {
-      unsigned long long tag = b.varint();
-      if (!b.ok || (tag >> 3) == 0) return false;
+      const uint32_t tag = b.tag();
+      if (!b.ok) return false;
       const int f = (int)(tag >> 3), wt = (int)(tag & 7);
       if (wt == 0 && f >= 1 && f <= 4) {
-        int v = (int)(uint32_t)b.varint();
+        const int v = (int)b.int32();
         if (!b.ok) return false;
         if (f == 1) v0 = v; else if (f == 2) v1 = v; else if (f == 3) v2 = v; else v3 = v;
         have |= 1u << (f - 1);
@@ -104,18 +141,18 @@ __device__ __forceinline__ bool wire_decode_one(int inbound, const uint8_t* mem,
     *out = make_int4(v0, v1, v2, v3);
   } else if (which == f_p2a) {
     int slot = 0, round = 0;
-    long long off = 0, len = 0;
+    uint32_t off = 0, len = 0;
     unsigned have = 0;
     while (!b.done()) {
-      unsigned long long tag = b.varint();
-      if (!b.ok || (tag >> 3) == 0) return false;
+      const uint32_t tag = b.tag();
+      if (!b.ok) return false;
       const int f = (int)(tag >> 3), wt = (int)(tag & 7);
-      if (wt == 0 && f == 1) { slot = (int)(uint32_t)b.varint(); have |= 1u; if (!b.ok) return false; }
-      else if (wt == 0 && f == 2) { round = (int)(uint32_t)b.varint(); have |= 2u; if (!b.ok) return false; }
+      if (wt == 0 && f == 1) { slot = (int)b.int32(); have |= 1u; if (!b.ok) return false; }
+      else if (wt == 0 && f == 2) { round = (int)b.int32(); have |= 2u; if (!b.ok) return false; }
       else if (wt == 2 && f == 3) {
-        unsigned long long n = b.varint();
-        if (!b.ok || (unsigned long long)(b.end - b.p) < n || (have & 4u)) return false;
-        off = b.p; len = (long long)n; have |= 4u; b.p += (long long)n;   // the value bytes are not read
+        const uint32_t n = b.small();
+        if (!b.ok || b.end - b.p < n || (have & 4u)) return false;
+        off = b.p; len = n; have |= 4u; b.p += n;               // the value bytes are not read
       } else if (!b.skip(wt)) {
         return false;
       }
@@ -164,7 +201,16 @@ __global__ void __launch_bounds__(kWireDecThreads) wire_decode_kernel(WireDecode
   int kind = 0;
   int4 rec = make_int4(0, 0, 0, 0);
   bool ok = sane && a <= b && a >= lo && b <= hi;      // offsets must be monotone
-  if (ok) ok = wire_decode_one(P.inbound, staged ? s_buf - base : P.bytes, a, b, &kind, &rec);
+  if (ok) {
+    if (staged) {
+      WireReader<true> r{(uint32_t)__cvta_generic_to_shared(s_buf), nullptr, (uint32_t)(a - base), (uint32_t)(b - base), true};
+      ok = wire_decode_one<true>(P.inbound, r, &kind, &rec);
+      if (ok && kind != 0 && !(kind == 2 && P.inbound == FPX_WIRE_PROXYLEADER_INBOUND)) rec.z += (int)base;   // window -> buffer offsets
+    } else {
+      WireReader<false> r{0u, P.bytes, (uint32_t)a, (uint32_t)b, true};
+      ok = wire_decode_one<false>(P.inbound, r, &kind, &rec);
+    }
+  }
   if (!ok) report_error(P.st, FPX_ERR_WIRE, i);
   P.kind[i] = kind;
   P.out[i] = rec;
@@ -179,16 +225,29 @@ __device__ __forceinline__ int wire_varint_size(unsigned long long v) {
   return n;
 }
 __device__ __forceinline__ int wire_int32_size(int v) {   // negative int32 is sign-extended: 10 bytes
-  return v < 0 ? 10 : wire_varint_size((unsigned long long)(uint32_t)v);
+  // ceil(bits / 7) for bits = 1 .. 32 is ((bits + 6) * 37) >> 8
+  return v < 0 ? 10 : ((38 - __clz(v | 1)) * 37) >> 8;
 }
 __device__ __forceinline__ uint8_t* wire_put_varint(uint8_t* p, unsigned long long v) {
   while (v >= 0x80) { *p++ = (uint8_t)(v | 0x80); v >>= 7; }
   *p++ = (uint8_t)v;
   return p;
 }
+__device__ __noinline__ uint8_t* wire_put_negative(uint8_t* p, int v) {   // sign-extended: ten bytes, rare
+  return wire_put_varint(p, (unsigned long long)(long long)v);
+}
 __device__ __forceinline__ uint8_t* wire_put_int32(uint8_t* p, int field, int v) {
   *p++ = (uint8_t)(field << 3);
-  return wire_put_varint(p, (unsigned long long)(long long)v);
+  if (v < 0) return wire_put_negative(p, v);
+  // 1..5 bytes without a data-dependent loop: byte k is written iff the value has more than 7k bits
+  const uint32_t u = (uint32_t)v;
+  const int n = ((38 - __clz(v | 1)) * 37) >> 8;
+  p[0] = (uint8_t)((u & 0x7f) | (n > 1 ? 0x80 : 0));
+  if (n > 1) p[1] = (uint8_t)(((u >> 7) & 0x7f) | (n > 2 ? 0x80 : 0));
+  if (n > 2) p[2] = (uint8_t)(((u >> 14) & 0x7f) | (n > 3 ? 0x80 : 0));
+  if (n > 3) p[3] = (uint8_t)(((u >> 21) & 0x7f) | (n > 4 ? 0x80 : 0));
+  if (n > 4) p[4] = (uint8_t)(u >> 28);
+  return p + n;
 }
 
 enum { kWirePhase2b = 0, kWireNack = 1, kWireChosen = 2 };
@@ -234,7 +293,7 @@ __global__ void __launch_bounds__(kWireEncThreads) wire_size_kernel(WireEncodePa
   bool bad = false;
   int first_bad = INT_MAX;
   for (int u = 0; u < kWireEncPer; ++u) {
-    int i = blockIdx.x * kWireEncTile + u * kWireEncThreads + threadIdx.x;
+    int i = blockIdx.x * kWireEncTile + (int)threadIdx.x * kWireEncPer + u;
     if (i < P.n) {
       bool b = false;
       sum += (uint32_t)wire_size_of<KIND>(P, i, &b);
@@ -294,47 +353,87 @@ __device__ __forceinline__ uint32_t cta_excl_scan(uint32_t v, uint32_t* s_w, uin
   }
   if (lane == 31) s_w[warp] = x;
   __syncthreads();
-  uint32_t woff = 0, tot = 0;
-  for (int w = 0; w < kWireEncThreads / 32; ++w) { if (w < warp) woff += s_w[w]; tot += s_w[w]; }
+  const uint32_t wt = lane < kWireEncThreads / 32 ? s_w[lane] : 0u;   // every warp scans the 8 warp totals itself
+  uint32_t wx = wt;
+  for (int d = 1; d < kWireEncThreads / 32; d <<= 1) {
+    uint32_t o = __shfl_up_sync(0xffffffffu, wx, d);
+    if (lane >= d) wx += o;
+  }
+  const uint32_t woff = __shfl_sync(0xffffffffu, wx - wt, warp);
+  const uint32_t tot = __shfl_sync(0xffffffffu, wx, kWireEncThreads / 32 - 1);
   __syncthreads();
   *s_total = tot;
   return woff + x - v;
 }
 
-// pass 3 (Phase2b / Nack): serialise the tile into shared memory, copy the span out
+// pass 2 (Phase2b / Nack).  tile_sum[] holds the byte count of every tile (pass 1); a CTA finds its
+// output offset by summing the counts of the tiles before it straight from L2 (<= a few thousand
+// values: cheaper than a scan kernel or a look-back chain), serialises its tile into shared memory at
+// the output's 16-byte phase and copies the span out with 128-bit stores.  Thread t owns the
+// kWireEncPer consecutive records 4t .. 4t+3 of the tile: one CTA scan per tile.
 template <int KIND>
-__global__ void __launch_bounds__(kWireEncThreads) wire_emit_small_kernel(WireEncodeParams P) {
+__global__ void __launch_bounds__(kWireEncThreads) wire_emit_small_kernel(WireEncodeParams P, int tiles) {
   extern __shared__ __align__(16) uint8_t s_out[];   // 16 + tile * max message size
   __shared__ uint32_t s_w[kWireEncThreads / 32];
-  const uint32_t tiles = gridDim.x;
-  if (__ldcg(&P.tile_sum[tiles]) > (uint32_t)P.out_capacity) return;   // reported by the scan
-  const uint32_t gbase = __ldcg(&P.tile_sum[blockIdx.x]);
-  const uint32_t phase = gbase & 15u;
-  uint32_t run = 0;
+  __shared__ unsigned long long s_pre[kWireEncThreads / 32];
+  const int tile = blockIdx.x;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int i0 = tile * kWireEncTile + (int)threadIdx.x * kWireEncPer;
+  int4 rec[kWireEncPer];
+  uint32_t sz[kWireEncPer];
+  uint32_t mine = 0;
+#pragma unroll
   for (int u = 0; u < kWireEncPer; ++u) {
-    const int i = blockIdx.x * kWireEncTile + u * kWireEncThreads + threadIdx.x;
-    bool bad = false;
-    const uint32_t sz = i < P.n ? (uint32_t)wire_size_of<KIND>(P, i, &bad) : 0u;
-    uint32_t tot;
-    const uint32_t off = run + cta_excl_scan(sz, s_w, &tot);
-    run += tot;
+    const int i = i0 + u;
+    sz[u] = 0;
+    rec[u] = make_int4(0, 0, 0, 0);
     if (i < P.n) {
-      P.offs[i] = (int32_t)(gbase + off);
-      uint8_t* p = s_out + phase + off;
       if (KIND == kWirePhase2b) {
-        int4 r = ((const int4*)P.in)[i];
-        *p++ = 0x12; *p++ = (uint8_t)(sz - 2);
-        p = wire_put_int32(p, 1, r.x); p = wire_put_int32(p, 2, r.y); p = wire_put_int32(p, 3, r.z);
-        p = wire_put_int32(p, 4, r.w);
+        rec[u] = __ldcg((const int4*)P.in + i);      // second read of the records: L2
+        sz[u] = 2 + 4 + wire_int32_size(rec[u].x) + wire_int32_size(rec[u].y) + wire_int32_size(rec[u].z) +
+                wire_int32_size(rec[u].w);
       } else {
-        int2 r = ((const int2*)P.in)[i];
-        *p++ = 0x32; *p++ = (uint8_t)(sz - 2);
-        p = wire_put_int32(p, 1, r.y);
+        int2 r = __ldcg((const int2*)P.in + i);
+        rec[u].y = r.y;
+        sz[u] = 2 + 1 + wire_int32_size(r.y);
       }
     }
+    mine += sz[u];
   }
-  if (blockIdx.x == tiles - 1 && threadIdx.x == 0) P.offs[P.n] = (int32_t)(gbase + run);
+  // bytes of all tiles before this one (and, for the last tile, the grand total)
+  unsigned long long pre = 0;
+  for (int t = threadIdx.x; t < tile; t += kWireEncThreads) pre += __ldcg(&P.tile_sum[t]);
+  for (int dlt = 16; dlt; dlt >>= 1) pre += __shfl_xor_sync(0xffffffffu, pre, dlt);
+  if (lane == 0) s_pre[warp] = pre;
+  uint32_t run;
+  uint32_t off = cta_excl_scan(mine, s_w, &run);     // (its barriers also publish s_pre)
+  unsigned long long gb = 0;
+#pragma unroll
+  for (int w = 0; w < kWireEncThreads / 32; ++w) gb += s_pre[w];
+  const bool fits = gb + run <= (unsigned long long)P.out_capacity;
+  if (!fits && gb <= (unsigned long long)P.out_capacity && threadIdx.x == 0)
+    report_error(P.st, FPX_ERR_INVALID_ARG, 0);      // output buffer too small
+  const uint32_t gbase = (uint32_t)gb;
+  const uint32_t phase = gbase & 15u;
+  uint8_t* p = s_out + phase + off;
+#pragma unroll
+  for (int u = 0; u < kWireEncPer; ++u) {
+    const int i = i0 + u;
+    if (i >= P.n) break;
+    P.offs[i] = (int32_t)(gbase + off);
+    off += sz[u];
+    if (KIND == kWirePhase2b) {
+      *p++ = 0x12; *p++ = (uint8_t)(sz[u] - 2);
+      p = wire_put_int32(p, 1, rec[u].x); p = wire_put_int32(p, 2, rec[u].y); p = wire_put_int32(p, 3, rec[u].z);
+      p = wire_put_int32(p, 4, rec[u].w);
+    } else {
+      *p++ = 0x32; *p++ = (uint8_t)(sz[u] - 2);
+      p = wire_put_int32(p, 1, rec[u].y);
+    }
+  }
+  if (tile == tiles - 1 && threadIdx.x == 0) P.offs[P.n] = (int32_t)(gbase + run);
   __syncthreads();
+  if (!fits) return;
   // global [gbase, gbase + run) <- shared [phase, phase + run): aligned 16-byte chunks in the middle
   const uint32_t end = phase + run;
   const uint32_t body_lo = phase ? 16u : 0u, body_hi = end & ~15u;
