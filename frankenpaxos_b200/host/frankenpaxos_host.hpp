@@ -222,6 +222,13 @@ class Backend {
   // Acceptor state read-back (Phase1b's `states.iteratorFrom`, Acceptor.scala:171-179)
   virtual void snapshot(int group, int acceptor, int* round, int* max_voted_slot, int first_slot, int n_slots,
                         int32_t* vote_round, int32_t* vote_value) = 0;
+  // Optional: the backend parses / serialises the hot messages itself (fpx_wire_*), so the actors
+  // hand it the transport's raw bytes for Phase2b and get reply bytes back.
+  virtual bool has_wire() const { return false; }
+  virtual int wire_decode_proxyleader(const uint8_t*, const int32_t*, int, int32_t*, fpx_wire_rec*, int64_t*) {
+    return FPX_ERR_UNSUPPORTED;
+  }
+  virtual int wire_encode_phase2b(const fpx_p2b*, int, uint8_t*, int, int32_t*, int64_t*) { return FPX_ERR_UNSUPPORTED; }
 };
 class GpuBackend : public Backend {
  public:
@@ -248,6 +255,14 @@ class GpuBackend : public Backend {
   void snapshot(int group, int acceptor, int* round, int* max_voted_slot, int first_slot, int n_slots,
                 int32_t* vote_round, int32_t* vote_value) override {
     fpx_snapshot_acceptor(e_, group, acceptor, round, max_voted_slot, first_slot, n_slots, vote_round, vote_value);
+  }
+  bool has_wire() const override { return true; }
+  int wire_decode_proxyleader(const uint8_t* bytes, const int32_t* offs, int n, int32_t* kind, fpx_wire_rec* out,
+                              int64_t* err) override {
+    return fpx_wire_decode_inbound(e_, FPX_WIRE_PROXYLEADER_INBOUND, bytes, offs, n, kind, out, err);
+  }
+  int wire_encode_phase2b(const fpx_p2b* in, int n, uint8_t* out, int cap, int32_t* offs, int64_t* err) override {
+    return fpx_wire_encode_phase2b(e_, in, n, out, cap, offs, err);
   }
   fpx_engine* engine() { return e_; }
  private:
@@ -312,6 +327,18 @@ class GpuAcceptor : public Actor {
     // Replies come back compacted, each stream in delivery order: walk the batch and
     // hand every message its reply (a Phase2b carries its round, a Nack does not
     // carry the slot, so Nacks are matched by position among the rejected ones).
+    // With a wire-capable backend the accepted replies are serialised in one batch
+    // (ProxyLeaderInbound{phase2b} bytes, identical to wrap(kProxyLeaderPhase2b, encode(m))).
+    std::vector<uint8_t> reply_bytes;
+    std::vector<int32_t> reply_offs;
+    if (b.backend.has_wire() && n_out > 0) {
+      reply_bytes.resize((size_t)n_out * 46 + 16);
+      reply_offs.resize((size_t)n_out + 1);
+      int64_t werr = -1;
+      int wst = b.backend.wire_encode_phase2b(out.data(), n_out, reply_bytes.data(), (int)reply_bytes.size(),
+                                              reply_offs.data(), &werr);
+      if (wst != FPX_OK) logger.fatal(std::string("fpx_wire_encode_phase2b: ") + fpx_strerror(wst));
+    }
     size_t ip = 0, in_ = 0;
     for (size_t i = 0; i < n; ++i) {
       auto& pd = b.pending[i];
@@ -321,8 +348,12 @@ class GpuAcceptor : public Actor {
       bool accepted = ip < (size_t)n_out && out[ip].slot == pd.rec.slot && out[ip].round == pd.rec.round &&
                       ((out[ip].group << 16) | out[ip].acceptor) == pd.rec.dst;
       if (accepted) {
-        Phase2b m{out[ip].group, out[ip].acceptor, out[ip].slot, out[ip].round};
-        pd.acceptor->send(pd.src, wrap(kProxyLeaderPhase2b, encode(m)));                     // :211-219
+        if (!reply_offs.empty()) {
+          pd.acceptor->send(pd.src, Bytes(reply_bytes.begin() + reply_offs[ip], reply_bytes.begin() + reply_offs[ip + 1]));
+        } else {
+          Phase2b m{out[ip].group, out[ip].acceptor, out[ip].slot, out[ip].round};
+          pd.acceptor->send(pd.src, wrap(kProxyLeaderPhase2b, encode(m)));                   // :211-219
+        }
         ++ip;
       } else {
         const fpx_nack& k = nack.at(in_++);
@@ -360,8 +391,13 @@ class GpuProxyLeader : public Actor {
         for (auto& ga : chooser_(p))
           send(config_.acceptorAddresses.at((size_t)ga.first).at((size_t)ga.second), wrap(kAcceptorPhase2a, encode(p)));
     } else if (in.field == kProxyLeaderPhase2b) {               // handlePhase2b (:217-258)
-      Phase2b b = decode_phase2b(in.body);
-      votes_.push_back(fpx_p2b{b.groupIndex, b.acceptorIndex, b.slot, b.round});
+      if (backend_.has_wire()) {                                // parsed on the GPU at flush time
+        raw_votes_.insert(raw_votes_.end(), inbound.begin(), inbound.end());
+        raw_offs_.push_back((int32_t)raw_votes_.size());
+      } else {
+        Phase2b b = decode_phase2b(in.body);
+        votes_.push_back(fpx_p2b{b.groupIndex, b.acceptorIndex, b.slot, b.round});
+      }
     } else {
       logger_.fatal("Empty ProxyLeaderInbound encountered.");   // :166-167
     }
@@ -373,6 +409,16 @@ class GpuProxyLeader : public Actor {
       int st = backend_.arm(arms_.data(), (int)arms_.size(), &err);
       if (st != FPX_OK) logger_.fatal(std::string("fpx status ") + fpx_strerror(st) + " at record " + std::to_string(err));
       arms_.clear();
+    }
+    if (raw_offs_.size() > 1) {                                  // the burst's Phase2b messages, still as wire bytes
+      const int n = (int)raw_offs_.size() - 1;
+      std::vector<int32_t> kind((size_t)n);
+      std::vector<fpx_wire_rec> rec((size_t)n);
+      int st = backend_.wire_decode_proxyleader(raw_votes_.data(), raw_offs_.data(), n, kind.data(), rec.data(), &err);
+      if (st != FPX_OK) logger_.fatal(std::string("fpx status ") + fpx_strerror(st) + " at message " + std::to_string(err));
+      for (int i = 0; i < n; ++i) votes_.push_back(fpx_p2b{rec[(size_t)i].a, rec[(size_t)i].b, rec[(size_t)i].c, rec[(size_t)i].d});
+      raw_votes_.clear();
+      raw_offs_.assign(1, 0);
     }
     if (!votes_.empty()) {
       std::vector<fpx_chosen> out(votes_.size());
@@ -394,6 +440,8 @@ class GpuProxyLeader : public Actor {
   QuorumChooser chooser_;
   std::vector<fpx_p2a> arms_;
   std::vector<fpx_p2b> votes_;
+  std::vector<uint8_t> raw_votes_;                   // wire-capable backend: undecoded ProxyLeaderInbound{phase2b}
+  std::vector<int32_t> raw_offs_{0};
   std::set<std::pair<int, int>> seen_;
 };
 
