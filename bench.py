@@ -267,8 +267,13 @@ def main():
     d_out_p2b = torch.empty((nrec, 4), dtype=torch.int32, device=dev)
     d_out_nack = torch.empty((nrec, 2), dtype=torch.int32, device=dev)
     d_out_chosen = torch.empty((nrec, 2), dtype=torch.int32, device=dev)
-    d_wm = torch.zeros(1, dtype=torch.int32, device=dev)
-    d_wm_all = torch.zeros(N, dtype=torch.int32, device=dev)
+    # the per-step exchange (first-unchosen slot of every rank) runs on its own stream, double-buffered,
+    # so that it overlaps the next step's kernels instead of sitting on the engine's stream
+    d_wm = [torch.zeros(1, dtype=torch.int32, device=dev) for _ in range(2)]
+    d_wm_all = [torch.zeros(N, dtype=torch.int32, device=dev) for _ in range(2)]
+    comm = torch.cuda.Stream(device=dev) if N > 1 else None
+    ev_wm = [torch.cuda.Event() for _ in range(2)]
+    ev_gathered = [None, None]
     torch.cuda.synchronize()
 
     def step(s, ev=None):
@@ -279,10 +284,17 @@ def main():
         eng.proxyleader_phase2b_dev(d_p2b[s].data_ptr(), nrec, d_out_chosen.data_ptr())
         if ev: ev[2].record(ext)
         eng.replica_chosen_last_dev(d_out_chosen.data_ptr())
-        eng.chosen_watermark_dev(d_wm.data_ptr())
+        par = s & 1
+        if ev_gathered[par] is not None:
+            ext.wait_event(ev_gathered[par])          # the all-gather of step s-2 has read this buffer
+        eng.chosen_watermark_dev(d_wm[par].data_ptr())
         if N > 1:
-            with torch.cuda.stream(ext):
-                dist.all_gather_into_tensor(d_wm_all, d_wm)
+            ev_wm[par].record(ext)
+            comm.wait_event(ev_wm[par])
+            with torch.cuda.stream(comm):
+                dist.all_gather_into_tensor(d_wm_all[par], d_wm[par])
+                ev_gathered[par] = torch.cuda.Event()
+                ev_gathered[par].record(comm)
 
     def barrier():
         if N > 1:
@@ -304,6 +316,8 @@ def main():
     e_begin.record(ext)
     for k in range(K):
         step(W + k, evs[k])
+    if N > 1:
+        ext.wait_stream(comm)                         # the last exchanges are part of the timed region
     e_end.record(ext)
     barrier()
     t_timed1 = time.perf_counter()
@@ -313,6 +327,9 @@ def main():
     assert r.status == 0 and r.n_chosen == SLOTS_PER_STEP and r.n_nack == 0
     exp_wm = (S * SLOTS_PER_STEP) * N + rank
     assert r.watermark == exp_wm, (r.watermark, exp_wm)
+    if N > 1:   # the gathered frontiers of the last step: every rank's first-unchosen slot, global prefix = min
+        last = d_wm_all[(S - 1) & 1].cpu().numpy()
+        assert last.tolist() == [(S * SLOTS_PER_STEP) * N + g for g in range(N)], last
 
     t = torch.tensor([ms], dtype=torch.float64, device=dev)
     if N > 1:
@@ -351,8 +368,8 @@ def main():
             st |= L.fpx_chosen_watermark(eng.h, ctypes.byref(wm))
             assert st == 0 and n3.value == SLOTS_PER_STEP and n1.value == nrec, (st, n1.value, n3.value)
             if N > 1:
-                d_wm.fill_(wm.value)
-                dist.all_gather_into_tensor(d_wm_all, d_wm)
+                d_wm[0].fill_(wm.value)
+                dist.all_gather_into_tensor(d_wm_all[0], d_wm[0])
 
         for s in range(W):
             e2e_step(s)
