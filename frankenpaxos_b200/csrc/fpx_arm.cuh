@@ -114,7 +114,7 @@ __device__ __forceinline__ bool arm_finish(const ArmParams& P, const int4& rec, 
   }
 }
 
-constexpr int kArmUnroll = 4;
+constexpr int kArmUnroll = 8;
 
 __global__ void __launch_bounds__(256) arm_kernel(ArmParams P) {
   const Geometry& g = P.g;

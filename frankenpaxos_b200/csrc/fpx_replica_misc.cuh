@@ -77,8 +77,16 @@ __global__ void __launch_bounds__(256) watermark_scan_kernel(Geometry g, const u
   const int lo = __ldcg(&st->wm_local);
   const int hi = min(__ldcg(&st->max_chosen_local) + 2, g.local_slots);  // one past the last candidate hole
   int found = INT_MAX;
-  for (int i = lo + blockIdx.x * blockDim.x + threadIdx.x; i < hi && found == INT_MAX; i += gridDim.x * blockDim.x)
-    if (__ldcg(&rlog[i]) == kU64Empty) found = i;
+  // four independent loads per round trip (the early exit makes consecutive iterations dependent)
+  const int stride = gridDim.x * blockDim.x;
+  for (int i = lo + blockIdx.x * blockDim.x + threadIdx.x; i < hi && found == INT_MAX; i += 4 * stride) {
+    unsigned long long v[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) v[u] = (i + u * stride < hi) ? __ldcg(&rlog[i + u * stride]) : 0ull;
+#pragma unroll
+    for (int u = 3; u >= 0; --u)
+      if (i + u * stride < hi && v[u] == kU64Empty) found = i + u * stride;   // ascending: the smallest one last
+  }
   found = __reduce_min_sync(0xffffffffu, found);
   if ((threadIdx.x & 31) == 0) s_found[threadIdx.x >> 5] = found;
   __syncthreads();
