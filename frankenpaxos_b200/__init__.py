@@ -8,6 +8,7 @@ does -- there is no CPU fallback.
 """
 from .engine import (CHOSEN, NACK, P2A, P2B, Engine, FpxError, dst,  # noqa: F401
                      MULTIPAXOS, MENCIUS, VANILLA_MENCIUS, P2A_RANGE, P2B_RANGE, CHOSEN_RANGE, VM_SKIP, VALUE_NOOP,
-                     WIRE_REC, WIRE_PROXYLEADER_INBOUND, WIRE_ACCEPTOR_INBOUND)
+                     WIRE_REC, WIRE_PROXYLEADER_INBOUND, WIRE_ACCEPTOR_INBOUND,
+                     WIRE_MENCIUS_PROXYLEADER_INBOUND, WIRE_MENCIUS_ACCEPTOR_INBOUND)
 
 __all__ = ["Engine", "FpxError", "P2A", "P2B", "CHOSEN", "NACK", "dst"]

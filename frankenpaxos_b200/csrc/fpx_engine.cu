@@ -828,11 +828,12 @@ static bool aligned16(const void* p) { return ((uintptr_t)p & 15u) == 0; }
 
 int fpx_wire_decode_inbound_dev(fpx_engine* e, int32_t inbound, const uint8_t* d_bytes, const int32_t* d_offsets,
                                 int32_t n, int32_t* d_kind, fpx_wire_rec* d_out) {
-  if (!e || n < 0 || (inbound != FPX_WIRE_PROXYLEADER_INBOUND && inbound != FPX_WIRE_ACCEPTOR_INBOUND))
+  if (!e || n < 0 || inbound < FPX_WIRE_PROXYLEADER_INBOUND || inbound > FPX_WIRE_MENCIUS_ACCEPTOR_INBOUND)
     return FPX_ERR_INVALID_ARG;
+  if (inbound >= FPX_WIRE_MENCIUS_PROXYLEADER_INBOUND && e->g.protocol != FPX_MENCIUS) return FPX_ERR_UNSUPPORTED;
   if (n == 0) return FPX_OK;
   if (!d_bytes || !d_offsets || !d_kind || !d_out || !aligned16(d_bytes)) return FPX_ERR_INVALID_ARG;
-  WireDecodeParams P{d_bytes, d_offsets, n, inbound, d_kind, (int4*)d_out, e->st};
+  WireDecodeParams P{d_bytes, d_offsets, n, inbound, e->g.lgroups, e->g.agroups, d_kind, (int4*)d_out, e->st};
   wire_decode_kernel<<<(n + kWireDecThreads - 1) / kWireDecThreads, kWireDecThreads, 0, e->stream>>>(P);
   e->launches++;
   CK(e, cudaGetLastError());
@@ -879,7 +880,7 @@ static int wire_encode_launch(fpx_engine* e, const void* d_in, int32_t n, uint8_
     e->launches += 3;
   } else {
     // two passes: bytes per tile, then emit (each CTA sums the tiles before it itself)
-    const size_t smem = 16 + (size_t)kWireEncTile * (KIND == kWirePhase2b ? kWireMaxP2b : kWireMaxNack);
+    const size_t smem = 16 + (size_t)kWireEncTile * (KIND == kWireNack ? kWireMaxNack : kWireMaxP2b);
     wire_size_kernel<KIND><<<tiles, kWireEncThreads, 0, e->stream>>>(P);
     wire_emit_small_kernel<KIND><<<tiles, kWireEncThreads, smem, e->stream>>>(P, tiles);
     e->launches += 2;
@@ -894,6 +895,8 @@ int fpx_wire_encode_phase2b_dev(fpx_engine* e, const fpx_p2b* d_in, int32_t n, u
   if (!e || n < 0 || out_capacity < 0) return FPX_ERR_INVALID_ARG;
   if (n == 0) return FPX_OK;
   if (!d_in || !d_out || !d_offsets || !aligned16(d_out)) return FPX_ERR_INVALID_ARG;
+  if (e->g.protocol == FPX_MENCIUS)   // S/mencius: Phase2b carries no group index, ProxyLeaderInbound.phase2b = 4
+    return wire_encode_launch<kWireMenciusPhase2b>(e, d_in, n, d_out, out_capacity, d_offsets, nullptr, nullptr, 0);
   return wire_encode_launch<kWirePhase2b>(e, d_in, n, d_out, out_capacity, d_offsets, nullptr, nullptr, 0);
 }
 
@@ -944,6 +947,8 @@ extern "C" {
 
 int fpx_wire_encode_phase2b(fpx_engine* e, const fpx_p2b* in, int32_t n, uint8_t* out, int32_t out_capacity,
                             int32_t* offsets, int64_t* err_index) {
+  if (e && e->g.protocol == FPX_MENCIUS)
+    return wire_encode_host<kWireMenciusPhase2b>(e, in, 16, n, nullptr, nullptr, 0, out, out_capacity, offsets, err_index);
   return wire_encode_host<kWirePhase2b>(e, in, 16, n, nullptr, nullptr, 0, out, out_capacity, offsets, err_index);
 }
 int fpx_wire_encode_nack(fpx_engine* e, const fpx_nack* in, int32_t n, uint8_t* out, int32_t out_capacity,

@@ -96,10 +96,26 @@ struct WireReader {
   }
 };
 
-// inbound 0 = ProxyLeaderInbound {phase2a = 1, phase2b = 2}, 1 = AcceptorInbound {phase2a = 2}.
-// [lo, hi) and the offsets written to *out are reader positions; the caller rebases them.
+// A oneof member on the path = n leading required int32 fields (numbered 1..n) plus, for Phase2a, one
+// nested value (field 3) that is located, not parsed.
+//   inbound 0  multipaxos ProxyLeaderInbound (MultiPaxos.proto:541-549)  phase2a = 1, phase2b = 2
+//   inbound 1  multipaxos AcceptorInbound    (:551-561)                  phase2a = 2
+//   inbound 2  mencius ProxyLeaderInbound    (Mencius.proto:339-350)     phase2a = 2, phase2a_noop_range = 3,
+//                                                                        phase2b = 4, phase2b_noop_range = 5
+//   inbound 3  mencius AcceptorInbound       (:352-361)                  phase2a = 2, phase2a_noop_range = 3
+enum WireMember { kWmOpaque = 0, kWmP2a, kWmP2b4, kWmRange3, kWmMenciusP2b, kWmRangeVote5 };
+__device__ __forceinline__ int wire_member(int inbound, int which) {
+  if (inbound == 0) return which == 1 ? kWmP2a : which == 2 ? kWmP2b4 : kWmOpaque;
+  if (inbound == 1) return which == 2 ? kWmP2a : kWmOpaque;
+  if (inbound == 2)
+    return which == 2 ? kWmP2a : which == 3 ? kWmRange3 : which == 4 ? kWmMenciusP2b : which == 5 ? kWmRangeVote5 : kWmOpaque;
+  return which == 2 ? kWmP2a : which == 3 ? kWmRange3 : kWmOpaque;
+}
+
+// Reader positions in, reader positions out (*value_pos: out->z is a position the caller rebases).
 template <bool kShared>
-__device__ __forceinline__ bool wire_decode_one(int inbound, WireReader<kShared> r, int* kind, int4* out) {
+__device__ __forceinline__ bool wire_decode_one(int inbound, int lgroups, int agroups, WireReader<kShared> r, int* kind,
+                                                int4* out, bool* value_pos) {
   int which = 0;
   uint32_t blo = 0, bhi = 0;
   while (!r.done()) {
@@ -117,50 +133,48 @@ __device__ __forceinline__ bool wire_decode_one(int inbound, WireReader<kShared>
   }
   *kind = which;
   *out = make_int4(0, 0, 0, 0);
+  *value_pos = false;
   if (which == 0) return true;
-  const int f_p2a = inbound == 0 ? 1 : 2, f_p2b = inbound == 0 ? 2 : -1;
+  const int mk = wire_member(inbound, which);
+  if (mk == kWmOpaque) {
+    *out = make_int4(0, 0, (int)blo, (int)(bhi - blo));
+    *value_pos = true;
+    return true;
+  }
+  const int n_ints = mk == kWmP2a ? 2 : mk == kWmP2b4 ? 4 : mk == kWmRangeVote5 ? 5 : 3;
   WireReader<kShared> b = r;
   b.p = blo; b.end = bhi; b.ok = true;
-  if (which == f_p2b) {
-    int v0 = 0, v1 = 0, v2 = 0, v3 = 0;
-    unsigned have = 0;
-    while (!b.done()) {
-      const uint32_t tag = b.tag();
+  int v0 = 0, v1 = 0, v2 = 0, v3 = 0, v4 = 0;
+  unsigned have = 0;
+  uint32_t off = 0, len = 0;
+  bool have_value = false;
+  while (!b.done()) {
+    const uint32_t tag = b.tag();
+    if (!b.ok) return false;
+    const int f = (int)(tag >> 3), wt = (int)(tag & 7);
+    if (wt == 0 && f >= 1 && f <= n_ints) {
+      const int v = (int)b.int32();
       if (!b.ok) return false;
-      const int f = (int)(tag >> 3), wt = (int)(tag & 7);
-      if (wt == 0 && f >= 1 && f <= 4) {
-        const int v = (int)b.int32();
-        if (!b.ok) return false;
-        if (f == 1) v0 = v; else if (f == 2) v1 = v; else if (f == 3) v2 = v; else v3 = v;
-        have |= 1u << (f - 1);
-      } else if (!b.skip(wt)) {
-        return false;
-      }
+      if (f == 1) v0 = v; else if (f == 2) v1 = v; else if (f == 3) v2 = v; else if (f == 4) v3 = v; else v4 = v;
+      have |= 1u << (f - 1);
+    } else if (wt == 2 && mk == kWmP2a && f == 3) {
+      const uint32_t n = b.small();
+      if (!b.ok || b.end - b.p < n || have_value) return false;
+      off = b.p; len = n; have_value = true; b.p += n;          // the value bytes are not read
+    } else if (!b.skip(wt)) {
+      return false;
     }
-    if (have != 0xfu) return false;                    // "Message missing required fields."
-    *out = make_int4(v0, v1, v2, v3);
-  } else if (which == f_p2a) {
-    int slot = 0, round = 0;
-    uint32_t off = 0, len = 0;
-    unsigned have = 0;
-    while (!b.done()) {
-      const uint32_t tag = b.tag();
-      if (!b.ok) return false;
-      const int f = (int)(tag >> 3), wt = (int)(tag & 7);
-      if (wt == 0 && f == 1) { slot = (int)b.int32(); have |= 1u; if (!b.ok) return false; }
-      else if (wt == 0 && f == 2) { round = (int)b.int32(); have |= 2u; if (!b.ok) return false; }
-      else if (wt == 2 && f == 3) {
-        const uint32_t n = b.small();
-        if (!b.ok || b.end - b.p < n || (have & 4u)) return false;
-        off = b.p; len = n; have |= 4u; b.p += n;               // the value bytes are not read
-      } else if (!b.skip(wt)) {
-        return false;
-      }
-    }
-    if (have != 7u) return false;
-    *out = make_int4(slot, round, (int)off, (int)len);
-  } else {
-    *out = make_int4(0, 0, (int)blo, (int)(bhi - blo));
+  }
+  if (have != (1u << n_ints) - 1u || (mk == kWmP2a && !have_value)) return false;   // "Message missing required fields."
+  if (mk == kWmP2a) { *out = make_int4(v0, v1, (int)off, (int)len); *value_pos = true; }
+  else if (mk == kWmP2b4) *out = make_int4(v0, v1, v2, v3);
+  else if (mk == kWmRange3) *out = make_int4(v0, v1, v2, 0);               // {slot_start, slot_end, round, -}
+  else if (mk == kWmMenciusP2b) *out = make_int4(0, v0, v1, v2);           // an fpx_p2b; the group follows from the slot
+  else {                                                                    // Phase2bNoopRange -> an fpx_p2b_range
+    int dst = -1;
+    if (v0 >= 0 && v0 < agroups && v1 >= 0 && v1 < 0x10000 && lgroups > 0)
+      dst = ((((v2 % lgroups) + lgroups) % lgroups) * agroups + v0) << 16 | v1;
+    *out = make_int4(dst, v2, v3, v4);
   }
   return true;
 }
@@ -170,6 +184,7 @@ struct WireDecodeParams {
   const int32_t* offs;      // n + 1
   int32_t n;
   int32_t inbound;
+  int32_t lgroups, agroups;   // mencius geometry (Phase2bNoopRange's dst)
   int32_t* kind;
   int4* out;
   DevStatus* st;
@@ -202,13 +217,14 @@ __global__ void __launch_bounds__(kWireDecThreads) wire_decode_kernel(WireDecode
   int4 rec = make_int4(0, 0, 0, 0);
   bool ok = sane && a <= b && a >= lo && b <= hi;      // offsets must be monotone
   if (ok) {
+    bool value_pos = false;
     if (staged) {
       WireReader<true> r{(uint32_t)__cvta_generic_to_shared(s_buf), nullptr, (uint32_t)(a - base), (uint32_t)(b - base), true};
-      ok = wire_decode_one<true>(P.inbound, r, &kind, &rec);
-      if (ok && kind != 0 && !(kind == 2 && P.inbound == FPX_WIRE_PROXYLEADER_INBOUND)) rec.z += (int)base;   // window -> buffer offsets
+      ok = wire_decode_one<true>(P.inbound, P.lgroups, P.agroups, r, &kind, &rec, &value_pos);
+      if (ok && value_pos) rec.z += (int)base;                  // window -> buffer offsets
     } else {
       WireReader<false> r{0u, P.bytes, (uint32_t)a, (uint32_t)b, true};
-      ok = wire_decode_one<false>(P.inbound, r, &kind, &rec);
+      ok = wire_decode_one<false>(P.inbound, P.lgroups, P.agroups, r, &kind, &rec, &value_pos);
     }
   }
   if (!ok) report_error(P.st, FPX_ERR_WIRE, i);
@@ -250,7 +266,7 @@ __device__ __forceinline__ uint8_t* wire_put_int32(uint8_t* p, int field, int v)
   return p + n;
 }
 
-enum { kWirePhase2b = 0, kWireNack = 1, kWireChosen = 2 };
+enum { kWirePhase2b = 0, kWireNack = 1, kWireChosen = 2, kWireMenciusPhase2b = 3 };
 
 struct WireEncodeParams {
   const void* in;             // fpx_p2b (int4) | fpx_nack (int2) | fpx_chosen (int2)
@@ -272,6 +288,10 @@ __device__ __forceinline__ int wire_size_of(const WireEncodeParams& P, int i, bo
     int4 r = ((const int4*)P.in)[i];
     // ProxyLeaderInbound{phase2b = 2}: 0x12, len (< 128: one byte), four int32 fields
     return 2 + 4 + wire_int32_size(r.x) + wire_int32_size(r.y) + wire_int32_size(r.z) + wire_int32_size(r.w);
+  } else if (KIND == kWireMenciusPhase2b) {
+    int4 r = ((const int4*)P.in)[i];
+    // mencius ProxyLeaderInbound{phase2b = 4 {acceptor_index = 1, slot = 2, round = 3}}
+    return 2 + 3 + wire_int32_size(r.y) + wire_int32_size(r.z) + wire_int32_size(r.w);
   } else if (KIND == kWireNack) {
     int2 r = ((const int2*)P.in)[i];
     return 2 + 1 + wire_int32_size(r.y);     // LeaderInbound{nack = 6 {round = 1}}
@@ -392,6 +412,9 @@ __global__ void __launch_bounds__(kWireEncThreads) wire_emit_small_kernel(WireEn
         rec[u] = __ldcg((const int4*)P.in + i);      // second read of the records: L2
         sz[u] = 2 + 4 + wire_int32_size(rec[u].x) + wire_int32_size(rec[u].y) + wire_int32_size(rec[u].z) +
                 wire_int32_size(rec[u].w);
+      } else if (KIND == kWireMenciusPhase2b) {
+        rec[u] = __ldcg((const int4*)P.in + i);
+        sz[u] = 2 + 3 + wire_int32_size(rec[u].y) + wire_int32_size(rec[u].z) + wire_int32_size(rec[u].w);
       } else {
         int2 r = __ldcg((const int2*)P.in + i);
         rec[u].y = r.y;
@@ -426,6 +449,9 @@ __global__ void __launch_bounds__(kWireEncThreads) wire_emit_small_kernel(WireEn
       *p++ = 0x12; *p++ = (uint8_t)(sz[u] - 2);
       p = wire_put_int32(p, 1, rec[u].x); p = wire_put_int32(p, 2, rec[u].y); p = wire_put_int32(p, 3, rec[u].z);
       p = wire_put_int32(p, 4, rec[u].w);
+    } else if (KIND == kWireMenciusPhase2b) {
+      *p++ = 0x22; *p++ = (uint8_t)(sz[u] - 2);
+      p = wire_put_int32(p, 1, rec[u].y); p = wire_put_int32(p, 2, rec[u].z); p = wire_put_int32(p, 3, rec[u].w);
     } else {
       *p++ = 0x32; *p++ = (uint8_t)(sz[u] - 2);
       p = wire_put_int32(p, 1, rec[u].y);

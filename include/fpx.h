@@ -357,11 +357,17 @@ int fpx_mencius_replica_chosen_range(fpx_engine* e, const fpx_chosen_range* in, 
  * are FPX_ERR_WIRE too).  Encoders emit the canonical form (fields in number order, minimal
  * varints, negative int32 as 10 bytes), which is what toByteArray produces.  Buffers: bytes
  * and out 16-byte aligned for the *_dev forms; total size below 2^31. */
-enum { FPX_WIRE_PROXYLEADER_INBOUND = 0, FPX_WIRE_ACCEPTOR_INBOUND = 1 };
+enum { FPX_WIRE_PROXYLEADER_INBOUND = 0, FPX_WIRE_ACCEPTOR_INBOUND = 1,
+       /* S/mencius/Mencius.proto (protocol FPX_MENCIUS): ProxyLeaderInbound :339-350 {phase2a = 2,
+        * phase2a_noop_range = 3, phase2b = 4, phase2b_noop_range = 5}, AcceptorInbound :352-361 */
+       FPX_WIRE_MENCIUS_PROXYLEADER_INBOUND = 2, FPX_WIRE_MENCIUS_ACCEPTOR_INBOUND = 3 };
 /* One decoded message.  kind[i] = field number of the `request` oneof member that is set
- * (0: none).  Phase2b -> {group, acceptor, slot, round} (an fpx_p2b); Phase2a -> {slot,
- * round, value_off, value_len}: the CommandBatchOrNoop is bytes[value_off .. +value_len),
- * never read; any other member -> {0, 0, body_off, body_len} for the host to parse. */
+ * (0: none).  Phase2b -> {group, acceptor, slot, round} (an fpx_p2b; mencius' Phase2b :169-176
+ * has no group index: 0); Phase2a -> {slot, round, value_off, value_len}: the
+ * CommandBatchOrNoop is bytes[value_off .. +value_len), never read; mencius
+ * Phase2aNoopRange :160-167 -> {slot_start, slot_end, round, 0}; Phase2bNoopRange :178-187 ->
+ * an fpx_p2b_range (dst built from acceptor_group_index and the leader group of slot_start;
+ * -1 if out of range); any other member -> {0, 0, body_off, body_len} for the host. */
 typedef struct { int32_t a, b, c, d; } fpx_wire_rec;
 
 int fpx_wire_decode_inbound(fpx_engine* e, int32_t inbound, const uint8_t* bytes, const int32_t* offsets, int32_t n,
@@ -369,7 +375,8 @@ int fpx_wire_decode_inbound(fpx_engine* e, int32_t inbound, const uint8_t* bytes
 int fpx_wire_decode_inbound_dev(fpx_engine* e, int32_t inbound, const uint8_t* d_bytes, const int32_t* d_offsets,
                                 int32_t n, int32_t* d_kind, fpx_wire_rec* d_out);
 /* ProxyLeaderInbound{phase2b}: the acceptor's replies, ready for transport.send.  offsets[n+1]
- * is written; the bytes must fit out_capacity (FPX_ERR_INVALID_ARG otherwise). */
+ * is written; the bytes must fit out_capacity (FPX_ERR_INVALID_ARG otherwise).  With protocol
+ * FPX_MENCIUS the mencius shape is written ({acceptor_index, slot, round} under field 4). */
 int fpx_wire_encode_phase2b(fpx_engine* e, const fpx_p2b* in, int32_t n, uint8_t* out, int32_t out_capacity,
                             int32_t* offsets, int64_t* err_index);
 int fpx_wire_encode_phase2b_dev(fpx_engine* e, const fpx_p2b* d_in, int32_t n, uint8_t* d_out, int32_t out_capacity,

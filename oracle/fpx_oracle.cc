@@ -1062,8 +1062,27 @@ struct Reader {
   }
 };
 struct Rec { int32_t a, b, c, d; };
-// inbound 0 = ProxyLeaderInbound (phase2a = 1, phase2b = 2), 1 = AcceptorInbound (phase2a = 2)
-inline int decode_one(int inbound, const uint8_t* base, int64_t lo, int64_t hi, int32_t* kind, Rec* out) {
+// A oneof member on the path = n leading required int32 fields (numbered 1..n) plus, for Phase2a,
+// one nested value (field 3) that is located, not parsed.
+//   inbound 0  multipaxos ProxyLeaderInbound  (MultiPaxos.proto:541-549)  phase2a = 1, phase2b = 2
+//   inbound 1  multipaxos AcceptorInbound     (:551-561)                  phase2a = 2
+//   inbound 2  mencius ProxyLeaderInbound     (Mencius.proto:339-350)     phase2a = 2, phase2a_noop_range = 3,
+//                                                                         phase2b = 4, phase2b_noop_range = 5
+//   inbound 3  mencius AcceptorInbound        (:352-361)                  phase2a = 2, phase2a_noop_range = 3
+enum MemberKind { kOpaque = 0, kP2a, kP2b4, kRange3, kMenciusP2b, kRangeVote5 };
+inline MemberKind member_kind(int inbound, int which) {
+  switch (inbound) {
+    case 0: return which == 1 ? kP2a : which == 2 ? kP2b4 : kOpaque;
+    case 1: return which == 2 ? kP2a : kOpaque;
+    case 2: return which == 2 ? kP2a : which == 3 ? kRange3 : which == 4 ? kMenciusP2b : which == 5 ? kRangeVote5 : kOpaque;
+    case 3: return which == 2 ? kP2a : which == 3 ? kRange3 : kOpaque;
+    default: return kOpaque;
+  }
+}
+// lgroups / agroups: the mencius geometry, only used to turn Phase2bNoopRange's (acceptor_group_index,
+// acceptor_index) into the engine's dst = (leader_group * agroups + acceptor_group) << 16 | acceptor
+inline int decode_one(int inbound, const uint8_t* base, int64_t lo, int64_t hi, int lgroups, int agroups, int32_t* kind,
+                      Rec* out) {
   Reader r{base + lo, base + hi};
   int which = 0; const uint8_t* blo = nullptr; const uint8_t* bhi = nullptr;
   while (!r.done()) {
@@ -1082,38 +1101,38 @@ inline int decode_one(int inbound, const uint8_t* base, int64_t lo, int64_t hi, 
   *kind = which;
   *out = Rec{0, 0, 0, 0};
   if (which == 0) return 0;
-  const int f_p2a = inbound == 0 ? 1 : 2, f_p2b = inbound == 0 ? 2 : -1;
+  const MemberKind mk = member_kind(inbound, which);
+  if (mk == kOpaque) { *out = Rec{0, 0, (int32_t)(blo - base), (int32_t)(bhi - blo)}; return 0; }
+  const int n_ints = mk == kP2a ? 2 : mk == kP2b4 ? 4 : mk == kRangeVote5 ? 5 : 3;
   Reader b{blo, bhi};
-  if (which == f_p2b) {
-    int32_t v[4] = {0, 0, 0, 0}; unsigned have = 0;
-    while (!b.done()) {
-      uint64_t tag = b.varint();
-      if (!b.ok || (tag >> 3) == 0) return kWireError;
-      int f = (int)(tag >> 3), wt = (int)(tag & 7);
-      if (wt == 0 && f >= 1 && f <= 4) { v[f - 1] = (int32_t)b.varint(); have |= 1u << (f - 1); if (!b.ok) return kWireError; }
-      else if (!b.skip(wt)) return kWireError;
+  int32_t v[5] = {0, 0, 0, 0, 0}; unsigned have = 0;
+  int64_t off = 0, len = 0; bool have_value = false;
+  while (!b.done()) {
+    uint64_t tag = b.varint();
+    if (!b.ok || (tag >> 3) == 0) return kWireError;
+    int f = (int)(tag >> 3), wt = (int)(tag & 7);
+    if (wt == 0 && f >= 1 && f <= n_ints) { v[f - 1] = (int32_t)b.varint(); have |= 1u << (f - 1); if (!b.ok) return kWireError; }
+    else if (wt == 2 && mk == kP2a && f == 3) {
+      uint64_t n = b.varint();
+      if (!b.ok || (uint64_t)(b.end - b.p) < n) return kWireError;
+      if (have_value) return kWireError;              // a second value would be MERGED by the parser: never emitted, not supported
+      off = b.p - base; len = (int64_t)n; have_value = true; b.p += n;
+    } else if (!b.skip(wt)) return kWireError;
+  }
+  if (have != (1u << n_ints) - 1u || (mk == kP2a && !have_value)) return kWireError;   // "Message missing required fields"
+  switch (mk) {
+    case kP2a: *out = Rec{v[0], v[1], (int32_t)off, (int32_t)len}; break;
+    case kP2b4: *out = Rec{v[0], v[1], v[2], v[3]}; break;
+    case kRange3: *out = Rec{v[0], v[1], v[2], 0}; break;                 // {slot_start, slot_end, round, -}
+    case kMenciusP2b: *out = Rec{0, v[0], v[1], v[2]}; break;            // an fpx_p2b; the group follows from the slot
+    case kRangeVote5: {                                                   // an fpx_p2b_range
+      int32_t dst = -1;
+      if (v[0] >= 0 && v[0] < agroups && v[1] >= 0 && v[1] < 0x10000 && lgroups > 0)
+        dst = ((((v[2] % lgroups) + lgroups) % lgroups) * agroups + v[0]) << 16 | v[1];
+      *out = Rec{dst, v[2], v[3], v[4]};
+      break;
     }
-    if (have != 0xf) return kWireError;               // "Message missing required fields"
-    *out = Rec{v[0], v[1], v[2], v[3]};
-  } else if (which == f_p2a) {
-    int32_t slot = 0, round = 0; int64_t off = 0, len = 0; unsigned have = 0;
-    while (!b.done()) {
-      uint64_t tag = b.varint();
-      if (!b.ok || (tag >> 3) == 0) return kWireError;
-      int f = (int)(tag >> 3), wt = (int)(tag & 7);
-      if (wt == 0 && f == 1) { slot = (int32_t)b.varint(); have |= 1; if (!b.ok) return kWireError; }
-      else if (wt == 0 && f == 2) { round = (int32_t)b.varint(); have |= 2; if (!b.ok) return kWireError; }
-      else if (wt == 2 && f == 3) {
-        uint64_t n = b.varint();
-        if (!b.ok || (uint64_t)(b.end - b.p) < n) return kWireError;
-        if (have & 4) return kWireError;                // a second value would be MERGED by the parser: never emitted, not supported
-        off = b.p - base; len = (int64_t)n; have |= 4; b.p += n;
-      } else if (!b.skip(wt)) return kWireError;
-    }
-    if (have != 7) return kWireError;
-    *out = Rec{slot, round, (int32_t)off, (int32_t)len};
-  } else {
-    *out = Rec{0, 0, (int32_t)(blo - base), (int32_t)(bhi - blo)};
+    default: break;
   }
   return 0;
 }
@@ -1387,11 +1406,12 @@ void fpo_ep_largest_ballot(void* p, int* out) {
 
 
 // ---- wire codec.  offsets[n+1] delimit the messages inside `bytes`.
-int fpo_wire_decode_inbound(int inbound, const uint8_t* bytes, const int32_t* offsets, int n, int32_t* kind,
-                            int32_t* out /* n x 4 */, int64_t* err) {
+int fpo_wire_decode_inbound(int inbound, const uint8_t* bytes, const int32_t* offsets, int n, int lgroups, int agroups,
+                            int32_t* kind, int32_t* out /* n x 4 */, int64_t* err) {
   *err = -1;
   for (int i = 0; i < n; ++i) {
-    int st = fpo::wire::decode_one(inbound, bytes, offsets[i], offsets[i + 1], &kind[i], (fpo::wire::Rec*)(out + 4 * i));
+    int st = fpo::wire::decode_one(inbound, bytes, offsets[i], offsets[i + 1], lgroups, agroups, &kind[i],
+                                   (fpo::wire::Rec*)(out + 4 * i));
     if (st != 0) { *err = i; return st; }
   }
   return 0;
@@ -1405,6 +1425,19 @@ int64_t fpo_wire_encode_phase2b(const P2b* in, int n, uint8_t* out, int32_t* off
     int body = 4 + int32_size(in[i].group) + int32_size(in[i].acceptor) + int32_size(in[i].slot) + int32_size(in[i].round);
     *p++ = 0x12; p = put_varint(p, (uint64_t)body);
     p = put_int32(p, 1, in[i].group); p = put_int32(p, 2, in[i].acceptor); p = put_int32(p, 3, in[i].slot); p = put_int32(p, 4, in[i].round);
+  }
+  offsets[n] = (int32_t)(p - out);
+  return p - out;
+}
+// mencius ProxyLeaderInbound{phase2b = 4 {acceptor_index = 1, slot = 2, round = 3}} (Mencius.proto:169-176, 339-350)
+int64_t fpo_wire_encode_mencius_phase2b(const P2b* in, int n, uint8_t* out, int32_t* offsets) {
+  using namespace fpo::wire;
+  uint8_t* p = out;
+  for (int i = 0; i < n; ++i) {
+    offsets[i] = (int32_t)(p - out);
+    int body = 3 + int32_size(in[i].acceptor) + int32_size(in[i].slot) + int32_size(in[i].round);
+    *p++ = 0x22; p = put_varint(p, (uint64_t)body);
+    p = put_int32(p, 1, in[i].acceptor); p = put_int32(p, 2, in[i].slot); p = put_int32(p, 3, in[i].round);
   }
   offsets[n] = (int32_t)(p - out);
   return p - out;

@@ -109,9 +109,10 @@ def lib():
         L.fpo_ep_entry.argtypes = [vp, i32, i32, vp]; L.fpo_ep_entry.restype = i32
         L.fpo_ep_leader_kind.argtypes = [vp, i32, i32]; L.fpo_ep_leader_kind.restype = i32
         L.fpo_ep_largest_ballot.argtypes = [vp, vp]
-        L.fpo_wire_decode_inbound.argtypes = [i32, vp, vp, i32, vp, vp, i64p]; L.fpo_wire_decode_inbound.restype = i32
+        L.fpo_wire_decode_inbound.argtypes = [i32, vp, vp, i32, i32, i32, vp, vp, i64p]; L.fpo_wire_decode_inbound.restype = i32
         L.fpo_wire_encode_phase2b.argtypes = [vp, i32, vp, vp]; L.fpo_wire_encode_phase2b.restype = C.c_int64
         L.fpo_wire_encode_nack.argtypes = [vp, i32, vp, vp]; L.fpo_wire_encode_nack.restype = C.c_int64
+        L.fpo_wire_encode_mencius_phase2b.argtypes = [vp, i32, vp, vp]; L.fpo_wire_encode_mencius_phase2b.restype = C.c_int64
         L.fpo_wire_encode_chosen.argtypes = [vp, i32, vp, vp, i32, vp, vp, i64p]; L.fpo_wire_encode_chosen.restype = C.c_int64
         L.fpo_vm_new.argtypes = [i32]; L.fpo_vm_new.restype = vp
         L.fpo_vm_free.argtypes = [vp]
@@ -461,6 +462,7 @@ class VanillaMencius:
 # --------------------------------------------------------------------------- wire codec
 WIRE_REC = np.dtype([("a", "<i4"), ("b", "<i4"), ("c", "<i4"), ("d", "<i4")])
 WIRE_PROXYLEADER_INBOUND, WIRE_ACCEPTOR_INBOUND = 0, 1
+WIRE_MENCIUS_PROXYLEADER_INBOUND, WIRE_MENCIUS_ACCEPTOR_INBOUND = 2, 3
 
 
 def pack_messages(msgs):
@@ -471,14 +473,14 @@ def pack_messages(msgs):
     return buf, offs
 
 
-def wire_decode_inbound(inbound, buf, offs):
+def wire_decode_inbound(inbound, buf, offs, lgroups=1, agroups=1):
     buf = np.ascontiguousarray(buf, dtype=np.uint8); offs = np.ascontiguousarray(offs, dtype=np.int32)
     n = len(offs) - 1
     kind = np.zeros(max(n, 1), dtype=np.int32); out = np.zeros(max(n, 1), dtype=WIRE_REC)
     err = C.c_int64(-1)
     pad = buf if len(buf) else np.zeros(1, dtype=np.uint8)
-    st = lib().fpo_wire_decode_inbound(inbound, pad.ctypes.data, offs.ctypes.data, n, kind.ctypes.data, out.ctypes.data,
-                                       C.byref(err))
+    st = lib().fpo_wire_decode_inbound(inbound, pad.ctypes.data, offs.ctypes.data, n, lgroups, agroups, kind.ctypes.data,
+                                       out.ctypes.data, C.byref(err))
     return st, err.value, kind[:n], out[:n]
 
 
@@ -492,6 +494,10 @@ def _wire_encode(fn, recs, dtype, max_per):
 
 def wire_encode_phase2b(recs):
     return _wire_encode(lib().fpo_wire_encode_phase2b, recs, P2B, 46)
+
+
+def wire_encode_mencius_phase2b(recs):
+    return _wire_encode(lib().fpo_wire_encode_mencius_phase2b, recs, P2B, 46)
 
 
 def wire_encode_nack(recs):

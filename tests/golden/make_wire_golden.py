@@ -62,6 +62,40 @@ def build_pool():
     msg("ReplicaInbound", [("chosen", 1, MSG, OPT, "Chosen")], "request")
     pool = descriptor_pool.DescriptorPool()
     pool.Add(fdp)
+    # S/mencius/Mencius.proto: Phase2a :151-158, Phase2aNoopRange :160-167, Phase2b :169-176 (no group
+    # index), Phase2bNoopRange :178-187, ProxyLeaderInbound :339-350, AcceptorInbound :352-361
+    mdp = descriptor_pb2.FileDescriptorProto()
+    mdp.name = "Mencius.proto"; mdp.package = "frankenpaxos.mencius"; mdp.syntax = "proto2"
+    mdp.dependency.append("MultiPaxos.proto")
+
+    def mmsg(name, fields, oneof=None):
+        m = mdp.message_type.add(); m.name = name
+        if oneof:
+            m.oneof_decl.add().name = oneof
+        for (fname, num, ftype, label, tname) in fields:
+            f = m.field.add(); f.name = fname; f.number = num; f.type = ftype; f.label = label
+            if tname:
+                f.type_name = tname
+            if oneof:
+                f.oneof_index = 0
+
+    MP = ".frankenpaxos.mencius."
+    mmsg("Phase2a", [("slot", 1, I32, REQ, None), ("round", 2, I32, REQ, None),
+                     ("command_batch_or_noop", 3, MSG, REQ, f".{PKG}.CommandBatchOrNoop")])
+    mmsg("Phase2aNoopRange", [("slot_start_inclusive", 1, I32, REQ, None), ("slot_end_exclusive", 2, I32, REQ, None),
+                              ("round", 3, I32, REQ, None)])
+    mmsg("Phase2b", [("acceptor_index", 1, I32, REQ, None), ("slot", 2, I32, REQ, None), ("round", 3, I32, REQ, None)])
+    mmsg("Phase2bNoopRange", [("acceptor_group_index", 1, I32, REQ, None), ("acceptor_index", 2, I32, REQ, None),
+                              ("slot_start_inclusive", 3, I32, REQ, None), ("slot_end_exclusive", 4, I32, REQ, None),
+                              ("round", 5, I32, REQ, None)])
+    mmsg("HighWatermark", [("next_slot", 1, I32, REQ, None)])
+    mmsg("ProxyLeaderInbound", [("high_watermark", 1, MSG, OPT, MP + "HighWatermark"), ("phase2a", 2, MSG, OPT, MP + "Phase2a"),
+                                ("phase2a_noop_range", 3, MSG, OPT, MP + "Phase2aNoopRange"),
+                                ("phase2b", 4, MSG, OPT, MP + "Phase2b"),
+                                ("phase2b_noop_range", 5, MSG, OPT, MP + "Phase2bNoopRange")], "request")
+    mmsg("AcceptorInbound", [("phase2a", 2, MSG, OPT, MP + "Phase2a"),
+                             ("phase2a_noop_range", 3, MSG, OPT, MP + "Phase2aNoopRange")], "request")
+    pool.Add(mdp)
     return pool
 
 
@@ -70,6 +104,10 @@ POOL = build_pool()
 
 def cls(name):
     return message_factory.GetMessageClass(POOL.FindMessageTypeByName(f"{PKG}.{name}"))
+
+
+def mcls(name):
+    return message_factory.GetMessageClass(POOL.FindMessageTypeByName(f"frankenpaxos.mencius.{name}"))
 
 
 def payload(g, n_cmds, cmd_len):
@@ -128,6 +166,31 @@ def main():
     # another member of the AcceptorInbound oneof: reported by kind, not decoded
     m = cls("AcceptorInbound")(phase1a=cls("Phase1a")(round=7, chosen_watermark=1000))
     cases.append({"type": "AcceptorInbound.phase1a", "hex": m.SerializeToString().hex(), "round": 7, "chosen_watermark": 1000})
+    # S/mencius shapes
+    for k in range(len(EDGE)):
+        a, sl, rd = EDGE[k] % 5 if EDGE[k] >= 0 else EDGE[k], EDGE[(k + 2) % len(EDGE)], EDGE[(k + 4) % len(EDGE)]
+        m = mcls("ProxyLeaderInbound")(phase2b=mcls("Phase2b")(acceptor_index=a, slot=sl, round=rd))
+        cases.append({"type": "mencius.ProxyLeaderInbound.phase2b", "hex": m.SerializeToString().hex(),
+                      "acceptor_index": a, "slot": sl, "round": rd})
+        ag, st, en = k % 3, EDGE[(k + 1) % len(EDGE)], EDGE[(k + 3) % len(EDGE)]
+        m = mcls("ProxyLeaderInbound")(phase2b_noop_range=mcls("Phase2bNoopRange")(
+            acceptor_group_index=ag, acceptor_index=k % 3, slot_start_inclusive=st, slot_end_exclusive=en, round=rd))
+        cases.append({"type": "mencius.ProxyLeaderInbound.phase2b_noop_range", "hex": m.SerializeToString().hex(),
+                      "acceptor_group_index": ag, "acceptor_index": k % 3, "slot_start": st, "slot_end": en, "round": rd})
+        rng = mcls("Phase2aNoopRange")(slot_start_inclusive=st, slot_end_exclusive=en, round=rd)
+        for outer in ("ProxyLeaderInbound", "AcceptorInbound"):
+            m = mcls(outer)(phase2a_noop_range=rng)
+            cases.append({"type": f"mencius.{outer}.phase2a_noop_range", "hex": m.SerializeToString().hex(),
+                          "slot_start": st, "slot_end": en, "round": rd})
+    for k, (n_cmds, cmd_len) in enumerate([(-1, 0), (1, 50), (2, 130)]):
+        v = payload(g, n_cmds, cmd_len)
+        p2a = mcls("Phase2a")(slot=EDGE[k + 3], round=k, command_batch_or_noop=v)
+        for outer in ("ProxyLeaderInbound", "AcceptorInbound"):
+            m = mcls(outer)(phase2a=p2a)
+            cases.append({"type": f"mencius.{outer}.phase2a", "hex": m.SerializeToString().hex(), "slot": EDGE[k + 3],
+                          "round": k, "payload_hex": v.SerializeToString().hex()})
+    m = mcls("ProxyLeaderInbound")(high_watermark=mcls("HighWatermark")(next_slot=77))
+    cases.append({"type": "mencius.ProxyLeaderInbound.high_watermark", "hex": m.SerializeToString().hex(), "next_slot": 77})
     # parser robustness: hand-made byte strings and what an independent parser makes of them
     good = cls("ProxyLeaderInbound")(phase2b=cls("Phase2b")(group_index=1, acceptor_index=2, slot=128, round=255)).SerializeToString()
     body = bytes.fromhex("2007" "1803" "0801" "1002" "2009" "2a03616263" "3d01020304" "0a0178")

@@ -163,3 +163,50 @@ def test_malformed_random_mutations_agree_with_oracle(eng):
             ms[k] = bytes(m)
         bad += same_decode(eng, WIRE_PROXYLEADER_INBOUND, ms) != 0
     assert bad > 10
+
+
+def test_mencius_shapes(golden_dir=None):
+    """S/mencius message shapes (Mencius.proto): golden vectors, oracle agreement, and the decoded range
+    records drive the range entry points directly."""
+    from frankenpaxos_b200 import (MENCIUS, WIRE_MENCIUS_ACCEPTOR_INBOUND, WIRE_MENCIUS_PROXYLEADER_INBOUND, P2B_RANGE)
+    LG, AG, per = 3, 3, 3
+    e = Engine(1, AG, per, num_leaders=2, num_replicas=2, slot_capacity=1 << 12, max_batch=1 << 12, protocol=MENCIUS,
+               num_leader_groups=LG)
+    for t, inbound in (("mencius.ProxyLeaderInbound.phase2b", 2), ("mencius.ProxyLeaderInbound.phase2b_noop_range", 2),
+                       ("mencius.ProxyLeaderInbound.phase2a_noop_range", 2), ("mencius.AcceptorInbound.phase2a_noop_range", 3),
+                       ("mencius.ProxyLeaderInbound.phase2a", 2), ("mencius.AcceptorInbound.phase2a", 3),
+                       ("mencius.ProxyLeaderInbound.high_watermark", 2)):
+        msgs = [bytes.fromhex(c["hex"]) for c in of_type(t)]
+        buf, offs = O.pack_messages(msgs)
+        st, err, okind, orec = O.wire_decode_inbound(inbound, buf, offs, LG, AG)
+        kind, rec = e.wire_decode_inbound(inbound, buf, offs)
+        assert st == 0 and np.array_equal(kind, okind) and np.array_equal(rec.view(np.int32), orec.view(np.int32)), t
+    cs = of_type("mencius.ProxyLeaderInbound.phase2b")
+    recs = np.array([(0, c["acceptor_index"], c["slot"], c["round"]) for c in cs], dtype=P2B)
+    out, offs = e.wire_encode_phase2b(recs)                       # protocol FPX_MENCIUS: the mencius shape
+    assert [bytes(out[offs[i]: offs[i + 1]]).hex() for i in range(len(cs))] == [c["hex"] for c in cs]
+    g = np.random.Generator(np.random.PCG64(5))
+    recs = np.zeros(3000, dtype=P2B)
+    for f in ("acceptor", "slot", "round"):
+        recs[f] = rand_i32(g, len(recs))
+    out, offs = e.wire_encode_phase2b(recs)
+    oout, ooffs = O.wire_encode_mencius_phase2b(recs)
+    assert np.array_equal(offs, ooffs) and np.array_equal(out, oout)
+    kind, rec = e.wire_decode_inbound(WIRE_MENCIUS_PROXYLEADER_INBOUND, out, offs)
+    assert (kind == 4).all() and np.array_equal(rec.view(np.int32), recs.view(np.int32))
+    # wire -> range entry points: arm a range, decode the acceptors' Phase2bNoopRange bytes, tally them
+    from frankenpaxos_b200 import P2A_RANGE
+    e.mencius_arm_range(np.array([(1, 301, 0, -1)], dtype=P2A_RANGE))
+    votes = b"".join(bytes([0x2a, 11, 0x08, ag, 0x10, a, 0x18, 0x01, 0x20, 0xad, 0x02, 0x28, 0x00])
+                     for ag in range(AG) for a in range(2))
+    offs = np.arange(0, len(votes) + 1, 13, dtype=np.int32)
+    kind, rec = e.wire_decode_inbound(WIRE_MENCIUS_PROXYLEADER_INBOUND, np.frombuffer(votes, dtype=np.uint8), offs)
+    assert (kind == 5).all()
+    chosen = e.mencius_range_phase2b(rec.view(P2B_RANGE))
+    assert chosen.tolist() == [(1, 301)]
+    # the mencius shapes need a mencius engine (its geometry builds the range votes' dst)
+    e2 = Engine(1, 1, 3, slot_capacity=64, max_batch=64)
+    with pytest.raises(FpxError) as ei:
+        e2.wire_decode_inbound(WIRE_MENCIUS_ACCEPTOR_INBOUND, np.zeros(1, dtype=np.uint8), np.array([0, 1], dtype=np.int32))
+    assert ei.value.status == -11
+    e.close(); e2.close()

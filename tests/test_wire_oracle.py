@@ -122,3 +122,42 @@ def test_parser_robustness_agrees_with_an_independent_parser():
                 assert rec[0].tolist() == (v["group_index"], v["acceptor_index"], v["slot"], v["round"]), c["name"]
             if v["kind"] == 1:
                 assert (rec[0]["a"], rec[0]["b"]) == (v["slot"], v["round"])
+
+
+def test_mencius_shapes_golden():
+    """S/mencius/Mencius.proto: Phase2b has no group index, the oneofs are numbered differently, and the
+    NoopRange messages decode straight into the engine's range records."""
+    LG, AG = 3, 3
+    cs = of_type("mencius.ProxyLeaderInbound.phase2b")
+    buf, offs = O.pack_messages([bytes.fromhex(c["hex"]) for c in cs])
+    st, err, kind, rec = O.wire_decode_inbound(O.WIRE_MENCIUS_PROXYLEADER_INBOUND, buf, offs, LG, AG)
+    assert st == 0 and (kind == 4).all()
+    assert rec.tolist() == [(0, c["acceptor_index"], c["slot"], c["round"]) for c in cs]
+    recs = np.array([(0, c["acceptor_index"], c["slot"], c["round"]) for c in cs], dtype=O.P2B)
+    out, eoffs = O.wire_encode_mencius_phase2b(recs)
+    assert [bytes(out[eoffs[i]: eoffs[i + 1]]).hex() for i in range(len(cs))] == [c["hex"] for c in cs]
+    cs = of_type("mencius.ProxyLeaderInbound.phase2b_noop_range")
+    buf, offs = O.pack_messages([bytes.fromhex(c["hex"]) for c in cs])
+    st, err, kind, rec = O.wire_decode_inbound(O.WIRE_MENCIUS_PROXYLEADER_INBOUND, buf, offs, LG, AG)
+    assert st == 0 and (kind == 5).all()
+    for c, r in zip(cs, rec):
+        lg = c["slot_start"] % LG                      # Python's % is already non-negative
+        dst = ((lg * AG + c["acceptor_group_index"]) << 16) | c["acceptor_index"]
+        assert r.tolist() == (dst, c["slot_start"], c["slot_end"], c["round"])
+    for outer, inbound in (("ProxyLeaderInbound", O.WIRE_MENCIUS_PROXYLEADER_INBOUND), ("AcceptorInbound", O.WIRE_MENCIUS_ACCEPTOR_INBOUND)):
+        cs = of_type(f"mencius.{outer}.phase2a_noop_range")
+        buf, offs = O.pack_messages([bytes.fromhex(c["hex"]) for c in cs])
+        st, err, kind, rec = O.wire_decode_inbound(inbound, buf, offs, LG, AG)
+        assert st == 0 and (kind == 3).all()
+        assert rec.tolist() == [(c["slot_start"], c["slot_end"], c["round"], 0) for c in cs]
+        cs = of_type(f"mencius.{outer}.phase2a")
+        buf, offs = O.pack_messages([bytes.fromhex(c["hex"]) for c in cs])
+        st, err, kind, rec = O.wire_decode_inbound(inbound, buf, offs, LG, AG)
+        assert st == 0 and (kind == 2).all()
+        for c, r in zip(cs, rec):
+            assert (r["a"], r["b"]) == (c["slot"], c["round"])
+            assert bytes(buf[r["c"]: r["c"] + r["d"]]).hex() == c["payload_hex"]
+    c = of_type("mencius.ProxyLeaderInbound.high_watermark")[0]
+    buf, offs = O.pack_messages([bytes.fromhex(c["hex"])])
+    st, err, kind, rec = O.wire_decode_inbound(O.WIRE_MENCIUS_PROXYLEADER_INBOUND, buf, offs, LG, AG)
+    assert st == 0 and kind.tolist() == [1] and bytes(buf[rec[0]["c"]: rec[0]["c"] + rec[0]["d"]]).hex() == "084d"
