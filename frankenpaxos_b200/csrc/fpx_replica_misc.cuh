@@ -78,14 +78,14 @@ __global__ void __launch_bounds__(256) watermark_scan_kernel(Geometry g, const u
   const int hi = min(__ldcg(&st->max_chosen_local) + 2, g.local_slots);  // one past the last candidate hole
   int found = INT_MAX;
   // four independent loads per round trip (the early exit makes consecutive iterations dependent)
-  const int stride = gridDim.x * blockDim.x;
-  for (int i = lo + blockIdx.x * blockDim.x + threadIdx.x; i < hi && found == INT_MAX; i += 4 * stride) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = lo + (long long)blockIdx.x * blockDim.x + threadIdx.x; i < hi && found == INT_MAX; i += 4 * stride) {
     unsigned long long v[4];
 #pragma unroll
     for (int u = 0; u < 4; ++u) v[u] = (i + u * stride < hi) ? __ldcg(&rlog[i + u * stride]) : 0ull;
 #pragma unroll
     for (int u = 3; u >= 0; --u)
-      if (i + u * stride < hi && v[u] == kU64Empty) found = i + u * stride;   // ascending: the smallest one last
+      if (i + u * stride < hi && v[u] == kU64Empty) found = (int)(i + u * stride);   // ascending: the smallest one last
   }
   found = __reduce_min_sync(0xffffffffu, found);
   if ((threadIdx.x & 31) == 0) s_found[threadIdx.x >> 5] = found;
