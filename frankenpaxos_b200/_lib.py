@@ -19,7 +19,7 @@ SYMBOLS = [
     "fpx_replica_chosen_dev", "fpx_replica_chosen_last_dev", "fpx_chosen_watermark_dev", "fpx_sync",
     "fpx_stream", "fpx_launch_count", "fpx_set_coop_ctas_per_sm",
     "fpx_acceptor_phase1a", "fpx_leader_safe_values",
-    "fpx_vm_client_request", "fpx_vm_phase2a", "fpx_vm_learn_chosen", "fpx_vm_skip",
+    "fpx_vm_client_request", "fpx_vm_phase2a", "fpx_vm_learn_chosen", "fpx_vm_skip", "fpx_vm_client_request_dev", "fpx_vm_phase2a_dev",
     "fpx_mencius_arm_range", "fpx_mencius_acceptor_noop_range", "fpx_mencius_range_phase2b",
     "fpx_mencius_replica_chosen_range",
     "fpx_wire_decode_inbound", "fpx_wire_decode_inbound_dev", "fpx_wire_encode_phase2b", "fpx_wire_encode_phase2b_dev",
@@ -86,6 +86,8 @@ def lib():
     L.fpx_vm_phase2a.argtypes = [vp, vp, i32, vp, p(i64)]; L.fpx_vm_phase2a.restype = i32
     L.fpx_vm_learn_chosen.argtypes = [vp, vp, i32, p(i64)]; L.fpx_vm_learn_chosen.restype = i32
     L.fpx_vm_skip.argtypes = [vp, vp, i32, p(i64)]; L.fpx_vm_skip.restype = i32
+    L.fpx_vm_client_request_dev.argtypes = [vp, vp, i32]; L.fpx_vm_client_request_dev.restype = i32
+    L.fpx_vm_phase2a_dev.argtypes = [vp, vp, i32, vp]; L.fpx_vm_phase2a_dev.restype = i32
     L.fpx_mencius_arm_range.argtypes = [vp, vp, i32, p(i64)]; L.fpx_mencius_arm_range.restype = i32
     L.fpx_mencius_acceptor_noop_range.argtypes = [vp, vp, i32, vp, p(i32), vp, p(i32), p(i64)]
     L.fpx_mencius_acceptor_noop_range.restype = i32

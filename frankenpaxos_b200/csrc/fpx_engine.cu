@@ -629,6 +629,11 @@ int fpx_proxyleader_phase2b(fpx_engine* e, const fpx_p2b* in, int32_t n, fpx_cho
 
 // --------------------------------------------------------------------------- vanilla Mencius
 
+int fpx_vm_client_request_dev(fpx_engine* e, const fpx_p2a* d_in, int32_t n) {
+  if (e && e->g.protocol != FPX_VANILLA_MENCIUS) return FPX_ERR_UNSUPPORTED;
+  return arm_launch(e, d_in, n, 1);
+}
+
 int fpx_vm_client_request(fpx_engine* e, const fpx_p2a* in, int32_t n, int64_t* err_index) {
   if (err_index) *err_index = -1;
   int c = check_n(e, in, n);
@@ -636,12 +641,34 @@ int fpx_vm_client_request(fpx_engine* e, const fpx_p2a* in, int32_t n, int64_t* 
   if (e->g.protocol != FPX_VANILLA_MENCIUS) return FPX_ERR_UNSUPPORTED;
   CK(e, cudaSetDevice(e->cfg.device));
   CK(e, cudaMemcpyAsync(e->d_in, in, (size_t)n * 16, cudaMemcpyHostToDevice, e->stream));
-  c = arm_launch(e, (const fpx_p2a*)e->d_in, n, 1);
+  c = fpx_vm_client_request_dev(e, (const fpx_p2a*)e->d_in, n);
   if (c != FPX_OK) return c;
   fpx_sync_result r;
   c = fpx_sync(e, &r);
   if (err_index) *err_index = r.err_index;
   return c;
+}
+
+// which: 0 handlePhase2a (d_reply dense), 1 handleChosen
+static int vm_launch(fpx_engine* e, const void* d_in, int32_t n, fpx_p2b* d_reply, int which) {
+  int c = check_n(e, d_in, n);
+  if (c != FPX_OK || n == 0) return c;
+  if (e->g.protocol != FPX_VANILLA_MENCIUS) return FPX_ERR_UNSUPPORTED;
+  if (which == 0 && !d_reply) return FPX_ERR_INVALID_ARG;
+  VmParams P;
+  P.g = e->g; P.in = (const int4*)d_in; P.out = (int4*)d_reply; P.n = n; P.votes = e->votes;
+  P.claim = e->vm_claim; P.rows = e->rows; P.st = e->st;
+  P.tag = e->vm_tag++;
+  if (e->vm_tag == 0xffffffffu) e->vm_tag = 1;
+  if (which == 0) vm_phase2a_kernel<<<(n + 255) / 256, 256, 0, e->stream>>>(P);
+  else vm_learn_chosen_kernel<<<(n + 255) / 256, 256, 0, e->stream>>>(P);
+  e->launches++;
+  CK(e, cudaGetLastError());
+  return FPX_OK;
+}
+
+int fpx_vm_phase2a_dev(fpx_engine* e, const fpx_p2a* d_in, int32_t n, fpx_p2b* d_reply) {
+  return vm_launch(e, d_in, n, d_reply, 0);
 }
 
 static int vm_call(fpx_engine* e, const void* in, int32_t n, fpx_p2b* reply, int64_t* err_index, int which) {
@@ -652,15 +679,8 @@ static int vm_call(fpx_engine* e, const void* in, int32_t n, fpx_p2b* reply, int
   if (which == 0 && !reply) return FPX_ERR_INVALID_ARG;
   CK(e, cudaSetDevice(e->cfg.device));
   CK(e, cudaMemcpyAsync(e->d_in, in, (size_t)n * 16, cudaMemcpyHostToDevice, e->stream));
-  VmParams P;
-  P.g = e->g; P.in = (const int4*)e->d_in; P.out = (int4*)e->d_out_a; P.n = n; P.votes = e->votes;
-  P.claim = e->vm_claim; P.rows = e->rows; P.st = e->st;
-  P.tag = e->vm_tag++;
-  if (e->vm_tag == 0xffffffffu) e->vm_tag = 1;
-  if (which == 0) vm_phase2a_kernel<<<(n + 255) / 256, 256, 0, e->stream>>>(P);
-  else vm_learn_chosen_kernel<<<(n + 255) / 256, 256, 0, e->stream>>>(P);
-  e->launches++;
-  CK(e, cudaGetLastError());
+  c = vm_launch(e, e->d_in, n, (fpx_p2b*)e->d_out_a, which);
+  if (c != FPX_OK) return c;
   if (which == 0) CK(e, cudaMemcpyAsync(reply, e->d_out_a, (size_t)n * 16, cudaMemcpyDeviceToHost, e->stream));
   fpx_sync_result r;
   c = fpx_sync(e, &r);

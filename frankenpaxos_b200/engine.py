@@ -285,6 +285,12 @@ class Engine:
         return self._wire_encode(self._L.fpx_wire_encode_chosen, recs, CHOSEN, 0, arena.ctypes.data if len(arena) else None,
                                  value_offsets.ctypes.data, len(value_offsets) - 1, cap)
 
+    def vm_client_request_dev(self, d_in, n):
+        self._check(self._L.fpx_vm_client_request_dev(self.h, d_in, n))
+
+    def vm_phase2a_dev(self, d_in, n, d_reply):
+        self._check(self._L.fpx_vm_phase2a_dev(self.h, d_in, n, d_reply))
+
     def wire_decode_inbound_dev(self, inbound, d_bytes, d_offsets, n, d_kind, d_out):
         self._check(self._L.fpx_wire_decode_inbound_dev(self.h, inbound, d_bytes, d_offsets, n, d_kind, d_out))
 

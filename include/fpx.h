@@ -280,6 +280,9 @@ int fpx_vm_client_request(fpx_engine* e, const fpx_p2a* in, int32_t n, int64_t* 
  *   kind 1  Phase2Nack(slot, round = the entry's round)  (:1044-1051)
  *   kind 2  Chosen(slot, value in `round`)               (:1018-1027, entry already chosen) */
 int fpx_vm_phase2a(fpx_engine* e, const fpx_p2a* in, int32_t n, fpx_p2b* reply, int64_t* err_index);
+/* device-pointer forms (asynchronous on the engine's stream, errors surface at fpx_sync) */
+int fpx_vm_client_request_dev(fpx_engine* e, const fpx_p2a* d_in, int32_t n);
+int fpx_vm_phase2a_dev(fpx_engine* e, const fpx_p2a* d_in, int32_t n, fpx_p2b* d_reply);
 
 /* Server.handlePhase2b (:1084-1142) is fpx_proxyleader_phase2b with this protocol's
  * rules: no Phase 2 running for the slot -> ignored (:1099-1106), stale round ->
