@@ -9,7 +9,7 @@ import numpy as np
 import pytest
 
 import harness as H
-from frankenpaxos_b200 import CHOSEN, P2A, P2B, Engine, FpxError, dst
+from frankenpaxos_b200 import CHOSEN, NACK, P2A, P2B, Engine, FpxError, dst
 from frankenpaxos_b200 import traces as T
 from oracle import fpx_oracle_py as O
 
@@ -638,3 +638,45 @@ def test_vanilla_mencius_sharded_by_slot_residue():
         eng.close()
     allc = np.concatenate(whole)
     assert np.array_equal(np.sort(allc["slot"]), np.arange(per * P))
+
+
+def test_device_pointer_path_matches_oracle():
+    """The *_dev entry points bench.py times (inputs and outputs resident in HBM, one fpx_sync at the
+    end): arm -> acceptor -> tally -> replica (count taken from the device) -> watermark, with a round
+    bump in the middle so that the Nack stream and the exact compaction are exercised too."""
+    import torch
+    cfg, _ = T.config_by_name("cfg2")
+    n_slots = 20000
+    eng, ora = H.make_pair(cfg, n_slots, max_batch=1 << 17, overflow_capacity=1 << 12)
+    g = T.rng(77)
+    dev = torch.device("cuda", 0)
+    slots = np.arange(n_slots, dtype=np.int32)
+    a = T.arms(slots, 0, slots * 2 + 1)
+    p = T.phase2as(g, slots, cfg["f"], 1, 5, False, 0, slots * 2 + 1)
+    hi = T.phase2as(g, slots[::50], cfg["f"], 1, 5, False, 2, slots[::50] * 2)      # a newer leader's messages
+    p = np.concatenate([p[: len(p) // 2], hi, p[len(p) // 2:]])                       # later round-0 messages get Nacks
+    st, idx = ora.arm(np.concatenate([a, T.arms(slots[::50], 2, slots[::50] * 2)]))
+    _, _, ob, on = ora.acceptor_phase2a(p)
+    votes = ob[g.permutation(len(ob))]
+    _, _, oc = ora.proxyleader_phase2b(votes)
+    ora.replica_chosen(oc)
+
+    def td(x):
+        return torch.from_numpy(x.view(np.int32).reshape(len(x), -1).copy()).to(dev)
+    d_a = td(np.concatenate([a, T.arms(slots[::50], 2, slots[::50] * 2)])); d_p = td(p); d_v = td(votes)
+    d_p2b = torch.zeros((len(p), 4), dtype=torch.int32, device=dev); d_nack = torch.zeros((len(p), 2), dtype=torch.int32, device=dev)
+    d_ch = torch.zeros((len(votes), 2), dtype=torch.int32, device=dev); d_wm = torch.zeros(1, dtype=torch.int32, device=dev)
+    eng.proxyleader_arm_dev(d_a.data_ptr(), len(d_a))
+    eng.acceptor_phase2a_dev(d_p.data_ptr(), len(p), d_p2b.data_ptr(), d_nack.data_ptr())
+    eng.proxyleader_phase2b_dev(d_v.data_ptr(), len(votes), d_ch.data_ptr())
+    eng.replica_chosen_last_dev(d_ch.data_ptr())
+    eng.chosen_watermark_dev(d_wm.data_ptr())
+    r = eng.sync()
+    assert (r.status, r.n_p2b, r.n_nack, r.n_chosen) == (0, len(ob), len(on), len(oc)) and len(on) > 0
+    assert r.watermark == ora.executed_watermark() == int(d_wm.item())
+    H.same(d_p2b[: r.n_p2b].cpu().numpy().view(P2B).reshape(-1), ob, "Phase2b stream (device)")
+    H.same(d_nack[: r.n_nack].cpu().numpy().view(NACK).reshape(-1), on, "Nack stream (device)")
+    H.same(d_ch[: r.n_chosen].cpu().numpy().view(CHOSEN).reshape(-1), oc, "Chosen stream (device)")
+    H.compare_acceptors(eng, ora, cfg, 0, n_slots)
+    H.compare_log(eng, ora, 0, n_slots)
+    eng.close()
