@@ -276,7 +276,7 @@ int fpx_create(fpx_engine** out, const fpx_config* cfg) {
                                                       (size_t)g.num_keys * kThreads * 4));
     e->occ_acceptor = std::max(occ, 1);
     e->grid_acceptor = std::min(std::max(occ, 1) * e->num_sms, kMaxGrid);
-    const int smem_cap = 56 * 1024;  // Chosen buffer: kWarps * per * 8 bytes
+    const int smem_cap = 55 * 1024;  // Chosen buffer: kWarps * per * 8 bytes; 4 CTAs x (55 + 1 reserved) KB fit one SM
     e->tally_per_cap = (smem_cap / (kWarps * 8)) & ~31;   // warp ranges are rounded up to 32 records: stay within smem_cap
     const void* tk = tally_kernel_ptr(g.row_words);
     CKC(cudaFuncSetAttribute(tk, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_cap));
