@@ -161,19 +161,25 @@ class ClockSampler(threading.Thread):
         except Exception:
             self.ok = False
 
-    def run(self):
+    def sample_now(self):
+        """One sample.  (Sampling from the launch loop itself was tried: an NVML query costs ~0.1 ms of
+        host time and showed up 1:1 in the step time, so the polling thread stays the only sampler; when
+        it is starved of the GIL during the short timed region, summary() falls back to a wider window.)"""
         if not self.ok:
             return
         nv = self.nv
-        while not self.stop_flag:
-            try:
-                mhz = nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)
-                reasons = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h) \
-                    if hasattr(nv, "nvmlDeviceGetCurrentClocksEventReasons") \
-                    else nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
-                self.samples.append((time.perf_counter(), mhz, reasons))
-            except Exception:
-                pass
+        try:
+            mhz = nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)
+            reasons = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h) \
+                if hasattr(nv, "nvmlDeviceGetCurrentClocksEventReasons") \
+                else nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+            self.samples.append((time.perf_counter(), mhz, reasons))
+        except Exception:
+            pass
+
+    def run(self):
+        while self.ok and not self.stop_flag:
+            self.sample_now()
             time.sleep(0.0001)
 
     def summary(self, windows):
