@@ -28,6 +28,7 @@
 using namespace fpx;
 
 constexpr int kMaxEvents = 16;
+constexpr int kStepRing = 1024;
 
 struct fpx_engine {
   fpx_config cfg;
@@ -50,6 +51,8 @@ struct fpx_engine {
   int32_t* rng_dec = nullptr;              // per-record scratch of the range kernels (FPX_MAX_RANGE_BATCH)
   uint32_t rng_seq_base = 1;               // Phase2bNoopRange delivery sequence numbers
   int unit_ranges = 0;                     // a one-slot range was ever armed: arms must look at the range keys
+  // fpx_step_dev: CUDA events around the acceptor and tally kernels of the last kStepRing steps
+  cudaEvent_t* step_ev = nullptr;          // [kStepRing][3], created on first use
   // wire codec staging (grown on demand)
   struct WireBuf { void* p = nullptr; size_t cap = 0; };
   WireBuf w_bytes, w_offs, w_kind, w_rec, w_out, w_tiles, w_arena, w_voffs;
@@ -303,6 +306,10 @@ void fpx_destroy(fpx_engine* e) {
   cudaFree(e->rows); cudaFree(e->ovf_keys); cudaFree(e->ovf_rows); cudaFree(e->votes);
   cudaFree(e->acc_round); cudaFree(e->acc_max_voted); cudaFree(e->rlog); cudaFree(e->vm_claim); cudaFree(e->st);
   cudaFree(e->rng_tab); cudaFree(e->rng_dec);
+  if (e->step_ev) {
+    for (int i = 0; i < kStepRing * 3; ++i) cudaEventDestroy(e->step_ev[i]);
+    delete[] e->step_ev;
+  }
   for (fpx_engine::WireBuf* b : {&e->w_bytes, &e->w_offs, &e->w_kind, &e->w_rec, &e->w_out, &e->w_tiles, &e->w_arena,
                                  &e->w_voffs})
     cudaFree(b->p);
@@ -512,6 +519,42 @@ int fpx_chosen_watermark_dev(fpx_engine* e, int32_t* d_out) {
   watermark_scan_kernel<<<e->num_sms * 4, 256, 0, e->stream>>>(e->g, e->rlog, e->st, d_out);
   e->launches += 1;
   CK(e, cudaGetLastError());
+  return FPX_OK;
+}
+
+int fpx_step_dev(fpx_engine* e, const fpx_p2a* d_arm, int32_t n_arm, const fpx_p2a* d_p2a, int32_t n_p2a,
+                 fpx_p2b* d_out_p2b, fpx_nack* d_out_nack, const fpx_p2b* d_p2b, int32_t n_p2b, fpx_chosen* d_out_chosen,
+                 int32_t* d_watermark, int32_t ring_slot) {
+  if (!e) return FPX_ERR_INVALID_ARG;
+  cudaEvent_t* ev = nullptr;
+  if (ring_slot >= 0) {
+    if (!e->step_ev) {
+      e->step_ev = new (std::nothrow) cudaEvent_t[kStepRing * 3];
+      if (!e->step_ev) return FPX_ERR_INVALID_ARG;
+      for (int i = 0; i < kStepRing * 3; ++i) CK(e, cudaEventCreate(&e->step_ev[i]));
+    }
+    ev = e->step_ev + (size_t)(ring_slot % kStepRing) * 3;
+  }
+  int c = fpx_proxyleader_arm_dev(e, d_arm, n_arm);
+  if (c != FPX_OK) return c;
+  if (ev) CK(e, cudaEventRecord(ev[0], e->stream));
+  c = fpx_acceptor_phase2a_dev(e, d_p2a, n_p2a, d_out_p2b, d_out_nack);
+  if (c != FPX_OK) return c;
+  if (ev) CK(e, cudaEventRecord(ev[1], e->stream));
+  c = fpx_proxyleader_phase2b_dev(e, d_p2b, n_p2b, d_out_chosen);
+  if (c != FPX_OK) return c;
+  if (ev) CK(e, cudaEventRecord(ev[2], e->stream));
+  c = fpx_replica_chosen_last_dev(e, d_out_chosen);
+  if (c != FPX_OK) return c;
+  return fpx_chosen_watermark_dev(e, d_watermark);
+}
+
+int fpx_step_kernel_ms(fpx_engine* e, int32_t ring_slot, float* acceptor_ms, float* tally_ms) {
+  if (!e || !e->step_ev || ring_slot < 0 || !acceptor_ms || !tally_ms) return FPX_ERR_INVALID_ARG;
+  cudaEvent_t* ev = e->step_ev + (size_t)(ring_slot % kStepRing) * 3;
+  CK(e, cudaEventSynchronize(ev[2]));
+  CK(e, cudaEventElapsedTime(acceptor_ms, ev[0], ev[1]));
+  CK(e, cudaEventElapsedTime(tally_ms, ev[1], ev[2]));
   return FPX_OK;
 }
 

@@ -316,6 +316,16 @@ class Engine:
     def chosen_watermark_dev(self, d_out=None):
         self._check(self._L.fpx_chosen_watermark_dev(self.h, d_out))
 
+    def step_dev(self, d_arm, n_arm, d_p2a, n_p2a, d_out_p2b, d_out_nack, d_p2b, n_p2b, d_out_chosen, d_wm, ring_slot=-1):
+        """arm -> acceptor -> tally -> replica (count from the device) -> watermark, one C call."""
+        self._check(self._L.fpx_step_dev(self.h, d_arm, n_arm, d_p2a, n_p2a, d_out_p2b, d_out_nack, d_p2b, n_p2b,
+                                         d_out_chosen, d_wm, ring_slot))
+
+    def step_kernel_ms(self, ring_slot):
+        a, t = C.c_float(0), C.c_float(0)
+        self._check(self._L.fpx_step_kernel_ms(self.h, ring_slot, C.byref(a), C.byref(t)))
+        return a.value, t.value
+
     def set_coop_ctas_per_sm(self, k):
         """Cap the cooperative kernels at k resident CTAs per SM (0 = full grid) so that
         several engines can run side by side on one GPU."""

@@ -501,6 +501,18 @@ typedef struct {
 
 int fpx_sync(fpx_engine* e, fpx_sync_result* out);
 
+/* One pipeline step on device-resident buffers, issued back to back from C: fpx_proxyleader_arm_dev,
+ * fpx_acceptor_phase2a_dev, fpx_proxyleader_phase2b_dev, fpx_replica_chosen_last_dev,
+ * fpx_chosen_watermark_dev -- exactly those five calls (co-located roles chained on one GPU; a
+ * caller-side loop in a slow language otherwise pays its per-call overhead five times per step).
+ * ring_slot >= 0 additionally records CUDA events on the engine's stream before and after the
+ * acceptor and the tally kernel; fpx_step_kernel_ms(ring_slot) returns their durations once the
+ * step has run (a ring of 1024 steps). */
+int fpx_step_dev(fpx_engine* e, const fpx_p2a* d_arm, int32_t n_arm, const fpx_p2a* d_p2a, int32_t n_p2a,
+                 fpx_p2b* d_out_p2b, fpx_nack* d_out_nack, const fpx_p2b* d_p2b, int32_t n_p2b, fpx_chosen* d_out_chosen,
+                 int32_t* d_watermark, int32_t ring_slot);
+int fpx_step_kernel_ms(fpx_engine* e, int32_t ring_slot, float* acceptor_ms, float* tally_ms);
+
 /* The engine's CUDA stream (a cudaStream_t) so a caller can order its own work
  * (events, NCCL collectives) with the engine's. */
 void* fpx_stream(fpx_engine* e);

@@ -640,8 +640,10 @@ def test_vanilla_mencius_sharded_by_slot_residue():
     assert np.array_equal(np.sort(allc["slot"]), np.arange(per * P))
 
 
-def test_device_pointer_path_matches_oracle():
-    """The *_dev entry points bench.py times (inputs and outputs resident in HBM, one fpx_sync at the
+@pytest.mark.parametrize("one_call", [False, True])
+def test_device_pointer_path_matches_oracle(one_call):
+    """(one_call: the same five launches issued by fpx_step_dev, with its event ring.)
+    The *_dev entry points bench.py times (inputs and outputs resident in HBM, one fpx_sync at the
     end): arm -> acceptor -> tally -> replica (count taken from the device) -> watermark, with a round
     bump in the middle so that the Nack stream and the exact compaction are exercised too."""
     import torch
@@ -666,12 +668,19 @@ def test_device_pointer_path_matches_oracle():
     d_a = td(np.concatenate([a, T.arms(slots[::50], 2, slots[::50] * 2)])); d_p = td(p); d_v = td(votes)
     d_p2b = torch.zeros((len(p), 4), dtype=torch.int32, device=dev); d_nack = torch.zeros((len(p), 2), dtype=torch.int32, device=dev)
     d_ch = torch.zeros((len(votes), 2), dtype=torch.int32, device=dev); d_wm = torch.zeros(1, dtype=torch.int32, device=dev)
-    eng.proxyleader_arm_dev(d_a.data_ptr(), len(d_a))
-    eng.acceptor_phase2a_dev(d_p.data_ptr(), len(p), d_p2b.data_ptr(), d_nack.data_ptr())
-    eng.proxyleader_phase2b_dev(d_v.data_ptr(), len(votes), d_ch.data_ptr())
-    eng.replica_chosen_last_dev(d_ch.data_ptr())
-    eng.chosen_watermark_dev(d_wm.data_ptr())
+    if one_call:
+        eng.step_dev(d_a.data_ptr(), len(d_a), d_p.data_ptr(), len(p), d_p2b.data_ptr(), d_nack.data_ptr(),
+                     d_v.data_ptr(), len(votes), d_ch.data_ptr(), d_wm.data_ptr(), ring_slot=3)
+    else:
+        eng.proxyleader_arm_dev(d_a.data_ptr(), len(d_a))
+        eng.acceptor_phase2a_dev(d_p.data_ptr(), len(p), d_p2b.data_ptr(), d_nack.data_ptr())
+        eng.proxyleader_phase2b_dev(d_v.data_ptr(), len(votes), d_ch.data_ptr())
+        eng.replica_chosen_last_dev(d_ch.data_ptr())
+        eng.chosen_watermark_dev(d_wm.data_ptr())
     r = eng.sync()
+    if one_call:
+        acc_ms, tally_ms = eng.step_kernel_ms(3)
+        assert 0 < acc_ms < 50 and 0 < tally_ms < 50
     assert (r.status, r.n_p2b, r.n_nack, r.n_chosen) == (0, len(ob), len(on), len(oc)) and len(on) > 0
     assert r.watermark == ora.executed_watermark() == int(d_wm.item())
     H.same(d_p2b[: r.n_p2b].cpu().numpy().view(P2B).reshape(-1), ob, "Phase2b stream (device)")
