@@ -352,6 +352,41 @@ struct TopOne {
   }
 };
 
+// KeyValueStore.typedTopKConflictIndex(k = 1) (S/statemachine/KeyValueStore.scala:219-302): the
+// conflict index an EPaxos replica consults in computeSequenceNumberAndDependencies
+// (S/epaxos/Replica.scala:569-600) -- per key one TopOne of the gets and one of the sets, plus
+// the snapshots' TopOne.  Keys are caller-assigned integers (the reference uses strings).
+// Groundwork for SURVEY 8(f) rank 4; pinned by T/statemachine/TopKConflictIndexTest.scala:281-330,
+// 380-437 (k = 1 cases).
+struct KvTopOneConflictIndex {
+  int num_leaders;
+  std::map<int, TopOne> gets, sets;
+  TopOne snapshots;
+  explicit KvTopOneConflictIndex(int n) : num_leaders(n), snapshots(n) {}
+  // put(commandKey, command) (:229-251)
+  void put(int leader, int id, bool is_set, const int* keys, int n_keys) {
+    auto& m = is_set ? sets : gets;
+    for (int i = 0; i < n_keys; ++i) m.emplace(keys[i], TopOne(num_leaders)).first->second.put(leader, id);
+  }
+  void put_snapshot(int leader, int id) { snapshots.put(leader, id); }           // :253-254
+  // getTopOneConflicts(command) (:256-300): a get conflicts with the sets of its keys, a set with
+  // their gets and sets; no keys -> the snapshots alone
+  TopOne top_one_conflicts(bool is_set, const int* keys, int n_keys) const {
+    if (n_keys == 0) return snapshots;                                            // :261-262 / :277-278
+    TopOne merged(num_leaders);
+    for (int i = 0; i < n_keys; ++i) {
+      auto s = sets.find(keys[i]);
+      if (s != sets.end()) merged.merge_equals(s->second);
+      if (is_set) {
+        auto g = gets.find(keys[i]);
+        if (g != gets.end()) merged.merge_equals(g->second);
+      }
+    }
+    merged.merge_equals(snapshots);                                               // :271 / :293
+    return merged;
+  }
+};
+
 // util.QuorumWatermark (S/util/QuorumWatermark.scala:31-48)
 struct QuorumWatermark {
   std::vector<int> w;
@@ -1243,6 +1278,16 @@ void fpo_topone_merge(void* a, void* b) { ((TopOne*)a)->merge_equals(*(TopOne*)b
 void fpo_topone_get(void* p, int* out) {
   auto& t = ((TopOne*)p)->top;
   std::copy(t.begin(), t.end(), out);
+}
+void* fpo_kvci_new(int num_leaders) { return new KvTopOneConflictIndex(num_leaders); }
+void fpo_kvci_free(void* p) { delete (KvTopOneConflictIndex*)p; }
+void fpo_kvci_put(void* p, int leader, int id, int is_set, const int* keys, int n_keys) {
+  ((KvTopOneConflictIndex*)p)->put(leader, id, is_set != 0, keys, n_keys);
+}
+void fpo_kvci_put_snapshot(void* p, int leader, int id) { ((KvTopOneConflictIndex*)p)->put_snapshot(leader, id); }
+void fpo_kvci_top_one_conflicts(void* p, int is_set, const int* keys, int n_keys, int* out) {
+  TopOne t = ((KvTopOneConflictIndex*)p)->top_one_conflicts(is_set != 0, keys, n_keys);
+  std::copy(t.top.begin(), t.top.end(), out);
 }
 void* fpo_qw_new(int n) { return new QuorumWatermark(n); }
 void fpo_qw_free(void* p) { delete (QuorumWatermark*)p; }

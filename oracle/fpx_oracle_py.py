@@ -68,6 +68,11 @@ def lib():
         L.fpo_topone_put.argtypes = [vp, i32, i32]
         L.fpo_topone_merge.argtypes = [vp, vp]
         L.fpo_topone_get.argtypes = [vp, ip]
+        L.fpo_kvci_new.argtypes = [i32]; L.fpo_kvci_new.restype = vp
+        L.fpo_kvci_free.argtypes = [vp]
+        L.fpo_kvci_put.argtypes = [vp, i32, i32, i32, ip, i32]
+        L.fpo_kvci_put_snapshot.argtypes = [vp, i32, i32]
+        L.fpo_kvci_top_one_conflicts.argtypes = [vp, i32, ip, i32, ip]
         L.fpo_qw_new.argtypes = [i32]; L.fpo_qw_new.restype = vp
         L.fpo_qw_free.argtypes = [vp]
         L.fpo_qw_update.argtypes = [vp, i32, i32]
@@ -518,3 +523,30 @@ def wire_encode_chosen(recs, arena, value_offsets):
     if total < 0:
         return int(total), err.value, None, None
     return 0, -1, out[:total].copy(), offs
+
+
+class KvTopOneConflictIndex:
+    """KeyValueStore.typedTopKConflictIndex(k = 1): integer keys instead of strings."""
+
+    def __init__(self, num_leaders):
+        self.n = num_leaders
+        self.h = lib().fpo_kvci_new(num_leaders)
+
+    def __del__(self):
+        try:
+            lib().fpo_kvci_free(self.h)
+        except Exception:
+            pass
+
+    def put(self, command_key, is_set, keys):
+        k, n = _iarr(keys)
+        lib().fpo_kvci_put(self.h, command_key[0], command_key[1], int(is_set), k, n)
+
+    def put_snapshot(self, command_key):
+        lib().fpo_kvci_put_snapshot(self.h, command_key[0], command_key[1])
+
+    def top_one_conflicts(self, is_set, keys):
+        k, n = _iarr(keys)
+        out = (C.c_int * self.n)()
+        lib().fpo_kvci_top_one_conflicts(self.h, int(is_set), k, n, out)
+        return list(out)

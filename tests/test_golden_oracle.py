@@ -140,3 +140,21 @@ def test_buffer_map_known_answers(golden_dir):
             else:
                 assert L.fpo_bm_get(h, op[1]) == op[2], (t["name"], op)
         L.fpo_bm_free(h)
+
+
+def test_kv_top_one_conflict_index_known_answers(golden_dir):
+    """KeyValueStore.typedTopKConflictIndex(k = 1) (S/statemachine/KeyValueStore.scala:219-302) against the
+    reference's own expectations (T/statemachine/TopKConflictIndexTest.scala, k = 1 cases): the step
+    that produces the dependency vectors the EPaxos entry points take as input."""
+    from oracle import fpx_oracle_py as O
+    data = json.load(open(os.path.join(golden_dir, "kv_conflict_index.json")))
+    for t in data["tests"]:
+        ci = O.KvTopOneConflictIndex(t["num_leaders"])
+        for key, kind, keys in t["puts"]:
+            ci.put(tuple(key), kind == "set", keys)
+        for key in t["snapshots"]:
+            ci.put_snapshot(tuple(key))
+        for kind, keys, expect in t["queries"]:
+            assert ci.top_one_conflicts(kind == "set", keys) == expect, (t["name"], kind, keys)
+    # no keys: the snapshots alone (KeyValueStore.scala:261-262)
+    assert ci.top_one_conflicts(False, []) == [0, 0, 0, 21]
