@@ -387,6 +387,71 @@ struct KvTopOneConflictIndex {
   }
 };
 
+// depgraph.TarjanDependencyGraph (S/depgraph/TarjanDependencyGraph.scala:149-451): commit, updateExecuted and
+// executeByComponent -- Tarjan's SCC interlaced with the eligibility DFS (a vertex is executable iff
+// everything it transitively depends on is committed).  Components come out in reverse topological
+// order, each sorted by (sequenceNumber, key) (:441-444).  Keys and sequence numbers are ints, a
+// dependency set is a sorted int list.  The reference walks `vertices` in mutable.Map (hash) order
+// (:343), which only decides the order among INDEPENDENT components and is pinned by no test
+// (T/depgraph/DependencyGraphTest.scala accepts any of them); this restatement walks in ascending key
+// order.  Groundwork for SURVEY 8(f) rank 4.
+struct TarjanDependencyGraph {
+  struct Vertex { int seq; std::vector<int> deps; };
+  struct Meta { int number, low_link, stack_index; bool eligible; };
+  std::map<int, Vertex> vertices;
+  std::set<int> executed;
+  std::map<int, Meta> metas;
+  std::vector<int> stack;
+
+  void commit(int key, int seq, const int* deps, int n) {                       // :259-272
+    if (vertices.count(key) || executed.count(key)) return;
+    Vertex v{seq, std::vector<int>(deps, deps + n)};
+    std::sort(v.deps.begin(), v.deps.end());
+    vertices[key] = v;
+  }
+  void update_executed(const int* keys, int n) {                                // :274-277
+    for (int i = 0; i < n; ++i) { executed.insert(keys[i]); vertices.erase(keys[i]); }
+  }
+  void strong_connect(int v, std::vector<std::vector<int>>& out, std::set<int>& blockers) {   // :372-448
+    int number = (int)metas.size();
+    metas[v] = Meta{number, number, (int)stack.size(), true};
+    stack.push_back(v);
+    for (int w : vertices[v].deps) {                                            // dependencies.materializedDiff(executed)
+      if (executed.count(w)) continue;
+      if (!vertices.count(w)) { metas[v].eligible = false; blockers.insert(w); return; }        // uncommitted child
+      if (!metas.count(w)) {                                                                     // unexplored child
+        strong_connect(w, out, blockers);
+        if (!metas[w].eligible) { metas[v].eligible = false; return; }
+        metas[v].low_link = std::min(metas[v].low_link, metas[w].low_link);
+      } else if (!metas[w].eligible) { metas[v].eligible = false; return; }                     // ineligible child
+      else if (metas[w].stack_index != -1) metas[v].low_link = std::min(metas[v].low_link, metas[w].number);  // on stack
+    }
+    if (metas[v].low_link != metas[v].number) return;                          // not the root of its component
+    std::vector<int> comp(stack.begin() + metas[v].stack_index, stack.end());
+    stack.resize((size_t)metas[v].stack_index);
+    for (int w : comp) metas[w].stack_index = -1;
+    std::sort(comp.begin(), comp.end(), [&](int a, int b) {
+      return std::make_pair(vertices[a].seq, a) < std::make_pair(vertices[b].seq, b);            // :441-444
+    });
+    out.push_back(comp);
+  }
+  // executeByComponent(numBlockers) (:318-337, 339-370); num_blockers < 0 = None
+  std::vector<std::vector<int>> execute_by_component(int num_blockers, std::set<int>* blockers) {
+    metas.clear(); stack.clear();
+    std::vector<std::vector<int>> out;
+    std::vector<int> keys;
+    for (auto& kv : vertices) keys.push_back(kv.first);
+    for (int key : keys) {
+      if (metas.count(key)) continue;
+      strong_connect(key, out, *blockers);
+      if (!metas[key].eligible) stack.clear();                                  // :350-353
+      if (num_blockers >= 0 && (int)blockers->size() >= num_blockers) break;    // :358-363
+    }
+    for (auto& comp : out) for (int k : comp) { vertices.erase(k); executed.insert(k); }
+    return out;
+  }
+};
+
 // util.QuorumWatermark (S/util/QuorumWatermark.scala:31-48)
 struct QuorumWatermark {
   std::vector<int> w;
@@ -1278,6 +1343,26 @@ void fpo_topone_merge(void* a, void* b) { ((TopOne*)a)->merge_equals(*(TopOne*)b
 void fpo_topone_get(void* p, int* out) {
   auto& t = ((TopOne*)p)->top;
   std::copy(t.begin(), t.end(), out);
+}
+void* fpo_dg_new() { return new TarjanDependencyGraph(); }
+void fpo_dg_free(void* p) { delete (TarjanDependencyGraph*)p; }
+void fpo_dg_commit(void* p, int key, int seq, const int* deps, int n) { ((TarjanDependencyGraph*)p)->commit(key, seq, deps, n); }
+void fpo_dg_update_executed(void* p, const int* keys, int n) { ((TarjanDependencyGraph*)p)->update_executed(keys, n); }
+// out: the executed keys, component by component; comp_sizes: one entry per component.  Returns the
+// number of components; *n_blockers / blockers: the uncommitted keys execution is waiting for.
+int fpo_dg_execute_by_component(void* p, int num_blockers, int* out, int* comp_sizes, int cap, int* blockers, int* n_blockers) {
+  std::set<int> bl;
+  auto comps = ((TarjanDependencyGraph*)p)->execute_by_component(num_blockers, &bl);
+  int k = 0, c = 0;
+  for (auto& comp : comps) {
+    if (c < cap) comp_sizes[c] = (int)comp.size();
+    ++c;
+    for (int key : comp) { if (k < cap) out[k] = key; ++k; }
+  }
+  int nb = 0;
+  for (int b : bl) { if (nb < cap) blockers[nb] = b; ++nb; }
+  *n_blockers = nb;
+  return c;
 }
 void* fpo_kvci_new(int num_leaders) { return new KvTopOneConflictIndex(num_leaders); }
 void fpo_kvci_free(void* p) { delete (KvTopOneConflictIndex*)p; }

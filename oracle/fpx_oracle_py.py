@@ -68,6 +68,11 @@ def lib():
         L.fpo_topone_put.argtypes = [vp, i32, i32]
         L.fpo_topone_merge.argtypes = [vp, vp]
         L.fpo_topone_get.argtypes = [vp, ip]
+        L.fpo_dg_new.argtypes = []; L.fpo_dg_new.restype = vp
+        L.fpo_dg_free.argtypes = [vp]
+        L.fpo_dg_commit.argtypes = [vp, i32, i32, ip, i32]
+        L.fpo_dg_update_executed.argtypes = [vp, ip, i32]
+        L.fpo_dg_execute_by_component.argtypes = [vp, i32, ip, ip, i32, ip, ip]; L.fpo_dg_execute_by_component.restype = i32
         L.fpo_kvci_new.argtypes = [i32]; L.fpo_kvci_new.restype = vp
         L.fpo_kvci_free.argtypes = [vp]
         L.fpo_kvci_put.argtypes = [vp, i32, i32, i32, ip, i32]
@@ -550,3 +555,32 @@ class KvTopOneConflictIndex:
         out = (C.c_int * self.n)()
         lib().fpo_kvci_top_one_conflicts(self.h, int(is_set), k, n, out)
         return list(out)
+
+
+class TarjanDependencyGraph:
+    """depgraph.TarjanDependencyGraph over int keys: commit / updateExecuted / executeByComponent."""
+
+    def __init__(self):
+        self.h = lib().fpo_dg_new()
+
+    def __del__(self):
+        try:
+            lib().fpo_dg_free(self.h)
+        except Exception:
+            pass
+
+    def commit(self, key, seq, deps):
+        d, n = _iarr(deps)
+        lib().fpo_dg_commit(self.h, key, seq, d, n)
+
+    def update_executed(self, keys):
+        k, n = _iarr(keys)
+        lib().fpo_dg_update_executed(self.h, k, n)
+
+    def execute_by_component(self, num_blockers=-1, cap=1 << 16):
+        out = (C.c_int * cap)(); sizes = (C.c_int * cap)(); bl = (C.c_int * cap)(); nb = C.c_int(0)
+        nc = lib().fpo_dg_execute_by_component(self.h, num_blockers, out, sizes, cap, bl, C.byref(nb))
+        comps, k = [], 0
+        for c in range(nc):
+            comps.append(list(out[k:k + sizes[c]])); k += sizes[c]
+        return comps, sorted(bl[:nb.value])
