@@ -161,3 +161,49 @@ def test_mencius_shapes_golden():
     buf, offs = O.pack_messages([bytes.fromhex(c["hex"])])
     st, err, kind, rec = O.wire_decode_inbound(O.WIRE_MENCIUS_PROXYLEADER_INBOUND, buf, offs, LG, AG)
     assert st == 0 and kind.tolist() == [1] and bytes(buf[rec[0]["c"]: rec[0]["c"] + rec[0]["d"]]).hex() == "084d"
+
+
+def test_oracle_against_the_protobuf_runtime_on_random_messages():
+    """Beyond the fixed fixture: random messages serialised by Google's Python protobuf runtime (same
+    dynamic descriptors as tests/golden/make_wire_golden.py) decode to the same fields, and the oracle's
+    encoders reproduce the runtime's bytes."""
+    pytest.importorskip("google.protobuf")
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("make_wire_golden",
+                                                  os.path.join(os.path.dirname(__file__), "golden", "make_wire_golden.py"))
+    G = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(G)
+    g = np.random.Generator(np.random.PCG64(2026))
+
+    def r32():
+        return int(g.integers(-(1 << 31), 1 << 31) >> int(g.integers(0, 32)))
+    msgs, exp = [], []
+    for _ in range(300):
+        f = [r32() for _ in range(4)]
+        m = G.cls("ProxyLeaderInbound")(phase2b=G.cls("Phase2b")(group_index=f[0], acceptor_index=f[1], slot=f[2], round=f[3]))
+        msgs.append(m.SerializeToString()); exp.append(tuple(f))
+    buf, offs = O.pack_messages(msgs)
+    st, err, kind, rec = O.wire_decode_inbound(0, buf, offs)
+    assert st == 0 and (kind == 2).all() and rec.tolist() == exp
+    out, eoffs = O.wire_encode_phase2b(np.array(exp, dtype=O.P2B))
+    assert bytes(out) == b"".join(msgs) and np.array_equal(eoffs, offs)
+    # Phase2a with random command batches, Chosen with the same values
+    msgs, exp, vals, chosen = [], [], [], []
+    for k in range(120):
+        v = G.payload(g, int(g.integers(-1, 4)), int(g.integers(0, 300)))
+        sl, rd = r32(), r32()
+        msgs.append(G.cls("AcceptorInbound")(phase2a=G.cls("Phase2a")(slot=sl, round=rd, command_batch_or_noop=v)).SerializeToString())
+        exp.append((sl, rd, v.SerializeToString()))
+        vals.append(v.SerializeToString())
+        chosen.append(G.cls("ReplicaInbound")(chosen=G.cls("Chosen")(slot=sl, command_batch_or_noop=v)).SerializeToString())
+    buf, offs = O.pack_messages(msgs)
+    st, err, kind, rec = O.wire_decode_inbound(1, buf, offs)
+    assert st == 0 and (kind == 2).all()
+    for (sl, rd, pl), r in zip(exp, rec):
+        assert (r["a"], r["b"]) == (sl, rd) and bytes(buf[r["c"]: r["c"] + r["d"]]) == pl
+    arena, voffs = O.pack_messages(vals)
+    st, err, out, eoffs = O.wire_encode_chosen(np.array([(e[0], k) for k, e in enumerate(exp)], dtype=O.CHOSEN), arena, voffs)
+    assert st == 0 and bytes(out) == b"".join(chosen)
+    nacks = [r32() for _ in range(100)]
+    out, eoffs = O.wire_encode_nack(np.array([(0, r) for r in nacks], dtype=O.NACK))
+    assert bytes(out) == b"".join(G.cls("LeaderInbound")(nack=G.cls("Nack")(round=r)).SerializeToString() for r in nacks)
