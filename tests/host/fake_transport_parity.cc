@@ -72,7 +72,9 @@ static Bytes value_of(int slot, int round) {
   return Bytes(v.begin(), v.end());
 }
 
-static std::vector<std::string> run(bool gpu, uint64_t seed, int n_slots) {
+// gpu: the CUDA backend (else the oracle backend); batched: one flush per delivery burst (the product's
+// mode) instead of one per message (the reference's one-handler-per-message behaviour)
+static std::vector<std::string> run(bool gpu, bool batched, uint64_t seed, int n_slots) {
   FakeLogger logger;
   FakeTransport transport(logger);
   Config config;
@@ -128,9 +130,9 @@ static std::vector<std::string> run(bool gpu, uint64_t seed, int n_slots) {
     for (auto& m : burst) {
       transport.messages.insert(transport.messages.begin(), m);
       transport.deliverMessage(0);                 // FakeTransport.deliverMessage (:142-159)
-      if (!gpu) flush_all();                       // reference behaviour: one handler per message
+      if (!batched) flush_all();                   // reference behaviour: one handler per message
     }
-    if (gpu) flush_all();                          // product: one batch per burst
+    if (batched) flush_all();                      // product: one batch per burst
   }
   std::vector<std::string> transcript;
   for (Recorder* r : {&l0, &l1, &r0, &r1}) transcript.insert(transcript.end(), r->log.begin(), r->log.end());
@@ -149,9 +151,12 @@ static std::vector<std::string> run(bool gpu, uint64_t seed, int n_slots) {
 
 int main(int argc, char** argv) {
   int n_slots = argc > 1 ? atoi(argv[1]) : 128;
+  // "cpu": no device needed -- the batching shim itself (buffer a burst, flush once, route the replies)
+  // against per-message handling, both on the oracle backend
+  const bool cpu_only = argc > 2 && std::string(argv[2]) == "cpu";
   int failures = 0;
   for (uint64_t seed = 0; seed < 3; ++seed) {
-    std::vector<std::string> ref = run(false, seed, n_slots), got = run(true, seed, n_slots);
+    std::vector<std::string> ref = run(false, false, seed, n_slots), got = run(!cpu_only, true, seed, n_slots);
     size_t chosen = 0, nacks = 0;
     for (auto& l : ref) { chosen += l.find("Chosen(") != std::string::npos; nacks += l.find("Nack(") != std::string::npos; }
     bool ok = ref == got;

@@ -26,6 +26,16 @@ def test_host_mirror_compiles_and_links():
     assert os.path.exists(build())
 
 
+def test_batching_shim_on_the_oracle_backend():
+    """No GPU: the host logic alone (GpuProxyLeader / GpuAcceptor buffering a delivery burst, one flush,
+    replies routed back in order) against one-handler-per-message, both over the oracle backend --
+    BASELINE cfg1 on FakeTransport with a leader change, three seeds."""
+    r = subprocess.run([build(), "128", "cpu"], capture_output=True, text=True, timeout=600)
+    print(r.stdout, r.stderr)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert r.stdout.count("PARITY OK") == 3
+
+
 @pytest.mark.gpu
 def test_fake_transport_run_cfg1_parity():
     """BASELINE cfg1 (MultiPaxos f=1, 3 acceptors, 128 slots on FakeTransport) with a
