@@ -738,292 +738,8 @@ int fpx_vm_learn_chosen(fpx_engine* e, const fpx_p2b* in, int32_t n, int64_t* er
   return vm_call(e, in, n, nullptr, err_index, 1);
 }
 
-// --------------------------------------------------------------------------- range fills
-
-static int range_call_begin(fpx_engine* e, const void* in, int32_t n, int64_t* err_index, int protocol) {
-  if (err_index) *err_index = -1;
-  if (!e || n < 0 || n > FPX_MAX_RANGE_BATCH || n > e->cfg.max_batch || (n > 0 && !in)) return FPX_ERR_INVALID_ARG;
-  if (e->g.protocol != protocol) return FPX_ERR_UNSUPPORTED;
-  return FPX_OK;
-}
-static int range_call_end(fpx_engine* e, fpx_sync_result* r, int64_t* err_index) {
-  int c = fpx_sync(e, r);
-  if (err_index) *err_index = r->err_index;
-  return c;
-}
-// CTAs along x for strided fills of at most `max_count` elements per record (grid = (x, n))
-static unsigned fill_grid_x(const fpx_engine* e, long long max_count, int32_t n) {
-  long long want = (max_count + 255) / 256;
-  long long cap = std::max(1LL, (long long)e->num_sms * 8 / std::max(1, n));
-  return (unsigned)std::max(1LL, std::min(want, std::max(cap, 1LL)));
-}
-
-int fpx_vm_skip(fpx_engine* e, const fpx_vm_skip_rec* in, int32_t n, int64_t* err_index) {
-  int c = range_call_begin(e, in, n, err_index, FPX_VANILLA_MENCIUS);
-  if (c != FPX_OK || n == 0) return c;
-  CK(e, cudaSetDevice(e->cfg.device));
-  long long mx = 0;
-  for (int32_t i = 0; i < n; ++i) mx = std::max(mx, ((long long)in[i].slot_stop - in[i].slot_start) / e->g.per_group + 1);
-  CK(e, cudaMemcpyAsync(e->d_in, in, (size_t)n * 16, cudaMemcpyHostToDevice, e->stream));
-  VmSkipParams P{e->g, (const int4*)e->d_in, e->votes, e->rows, e->st};
-  vm_skip_kernel<<<dim3(fill_grid_x(e, mx, n), n), 256, 0, e->stream>>>(P);
-  e->launches++;
-  CK(e, cudaGetLastError());
-  fpx_sync_result r;
-  return range_call_end(e, &r, err_index);
-}
-
-int fpx_mencius_arm_range(fpx_engine* e, const fpx_p2a_range* in, int32_t n, int64_t* err_index) {
-  int c = range_call_begin(e, in, n, err_index, FPX_MENCIUS);
-  if (c != FPX_OK || n == 0) return c;
-  CK(e, cudaSetDevice(e->cfg.device));
-  for (int32_t i = 0; i < n; ++i)
-    if (in[i].slot_end == in[i].slot_start + 1) e->unit_ranges = 1;
-  CK(e, cudaMemcpyAsync(e->d_in, in, (size_t)n * 16, cudaMemcpyHostToDevice, e->stream));
-  RangeArmParams P{e->g, PLState{e->rows, e->ovf_keys, e->ovf_rows},
-                   RangeTable{e->rng_tab, (uint32_t)e->rng_cap - 1u, e->rng_cap}, (const int4*)e->d_in, n, e->st};
-  range_arm_kernel<<<(n + 255) / 256, 256, 0, e->stream>>>(P);
-  e->launches++;
-  CK(e, cudaGetLastError());
-  fpx_sync_result r;
-  return range_call_end(e, &r, err_index);
-}
-
-int fpx_mencius_acceptor_noop_range(fpx_engine* e, const fpx_p2a_range* in, int32_t n, fpx_p2b_range* out,
-                                    int32_t* n_out, fpx_nack* out_nack, int32_t* n_nack, int64_t* err_index) {
-  if (n_out) *n_out = 0;
-  if (n_nack) *n_nack = 0;
-  int c = range_call_begin(e, in, n, err_index, FPX_MENCIUS);
-  if (c != FPX_OK || n == 0) return c;
-  if (!out || !n_out || !out_nack || !n_nack) return FPX_ERR_INVALID_ARG;
-  CK(e, cudaSetDevice(e->cfg.device));
-  long long mx = 0;
-  for (int32_t i = 0; i < n; ++i) mx = std::max(mx, ((long long)in[i].slot_end - in[i].slot_start) / e->g.groups + 1);
-  CK(e, cudaMemcpyAsync(e->d_in, in, (size_t)n * 16, cudaMemcpyHostToDevice, e->stream));
-  RangeAcceptorParams P{e->g, (const int4*)e->d_in, n, (int4*)e->d_out_a, (int2*)e->d_out_b, e->rng_dec,
-                        e->acc_round, e->st};
-  range_acceptor_kernel<<<1, kRangeCtaThreads, 0, e->stream>>>(P);
-  RangeFillParams F{e->g, (const int4*)e->d_in, e->rng_dec, e->votes};
-  range_fill_kernel<<<dim3(fill_grid_x(e, mx, n), n), 256, 0, e->stream>>>(F);
-  e->launches += 2;
-  CK(e, cudaGetLastError());
-  fpx_sync_result r;
-  c = range_call_end(e, &r, err_index);
-  if (c != FPX_OK) return c;
-  *n_out = r.n_p2b;
-  *n_nack = r.n_nack;
-  if (r.n_p2b) CK(e, cudaMemcpyAsync(out, e->d_out_a, (size_t)r.n_p2b * 16, cudaMemcpyDeviceToHost, e->stream));
-  if (r.n_nack) CK(e, cudaMemcpyAsync(out_nack, e->d_out_b, (size_t)r.n_nack * 8, cudaMemcpyDeviceToHost, e->stream));
-  CK(e, cudaStreamSynchronize(e->stream));
-  return FPX_OK;
-}
-
-int fpx_mencius_range_phase2b(fpx_engine* e, const fpx_p2b_range* in, int32_t n, fpx_chosen_range* out,
-                              int32_t* n_out, int64_t* err_index) {
-  if (n_out) *n_out = 0;
-  int c = range_call_begin(e, in, n, err_index, FPX_MENCIUS);
-  if (c != FPX_OK || n == 0) return c;
-  if (!out || !n_out) return FPX_ERR_INVALID_ARG;
-  CK(e, cudaSetDevice(e->cfg.device));
-  RangeTable tab{e->rng_tab, (uint32_t)e->rng_cap - 1u, e->rng_cap};
-  if (e->rng_seq_base > 0xffffffffu - (uint32_t)n - 16u) {
-    renormalize_range_stamps_kernel<<<(e->rng_cap + 255) / 256, 256, 0, e->stream>>>(tab);
-    e->launches++;
-    e->rng_seq_base = 1;
-  }
-  CK(e, cudaMemcpyAsync(e->d_in, in, (size_t)n * 16, cudaMemcpyHostToDevice, e->stream));
-  RangeTallyParams P{e->g, PLState{e->rows, e->ovf_keys, e->ovf_rows}, tab, (const int4*)e->d_in, n,
-                     e->rng_seq_base, (int2*)e->d_out_b, e->rng_dec, e->st};
-  e->rng_seq_base += (uint32_t)n;
-  range_tally_kernel<<<1, kRangeCtaThreads, 0, e->stream>>>(P);
-  e->launches++;
-  CK(e, cudaGetLastError());
-  fpx_sync_result r;
-  c = range_call_end(e, &r, err_index);
-  if (c != FPX_OK) return c;
-  *n_out = r.n_chosen;
-  if (r.n_chosen) {
-    CK(e, cudaMemcpyAsync(out, e->d_out_b, (size_t)r.n_chosen * 8, cudaMemcpyDeviceToHost, e->stream));
-    CK(e, cudaStreamSynchronize(e->stream));
-  }
-  return FPX_OK;
-}
-
-int fpx_mencius_replica_chosen_range(fpx_engine* e, const fpx_chosen_range* in, int32_t n, int64_t* err_index) {
-  int c = range_call_begin(e, in, n, err_index, FPX_MENCIUS);
-  if (c != FPX_OK || n == 0) return c;
-  CK(e, cudaSetDevice(e->cfg.device));
-  if (e->rseq_base > 0xffffffffu - (uint32_t)n - 16u) {
-    size_t nl = (size_t)e->g.local_slots;
-    renormalize_rlog_kernel<<<(unsigned)((nl + 255) / 256), 256, 0, e->stream>>>(e->rlog, nl);
-    e->launches++;
-    e->rseq_base = 1;
-  }
-  long long mx = 0;
-  for (int32_t i = 0; i < n; ++i) mx = std::max(mx, ((long long)in[i].slot_end - in[i].slot_start) / e->g.lgroups + 1);
-  CK(e, cudaMemcpyAsync(e->d_in, in, (size_t)n * 8, cudaMemcpyHostToDevice, e->stream));
-  CK(e, cudaMemsetAsync(e->rng_dec, 0x7f, (size_t)n * 4, e->stream));
-  ReplicaRangeParams P{e->g, (const int2*)e->d_in, n, e->rseq_base, e->rlog, e->rng_dec, e->st};
-  e->rseq_base += (uint32_t)n;
-  dim3 grid(fill_grid_x(e, mx, n), n);
-  replica_range_first_kernel<<<grid, 256, 0, e->stream>>>(P);
-  replica_range_fill_kernel<<<grid, 256, 0, e->stream>>>(P);
-  e->launches += 2;
-  CK(e, cudaGetLastError());
-  fpx_sync_result r;
-  return range_call_end(e, &r, err_index);
-}
-
-// --------------------------------------------------------------------------- wire codec
-
-static int wire_reserve(fpx_engine* e, fpx_engine::WireBuf* b, size_t need) {
-  need += 64;                               // the kernels may touch the last partial 16-byte chunk
-  if (b->cap >= need) return FPX_OK;
-  CK(e, cudaStreamSynchronize(e->stream));
-  cudaFree(b->p);
-  b->p = nullptr; b->cap = 0;
-  size_t cap = need + need / 2;
-  CK(e, cudaMalloc(&b->p, cap));
-  b->cap = cap;
-  return FPX_OK;
-}
-static bool aligned16(const void* p) { return ((uintptr_t)p & 15u) == 0; }
-
-int fpx_wire_decode_inbound_dev(fpx_engine* e, int32_t inbound, const uint8_t* d_bytes, const int32_t* d_offsets,
-                                int32_t n, int32_t* d_kind, fpx_wire_rec* d_out) {
-  if (!e || n < 0 || inbound < FPX_WIRE_PROXYLEADER_INBOUND || inbound > FPX_WIRE_MENCIUS_ACCEPTOR_INBOUND)
-    return FPX_ERR_INVALID_ARG;
-  if (inbound >= FPX_WIRE_MENCIUS_PROXYLEADER_INBOUND && e->g.protocol != FPX_MENCIUS) return FPX_ERR_UNSUPPORTED;
-  if (n == 0) return FPX_OK;
-  if (!d_bytes || !d_offsets || !d_kind || !d_out || !aligned16(d_bytes)) return FPX_ERR_INVALID_ARG;
-  WireDecodeParams P{d_bytes, d_offsets, n, inbound, e->g.lgroups, e->g.agroups, d_kind, (int4*)d_out, e->st};
-  wire_decode_kernel<<<(n + kWireDecThreads - 1) / kWireDecThreads, kWireDecThreads, 0, e->stream>>>(P);
-  e->launches++;
-  CK(e, cudaGetLastError());
-  return FPX_OK;
-}
-
-int fpx_wire_decode_inbound(fpx_engine* e, int32_t inbound, const uint8_t* bytes, const int32_t* offsets, int32_t n,
-                            int32_t* kind, fpx_wire_rec* out, int64_t* err_index) {
-  if (err_index) *err_index = -1;
-  if (!e || n < 0 || (n > 0 && (!offsets || !kind || !out))) return FPX_ERR_INVALID_ARG;
-  if (n == 0) return FPX_OK;
-  const int64_t total = offsets[n];
-  if (offsets[0] < 0 || total < offsets[0] || (total > 0 && !bytes)) return FPX_ERR_INVALID_ARG;
-  CK(e, cudaSetDevice(e->cfg.device));
-  int c;
-  if ((c = wire_reserve(e, &e->w_bytes, (size_t)total)) || (c = wire_reserve(e, &e->w_offs, ((size_t)n + 1) * 4)) ||
-      (c = wire_reserve(e, &e->w_kind, (size_t)n * 4)) || (c = wire_reserve(e, &e->w_rec, (size_t)n * 16)))
-    return c;
-  if (total) CK(e, cudaMemcpyAsync(e->w_bytes.p, bytes, (size_t)total, cudaMemcpyHostToDevice, e->stream));
-  CK(e, cudaMemcpyAsync(e->w_offs.p, offsets, ((size_t)n + 1) * 4, cudaMemcpyHostToDevice, e->stream));
-  c = fpx_wire_decode_inbound_dev(e, inbound, (const uint8_t*)e->w_bytes.p, (const int32_t*)e->w_offs.p, n,
-                                  (int32_t*)e->w_kind.p, (fpx_wire_rec*)e->w_rec.p);
-  if (c != FPX_OK) return c;
-  CK(e, cudaMemcpyAsync(kind, e->w_kind.p, (size_t)n * 4, cudaMemcpyDeviceToHost, e->stream));
-  CK(e, cudaMemcpyAsync(out, e->w_rec.p, (size_t)n * 16, cudaMemcpyDeviceToHost, e->stream));
-  fpx_sync_result r;
-  c = fpx_sync(e, &r);
-  if (err_index) *err_index = r.err_index;
-  return c;
-}
-
-}  // extern "C"
-template <int KIND>
-static int wire_encode_launch(fpx_engine* e, const void* d_in, int32_t n, uint8_t* d_out, int32_t out_capacity,
-                              int32_t* d_offs, const uint8_t* d_arena, const int32_t* d_voffs, int32_t num_values) {
-  const int tiles = (n + kWireEncTile - 1) / kWireEncTile;
-  int c = wire_reserve(e, &e->w_tiles, ((size_t)tiles + 2) * 8);
-  if (c != FPX_OK) return c;
-  WireEncodeParams P{d_in, n, d_out, out_capacity, d_offs, (uint32_t*)e->w_tiles.p, d_arena, d_voffs, num_values, e->st};
-  if (KIND == kWireChosen) {
-    wire_size_kernel<KIND><<<tiles, kWireEncThreads, 0, e->stream>>>(P);
-    wire_scan_kernel<<<1, 1024, 0, e->stream>>>((uint32_t*)e->w_tiles.p, tiles, out_capacity, e->st);
-    wire_emit_chosen_kernel<<<tiles, kWireEncThreads, 0, e->stream>>>(P);
-    e->launches += 3;
-  } else {
-    // two passes: bytes per tile, then emit (each CTA sums the tiles before it itself)
-    const size_t smem = 16 + (size_t)kWireEncTile * (KIND == kWireNack ? kWireMaxNack : kWireMaxP2b);
-    wire_size_kernel<KIND><<<tiles, kWireEncThreads, 0, e->stream>>>(P);
-    wire_emit_small_kernel<KIND><<<tiles, kWireEncThreads, smem, e->stream>>>(P, tiles);
-    e->launches += 2;
-  }
-  CK(e, cudaGetLastError());
-  return FPX_OK;
-}
-extern "C" {
-
-int fpx_wire_encode_phase2b_dev(fpx_engine* e, const fpx_p2b* d_in, int32_t n, uint8_t* d_out, int32_t out_capacity,
-                                int32_t* d_offsets) {
-  if (!e || n < 0 || out_capacity < 0) return FPX_ERR_INVALID_ARG;
-  if (n == 0) return FPX_OK;
-  if (!d_in || !d_out || !d_offsets || !aligned16(d_out)) return FPX_ERR_INVALID_ARG;
-  if (e->g.protocol == FPX_MENCIUS)   // S/mencius: Phase2b carries no group index, ProxyLeaderInbound.phase2b = 4
-    return wire_encode_launch<kWireMenciusPhase2b>(e, d_in, n, d_out, out_capacity, d_offsets, nullptr, nullptr, 0);
-  return wire_encode_launch<kWirePhase2b>(e, d_in, n, d_out, out_capacity, d_offsets, nullptr, nullptr, 0);
-}
-
-}  // extern "C"
-// host form of the three encoders: records in, (bytes, offsets) out
-template <int KIND>
-static int wire_encode_host(fpx_engine* e, const void* in, size_t rec_bytes, int32_t n, const uint8_t* arena,
-                            const int32_t* value_offsets, int32_t num_values, uint8_t* out, int32_t out_capacity,
-                            int32_t* offsets, int64_t* err_index) {
-  if (err_index) *err_index = -1;
-  if (!e || n < 0 || out_capacity < 0 || !offsets) return FPX_ERR_INVALID_ARG;
-  if (n == 0) { offsets[0] = 0; return FPX_OK; }
-  if (!in || !out) return FPX_ERR_INVALID_ARG;
-  CK(e, cudaSetDevice(e->cfg.device));
-  int c;
-  if ((c = wire_reserve(e, &e->w_rec, (size_t)n * rec_bytes)) || (c = wire_reserve(e, &e->w_offs, ((size_t)n + 1) * 4)) ||
-      (c = wire_reserve(e, &e->w_out, (size_t)out_capacity)))
-    return c;
-  CK(e, cudaMemcpyAsync(e->w_rec.p, in, (size_t)n * rec_bytes, cudaMemcpyHostToDevice, e->stream));
-  const uint8_t* d_arena = nullptr;
-  const int32_t* d_voffs = nullptr;
-  if (KIND == kWireChosen) {
-    if (num_values < 0 || !value_offsets || value_offsets[0] < 0) return FPX_ERR_INVALID_ARG;
-    const size_t alen = (size_t)value_offsets[num_values];
-    if (alen && !arena) return FPX_ERR_INVALID_ARG;
-    if ((c = wire_reserve(e, &e->w_arena, alen)) || (c = wire_reserve(e, &e->w_voffs, ((size_t)num_values + 1) * 4)))
-      return c;
-    if (alen) CK(e, cudaMemcpyAsync(e->w_arena.p, arena, alen, cudaMemcpyHostToDevice, e->stream));
-    CK(e, cudaMemcpyAsync(e->w_voffs.p, value_offsets, ((size_t)num_values + 1) * 4, cudaMemcpyHostToDevice, e->stream));
-    d_arena = (const uint8_t*)e->w_arena.p;
-    d_voffs = (const int32_t*)e->w_voffs.p;
-  }
-  c = wire_encode_launch<KIND>(e, e->w_rec.p, n, (uint8_t*)e->w_out.p, out_capacity, (int32_t*)e->w_offs.p, d_arena,
-                               d_voffs, num_values);
-  if (c != FPX_OK) return c;
-  CK(e, cudaMemcpyAsync(offsets, e->w_offs.p, ((size_t)n + 1) * 4, cudaMemcpyDeviceToHost, e->stream));
-  fpx_sync_result r;
-  c = fpx_sync(e, &r);
-  if (err_index) *err_index = r.err_index;
-  if (c != FPX_OK) return c;
-  if (offsets[n] > 0) {
-    CK(e, cudaMemcpyAsync(out, e->w_out.p, (size_t)offsets[n], cudaMemcpyDeviceToHost, e->stream));
-    CK(e, cudaStreamSynchronize(e->stream));
-  }
-  return FPX_OK;
-}
-extern "C" {
-
-int fpx_wire_encode_phase2b(fpx_engine* e, const fpx_p2b* in, int32_t n, uint8_t* out, int32_t out_capacity,
-                            int32_t* offsets, int64_t* err_index) {
-  if (e && e->g.protocol == FPX_MENCIUS)
-    return wire_encode_host<kWireMenciusPhase2b>(e, in, 16, n, nullptr, nullptr, 0, out, out_capacity, offsets, err_index);
-  return wire_encode_host<kWirePhase2b>(e, in, 16, n, nullptr, nullptr, 0, out, out_capacity, offsets, err_index);
-}
-int fpx_wire_encode_nack(fpx_engine* e, const fpx_nack* in, int32_t n, uint8_t* out, int32_t out_capacity,
-                         int32_t* offsets, int64_t* err_index) {
-  return wire_encode_host<kWireNack>(e, in, 8, n, nullptr, nullptr, 0, out, out_capacity, offsets, err_index);
-}
-int fpx_wire_encode_chosen(fpx_engine* e, const fpx_chosen* in, int32_t n, const uint8_t* arena,
-                           const int32_t* value_offsets, int32_t num_values, uint8_t* out, int32_t out_capacity,
-                           int32_t* offsets, int64_t* err_index) {
-  return wire_encode_host<kWireChosen>(e, in, 8, n, arena, value_offsets, num_values, out, out_capacity, offsets,
-                                       err_index);
-}
+#include "fpx_engine_ranges.inc"
+#include "fpx_engine_wire.inc"
 
 int fpx_replica_chosen(fpx_engine* e, const fpx_chosen* in, int32_t n, int64_t* err_index) {
   if (err_index) *err_index = -1;
@@ -1154,243 +870,4 @@ int fpx_snapshot_log(fpx_engine* e, int32_t first_slot, int32_t n_slots, int32_t
 
 }  // extern "C"
 
-// --------------------------------------------------------------------------- EPaxos
-
-struct fpx_epaxos {
-  fpx_epaxos_config cfg;
-  EpGeometry g;
-  EpState s;
-  cudaStream_t stream = nullptr;
-  int32_t* d_in = nullptr;
-  int32_t* d_out = nullptr;
-  DevStatus* h_st = nullptr;
-  uint32_t tag = 1;
-  uint32_t seq_base = 1;
-  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
-  std::string last_error;
-};
-
-#define CKE(e, call)                                                             \
-  do {                                                                           \
-    cudaError_t _err = (call);                                                   \
-    if (_err != cudaSuccess) {                                                   \
-      (e)->last_error = std::string(#call) + ": " + cudaGetErrorString(_err);   \
-      fprintf(stderr, "fpx_epaxos: %s\n", (e)->last_error.c_str());            \
-      return FPX_ERR_CUDA;                                                       \
-    }                                                                            \
-  } while (0)
-
-static int ep_finish(fpx_epaxos* e, int64_t* err_index) {
-  CKE(e, cudaMemcpyAsync(e->h_st, e->s.st, sizeof(DevStatus), cudaMemcpyDeviceToHost, e->stream));
-  CKE(e, cudaStreamSynchronize(e->stream));
-  if (err_index) *err_index = -1;
-  if (e->h_st->err_word == ~0ull) return FPX_OK;
-  int status = -(int)(e->h_st->err_word & 0xff);
-  if (err_index) *err_index = (long long)(e->h_st->err_word >> 8);
-  unsigned long long none = ~0ull;
-  CKE(e, cudaMemcpyAsync(&e->s.st->err_word, &none, 8, cudaMemcpyHostToDevice, e->stream));
-  CKE(e, cudaStreamSynchronize(e->stream));
-  return status;
-}
-
-extern "C" {
-
-int fpx_epaxos_create(fpx_epaxos** out, const fpx_epaxos_config* cfg) {
-  if (!out || !cfg || cfg->struct_size != (int32_t)sizeof(fpx_epaxos_config)) return FPX_ERR_INVALID_ARG;
-  *out = nullptr;
-  if (cfg->f < 1) return FPX_ERR_CONFIG;
-  int n = 2 * cfg->f + 1;
-  if (n > kEpMaxN - 1) return FPX_ERR_UNSUPPORTED;
-  if (cfg->replica_index < 0 || cfg->replica_index >= n || cfg->instances_per_replica < 1 || cfg->max_batch < 1)
-    return FPX_ERR_INVALID_ARG;
-  int ndev = 0;
-  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0 || cfg->device < 0 || cfg->device >= ndev)
-    return FPX_ERR_NO_DEVICE;
-  fpx_epaxos* e = new (std::nothrow) fpx_epaxos();
-  if (!e) return FPX_ERR_INVALID_ARG;
-  e->cfg = *cfg;
-  e->g = EpGeometry{cfg->f, n, cfg->replica_index, n - 1, cfg->f + 1, cfg->instances_per_replica};
-  size_t ninst = (size_t)n * cfg->instances_per_replica;
-  size_t mb = (size_t)cfg->max_batch;
-  auto fail = [&](int code) { fpx_epaxos_destroy(e); return code; };
-#define CKC(call) do { if ((call) != cudaSuccess) return fail(FPX_ERR_CUDA); } while (0)
-  CKC(cudaSetDevice(cfg->device));
-  CKC(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
-  CKC(cudaMalloc(&e->s.cmd, ninst * kEpCmdWords * 4));
-  CKC(cudaMalloc(&e->s.lead, ninst * kEpLeadWords * 4));
-  CKC(cudaMalloc(&e->s.claim, ninst * 8));
-  CKC(cudaMalloc(&e->s.count, ninst * 8));
-  CKC(cudaMalloc(&e->s.largest, 16));
-  CKC(cudaMalloc(&e->s.proc_ballot, mb * 8));
-  CKC(cudaMalloc(&e->s.st, sizeof(DevStatus)));
-  CKC(cudaMalloc(&e->d_in, mb * (6 + 2 * kEpMaxN) * 4));
-  CKC(cudaMalloc(&e->d_out, mb * (4 + kEpMaxN) * 4));
-  CKC(cudaMallocHost(&e->h_st, sizeof(DevStatus)));
-  CKC(cudaEventCreate(&e->ev0));
-  CKC(cudaEventCreate(&e->ev1));
-  CKC(cudaMemsetAsync(e->s.cmd, 0, ninst * kEpCmdWords * 4, e->stream));
-  CKC(cudaMemsetAsync(e->s.lead, 0, ninst * kEpLeadWords * 4, e->stream));
-  CKC(cudaMemsetAsync(e->s.claim, 0xff, ninst * 8, e->stream));
-  CKC(cudaMemsetAsync(e->s.count, 0, ninst * 8, e->stream));
-  CKC(cudaMemsetAsync(e->s.largest, 0, 16, e->stream));
-  memset(e->h_st, 0, sizeof(DevStatus));
-  e->h_st->err_word = ~0ull;
-  CKC(cudaMemcpyAsync(e->s.st, e->h_st, sizeof(DevStatus), cudaMemcpyHostToDevice, e->stream));
-  CKC(cudaStreamSynchronize(e->stream));
-#undef CKC
-  *out = e;
-  return FPX_OK;
-}
-
-void fpx_epaxos_destroy(fpx_epaxos* e) {
-  if (!e) return;
-  cudaSetDevice(e->cfg.device);
-  if (e->stream) cudaStreamSynchronize(e->stream);
-  cudaFree(e->s.cmd); cudaFree(e->s.lead); cudaFree(e->s.claim); cudaFree(e->s.count); cudaFree(e->s.largest);
-  cudaFree(e->s.proc_ballot); cudaFree(e->s.st); cudaFree(e->d_in); cudaFree(e->d_out);
-  if (e->h_st) cudaFreeHost(e->h_st);
-  if (e->ev0) cudaEventDestroy(e->ev0);
-  if (e->ev1) cudaEventDestroy(e->ev1);
-  if (e->stream) cudaStreamDestroy(e->stream);
-  delete e;
-}
-
-float fpx_epaxos_last_kernel_ms(fpx_epaxos* e) {
-  float ms = 0.f;
-  if (!e || cudaEventElapsedTime(&ms, e->ev0, e->ev1) != cudaSuccess) return -1.f;
-  return ms;
-}
-
-static int ep_call(fpx_epaxos* e, const int32_t* in, int32_t n_rec, int w_in, int32_t* out, int w_out, int which,
-                   int64_t* err_index) {
-  if (err_index) *err_index = -1;
-  if (!e || n_rec < 0 || n_rec > e->cfg.max_batch || (n_rec > 0 && (!in || (w_out && !out)))) return FPX_ERR_INVALID_ARG;
-  if (n_rec == 0) return FPX_OK;
-  CKE(e, cudaSetDevice(e->cfg.device));
-  CKE(e, cudaMemcpyAsync(e->d_in, in, (size_t)n_rec * w_in * 4, cudaMemcpyHostToDevice, e->stream));
-  EpParams P;
-  P.g = e->g; P.s = e->s; P.in = e->d_in; P.out = e->d_out; P.n_rec = n_rec;
-  P.tag = e->tag++;
-  if (e->tag == 0xffffffffu) e->tag = 1;
-  P.seq_base = e->seq_base;
-  int blocks = (n_rec + 255) / 256;
-  CKE(e, cudaEventRecord(e->ev0, e->stream));
-  switch (which) {
-    case 0: ep_lead_kernel<<<blocks, 256, 0, e->stream>>>(P); break;
-    case 1:
-    case 2:
-      if (which == 1) ep_acceptor_kernel<false><<<blocks, 256, 0, e->stream>>>(P);
-      else ep_acceptor_kernel<true><<<blocks, 256, 0, e->stream>>>(P);
-      ep_nack_fixup_kernel<<<std::min(n_rec, 1024), 256, 0, e->stream>>>(P, w_out);
-      ep_largest_commit_kernel<<<1, 1, 0, e->stream>>>(e->s);
-      break;
-    case 3:
-      if (e->seq_base > 0xffffffffu - (uint32_t)n_rec - 16u) return FPX_ERR_UNSUPPORTED;
-      e->seq_base += (uint32_t)n_rec;
-      ep_response_stamp_kernel<false><<<blocks, 256, 0, e->stream>>>(P);
-      ep_response_decide_kernel<false><<<blocks, 256, 0, e->stream>>>(P);
-      break;
-    default:
-      if (e->seq_base > 0xffffffffu - (uint32_t)n_rec - 16u) return FPX_ERR_UNSUPPORTED;
-      e->seq_base += (uint32_t)n_rec;
-      ep_response_stamp_kernel<true><<<blocks, 256, 0, e->stream>>>(P);
-      ep_response_decide_kernel<true><<<blocks, 256, 0, e->stream>>>(P);
-      break;
-  }
-  CKE(e, cudaEventRecord(e->ev1, e->stream));
-  CKE(e, cudaGetLastError());
-  if (w_out) CKE(e, cudaMemcpyAsync(out, e->d_out, (size_t)n_rec * w_out * 4, cudaMemcpyDeviceToHost, e->stream));
-  return ep_finish(e, err_index);
-}
-
-int fpx_epaxos_lead(fpx_epaxos* e, const int32_t* in, int32_t n_rec, int64_t* err_index) {
-  return ep_call(e, in, n_rec, e ? 8 + e->g.n : 0, nullptr, 0, 0, err_index);
-}
-int fpx_epaxos_preaccept(fpx_epaxos* e, const int32_t* in, int32_t n_rec, int32_t* reply, int64_t* err_index) {
-  return ep_call(e, in, n_rec, e ? 6 + 2 * e->g.n : 0, reply, e ? 4 + e->g.n : 0, 1, err_index);
-}
-int fpx_epaxos_accept(fpx_epaxos* e, const int32_t* in, int32_t n_rec, int32_t* reply, int64_t* err_index) {
-  return ep_call(e, in, n_rec, e ? 6 + e->g.n : 0, reply, e ? 4 + e->g.n : 0, 2, err_index);
-}
-int fpx_epaxos_preacceptok(fpx_epaxos* e, const int32_t* in, int32_t n_rec, int32_t* event, int64_t* err_index) {
-  return ep_call(e, in, n_rec, e ? 6 + e->g.n : 0, event, e ? 2 + e->g.n : 0, 3, err_index);
-}
-int fpx_epaxos_acceptok(fpx_epaxos* e, const int32_t* in, int32_t n_rec, int32_t* event, int64_t* err_index) {
-  return ep_call(e, in, n_rec, 6, event, e ? 2 + e->g.n : 0, 4, err_index);
-}
-
-int fpx_epaxos_entry(fpx_epaxos* e, int32_t rep, int32_t num, int32_t* out, int32_t* leader_kind,
-                     int32_t* largest_ballot) {
-  if (!e || !out || rep < 0 || rep >= e->g.n || num < 0 || num >= e->g.per_replica) return FPX_ERR_INVALID_ARG;
-  CKE(e, cudaSetDevice(e->cfg.device));
-  size_t inst = (size_t)num * e->g.n + rep;
-  int32_t row[kEpCmdWords];
-  CKE(e, cudaMemcpyAsync(row, e->s.cmd + inst * kEpCmdWords, sizeof(row), cudaMemcpyDeviceToHost, e->stream));
-  int32_t lk = 0;
-  CKE(e, cudaMemcpyAsync(&lk, e->s.lead + inst * kEpLeadWords, 4, cudaMemcpyDeviceToHost, e->stream));
-  unsigned long long lb = 0;
-  CKE(e, cudaMemcpyAsync(&lb, e->s.largest, 8, cudaMemcpyDeviceToHost, e->stream));
-  CKE(e, cudaStreamSynchronize(e->stream));
-  out[0] = row[C_KIND]; out[1] = row[C_BORD]; out[2] = row[C_BREP]; out[3] = row[C_VBORD]; out[4] = row[C_VBREP];
-  out[5] = row[C_VALUE]; out[6] = row[C_SEQ];
-  if (row[C_KIND] == EK_NONE) { out[1] = out[2] = out[3] = out[4] = -1; }
-  if (row[C_KIND] == EK_COMMITTED) { out[1] = out[2] = out[3] = out[4] = -1; }
-  for (int k = 0; k < e->g.n; ++k) out[7 + k] = row[C_DEPS + k];
-  if (leader_kind) *leader_kind = lk;
-  if (largest_ballot) {
-    largest_ballot[0] = (int)(uint32_t)(lb >> 32) - 1;
-    largest_ballot[1] = (int)(uint32_t)lb - 1;
-  }
-  return FPX_OK;
-}
-
-int fpx_depset_union_dense_dev(int32_t device, const int32_t* d_in, int32_t n_groups, int32_t sets_per_group,
-                               int32_t n_replicas, int32_t* d_out, void* stream) {
-  if (n_groups < 0 || sets_per_group < 1 || n_replicas < 1 || (n_groups > 0 && (!d_in || !d_out))) return FPX_ERR_INVALID_ARG;
-  if (n_groups == 0) return FPX_OK;
-  if (cudaSetDevice(device) != cudaSuccess) return FPX_ERR_NO_DEVICE;
-  size_t smem = (size_t)kUnionTile * (sets_per_group + 1) * n_replicas * 4;
-  if (smem > 48 * 1024) return FPX_ERR_UNSUPPORTED;   // (R+1)*n <= 48
-  int blocks = (int)std::min<long long>(((long long)n_groups + kUnionTile - 1) / kUnionTile, 148 * 8);
-  depset_union_dense_kernel<<<blocks, kUnionTile, smem, (cudaStream_t)stream>>>(d_in, n_groups, sets_per_group,
-                                                                               n_replicas, d_out);
-  return cudaGetLastError() == cudaSuccess ? FPX_OK : FPX_ERR_CUDA;
-}
-
-int fpx_depset_union(int32_t device, const int32_t* watermark, const int32_t* off, const int32_t* values,
-                     int32_t n_sets, const int32_t* group_off, int32_t n_groups, int32_t* out_watermark,
-                     int32_t* out_count, int32_t* out_values) {
-  if (n_sets < 0 || n_groups < 0 || (n_groups > 0 && (!watermark || !off || !group_off || !out_watermark || !out_count)))
-    return FPX_ERR_INVALID_ARG;
-  if (n_groups == 0) return FPX_OK;
-  int ndev = 0;
-  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0 || device < 0 || device >= ndev) return FPX_ERR_NO_DEVICE;
-  if (cudaSetDevice(device) != cudaSuccess) return FPX_ERR_CUDA;
-  int32_t nv = off[n_sets];
-  if (nv > 0 && (!values || !out_values)) return FPX_ERR_INVALID_ARG;
-  int32_t *d_w = nullptr, *d_off = nullptr, *d_v = nullptr, *d_g = nullptr, *d_ow = nullptr, *d_on = nullptr, *d_ov = nullptr;
-  int rc = FPX_OK;
-#define CKU(call) do { if ((call) != cudaSuccess) { rc = FPX_ERR_CUDA; goto done; } } while (0)
-  CKU(cudaMalloc(&d_w, (size_t)std::max(n_sets, 1) * 4));
-  CKU(cudaMalloc(&d_off, (size_t)(n_sets + 1) * 4));
-  CKU(cudaMalloc(&d_v, (size_t)std::max(nv, 1) * 4));
-  CKU(cudaMalloc(&d_g, (size_t)(n_groups + 1) * 4));
-  CKU(cudaMalloc(&d_ow, (size_t)n_groups * 4));
-  CKU(cudaMalloc(&d_on, (size_t)n_groups * 4));
-  CKU(cudaMalloc(&d_ov, (size_t)std::max(nv, 1) * 4));
-  CKU(cudaMemcpy(d_w, watermark, (size_t)n_sets * 4, cudaMemcpyHostToDevice));
-  CKU(cudaMemcpy(d_off, off, (size_t)(n_sets + 1) * 4, cudaMemcpyHostToDevice));
-  if (nv) CKU(cudaMemcpy(d_v, values, (size_t)nv * 4, cudaMemcpyHostToDevice));
-  CKU(cudaMemcpy(d_g, group_off, (size_t)(n_groups + 1) * 4, cudaMemcpyHostToDevice));
-  depset_union_kernel<<<(n_groups + 127) / 128, 128>>>(d_w, d_off, d_v, d_g, n_groups, d_ow, d_on, d_ov);
-  CKU(cudaGetLastError());
-  CKU(cudaMemcpy(out_watermark, d_ow, (size_t)n_groups * 4, cudaMemcpyDeviceToHost));
-  CKU(cudaMemcpy(out_count, d_on, (size_t)n_groups * 4, cudaMemcpyDeviceToHost));
-  if (nv) CKU(cudaMemcpy(out_values, d_ov, (size_t)nv * 4, cudaMemcpyDeviceToHost));
-#undef CKU
-done:
-  cudaFree(d_w); cudaFree(d_off); cudaFree(d_v); cudaFree(d_g); cudaFree(d_ow); cudaFree(d_on); cudaFree(d_ov);
-  return rc;
-}
-
-}  // extern "C"
+#include "fpx_engine_epaxos.inc"

@@ -25,6 +25,6 @@ def test_product_paths_never_import_the_oracle():
     pkg = os.path.join(ROOT, "frankenpaxos_b200")
     for dirpath, _, files in os.walk(pkg):
         for f in files:
-            if f.endswith((".py", ".cu", ".cuh", ".c", ".h", ".hpp")):
+            if f.endswith((".py", ".cu", ".cuh", ".inc", ".c", ".h", ".hpp")):
                 text = open(os.path.join(dirpath, f), errors="ignore").read()
                 assert "fpx_oracle" not in text and "from oracle" not in text and "import oracle" not in text, f
