@@ -48,8 +48,8 @@ def lib():
     global _lib
     if _lib is not None:
         return _lib
-    path = _build.LIB
-    if not os.path.exists(path) or (_build.stale() and _build.have_nvcc()):
+    path = os.environ.get("FPX_LIB_OVERRIDE") or _build.LIB      # override: A/B against another build (profiles/)
+    if path == _build.LIB and (not os.path.exists(path) or (_build.stale() and _build.have_nvcc())):
         path = _build.build(force=True)
     L = C.CDLL(path)
     missing = [s for s in SYMBOLS if not hasattr(L, s)]
@@ -107,6 +107,9 @@ def lib():
     L.fpx_set_coop_ctas_per_sm.argtypes = [vp, i32]; L.fpx_set_coop_ctas_per_sm.restype = i32
     L.fpx_stream.argtypes = [vp]; L.fpx_stream.restype = vp
     L.fpx_launch_count.argtypes = [vp]; L.fpx_launch_count.restype = i64
+    if hasattr(L, "fpx_debug_set_tally_path"):
+        L.fpx_debug_set_tally_path.argtypes = [vp, i32]; L.fpx_debug_set_tally_path.restype = i32
+        L.fpx_debug_last_tally_path.argtypes = [vp]; L.fpx_debug_last_tally_path.restype = i32
     if L.fpx_abi_version() != 1:
         raise ImportError("libfpx.so ABI version mismatch")
     _lib = L

@@ -41,9 +41,9 @@ struct AcceptorParams {
   uint32_t* accept_bits;           // ceil(n/32)
   int32_t* g_agg;                  // [grid][kMaxKeys] per-CTA max round per acceptor
   uint32_t* g_wacc;                // [grid*kWarps] accepted records per warp range
-  uint32_t bar_base;               // st->barrier when this launch starts
   uint32_t parity;                 // which nack counter this launch uses
   int32_t append;                  // 1: continue the reply streams of the previous launch (chunked host call)
+  int32_t demote;                  // pass 2 re-reads the stream with evict_first: it is dead afterwards
   DevStatus* st;
   VoteConflict* conflicts;
 };
@@ -93,7 +93,7 @@ __device__ __forceinline__ void acceptor_apply(const AcceptorParams& P, int4* ou
 #pragma unroll
     for (int u = 0; u < kAccUnroll; ++u) {
       int i = base + u * 32 + lane;
-      rec[u] = (i < whi) ? ld_cg(P.in + i) : make_int4(0, -1, 0, -1);
+      rec[u] = (i < whi) ? (P.demote && !kExact ? ld_hint(P.in + i, pol_out) : ld_cg(P.in + i)) : make_int4(0, -1, 0, -1);
       cell[u] = 0; old[u] = 0;
     }
 #pragma unroll
@@ -252,7 +252,7 @@ __global__ void __launch_bounds__(kThreads) acceptor_phase2a_kernel(AcceptorPara
     __stcg(&P.g_agg[blockIdx.x * kMaxKeys + lane], cta_agg);
   }
   FPX_MARK(P.st->t_acceptor, 1);
-  grid_barrier(&P.st->barrier, P.bar_base + gridDim.x);
+  grid_sync(P.st);
   FPX_MARK(P.st->t_acceptor, 2);
 
   // ---- carry-in: acceptor rounds at batch start + every CTA before this one.
@@ -290,7 +290,7 @@ __global__ void __launch_bounds__(kThreads) acceptor_phase2a_kernel(AcceptorPara
     if (lane == 0 && m != INT_MIN) atomicMax(&P.acc_max_voted[k], m);
   }
   FPX_MARK(P.st->t_acceptor, 4);
-  grid_barrier(&P.st->barrier, P.bar_base + 2 * gridDim.x);
+  grid_sync(P.st);
   FPX_MARK(P.st->t_acceptor, 5);
 
   // round after the batch = max over everything (:204); only now is it safe to

@@ -36,6 +36,7 @@ constexpr int kWarps = kThreads / 32;
 constexpr int kMaxKeys = FPX_MAX_ACCEPTORS;       // acceptors tracked by the round scan (lane = key)
 constexpr int kMaxConflicts = 1024;
 constexpr int kMaxGrid = 148 * 8;                 // upper bound on CTAs of a cooperative launch
+constexpr uint32_t kTsBadVoter = 1u, kTsAnomaly = 2u, kTsPoison = 4u;  // DevStatus::ts_flags
 
 // Device-resident status block (one per engine).
 struct DevStatus {
@@ -46,10 +47,16 @@ struct DevStatus {
   int32_t wm_local;             // replica: first local index not yet chosen
   int32_t max_chosen_local;     // replica: largest local index ever chosen
   int32_t wm_found;             // scratch of the watermark scan
-  uint32_t barrier;             // monotone arrival counter of the grid barriers
+  uint32_t bar_count;           // grid barrier: CTAs arrived at the running barrier (self-resetting)
   uint32_t nack_total;          // acceptor kernel: Nacks of the running call
   uint32_t pad[2];              // [0] second Nack counter (parity), [1] tally: a vote hit a poisoned row
-  int32_t max_armed_local;      // largest local slot ever armed (prefetch window of the tally)
+  int32_t max_armed_local;      // largest local slot ever armed
+  uint32_t bar_gen;             // grid barrier: generation, bumped by the last CTA to arrive
+  // tally: statistics of the running batch (phase A), reset by CTA 0 before the kernel ends
+  int32_t ts_min_local, ts_max_local;   // window of local slots the batch's votes touch
+  int32_t ts_min_round, ts_max_round;   // rounds carried by the batch's votes
+  uint32_t ts_flags;                    // kTsBadVoter | kTsAnomaly
+  uint32_t ts_path;                     // path the LAST tally launch took: 1 sweep, 2 exact (diagnostic)
   unsigned long long t_acceptor[8];  // %globaltimer at the phase boundaries of CTA 0 (profiling aid)
   unsigned long long t_tally[8];
 };
@@ -106,6 +113,11 @@ __device__ __forceinline__ unsigned long long l2_policy_evict_last() {
   asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
   return pol;
 }
+__device__ __forceinline__ unsigned long long l2_policy_evict_normal() {
+  unsigned long long pol;
+  asm volatile("createpolicy.fractional.L2::evict_normal.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
 __device__ __forceinline__ unsigned long long l2_policy_evict_first() {
   unsigned long long pol;
   asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
@@ -122,6 +134,28 @@ __device__ __forceinline__ int4 ld_keep(const int4* p, unsigned long long pol) {
                : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
                : "l"(p), "l"(pol));
   return r;
+}
+__device__ __forceinline__ int4 ld_hint(const int4* p, unsigned long long pol) {
+  int4 r;
+  asm volatile("ld.global.L1::no_allocate.L2::cache_hint.v4.s32 {%0,%1,%2,%3}, [%4], %5;"
+               : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+               : "l"(p), "l"(pol));
+  return r;
+}
+// Reductions WITHOUT a return value.  atomicMin/atomicMax/atomicOr whose result is unused compile to
+// ATOMG with the destination discarded (RZ), which still holds a scoreboard slot and a return packet;
+// `red` is the fire-and-forget form (REDG).
+__device__ __forceinline__ void red_min_u32(uint32_t* p, uint32_t v) {
+  asm volatile("red.global.min.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ void red_or_u32(uint32_t* p, uint32_t v) {
+  asm volatile("red.global.or.b32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ void red_min_u64(unsigned long long* p, unsigned long long v) {
+  asm volatile("red.global.min.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ void red_max_u64(unsigned long long* p, unsigned long long v) {
+  asm volatile("red.global.max.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
 __device__ __forceinline__ void st_stream(int4* p, int4 v) {
   asm volatile("st.global.L1::no_allocate.v4.s32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(v.x), "r"(v.y),
@@ -243,18 +277,26 @@ __device__ __forceinline__ RowRef find_row(const Geometry& g, const PLState& s, 
 }
 
 // ---------------------------------------------------------------------------
-// Grid barrier for cooperative (co-resident) launches.  `st->barrier` only ever
-// grows; the host passes the value it will have when every CTA has arrived.
+// Grid barrier for cooperative (co-resident) launches: arrival counter + generation.
+// The last CTA to arrive resets the counter and bumps the generation, so the barrier
+// needs no per-launch bookkeeping on the host (any number of barriers per launch,
+// data-dependent paths included, as long as every CTA takes the same path).
 // ---------------------------------------------------------------------------
-__device__ __forceinline__ void grid_barrier(uint32_t* bar, uint32_t target) {
+__device__ __forceinline__ void grid_sync(DevStatus* st) {
   __syncthreads();
   if (threadIdx.x == 0) {
+    uint32_t gen, v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(gen) : "l"(&st->bar_gen) : "memory");
     __threadfence();
-    asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(bar) : "memory");
-    uint32_t v;
-    do {
-      asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(bar) : "memory");
-    } while ((int32_t)(v - target) < 0);
+    if (atomicAdd(&st->bar_count, 1u) == gridDim.x - 1) {
+      st->bar_count = 0;
+      __threadfence();
+      asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(&st->bar_gen) : "memory");
+    } else {
+      do {
+        asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(&st->bar_gen) : "memory");
+      } while (v == gen);
+    }
     __threadfence();
   }
   __syncthreads();

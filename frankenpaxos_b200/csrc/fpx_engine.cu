@@ -61,7 +61,10 @@ struct fpx_engine {
   uint32_t* bits = nullptr;            // accept / win bitmask, max_batch/32 words
   int32_t* g_agg = nullptr;            // [kMaxGrid][kMaxKeys] acceptor kernel CTA aggregates
   uint32_t* g_wacc = nullptr;          // [kMaxGrid*kWarps] accepted per warp range
-  uint32_t* g_ccnt = nullptr;          // [kMaxGrid] Chosen per CTA
+  uint2* t_bw = nullptr;               // tally: completing-vote bitmap of the running batch + per-word prefix
+  uint32_t* t_cc = nullptr;            // tally: completing votes per 1024-vote chunk
+  void* t_tmp = nullptr;               // tally: Chosen records parked at their vote's index (max_batch * 8)
+  int tally_path = 0;                  // 0 auto, 2 force the exact per-vote path
   void* conflicts = nullptr;           // kMaxConflicts * 8 bytes
   // staging for host-pointer calls
   void* d_in = nullptr;                // max_batch * 16
@@ -69,12 +72,11 @@ struct fpx_engine {
   void* d_out_b = nullptr;             // max_batch * 8  (nack / chosen)
   DevStatus* h_st = nullptr;           // pinned mirror
   // host bookkeeping
-  uint32_t bar = 0;                    // value of st->barrier when the next launch starts
   uint32_t parity = 0;                 // nack counter the next acceptor launch uses
   int grid_acceptor = 0;               // co-resident CTAs of the cooperative kernels
   int grid_tally = 0;
   int occ_acceptor = 0, occ_tally = 0; // resident CTAs per SM each kernel could have alone
-  int tally_per_cap = 0;               // max records per warp range (shared-memory buffer)
+  int tally_max_sub = 0;               // votes one tally launch takes (shared-memory scan of the chunk counts)
   int num_sms = 0;
   uint32_t seq_base = 1;               // Phase2b delivery sequence numbers
   uint32_t rseq_base = 1;              // Chosen delivery sequence numbers
@@ -157,11 +159,12 @@ static int reset_state(fpx_engine* e) {
   init.max_chosen_local = -1;
   init.max_armed_local = -1;
   init.wm_found = INT_MAX;
+  init.ts_min_local = INT_MAX; init.ts_max_local = -1;
+  init.ts_min_round = INT_MAX; init.ts_max_round = INT_MIN;
   init.watermark = g.shard_index;
   *e->h_st = init;
   CK(e, cudaMemcpyAsync(e->st, e->h_st, sizeof(DevStatus), cudaMemcpyHostToDevice, e->stream));
   CK(e, cudaStreamSynchronize(e->stream));
-  e->bar = 0;
   e->parity = 0;
   e->seq_base = 1;
   e->rseq_base = 1;
@@ -267,7 +270,9 @@ int fpx_create(fpx_engine** out, const fpx_config* cfg) {
   CKC(cudaMalloc(&e->bits, (mb / 32 + 2) * 4));
   CKC(cudaMalloc(&e->g_agg, (size_t)kMaxGrid * kMaxKeys * 4));
   CKC(cudaMalloc(&e->g_wacc, (size_t)kMaxGrid * kWarps * 4));
-  CKC(cudaMalloc(&e->g_ccnt, (size_t)kMaxGrid * 4));
+  CKC(cudaMalloc(&e->t_bw, (mb / kChunkVotes + 2) * 32 * 8));
+  CKC(cudaMalloc(&e->t_cc, (mb / kChunkVotes + 2) * 4));
+  CKC(cudaMalloc(&e->t_tmp, (mb + kChunkVotes) * 8));   // padded to a whole chunk: phase D loads unconditionally
   {
     // cooperative (co-resident) grids: SMs x resident CTAs per SM
     cudaDeviceProp prop;
@@ -279,10 +284,11 @@ int fpx_create(fpx_engine** out, const fpx_config* cfg) {
                                                       (size_t)g.num_keys * kThreads * 4));
     e->occ_acceptor = std::max(occ, 1);
     e->grid_acceptor = std::min(std::max(occ, 1) * e->num_sms, kMaxGrid);
-    const int smem_cap = 55 * 1024;  // Chosen buffer: kWarps * per * 8 bytes; 4 CTAs x (55 + 1 reserved) KB fit one SM
-    e->tally_per_cap = (smem_cap / (kWarps * 8)) & ~31;   // warp ranges are rounded up to 32 records: stay within smem_cap
+    // the tally's dynamic shared memory: scan of the per-chunk counts (4 B per 1024 votes) + the CTA's kept
+    // {vote, value} entries of the sweep (8 B per window row); one launch takes at most 40 KB of it for the scan
+    const int smem_cap = 48 * 1024;
+    e->tally_max_sub = (40 * 1024 / 4) * kChunkVotes;
     const void* tk = tally_kernel_ptr(g.row_words);
-    CKC(cudaFuncSetAttribute(tk, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_cap));
     CKC(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, tk, kThreads, smem_cap));
     e->occ_tally = std::max(occ, 1);
     e->grid_tally = std::min(std::max(occ, 1) * e->num_sms, kMaxGrid);
@@ -295,6 +301,8 @@ int fpx_create(fpx_engine** out, const fpx_config* cfg) {
 #undef CKC
   int r = reset_state(e);
   if (r != FPX_OK) { fprintf(stderr, "fpx_create: %s\n", e->last_error.c_str()); return fail(r); }
+  // test / A-B knob: FPX_TALLY_PATH=exact makes every tally launch take the per-vote path
+  if (const char* tp = getenv("FPX_TALLY_PATH")) e->tally_path = strcmp(tp, "exact") == 0 ? 2 : 0;
   *out = e;
   return FPX_OK;
 }
@@ -313,7 +321,7 @@ void fpx_destroy(fpx_engine* e) {
   for (fpx_engine::WireBuf* b : {&e->w_bytes, &e->w_offs, &e->w_kind, &e->w_rec, &e->w_out, &e->w_tiles, &e->w_arena,
                                  &e->w_voffs})
     cudaFree(b->p);
-  cudaFree(e->bits); cudaFree(e->g_agg); cudaFree(e->g_wacc); cudaFree(e->g_ccnt); cudaFree(e->conflicts);
+  cudaFree(e->bits); cudaFree(e->g_agg); cudaFree(e->g_wacc); cudaFree(e->t_bw); cudaFree(e->t_cc); cudaFree(e->t_tmp); cudaFree(e->conflicts);
   cudaFree(e->d_in); cudaFree(e->d_out_a); cudaFree(e->d_out_b);
   if (e->h_st) cudaFreeHost(e->h_st);
   for (int i = 0; i < kMaxEvents; ++i) if (e->ev[i]) cudaEventDestroy(e->ev[i]);
@@ -350,6 +358,20 @@ int fpx_debug_phase_times(fpx_engine* e, unsigned long long* acceptor8, unsigned
   return FPX_OK;
 }
 int64_t fpx_launch_count(const fpx_engine* e) { return e ? e->launches : 0; }
+// Undocumented test/profiling aids: force the tally's exact per-vote path (path = 2; 0 = automatic), and
+// which path the last tally launch took (1 sweep, 2 exact).
+int fpx_debug_set_tally_path(fpx_engine* e, int32_t path) {
+  if (!e || (path & ~0x7e)) return FPX_ERR_INVALID_ARG;
+  e->tally_path = path;
+  return FPX_OK;
+}
+int fpx_debug_last_tally_path(fpx_engine* e) {
+  if (!e) return FPX_ERR_INVALID_ARG;
+  uint32_t v = 0;
+  CK(e, cudaStreamSynchronize(e->stream));
+  CK(e, cudaMemcpy(&v, &e->st->ts_path, 4, cudaMemcpyDeviceToHost));
+  return (int)v;
+}
 
 // --------------------------------------------------------------------------- device entry points
 
@@ -418,10 +440,9 @@ static int acceptor_launch(fpx_engine* e, const fpx_p2a* d_in, int32_t n, fpx_p2
   P.st = e->st;
   P.conflicts = (VoteConflict*)e->conflicts;
   int grid = std::max(1, std::min(e->grid_acceptor, (n + kThreads - 1) / kThreads));
-  P.bar_base = e->bar;
   P.parity = e->parity;
   P.append = append;
-  e->bar += 2u * (uint32_t)grid;
+  P.demote = (e->tally_path & 64) ? 1 : 0;
   e->parity ^= 1u;
   void* args[] = {&P};
   CK(e, cudaLaunchCooperativeKernel((const void*)acceptor_phase2a_kernel, dim3(grid), dim3(kThreads), args,
@@ -449,13 +470,10 @@ int fpx_proxyleader_phase2b_dev(fpx_engine* e, const fpx_p2b* d_in, int32_t n, f
     e->launches += 2;
     e->seq_base = 1;
   }
-  const int grid_cap = e->grid_tally;
-  const int max_sub = grid_cap * kWarps * e->tally_per_cap;  // records one launch can buffer
   const void* tk = tally_kernel_ptr(e->g.row_words);
   for (int32_t done = 0; done < n;) {
-    int32_t sub = std::min(n - done, max_sub);
-    int grid = std::max(1, std::min(grid_cap, (sub + kThreads - 1) / kThreads));
-    int per = (((sub + grid * kWarps - 1) / (grid * kWarps)) + 31) & ~31;
+    int32_t sub = std::min(n - done, e->tally_max_sub);
+    int grid = std::max(1, std::min(e->grid_tally, (sub + kThreads - 1) / kThreads));
     TallyParams P;
     P.g = e->g;
     P.pl = PLState{e->rows, e->ovf_keys, e->ovf_rows};
@@ -463,16 +481,19 @@ int fpx_proxyleader_phase2b_dev(fpx_engine* e, const fpx_p2b* d_in, int32_t n, f
     P.n = sub;
     P.seq_base = e->seq_base;
     P.out_chosen = (int2*)d_out;
-    P.g_ccnt = e->g_ccnt;
-    P.bar_base = e->bar;
+    P.bw = e->t_bw;
+    P.cc = e->t_cc;
+    P.tmp = (int2*)e->t_tmp;
     P.first = done == 0;
-    P.per = per;
+    P.path = e->tally_path;
     P.votes = e->votes;
     P.st = e->st;
-    e->bar += 4u * (uint32_t)grid;
     e->seq_base += (uint32_t)sub;
     void* args[] = {&P};
-    CK(e, cudaLaunchCooperativeKernel(tk, dim3(grid), dim3(kThreads), args, (size_t)kWarps * per * 8, e->stream));
+    const int nchunks = (sub + kChunkVotes - 1) / kChunkVotes;
+    const size_t smem = 48 * 1024;
+    P.keep_cap = (int)((smem - (size_t)((nchunks + 1) & ~1) * 4) / 8);
+    CK(e, cudaLaunchCooperativeKernel(tk, dim3(grid), dim3(kThreads), args, smem, e->stream));
     e->launches++;
     done += sub;
   }

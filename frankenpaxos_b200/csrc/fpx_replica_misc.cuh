@@ -53,7 +53,7 @@ __global__ void __launch_bounds__(256) replica_chosen_kernel(ReplicaParams P) {
       int local = local_slot(g, rec[u].x);
       if (local < 0) { report_error(P.st, FPX_ERR_SLOT_RANGE, i); continue; }
       // first Chosen per slot wins (Replica.scala:580-588): min over (delivery seq : value)
-      atomicMin(&P.rlog[local], ((unsigned long long)(P.seq_base + (uint32_t)i) << 32) | (uint32_t)rec[u].y);
+      red_min_u64(&P.rlog[local], ((unsigned long long)(P.seq_base + (uint32_t)i) << 32) | (uint32_t)rec[u].y);
       mx = max(mx, local);
     }
   }

@@ -5,38 +5,51 @@
 //   that makes the test pass sends Chosen (:246-253) and flips the key to Done
 //   (:256); later votes see Done (:227-232).  Which vote completes depends on
 //   delivery order, and the order of Chosen records in the output is the order
-//   of their completing votes.  One persistent cooperative kernel, every warp
-//   owns a contiguous range of the delivery stream, no sort:
-//     phase A  stamp[slot][voter] = min(stamp, seq_i)         one RED per record
-//     barrier
-//     phase B  record i is the completing vote of its key iff it is the first
-//              delivery of its voter (stamp == seq_i), the voters with
-//              stamp < seq_i are NOT a quorum, and with voter i they ARE.  The
-//              warp appends its completing records, in order, to its slice of a
-//              shared-memory buffer;
-//     barrier  CTA counts -> global, each CTA sums the CTAs before it
-//     phase C  coalesced copy of the buffered Chosen records to their exact
-//              positions: the output is the Chosen stream in delivery order.
-//   seq_i = seq_base + i is a per-engine running sequence number, so first
-//   deliveries of earlier batches order before this batch.  `Done` (:256) is not
-//   stored: a key is Done at delivery i iff the stamps below seq_i already form
-//   a quorum, which is exactly what phase B evaluates (later votes of a Done key
-//   only add larger stamps, which never change that).
+//   of their completing votes.
 //
-//   Cost model (measured, profiles/): the Phase2b stream is shuffled, so every
-//   row access is a fully divergent warp access = one L1TEX wavefront per lane
-//   PER INSTRUCTION (~23 us per divergent instruction per 3*2^20 votes).  A row
-//   {round, value, stamp[voters]} is ONE 32-byte sector for <= 6 voters, read
-//   with one 256-bit load; and phase A stamps BLINDLY -- without loading the
-//   row's header to check the round -- which is sound because a slot whose
-//   primary row is in normal state has exactly ONE armed round: arming a second
-//   round of a slot (leader change) moves the first one to the (slot, round) table
-//   and poisons the primary row (fpx_arm.cuh), after which the row's stamps are
-//   never read again.  Phase B reads the header anyway; a vote that finds a poisoned
-//   header is stamped into its table entry there, and if any vote did, all warps
-//   redo phase B after the barrier (leader-change batches only).  Vanilla Mencius
-//   ignores stale-round votes instead of failing on them, so it keeps the checked
-//   (header-loading) phase A.
+//   Every vote gets a sequence number seq_i = seq_base + i (per-engine running
+//   counter); a row keeps, per voter, the SMALLEST seq that voter was delivered
+//   with (its first delivery).  With those stamps the completing vote of a key has
+//   a closed form that needs no per-vote evaluation:
+//       non-flexible (:238)   c(key) = the (f+1)-th smallest stamp of the row
+//       flexible grid (:241)  c(key) = max over grid rows of (min stamp in the row)
+//   (the first moment `phase2bs.size >= f+1` / `isWriteQuorum(phase2bs.keys)` holds).
+//   The key emits Chosen in THIS batch iff seq_base <= c(key) < seq_base + n, and
+//   the Chosen stream is the keys ordered by c.
+//
+//   One persistent cooperative kernel, no sort:
+//     phase A  stamp[slot][voter] = min(stamp, seq_i): one blind RED per vote, no
+//              row load; per-batch statistics (slot window, rounds) on the side
+//     barrier
+//     phase B  SWEEP (steady state): the window's rows are read once, coalesced
+//              (one 256-bit load per row, every CTA a contiguous run of rows),
+//              c(key) evaluated per row; a key completed by vote i of this batch sets
+//              bit i of a bitmap and keeps {i, value} in the CTA's shared memory;
+//           or EXACT (fallback): one divergent row load per vote and the reference's
+//              test evaluated at that vote ("first delivery of its voter, not a
+//              quorum before, a quorum with it"); a completing vote sets bit i and
+//              parks its Chosen record at tmp[i]
+//     barrier
+//     phase C  per 1024-vote chunk: completing votes before each bitmap word, chunk total
+//     barrier
+//     phase D  rank(i) = number of completing votes before i = chunk prefix + word
+//              prefix + popcount below bit i.  SWEEP: every kept {i, value} goes
+//              straight to out[rank(i)] (a window too large for shared memory is swept
+//              a second time instead).  EXACT: ordered compaction of tmp[].
+//
+//   When is the sweep sound?  It never looks at a vote, so every property of a vote
+//   that the reference checks must be implied by the batch statistics and the rows:
+//   (1) all votes of the batch carry ONE round R and every armed row of the window
+//   holds exactly that round (else a vote of another round -- which is
+//   `logger.fatal`, :220-225, or belongs to a second live round of the slot -- could
+//   hide behind an older stamp of its voter), (2) no poisoned row (several live
+//   rounds, see fpx_arm.cuh) lies in the window, (3) no touched row is unarmed,
+//   (4) every voter is a member of the slot's quorum system, (5) the window is not
+//   much larger than the batch.  Any violation flips the WHOLE batch to the exact
+//   path, which also produces the reference's error index.  Blind stamping is sound
+//   for the same reason as before: a primary row in normal state has exactly ONE
+//   armed round.  Vanilla Mencius (stale votes are ignored, not fatal) always takes
+//   the exact path with the checked phase A.
 #pragma once
 #include "fpx_common.cuh"
 
@@ -49,15 +62,19 @@ struct TallyParams {
   int32_t n;
   uint32_t seq_base;
   int2* out_chosen;
-  uint32_t* g_ccnt;        // [grid] Chosen records produced per CTA
-  uint32_t bar_base;
-  int32_t first;           // 1: first launch of a call (output offset 0), else append at st->n_chosen
-  int32_t per;             // records per warp range == shared buffer entries per warp
+  uint2* bw;               // [ceil(n/1024)*32] {x: bit i = vote i completes its key, y: completing votes before the word, in its chunk}
+  uint32_t* cc;            // [ceil(n/1024)]    completing votes per 1024-vote chunk
+  int2* tmp;               // [n] exact path: Chosen record of completing vote i, parked at i
+  int32_t first;           // 1: output offset 0, else append at st->n_chosen (sub-launches of one call)
+  int32_t path;            // 0: sweep when sound; 2: always the exact per-vote path (tests, A/B); 4: profiling, no REDs
+  int32_t keep_cap;        // rows of the window one CTA can keep in shared memory between phases B and D
   unsigned long long* votes;  // vanilla Mencius: the coordinator's log entry turns ChosenEntry on completion
   DevStatus* st;
 };
 
-constexpr int kTallyUnroll = 4;  // chunks in flight per warp (phase B: 32 / ROWW)
+constexpr int kTallyUnroll = 4;   // chunks of 32 votes per warp per pipeline stage in phase A
+constexpr int kChunkVotes = 1024; // votes per rank chunk (one bitmap word per lane)
+constexpr uint32_t kNoVote = 0xffffffffu;
 
 // One proxy-leader row from L2 with a single 256-bit load per 8 words (LDG.E.256, sm_100+).
 template <int ROWW>
@@ -71,17 +88,111 @@ __device__ __forceinline__ void load_row(const uint32_t* p, uint32_t (&w)[ROWW])
   }
 }
 
-// Phase B over the warp's range.  kRedo = false: first evaluation; a vote whose slot
-// is poisoned is stamped into its table entry and the any_slow flag is raised.
-// kRedo = true: everything is evaluated, poisoned slots against their (now fully
-// stamped) table entry.
+// ---------------------------------------------------------------------------
+// sweep: the completing vote of one row of the window.  Returns false on an anomaly;
+// *vote = index (in this batch) of the vote that completes the key, or kNoVote.
+// ---------------------------------------------------------------------------
+template <int ROWW>
+__device__ __forceinline__ bool row_completion(const TallyParams& P, const uint32_t (&w)[ROWW], int R, uint32_t* vote) {
+  const Geometry& g = P.g;
+  const uint32_t hw = w[0];
+  *vote = kNoVote;
+  bool touched = false;
+#pragma unroll
+  for (int v = 0; v < ROWW - 2; ++v)
+    if (v < g.voters) touched |= (w[2 + v] - P.seq_base) < (uint32_t)P.n;
+  if (hw == kUnarmed) return !touched;                 // a vote for a key that was never armed (:220-225)
+  if (hw == kPoison || hw == kBusy) return false;      // several live rounds: its keys live in the table
+  if ((int)(hw & ~kDoneBit) != R) return false;        // a vote of round R could hide behind an older stamp
+  if (!touched) return true;
+  uint32_t c = kStampEmpty;
+  if (!g.flexible) {
+    // phase2bs.size >= f+1 (:238): the (f+1)-th smallest first-delivery stamp
+    const int k = g.quorum - 1;
+#pragma unroll
+    for (int v = 0; v < ROWW - 2; ++v) {
+      if (v >= g.voters) break;
+      const uint32_t s = w[2 + v];
+      int below = 0;
+#pragma unroll
+      for (int u = 0; u < ROWW - 2; ++u)
+        if (u < g.voters) below += (w[2 + u] < s) || (w[2 + u] == s && u < v);
+      if (below == k) c = s;
+    }
+  } else {
+    // Grid.isWriteQuorum: one member of every row (S/quorums/Grid.scala:49)
+    c = 0;
+    for (int r = 0; r < g.groups; ++r) {
+      uint32_t m = kStampEmpty;
+#pragma unroll
+      for (int v = 0; v < ROWW - 2; ++v) {
+        const int lo = r * g.per_group;
+        if (v >= lo && v < lo + g.per_group) m = min(m, w[2 + v]);
+      }
+      c = max(c, m);
+    }
+  }
+  const uint32_t i = c - P.seq_base;
+  if (i < (uint32_t)P.n) *vote = i;                    // Chosen is sent by vote i of this batch (:246-253)
+  return true;
+}
+
+// rank(i): completing votes of the batch before vote i (phase D)
+__device__ __forceinline__ uint32_t vote_rank(const TallyParams& P, const uint32_t* s_ccx, uint32_t i) {
+  const uint2 wd = __ldcg(&P.bw[i >> 5]);
+  return s_ccx[i >> 10] + wd.y + __popc(wd.x & ((1u << (i & 31)) - 1u));
+}
+
+// Sweep over the CTA's contiguous run of window rows.  kEmit = false (phase B): mark
+// the completing votes, keep {vote, value} in shared memory when it fits.  kEmit = true
+// (phase D without kept entries): recompute and emit.
+template <int ROWW, bool kEmit>
+__device__ __forceinline__ void tally_sweep(const TallyParams& P, int w_lo, int w_hi, int R, int rows_per_cta, bool keep,
+                                            uint2* s_keep, const uint32_t* s_ccx, uint32_t out_base) {
+  constexpr int U = ROWW == 8 ? 4 : (ROWW == 16 ? 2 : 1);
+  const Geometry& g = P.g;
+  const long long nrows = (long long)w_hi - w_lo + 1;
+  const long long r_begin = (long long)blockIdx.x * rows_per_cta;
+  const long long r_end = min(nrows, r_begin + rows_per_cta);
+  bool ok = true;
+  for (long long r0 = r_begin + threadIdx.x; r0 < r_end; r0 += (long long)kThreads * U) {
+    uint32_t w[U][ROWW];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const long long r = r0 + u * kThreads;
+      if (r < r_end) load_row<ROWW>(P.pl.rows + (size_t)(w_lo + r) * ROWW, w[u]);
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const long long r = r0 + u * kThreads;
+      if (r >= r_end) continue;
+      uint32_t i;
+      ok &= row_completion<ROWW>(P, w[u], R, &i);
+      if (!kEmit) {
+        if (i != kNoVote) red_or_u32(&P.bw[i >> 5].x, 1u << (i & 31));
+        if (keep) s_keep[r - r_begin] = make_uint2(i, w[u][1]);
+      } else if (i != kNoVote) {
+        // Chosen(slot, pending.phase2a.value) (:249-251) at its place in the order of the completing votes
+        st_stream2(P.out_chosen + out_base + vote_rank(P, s_ccx, i),
+                   make_int2((int)(w_lo + r) * g.shard_count + g.shard_index, (int)w[u][1]));
+      }
+    }
+  }
+  if (!kEmit && __any_sync(0xffffffffu, !ok) && (threadIdx.x & 31) == 0) atomicOr(&P.st->ts_flags, kTsAnomaly);
+}
+
+// ---------------------------------------------------------------------------
+// phase B, exact: the reference's test at every vote of the warp's range.
+// kRedo = false: first evaluation; a vote whose slot is poisoned is stamped into its
+// table entry and kTsPoison is raised.  kRedo = true: only those votes, against their
+// (now fully stamped) table entries.
+// ---------------------------------------------------------------------------
 template <int ROWW, bool kRedo>
-__device__ __forceinline__ uint32_t tally_phase_b(const TallyParams& P, int wlo, int whi, int lane, int2* my_buf) {
+__device__ __forceinline__ void tally_exact(const TallyParams& P, int wlo, int whi, int lane) {
   const Geometry& g = P.g;
   const unsigned full = 0xffffffffu;
   const bool vanilla = g.protocol == FPX_VANILLA_MENCIUS;
   constexpr int kUB = ROWW <= 16 ? 2 : 1;
-  uint32_t wcnt = 0;
   for (int base = wlo; base < whi; base += 32 * kUB) {
     int4 rec[kUB];
 #pragma unroll
@@ -113,7 +224,9 @@ __device__ __forceinline__ uint32_t tally_phase_b(const TallyParams& P, int wlo,
         uint32_t* r = row[u];
         const uint32_t hw = w[u][0];
         bool ok = true;
-        if (vanilla) {
+        if (kRedo && hw != kPoison) {
+          ok = false;                                    // judged in the first evaluation
+        } else if (vanilla) {
           // Server.handlePhase2b: no Phase 2 for the slot / already chosen -> ignore
           // (:1088-1106); stale round -> ignore (:1109-1112); larger: checkEq (:1116), phase A
           ok = hw != kUnarmed && !(hw & kDoneBit) && rec[u].w == (int)hw;
@@ -125,8 +238,8 @@ __device__ __forceinline__ uint32_t tally_phase_b(const TallyParams& P, int wlo,
             ok = false;
           } else if (!kRedo) {
             const int v = voter_index(g, rec[u].x, rec[u].y, rec[u].z);
-            if (v >= 0) atomicMin(&rr.p[2 + v], P.seq_base + (uint32_t)i);            // late stamp (:237)
-            P.st->pad[1] = 1;                                                          // any_slow
+            if (v >= 0) red_min_u32(&rr.p[2 + v], P.seq_base + (uint32_t)i);           // late stamp (:237)
+            atomicOr(&P.st->ts_flags, kTsPoison);
             ok = false;
           } else {
             r = rr.p;
@@ -134,7 +247,7 @@ __device__ __forceinline__ uint32_t tally_phase_b(const TallyParams& P, int wlo,
           }
         } else if (hw == kUnarmed || (int)hw != rec[u].w) {
           // the slot has one armed round and it is not this vote's: never armed (:220-225)
-          if (!kRedo) report_error(P.st, FPX_ERR_UNKNOWN_SLOT_ROUND, i);
+          report_error(P.st, FPX_ERR_UNKNOWN_SLOT_ROUND, i);
           ok = false;
         }
         if (ok) {
@@ -147,7 +260,7 @@ __device__ __forceinline__ uint32_t tally_phase_b(const TallyParams& P, int wlo,
             const int v = voter_index(g, rec[u].x, rec[u].y, rec[u].z);
             if (v < 0) {
               // Grid.isWriteQuorum `require(xs subsetOf nodes)` (Grid.scala:44-47)
-              if (!kRedo || hw == kPoison) report_error(P.st, FPX_ERR_BAD_ACCEPTOR, i);
+              report_error(P.st, FPX_ERR_BAD_ACCEPTOR, i);
             } else {
               uint32_t mine = 0;
 #pragma unroll
@@ -159,63 +272,88 @@ __device__ __forceinline__ uint32_t tally_phase_b(const TallyParams& P, int wlo,
                 if (vanilla) {
                   // choose(): the coordinator's own entry becomes ChosenEntry, phase2s.remove (:622-625)
                   int owner = rec[u].z % g.per_group;
-                  atomicMax(&P.votes[(size_t)local_slot(g, rec[u].z) * g.voters + owner], kCellChosen | w[u][1]);
-                  atomicOr(r, kDoneBit);
+                  red_max_u64(&P.votes[(size_t)local_slot(g, rec[u].z) * g.voters + owner], kCellChosen | w[u][1]);
+                  red_or_u32(r, kDoneBit);
                 }
               }
             }
           }
         }
       }
-      unsigned b = __ballot_sync(full, complete);
-      if (complete) my_buf[wcnt + __popc(b & lanemask_lt())] = out;
-      wcnt += __popc(b);
+      const unsigned b = __ballot_sync(full, complete);
+      if (complete) P.tmp[i] = out;
+      if (b != 0 && lane == 0) red_or_u32(&P.bw[(base + u * 32) >> 5].x, b);   // base is a multiple of 32
     }
   }
-  return wcnt;
 }
 
 template <int ROWW>
-__global__ void __launch_bounds__(kThreads, ROWW == 8 ? 4 : 1) tally_kernel(TallyParams P) {
+__global__ void __launch_bounds__(kThreads, ROWW == 8 ? 4 : (ROWW == 16 ? 2 : 1)) tally_kernel(TallyParams P) {
   const Geometry& g = P.g;
-  extern __shared__ int2 s_buf[];  // kWarps * P.per Chosen records
-  __shared__ uint32_t s_wcnt[kWarps];
-  __shared__ uint32_t s_woff[kWarps];
-  __shared__ uint32_t s_cta_off;
+  extern __shared__ uint32_t s_dyn[];  // [nchunks] exclusive scan of the chunk counts, then [keep_cap] kept {vote, value}
+  __shared__ int s_red[4][kWarps];
+  __shared__ uint32_t s_flags;
+  __shared__ uint32_t s_scan[kWarps];
 
   const unsigned full = 0xffffffffu;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int per = P.per;
+  const int per = warp_range_len(P.n);
   const int gw = blockIdx.x * kWarps + warp;
+  const int total_warps = gridDim.x * kWarps;
   const int wlo = (int)min((long long)P.n, (long long)gw * per);
   const int whi = (int)min((long long)P.n, (long long)wlo + per);
   const bool vanilla = g.protocol == FPX_VANILLA_MENCIUS;
+  const int nchunks = (P.n + kChunkVotes - 1) / kChunkVotes;
+  uint32_t* const s_ccx = s_dyn;
+  uint2* const s_keep = (uint2*)(s_dyn + ((nchunks + 1) & ~1));
+  const uint32_t out_base = P.first ? 0u : (uint32_t)__ldcg(&P.st->n_chosen);   // rewritten only after the last barrier
 
-  // ---- phase A: first-delivery stamps (stream tagged evict_last: phase B re-reads it from L2)
-  const unsigned long long pol_keep = l2_policy_evict_last();
+  // ---- phase A: clear the bitmap, first-delivery stamps, batch statistics
   FPX_MARK(P.st->t_tally, 0);
-  for (int base = wlo; base < whi; base += 32 * kTallyUnroll) {
-    int4 rec[kTallyUnroll];
+  for (int wd = blockIdx.x * kThreads + tid; wd < nchunks * 32; wd += gridDim.x * kThreads)
+    __stcg(&P.bw[wd], make_uint2(0u, 0u));
+  int lo = INT_MAX, hi = -1, rmin = INT_MAX, rmax = INT_MIN;
+  uint32_t flags = 0;
+  if (!vanilla) {
+    // blind: no row header load (see the file comment); phase2bs((g,a)) = msg (:237).
+    // Software-pipelined: the records of stage k+1 are in flight while stage k's REDs issue.
+    int4 rec[kTallyUnroll], nxt[kTallyUnroll];
 #pragma unroll
     for (int u = 0; u < kTallyUnroll; ++u) {
-      int i = base + u * 32 + lane;
-      rec[u] = (i < whi) ? ld_keep(P.in + i, pol_keep) : make_int4(-1, -1, -1, -1);  // {group, acceptor, slot, round}
+      int i = wlo + u * 32 + lane;
+      nxt[u] = (i < whi) ? ld_stream(P.in + i) : make_int4(-1, -1, -1, -1);  // {group, acceptor, slot, round}
     }
-    if (!vanilla) {
-      // blind: no row header load (see the file comment); phase2bs((g,a)) = msg (:237)
+    for (int base = wlo; base < whi; base += 32 * kTallyUnroll) {
+#pragma unroll
+      for (int u = 0; u < kTallyUnroll; ++u) rec[u] = nxt[u];
+#pragma unroll
+      for (int u = 0; u < kTallyUnroll; ++u) {
+        int i = base + 32 * kTallyUnroll + u * 32 + lane;
+        nxt[u] = (i < whi) ? ld_stream(P.in + i) : make_int4(-1, -1, -1, -1);
+      }
 #pragma unroll
       for (int u = 0; u < kTallyUnroll; ++u) {
         int i = base + u * 32 + lane;
         if (i >= whi) continue;
         int local = local_slot(g, rec[u].z);
         if (local < 0) { report_error(P.st, FPX_ERR_SLOT_RANGE, i); continue; }
+        lo = min(lo, local); hi = max(hi, local);
+        rmin = min(rmin, rec[u].w); rmax = max(rmax, rec[u].w);
         int v = voter_index(g, rec[u].x, rec[u].y, rec[u].z);
-        if (v < 0) continue;                                         // judged in phase B (needs Done-ness at i)
-        atomicMin(P.pl.rows + (size_t)local * g.row_words + 2 + v, P.seq_base + (uint32_t)i);
+        if (v < 0) { flags |= kTsBadVoter; continue; }               // judged by the exact path (needs Done-ness at i)
+        if (!(P.path & 4)) red_min_u32(P.pl.rows + (size_t)local * g.row_words + 2 + v, P.seq_base + (uint32_t)i);
       }
-    } else {
+    }
+  } else {
+    for (int base = wlo; base < whi; base += 32 * kTallyUnroll) {
+      int4 rec[kTallyUnroll];
       uint32_t* row[kTallyUnroll];
       uint32_t rw[kTallyUnroll];
+#pragma unroll
+      for (int u = 0; u < kTallyUnroll; ++u) {
+        int i = base + u * 32 + lane;
+        rec[u] = (i < whi) ? ld_cg(P.in + i) : make_int4(-1, -1, -1, -1);
+      }
 #pragma unroll
       for (int u = 0; u < kTallyUnroll; ++u) {
         int i = base + u * 32 + lane;
@@ -242,70 +380,168 @@ __global__ void __launch_bounds__(kThreads, ROWW == 8 ? 4 : 1) tally_kernel(Tall
         if (rec[u].w > (int)w) { report_error(P.st, FPX_ERR_UNKNOWN_SLOT_ROUND, i); continue; }
         int v = voter_index(g, rec[u].x, rec[u].y, rec[u].z);
         if (v < 0) continue;
-        atomicMin(&row[u][2 + v], P.seq_base + (uint32_t)i);
+        red_min_u32(&row[u][2 + v], P.seq_base + (uint32_t)i);
+      }
+    }
+  }
+  if (!vanilla) {
+    lo = __reduce_min_sync(full, lo); hi = __reduce_max_sync(full, hi);
+    rmin = __reduce_min_sync(full, rmin); rmax = __reduce_max_sync(full, rmax);
+    flags = __reduce_or_sync(full, flags);
+    if (tid == 0) s_flags = 0;
+    if (lane == 0) { s_red[0][warp] = lo; s_red[1][warp] = hi; s_red[2][warp] = rmin; s_red[3][warp] = rmax; }
+    __syncthreads();
+    if (lane == 0 && flags) atomicOr(&s_flags, flags);
+    __syncthreads();
+    if (warp == 0) {
+      lo = lane < kWarps ? s_red[0][lane] : INT_MAX; hi = lane < kWarps ? s_red[1][lane] : -1;
+      rmin = lane < kWarps ? s_red[2][lane] : INT_MAX; rmax = lane < kWarps ? s_red[3][lane] : INT_MIN;
+      lo = __reduce_min_sync(full, lo); hi = __reduce_max_sync(full, hi);
+      rmin = __reduce_min_sync(full, rmin); rmax = __reduce_max_sync(full, rmax);
+      if (lane == 0 && hi >= 0) {
+        atomicMin(&P.st->ts_min_local, lo); atomicMax(&P.st->ts_max_local, hi);
+        atomicMin(&P.st->ts_min_round, rmin); atomicMax(&P.st->ts_max_round, rmax);
+        if (s_flags) atomicOr(&P.st->ts_flags, s_flags);
       }
     }
   }
   FPX_MARK(P.st->t_tally, 1);
-  grid_barrier(&P.st->barrier, P.bar_base + gridDim.x);
+  grid_sync(P.st);
   FPX_MARK(P.st->t_tally, 2);
 
-  // ---- phase B: completing votes, buffered in delivery order per warp
-  int2* my_buf = s_buf + (size_t)warp * per;
-  uint32_t wcnt = tally_phase_b<ROWW, false>(P, wlo, whi, lane, my_buf);
-  auto publish = [&]() {
-    if (lane == 0) s_wcnt[warp] = wcnt;
-    __syncthreads();
-    if (tid == 0) {
-      uint32_t run = 0;
-#pragma unroll
-      for (int wv = 0; wv < kWarps; ++wv) { s_woff[wv] = run; run += s_wcnt[wv]; }
-      __stcg(&P.g_ccnt[blockIdx.x], run);
+  // ---- phase B: which votes complete their key
+  const int w_lo = __ldcg(&P.st->ts_min_local), w_hi = __ldcg(&P.st->ts_max_local);
+  const int R = __ldcg(&P.st->ts_min_round);
+  bool sweep = !(P.path & 2) && !vanilla && __ldcg(&P.st->ts_flags) == 0 && w_hi >= w_lo &&
+               R == __ldcg(&P.st->ts_max_round) && (long long)w_hi - w_lo <= 4ll * P.n + 4096;
+  // every CTA sweeps a contiguous run of the window's rows (a multiple of the CTA size)
+  const int rows_per_cta = sweep ? (int)((((long long)w_hi - w_lo + gridDim.x) / gridDim.x + kThreads - 1) / kThreads) * kThreads : 0;
+  const bool keep = rows_per_cta <= P.keep_cap;
+  if (sweep) {
+    tally_sweep<ROWW, false>(P, w_lo, w_hi, R, rows_per_cta, keep, s_keep, s_ccx, out_base);
+    FPX_MARK(P.st->t_tally, 3);
+    grid_sync(P.st);
+    if (__ldcg(&P.st->ts_flags) & kTsAnomaly) {
+      // not a steady-state batch after all: forget the sweep's marks, evaluate every vote
+      sweep = false;
+      for (int wd = blockIdx.x * kThreads + tid; wd < nchunks * 32; wd += gridDim.x * kThreads)
+        __stcg(&P.bw[wd], make_uint2(0u, 0u));
+      grid_sync(P.st);
     }
-  };
-  publish();
-  FPX_MARK(P.st->t_tally, 3);
-  grid_barrier(&P.st->barrier, P.bar_base + 2 * gridDim.x);
+  }
+  if (!sweep) {
+    tally_exact<ROWW, false>(P, wlo, whi, lane);
+    FPX_MARK(P.st->t_tally, 3);
+    grid_sync(P.st);
+    if (__ldcg(&P.st->ts_flags) & kTsPoison) {
+      // some votes belong to slots with several armed rounds (leader change): their table
+      // entries are fully stamped now
+      tally_exact<ROWW, true>(P, wlo, whi, lane);
+      grid_sync(P.st);
+    }
+  }
   FPX_MARK(P.st->t_tally, 4);
-  if (__ldcg(&P.st->pad[1]) != 0) {
-    // some votes belong to slots with several armed rounds (leader change): their table
-    // entries are fully stamped now; evaluate everything again, in order
-    wcnt = tally_phase_b<ROWW, true>(P, wlo, whi, lane, my_buf);
-    __syncthreads();
-    publish();
-    grid_barrier(&P.st->barrier, P.bar_base + 3 * gridDim.x);
-  } else if (tid == 0) {
-    __threadfence();
-    asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(&P.st->barrier) : "memory");  // arrivals stay 4 per CTA
-  }
 
-  // ---- phase C: exact output positions, coalesced copy-out
-  if (warp == 0) {
-    uint32_t off = 0;
-    for (int c = lane; c < (int)blockIdx.x; c += 32) off += __ldcg(&P.g_ccnt[c]);
-    off = __reduce_add_sync(full, off);
-    uint32_t out_base = P.first ? 0u : (uint32_t)__ldcg(&P.st->n_chosen);
-    if (lane == 0) s_cta_off = out_base + off;
-  }
-  __syncthreads();
-  {
-    const uint32_t dst0 = s_cta_off + s_woff[warp];
-    for (uint32_t j = lane; j < wcnt; j += 32) st_stream2(P.out_chosen + dst0 + j, my_buf[j]);
+  // ---- phase C: completing votes before every bitmap word of a chunk, and per chunk
+  for (int k = gw; k < nchunks; k += total_warps) {
+    const uint32_t cnt = __popc(__ldcg(&P.bw[k * 32 + lane].x));
+    uint32_t inc = cnt;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      uint32_t o = __shfl_up_sync(full, inc, d);
+      if (lane >= d) inc += o;
+    }
+    __stcg(&P.bw[k * 32 + lane].y, inc - cnt);
+    if (lane == 31) __stcg(&P.cc[k], inc);
   }
   FPX_MARK(P.st->t_tally, 5);
-  if (blockIdx.x == gridDim.x - 1) {
-    // every CTA has read the old n_chosen / any_slow before this one may overwrite them
-    grid_barrier(&P.st->barrier, P.bar_base + 4 * gridDim.x);
-    if (tid == 0) {
-      P.st->n_chosen = (int)(s_cta_off + s_woff[kWarps - 1] + s_wcnt[kWarps - 1]);
-      P.st->pad[1] = 0;
+  grid_sync(P.st);
+  FPX_MARK(P.st->t_tally, 6);
+
+  // ---- phase D: exclusive scan of the chunk counts (every CTA, in shared memory), then the
+  //      Chosen stream in the order of the completing votes
+  {
+    // coalesced copy of the counts, then a blocked scan in place: thread t owns chunks [t*per_t, (t+1)*per_t)
+    for (int k = tid; k < nchunks; k += kThreads) s_ccx[k] = __ldcg(&P.cc[k]);
+    __syncthreads();
+    const int per_t = (nchunks + kThreads - 1) / kThreads;
+    const int c0 = min(nchunks, tid * per_t), c1 = min(nchunks, c0 + per_t);
+    uint32_t sum = 0;
+    for (int k = c0; k < c1; ++k) sum += s_ccx[k];
+    uint32_t incl = sum;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      uint32_t o = __shfl_up_sync(full, incl, d);
+      if (lane >= d) incl += o;
     }
-  } else {
-    if (tid == 0) {
-      __threadfence();
-      asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(&P.st->barrier) : "memory");
+    if (lane == 31) s_scan[warp] = incl;
+    __syncthreads();
+    uint32_t run = incl - sum;
+#pragma unroll
+    for (int wv = 0; wv < kWarps; ++wv) if (wv < warp) run += s_scan[wv];
+    for (int k = c0; k < c1; ++k) { uint32_t c = s_ccx[k]; s_ccx[k] = run; run += c; }
+    __syncthreads();
+    uint32_t total = 0;
+#pragma unroll
+    for (int wv = 0; wv < kWarps; ++wv) total += s_scan[wv];
+
+    if (sweep && keep) {
+      // the CTA's kept {vote, value} entries: one random 8-byte load (word + prefix), one 8-byte store each
+      const long long nrows = (long long)w_hi - w_lo + 1;
+      const long long r_begin = (long long)blockIdx.x * rows_per_cta;
+      const int mine = (int)max(0ll, min(nrows, r_begin + rows_per_cta) - r_begin);
+      for (int e0 = tid; e0 < mine; e0 += kThreads * 4) {
+        uint2 ent[4];
+        uint2 wd[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int e = e0 + u * kThreads;
+          ent[u] = e < mine ? s_keep[e] : make_uint2(kNoVote, 0u);
+          if (ent[u].x != kNoVote) wd[u] = __ldcg(&P.bw[ent[u].x >> 5]);
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          if (ent[u].x == kNoVote) continue;
+          const uint32_t i = ent[u].x;
+          const uint32_t rank = s_ccx[i >> 10] + wd[u].y + __popc(wd[u].x & ((1u << (i & 31)) - 1u));
+          const int e = e0 + u * kThreads;
+          st_stream2(P.out_chosen + out_base + rank,
+                     make_int2((int)(w_lo + r_begin + e) * g.shard_count + g.shard_index, (int)ent[u].y));
+        }
+      }
+    } else if (sweep) {
+      tally_sweep<ROWW, true>(P, w_lo, w_hi, R, rows_per_cta, false, s_keep, s_ccx, out_base);
+    } else {
+      for (int k = gw; k < nchunks; k += total_warps) {
+        const uint2 wd = __ldcg(&P.bw[k * 32 + lane]);
+        const uint32_t wpre = out_base + s_ccx[k] + wd.y;        // records before this lane's word
+        const int2* src = P.tmp + (size_t)k * kChunkVotes + lane;
+        // 8 steps at a time: the parked records are loaded unconditionally (tmp is padded to a whole
+        // chunk) so that the 8 loads are in flight together; only completing votes are stored
+#pragma unroll
+        for (int s0 = 0; s0 < 32; s0 += 8) {
+          int2 rec[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) rec[j] = __ldcg(src + (s0 + j) * 32);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const uint32_t wv = __shfl_sync(full, wd.x, s0 + j);
+            const uint32_t pre = __shfl_sync(full, wpre, s0 + j);
+            if ((wv >> lane) & 1u) st_stream2(P.out_chosen + pre + __popc(wv & lanemask_lt()), rec[j]);
+          }
+        }
+      }
+    }
+    if (blockIdx.x == 0 && tid == 0) {
+      // every CTA is past its reads of the statistics (barrier after phase C): reset them for the next launch
+      P.st->n_chosen = (int)(out_base + total);
+      P.st->ts_min_local = INT_MAX; P.st->ts_max_local = -1;
+      P.st->ts_min_round = INT_MAX; P.st->ts_max_round = INT_MIN;
+      P.st->ts_flags = 0;
+      P.st->ts_path = sweep ? 1u : 2u;
     }
   }
+  FPX_MARK(P.st->t_tally, 7);
 }
 
 }  // namespace fpx

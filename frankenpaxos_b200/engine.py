@@ -109,6 +109,16 @@ class Engine:
     def launch_count(self):
         return self._L.fpx_launch_count(self.h)
 
+    # -- test / profiling aids (not part of include/fpx.h)
+    def set_tally_path(self, exact):
+        """exact=True: every tally launch evaluates each vote (no row sweep)."""
+        self._check(self._L.fpx_debug_set_tally_path(self.h, 2 if exact else 0))
+
+    @property
+    def last_tally_path(self):
+        """'sweep' / 'exact': what the last proxyleader_phase2b launch did."""
+        return {1: "sweep", 2: "exact"}.get(self._L.fpx_debug_last_tally_path(self.h), "none")
+
     # -- host-pointer calls (numpy in / numpy out)
     def proxyleader_arm(self, p2a):
         p2a = np.ascontiguousarray(p2a, dtype=P2A)

@@ -23,10 +23,11 @@ N_SLOTS = 24
 _engines = {}
 
 
-def engine(shape):
+def engine(shape, exact):
     if shape not in _engines:
         _engines[shape] = Engine(slot_capacity=N_SLOTS, max_batch=4096, overflow_capacity=256, **SHAPES[shape])
     _engines[shape].reset()
+    _engines[shape].set_tally_path(exact)
     return _engines[shape]
 
 
@@ -41,13 +42,14 @@ step = st.one_of(
 )
 
 
+@pytest.mark.parametrize("exact", [False, True], ids=["auto", "exact"])
 @pytest.mark.parametrize("shape", list(SHAPES))
 @settings(max_examples=120, deadline=None, suppress_health_check=list(HealthCheck))
 @given(script=st.lists(step, min_size=1, max_size=8))
-def test_fuzz_against_oracle(shape, script):
+def test_fuzz_against_oracle(shape, exact, script):
     cfg = SHAPES[shape]
     G, A = cfg["num_acceptor_groups"], cfg["acceptors_per_group"]
-    eng = engine(shape)
+    eng = engine(shape, exact)
     ora = O.MultiPaxos(cfg["f"], G, A, cfg["flexible"], cfg["num_leaders"], cfg["num_replicas"])
     for kind, recs in script:
         if kind == "arm":

@@ -16,6 +16,14 @@ from oracle import fpx_oracle_py as O
 pytestmark = pytest.mark.gpu
 
 
+@pytest.fixture(autouse=True, params=["auto", "exact"])
+def tally_path(request, monkeypatch):
+    """Every test of this module runs twice: with the tally free to take its row sweep
+    (steady-state batches) and forced onto the exact per-vote path (FPX_TALLY_PATH)."""
+    monkeypatch.setenv("FPX_TALLY_PATH", request.param)
+    return request.param
+
+
 def D(g, a):
     return (g << 16) | a
 
@@ -177,6 +185,69 @@ def test_conflict_cap_is_reported_not_silently_wrong():
     with pytest.raises(FpxError) as ei:
         eng.proxyleader_arm(a)
     assert ei.value.status == -9
+    eng.close()
+
+
+# --------------------------------------------------------------------------- the tally's two paths
+def test_tally_takes_the_sweep_in_steady_state_and_falls_back_otherwise(tally_path):
+    """fpx_tally.cuh: a one-round batch over armed rows of that round is evaluated by the row
+    sweep; a batch that mixes rounds, touches an unarmed row, hides a vote of another round
+    behind an older stamp, or carries a foreign voter is evaluated per vote.  Same outputs."""
+    cfg, _ = T.config_by_name("cfg2")
+    n_slots = 6000
+    eng, ora = H.make_pair(cfg, 3 * n_slots, max_batch=1 << 16, overflow_capacity=1 << 10)
+    want = "sweep" if tally_path == "auto" else "exact"
+    a, p, b = T.workload(5, cfg, n_slots)
+    H.arm(eng, ora, a)
+    ob, _ = H.phase2a(eng, ora, p)
+    # votes of one key spread over several batches: completion decided by stamps of earlier batches
+    for chunk in np.array_split(b, 7):
+        st, c = H.phase2b(eng, ora, chunk)
+        assert st == 0 and eng.last_tally_path == want
+        H.replica(eng, ora, c)
+    # duplicates of old votes only: nothing new is chosen, still a sweep
+    st, c = H.phase2b(eng, ora, b[:500])
+    assert st == 0 and len(c) == 0 and eng.last_tally_path == want
+    # a second window in round 1; one batch mixes it with late round-0 votes -> exact
+    a1, p1, b1 = T.workload(6, cfg, n_slots, slot0=n_slots, round_=1)
+    H.arm(eng, ora, a1)
+    mix = np.concatenate([b1[:3000], b[:10]])
+    st, c = H.phase2b(eng, ora, mix)
+    assert st == 0 and eng.last_tally_path == "exact"
+    H.replica(eng, ora, c)
+    st, c = H.phase2b(eng, ora, b1[3000:])
+    assert st == 0 and eng.last_tally_path == want
+    H.replica(eng, ora, c)
+    H.compare_log(eng, ora, 0, 2 * n_slots)
+    # a vote of round 1 for a round-0 key whose voter already voted: hidden behind the older stamp
+    hidden = b[:1].copy()
+    hidden["round"] = 1
+    st, _ = H.phase2b(eng, ora, hidden)
+    assert st == -4 and eng.last_tally_path == "exact"
+    eng.close()
+
+
+def test_sweep_error_paths_report_the_reference_index(tally_path):
+    cfg, _ = T.config_by_name("cfg2")
+    n_slots = 4000
+    # an unarmed slot in the middle of the window: every one of its votes is fatal, the first is reported
+    eng, ora = H.make_pair(cfg, n_slots)
+    a, p, b = T.workload(8, cfg, n_slots)
+    H.arm(eng, ora, a[a["slot"] != 1234])
+    st, _ = H.phase2b(eng, ora, b)
+    assert st == -4
+    eng.close()
+
+
+def test_sweep_window_far_larger_than_the_batch_uses_the_exact_path(tally_path):
+    cfg, _ = T.config_by_name("cfg2")
+    n_slots = 1 << 20
+    eng, ora = H.make_pair(cfg, n_slots, max_batch=1 << 12)
+    slots = np.array([3, n_slots - 5, 77777, 500000], dtype=np.int32)
+    H.arm(eng, ora, T.arms(slots, 0, slots + 1))
+    v = T.votes_of(T.phase2as(T.rng(1), slots, cfg["f"], 1, 5, False, 0, slots + 1))
+    st, c = H.phase2b(eng, ora, v)
+    assert st == 0 and len(c) == 4 and eng.last_tally_path == "exact"
     eng.close()
 
 
@@ -688,4 +759,89 @@ def test_device_pointer_path_matches_oracle(one_call):
     H.same(d_ch[: r.n_chosen].cpu().numpy().view(CHOSEN).reshape(-1), oc, "Chosen stream (device)")
     H.compare_acceptors(eng, ora, cfg, 0, n_slots)
     H.compare_log(eng, ora, 0, n_slots)
+    eng.close()
+
+
+# --------------------------------------------------------------------------- full size, bit-exact vs the oracle
+def _full_size(name, seed, partitions=None):
+    cfg, n_slots = T.config_by_name(name)
+    a, p, b = T.workload(seed, cfg, n_slots, partitions=partitions)
+    eng, ora = H.make_pair(cfg, n_slots, max_batch=len(p), overflow_capacity=1 << 10)
+    H.arm(eng, ora, a)
+    ob, on = H.phase2a(eng, ora, p)                  # Phase2b / Nack streams, bit-exact incl. order
+    assert len(on) == 0
+    H.compare_acceptors(eng, ora, cfg, 0, n_slots)   # every acceptor: round, maxVotedSlot, voteRound[], voteValue[]
+    st, c = H.phase2b(eng, ora, b)                   # Chosen stream, bit-exact incl. order
+    assert st == 0 and len(c) == n_slots
+    H.replica(eng, ora, c)
+    H.compare_log(eng, ora, 0, n_slots)
+    eng.close()
+
+
+def test_full_size_bit_exact_cfg2(tally_path):
+    """BASELINE cfg2 at its full size (2^20 slots, 3*2^20 Phase2a / Phase2b) against the oracle:
+    every stream, every acceptor's state, the replica log."""
+    _full_size("cfg2", 0)
+
+
+def test_full_size_bit_exact_cfg3(tally_path):
+    """BASELINE cfg3 at its full size (2x3 grid, 2^22 slots, 10 proxy-leader partitions)."""
+    if tally_path == "exact":
+        pytest.skip("full-size cfg3 runs once (oracle time); the exact path is covered at 30000 slots")
+    _full_size("cfg3", 1, partitions=10)
+
+
+def test_full_size_bit_exact_cfg5_vanilla_mencius(tally_path):
+    """BASELINE cfg5 at its full size (n=7, 2^20 slots, 6 Phase2a + 6 Phase2b per slot) against the oracle."""
+    if tally_path == "exact":
+        pytest.skip("vanilla Mencius always takes the exact path")
+    from frankenpaxos_b200 import VANILLA_MENCIUS
+    cfg, n_slots = T.config_by_name("cfg5")
+    f, n = cfg["f"], cfg["acceptors_per_group"]
+    eng = Engine(slot_capacity=n_slots, max_batch=(n - 1) * n_slots, protocol=VANILLA_MENCIUS, **cfg)
+    ora = O.VanillaMencius(f)
+    req, p, b = T.vanilla_cfg5(2, f, n_slots)
+    eng.vm_client_request(req)
+    assert ora.client_request(req) == (0, -1)
+    st, _, orep = ora.phase2a(p)
+    H.same(eng.vm_phase2a(p), orep, "vanilla Phase2a replies")
+    st, c = H.phase2b(eng, ora, b)
+    assert st == 0 and len(c) == n_slots
+    eng.close()
+
+
+def test_bench_shaped_step_on_a_rebased_window_matches_the_oracle(tally_path):
+    """What bench.py times: the device-pointer path on window w != 0 of a long log (slots
+    w*2^20 .. (w+1)*2^20, earlier windows already committed), compared with the oracle."""
+    import torch
+    cfg, _ = T.config_by_name("cfg2")
+    W, win = 1 << 20, 2
+    eng, ora = H.make_pair(cfg, 3 * W, max_batch=3 * W, overflow_capacity=1 << 10)
+    dev = torch.device("cuda", 0)
+
+    def td(x):
+        return torch.from_numpy(x.view(np.int32).reshape(len(x), -1).copy()).to(dev)
+    d_p2b = torch.zeros((3 * W, 4), dtype=torch.int32, device=dev)
+    d_nack = torch.zeros((3 * W, 2), dtype=torch.int32, device=dev)
+    d_ch = torch.zeros((3 * W, 2), dtype=torch.int32, device=dev)
+    d_wm = torch.zeros(1, dtype=torch.int32, device=dev)
+    for w in range(win + 1):
+        a, p, b = T.workload(40 + w, cfg, W, slot0=w * W)
+        ora.arm(a)
+        _, _, ob, on = ora.acceptor_phase2a(p)
+        _, _, oc = ora.proxyleader_phase2b(b)
+        ora.replica_chosen(oc)
+        d_a, d_p, d_b = td(a), td(p), td(b)
+        eng.proxyleader_arm_dev(d_a.data_ptr(), len(a))
+        eng.acceptor_phase2a_dev(d_p.data_ptr(), len(p), d_p2b.data_ptr(), d_nack.data_ptr())
+        eng.proxyleader_phase2b_dev(d_b.data_ptr(), len(b), d_ch.data_ptr())
+        eng.replica_chosen_last_dev(d_ch.data_ptr())
+        eng.chosen_watermark_dev(d_wm.data_ptr())
+        r = eng.sync()
+        assert (r.status, r.n_p2b, r.n_nack, r.n_chosen) == (0, len(ob), 0, len(oc))
+        assert r.watermark == ora.executed_watermark() == (w + 1) * W
+        H.same(d_p2b[: r.n_p2b].cpu().numpy().view(P2B).reshape(-1), ob, f"Phase2b stream, window {w}")
+        H.same(d_ch[: r.n_chosen].cpu().numpy().view(CHOSEN).reshape(-1), oc, f"Chosen stream, window {w}")
+    H.compare_acceptors(eng, ora, cfg, win * W, W)
+    H.compare_log(eng, ora, win * W, W)
     eng.close()
