@@ -40,7 +40,7 @@ struct AcceptorParams {
   int32_t* acc_max_voted;          // num_keys
   uint32_t* accept_bits;           // ceil(n/32)
   int32_t* g_agg;                  // [grid][kMaxKeys] per-CTA max round per acceptor
-  uint32_t* g_wacc;                // [grid*kWarps] accepted records per warp range
+  uint32_t* g_wacc;                // [grid*kAW] accepted records per warp range
   uint32_t parity;                 // which nack counter this launch uses
   int32_t append;                  // 1: continue the reply streams of the previous launch (chunked host call)
   int32_t demote;                  // pass 2 re-reads the stream with evict_first: it is dead afterwards
@@ -49,6 +49,9 @@ struct AcceptorParams {
 };
 
 constexpr int kAccUnroll = 4;
+// one CTA of 32 warps per SM (see fpx_tally.cuh: several CTAs per SM spread up to 2x, and both passes end at a grid barrier)
+constexpr int kAT = 1024;
+constexpr int kAW = kAT / 32;
 __device__ __forceinline__ int grp_of(int dst) { return dst >> 16; }
 
 // decode + validate one Phase2a record; key = global acceptor id or -1
@@ -76,7 +79,7 @@ __device__ __noinline__ void acceptor_error(DevStatus* st, int code, int index) 
 
 // Pass 2 (kExact = false: effects + dense replies) and pass 3 (kExact = true:
 // compacted replies only).  `run` is lane-indexed: lane k holds acceptor k's
-// round as of the start of the warp's range.  s_mv is a [num_keys][kThreads]
+// round as of the start of the warp's range.  s_mv is a [num_keys][kAT]
 // table of per-thread private maxima of accepted slots (maxVotedSlot, :209).
 template <bool kExact>
 __device__ __forceinline__ void acceptor_apply(const AcceptorParams& P, int4* out_p2b, int2* out_nack, int wlo, int whi,
@@ -150,7 +153,7 @@ __device__ __forceinline__ void acceptor_apply(const AcceptorParams& P, int4* ou
           cell[u] = ((unsigned long long)(uint32_t)(r + 1) << 32) | (uint32_t)rec[u].z;
           old[u] = atomicMax(&P.votes[(size_t)loc * g.voters + vix], cell[u]);
           // maxVotedSlot = max(maxVotedSlot, slot) (:209): thread-private column
-          atomicMax(&s_mv[key * kThreads + threadIdx.x], rec[u].x);
+          atomicMax(&s_mv[key * kAT + threadIdx.x], rec[u].x);
         }
         wnack += __popc(__ballot_sync(full, valid && !accept));
       } else {
@@ -180,18 +183,18 @@ __device__ __forceinline__ void acceptor_apply(const AcceptorParams& P, int4* ou
   }
 }
 
-__global__ void __launch_bounds__(kThreads) acceptor_phase2a_kernel(AcceptorParams P) {
+__global__ void __launch_bounds__(kAT, 1) acceptor_phase2a_kernel(AcceptorParams P) {
   const Geometry& g = P.g;
-  extern __shared__ int s_mv[];  // [num_keys][kThreads] private maxVotedSlot columns
-  __shared__ int s_wagg[kWarps][kMaxKeys];
-  __shared__ int s_tmp[kWarps][kMaxKeys];
-  __shared__ bool s_last;
+  extern __shared__ int s_mv[];  // [num_keys][kAT] private maxVotedSlot columns
+  __shared__ int s_wagg[kAW][kMaxKeys];
+  __shared__ int s_tmp[kAW][kMaxKeys];
   __shared__ int s_win;
 
   const unsigned full = 0xffffffffu;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int per = warp_range_len(P.n);
-  const int gw = blockIdx.x * kWarps + warp;
+  const int total_warps = gridDim.x * kAW;
+  const int per = (((P.n + total_warps - 1) / total_warps) + 31) & ~31;   // contiguous range of every warp
+  const int gw = blockIdx.x * kAW + warp;
   const int wlo = (int)min((long long)P.n, (long long)gw * per);
   const int whi = (int)min((long long)P.n, (long long)wlo + per);
   uint32_t* nack_ctr = P.parity ? &P.st->nack_total : &P.st->pad[0];
@@ -203,7 +206,7 @@ __global__ void __launch_bounds__(kThreads) acceptor_phase2a_kernel(AcceptorPara
   const uint32_t base_nack = P.append ? (uint32_t)__ldcg(&P.st->n_nack) : 0u;
   int4* const out_p2b = P.out_p2b + base_p2b;
   int2* const out_nack = P.out_nack + base_nack;
-  for (int k = 0; k < g.num_keys; ++k) s_mv[k * kThreads + tid] = INT_MIN;
+  for (int k = 0; k < g.num_keys; ++k) s_mv[k * kAT + tid] = INT_MIN;
   FPX_MARK(P.st->t_acceptor, 0);
 
   // ---- pass 1: per-acceptor max round of the warp's range (lane = acceptor).
@@ -248,7 +251,7 @@ __global__ void __launch_bounds__(kThreads) acceptor_phase2a_kernel(AcceptorPara
   int cta_agg = INT_MIN;
   if (warp == 0) {
 #pragma unroll
-    for (int w = 0; w < kWarps; ++w) cta_agg = max(cta_agg, s_wagg[w][lane]);
+    for (int w = 0; w < kAW; ++w) cta_agg = max(cta_agg, s_wagg[w][lane]);
     __stcg(&P.g_agg[blockIdx.x * kMaxKeys + lane], cta_agg);
   }
   FPX_MARK(P.st->t_acceptor, 1);
@@ -259,7 +262,7 @@ __global__ void __launch_bounds__(kThreads) acceptor_phase2a_kernel(AcceptorPara
   // thread t covers CTAs t, t+256, ... for every acceptor: all loads independent.
   for (int k = 0; k < g.num_keys; ++k) {
     int v = INT_MIN;
-    for (int c = tid; c < (int)blockIdx.x; c += kThreads) v = max(v, __ldcg(&P.g_agg[c * kMaxKeys + k]));
+    for (int c = tid; c < (int)blockIdx.x; c += kAT) v = max(v, __ldcg(&P.g_agg[c * kMaxKeys + k]));
     v = __reduce_max_sync(full, v);
     if (lane == 0) s_tmp[warp][k] = v;
   }
@@ -268,7 +271,7 @@ __global__ void __launch_bounds__(kThreads) acceptor_phase2a_kernel(AcceptorPara
   if (lane < g.num_keys) {
     cta_carry = __ldcg(&P.acc_round[lane]);
 #pragma unroll
-    for (int w = 0; w < kWarps; ++w) cta_carry = max(cta_carry, s_tmp[w][lane]);
+    for (int w = 0; w < kAW; ++w) cta_carry = max(cta_carry, s_tmp[w][lane]);
   }
   int run = cta_carry;
   for (int w = 0; w < warp; ++w) run = max(run, s_wagg[w][lane]);
@@ -282,10 +285,10 @@ __global__ void __launch_bounds__(kThreads) acceptor_phase2a_kernel(AcceptorPara
     if (wnack) atomicAdd(nack_ctr, wnack);
   }
   __syncthreads();
-  for (int k = warp; k < g.num_keys; k += kWarps) {
+  for (int k = warp; k < g.num_keys; k += kAW) {
     int m = INT_MIN;
 #pragma unroll
-    for (int t = lane; t < kThreads; t += 32) m = max(m, s_mv[k * kThreads + t]);
+    for (int t = lane; t < kAT; t += 32) m = max(m, s_mv[k * kAT + t]);
     m = __reduce_max_sync(full, m);
     if (lane == 0 && m != INT_MIN) atomicMax(&P.acc_max_voted[k], m);
   }
@@ -298,7 +301,7 @@ __global__ void __launch_bounds__(kThreads) acceptor_phase2a_kernel(AcceptorPara
   if (blockIdx.x == gridDim.x - 1 && warp == 0 && lane < g.num_keys) {
     int tot = cta_carry;
 #pragma unroll
-    for (int w = 0; w < kWarps; ++w) tot = max(tot, s_wagg[w][lane]);
+    for (int w = 0; w < kAW; ++w) tot = max(tot, s_wagg[w][lane]);
     P.acc_round[lane] = tot;
   }
   const uint32_t total_nacks = __ldcg(nack_ctr);
@@ -311,22 +314,17 @@ __global__ void __launch_bounds__(kThreads) acceptor_phase2a_kernel(AcceptorPara
     before = __reduce_add_sync(full, before);
     uint32_t wacc2 = 0, wnack2 = 0;
     acceptor_apply<true>(P, out_p2b, out_nack, wlo, whi, lane, run, before, s_mv, wacc2, wnack2);
-    if (gw == (int)gridDim.x * kWarps - 1 && lane == 0) {
+    if (gw == (int)gridDim.x * kAW - 1 && lane == 0) {
       P.st->n_p2b = (int)(base_p2b + before + wacc2);
       P.st->n_nack = (int)base_nack + P.n - (int)(before + wacc2);
     }
   }
 
-  // ---- last block: same (acceptor, slot, round) voted twice with different
-  // values in one batch -> the later delivery must win (map overwrite, :205)
-  __threadfence();
-  __syncthreads();
-  if (tid == 0) s_last = (atomicAdd(&P.st->ticket, 1u) == gridDim.x - 1);
-  __syncthreads();
-  if (!s_last) return;
-  __threadfence();
-  uint32_t nc = *(volatile uint32_t*)&P.st->n_conflicts;
-  if (tid == 0) P.st->ticket = 0;
+  // ---- CTA 0: same (acceptor, slot, round) voted twice with different values in one batch -> the
+  // later delivery must win (map overwrite, :205).  Every conflict was recorded in pass 2, i.e. before
+  // the second grid barrier.
+  if (blockIdx.x != 0) return;
+  uint32_t nc = __ldcg(&P.st->n_conflicts);
   if (nc == 0) return;
   if (nc > (uint32_t)kMaxConflicts) {
     if (tid == 0) { report_error(P.st, FPX_ERR_CONFLICT, 0); P.st->n_conflicts = 0; }
@@ -336,7 +334,7 @@ __global__ void __launch_bounds__(kThreads) acceptor_phase2a_kernel(AcceptorPara
     int dst = P.conflicts[cix].dst, slot = P.conflicts[cix].slot;
     if (tid == 0) s_win = -1;
     __syncthreads();
-    for (int j = tid; j < P.n; j += kThreads) {
+    for (int j = tid; j < P.n; j += kAT) {
       int4 rr = P.in[j];
       if (rr.w == dst && rr.x == slot && ((__ldcg(&P.accept_bits[j >> 5]) >> (j & 31)) & 1u)) atomicMax(&s_win, j);
     }

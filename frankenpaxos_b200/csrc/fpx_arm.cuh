@@ -31,7 +31,7 @@ struct ArmParams {
 };
 
 __device__ __forceinline__ void note_arm_conflict(const ArmParams& P, int slot, int round) {
-  uint32_t c = atomicAdd(&P.st->n_conflicts, 1u);
+  uint32_t c = atomicAdd(&P.st->n_arm_conflicts, 1u);
   if (c < (uint32_t)kMaxConflicts) P.conflicts[c] = ArmConflict{slot, round};
 }
 
@@ -115,89 +115,95 @@ __device__ __forceinline__ bool arm_finish(const ArmParams& P, const int4& rec, 
 }
 
 constexpr int kArmUnroll = 8;
+constexpr int kArmThreads = 1024;   // one CTA of 32 warps per SM, at most one wave (grid-stride loop)
 
-__global__ void __launch_bounds__(256) arm_kernel(ArmParams P) {
+// The arm work of warp `gwarp` of `total_warps` (arm_kernel; also called from the acceptor kernel when
+// fpx_step_dev runs both roles in one launch).  Warp-strided 32-record chunks; per lane kArmUnroll
+// independent record loads, then kArmUnroll independent header CASes, are in flight before any result is
+// used.  Only the row index and the CAS result stay live across the round trip; the rare slow paths
+// (key exists, second round of a slot, vanilla self vote) re-read their record.
+__device__ __forceinline__ int arm_chunks(const ArmParams& P, int gwarp, int total_warps, int lane) {
   const Geometry& g = P.g;
-  const int lane = threadIdx.x & 31;
-  const int total_warps = gridDim.x * (blockDim.x >> 5);
-  const int gwarp = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int n_chunks = (P.n + 31) >> 5;
-  // warp-strided 32-record chunks; per lane kArmUnroll independent record loads,
-  // then kArmUnroll independent header CASes, are in flight before any is used
   int max_local = -1;
   for (int c0 = gwarp * kArmUnroll; c0 < n_chunks; c0 += total_warps * kArmUnroll) {
-    int4 rec[kArmUnroll];
     unsigned long long old[kArmUnroll];
-    bool ok[kArmUnroll];
+    unsigned long long want[kArmUnroll];
+    int local[kArmUnroll];          // row of the record, -1: not a valid arm
+    {
+      int4 rec[kArmUnroll];
 #pragma unroll
-    for (int u = 0; u < kArmUnroll; ++u) {
-      int i = (c0 + u) * 32 + lane;
-      rec[u] = (c0 + u < n_chunks && i < P.n) ? ld_stream(P.in + i) : make_int4(-1, 0, 0, 0);  // {slot, round, value_id, dst}
-    }
+      for (int u = 0; u < kArmUnroll; ++u) {
+        int i = (c0 + u) * 32 + lane;
+        rec[u] = (c0 + u < n_chunks && i < P.n) ? ld_stream(P.in + i) : make_int4(-1, 0, 0, 0);  // {slot, round, value_id, dst}
+      }
 #pragma unroll
-    for (int u = 0; u < kArmUnroll; ++u) {
-      int i = (c0 + u) * 32 + lane;
-      ok[u] = false;
-      old[u] = 0;
-      if (c0 + u < n_chunks && i < P.n) {
-        int local = local_slot(g, rec[u].x);
-        if (local < 0) {
-          report_error(P.st, FPX_ERR_SLOT_RANGE, i);
-        } else if ((uint32_t)rec[u].y > (uint32_t)FPX_MAX_ROUND) {
-          report_error(P.st, FPX_ERR_ROUND_RANGE, i);
-        } else if (P.vanilla && ((rec[u].w >> 16) != 0 || (rec[u].w & 0xffff) >= g.per_group ||
-                                 rec[u].x % g.per_group != (rec[u].w & 0xffff))) {
-          report_error(P.st, FPX_ERR_BAD_ACCEPTOR, i);   // only the slot's owner coordinates it (:773, slotSystem)
-        } else if (P.check_rng && range_find(P.rng, rec[u].x, rec[u].x + 1, rec[u].y) != nullptr) {
-          // S/mencius: SlotRound(slot, slot+1, round) is held by a one-slot Phase2aNoopRange:
-          // `case Some(_)` -> ignored (mencius/ProxyLeader.scala:220-226)
-        } else {
-          ok[u] = true;
-          unsigned long long want = ((unsigned long long)(uint32_t)rec[u].z << 32) | (uint32_t)rec[u].y;
-          old[u] = atomicCAS((unsigned long long*)(P.pl.rows + (size_t)local * g.row_words), kU64Empty, want);
+      for (int u = 0; u < kArmUnroll; ++u) {
+        int i = (c0 + u) * 32 + lane;
+        local[u] = -1;
+        old[u] = 0;
+        if (c0 + u < n_chunks && i < P.n) {
+          int l = local_slot(g, rec[u].x);
+          if (l < 0) {
+            report_error(P.st, FPX_ERR_SLOT_RANGE, i);
+          } else if ((uint32_t)rec[u].y > (uint32_t)FPX_MAX_ROUND) {
+            report_error(P.st, FPX_ERR_ROUND_RANGE, i);
+          } else if (P.vanilla && ((rec[u].w >> 16) != 0 || (rec[u].w & 0xffff) >= g.per_group ||
+                                   rec[u].x % g.per_group != (rec[u].w & 0xffff))) {
+            report_error(P.st, FPX_ERR_BAD_ACCEPTOR, i);   // only the slot's owner coordinates it (:773, slotSystem)
+          } else if (P.check_rng && range_find(P.rng, rec[u].x, rec[u].x + 1, rec[u].y) != nullptr) {
+            // S/mencius: SlotRound(slot, slot+1, round) is held by a one-slot Phase2aNoopRange:
+            // `case Some(_)` -> ignored (mencius/ProxyLeader.scala:220-226)
+          } else {
+            // the header is READ first: a plain load misses to DRAM far more cheaply than an atomic does,
+            // and a key that already exists needs no CAS at all (`case Some(_)`, :177-183)
+            local[u] = l;
+            want[u] = ((unsigned long long)(uint32_t)rec[u].z << 32) | (uint32_t)rec[u].y;
+            old[u] = __ldcg((const unsigned long long*)(P.pl.rows + (size_t)l * g.row_words));
+          }
         }
       }
     }
 #pragma unroll
+    for (int u = 0; u < kArmUnroll; ++u)
+      if (local[u] >= 0 && old[u] == kU64Empty)
+        old[u] = atomicCAS((unsigned long long*)(P.pl.rows + (size_t)local[u] * g.row_words), kU64Empty, want[u]);
+#pragma unroll
     for (int u = 0; u < kArmUnroll; ++u) {
       if (c0 + u >= n_chunks) break;
       int i = (c0 + u) * 32 + lane;
-      bool won = ok[u] && arm_finish(P, rec[u], old[u], i);  // created the key's Pending entry (:213)
-      if (won && P.vanilla) {
-        // Server.handleClientRequest: log.put(slot, PendingEntry(0, 0, value)) (:779) and
-        // phase2s(slot).phase2bs = {index -> Phase2b} (:818-825): own vote, stamped "before everything"
-        int local = local_slot(g, rec[u].x);
-        int self = rec[u].w & 0xffff;
-        P.pl.rows[(size_t)local * g.row_words + 2 + self] = 0;
-        atomicMax(&P.votes[(size_t)local * g.voters + self],
-                  ((unsigned long long)(uint32_t)(rec[u].y + 1) << 32) | (uint32_t)rec[u].z);
+      bool won = local[u] >= 0 && old[u] == kU64Empty;       // Pending(phase2a, {}) created (:213)
+      if (local[u] >= 0 && (old[u] != kU64Empty || P.vanilla)) {
+        const int4 rec = __ldcg(P.in + i);
+        won = arm_finish(P, rec, old[u], i);
+        if (won && P.vanilla) {
+          // Server.handleClientRequest: log.put(slot, PendingEntry(0, 0, value)) (:779) and
+          // phase2s(slot).phase2bs = {index -> Phase2b} (:818-825): own vote, stamped "before everything"
+          int self = rec.w & 0xffff;
+          P.pl.rows[(size_t)local[u] * g.row_words + 2 + self] = 0;
+          atomicMax(&P.votes[(size_t)local[u] * g.voters + self],
+                    ((unsigned long long)(uint32_t)(rec.y + 1) << 32) | (uint32_t)rec.z);
+        }
       }
       unsigned wb = __ballot_sync(0xffffffffu, won);
       if (lane == 0) P.win_bits[c0 + u] = wb;
-      int ml = __reduce_max_sync(0xffffffffu, won ? local_slot(g, rec[u].x) : -1);
+      int ml = __reduce_max_sync(0xffffffffu, won ? local[u] : -1);
       if (lane == 0 && ml > max_local) max_local = ml;
     }
   }
+  return max_local;
+}
 
-  if (lane == 0 && max_local >= 0) atomicMax(&P.st->max_armed_local, max_local);
-
-  // ---- last block: two arms of one key with different values.  If the key was
-  // created by a record of THIS batch, the lowest-index arm is the one the
-  // reference would have kept (later ones hit `case Some(_)`, :177-183); if it
-  // existed before the batch, the stored value stands.
-  __shared__ bool s_last;
+// Two arms of one key with different values: if the key was created by a record of THIS batch, the
+// lowest-index arm is the one the reference would have kept (later ones hit `case Some(_)`, :177-183);
+// if it existed before the batch, the stored value stands.  One CTA, after every arm of the batch.
+__device__ __forceinline__ void arm_resolve_conflicts(const ArmParams& P) {
+  const Geometry& g = P.g;
   __shared__ int s_min, s_any;
-  __threadfence();
-  __syncthreads();
-  if (threadIdx.x == 0) s_last = (atomicAdd(&P.st->ticket, 1u) == gridDim.x - 1);
-  __syncthreads();
-  if (!s_last) return;
-  __threadfence();
-  uint32_t nc = *(volatile uint32_t*)&P.st->n_conflicts;
-  if (threadIdx.x == 0) P.st->ticket = 0;
+  uint32_t nc = __ldcg(&P.st->n_arm_conflicts);
   if (nc == 0) return;
   if (nc > (uint32_t)kMaxConflicts) {
-    if (threadIdx.x == 0) { report_error(P.st, FPX_ERR_CONFLICT, 0); P.st->n_conflicts = 0; }
+    if (threadIdx.x == 0) { report_error(P.st, FPX_ERR_CONFLICT, 0); P.st->n_arm_conflicts = 0; }
     return;
   }
   for (uint32_t c = 0; c < nc; ++c) {
@@ -218,7 +224,26 @@ __global__ void __launch_bounds__(256) arm_kernel(ArmParams P) {
     }
     __syncthreads();
   }
-  if (threadIdx.x == 0) P.st->n_conflicts = 0;
+  if (threadIdx.x == 0) P.st->n_arm_conflicts = 0;
+}
+
+__global__ void __launch_bounds__(kArmThreads, 1) arm_kernel(ArmParams P) {
+  const int lane = threadIdx.x & 31;
+  const int max_local = arm_chunks(P, blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), gridDim.x * (blockDim.x >> 5), lane);
+  if (lane == 0 && max_local >= 0) atomicMax(&P.st->max_armed_local, max_local);
+
+  // ---- last block: conflicting arms of one key
+  __shared__ bool s_last;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();   // cumulative: orders the whole CTA's writes (barrier above) before the ticket
+    s_last = (atomicAdd(&P.st->ticket, 1u) == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  if (threadIdx.x == 0) P.st->ticket = 0;
+  arm_resolve_conflicts(P);
 }
 
 }  // namespace fpx

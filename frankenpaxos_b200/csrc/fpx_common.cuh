@@ -57,6 +57,7 @@ struct DevStatus {
   int32_t ts_min_round, ts_max_round;   // rounds carried by the batch's votes
   uint32_t ts_flags;                    // kTsBadVoter | kTsAnomaly
   uint32_t ts_path;                     // path the LAST tally launch took: 1 sweep, 2 exact (diagnostic)
+  uint32_t n_arm_conflicts;             // entries in the arm kernel's conflict list
   unsigned long long t_acceptor[8];  // %globaltimer at the phase boundaries of CTA 0 (profiling aid)
   unsigned long long t_tally[8];
 };

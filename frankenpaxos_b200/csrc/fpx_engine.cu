@@ -28,6 +28,7 @@
 using namespace fpx;
 
 constexpr int kMaxEvents = 16;
+constexpr int kTallySmem = 200 * 1024;  // dynamic shared memory of a tally CTA (one CTA of 1024 threads per SM)
 constexpr int kStepRing = 1024;
 
 struct fpx_engine {
@@ -65,7 +66,9 @@ struct fpx_engine {
   uint32_t* t_cc = nullptr;            // tally: completing votes per 1024-vote chunk
   void* t_tmp = nullptr;               // tally: Chosen records parked at their vote's index (max_batch * 8)
   int tally_path = 0;                  // 0 auto, 2 force the exact per-vote path
-  void* conflicts = nullptr;           // kMaxConflicts * 8 bytes
+  void* conflicts = nullptr;           // kMaxConflicts * 8 bytes (acceptor kernel)
+  void* arm_conflicts = nullptr;       // kMaxConflicts * 8 bytes (arm kernel)
+  uint32_t* arm_bits = nullptr;        // arm kernel: record i created its key, max_batch/32 words
   // staging for host-pointer calls
   void* d_in = nullptr;                // max_batch * 16
   void* d_out_a = nullptr;             // max_batch * 16 (p2b)
@@ -269,7 +272,7 @@ int fpx_create(fpx_engine** out, const fpx_config* cfg) {
   CKC(cudaMalloc(&e->st, sizeof(DevStatus)));
   CKC(cudaMalloc(&e->bits, (mb / 32 + 2) * 4));
   CKC(cudaMalloc(&e->g_agg, (size_t)kMaxGrid * kMaxKeys * 4));
-  CKC(cudaMalloc(&e->g_wacc, (size_t)kMaxGrid * kWarps * 4));
+  CKC(cudaMalloc(&e->g_wacc, (size_t)kMaxGrid * kAW * 4));
   CKC(cudaMalloc(&e->t_bw, (mb / kChunkVotes + 2) * 32 * 8));
   CKC(cudaMalloc(&e->t_cc, (mb / kChunkVotes + 2) * 4));
   CKC(cudaMalloc(&e->t_tmp, (mb + kChunkVotes) * 8));   // padded to a whole chunk: phase D loads unconditionally
@@ -280,20 +283,25 @@ int fpx_create(fpx_engine** out, const fpx_config* cfg) {
     if (!prop.cooperativeLaunch) return fail(FPX_ERR_UNSUPPORTED);
     e->num_sms = prop.multiProcessorCount;
     int occ = 0;
-    CKC(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, acceptor_phase2a_kernel, kThreads,
-                                                      (size_t)g.num_keys * kThreads * 4));
+    CKC(cudaFuncSetAttribute(acceptor_phase2a_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             kMaxKeys * kAT * 4));
+    CKC(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, acceptor_phase2a_kernel, kAT,
+                                                      (size_t)g.num_keys * kAT * 4));
     e->occ_acceptor = std::max(occ, 1);
     e->grid_acceptor = std::min(std::max(occ, 1) * e->num_sms, kMaxGrid);
     // the tally's dynamic shared memory: scan of the per-chunk counts (4 B per 1024 votes) + the CTA's kept
     // {vote, value} entries of the sweep (8 B per window row); one launch takes at most 40 KB of it for the scan
-    const int smem_cap = 48 * 1024;
+    const int smem_cap = kTallySmem;
     e->tally_max_sub = (40 * 1024 / 4) * kChunkVotes;
     const void* tk = tally_kernel_ptr(g.row_words);
-    CKC(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, tk, kThreads, smem_cap));
+    CKC(cudaFuncSetAttribute(tk, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_cap));
+    CKC(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, tk, kTT, smem_cap));
     e->occ_tally = std::max(occ, 1);
     e->grid_tally = std::min(std::max(occ, 1) * e->num_sms, kMaxGrid);
   }
   CKC(cudaMalloc(&e->conflicts, kMaxConflicts * 8));
+  CKC(cudaMalloc(&e->arm_conflicts, kMaxConflicts * 8));
+  CKC(cudaMalloc(&e->arm_bits, (mb / 32 + 2) * 4));
   CKC(cudaMalloc(&e->d_in, mb * 16));
   CKC(cudaMalloc(&e->d_out_a, mb * 16));
   CKC(cudaMalloc(&e->d_out_b, mb * 8));
@@ -315,13 +323,13 @@ void fpx_destroy(fpx_engine* e) {
   cudaFree(e->acc_round); cudaFree(e->acc_max_voted); cudaFree(e->rlog); cudaFree(e->vm_claim); cudaFree(e->st);
   cudaFree(e->rng_tab); cudaFree(e->rng_dec);
   if (e->step_ev) {
-    for (int i = 0; i < kStepRing * 3; ++i) cudaEventDestroy(e->step_ev[i]);
+    for (int i = 0; i < kStepRing * 4; ++i) cudaEventDestroy(e->step_ev[i]);
     delete[] e->step_ev;
   }
   for (fpx_engine::WireBuf* b : {&e->w_bytes, &e->w_offs, &e->w_kind, &e->w_rec, &e->w_out, &e->w_tiles, &e->w_arena,
                                  &e->w_voffs})
     cudaFree(b->p);
-  cudaFree(e->bits); cudaFree(e->g_agg); cudaFree(e->g_wacc); cudaFree(e->t_bw); cudaFree(e->t_cc); cudaFree(e->t_tmp); cudaFree(e->conflicts);
+  cudaFree(e->bits); cudaFree(e->g_agg); cudaFree(e->g_wacc); cudaFree(e->t_bw); cudaFree(e->t_cc); cudaFree(e->t_tmp); cudaFree(e->conflicts); cudaFree(e->arm_conflicts); cudaFree(e->arm_bits);
   cudaFree(e->d_in); cudaFree(e->d_out_a); cudaFree(e->d_out_b);
   if (e->h_st) cudaFreeHost(e->h_st);
   for (int i = 0; i < kMaxEvents; ++i) if (e->ev[i]) cudaEventDestroy(e->ev[i]);
@@ -380,23 +388,28 @@ static int check_n(fpx_engine* e, const void* p, int32_t n) {
   return FPX_OK;
 }
 
-static int arm_launch(fpx_engine* e, const fpx_p2a* d_in, int32_t n, int vanilla) {
-  int c = check_n(e, d_in, n);
-  if (c != FPX_OK || n == 0) return c;
+static ArmParams arm_params(fpx_engine* e, const fpx_p2a* d_in, int32_t n, int vanilla) {
   ArmParams P;
   P.g = e->g;
   P.pl = PLState{e->rows, e->ovf_keys, e->ovf_rows};
   P.in = (const int4*)d_in;
   P.n = n;
   P.st = e->st;
-  P.conflicts = (ArmConflict*)e->conflicts;
-  P.win_bits = e->bits;
+  P.conflicts = (ArmConflict*)e->arm_conflicts;
+  P.win_bits = e->arm_bits;
   P.votes = e->votes;
   P.vanilla = vanilla;
   P.rng = RangeTable{e->rng_tab, (uint32_t)e->rng_cap - 1u, e->rng_cap};
   P.check_rng = e->unit_ranges;
-  int arm_blocks = std::min((n + 256 * kArmUnroll - 1) / (256 * kArmUnroll), e->num_sms * 8);
-  arm_kernel<<<arm_blocks, 256, 0, e->stream>>>(P);
+  return P;
+}
+
+static int arm_launch(fpx_engine* e, const fpx_p2a* d_in, int32_t n, int vanilla) {
+  int c = check_n(e, d_in, n);
+  if (c != FPX_OK || n == 0) return c;
+  ArmParams P = arm_params(e, d_in, n, vanilla);
+  int arm_blocks = std::min((n + kArmThreads * kArmUnroll - 1) / (kArmThreads * kArmUnroll), e->num_sms);
+  arm_kernel<<<arm_blocks, kArmThreads, 0, e->stream>>>(P);
   e->launches++;
   CK(e, cudaGetLastError());
   return FPX_OK;
@@ -439,27 +452,34 @@ static int acceptor_launch(fpx_engine* e, const fpx_p2a* d_in, int32_t n, fpx_p2
   P.g_wacc = e->g_wacc;
   P.st = e->st;
   P.conflicts = (VoteConflict*)e->conflicts;
-  int grid = std::max(1, std::min(e->grid_acceptor, (n + kThreads - 1) / kThreads));
+  int grid = std::max(1, std::min(e->grid_acceptor, (n + kAT - 1) / kAT));
   P.parity = e->parity;
   P.append = append;
   P.demote = (e->tally_path & 64) ? 1 : 0;
   e->parity ^= 1u;
   void* args[] = {&P};
-  CK(e, cudaLaunchCooperativeKernel((const void*)acceptor_phase2a_kernel, dim3(grid), dim3(kThreads), args,
-                                    (size_t)e->g.num_keys * kThreads * 4, stream));
+  CK(e, cudaLaunchCooperativeKernel((const void*)acceptor_phase2a_kernel, dim3(grid), dim3(kAT), args,
+                                    (size_t)e->g.num_keys * kAT * 4, stream));
   e->launches++;
   CK(e, cudaGetLastError());
   return FPX_OK;
 }
 
-int fpx_proxyleader_phase2b_dev(fpx_engine* e, const fpx_p2b* d_in, int32_t n, fpx_chosen* d_out) {
+static int renormalize_rlog_if_needed(fpx_engine* e, int32_t bound);
+
+// fuse: 0 = the proxy leader alone; 1 = + the co-located replica's handleChosen and watermark (fpx_step_dev)
+static int tally_launch(fpx_engine* e, const fpx_p2b* d_in, int32_t n, fpx_chosen* d_out, int fuse, int32_t* d_wm) {
   int c = check_n(e, d_in, n);
   if (c != FPX_OK) return c;
   if (n > 0 && !d_out) return FPX_ERR_INVALID_ARG;
   e->last_p2b_n = n;
   if (n == 0) {
     CK(e, cudaMemsetAsync(&e->st->n_chosen, 0, 4, e->stream));
-    return FPX_OK;
+    return fuse ? fpx_chosen_watermark_dev(e, d_wm) : FPX_OK;
+  }
+  if (fuse) {
+    c = renormalize_rlog_if_needed(e, 2 * n > n ? 2 * n : n);
+    if (c != FPX_OK) return c;
   }
   if (e->seq_base > 0xffffffffu - (uint32_t)n - 16u) {
     size_t nrows = (size_t)e->g.local_slots;
@@ -473,7 +493,7 @@ int fpx_proxyleader_phase2b_dev(fpx_engine* e, const fpx_p2b* d_in, int32_t n, f
   const void* tk = tally_kernel_ptr(e->g.row_words);
   for (int32_t done = 0; done < n;) {
     int32_t sub = std::min(n - done, e->tally_max_sub);
-    int grid = std::max(1, std::min(e->grid_tally, (sub + kThreads - 1) / kThreads));
+    int grid = std::max(1, std::min(e->grid_tally, (sub + kTT - 1) / kTT));
     TallyParams P;
     P.g = e->g;
     P.pl = PLState{e->rows, e->ovf_keys, e->ovf_rows};
@@ -487,28 +507,44 @@ int fpx_proxyleader_phase2b_dev(fpx_engine* e, const fpx_p2b* d_in, int32_t n, f
     P.first = done == 0;
     P.path = e->tally_path;
     P.votes = e->votes;
+    P.rlog = fuse ? e->rlog : nullptr;
+    P.rseq_base = e->rseq_base + (uint32_t)done;   // later sub-launches number their records after earlier ones
+    P.fuse_watermark = fuse && done + sub == n;
+    P.d_watermark = d_wm;
     P.st = e->st;
     e->seq_base += (uint32_t)sub;
     void* args[] = {&P};
     const int nchunks = (sub + kChunkVotes - 1) / kChunkVotes;
-    const size_t smem = 48 * 1024;
+    const size_t smem = kTallySmem;
     P.keep_cap = (int)((smem - (size_t)((nchunks + 1) & ~1) * 4) / 8);
-    CK(e, cudaLaunchCooperativeKernel(tk, dim3(grid), dim3(kThreads), args, smem, e->stream));
+    CK(e, cudaLaunchCooperativeKernel(tk, dim3(grid), dim3(kTT), args, smem, e->stream));
     e->launches++;
     done += sub;
   }
+  if (fuse) e->rseq_base += 2u * (uint32_t)n;  // numbers used: below rseq_base + done + sub <= rseq_base + 2n
   CK(e, cudaGetLastError());
   return FPX_OK;
 }
 
-static int replica_launch(fpx_engine* e, const fpx_chosen* d_in, int32_t n, int32_t bound) {
-  if (bound == 0) return FPX_OK;
+int fpx_proxyleader_phase2b_dev(fpx_engine* e, const fpx_p2b* d_in, int32_t n, fpx_chosen* d_out) {
+  return tally_launch(e, d_in, n, d_out, 0, nullptr);
+}
+
+static int renormalize_rlog_if_needed(fpx_engine* e, int32_t bound) {
   if (e->rseq_base > 0xffffffffu - (uint32_t)bound - 16u) {
     size_t nl = (size_t)e->g.local_slots;
     renormalize_rlog_kernel<<<(unsigned)((nl + 255) / 256), 256, 0, e->stream>>>(e->rlog, nl);
     e->launches++;
     e->rseq_base = 1;
+    CK(e, cudaGetLastError());
   }
+  return FPX_OK;
+}
+
+static int replica_launch(fpx_engine* e, const fpx_chosen* d_in, int32_t n, int32_t bound) {
+  if (bound == 0) return FPX_OK;
+  int rc = renormalize_rlog_if_needed(e, bound);
+  if (rc != FPX_OK) return rc;
   ReplicaParams P;
   P.g = e->g;
   P.in = (const int2*)d_in;
@@ -550,32 +586,35 @@ int fpx_step_dev(fpx_engine* e, const fpx_p2a* d_arm, int32_t n_arm, const fpx_p
   cudaEvent_t* ev = nullptr;
   if (ring_slot >= 0) {
     if (!e->step_ev) {
-      e->step_ev = new (std::nothrow) cudaEvent_t[kStepRing * 3];
+      e->step_ev = new (std::nothrow) cudaEvent_t[kStepRing * 4];
       if (!e->step_ev) return FPX_ERR_INVALID_ARG;
-      for (int i = 0; i < kStepRing * 3; ++i) CK(e, cudaEventCreate(&e->step_ev[i]));
+      for (int i = 0; i < kStepRing * 4; ++i) CK(e, cudaEventCreate(&e->step_ev[i]));
     }
-    ev = e->step_ev + (size_t)(ring_slot % kStepRing) * 3;
+    ev = e->step_ev + (size_t)(ring_slot % kStepRing) * 4;
   }
-  int c = fpx_proxyleader_arm_dev(e, d_arm, n_arm);
-  if (c != FPX_OK) return c;
+  // The arm batch and the acceptor batch touch disjoint state (proxy-leader rows / vote cells), so their
+  // order is free; the acceptors go first so that the rows armed last are still L2-resident when the
+  // votes are tallied.  The co-located replica (handleChosen + watermark) rides in the tally kernel.
+  // (Running the arm batch inside the acceptor kernel was tried and lost: profiles/experiments.md.)
   if (ev) CK(e, cudaEventRecord(ev[0], e->stream));
-  c = fpx_acceptor_phase2a_dev(e, d_p2a, n_p2a, d_out_p2b, d_out_nack);
+  int c = fpx_acceptor_phase2a_dev(e, d_p2a, n_p2a, d_out_p2b, d_out_nack);
   if (c != FPX_OK) return c;
   if (ev) CK(e, cudaEventRecord(ev[1], e->stream));
-  c = fpx_proxyleader_phase2b_dev(e, d_p2b, n_p2b, d_out_chosen);
+  c = fpx_proxyleader_arm_dev(e, d_arm, n_arm);
   if (c != FPX_OK) return c;
   if (ev) CK(e, cudaEventRecord(ev[2], e->stream));
-  c = fpx_replica_chosen_last_dev(e, d_out_chosen);
+  c = tally_launch(e, d_p2b, n_p2b, d_out_chosen, 1, d_watermark);
   if (c != FPX_OK) return c;
-  return fpx_chosen_watermark_dev(e, d_watermark);
+  if (ev) CK(e, cudaEventRecord(ev[3], e->stream));
+  return FPX_OK;
 }
 
 int fpx_step_kernel_ms(fpx_engine* e, int32_t ring_slot, float* acceptor_ms, float* tally_ms) {
   if (!e || !e->step_ev || ring_slot < 0 || !acceptor_ms || !tally_ms) return FPX_ERR_INVALID_ARG;
-  cudaEvent_t* ev = e->step_ev + (size_t)(ring_slot % kStepRing) * 3;
-  CK(e, cudaEventSynchronize(ev[2]));
+  cudaEvent_t* ev = e->step_ev + (size_t)(ring_slot % kStepRing) * 4;
+  CK(e, cudaEventSynchronize(ev[3]));
   CK(e, cudaEventElapsedTime(acceptor_ms, ev[0], ev[1]));
-  CK(e, cudaEventElapsedTime(tally_ms, ev[1], ev[2]));
+  CK(e, cudaEventElapsedTime(tally_ms, ev[2], ev[3]));
   return FPX_OK;
 }
 

@@ -69,12 +69,22 @@ struct TallyParams {
   int32_t path;            // 0: sweep when sound; 2: always the exact per-vote path (tests, A/B); 4: profiling, no REDs
   int32_t keep_cap;        // rows of the window one CTA can keep in shared memory between phases B and D
   unsigned long long* votes;  // vanilla Mencius: the coordinator's log entry turns ChosenEntry on completion
+  // fpx_step_dev: the co-located replica's handleChosen (+ executeLog's prefix rule) applied to the Chosen
+  // stream as it is emitted (fpx_replica_misc.cuh), instead of two more launches
+  unsigned long long* rlog;   // non-null: Replica.handleChosen on every emitted record
+  uint32_t rseq_base;         // delivery sequence number of this call's first Chosen record
+  int32_t fuse_watermark;     // 1: also the first-hole scan (last sub-launch of a call)
+  int32_t* d_watermark;       // optional device copy of the new watermark
   DevStatus* st;
 };
 
 constexpr int kTallyUnroll = 4;   // chunks of 32 votes per warp per pipeline stage in phase A
 constexpr int kChunkVotes = 1024; // votes per rank chunk (one bitmap word per lane)
 constexpr uint32_t kNoVote = 0xffffffffu;
+// One CTA of 32 warps per SM: several CTAs per SM spread up to 2x in duration (their loads queue behind
+// each other in the SM's L1TEX, B300_MICROARCH "Multi-CTA spread"), and every phase ends at a grid barrier.
+constexpr int kTT = 1024;
+constexpr int kTW = kTT / 32;
 
 // One proxy-leader row from L2 with a single 256-bit load per 8 words (LDG.E.256, sm_100+).
 template <int ROWW>
@@ -137,6 +147,17 @@ __device__ __forceinline__ bool row_completion(const TallyParams& P, const uint3
   return true;
 }
 
+// One record of the Chosen stream at position `pos` of this call's output; with a co-located replica
+// also Replica.handleChosen: the first Chosen of a slot wins (S/multipaxos/Replica.scala:580-588)
+template <bool kReplica>
+__device__ __forceinline__ void emit_chosen(const TallyParams& P, uint32_t pos, int slot, int local, int value, int& mx) {
+  st_stream2(P.out_chosen + pos, make_int2(slot, value));
+  if (kReplica && P.rlog != nullptr) {
+    red_min_u64(&P.rlog[local], ((unsigned long long)(P.rseq_base + pos) << 32) | (uint32_t)value);
+    mx = max(mx, local);
+  }
+}
+
 // rank(i): completing votes of the batch before vote i (phase D)
 __device__ __forceinline__ uint32_t vote_rank(const TallyParams& P, const uint32_t* s_ccx, uint32_t i) {
   const uint2 wd = __ldcg(&P.bw[i >> 5]);
@@ -148,33 +169,42 @@ __device__ __forceinline__ uint32_t vote_rank(const TallyParams& P, const uint32
 // (phase D without kept entries): recompute and emit.
 template <int ROWW, bool kEmit>
 __device__ __forceinline__ void tally_sweep(const TallyParams& P, int w_lo, int w_hi, int R, int rows_per_cta, bool keep,
-                                            uint2* s_keep, const uint32_t* s_ccx, uint32_t out_base) {
+                                            uint2* s_keep, const uint32_t* s_ccx, uint32_t out_base, int& mx) {
   constexpr int U = ROWW == 8 ? 4 : (ROWW == 16 ? 2 : 1);
   const Geometry& g = P.g;
   const long long nrows = (long long)w_hi - w_lo + 1;
   const long long r_begin = (long long)blockIdx.x * rows_per_cta;
   const long long r_end = min(nrows, r_begin + rows_per_cta);
   bool ok = true;
-  for (long long r0 = r_begin + threadIdx.x; r0 < r_end; r0 += (long long)kThreads * U) {
+  for (long long r0 = r_begin + threadIdx.x; r0 < r_end; r0 += (long long)kTT * U) {
     uint32_t w[U][ROWW];
 #pragma unroll
     for (int u = 0; u < U; ++u) {
-      const long long r = r0 + u * kThreads;
+      const long long r = r0 + u * kTT;
       if (r < r_end) load_row<ROWW>(P.pl.rows + (size_t)(w_lo + r) * ROWW, w[u]);
     }
 #pragma unroll
     for (int u = 0; u < U; ++u) {
-      const long long r = r0 + u * kThreads;
+      const long long r = r0 + u * kTT;
       if (r >= r_end) continue;
       uint32_t i;
       ok &= row_completion<ROWW>(P, w[u], R, &i);
       if (!kEmit) {
-        if (i != kNoVote) red_or_u32(&P.bw[i >> 5].x, 1u << (i & 31));
+        if (i != kNoVote) {
+          red_or_u32(&P.bw[i >> 5].x, 1u << (i & 31));
+          if (P.rlog != nullptr) {
+            // co-located replica (Replica.scala:580-588), here rather than at emission: consecutive threads
+            // hold consecutive log entries.  Sound in a sweep: one round per batch = at most one Chosen per
+            // slot in this call, so only earlier calls can have the slot, and their numbers are smaller.
+            red_min_u64(&P.rlog[w_lo + r], ((unsigned long long)(P.rseq_base + i) << 32) | w[u][1]);
+            mx = max(mx, (int)(w_lo + r));
+          }
+        }
         if (keep) s_keep[r - r_begin] = make_uint2(i, w[u][1]);
       } else if (i != kNoVote) {
         // Chosen(slot, pending.phase2a.value) (:249-251) at its place in the order of the completing votes
-        st_stream2(P.out_chosen + out_base + vote_rank(P, s_ccx, i),
-                   make_int2((int)(w_lo + r) * g.shard_count + g.shard_index, (int)w[u][1]));
+        emit_chosen<false>(P, out_base + vote_rank(P, s_ccx, i), (int)(w_lo + r) * g.shard_count + g.shard_index,
+                           (int)(w_lo + r), (int)w[u][1], mx);
       }
     }
   }
@@ -288,18 +318,18 @@ __device__ __forceinline__ void tally_exact(const TallyParams& P, int wlo, int w
 }
 
 template <int ROWW>
-__global__ void __launch_bounds__(kThreads, ROWW == 8 ? 4 : (ROWW == 16 ? 2 : 1)) tally_kernel(TallyParams P) {
+__global__ void __launch_bounds__(kTT, 1) tally_kernel(TallyParams P) {
   const Geometry& g = P.g;
   extern __shared__ uint32_t s_dyn[];  // [nchunks] exclusive scan of the chunk counts, then [keep_cap] kept {vote, value}
-  __shared__ int s_red[4][kWarps];
+  __shared__ int s_red[4][kTW];
   __shared__ uint32_t s_flags;
-  __shared__ uint32_t s_scan[kWarps];
+  __shared__ uint32_t s_scan[kTW];
 
   const unsigned full = 0xffffffffu;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int per = warp_range_len(P.n);
-  const int gw = blockIdx.x * kWarps + warp;
-  const int total_warps = gridDim.x * kWarps;
+  const int total_warps = gridDim.x * kTW;
+  const int per = (((P.n + total_warps - 1) / total_warps) + 31) & ~31;   // votes per warp: contiguous ranges
+  const int gw = blockIdx.x * kTW + warp;
   const int wlo = (int)min((long long)P.n, (long long)gw * per);
   const int whi = (int)min((long long)P.n, (long long)wlo + per);
   const bool vanilla = g.protocol == FPX_VANILLA_MENCIUS;
@@ -307,10 +337,11 @@ __global__ void __launch_bounds__(kThreads, ROWW == 8 ? 4 : (ROWW == 16 ? 2 : 1)
   uint32_t* const s_ccx = s_dyn;
   uint2* const s_keep = (uint2*)(s_dyn + ((nchunks + 1) & ~1));
   const uint32_t out_base = P.first ? 0u : (uint32_t)__ldcg(&P.st->n_chosen);   // rewritten only after the last barrier
+  int mx_local = INT_MIN;   // co-located replica: largest local slot this thread put into the log
 
   // ---- phase A: clear the bitmap, first-delivery stamps, batch statistics
   FPX_MARK(P.st->t_tally, 0);
-  for (int wd = blockIdx.x * kThreads + tid; wd < nchunks * 32; wd += gridDim.x * kThreads)
+  for (int wd = blockIdx.x * kTT + tid; wd < nchunks * 32; wd += gridDim.x * kTT)
     __stcg(&P.bw[wd], make_uint2(0u, 0u));
   int lo = INT_MAX, hi = -1, rmin = INT_MAX, rmax = INT_MIN;
   uint32_t flags = 0;
@@ -394,8 +425,8 @@ __global__ void __launch_bounds__(kThreads, ROWW == 8 ? 4 : (ROWW == 16 ? 2 : 1)
     if (lane == 0 && flags) atomicOr(&s_flags, flags);
     __syncthreads();
     if (warp == 0) {
-      lo = lane < kWarps ? s_red[0][lane] : INT_MAX; hi = lane < kWarps ? s_red[1][lane] : -1;
-      rmin = lane < kWarps ? s_red[2][lane] : INT_MAX; rmax = lane < kWarps ? s_red[3][lane] : INT_MIN;
+      lo = lane < kTW ? s_red[0][lane] : INT_MAX; hi = lane < kTW ? s_red[1][lane] : -1;
+      rmin = lane < kTW ? s_red[2][lane] : INT_MAX; rmax = lane < kTW ? s_red[3][lane] : INT_MIN;
       lo = __reduce_min_sync(full, lo); hi = __reduce_max_sync(full, hi);
       rmin = __reduce_min_sync(full, rmin); rmax = __reduce_max_sync(full, rmax);
       if (lane == 0 && hi >= 0) {
@@ -415,16 +446,16 @@ __global__ void __launch_bounds__(kThreads, ROWW == 8 ? 4 : (ROWW == 16 ? 2 : 1)
   bool sweep = !(P.path & 2) && !vanilla && __ldcg(&P.st->ts_flags) == 0 && w_hi >= w_lo &&
                R == __ldcg(&P.st->ts_max_round) && (long long)w_hi - w_lo <= 4ll * P.n + 4096;
   // every CTA sweeps a contiguous run of the window's rows (a multiple of the CTA size)
-  const int rows_per_cta = sweep ? (int)((((long long)w_hi - w_lo + gridDim.x) / gridDim.x + kThreads - 1) / kThreads) * kThreads : 0;
+  const int rows_per_cta = sweep ? (int)((((long long)w_hi - w_lo + gridDim.x) / gridDim.x + kTT - 1) / kTT) * kTT : 0;
   const bool keep = rows_per_cta <= P.keep_cap;
   if (sweep) {
-    tally_sweep<ROWW, false>(P, w_lo, w_hi, R, rows_per_cta, keep, s_keep, s_ccx, out_base);
+    tally_sweep<ROWW, false>(P, w_lo, w_hi, R, rows_per_cta, keep, s_keep, s_ccx, out_base, mx_local);
     FPX_MARK(P.st->t_tally, 3);
     grid_sync(P.st);
     if (__ldcg(&P.st->ts_flags) & kTsAnomaly) {
       // not a steady-state batch after all: forget the sweep's marks, evaluate every vote
       sweep = false;
-      for (int wd = blockIdx.x * kThreads + tid; wd < nchunks * 32; wd += gridDim.x * kThreads)
+      for (int wd = blockIdx.x * kTT + tid; wd < nchunks * 32; wd += gridDim.x * kTT)
         __stcg(&P.bw[wd], make_uint2(0u, 0u));
       grid_sync(P.st);
     }
@@ -462,9 +493,9 @@ __global__ void __launch_bounds__(kThreads, ROWW == 8 ? 4 : (ROWW == 16 ? 2 : 1)
   //      Chosen stream in the order of the completing votes
   {
     // coalesced copy of the counts, then a blocked scan in place: thread t owns chunks [t*per_t, (t+1)*per_t)
-    for (int k = tid; k < nchunks; k += kThreads) s_ccx[k] = __ldcg(&P.cc[k]);
+    for (int k = tid; k < nchunks; k += kTT) s_ccx[k] = __ldcg(&P.cc[k]);
     __syncthreads();
-    const int per_t = (nchunks + kThreads - 1) / kThreads;
+    const int per_t = (nchunks + kTT - 1) / kTT;
     const int c0 = min(nchunks, tid * per_t), c1 = min(nchunks, c0 + per_t);
     uint32_t sum = 0;
     for (int k = c0; k < c1; ++k) sum += s_ccx[k];
@@ -478,24 +509,24 @@ __global__ void __launch_bounds__(kThreads, ROWW == 8 ? 4 : (ROWW == 16 ? 2 : 1)
     __syncthreads();
     uint32_t run = incl - sum;
 #pragma unroll
-    for (int wv = 0; wv < kWarps; ++wv) if (wv < warp) run += s_scan[wv];
+    for (int wv = 0; wv < kTW; ++wv) if (wv < warp) run += s_scan[wv];
     for (int k = c0; k < c1; ++k) { uint32_t c = s_ccx[k]; s_ccx[k] = run; run += c; }
     __syncthreads();
     uint32_t total = 0;
 #pragma unroll
-    for (int wv = 0; wv < kWarps; ++wv) total += s_scan[wv];
+    for (int wv = 0; wv < kTW; ++wv) total += s_scan[wv];
 
     if (sweep && keep) {
       // the CTA's kept {vote, value} entries: one random 8-byte load (word + prefix), one 8-byte store each
       const long long nrows = (long long)w_hi - w_lo + 1;
       const long long r_begin = (long long)blockIdx.x * rows_per_cta;
       const int mine = (int)max(0ll, min(nrows, r_begin + rows_per_cta) - r_begin);
-      for (int e0 = tid; e0 < mine; e0 += kThreads * 4) {
+      for (int e0 = tid; e0 < mine; e0 += kTT * 4) {
         uint2 ent[4];
         uint2 wd[4];
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
-          const int e = e0 + u * kThreads;
+          const int e = e0 + u * kTT;
           ent[u] = e < mine ? s_keep[e] : make_uint2(kNoVote, 0u);
           if (ent[u].x != kNoVote) wd[u] = __ldcg(&P.bw[ent[u].x >> 5]);
         }
@@ -504,13 +535,13 @@ __global__ void __launch_bounds__(kThreads, ROWW == 8 ? 4 : (ROWW == 16 ? 2 : 1)
           if (ent[u].x == kNoVote) continue;
           const uint32_t i = ent[u].x;
           const uint32_t rank = s_ccx[i >> 10] + wd[u].y + __popc(wd[u].x & ((1u << (i & 31)) - 1u));
-          const int e = e0 + u * kThreads;
-          st_stream2(P.out_chosen + out_base + rank,
-                     make_int2((int)(w_lo + r_begin + e) * g.shard_count + g.shard_index, (int)ent[u].y));
+          const int e = e0 + u * kTT;
+          const int local = (int)(w_lo + r_begin + e);
+          emit_chosen<false>(P, out_base + rank, local * g.shard_count + g.shard_index, local, (int)ent[u].y, mx_local);
         }
       }
     } else if (sweep) {
-      tally_sweep<ROWW, true>(P, w_lo, w_hi, R, rows_per_cta, false, s_keep, s_ccx, out_base);
+      tally_sweep<ROWW, true>(P, w_lo, w_hi, R, rows_per_cta, false, s_keep, s_ccx, out_base, mx_local);
     } else {
       for (int k = gw; k < nchunks; k += total_warps) {
         const uint2 wd = __ldcg(&P.bw[k * 32 + lane]);
@@ -527,7 +558,8 @@ __global__ void __launch_bounds__(kThreads, ROWW == 8 ? 4 : (ROWW == 16 ? 2 : 1)
           for (int j = 0; j < 8; ++j) {
             const uint32_t wv = __shfl_sync(full, wd.x, s0 + j);
             const uint32_t pre = __shfl_sync(full, wpre, s0 + j);
-            if ((wv >> lane) & 1u) st_stream2(P.out_chosen + pre + __popc(wv & lanemask_lt()), rec[j]);
+            if ((wv >> lane) & 1u)
+              emit_chosen<true>(P, pre + __popc(wv & lanemask_lt()), rec[j].x, local_slot(g, rec[j].x), rec[j].y, mx_local);
           }
         }
       }
@@ -539,6 +571,53 @@ __global__ void __launch_bounds__(kThreads, ROWW == 8 ? 4 : (ROWW == 16 ? 2 : 1)
       P.st->ts_min_round = INT_MAX; P.st->ts_max_round = INT_MIN;
       P.st->ts_flags = 0;
       P.st->ts_path = sweep ? 1u : 2u;
+    }
+  }
+  FPX_MARK(P.st->t_tally, 7);
+  if (P.rlog == nullptr) return;
+
+  // ---- co-located replica: largest chosen slot, then executeLog's prefix rule (Replica.scala:394-402):
+  //      the first hole at or after the old watermark
+  mx_local = __reduce_max_sync(full, mx_local);
+  if (lane == 0) s_red[0][warp] = mx_local;
+  __syncthreads();
+  if (warp == 0) {
+    int m = __reduce_max_sync(full, s_red[0][lane]);
+    if (lane == 0 && m != INT_MIN) atomicMax(&P.st->max_chosen_local, m);
+  }
+  if (!P.fuse_watermark) return;
+  grid_sync(P.st);
+  {
+    const int lo_w = __ldcg(&P.st->wm_local);
+    const int hi_w = min(__ldcg(&P.st->max_chosen_local) + 2, g.local_slots);  // one past the last candidate hole
+    int found = INT_MAX;
+    const long long stride = (long long)gridDim.x * kTT;
+    for (long long i = lo_w + (long long)blockIdx.x * kTT + tid; i < hi_w && found == INT_MAX; i += 4 * stride) {
+      unsigned long long v[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) v[u] = (i + u * stride < hi_w) ? __ldcg(&P.rlog[i + u * stride]) : 0ull;
+#pragma unroll
+      for (int u = 3; u >= 0; --u)
+        if (i + u * stride < hi_w && v[u] == kU64Empty) found = (int)(i + u * stride);   // ascending: the smallest one last
+    }
+    found = __reduce_min_sync(full, found);
+    __syncthreads();
+    if (lane == 0) s_red[1][warp] = found;
+    __syncthreads();
+    if (warp == 0) {
+      found = __reduce_min_sync(full, s_red[1][lane]);
+      if (lane == 0 && found != INT_MAX) atomicMin(&P.st->wm_found, found);
+    }
+    grid_sync(P.st);
+    if (blockIdx.x == 0 && tid == 0) {
+      int f = min(__ldcg(&P.st->wm_found), hi_w);
+      f = max(f, lo_w);
+      if (f > g.local_slots) f = g.local_slots;
+      P.st->wm_local = f;
+      P.st->wm_found = INT_MAX;
+      const int global = f * g.shard_count + g.shard_index;
+      P.st->watermark = global;
+      if (P.d_watermark) *P.d_watermark = global;
     }
   }
   FPX_MARK(P.st->t_tally, 7);

@@ -327,7 +327,8 @@ class Engine:
         self._check(self._L.fpx_chosen_watermark_dev(self.h, d_out))
 
     def step_dev(self, d_arm, n_arm, d_p2a, n_p2a, d_out_p2b, d_out_nack, d_p2b, n_p2b, d_out_chosen, d_wm, ring_slot=-1):
-        """arm -> acceptor -> tally -> replica (count from the device) -> watermark, one C call."""
+        """One step of the co-located roles in one C call: acceptor batch, arm batch (disjoint state: order
+        free), then the tally with the replica's handleChosen and the watermark scan fused into it."""
         self._check(self._L.fpx_step_dev(self.h, d_arm, n_arm, d_p2a, n_p2a, d_out_p2b, d_out_nack, d_p2b, n_p2b,
                                          d_out_chosen, d_wm, ring_slot))
 

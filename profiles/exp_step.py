@@ -75,22 +75,48 @@ for variant in args.variants.split(","):
         elif which == "replica": eng.replica_chosen_last_dev(outc.data_ptr())
         else: eng.chosen_watermark_dev(wm.data_ptr())
 
+    fused = "step" in variant.split("_")
+    noev = "noev" in variant.split("_")
+    import time
+    t_host0 = time.perf_counter()
     for s in range(S):
-        evs[s][0].record(ext)
+        if s == 3 or not noev:
+            evs[s][0].record(ext)
+        if fused and noev:
+            da, dp, db = ins[s]
+            eng.step_dev(da.data_ptr(), n, dp.data_ptr(), 3 * n, outp.data_ptr(), outn.data_ptr(), db.data_ptr(), 3 * n,
+                         outc.data_ptr(), wm.data_ptr(), ring_slot=-1)
+            if s == S - 1:
+                evs[s][5].record(ext)
+            continue
+        if fused:                      # fpx_step_dev: acceptor, arm, tally + replica + watermark in one kernel
+            da, dp, db = ins[s]
+            eng.step_dev(da.data_ptr(), n, dp.data_ptr(), 3 * n, outp.data_ptr(), outn.data_ptr(), db.data_ptr(), 3 * n,
+                         outc.data_ptr(), wm.data_ptr(), ring_slot=s)
+            for j in range(5):
+                evs[s][j + 1].record(ext)
+            continue
         for j, which in enumerate(order):
             run(which, s)
             evs[s][j + 1].record(ext)
+    t_host = (time.perf_counter() - t_host0) / S * 1e6
     r = eng.sync()
     if "nored" not in variant:
         assert r.status == 0 and r.n_chosen == n and r.watermark == S * n, (r.status, r.n_chosen, r.watermark)
-    per = {which: float(np.mean([evs[s][j].elapsed_time(evs[s][j + 1]) for s in range(3, S)])) * 1e3
-           for j, which in enumerate(order)}
     step = evs[3][0].elapsed_time(evs[S - 1][5]) * 1e3 / (S - 3)
+    per = {} if noev else {which: float(np.mean([evs[s][j].elapsed_time(evs[s][j + 1]) for s in range(3, S)])) * 1e3
+                           for j, which in enumerate(order)}
+    if noev:
+        per = {}
+    elif fused:
+        ms = np.array([eng.step_kernel_ms(s) for s in range(3, S)])
+        per = {"acceptor": float(ms[:, 0].mean()) * 1e3, "tally+replica+wm": float(ms[:, 1].mean()) * 1e3}
+        per["arm"] = step - sum(per.values())
     ta = (ctypes.c_ulonglong * 8)(); tt = (ctypes.c_ulonglong * 8)()
     L.fpx_debug_phase_times(eng.h, ta, tt)
     tt = np.array(tt[:8], dtype=np.int64)
     ta = np.array(ta[:6], dtype=np.int64)
-    res = {"step_us": step, "kernels_us": per, "sum_kernels_us": sum(per.values()),
+    res = {"step_us": step, "host_enqueue_us_per_step": t_host, "kernels_us": per, "sum_kernels_us": sum(per.values()),
            "tally_path": "r1" if args.old_lib else eng.last_tally_path,
            "tally_phases_us(A,bar,B,bar,C,bar,D)": (np.diff(tt) / 1e3).round(1).tolist(),
            "acceptor_phases_us(p1,bar,carry,p2,bar)": (np.diff(ta) / 1e3).round(1).tolist()}
