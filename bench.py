@@ -4,14 +4,17 @@
 Workload (BASELINE.json configs[1], "cfg2"): MultiPaxos, 5 acceptors (f=2),
 thrifty quorum of 3, 2^20 slots in flight per GPU per step.  One STEP is one
 pass of the hot path over one window of 2^20 fresh slots:
-    arm 2^20 (slot, round)  ->  3*2^20 Phase2a at the acceptors (ballot CAS +
-    vote cells + Phase2b stream)  ->  3*2^20 shuffled Phase2b at the proxy leader
-    (tally + quorum check + ordered Chosen stream)  ->  replica log + chosen
-    watermark (+ NCCL all-gather of the per-GPU watermark when N > 1).
+    3*2^20 Phase2a at the acceptors (ballot CAS + vote cells + Phase2b stream),
+    arm 2^20 (slot, round) at the proxy leader  ->  3*2^20 shuffled Phase2b at
+    the proxy leader (tally + quorum check + ordered Chosen stream) with the
+    co-located replica's log + chosen watermark in the same launch (+ when N > 1
+    the new frontier stored into every peer GPU's table over NVLink by that
+    kernel: fpx_exchange_*).  One C call per step: fpx_step_dev.
 `value` times K steps with every input already resident in HBM (distinct
 buffers per step, > L2 in total, fresh state region per step);
-`e2e` times the same K steps through the host-pointer C ABI from pinned host
-buffers (H2D of every input, D2H of the Phase2b and Chosen replies).
+`e2e` times steps through the asynchronous host-pointer C ABI (fpx_step_submit /
+fpx_step_wait) from pinned host buffers: H2D of the Phase2a and Phase2b batches,
+D2H of the Phase2b and Chosen replies, double-buffered.
 
   python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
   python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...
@@ -37,6 +40,7 @@ Q = CFG["f"] + 1
 #   tally kernels    16Q+24 = read 16Q (Phase2b) + 8+8 slot state RMW + write 8 (Chosen)
 B_ACCEPTOR = 40 * Q
 B_TALLY = 16 * Q + 24
+B_TALLY_FUSED = B_TALLY + 8 + 8   # + the co-located replica: log put (8) and first-hole scan (8)
 B_SLOT = B_ACCEPTOR + B_TALLY
 N_BASE = 4  # distinct base traces; step s uses base s % N_BASE re-based onto its own slot window
 
@@ -60,14 +64,15 @@ def parse():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--cpu-sample-slots", type=int, default=SLOTS_PER_STEP)
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-extra", action="store_true", help="skip the extra keys (cfg5 on the same GPUs)")
     return ap.parse_args()
 
 
 def ncu_traffic(kernel):
     """dram__bytes_read.sum + dram__bytes_write.sum per launch of `kernel`, from the
-    committed ncu --set full capture (profiles/r1_traffic.json); None if absent."""
+    committed ncu --set full capture (profiles/r2_traffic.json); None if absent."""
     try:
-        with open(os.path.join(ROOT, "profiles", "r1_traffic.json")) as f:
+        with open(os.path.join(ROOT, "profiles", "r2_traffic.json")) as f:
             k = json.load(f)[kernel]
         return int(k["dram_bytes_read"] + k["dram_bytes_write"])
     except Exception:
@@ -249,19 +254,27 @@ def main():
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if N > 1:
+        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"     # stdout carries ONE line: the JSON record
         dist.init_process_group("nccl", device_id=dev)
 
     K, W = args.steps, max(args.warmup, 3)
     S = K + W
-    KE = min(K, 10)          # e2e steps: PCIe-bound and ~15x longer each, a bounded sample keeps the run short
+    KI = min(K, 20)          # instrumented steps (CUDA events around every kernel): per-kernel durations
+    KE = min(K, 10)          # e2e steps: PCIe-bound and ~12x longer each, a bounded sample keeps the run short
     SE = KE + W
-    total_windows = S + (0 if args.no_e2e else SE)
+    total_windows = S + KI + (0 if args.no_e2e else SE)
     if total_windows * SLOTS_PER_STEP * N >= (1 << 31):
         sys.exit(f"bench.py: (steps+warmup)*2^20*N must stay below 2^31 slots (int32 slot numbers)")
     n_slots_local = total_windows * SLOTS_PER_STEP
     eng = Engine(slot_capacity=n_slots_local * N, max_batch=Q * SLOTS_PER_STEP, overflow_capacity=1 << 10,
                  device=local_rank, shard_index=rank, shard_count=N, **CFG)
     ext = torch.cuda.ExternalStream(eng.stream, device=dev)
+    if N > 1:
+        # one global log, slot % N shards: every engine's watermark publication is stored into every peer's
+        # frontier table over NVLink by the publishing kernel itself (include/fpx.h, fpx_exchange_*)
+        from frankenpaxos_b200 import sharding
+        sharding.connect(eng)
 
     # ---- traces: N_BASE distinct seeded base traces on window 0; step s re-bases onto window s
     base = [T.workload(1000 * rank + b, CFG, SLOTS_PER_STEP) for b in range(N_BASE)]
@@ -281,41 +294,21 @@ def main():
         return t.to(dev, non_blocking=False)
 
     d_arm, d_p2a, d_p2b = [], [], []
-    for s in range(S):
+    for s in range(S + KI):
         a, p, b = step_inputs(s)
         d_arm.append(to_dev(a)); d_p2a.append(to_dev(p)); d_p2b.append(to_dev(b))
     nrec = Q * SLOTS_PER_STEP
     d_out_p2b = torch.empty((nrec, 4), dtype=torch.int32, device=dev)
     d_out_nack = torch.empty((nrec, 2), dtype=torch.int32, device=dev)
     d_out_chosen = torch.empty((nrec, 2), dtype=torch.int32, device=dev)
-    # the per-step exchange (first-unchosen slot of every rank) runs on its own stream, double-buffered,
-    # so that it overlaps the next step's kernels instead of sitting on the engine's stream
-    d_wm = [torch.zeros(1, dtype=torch.int32, device=dev) for _ in range(2)]
-    d_wm_all = [torch.zeros(N, dtype=torch.int32, device=dev) for _ in range(2)]
-    comm = torch.cuda.Stream(device=dev) if N > 1 else None
-    ev_wm = [torch.cuda.Event() for _ in range(2)]
-    ev_gathered = [None, None]
+    d_wm = torch.zeros(1, dtype=torch.int32, device=dev)
     torch.cuda.synchronize()
 
-    def step(s, ev=None):
-        eng.proxyleader_arm_dev(d_arm[s].data_ptr(), SLOTS_PER_STEP)
-        if ev: ev[0].record(ext)
-        eng.acceptor_phase2a_dev(d_p2a[s].data_ptr(), nrec, d_out_p2b.data_ptr(), d_out_nack.data_ptr())
-        if ev: ev[1].record(ext)
-        eng.proxyleader_phase2b_dev(d_p2b[s].data_ptr(), nrec, d_out_chosen.data_ptr())
-        if ev: ev[2].record(ext)
-        eng.replica_chosen_last_dev(d_out_chosen.data_ptr())
-        par = s & 1
-        if ev_gathered[par] is not None:
-            ext.wait_event(ev_gathered[par])          # the all-gather of step s-2 has read this buffer
-        eng.chosen_watermark_dev(d_wm[par].data_ptr())
-        if N > 1:
-            ev_wm[par].record(ext)
-            comm.wait_event(ev_wm[par])
-            with torch.cuda.stream(comm):
-                dist.all_gather_into_tensor(d_wm_all[par], d_wm[par])
-                ev_gathered[par] = torch.cuda.Event()
-                ev_gathered[par].record(comm)
+    def step(s, ring_slot=-1):
+        # one C call = one step of the co-located roles: acceptor batch, arm batch, tally + replica + watermark
+        # (+ the exchange: the tally's last CTA stores the new frontier into every peer's table)
+        eng.step_dev(d_arm[s].data_ptr(), SLOTS_PER_STEP, d_p2a[s].data_ptr(), nrec, d_out_p2b.data_ptr(),
+                     d_out_nack.data_ptr(), d_p2b[s].data_ptr(), nrec, d_out_chosen.data_ptr(), d_wm.data_ptr(), ring_slot)
 
     def barrier():
         if N > 1:
@@ -329,16 +322,13 @@ def main():
 
     sampler = ClockSampler(local_rank)
     sampler.start()
-    evs = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(K)]
     e_begin, e_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     launches0 = eng.launch_count
     barrier()
     t_timed0 = time.perf_counter()
     e_begin.record(ext)
     for k in range(K):
-        step(W + k, evs[k])
-    if N > 1:
-        ext.wait_stream(comm)                         # the last exchanges are part of the timed region
+        step(W + k)
     e_end.record(ext)
     barrier()
     t_timed1 = time.perf_counter()
@@ -348,9 +338,11 @@ def main():
     assert r.status == 0 and r.n_chosen == SLOTS_PER_STEP and r.n_nack == 0
     exp_wm = (S * SLOTS_PER_STEP) * N + rank
     assert r.watermark == exp_wm, (r.watermark, exp_wm)
-    if N > 1:   # the gathered frontiers of the last step: every rank's first-unchosen slot, global prefix = min
-        last = d_wm_all[(S - 1) & 1].cpu().numpy()
-        assert last.tolist() == [(S * SLOTS_PER_STEP) * N + g for g in range(N)], last
+    global_prefix = None
+    if N > 1:   # every shard's frontier after step S, as the peers stored it into THIS rank's table
+        global_prefix, fr = eng.global_watermark(epoch=S)
+        assert fr.tolist() == [(S * SLOTS_PER_STEP) * N + g for g in range(N)], fr
+        assert global_prefix == (S * SLOTS_PER_STEP) * N
 
     t = torch.tensor([ms], dtype=torch.float64, device=dev)
     if N > 1:
@@ -358,61 +350,78 @@ def main():
     ms_max = float(t.item())
     value = N * K * SLOTS_PER_STEP / (ms_max * 1e-3)
 
-    acc_ms = float(np.mean([evs[k][0].elapsed_time(evs[k][1]) for k in range(K)]))
-    tally_ms = float(np.mean([evs[k][1].elapsed_time(evs[k][2]) for k in range(K)]))
+    # ---- per-kernel durations: a second, instrumented pass (CUDA events between the kernels cost ~5 us
+    # each on the stream, so they stay out of the pass that produces `value`)
+    e_i0, e_i1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e_i0.record(ext)
+    for k in range(KI):
+        step(S + k, ring_slot=k)
+    e_i1.record(ext)
+    eng.sync()
+    kms = np.array([eng.step_kernel_ms(k) for k in range(KI)])
+    acc_ms, tally_ms = float(kms[:, 0].mean()), float(kms[:, 1].mean())
+    arm_ms = float(np.mean([eng.step_arm_ms(k) for k in range(KI)]))
     peak, peak_src = peaks()
     acc_gbs = B_ACCEPTOR * SLOTS_PER_STEP / (acc_ms * 1e-3) / 1e9
-    tally_gbs = B_TALLY * SLOTS_PER_STEP / (tally_ms * 1e-3) / 1e9
+    tally_gbs = B_TALLY_FUSED * SLOTS_PER_STEP / (tally_ms * 1e-3) / 1e9
 
-    # ---- e2e: host-pointer C ABI, pinned host buffers, copies inside the timed region
+    # ---- e2e: the asynchronous host-pointer step (fpx_step_submit / fpx_step_wait), pinned host buffers,
+    # every input copied H2D and every reply stream copied D2H inside the timed region
     e2e = None
     if not args.no_e2e:
         h_in = []
         for s in range(SE):
-            a, p, b = step_inputs(S + s)
-            h_in.append(tuple(torch.from_numpy(x.view(np.int32).reshape(len(x), -1)).pin_memory() for x in (a, p, b)))
-        h_p2b = torch.empty((nrec, 4), dtype=torch.int32).pin_memory()
-        h_nack = torch.empty((nrec, 2), dtype=torch.int32).pin_memory()
-        h_chosen = torch.empty((nrec, 2), dtype=torch.int32).pin_memory()
-        L = eng._L
-        n1, n2, n3, err = ctypes.c_int32(), ctypes.c_int32(), ctypes.c_int32(), ctypes.c_int64()
-        wm = ctypes.c_int32()
+            a, p, b = step_inputs(S + KI + s)
+            h_in.append(tuple(torch.from_numpy(x.view(np.int32).reshape(len(x), -1)).pin_memory() for x in (p, b)))
+        h_out = [(torch.empty((nrec, 4), dtype=torch.int32).pin_memory(), torch.empty((nrec, 2), dtype=torch.int32).pin_memory(),
+                  torch.empty((nrec, 2), dtype=torch.int32).pin_memory()) for _ in range(2)]
 
-        def e2e_step(s):
-            a, p, b = h_in[s]
-            st = L.fpx_proxyleader_arm(eng.h, a.data_ptr(), SLOTS_PER_STEP, ctypes.byref(err))
-            st |= L.fpx_acceptor_phase2a(eng.h, p.data_ptr(), nrec, h_p2b.data_ptr(), ctypes.byref(n1),
-                                         h_nack.data_ptr(), ctypes.byref(n2), ctypes.byref(err))
-            st |= L.fpx_proxyleader_phase2b(eng.h, b.data_ptr(), nrec, h_chosen.data_ptr(), ctypes.byref(n3),
-                                            ctypes.byref(err))
-            st |= L.fpx_replica_chosen(eng.h, h_chosen.data_ptr(), n3.value, ctypes.byref(err))
-            st |= L.fpx_chosen_watermark(eng.h, ctypes.byref(wm))
-            assert st == 0 and n3.value == SLOTS_PER_STEP and n1.value == nrec, (st, n1.value, n3.value)
-            if N > 1:
-                d_wm[0].fill_(wm.value)
-                dist.all_gather_into_tensor(d_wm_all[0], d_wm[0])
+        def submit(s):
+            p, b = h_in[s]
+            o1, o2, o3 = h_out[s & 1]
+            # arm = NULL: the proxy leader arms from the Phase2a batch it forwards (one upload, not two)
+            eng.step_submit(None, 0, p.data_ptr(), nrec, b.data_ptr(), nrec, o1.data_ptr(), o2.data_ptr(), o3.data_ptr())
 
-        for s in range(W):
-            e2e_step(s)
+        def wait(s):
+            n1, n2, n3, wm = eng.step_wait()
+            assert n1 == nrec and n2 == 0 and n3 == SLOTS_PER_STEP, (n1, n2, n3)
+            return wm
+
+        def e2e_run(first, count):
+            submit(first)
+            for s in range(first + 1, first + count):
+                submit(s)          # H2D of step s overlaps the kernels and the D2H of step s-1
+                wait(s - 1)
+            return wait(first + count - 1)
+
+        e2e_run(0, W)
         barrier()
         t0 = time.perf_counter()
-        for k in range(KE):
-            e2e_step(W + k)
+        wm_last = e2e_run(W, KE)
         barrier()
         dt = time.perf_counter() - t0
+        assert wm_last == ((S + KI + SE) * SLOTS_PER_STEP) * N + rank, wm_last
+        assert h_out[(SE - 1) & 1][2][:SLOTS_PER_STEP, 0].min().item() >= ((S + KI + SE - 1) * SLOTS_PER_STEP) * N
         t = torch.tensor([dt], dtype=torch.float64, device=dev)
         if N > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e = {"value": N * KE * SLOTS_PER_STEP / float(t.item()), "unit": "slots/s", "steps": KE,
-               "h2d_bytes_per_step": 16 * SLOTS_PER_STEP + 2 * 16 * nrec + 8 * SLOTS_PER_STEP,
-               "d2h_bytes_per_step": 16 * nrec + 8 * SLOTS_PER_STEP + 4,
+               "h2d_bytes_per_step": 2 * 16 * nrec, "d2h_bytes_per_step": 16 * nrec + 8 * SLOTS_PER_STEP + 160,
                "ms_per_step": 1e3 * float(t.item()) / KE,
-               "api": "fpx_proxyleader_arm + fpx_acceptor_phase2a + fpx_proxyleader_phase2b + "
-                      "fpx_replica_chosen + fpx_chosen_watermark (host pointers, pinned)"}
+               "api": "fpx_step_submit + fpx_step_wait (host pointers, pinned; double-buffered: H2D of step k+1 "
+                      "overlaps kernels and D2H of step k; the arm batch is the Phase2a batch)"}
     sampler.stop_flag = True
     t_all1 = time.perf_counter()
     clocks = sampler.summary([("timed region", t_timed0, t_timed1),
-                              ("timed region + e2e region (timed region too short to sample 3 times)", t_timed0, t_all1)])
+                              ("timed region + instrumented + e2e regions (timed region too short to sample 3 times)",
+                               t_timed0, t_all1)])
+    eng.close()
+    del d_arm, d_p2a, d_p2b
+    torch.cuda.empty_cache()
+
+    extra = {}
+    if not args.no_extra:
+        extra["cfg5"] = cfg5_extra(torch, dist, dev, rank, N, local_rank)
 
     cpu = None
     if rank == 0 and N == 1:
@@ -422,32 +431,106 @@ def main():
                          "single-threaded C++ oracle port of the Scala handlers (JVM reference not runnable offline)"}
 
     if rank == 0:
+        step_ms = ms_max / K
+        dominant = "tally_kernel" if tally_ms >= acc_ms else "acceptor_phase2a_kernel"
+        kern = {"acceptor_phase2a_kernel": {"ms": acc_ms, "GB/s": acc_gbs, "frac": acc_gbs / peak,
+                                            "algorithmic_bytes_per_launch": B_ACCEPTOR * SLOTS_PER_STEP,
+                                            "traffic": ncu_traffic("acceptor_phase2a_kernel")},
+                "tally_kernel": {"ms": tally_ms, "GB/s": tally_gbs, "frac": tally_gbs / peak,
+                                 "algorithmic_bytes_per_launch": B_TALLY_FUSED * SLOTS_PER_STEP,
+                                 "traffic": ncu_traffic("tally_kernel"),
+                                 "note": "ProxyLeader.handlePhase2b + the co-located replica's handleChosen and the "
+                                         "first-hole scan in one launch: 16Q+24 (tally) + 8 (log put) + 8 (scan) B/slot"},
+                "arm_kernel": {"ms": arm_ms}}
         line = {
             "metric": "committed slots/sec (simulated) at 1M in-flight slots",
             "value": value, "unit": "slots/s", "n_gpus": N, "steps": K, "warmup": W,
-            "ms_per_step": ms_max / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "int32", "data": "synthetic",
             "config": config_dict(N),
-            # the dominant kernel by time (43 % of the step in profiles/r1_launches_final.csv) is the tally
-            "roofline": {"bound": "hbm", "kernel": "tally_kernel", "achieved": tally_gbs, "peak": peak,
-                         "unit": "GB/s", "frac": tally_gbs / peak, "traffic": ncu_traffic("tally_kernel"),
-                         "algorithmic_bytes_per_launch": B_TALLY * SLOTS_PER_STEP, "ms_per_launch": tally_ms,
-                         "peak_source": peak_src,
-                         "note": "shuffled Phase2b stream: bound by L1TEX wavefronts of the 2 divergent row accesses "
-                                 "per vote, not by DRAM bytes (DESIGN.md section 4)"},
-            "kernels": {"acceptor_phase2a_kernel": {"ms": acc_ms, "GB/s": acc_gbs, "frac": acc_gbs / peak,
-                                                    "algorithmic_bytes_per_launch": B_ACCEPTOR * SLOTS_PER_STEP,
-                                                    "traffic": ncu_traffic("acceptor_phase2a_kernel")},
-                        "tally_kernel": {"ms": tally_ms, "GB/s": tally_gbs, "frac": tally_gbs / peak,
-                                         "algorithmic_bytes_per_launch": B_TALLY * SLOTS_PER_STEP,
-                                         "traffic": ncu_traffic("tally_kernel")},
-                        "whole_step_GB/s": B_SLOT * SLOTS_PER_STEP / (ms_max / K * 1e-3) / 1e9},
+            # the dominant kernel by time of the step (CUDA events of the instrumented pass)
+            "roofline": {"bound": "hbm", "kernel": dominant, "achieved": kern[dominant]["GB/s"], "peak": peak,
+                         "unit": "GB/s", "frac": kern[dominant]["frac"], "traffic": kern[dominant]["traffic"],
+                         "algorithmic_bytes_per_launch": kern[dominant]["algorithmic_bytes_per_launch"],
+                         "ms_per_launch": kern[dominant]["ms"], "peak_source": peak_src,
+                         "timing": f"CUDA events on the engine's stream around every kernel of {KI} instrumented steps "
+                                   "run right after the timed region (events between kernels cost ~5 us each, so the "
+                                   "pass that produces `value` carries none)"},
+            "kernels": dict(kern, **{"whole_step_GB/s": B_SLOT * SLOTS_PER_STEP / (step_ms * 1e-3) / 1e9,
+                                     "whole_step_frac": B_SLOT * SLOTS_PER_STEP / (step_ms * 1e-3) / 1e9 / peak}),
             "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
+            "exchange": None if N == 1 else {"kind": "peer-mapped NVLink stores from the tally kernel's last CTA into "
+                                                    "every shard's frontier table (fpx_exchange_*), no collective launch",
+                                             "global_prefix_after_timed_region": global_prefix},
+            "extra": extra,
         }
         print(json.dumps(line), flush=True)
-    eng.close()
     if N > 1:
         dist.destroy_process_group()
+
+
+def cfg5_extra(torch, dist, dev, rank, N, local_rank, K5=4, W5=2):
+    """BASELINE configs[4]: vanilla Mencius, 7 servers (f=3), owner = slot % 7, the log sharded slot % N over
+    the N GPUs of the box, the chosen prefix exchanged through the engines' frontier tables.  Device-resident
+    steps of 2^20 slots per GPU: client requests at the owners (arm + own vote), 6 Phase2a per slot at the
+    other servers, 6 shuffled Phase2b per slot tallied, replica log + watermark (+ exchange)."""
+    from frankenpaxos_b200 import VANILLA_MENCIUS, Engine
+    from frankenpaxos_b200 import traces as T
+    cfg, n = T.config_by_name("cfg5")
+    f, srv = cfg["f"], cfg["acceptors_per_group"]
+    S5 = K5 + W5
+    eng = Engine(slot_capacity=S5 * n * N, max_batch=(srv - 1) * n, protocol=VANILLA_MENCIUS, device=local_rank,
+                 shard_index=rank, shard_count=N, **cfg)
+    if N > 1:
+        from frankenpaxos_b200 import sharding
+        sharding.connect(eng)
+    ext = torch.cuda.ExternalStream(eng.stream, device=dev)
+    ins = []
+    for s in range(S5):
+        req, p, b = T.vanilla_cfg5(500 + 10 * rank + s % 2, f, n, slot_stride=N, slot_offset=rank + s * n * N)
+        ins.append(tuple(torch.from_numpy(x.view(np.int32).reshape(len(x), -1)).to(dev) for x in (req, p, b)))
+    nrec = (srv - 1) * n
+    o_rep = torch.empty((nrec, 4), dtype=torch.int32, device=dev)
+    o_ch = torch.empty((nrec, 2), dtype=torch.int32, device=dev)
+    wm = torch.zeros(1, dtype=torch.int32, device=dev)
+
+    def step(s):
+        dr, dp, db = ins[s]
+        eng.vm_client_request_dev(dr.data_ptr(), n)
+        eng.vm_phase2a_dev(dp.data_ptr(), nrec, o_rep.data_ptr())
+        eng.proxyleader_phase2b_dev(db.data_ptr(), nrec, o_ch.data_ptr())
+        eng.replica_chosen_last_dev(o_ch.data_ptr())
+        eng.chosen_watermark_dev(wm.data_ptr())
+    for s in range(W5):
+        step(s)
+    eng.sync()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    if N > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    e0.record(ext)
+    for k in range(K5):
+        step(W5 + k)
+    e1.record(ext)
+    if N > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    r = eng.sync()
+    assert r.status == 0 and r.n_chosen == n and r.watermark == S5 * n * N + rank, (r.status, r.n_chosen, r.watermark)
+    gp = None
+    if N > 1:
+        gp, fr = eng.global_watermark(epoch=S5)
+        assert gp == S5 * n * N, (gp, fr)
+    t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+    if N > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item()) / K5
+    eng.close()
+    return {"config": f"cfg5: vanilla Mencius n=7 f=3, owner = slot % 7, log sharded slot % {N}, 2^20 slots per GPU per "
+                      "step, 6 Phase2a + 6 Phase2b per slot, both shuffled", "n_gpus": N, "steps": K5, "warmup": W5,
+            "ms_per_step": ms, "value": N * n / (ms * 1e-3), "unit": "slots/s",
+            "messages_per_s": N * (1 + 2 * (srv - 1)) * n / (ms * 1e-3), "global_prefix": gp,
+            "calls": "vm_client_request + vm_phase2a + proxyleader_phase2b + replica_chosen + chosen_watermark (device pointers)"}
 
 
 if __name__ == "__main__":

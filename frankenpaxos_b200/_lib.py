@@ -17,13 +17,15 @@ SYMBOLS = [
     "fpx_chosen_watermark", "fpx_quorum_eval", "fpx_snapshot_acceptor", "fpx_snapshot_log",
     "fpx_proxyleader_arm_dev", "fpx_acceptor_phase2a_dev", "fpx_proxyleader_phase2b_dev",
     "fpx_replica_chosen_dev", "fpx_replica_chosen_last_dev", "fpx_chosen_watermark_dev", "fpx_sync",
-    "fpx_stream", "fpx_launch_count", "fpx_set_coop_ctas_per_sm", "fpx_step_dev", "fpx_step_kernel_ms",
+    "fpx_stream", "fpx_launch_count", "fpx_set_coop_ctas_per_sm", "fpx_step_dev", "fpx_step_kernel_ms", "fpx_step_arm_ms",
     "fpx_acceptor_phase1a", "fpx_leader_safe_values",
     "fpx_vm_client_request", "fpx_vm_phase2a", "fpx_vm_learn_chosen", "fpx_vm_skip", "fpx_vm_client_request_dev", "fpx_vm_phase2a_dev",
     "fpx_mencius_arm_range", "fpx_mencius_acceptor_noop_range", "fpx_mencius_range_phase2b",
     "fpx_mencius_replica_chosen_range",
     "fpx_wire_decode_inbound", "fpx_wire_decode_inbound_dev", "fpx_wire_encode_phase2b", "fpx_wire_encode_phase2b_dev",
     "fpx_wire_encode_nack", "fpx_wire_encode_chosen",
+    "fpx_step_submit", "fpx_step_wait", "fpx_exchange_export", "fpx_exchange_attach", "fpx_exchange_attach_local", "fpx_exchange_epoch",
+    "fpx_global_watermark", "fpx_global_watermark_dev",
     "fpx_epaxos_create", "fpx_epaxos_destroy", "fpx_epaxos_lead", "fpx_epaxos_preaccept", "fpx_epaxos_accept",
     "fpx_epaxos_preacceptok", "fpx_epaxos_acceptok", "fpx_epaxos_entry", "fpx_epaxos_last_kernel_ms", "fpx_depset_union", "fpx_depset_union_dense_dev",
 ]
@@ -103,10 +105,19 @@ def lib():
     L.fpx_wire_encode_chosen.restype = i32
     L.fpx_step_dev.argtypes = [vp, vp, i32, vp, i32, vp, vp, vp, i32, vp, vp, i32]; L.fpx_step_dev.restype = i32
     L.fpx_step_kernel_ms.argtypes = [vp, i32, p(C.c_float), p(C.c_float)]; L.fpx_step_kernel_ms.restype = i32
+    L.fpx_step_arm_ms.argtypes = [vp, i32, p(C.c_float)]; L.fpx_step_arm_ms.restype = i32
     L.fpx_sync.argtypes = [vp, p(SyncResult)]; L.fpx_sync.restype = i32
     L.fpx_set_coop_ctas_per_sm.argtypes = [vp, i32]; L.fpx_set_coop_ctas_per_sm.restype = i32
     L.fpx_stream.argtypes = [vp]; L.fpx_stream.restype = vp
     L.fpx_launch_count.argtypes = [vp]; L.fpx_launch_count.restype = i64
+    L.fpx_step_submit.argtypes = [vp, vp, i32, vp, i32, vp, i32, vp, vp, vp]; L.fpx_step_submit.restype = i32
+    L.fpx_step_wait.argtypes = [vp, p(i32), p(i32), p(i32), p(i32), p(i64)]; L.fpx_step_wait.restype = i32
+    L.fpx_exchange_export.argtypes = [vp, vp]; L.fpx_exchange_export.restype = i32
+    L.fpx_exchange_attach.argtypes = [vp, i32, vp]; L.fpx_exchange_attach.restype = i32
+    L.fpx_exchange_attach_local.argtypes = [vp, i32, vp]; L.fpx_exchange_attach_local.restype = i32
+    L.fpx_exchange_epoch.argtypes = [vp]; L.fpx_exchange_epoch.restype = C.c_uint32
+    L.fpx_global_watermark_dev.argtypes = [vp, C.c_uint32, i32, vp, vp]; L.fpx_global_watermark_dev.restype = i32
+    L.fpx_global_watermark.argtypes = [vp, C.c_uint32, i32, p(i32), vp]; L.fpx_global_watermark.restype = i32
     if hasattr(L, "fpx_debug_set_tally_path"):
         L.fpx_debug_set_tally_path.argtypes = [vp, i32]; L.fpx_debug_set_tally_path.restype = i32
         L.fpx_debug_last_tally_path.argtypes = [vp]; L.fpx_debug_last_tally_path.restype = i32

@@ -69,6 +69,26 @@ __device__ __forceinline__ unsigned long long global_timer_ns() {
 }
 #define FPX_MARK(arr, k) do { if (blockIdx.x == 0 && threadIdx.x == 0) (arr)[k] = global_timer_ns(); } while (0)
 
+// Multi-GPU exchange (fpx_exchange_*): every engine of a sharded log owns a frontier table
+// {epoch:32 | first unchosen global slot:32}[shards]; the kernel that publishes an engine's watermark also
+// stores its entry into every peer's table through peer-mapped pointers (NVLink), no collective launch.
+constexpr int kMaxShards = 64;
+struct DevExchange {
+  int32_t enabled, n, mine, pad;
+  uint32_t epoch;                       // publications so far
+  uint32_t pad2;
+  unsigned long long* tabs[kMaxShards]; // tabs[p] = shard p's table as mapped into THIS device (nullptr: not attached)
+};
+__device__ __forceinline__ void exchange_publish(DevExchange* x, int global_frontier) {
+  if (x == nullptr || !x->enabled) return;
+  const uint32_t ep = ++x->epoch;
+  const unsigned long long v = ((unsigned long long)ep << 32) | (uint32_t)global_frontier;
+  for (int p = 0; p < x->n; ++p)
+    if (x->tabs[p] != nullptr)
+      // the entry IS the message (epoch and frontier in one 64-bit word): no ordering with other data needed
+      asm volatile("st.global.relaxed.sys.u64 [%0], %1;" ::"l"(x->tabs[p] + x->mine), "l"(v) : "memory");
+}
+
 struct Geometry {
   int32_t protocol, f, groups, per_group, flexible, num_leaders;
   int32_t voters;          // acceptors that can vote on one slot (row width)

@@ -58,6 +58,13 @@ struct fpx_engine {
   struct WireBuf { void* p = nullptr; size_t cap = 0; };
   WireBuf w_bytes, w_offs, w_kind, w_rec, w_out, w_tiles, w_arena, w_voffs;
   DevStatus* st = nullptr;
+  // multi-GPU exchange
+  DevExchange* xch = nullptr;          // device copy of the exchange descriptor
+  DevExchange h_xch;                   // host mirror
+  unsigned long long* xch_table = nullptr;   // this engine's frontier table [kMaxShards]
+  void* xch_opened[kMaxShards] = {};   // peer tables opened with cudaIpcOpenMemHandle
+  uint32_t xch_epoch = 0;              // publications issued so far (host count)
+  int32_t* xch_out = nullptr;          // result of fpx_global_watermark: [1 + kMaxShards]
   // scratch
   uint32_t* bits = nullptr;            // accept / win bitmask, max_batch/32 words
   int32_t* g_agg = nullptr;            // [kMaxGrid][kMaxKeys] acceptor kernel CTA aggregates
@@ -74,6 +81,16 @@ struct fpx_engine {
   void* d_out_a = nullptr;             // max_batch * 16 (p2b)
   void* d_out_b = nullptr;             // max_batch * 8  (nack / chosen)
   DevStatus* h_st = nullptr;           // pinned mirror
+  // fpx_step_submit / fpx_step_wait: two lanes of device staging + pinned status
+  struct Lane {
+    void *d_p2a = nullptr, *d_p2b = nullptr, *d_arm = nullptr, *d_out_p2b = nullptr, *d_out_nack = nullptr, *d_out_chosen = nullptr;
+    cudaEvent_t ev_p2a = nullptr, ev_p2b = nullptr, ev_acc = nullptr, ev_done = nullptr, ev_d2h = nullptr;
+    DevStatus* h_st = nullptr;
+    fpx_p2b* out_p2b = nullptr; fpx_nack* out_nack = nullptr; fpx_chosen* out_chosen = nullptr;
+    int32_t n_p2a = 0;
+    bool busy = false;
+  } lane[2];
+  int lane_head = 0, lane_tail = 0, lanes_in_flight = 0;
   // host bookkeeping
   uint32_t parity = 0;                 // nack counter the next acceptor launch uses
   int grid_acceptor = 0;               // co-resident CTAs of the cooperative kernels
@@ -168,6 +185,11 @@ static int reset_state(fpx_engine* e) {
   *e->h_st = init;
   CK(e, cudaMemcpyAsync(e->st, e->h_st, sizeof(DevStatus), cudaMemcpyHostToDevice, e->stream));
   CK(e, cudaStreamSynchronize(e->stream));
+  CK(e, cudaMemsetAsync(e->xch_table, 0, kMaxShards * 8, e->stream));
+  e->h_xch.epoch = 0;
+  e->xch_epoch = 0;
+  CK(e, cudaMemcpyAsync(e->xch, &e->h_xch, sizeof(DevExchange), cudaMemcpyHostToDevice, e->stream));
+  CK(e, cudaStreamSynchronize(e->stream));
   e->parity = 0;
   e->seq_base = 1;
   e->rseq_base = 1;
@@ -196,6 +218,7 @@ const char* fpx_strerror(int s) {
     case FPX_ERR_BATCH_ORDER: return "EPaxos batch contract violated: split the batch at err_index";
     case FPX_ERR_CHECK_FAILED: return "a logger.check of the reference failed";
     case FPX_ERR_WIRE: return "malformed protobuf message (InvalidProtocolBufferException)";
+    case FPX_ERR_EXCHANGE_TIMEOUT: return "a shard of the log did not publish its watermark in time";
     case FPX_ERR_EPAXOS_STATE: return "transitionToPreAcceptPhase on a committed instance / regressing ballot";
     default: return "unknown status";
   }
@@ -270,6 +293,9 @@ int fpx_create(fpx_engine** out, const fpx_config* cfg) {
   }
   if (cfg->protocol != FPX_MULTIPAXOS) CKC(cudaMalloc(&e->rng_dec, (size_t)(FPX_MAX_RANGE_BATCH + 1) * 4));
   CKC(cudaMalloc(&e->st, sizeof(DevStatus)));
+  CKC(cudaMalloc(&e->xch, sizeof(DevExchange)));
+  CKC(cudaMalloc(&e->xch_table, kMaxShards * 8));
+  CKC(cudaMalloc(&e->xch_out, (1 + kMaxShards) * 4));
   CKC(cudaMalloc(&e->bits, (mb / 32 + 2) * 4));
   CKC(cudaMalloc(&e->g_agg, (size_t)kMaxGrid * kMaxKeys * 4));
   CKC(cudaMalloc(&e->g_wacc, (size_t)kMaxGrid * kAW * 4));
@@ -307,6 +333,11 @@ int fpx_create(fpx_engine** out, const fpx_config* cfg) {
   CKC(cudaMalloc(&e->d_out_b, mb * 8));
   CKC(cudaMallocHost(&e->h_st, sizeof(DevStatus)));
 #undef CKC
+  memset(&e->h_xch, 0, sizeof(e->h_xch));
+  e->h_xch.n = g.shard_count <= kMaxShards ? g.shard_count : 0;
+  e->h_xch.mine = g.shard_index;
+  e->h_xch.tabs[g.shard_index < kMaxShards ? g.shard_index : 0] = g.shard_count <= kMaxShards ? e->xch_table : nullptr;
+  e->h_xch.enabled = g.shard_count > 1 && g.shard_count <= kMaxShards;
   int r = reset_state(e);
   if (r != FPX_OK) { fprintf(stderr, "fpx_create: %s\n", e->last_error.c_str()); return fail(r); }
   // test / A-B knob: FPX_TALLY_PATH=exact makes every tally launch take the per-vote path
@@ -322,6 +353,13 @@ void fpx_destroy(fpx_engine* e) {
   cudaFree(e->rows); cudaFree(e->ovf_keys); cudaFree(e->ovf_rows); cudaFree(e->votes);
   cudaFree(e->acc_round); cudaFree(e->acc_max_voted); cudaFree(e->rlog); cudaFree(e->vm_claim); cudaFree(e->st);
   cudaFree(e->rng_tab); cudaFree(e->rng_dec);
+  for (auto& ln : e->lane) {
+    cudaFree(ln.d_p2a); cudaFree(ln.d_p2b); cudaFree(ln.d_arm); cudaFree(ln.d_out_p2b); cudaFree(ln.d_out_nack); cudaFree(ln.d_out_chosen);
+    for (cudaEvent_t ev : {ln.ev_p2a, ln.ev_p2b, ln.ev_acc, ln.ev_done, ln.ev_d2h}) if (ev) cudaEventDestroy(ev);
+    if (ln.h_st) cudaFreeHost(ln.h_st);
+  }
+  for (int p = 0; p < kMaxShards; ++p) if (e->xch_opened[p]) cudaIpcCloseMemHandle(e->xch_opened[p]);
+  cudaFree(e->xch); cudaFree(e->xch_table); cudaFree(e->xch_out);
   if (e->step_ev) {
     for (int i = 0; i < kStepRing * 4; ++i) cudaEventDestroy(e->step_ev[i]);
     delete[] e->step_ev;
@@ -511,6 +549,7 @@ static int tally_launch(fpx_engine* e, const fpx_p2b* d_in, int32_t n, fpx_chose
     P.rseq_base = e->rseq_base + (uint32_t)done;   // later sub-launches number their records after earlier ones
     P.fuse_watermark = fuse && done + sub == n;
     P.d_watermark = d_wm;
+    P.xch = e->xch;
     P.st = e->st;
     e->seq_base += (uint32_t)sub;
     void* args[] = {&P};
@@ -521,6 +560,7 @@ static int tally_launch(fpx_engine* e, const fpx_p2b* d_in, int32_t n, fpx_chose
     e->launches++;
     done += sub;
   }
+  if (fuse) e->xch_epoch++;                    // the fused tail published the watermark once
   if (fuse) e->rseq_base += 2u * (uint32_t)n;  // numbers used: below rseq_base + done + sub <= rseq_base + 2n
   CK(e, cudaGetLastError());
   return FPX_OK;
@@ -573,8 +613,9 @@ int fpx_replica_chosen_last_dev(fpx_engine* e, const fpx_chosen* d_in) {
 
 int fpx_chosen_watermark_dev(fpx_engine* e, int32_t* d_out) {
   if (!e) return FPX_ERR_INVALID_ARG;
-  watermark_scan_kernel<<<e->num_sms * 4, 256, 0, e->stream>>>(e->g, e->rlog, e->st, d_out);
+  watermark_scan_kernel<<<e->num_sms * 4, 256, 0, e->stream>>>(e->g, e->rlog, e->st, d_out, e->xch);
   e->launches += 1;
+  e->xch_epoch++;
   CK(e, cudaGetLastError());
   return FPX_OK;
 }
@@ -615,6 +656,164 @@ int fpx_step_kernel_ms(fpx_engine* e, int32_t ring_slot, float* acceptor_ms, flo
   CK(e, cudaEventSynchronize(ev[3]));
   CK(e, cudaEventElapsedTime(acceptor_ms, ev[0], ev[1]));
   CK(e, cudaEventElapsedTime(tally_ms, ev[2], ev[3]));
+  return FPX_OK;
+}
+
+// --------------------------------------------------------------------------- asynchronous host step
+
+static int lane_init(fpx_engine* e, fpx_engine::Lane& ln) {
+  if (ln.d_p2a) return FPX_OK;
+  size_t mb = (size_t)e->cfg.max_batch;
+  CK(e, cudaMalloc(&ln.d_p2a, mb * 16)); CK(e, cudaMalloc(&ln.d_p2b, mb * 16)); CK(e, cudaMalloc(&ln.d_arm, mb * 16));
+  CK(e, cudaMalloc(&ln.d_out_p2b, mb * 16)); CK(e, cudaMalloc(&ln.d_out_nack, mb * 8)); CK(e, cudaMalloc(&ln.d_out_chosen, mb * 8));
+  for (cudaEvent_t* ev : {&ln.ev_p2a, &ln.ev_p2b, &ln.ev_acc, &ln.ev_done, &ln.ev_d2h})
+    CK(e, cudaEventCreateWithFlags(ev, cudaEventDisableTiming));
+  CK(e, cudaMallocHost(&ln.h_st, sizeof(DevStatus)));
+  return FPX_OK;
+}
+
+int fpx_step_submit(fpx_engine* e, const fpx_p2a* arm, int32_t n_arm, const fpx_p2a* p2a, int32_t n_p2a,
+                    const fpx_p2b* p2b, int32_t n_p2b, fpx_p2b* out_p2b, fpx_nack* out_nack, fpx_chosen* out_chosen) {
+  int c = check_n(e, p2a, n_p2a);
+  if (c == FPX_OK) c = check_n(e, p2b, n_p2b);
+  if (c == FPX_OK && arm != nullptr) c = check_n(e, arm, n_arm);
+  if (c != FPX_OK) return c;
+  if ((n_p2a > 0 && (!out_p2b || !out_nack)) || (n_p2b > 0 && !out_chosen)) return FPX_ERR_INVALID_ARG;
+  if (e->g.protocol == FPX_VANILLA_MENCIUS) return FPX_ERR_UNSUPPORTED;
+  if (e->lanes_in_flight >= 2) return FPX_ERR_INVALID_ARG;   // fpx_step_wait first
+  CK(e, cudaSetDevice(e->cfg.device));
+  fpx_engine::Lane& ln = e->lane[e->lane_head];
+  c = lane_init(e, ln);
+  if (c != FPX_OK) return c;
+  // inputs: copy stream (the lane's previous kernels have finished: its step was waited for)
+  if (n_p2a) CK(e, cudaMemcpyAsync(ln.d_p2a, p2a, (size_t)n_p2a * 16, cudaMemcpyHostToDevice, e->h2d_stream));
+  if (arm && n_arm) CK(e, cudaMemcpyAsync(ln.d_arm, arm, (size_t)n_arm * 16, cudaMemcpyHostToDevice, e->h2d_stream));
+  CK(e, cudaEventRecord(ln.ev_p2a, e->h2d_stream));
+  if (n_p2b) CK(e, cudaMemcpyAsync(ln.d_p2b, p2b, (size_t)n_p2b * 16, cudaMemcpyHostToDevice, e->h2d_stream));
+  CK(e, cudaEventRecord(ln.ev_p2b, e->h2d_stream));
+  // kernels: the engine's stream
+  CK(e, cudaStreamWaitEvent(e->stream, ln.ev_p2a, 0));
+  c = fpx_acceptor_phase2a_dev(e, (const fpx_p2a*)ln.d_p2a, n_p2a, (fpx_p2b*)ln.d_out_p2b, (fpx_nack*)ln.d_out_nack);
+  if (c != FPX_OK) return c;
+  CK(e, cudaEventRecord(ln.ev_acc, e->stream));
+  c = arm ? fpx_proxyleader_arm_dev(e, (const fpx_p2a*)ln.d_arm, n_arm)
+          : fpx_proxyleader_arm_dev(e, (const fpx_p2a*)ln.d_p2a, n_p2a);
+  if (c != FPX_OK) return c;
+  CK(e, cudaStreamWaitEvent(e->stream, ln.ev_p2b, 0));
+  c = tally_launch(e, (const fpx_p2b*)ln.d_p2b, n_p2b, (fpx_chosen*)ln.d_out_chosen, 1, nullptr);
+  if (c != FPX_OK) return c;
+  CK(e, cudaMemcpyAsync(ln.h_st, e->st, sizeof(DevStatus), cudaMemcpyDeviceToHost, e->stream));
+  CK(e, cudaEventRecord(ln.ev_done, e->stream));
+  // replies: second copy stream, while the tally runs (dense positions = the stream unless a Nack was produced)
+  CK(e, cudaStreamWaitEvent(e->d2h_stream, ln.ev_acc, 0));
+  if (n_p2a) CK(e, cudaMemcpyAsync(out_p2b, ln.d_out_p2b, (size_t)n_p2a * 16, cudaMemcpyDeviceToHost, e->d2h_stream));
+  CK(e, cudaEventRecord(ln.ev_d2h, e->d2h_stream));
+  ln.out_p2b = out_p2b; ln.out_nack = out_nack; ln.out_chosen = out_chosen; ln.n_p2a = n_p2a;
+  ln.busy = true;
+  e->lane_head ^= 1;
+  e->lanes_in_flight++;
+  return FPX_OK;
+}
+
+int fpx_step_wait(fpx_engine* e, int32_t* n_out_p2b, int32_t* n_out_nack, int32_t* n_out_chosen, int32_t* watermark,
+                  int64_t* err_index) {
+  if (err_index) *err_index = -1;
+  if (!e || e->lanes_in_flight == 0) return FPX_ERR_INVALID_ARG;
+  CK(e, cudaSetDevice(e->cfg.device));
+  fpx_engine::Lane& ln = e->lane[e->lane_tail];
+  CK(e, cudaEventSynchronize(ln.ev_done));
+  const DevStatus& st = *ln.h_st;
+  int status = FPX_OK;
+  if (st.err_word != ~0ull) {
+    status = -(int)(st.err_word & 0xff);
+    if (err_index) *err_index = (long long)(st.err_word >> 8);
+    unsigned long long none = ~0ull;   // the reference process would be dead; clear for the caller's fpx_reset
+    CK(e, cudaMemcpyAsync(&e->st->err_word, &none, 8, cudaMemcpyHostToDevice, e->stream));
+  }
+  if (status == FPX_OK && st.n_chosen > 0)
+    CK(e, cudaMemcpyAsync(ln.out_chosen, ln.d_out_chosen, (size_t)st.n_chosen * 8, cudaMemcpyDeviceToHost, e->d2h_stream));
+  if (status == FPX_OK && st.n_nack > 0) {   // leader change in this batch: the dense copy is not the stream
+    if (st.n_p2b) CK(e, cudaMemcpyAsync(ln.out_p2b, ln.d_out_p2b, (size_t)st.n_p2b * 16, cudaMemcpyDeviceToHost, e->d2h_stream));
+    CK(e, cudaMemcpyAsync(ln.out_nack, ln.d_out_nack, (size_t)st.n_nack * 8, cudaMemcpyDeviceToHost, e->d2h_stream));
+  }
+  CK(e, cudaStreamSynchronize(e->d2h_stream));
+  if (n_out_p2b) *n_out_p2b = st.n_p2b;
+  if (n_out_nack) *n_out_nack = st.n_nack;
+  if (n_out_chosen) *n_out_chosen = st.n_chosen;
+  if (watermark) *watermark = st.watermark;
+  ln.busy = false;
+  e->lane_tail ^= 1;
+  e->lanes_in_flight--;
+  return status;
+}
+
+// --------------------------------------------------------------------------- multi-GPU exchange
+
+static int exchange_push(fpx_engine* e) {
+  // the descriptor changes only between steps; epoch is owned by the device once publishing started
+  CK(e, cudaSetDevice(e->cfg.device));
+  CK(e, cudaStreamSynchronize(e->stream));
+  CK(e, cudaMemcpy(&e->h_xch.epoch, &e->xch->epoch, 4, cudaMemcpyDeviceToHost));
+  CK(e, cudaMemcpy(e->xch, &e->h_xch, sizeof(DevExchange), cudaMemcpyHostToDevice));
+  return FPX_OK;
+}
+
+int fpx_exchange_export(fpx_engine* e, void* handle) {
+  if (!e || !handle) return FPX_ERR_INVALID_ARG;
+  static_assert(sizeof(cudaIpcMemHandle_t) == FPX_EXCHANGE_HANDLE_BYTES, "IPC handle size");
+  CK(e, cudaSetDevice(e->cfg.device));
+  CK(e, cudaIpcGetMemHandle((cudaIpcMemHandle_t*)handle, e->xch_table));
+  return FPX_OK;
+}
+
+int fpx_exchange_attach(fpx_engine* e, int32_t shard, const void* handle) {
+  if (!e || !handle || shard < 0 || shard >= e->g.shard_count || e->g.shard_count > kMaxShards) return FPX_ERR_INVALID_ARG;
+  if (shard == e->g.shard_index) return FPX_OK;
+  CK(e, cudaSetDevice(e->cfg.device));
+  cudaIpcMemHandle_t h;
+  memcpy(&h, handle, sizeof(h));
+  void* p = nullptr;
+  CK(e, cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+  if (e->xch_opened[shard]) cudaIpcCloseMemHandle(e->xch_opened[shard]);
+  e->xch_opened[shard] = p;
+  e->h_xch.tabs[shard] = (unsigned long long*)p;
+  return exchange_push(e);
+}
+
+int fpx_exchange_attach_local(fpx_engine* e, int32_t shard, fpx_engine* peer) {
+  if (!e || !peer || shard < 0 || shard >= e->g.shard_count || e->g.shard_count > kMaxShards ||
+      peer->g.shard_index != shard || peer->g.shard_count != e->g.shard_count)
+    return FPX_ERR_INVALID_ARG;
+  if (peer == e) return FPX_OK;
+  CK(e, cudaSetDevice(e->cfg.device));
+  if (peer->cfg.device != e->cfg.device) {
+    int can = 0;
+    CK(e, cudaDeviceCanAccessPeer(&can, e->cfg.device, peer->cfg.device));
+    if (!can) return FPX_ERR_UNSUPPORTED;
+    cudaError_t pe = cudaDeviceEnablePeerAccess(peer->cfg.device, 0);
+    if (pe != cudaSuccess && pe != cudaErrorPeerAccessAlreadyEnabled) CK(e, pe);
+    (void)cudaGetLastError();
+  }
+  e->h_xch.tabs[shard] = peer->xch_table;
+  return exchange_push(e);
+}
+
+uint32_t fpx_exchange_epoch(const fpx_engine* e) { return e ? e->xch_epoch : 0; }
+
+int fpx_global_watermark_dev(fpx_engine* e, uint32_t epoch, int32_t timeout_ms, int32_t* d_out, int32_t* d_frontiers) {
+  if (!e || timeout_ms < 0 || e->g.shard_count > kMaxShards) return FPX_ERR_INVALID_ARG;
+  global_watermark_kernel<<<1, 32, 0, e->stream>>>(e->xch, e->xch_table, epoch, d_out, d_frontiers, e->st,
+                                                   (unsigned long long)timeout_ms * 1000000ull);
+  e->launches++;
+  CK(e, cudaGetLastError());
+  return FPX_OK;
+}
+
+int fpx_step_arm_ms(fpx_engine* e, int32_t ring_slot, float* arm_ms) {
+  if (!e || !e->step_ev || ring_slot < 0 || !arm_ms) return FPX_ERR_INVALID_ARG;
+  cudaEvent_t* ev = e->step_ev + (size_t)(ring_slot % kStepRing) * 4;
+  CK(e, cudaEventSynchronize(ev[3]));
+  CK(e, cudaEventElapsedTime(arm_ms, ev[1], ev[2]));
   return FPX_OK;
 }
 
@@ -824,6 +1023,21 @@ int fpx_chosen_watermark(fpx_engine* e, int32_t* out) {
   c = fpx_sync(e, &r);
   *out = r.watermark;
   return c;
+}
+
+int fpx_global_watermark(fpx_engine* e, uint32_t epoch, int32_t timeout_ms, int32_t* out, int32_t* frontiers) {
+  if (!e || !out) return FPX_ERR_INVALID_ARG;
+  CK(e, cudaSetDevice(e->cfg.device));
+  int c = fpx_global_watermark_dev(e, epoch, timeout_ms, e->xch_out, e->xch_out + 1);
+  if (c != FPX_OK) return c;
+  fpx_sync_result r;
+  c = fpx_sync(e, &r);
+  if (c != FPX_OK) return c;
+  int32_t host[1 + kMaxShards];
+  CK(e, cudaMemcpy(host, e->xch_out, (size_t)(1 + e->g.shard_count) * 4, cudaMemcpyDeviceToHost));
+  *out = host[0];
+  if (frontiers) memcpy(frontiers, host + 1, (size_t)e->g.shard_count * 4);
+  return FPX_OK;
 }
 
 int fpx_quorum_eval(fpx_engine* e, int32_t which, const uint32_t* masks, int32_t n, uint8_t* out) {

@@ -71,7 +71,7 @@ __global__ void __launch_bounds__(256) replica_chosen_kernel(ReplicaParams P) {
 // watermark.  Coalesced scan of the replica log over [watermark, last chosen + 2); the
 // last CTA to finish publishes the result.
 __global__ void __launch_bounds__(256) watermark_scan_kernel(Geometry g, const unsigned long long* rlog,
-                                                            DevStatus* st, int32_t* d_out) {
+                                                            DevStatus* st, int32_t* d_out, DevExchange* xch) {
   __shared__ int s_found[8];
   __shared__ bool s_last;
   const int lo = __ldcg(&st->wm_local);
@@ -109,6 +109,33 @@ __global__ void __launch_bounds__(256) watermark_scan_kernel(Geometry g, const u
   int global = f * g.shard_count + g.shard_index;
   st->watermark = global;
   if (d_out) *d_out = global;
+  exchange_publish(xch, global);
+}
+
+// Global executable prefix of a sharded log as of publication `epoch` of every shard: lane p waits until
+// entry p of this engine's table carries an epoch >= `epoch` (peers store into it over NVLink), then the
+// minimum (Replica.scala:397-402: execution stops at the first hole of the GLOBAL log).  Bounded wait.
+__global__ void global_watermark_kernel(DevExchange* x, const unsigned long long* table, uint32_t epoch,
+                                        int32_t* d_out, int32_t* d_frontiers, DevStatus* st,
+                                        unsigned long long timeout_ns) {
+  const int lane = threadIdx.x;
+  int mine = INT_MAX;
+  bool late = false;
+  const unsigned long long t0 = global_timer_ns();
+  for (int p = lane; p < x->n; p += 32) {
+    unsigned long long v;
+    do {
+      asm volatile("ld.global.acquire.sys.u64 %0, [%1];" : "=l"(v) : "l"(table + p) : "memory");
+      if ((int32_t)((uint32_t)(v >> 32) - epoch) >= 0) break;
+      if (global_timer_ns() - t0 > timeout_ns) { late = true; break; }
+      __nanosleep(200);
+    } while (true);
+    if (d_frontiers) d_frontiers[p] = (int32_t)(uint32_t)v;
+    mine = min(mine, (int32_t)(uint32_t)v);
+  }
+  mine = __reduce_min_sync(0xffffffffu, mine);
+  if (__any_sync(0xffffffffu, late) && lane == 0) report_error(st, FPX_ERR_EXCHANGE_TIMEOUT, 0);
+  if (lane == 0 && d_out) *d_out = mine;
 }
 __global__ void renormalize_rlog_kernel(unsigned long long* rlog, size_t n) {
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;

@@ -75,6 +75,7 @@ struct TallyParams {
   uint32_t rseq_base;         // delivery sequence number of this call's first Chosen record
   int32_t fuse_watermark;     // 1: also the first-hole scan (last sub-launch of a call)
   int32_t* d_watermark;       // optional device copy of the new watermark
+  DevExchange* xch;           // multi-GPU: the new watermark also goes to every peer's frontier table
   DevStatus* st;
 };
 
@@ -618,6 +619,7 @@ __global__ void __launch_bounds__(kTT, 1) tally_kernel(TallyParams P) {
       const int global = f * g.shard_count + g.shard_index;
       P.st->watermark = global;
       if (P.d_watermark) *P.d_watermark = global;
+      exchange_publish(P.xch, global);
     }
   }
   FPX_MARK(P.st->t_tally, 7);

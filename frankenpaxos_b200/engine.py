@@ -109,6 +109,35 @@ class Engine:
     def launch_count(self):
         return self._L.fpx_launch_count(self.h)
 
+    # -- the exchange of a sharded log (include/fpx.h, fpx_exchange_*)
+    def exchange_export(self):
+        """IPC handle (bytes) of this engine's frontier table."""
+        buf = C.create_string_buffer(64)
+        self._check(self._L.fpx_exchange_export(self.h, buf))
+        return buf.raw
+
+    def exchange_attach(self, shard, handle):
+        """Open shard `shard`'s table (exported by another process) so that this engine's watermark
+        publications are also stored there over NVLink."""
+        self._check(self._L.fpx_exchange_attach(self.h, shard, C.c_char_p(bytes(handle))))
+
+    def exchange_attach_local(self, shard, peer):
+        self._check(self._L.fpx_exchange_attach_local(self.h, shard, peer.h))
+
+    @property
+    def exchange_epoch(self):
+        return self._L.fpx_exchange_epoch(self.h)
+
+    def global_watermark(self, epoch=None, timeout_ms=5000):
+        """(global executable prefix, every shard's frontier) as of publication `epoch` of every shard
+        (default: this engine's own latest publication)."""
+        n = self.cfg.shard_count
+        fr = np.empty(n, dtype=np.int32)
+        out = C.c_int32(0)
+        ep = self.exchange_epoch if epoch is None else epoch
+        self._check(self._L.fpx_global_watermark(self.h, ep, timeout_ms, C.byref(out), fr.ctypes.data))
+        return out.value, fr
+
     # -- test / profiling aids (not part of include/fpx.h)
     def set_tally_path(self, exact):
         """exact=True: every tally launch evaluates each vote (no row sweep)."""
@@ -332,10 +361,27 @@ class Engine:
         self._check(self._L.fpx_step_dev(self.h, d_arm, n_arm, d_p2a, n_p2a, d_out_p2b, d_out_nack, d_p2b, n_p2b,
                                          d_out_chosen, d_wm, ring_slot))
 
+    def step_submit(self, arm, n_arm, p2a, n_p2a, p2b, n_p2b, out_p2b, out_nack, out_chosen):
+        """Asynchronous step from HOST pointers (ints; pinned memory recommended), at most two in flight;
+        arm = None arms from the Phase2a batch itself.  Pair with step_wait()."""
+        self._check(self._L.fpx_step_submit(self.h, arm, n_arm, p2a, n_p2a, p2b, n_p2b, out_p2b, out_nack, out_chosen))
+
+    def step_wait(self):
+        """Completes the oldest submitted step: (n_p2b, n_nack, n_chosen, watermark)."""
+        a, b, c, w, err = C.c_int32(0), C.c_int32(0), C.c_int32(0), C.c_int32(0), C.c_int64(-1)
+        st = self._L.fpx_step_wait(self.h, C.byref(a), C.byref(b), C.byref(c), C.byref(w), C.byref(err))
+        self._check(st, err.value)
+        return a.value, b.value, c.value, w.value
+
     def step_kernel_ms(self, ring_slot):
         a, t = C.c_float(0), C.c_float(0)
         self._check(self._L.fpx_step_kernel_ms(self.h, ring_slot, C.byref(a), C.byref(t)))
         return a.value, t.value
+
+    def step_arm_ms(self, ring_slot):
+        a = C.c_float(0)
+        self._check(self._L.fpx_step_arm_ms(self.h, ring_slot, C.byref(a)))
+        return a.value
 
     def set_coop_ctas_per_sm(self, k):
         """Cap the cooperative kernels at k resident CTAs per SM (0 = full grid) so that

@@ -39,6 +39,29 @@ def global_watermark(first_unchosen_global_slot, group=None):
     return int(out.min().item()), out
 
 
+def connect(engine, group=None):
+    """Wire the engines of a sharded log (one per rank) together: every rank exports the IPC handle of
+    its frontier table, the handles are all-gathered (plumbing: torch.distributed, any backend), and
+    every rank attaches every peer's table.  After this, each engine's watermark publication lands in
+    all tables over NVLink from inside the publishing kernel (include/fpx.h, fpx_exchange_*), and
+    `engine.global_watermark()` is a local read."""
+    import torch
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return []
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    mine = torch.frombuffer(bytearray(engine.exchange_export()), dtype=torch.uint8).clone()
+    dev = "cuda" if dist.get_backend(group) == "nccl" else "cpu"
+    gathered = [torch.empty(64, dtype=torch.uint8, device=dev) for _ in range(world)]
+    dist.all_gather(gathered, mine.to(dev), group=group)
+    handles = [bytes(t.cpu().numpy().tobytes()) for t in gathered]
+    for shard, h in enumerate(handles):
+        if shard != rank:
+            engine.exchange_attach(shard, h)
+    dist.barrier(group=group)        # every table is attached everywhere before anyone publishes
+    return handles
+
+
 def merge_chosen_in_slot_order(per_rank_chosen):
     """A replica's view of the sharded log: Chosen records of all ranks by slot."""
     allc = np.concatenate(per_rank_chosen)

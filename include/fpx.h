@@ -105,6 +105,7 @@ typedef enum {
                                       advanceWithSkips: a slot to skip is not vacant)   */
   FPX_ERR_WIRE = -15,              /* malformed protobuf bytes: what parseFrom rejects with
                                       InvalidProtocolBufferException                    */
+  FPX_ERR_EXCHANGE_TIMEOUT = -16,  /* fpx_global_watermark: a shard did not publish in time */
   FPX_ERR_EPAXOS_STATE = -13       /* transitionToPreAcceptPhase on a committed instance or
                                       with a regressing ballot: logger.fatal / checkLe,
                                       S/epaxos/Replica.scala:663-681                       */
@@ -501,10 +502,12 @@ typedef struct {
 
 int fpx_sync(fpx_engine* e, fpx_sync_result* out);
 
-/* One pipeline step on device-resident buffers, issued back to back from C: fpx_proxyleader_arm_dev,
- * fpx_acceptor_phase2a_dev, fpx_proxyleader_phase2b_dev, fpx_replica_chosen_last_dev,
- * fpx_chosen_watermark_dev -- exactly those five calls (co-located roles chained on one GPU; a
- * caller-side loop in a slow language otherwise pays its per-call overhead five times per step).
+/* One pipeline step of co-located roles on device-resident buffers, issued from one C call, with the same
+ * results as fpx_proxyleader_arm_dev, fpx_acceptor_phase2a_dev, fpx_proxyleader_phase2b_dev,
+ * fpx_replica_chosen_last_dev, fpx_chosen_watermark_dev in that order -- in three launches: the acceptor
+ * batch, the arm batch (disjoint state, so the order of those two is free; the rows armed last are still
+ * L2-resident when the votes are tallied), and the tally with the replica's handleChosen and the watermark
+ * scan (+ the multi-GPU exchange store) riding in the same cooperative kernel.
  * ring_slot >= 0 additionally records CUDA events on the engine's stream before and after the
  * acceptor and the tally kernel; fpx_step_kernel_ms(ring_slot) returns their durations once the
  * step has run (a ring of 1024 steps). */
@@ -512,6 +515,47 @@ int fpx_step_dev(fpx_engine* e, const fpx_p2a* d_arm, int32_t n_arm, const fpx_p
                  fpx_p2b* d_out_p2b, fpx_nack* d_out_nack, const fpx_p2b* d_p2b, int32_t n_p2b, fpx_chosen* d_out_chosen,
                  int32_t* d_watermark, int32_t ring_slot);
 int fpx_step_kernel_ms(fpx_engine* e, int32_t ring_slot, float* acceptor_ms, float* tally_ms);
+int fpx_step_arm_ms(fpx_engine* e, int32_t ring_slot, float* arm_ms);   /* the arm kernel of the same step */
+
+/* One pipeline step from HOST buffers, asynchronous and double-buffered, for co-located roles on one GPU
+ * (pinned host memory recommended).  fpx_step_submit enqueues: H2D of the Phase2a batch and of the Phase2b
+ * batch on a copy stream; the acceptor batch; the arm batch -- arm == NULL arms from the Phase2a batch itself
+ * (ProxyLeader.handlePhase2a ignores a key it already holds, S/multipaxos/ProxyLeader.scala:177-183, so arming
+ * with every forwarded copy leaves the same state as arming once per slot); the tally with the replica's
+ * handleChosen and the watermark; D2H of the Phase2b replies on a second copy stream while the tally runs.
+ * fpx_step_wait completes the OLDEST submitted step: counts, watermark, error status, and the Chosen
+ * stream's D2H (its length is known only then).  At most 2 steps may be in flight, so the H2D of step k+1
+ * overlaps the kernels and the D2H of step k (full-duplex PCIe).  The output buffers of a step must stay
+ * valid until its fpx_step_wait returns.  Same semantics and errors as the five separate host calls. */
+int fpx_step_submit(fpx_engine* e, const fpx_p2a* arm, int32_t n_arm, const fpx_p2a* p2a, int32_t n_p2a,
+                    const fpx_p2b* p2b, int32_t n_p2b, fpx_p2b* out_p2b, fpx_nack* out_nack, fpx_chosen* out_chosen);
+int fpx_step_wait(fpx_engine* e, int32_t* n_out_p2b, int32_t* n_out_nack, int32_t* n_out_chosen, int32_t* watermark,
+                  int64_t* err_index);
+
+/* ---- the exchange of a sharded log -------------------------------------------------
+ * P engines, one per GPU (one process per GPU, or several engines in one process), shard_index g of
+ * shard_count P, each hold one residue class of ONE global log.  Replicas execute in slot order and stop
+ * at the first hole (S/multipaxos/Replica.scala:397-402; S/mencius/Replica.scala:334-370), so the global
+ * executable prefix is the minimum over the shards of each shard's first unchosen GLOBAL slot.  Every
+ * engine owns a frontier table {epoch, frontier}[P] in its device memory.  Once a peer's table is
+ * attached, the kernel that publishes this engine's watermark (fpx_chosen_watermark[_dev], fpx_step_dev)
+ * also stores {epoch, watermark} into entry g of that table over NVLink: peer-mapped stores from inside
+ * the kernel, an all-gather without a collective launch.  epoch = number of this engine's watermark
+ * publications since fpx_create / fpx_reset (every shard publishes once per step).
+ *   fpx_exchange_export   the IPC handle (cudaIpcMemHandle_t, FPX_EXCHANGE_HANDLE_BYTES) of this engine's table
+ *   fpx_exchange_attach   open shard `shard`'s table from its exported handle (other process, other GPU)
+ *   fpx_exchange_attach_local  same, for an engine of this process
+ *   fpx_global_watermark[_dev]  waits on the device (bounded: FPX_ERR_EXCHANGE_TIMEOUT after timeout_ms)
+ *                         until every shard's entry carries an epoch >= `epoch`, then returns the minimum;
+ *                         frontiers (optional, [P]) receives every shard's entry. */
+#define FPX_EXCHANGE_HANDLE_BYTES 64
+#define FPX_MAX_SHARDS 64
+int fpx_exchange_export(fpx_engine* e, void* handle);
+int fpx_exchange_attach(fpx_engine* e, int32_t shard, const void* handle);
+int fpx_exchange_attach_local(fpx_engine* e, int32_t shard, fpx_engine* peer);
+uint32_t fpx_exchange_epoch(const fpx_engine* e);
+int fpx_global_watermark_dev(fpx_engine* e, uint32_t epoch, int32_t timeout_ms, int32_t* d_out, int32_t* d_frontiers);
+int fpx_global_watermark(fpx_engine* e, uint32_t epoch, int32_t timeout_ms, int32_t* out, int32_t* frontiers);
 
 /* The engine's CUDA stream (a cudaStream_t) so a caller can order its own work
  * (events, NCCL collectives) with the engine's. */

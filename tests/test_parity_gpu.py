@@ -845,3 +845,63 @@ def test_bench_shaped_step_on_a_rebased_window_matches_the_oracle(tally_path):
     H.compare_acceptors(eng, ora, cfg, win * W, W)
     H.compare_log(eng, ora, win * W, W)
     eng.close()
+
+
+def test_async_host_step_matches_oracle(tally_path):
+    """fpx_step_submit / fpx_step_wait: double-buffered host-pointer steps (what bench.py's e2e times),
+    arming from the Phase2a batch itself (arm = NULL) and from an explicit arm batch; a round bump in the
+    middle exercises the Nack re-copy.  Streams, counts, watermark and final state vs the oracle."""
+    import torch
+    cfg, _ = T.config_by_name("cfg2")
+    W_, n_steps = 5000, 4
+    eng, ora = H.make_pair(cfg, n_steps * W_, max_batch=1 << 16, overflow_capacity=1 << 12)
+    g = T.rng(123)
+    steps = []
+    for w in range(n_steps):
+        a, p, b = T.workload(60 + w, cfg, W_, slot0=w * W_, round_=3 if w == 3 else 0)   # the new leader's round after the bump
+        if w == 2:   # a newer leader's Phase2as for some slots of this window, delivered in the middle
+            sl = np.arange(w * W_, w * W_ + W_, 40, dtype=np.int32)
+            hi = T.phase2as(g, sl, cfg["f"], 1, 5, False, 3, sl * 2)
+            p = np.concatenate([p[: len(p) // 2], hi, p[len(p) // 2:]])
+            a = np.concatenate([a, T.arms(sl, 3, sl * 2)])
+        steps.append((a, p))
+    pin = lambda x: torch.from_numpy(x.view(np.int32).reshape(len(x), x.dtype.itemsize // 4).copy()).pin_memory()
+    outs = []
+    expect = []
+    # the votes of step w are the oracle's replies of step w, shuffled: compute the oracle first
+    for w, (a, p) in enumerate(steps):
+        ora.arm(a)
+        _, _, ob, on = ora.acceptor_phase2a(p)
+        votes = ob[g.permutation(len(ob))]
+        _, _, oc = ora.proxyleader_phase2b(votes)
+        ora.replica_chosen(oc)
+        expect.append((ob, on, oc, ora.executed_watermark(), votes))
+    bufs = []
+    for w, (a, p) in enumerate(steps):
+        votes = expect[w][4]
+        hp, hv = pin(p), pin(votes)
+        ha = pin(a) if w % 2 else None          # odd steps: explicit arm batch; even steps: arm from the Phase2as
+        o1 = torch.zeros((len(p), 4), dtype=torch.int32).pin_memory()
+        o2 = torch.zeros((len(p), 2), dtype=torch.int32).pin_memory()
+        o3 = torch.zeros((len(votes), 2), dtype=torch.int32).pin_memory()
+        bufs.append((hp, hv, ha, o1, o2, o3))
+        if w == 2 and ha is None:
+            # arming from the Phase2a stream covers the bumped keys too (they are in the stream)
+            pass
+        eng.step_submit(ha.data_ptr() if ha is not None else None, len(a) if ha is not None else 0, hp.data_ptr(), len(p),
+                        hv.data_ptr(), len(votes), o1.data_ptr(), o2.data_ptr(), o3.data_ptr())
+        if w >= 1:
+            outs.append(eng.step_wait())
+    outs.append(eng.step_wait())
+    for w in range(n_steps):
+        ob, on, oc, wm, _ = expect[w]
+        n1, n2, n3, gw = outs[w]
+        assert (n1, n2, n3, gw) == (len(ob), len(on), len(oc), wm), (w, outs[w], (len(ob), len(on), len(oc), wm))
+        _, _, _, o1, o2, o3 = bufs[w]
+        H.same(o1[:n1].numpy().view(P2B).reshape(-1), ob, f"Phase2b stream, step {w}")
+        H.same(o2[:n2].numpy().view(NACK).reshape(-1), on, f"Nack stream, step {w}")
+        H.same(o3[:n3].numpy().view(CHOSEN).reshape(-1), oc, f"Chosen stream, step {w}")
+    assert len(expect[2][1]) > 0
+    H.compare_acceptors(eng, ora, cfg, 0, n_steps * W_)
+    H.compare_log(eng, ora, 0, n_steps * W_)
+    eng.close()

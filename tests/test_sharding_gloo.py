@@ -65,3 +65,41 @@ def test_global_watermark_two_ranks(hole):
     assert sum(r[3] for r in res) == n_slots - 1
     owner = hole % world
     assert res[0][2][owner] == hole and res[0][2][1 - owner] >= n_slots
+
+
+class _FakeEngine:
+    """Stands in for Engine: records what sharding.connect attaches (the C ABI is exercised on the GPU)."""
+    def __init__(self, rank):
+        self.rank, self.attached = rank, {}
+    def exchange_export(self):
+        return bytes([self.rank + 1]) * 64
+    def exchange_attach(self, shard, handle):
+        self.attached[shard] = handle
+
+
+def _connect_worker(rank, world, port, q):
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from frankenpaxos_b200 import sharding as S
+    e = _FakeEngine(rank)
+    handles = S.connect(e)
+    q.put((rank, sorted(e.attached), [h[0] for h in handles], all(len(h) == 64 for h in handles)))
+    dist.destroy_process_group()
+
+
+def test_connect_routes_every_peer_handle():
+    """sharding.connect: every rank attaches every OTHER rank's exported table handle (64 bytes each)."""
+    world = 3
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_connect_worker, args=(r, world, port, q)) for r in range(world)]
+    [p.start() for p in procs]
+    res = sorted(q.get(timeout=120) for _ in range(world))
+    [p.join(timeout=60) for p in procs]
+    assert all(p.exitcode == 0 for p in procs)
+    for rank, attached, first_bytes, ok in res:
+        assert attached == [g for g in range(world) if g != rank]
+        assert first_bytes == [1, 2, 3] and ok
