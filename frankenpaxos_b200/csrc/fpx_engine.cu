@@ -14,10 +14,13 @@
 #include <algorithm>
 #include <new>
 #include <string>
+#include <vector>
 
 #include "fpx_acceptor.cuh"
 #include "fpx_arm.cuh"
 #include "fpx_common.cuh"
+#include "fpx_conflict.cuh"
+#include "fpx_depgraph.cuh"
 #include "fpx_epaxos.cuh"
 #include "fpx_ranges.cuh"
 #include "fpx_replica_misc.cuh"
@@ -1145,3 +1148,4 @@ int fpx_snapshot_log(fpx_engine* e, int32_t first_slot, int32_t n_slots, int32_t
 }  // extern "C"
 
 #include "fpx_engine_epaxos.inc"
+#include "fpx_engine_f4.inc"

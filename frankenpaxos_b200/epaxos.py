@@ -133,3 +133,123 @@ def depset_union_dense_dev(d_in, n_groups, sets_per_group, n_replicas, d_out, st
     st = L.fpx_depset_union_dense_dev(device, d_in, n_groups, sets_per_group, n_replicas, d_out, stream)
     if st != 0:
         raise FpxError(st)
+
+
+# --------------------------------------------------------------------------- execution side
+def _bind_f4(L):
+    if getattr(L, "_f4_bound", False):
+        return
+    vp, i32, p = C.c_void_p, C.c_int32, C.POINTER
+    L.fpx_conflict_index_create.argtypes = [p(vp), i32, i32, i32, i32, i32]; L.fpx_conflict_index_create.restype = i32
+    L.fpx_conflict_index_destroy.argtypes = [vp]; L.fpx_conflict_index_destroy.restype = None
+    L.fpx_conflict_index_put_snapshot.argtypes = [vp, i32, i32]; L.fpx_conflict_index_put_snapshot.restype = i32
+    L.fpx_conflict_index_batch.argtypes = [vp, vp, vp, vp, vp, vp, i32, i32, vp, p(C.c_int64)]
+    L.fpx_conflict_index_batch.restype = i32
+    L.fpx_depgraph_create.argtypes = [p(vp), i32, i32, i32, i32]; L.fpx_depgraph_create.restype = i32
+    L.fpx_depgraph_destroy.argtypes = [vp]; L.fpx_depgraph_destroy.restype = None
+    L.fpx_depgraph_commit.argtypes = [vp, vp, vp, vp, vp, i32, p(C.c_int64)]; L.fpx_depgraph_commit.restype = i32
+    L.fpx_depgraph_update_executed.argtypes = [vp, vp, i32, p(C.c_int64)]; L.fpx_depgraph_update_executed.restype = i32
+    L.fpx_depgraph_execute.argtypes = [vp, vp, vp, p(i32), vp]; L.fpx_depgraph_execute.restype = i32
+    L._f4_bound = True
+
+
+class ConflictIndex:
+    """KeyValueStore's top-1 conflict index on the GPU (include/fpx.h, fpx_conflict_index_*)."""
+    QUERY_THEN_PUT, PUT, QUERY = 0, 1, 2
+
+    def __init__(self, num_leaders, key_capacity=1 << 16, max_commands=1 << 16, max_keys=1 << 17, device=0):
+        self._L = _lib.lib()
+        _bind_f4(self._L)
+        self.n = num_leaders
+        self.h = C.c_void_p()
+        st = self._L.fpx_conflict_index_create(C.byref(self.h), num_leaders, key_capacity, max_commands, max_keys, device)
+        if st != 0:
+            self.h = None
+            raise FpxError(st)
+
+    def close(self):
+        if getattr(self, "h", None):
+            self._L.fpx_conflict_index_destroy(self.h)
+            self.h = None
+
+    __del__ = close
+
+    def put_snapshot(self, leader, id_):
+        st = self._L.fpx_conflict_index_put_snapshot(self.h, leader, id_)
+        if st != 0:
+            raise FpxError(st)
+
+    def batch(self, leader, id_, is_set, key_lists, mode=0):
+        """Commands in delivery order; key_lists[i] = the keys of command i.  Returns deps [n_cmd, num_leaders]
+        (None for mode PUT)."""
+        n = len(leader)
+        leader = np.ascontiguousarray(leader, dtype=np.int32); id_ = np.ascontiguousarray(id_, dtype=np.int32)
+        is_set = np.ascontiguousarray(is_set, dtype=np.uint8)
+        off = np.zeros(n + 1, dtype=np.int32)
+        off[1:] = np.cumsum([len(k) for k in key_lists])
+        keys = np.ascontiguousarray(np.concatenate([np.asarray(k, dtype=np.int32) for k in key_lists])
+                                    if off[-1] else np.zeros(0, dtype=np.int32), dtype=np.int32)
+        out = np.zeros((max(n, 1), self.n), dtype=np.int32)
+        err = C.c_int64(-1)
+        st = self._L.fpx_conflict_index_batch(self.h, leader.ctypes.data, id_.ctypes.data, is_set.ctypes.data,
+                                              off.ctypes.data, keys.ctypes.data if len(keys) else None, n, mode,
+                                              out.ctypes.data, C.byref(err))
+        if st != 0:
+            raise FpxError(st, err.value)
+        return None if mode == self.PUT else out[:n]
+
+
+class DependencyGraph:
+    """TarjanDependencyGraph on the GPU (include/fpx.h, fpx_depgraph_*): int keys in [0, key_capacity)."""
+
+    def __init__(self, key_capacity=1 << 12, dep_pool_capacity=1 << 16, max_batch=1 << 12, device=0):
+        self._L = _lib.lib()
+        _bind_f4(self._L)
+        self.cap = key_capacity
+        self.h = C.c_void_p()
+        st = self._L.fpx_depgraph_create(C.byref(self.h), key_capacity, dep_pool_capacity, max_batch, device)
+        if st != 0:
+            self.h = None
+            raise FpxError(st)
+
+    def close(self):
+        if getattr(self, "h", None):
+            self._L.fpx_depgraph_destroy(self.h)
+            self.h = None
+
+    __del__ = close
+
+    def commit(self, keys, seqs, dep_lists):
+        n = len(keys)
+        keys = np.ascontiguousarray(keys, dtype=np.int32); seqs = np.ascontiguousarray(seqs, dtype=np.int32)
+        off = np.zeros(n + 1, dtype=np.int32)
+        off[1:] = np.cumsum([len(d) for d in dep_lists])
+        deps = np.ascontiguousarray(np.concatenate([np.asarray(d, dtype=np.int32) for d in dep_lists])
+                                    if off[-1] else np.zeros(0, dtype=np.int32), dtype=np.int32)
+        err = C.c_int64(-1)
+        st = self._L.fpx_depgraph_commit(self.h, keys.ctypes.data, seqs.ctypes.data, off.ctypes.data,
+                                         deps.ctypes.data if len(deps) else None, n, C.byref(err))
+        if st != 0:
+            raise FpxError(st, err.value)
+
+    def update_executed(self, keys):
+        keys = np.ascontiguousarray(keys, dtype=np.int32)
+        err = C.c_int64(-1)
+        st = self._L.fpx_depgraph_update_executed(self.h, keys.ctypes.data, len(keys), C.byref(err))
+        if st != 0:
+            raise FpxError(st, err.value)
+
+    def execute_by_component(self):
+        """(components in dependency order, each a list of keys sorted by (seq, key); sorted blockers)."""
+        out = np.zeros(self.cap, dtype=np.int32); head = np.zeros(self.cap, dtype=np.uint8)
+        bl = np.zeros(self.cap, dtype=np.uint8)
+        n = C.c_int32(0)
+        st = self._L.fpx_depgraph_execute(self.h, out.ctypes.data, head.ctypes.data, C.byref(n), bl.ctypes.data)
+        if st != 0:
+            raise FpxError(st)
+        comps = []
+        for p in range(n.value):
+            if head[p]:
+                comps.append([])
+            comps[-1].append(int(out[p]))
+        return comps, np.nonzero(bl)[0].tolist()

@@ -517,6 +517,40 @@ int fpx_step_dev(fpx_engine* e, const fpx_p2a* d_arm, int32_t n_arm, const fpx_p
 int fpx_step_kernel_ms(fpx_engine* e, int32_t ring_slot, float* acceptor_ms, float* tally_ms);
 int fpx_step_arm_ms(fpx_engine* e, int32_t ring_slot, float* arm_ms);   /* the arm kernel of the same step */
 
+/* ---- EPaxos, the execution side ----------------------------------------------
+ * Top-1 conflict index: KeyValueStore.typedTopKConflictIndex(k = 1), S/statemachine/KeyValueStore.scala:219-302,
+ * consulted by epaxos.Replica.computeSequenceNumberAndDependencies (S/epaxos/Replica.scala:569-600).  Keys are
+ * caller-assigned int32 ids of the reference's string keys (INT32_MIN is reserved).  One batch = commands in
+ * delivery order; command i is instance (leader[i], id[i]), a set (is_set[i] != 0) or a get, on the keys
+ * keys[key_off[i] .. key_off[i+1]).  mode 0: for every command getTopOneConflicts (it sees every earlier
+ * command of the batch and every earlier batch), then put (:1252, :1274); mode 1: put only; mode 2: query only.
+ * deps_out[i * num_leaders + L] = the TopOne watermark of leader column L (largest conflicting id + 1, 0 = none);
+ * a command without keys conflicts with the snapshots only.  FPX_ERR_OVERFLOW_FULL: more distinct keys than
+ * key_capacity (a power of two).  num_leaders <= 8. */
+typedef struct fpx_conflict_index fpx_conflict_index;
+int fpx_conflict_index_create(fpx_conflict_index** out, int32_t num_leaders, int32_t key_capacity, int32_t max_commands,
+                              int32_t max_keys, int32_t device);
+void fpx_conflict_index_destroy(fpx_conflict_index* c);
+int fpx_conflict_index_put_snapshot(fpx_conflict_index* c, int32_t leader, int32_t id);
+int fpx_conflict_index_batch(fpx_conflict_index* c, const int32_t* leader, const int32_t* id, const uint8_t* is_set,
+                             const int32_t* key_off, const int32_t* keys, int32_t n_cmd, int32_t mode, int32_t* deps_out,
+                             int64_t* err_index);
+/* Dependency graph: depgraph.TarjanDependencyGraph, S/depgraph/TarjanDependencyGraph.scala:225-451.  Keys are
+ * int32 in [0, key_capacity).  commit: a batch of (key, sequenceNumber, dependencies) in delivery order, CSR
+ * dependencies deps[dep_off[i] .. dep_off[i+1]); a key that is already committed or executed is ignored (:230-234).
+ * execute = executeByComponent(None): the executable keys (everything they transitively depend on is committed or
+ * executed), as components in dependency order (a component after every component it depends on), each sorted by
+ * (sequenceNumber, key); out_component_head[p] = 1 where a component starts.  The order among INDEPENDENT
+ * components is (level, root key) -- the reference's is a hash map's iteration order (:343), its tests accept any.
+ * blockers (optional, key_capacity bytes): 1 for every uncommitted key a committed one waits for. */
+typedef struct fpx_depgraph fpx_depgraph;
+int fpx_depgraph_create(fpx_depgraph** out, int32_t key_capacity, int32_t dep_pool_capacity, int32_t max_batch, int32_t device);
+void fpx_depgraph_destroy(fpx_depgraph* g);
+int fpx_depgraph_commit(fpx_depgraph* g, const int32_t* keys, const int32_t* seqs, const int32_t* dep_off, const int32_t* deps,
+                        int32_t n, int64_t* err_index);
+int fpx_depgraph_update_executed(fpx_depgraph* g, const int32_t* keys, int32_t n, int64_t* err_index);
+int fpx_depgraph_execute(fpx_depgraph* g, int32_t* out_keys, uint8_t* out_component_head, int32_t* n_out, uint8_t* blockers);
+
 /* One pipeline step from HOST buffers, asynchronous and double-buffered, for co-located roles on one GPU
  * (pinned host memory recommended).  fpx_step_submit enqueues: H2D of the Phase2a batch and of the Phase2b
  * batch on a copy stream; the acceptor batch; the arm batch -- arm == NULL arms from the Phase2a batch itself
