@@ -133,101 +133,201 @@ __global__ void ep_lead_kernel(EpParams P) {
 // in row preaccept: {rep, num, b_ord, b_rep, value, seq, local_deps[n], msg_deps[n]}
 // in row accept:    {rep, num, b_ord, b_rep, value, seq, deps[n]}
 // out row: {kind, b_ord, b_rep, seq, deps[n]}
+// A CTA takes a tile of 256 messages: the tile's input rows (one contiguous span) are staged in shared
+// memory with coalesced 128-bit loads (row stride padded to an odd word count: conflict-free reads), the
+// replies are staged the same way and leave with coalesced stores; the cmdLog row is one 64-byte line
+// read and written as four 128-bit words; largestBallot is reduced per CTA before it touches memory.
+constexpr int kEpTile = 256;
+__host__ __device__ __forceinline__ int ep_in_words(const EpGeometry& g, bool accept) { return accept ? 6 + g.n : 6 + 2 * g.n; }
+
 template <bool kAccept>
-__global__ void ep_acceptor_kernel(EpParams P) {
+__global__ void __launch_bounds__(kEpTile) ep_acceptor_kernel(EpParams P) {
   const EpGeometry& g = P.g;
-  const int W = kAccept ? 6 + g.n : 6 + 2 * g.n;
-  const int WO = 4 + g.n;
-  int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= P.n_rec) return;
-  const int32_t* r = P.in + (size_t)i * W;
-  int32_t* o = P.out + (size_t)i * WO;
-  P.s.proc_ballot[i] = 0;
-  o[0] = REPLY_NONE; o[1] = -1; o[2] = -1; o[3] = 0;
-  for (int k = 0; k < g.n; ++k) o[4 + k] = 0;
-  long long inst = ep_instance(g, r[0], r[1]);
-  if (inst < 0) { report_error(P.s.st, FPX_ERR_SLOT_RANGE, i); return; }
-  if (ep_claim(P.s, inst, P.tag, i)) return;
-  int32_t* c = P.s.cmd + inst * kEpCmdWords;
-  const unsigned long long b = ballot_key(r[2], r[3]);
-  const int kind = c[C_KIND];
-  if (kind == EK_COMMITTED) {                                   // :1223-1234 / :1466-1477 reply Commit
-    o[0] = REPLY_COMMIT; o[3] = c[C_SEQ];
-    for (int k = 0; k < g.n; ++k) o[4 + k] = c[C_DEPS + k];
-    return;
-  }
-  if (kind != EK_NONE) {
-    if (b < ballot_key(c[C_BORD], c[C_BREP])) {                 // stale ballot: Nack(largestBallot)
-      o[0] = REPLY_NACK;                                         // ballot filled by ep_nack_fixup_kernel
-      return;
-    }
-    unsigned long long vb = ballot_key(c[C_VBORD], c[C_VBREP]);
-    if (!kAccept) {
-      if (kind == EK_PREACCEPTED && b == vb) {                  // :1195-1208 re-send the stored answer
-        o[0] = REPLY_OK; o[1] = r[2]; o[2] = r[3]; o[3] = c[C_SEQ];
-        for (int k = 0; k < g.n; ++k) o[4 + k] = c[C_DEPS + k];
-        return;
+  extern __shared__ int32_t s_ep[];
+  __shared__ unsigned long long s_big[kEpTile / 32];
+  const int W = ep_in_words(g, kAccept), Wp = W | 1;
+  const int WO = 4 + g.n;                                       // odd: conflict-free as it is
+  int32_t* s_in = s_ep;
+  int32_t* s_out = s_ep + kEpTile * Wp;
+  const int tid = threadIdx.x;
+  const long long tile0 = (long long)blockIdx.x * kEpTile;
+  const int rows = (int)min((long long)kEpTile, P.n_rec - tile0);
+  {
+    const int words = rows * W;
+    const int4* src = (const int4*)(P.in + tile0 * W);          // 256 * W * 4 bytes per tile: 16-byte aligned
+    const uint32_t mW = 0xffffffffu / (uint32_t)W + 1u;         // e / W for e < 2^16
+    for (int v = tid; v < words / 4; v += kEpTile) {
+      const int4 x = ld_stream(src + v);
+      const int vals[4] = {x.x, x.y, x.z, x.w};
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const uint32_t e = 4u * v + q, row = __umulhi(e, mW);
+        s_in[row * Wp + (e - row * W)] = vals[q];
       }
-      if (kind == EK_ACCEPTED && b == vb) { o[1] = r[2]; o[2] = r[3]; return; }  // :1219-1221 drop
-    } else {
-      if (kind == EK_ACCEPTED && b == vb) {                     // :1455-1464 re-send AcceptOk
+    }
+    for (int e = (words & ~3) + tid; e < words; e += kEpTile) s_in[(e / W) * Wp + e % W] = P.in[tile0 * W + e];
+  }
+  __syncthreads();
+  const int i = (int)tile0 + tid;
+  unsigned long long proceeded = 0;
+  if (tid < rows) {
+    const int32_t* r = s_in + tid * Wp;
+    int32_t* o = s_out + tid * WO;
+    o[0] = REPLY_NONE; o[1] = -1; o[2] = -1; o[3] = 0;
+    for (int k = 0; k < g.n; ++k) o[4 + k] = 0;
+    const long long inst = ep_instance(g, r[0], r[1]);
+    if (inst < 0) {
+      report_error(P.s.st, FPX_ERR_SLOT_RANGE, i);
+    } else if (!ep_claim(P.s, inst, P.tag, i)) {
+      int4* c4 = (int4*)(P.s.cmd + inst * kEpCmdWords);
+      const int4 h0 = __ldcg(c4), h1 = __ldcg(c4 + 1);          // {kind, value, bord, brep} {vbord, vbrep, seq, pad}
+      const unsigned long long b = ballot_key(r[2], r[3]);
+      const int kind = h0.x;
+      bool done = false;
+      if (kind == EK_COMMITTED) {                               // :1223-1234 / :1466-1477 reply Commit
+        const int4 d0 = __ldcg(c4 + 2), d1 = __ldcg(c4 + 3);
+        const int dd[8] = {d0.x, d0.y, d0.z, d0.w, d1.x, d1.y, d1.z, d1.w};
+        o[0] = REPLY_COMMIT; o[3] = h1.z;
+        for (int k = 0; k < g.n; ++k) o[4 + k] = dd[k];
+        done = true;
+      } else if (kind != EK_NONE) {
+        if (b < ballot_key(h0.z, h0.w)) {                       // stale ballot: Nack(largestBallot)
+          o[0] = REPLY_NACK;                                    // ballot filled by the fix-up pass
+          atomicOr(&P.s.st->ts_flags, 1u);                      // this batch needs the fix-up
+          done = true;
+        } else {
+          const unsigned long long vb = ballot_key(h1.x, h1.y);
+          if (!kAccept && kind == EK_PREACCEPTED && b == vb) {  // :1195-1208 re-send the stored answer
+            const int4 d0 = __ldcg(c4 + 2), d1 = __ldcg(c4 + 3);
+            const int dd[8] = {d0.x, d0.y, d0.z, d0.w, d1.x, d1.y, d1.z, d1.w};
+            o[0] = REPLY_OK; o[1] = r[2]; o[2] = r[3]; o[3] = h1.z;
+            for (int k = 0; k < g.n; ++k) o[4 + k] = dd[k];
+            done = true;
+          } else if (!kAccept && kind == EK_ACCEPTED && b == vb) {
+            o[1] = r[2]; o[2] = r[3]; done = true;              // :1219-1221 drop
+          } else if (kAccept && kind == EK_ACCEPTED && b == vb) {
+            o[0] = REPLY_OK; o[1] = r[2]; o[2] = r[3]; done = true;   // :1455-1464 re-send AcceptOk
+          }
+        }
+      }
+      if (!done) {
+        // yield leadership to a higher ballot (:1240-1244 / :1482-1486)
+        int32_t* l = P.s.lead + inst * kEpLeadWords;
+        const int4 lh = __ldcg((const int4*)l);                 // {kind, value, bord, brep}
+        if (lh.x != LK_NONE && b > ballot_key(lh.z, lh.w)) l[L_KIND] = LK_NONE;
+        proceeded = b;                                          // largestBallot = max(..) (:1246 / :1489)
+        int seq = r[5];
+        int dd[8] = {0, 0, 0, 0, 0, 0, 0, 0};
         o[0] = REPLY_OK; o[1] = r[2]; o[2] = r[3];
-        return;
+        if (!kAccept) {
+          seq = max(0, seq);                                    // :1256 (local sequence number is 0, :599)
+          for (int k = 0; k < g.n; ++k) {
+            dd[k] = max(r[6 + k], r[6 + g.n + k]);              // deps.addAll(msg.deps) (:1257), dense
+            o[4 + k] = dd[k];
+          }
+          o[3] = seq;
+        } else {
+          for (int k = 0; k < g.n; ++k) dd[k] = r[6 + k];
+        }
+        __stcg(c4, make_int4(kAccept ? EK_ACCEPTED : EK_PREACCEPTED, r[4], r[2], r[3]));
+        __stcg(c4 + 1, make_int4(r[2], r[3], seq, 0));
+        __stcg(c4 + 2, make_int4(dd[0], dd[1], dd[2], dd[3]));
+        __stcg(c4 + 3, make_int4(dd[4], dd[5], dd[6], dd[7]));
       }
     }
+    P.s.proc_ballot[i] = proceeded;
   }
-  // yield leadership to a higher ballot (:1240-1244 / :1482-1486)
-  int32_t* l = P.s.lead + inst * kEpLeadWords;
-  if (l[L_KIND] != LK_NONE && b > ballot_key(l[L_BORD], l[L_BREP])) l[L_KIND] = LK_NONE;
-  P.s.proc_ballot[i] = b;                                       // largestBallot = max(..) (:1246 / :1489)
-  atomicMax(P.s.largest + 1, b);
-  int seq = r[5];
-  o[0] = REPLY_OK; o[1] = r[2]; o[2] = r[3];
-  if (!kAccept) {
-    seq = max(0, seq);                                          // :1256 (local sequence number is 0, :599)
-    for (int k = 0; k < g.n; ++k) {
-      int d = max(r[6 + k], r[6 + g.n + k]);                    // deps.addAll(msg.deps) (:1257), dense
-      c[C_DEPS + k] = d;
-      o[4 + k] = d;
-    }
-    o[3] = seq;
-    c[C_KIND] = EK_PREACCEPTED;
-  } else {
-    for (int k = 0; k < g.n; ++k) c[C_DEPS + k] = r[6 + k];
-    c[C_KIND] = EK_ACCEPTED;
+  // largestBallot of the batch: one atomic per CTA
+  unsigned long long m = proceeded;
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, d));
+  if ((tid & 31) == 0) s_big[tid >> 5] = m;
+  __syncthreads();
+  if (tid == 0) {
+#pragma unroll
+    for (int w = 1; w < kEpTile / 32; ++w) m = max(m, s_big[w]);
+    if (m) atomicMax(P.s.largest + 1, m);
   }
-  c[C_VALUE] = r[4]; c[C_BORD] = r[2]; c[C_BREP] = r[3]; c[C_VBORD] = r[2]; c[C_VBREP] = r[3]; c[C_SEQ] = seq;
+  // replies: coalesced
+  int32_t* dst = P.out + tile0 * WO;
+  for (int e = tid; e < rows * WO; e += kEpTile) __stcs(dst + e, s_out[e]);
 }
 
-// Nack(instance, largestBallot) carries largestBallot AS OF that delivery (:1166-1167):
-// the max over the handle's value at batch start and the ballots of the records
-// that proceeded before it.  One CTA per 256 records; each Nack scans its prefix.
-__global__ void ep_nack_fixup_kernel(EpParams P, int WO) {
-  __shared__ unsigned long long s_red[256];
-  const unsigned long long start = P.s.largest[0];
-  for (int i = blockIdx.x; i < P.n_rec; i += gridDim.x) {
+// Nack(instance, largestBallot) carries largestBallot AS OF that delivery (:1166-1167): the max over the
+// handle's value at batch start and the ballots of the records that proceeded before it -- an exclusive
+// prefix max over the batch.  Three small passes, run only when the batch produced a Nack.
+constexpr int kEpScanTile = 1024;
+__global__ void __launch_bounds__(kEpScanTile) ep_nack_tilemax_kernel(EpParams P, unsigned long long* tile_max) {
+  if (!(__ldcg(&P.s.st->ts_flags) & 1u)) return;
+  __shared__ unsigned long long s_w[32];
+  const int i = blockIdx.x * kEpScanTile + threadIdx.x;
+  unsigned long long m = i < P.n_rec ? P.s.proc_ballot[i] : 0ull;
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, d));
+  if ((threadIdx.x & 31) == 0) s_w[threadIdx.x >> 5] = m;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int w = 1; w < 32; ++w) m = max(m, s_w[w]);
+    tile_max[blockIdx.x] = m;
+  }
+}
+__global__ void __launch_bounds__(kEpScanTile) ep_nack_fixup_kernel(EpParams P, int WO, const unsigned long long* tile_max) {
+  if (!(__ldcg(&P.s.st->ts_flags) & 1u)) return;
+  __shared__ unsigned long long s_w[32];
+  __shared__ unsigned long long s_carry;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  // carry into this tile: largestBallot at batch start and every earlier tile
+  unsigned long long c = tid == 0 ? P.s.largest[0] : 0ull;
+  for (int t = tid; t < (int)blockIdx.x; t += kEpScanTile) c = max(c, tile_max[t]);
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) c = max(c, __shfl_xor_sync(0xffffffffu, c, d));
+  if (lane == 0) s_w[warp] = c;
+  __syncthreads();
+  if (tid == 0) { for (int w = 1; w < 32; ++w) c = max(c, s_w[w]); s_carry = c; }
+  __syncthreads();
+  const int i = blockIdx.x * kEpScanTile + tid;
+  const unsigned long long mine = i < P.n_rec ? P.s.proc_ballot[i] : 0ull;
+  unsigned long long incl = mine;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    unsigned long long o = __shfl_up_sync(0xffffffffu, incl, d);
+    if (lane >= d) incl = max(incl, o);
+  }
+  __syncthreads();
+  if (lane == 31) s_w[warp] = incl;
+  __syncthreads();
+  unsigned long long pre = s_carry;
+  for (int w = 0; w < warp; ++w) pre = max(pre, s_w[w]);
+  unsigned long long excl = __shfl_up_sync(0xffffffffu, incl, 1);
+  if (lane == 0) excl = 0;
+  excl = max(excl, pre);
+  if (i < P.n_rec) {
     int32_t* o = P.out + (size_t)i * WO;
-    if (o[0] != REPLY_NACK) continue;                           // uniform per block
-    unsigned long long m = start;
-    for (int j = threadIdx.x; j < i; j += blockDim.x) m = max(m, P.s.proc_ballot[j]);
-    s_red[threadIdx.x] = m;
-    __syncthreads();
-    for (int d = 128; d > 0; d >>= 1) {
-      if ((int)threadIdx.x < d) s_red[threadIdx.x] = max(s_red[threadIdx.x], s_red[threadIdx.x + d]);
-      __syncthreads();
-    }
-    if (threadIdx.x == 0) {
+    if (o[0] == REPLY_NACK) {
       int ord, rep;
-      key_ballot(s_red[0], ord, rep);
+      key_ballot(excl, ord, rep);
       o[1] = ord; o[2] = rep;
     }
-    __syncthreads();
   }
 }
 __global__ void ep_largest_commit_kernel(EpState s) {
   // largest[1] accumulated this batch's proceeding ballots; fold into largest[0]
   s.largest[0] = max(s.largest[0], s.largest[1]);
   s.largest[1] = 0;
+  s.st->ts_flags = 0;
+}
+
+// 32-bit response stamps: before they wrap, every recorded first-delivery stamp collapses to 0 ("before
+// everything"), like renormalize_stamps_kernel does for the MultiPaxos rows
+__global__ void ep_renormalize_kernel(EpState s, size_t n_inst) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_inst) return;
+  int32_t* l = s.lead + i * kEpLeadWords;
+  if (l[L_KIND] == LK_NONE) return;
+  for (int k = 0; k < kEpMaxN; ++k) {
+    if ((uint32_t)l[L_ASTAMP + k] != kStampEmpty) l[L_ASTAMP + k] = 0;
+    if ((uint32_t)l[L_RESP + k * kEpRespWords] != kStampEmpty) l[L_RESP + k * kEpRespWords] = 0;
+  }
 }
 
 // ---- handlePreAcceptOk (:1291-1419) / handleAcceptOk (:1514-1565), stamp pass

@@ -31,6 +31,13 @@ def _bind(L):
     L.fpx_depset_union.argtypes = [i32, vp, vp, vp, i32, vp, i32, vp, vp, vp]; L.fpx_depset_union.restype = i32
     L.fpx_epaxos_last_kernel_ms.argtypes = [vp]; L.fpx_epaxos_last_kernel_ms.restype = C.c_float
     L.fpx_depset_union_dense_dev.argtypes = [i32, vp, i32, i32, i32, vp, vp]; L.fpx_depset_union_dense_dev.restype = i32
+    L.fpx_epaxos_stream.argtypes = [vp]; L.fpx_epaxos_stream.restype = vp
+    L.fpx_epaxos_sync.argtypes = [vp, p(C.c_int64)]; L.fpx_epaxos_sync.restype = i32
+    L.fpx_epaxos_lead_dev.argtypes = [vp, vp, i32]; L.fpx_epaxos_lead_dev.restype = i32
+    for nm in ("fpx_epaxos_preaccept_dev", "fpx_epaxos_accept_dev", "fpx_epaxos_preacceptok_dev", "fpx_epaxos_acceptok_dev"):
+        f = getattr(L, nm)
+        f.argtypes = [vp, vp, i32, vp]; f.restype = i32
+    L.fpx_epaxos_preaccept_sets.argtypes = [vp, vp, i32, vp, vp, p(C.c_int64)]; L.fpx_epaxos_preaccept_sets.restype = i32
     L._ep_bound = True
 
 
@@ -90,6 +97,51 @@ class EpaxosReplica:
 
     def last_kernel_ms(self):
         return float(self._L.fpx_epaxos_last_kernel_ms(self.h))
+
+    # -- device-pointer calls (asynchronous on self.stream; errors collected by sync())
+    @property
+    def stream(self):
+        return self._L.fpx_epaxos_stream(self.h)
+
+    def sync(self):
+        err = C.c_int64(-1)
+        st = self._L.fpx_epaxos_sync(self.h, C.byref(err))
+        if st != 0:
+            raise FpxError(st, err.value)
+
+    def lead_dev(self, d_in, n):
+        st = self._L.fpx_epaxos_lead_dev(self.h, d_in, n)
+        if st != 0:
+            raise FpxError(st)
+
+    def _dev(self, fn, d_in, n, d_out):
+        st = fn(self.h, d_in, n, d_out)
+        if st != 0:
+            raise FpxError(st)
+
+    def preaccept_dev(self, d_in, n, d_reply):
+        self._dev(self._L.fpx_epaxos_preaccept_dev, d_in, n, d_reply)
+
+    def accept_dev(self, d_in, n, d_reply):
+        self._dev(self._L.fpx_epaxos_accept_dev, d_in, n, d_reply)
+
+    def preacceptok_dev(self, d_in, n, d_event):
+        self._dev(self._L.fpx_epaxos_preacceptok_dev, d_in, n, d_event)
+
+    def acceptok_dev(self, d_in, n, d_event):
+        self._dev(self._L.fpx_epaxos_acceptok_dev, d_in, n, d_event)
+
+    def preaccept_sets(self, rows, overflow_count):
+        """handlePreAccept for possibly sparse sets: FPX_ERR_UNSUPPORTED at the first message that carries
+        overflow values (this handle computes with dense watermark vectors)."""
+        rows = np.ascontiguousarray(rows, dtype=np.int32).reshape(-1, 6 + 2 * self.n)
+        oc = np.ascontiguousarray(overflow_count, dtype=np.int32)
+        out = np.zeros((max(len(rows), 1), 4 + self.n), dtype=np.int32)
+        err = C.c_int64(-1)
+        st = self._L.fpx_epaxos_preaccept_sets(self.h, rows.ctypes.data, len(rows), oc.ctypes.data, out.ctypes.data, C.byref(err))
+        if st != 0:
+            raise FpxError(st, err.value)
+        return out[:len(rows)]
 
     def entry(self, rep, num):
         out = np.zeros(7 + self.n, dtype=np.int32)

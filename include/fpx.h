@@ -449,6 +449,22 @@ int fpx_epaxos_preacceptok(fpx_epaxos* e, const int32_t* in, int32_t n_rec, int3
 /* handleAcceptOk, Replica.scala:1514-1565.  in rows of 6 ints: {inst_replica,
  * inst_number, ballot_ord, ballot_rep, from_replica, 0}; event rows as above (COMMIT). */
 int fpx_epaxos_acceptok(fpx_epaxos* e, const int32_t* in, int32_t n_rec, int32_t* event, int64_t* err_index);
+/* The same handlers on DEVICE-resident rows, asynchronous on the handle's stream (fpx_epaxos_stream, a
+ * cudaStream_t); status and first offending index are collected by fpx_epaxos_sync. */
+void* fpx_epaxos_stream(fpx_epaxos* e);
+int fpx_epaxos_sync(fpx_epaxos* e, int64_t* err_index);
+int fpx_epaxos_lead_dev(fpx_epaxos* e, const int32_t* d_in, int32_t n_rec);
+int fpx_epaxos_preaccept_dev(fpx_epaxos* e, const int32_t* d_in, int32_t n_rec, int32_t* d_reply);
+int fpx_epaxos_accept_dev(fpx_epaxos* e, const int32_t* d_in, int32_t n_rec, int32_t* d_reply);
+int fpx_epaxos_preacceptok_dev(fpx_epaxos* e, const int32_t* d_in, int32_t n_rec, int32_t* d_event);
+int fpx_epaxos_acceptok_dev(fpx_epaxos* e, const int32_t* d_in, int32_t n_rec, int32_t* d_event);
+/* handlePreAccept for callers whose dependency sets may be SPARSE (IntPrefixSet with overflow `values`,
+ * S/compact/IntPrefixSet.scala:388-398, created by subtractOne below the watermark / top-k > 1):
+ * overflow_count[i] = number of overflow values in message i's local + message sets.  This handle computes with
+ * dense watermark vectors only: a message with overflow values is FPX_ERR_UNSUPPORTED (err_index = that message,
+ * nothing of the batch is applied); union such sets with fpx_depset_union on the side. */
+int fpx_epaxos_preaccept_sets(fpx_epaxos* e, const int32_t* in, int32_t n_rec, const int32_t* overflow_count,
+                              int32_t* reply, int64_t* err_index);
 /* read-back: out[7+n] = {kind, b_ord, b_rep, vb_ord, vb_rep, value_id, seq, deps[n]},
  * kind 0 none 1 NoCommand 2 PreAccepted 3 Accepted 4 Committed; *leader_kind 0 none 1
  * PreAccepting 2 Accepting; largest_ballot[2] */

@@ -212,3 +212,47 @@ def test_dense_union_kernel_matches_numpy_and_oracle():
             for r in range(R):
                 acc.add_all(O.IntPrefixSet.from_watermark_values(int(x[q, r, k]), []))
             assert acc.watermark() == out[q, k] and not acc.values()
+
+
+def test_sparse_dependency_sets_are_refused_not_mangled():
+    """IntPrefixSet.subtractOne below the watermark / top-k > 1 create overflow `values`
+    (S/compact/IntPrefixSet.scala:388-398, S/epaxos/InstancePrefixSet.scala:30-47).  The handle computes
+    with dense watermark vectors: a batch with such a message is FPX_ERR_UNSUPPORTED at that message
+    and leaves the replica untouched; the same batch without it goes through."""
+    from frankenpaxos_b200 import FpxError
+    f, n = 1, 3
+    eng = EpaxosReplica(f, 0, 64, max_batch=256)
+    rows = np.zeros((3, 6 + 2 * n), dtype=np.int32)
+    rows[:, 0] = 1; rows[:, 1] = [0, 1, 2]; rows[:, 3] = 1; rows[:, 4] = [7, 8, 9]
+    with pytest.raises(FpxError) as ei:
+        eng.preaccept_sets(rows, [0, 2, 0])
+    assert (ei.value.status, ei.value.index) == (-11, 1)
+    assert eng.entry(1, 0)[0][0] == 0                       # nothing applied: entry still empty
+    rep = eng.preaccept_sets(rows, [0, 0, 0])
+    assert (rep[:, 0] == 1).all() and eng.entry(1, 0)[0][0] == 2
+    eng.close()
+
+
+def test_device_pointer_handlers_match_the_host_pointer_ones():
+    """fpx_epaxos_*_dev on device-resident rows == the host-pointer entry points (same replies, same state)."""
+    import torch
+    from frankenpaxos_b200 import traces as T
+    f, n, N = 2, 5, 1 << 12
+    lead, pa, ok = T.epaxos_cfg4(9, f=f, n_instances=N, me=0)
+    a = EpaxosReplica(f, 0, N // n + 2, max_batch=1 << 14)
+    b = EpaxosReplica(f, 0, N // n + 2, max_batch=1 << 14)
+    a.lead(lead); ra = a.preaccept(pa); ea = a.preacceptok(ok)
+    dev = torch.device("cuda", 0)
+    td = lambda x: torch.from_numpy(np.ascontiguousarray(x, dtype=np.int32)).to(dev)
+    d_lead, d_pa, d_ok = td(lead), td(pa), td(ok)
+    d_rep = torch.zeros((len(pa), 4 + n), dtype=torch.int32, device=dev)
+    d_ev = torch.zeros((len(ok), 2 + n), dtype=torch.int32, device=dev)
+    b.lead_dev(d_lead.data_ptr(), len(lead))
+    b.preaccept_dev(d_pa.data_ptr(), len(pa), d_rep.data_ptr())
+    b.preacceptok_dev(d_ok.data_ptr(), len(ok), d_ev.data_ptr())
+    b.sync()
+    assert np.array_equal(d_rep.cpu().numpy(), ra) and np.array_equal(d_ev.cpu().numpy(), ea)
+    for num in (0, 5, 100):
+        for rep in range(n):
+            assert np.array_equal(a.entry(rep, num)[0], b.entry(rep, num)[0])
+    a.close(); b.close()
