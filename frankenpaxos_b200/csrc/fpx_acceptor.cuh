@@ -151,7 +151,7 @@ __device__ __forceinline__ void acceptor_apply(const AcceptorParams& P, int4* ou
           st_evict_first(out_p2b + i, make_int4(rec[u].w >> 16, rec[u].w & 0xffff, rec[u].x, r), pol_out);
           // states(slot) = State(voteRound = round, voteValue) (:205-208)
           cell[u] = ((unsigned long long)(uint32_t)(r + 1) << 32) | (uint32_t)rec[u].z;
-          old[u] = atomicMax(&P.votes[(size_t)loc * g.voters + vix], cell[u]);
+          old[u] = atomicMax(&P.votes[cell_index(g, loc, vix)], cell[u]);
           // maxVotedSlot = max(maxVotedSlot, slot) (:209): thread-private column
           atomicMax(&s_mv[key * kAT + threadIdx.x], rec[u].x);
         }
@@ -343,7 +343,7 @@ __global__ void __launch_bounds__(kAT, 1) acceptor_phase2a_kernel(AcceptorParams
       int4 rr = P.in[s_win];
       int l = local_slot(g, slot);
       int v = voter_index(g, dst >> 16, dst & 0xffff, slot);
-      P.votes[(size_t)l * g.voters + v] = ((unsigned long long)(uint32_t)(rr.y + 1) << 32) | (uint32_t)rr.z;
+      P.votes[cell_index(g, l, v)] = ((unsigned long long)(uint32_t)(rr.y + 1) << 32) | (uint32_t)rr.z;
     }
     __syncthreads();
   }

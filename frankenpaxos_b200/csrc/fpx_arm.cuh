@@ -148,6 +148,8 @@ __device__ __forceinline__ int arm_chunks(const ArmParams& P, int gwarp, int tot
             report_error(P.st, FPX_ERR_SLOT_RANGE, i);
           } else if ((uint32_t)rec[u].y > (uint32_t)FPX_MAX_ROUND) {
             report_error(P.st, FPX_ERR_ROUND_RANGE, i);
+          } else if (P.vanilla && rec[u].y != 0) {
+            report_error(P.st, FPX_ERR_ROUND_RANGE, i);    // Server.handleClientRequest proposes in round 0 (:779, :806-815)
           } else if (P.vanilla && ((rec[u].w >> 16) != 0 || (rec[u].w & 0xffff) >= g.per_group ||
                                    rec[u].x % g.per_group != (rec[u].w & 0xffff))) {
             report_error(P.st, FPX_ERR_BAD_ACCEPTOR, i);   // only the slot's owner coordinates it (:773, slotSystem)
@@ -181,7 +183,7 @@ __device__ __forceinline__ int arm_chunks(const ArmParams& P, int gwarp, int tot
           // phase2s(slot).phase2bs = {index -> Phase2b} (:818-825): own vote, stamped "before everything"
           int self = rec.w & 0xffff;
           P.pl.rows[(size_t)local[u] * g.row_words + 2 + self] = 0;
-          atomicMax(&P.votes[(size_t)local[u] * g.voters + self],
+          atomicMax(&P.votes[cell_index(g, local[u], self)],
                     ((unsigned long long)(uint32_t)(rec.y + 1) << 32) | (uint32_t)rec.z);
         }
       }

@@ -103,6 +103,7 @@ struct Geometry {
   // Lemire fastmod/fastdiv constants (M = ceil(2^64 / d)) for the two runtime
   // divisors on the hot path: numAcceptorGroups and shard_count
   unsigned long long m_groups, m_shards;
+  int32_t cell_shift;         // vote cells are 8 << cell_shift bytes apart (vanilla Mencius: cell + batch claim share 16 B)
   int32_t lgroups, agroups;   // FPX_MENCIUS: leader groups, acceptor groups per leader group
   unsigned long long m_lgroups, m_agroups;
 };
@@ -203,6 +204,11 @@ __device__ __forceinline__ int local_slot(const Geometry& g, int slot) {
   uint32_t q = fastdiv_u32((uint32_t)slot, g.m_shards);
   if ((int)((uint32_t)slot - q * (uint32_t)g.shard_count) != g.shard_index) return -1;
   return (int)q;
+}
+
+// index of the vote cell of voter v of local slot `local` in the flat slot x voter array
+__device__ __forceinline__ size_t cell_index(const Geometry& g, int local, int v) {
+  return ((size_t)local * g.voters + v) << g.cell_shift;
 }
 
 // (group, acceptor) -> voter index within the slot's row, or -1.

@@ -48,7 +48,6 @@ struct fpx_engine {
   int32_t* acc_round = nullptr;
   int32_t* acc_max_voted = nullptr;
   unsigned long long* rlog = nullptr;
-  unsigned long long* vm_claim = nullptr;  // vanilla Mencius: per-cell batch claims
   uint32_t vm_tag = 1;
   uint32_t* rng_tab = nullptr;             // mencius: (start, end, round) key table of the NoopRange path
   int32_t rng_cap = 0;
@@ -168,11 +167,14 @@ static int reset_state(fpx_engine* e) {
     CK(e, cudaMemsetAsync(e->ovf_keys, 0xff, (size_t)g.ovf_cap * 8, e->stream));
     CK(e, cudaMemsetAsync(e->ovf_rows, 0xff, (size_t)g.ovf_cap * g.row_words * 4, e->stream));
   }
-  CK(e, cudaMemsetAsync(e->votes, 0, (size_t)g.local_slots * g.voters * 8, e->stream));
+  CK(e, cudaMemsetAsync(e->votes, 0, ((size_t)g.local_slots * g.voters * 8) << g.cell_shift, e->stream));
+  if (g.cell_shift) {   // vanilla Mencius: the claim word next to every vote cell starts at ~0
+    vm_claim_init_kernel<<<(unsigned)(((size_t)g.local_slots * g.voters + 255) / 256), 256, 0, e->stream>>>(e->votes, (size_t)g.local_slots * g.voters);
+    CK(e, cudaGetLastError());
+  }
   CK(e, cudaMemsetAsync(e->acc_round, 0xff, kMaxKeys * 4, e->stream));      // round = -1 (Acceptor.scala:95)
   CK(e, cudaMemsetAsync(e->acc_max_voted, 0xff, kMaxKeys * 4, e->stream));  // maxVotedSlot = -1 (:104)
   CK(e, cudaMemsetAsync(e->rlog, 0xff, (size_t)g.local_slots * 8, e->stream));
-  if (e->vm_claim) CK(e, cudaMemsetAsync(e->vm_claim, 0xff, (size_t)g.local_slots * g.voters * 8, e->stream));
   if (e->rng_tab) CK(e, cudaMemsetAsync(e->rng_tab, 0xff, (size_t)e->rng_cap * kRangeWords * 4, e->stream));
   e->rng_seq_base = 1;
   e->unit_ranges = 0;
@@ -258,6 +260,7 @@ int fpx_create(fpx_engine** out, const fpx_config* cfg) {
   g.shard_count = cfg->shard_count;
   g.local_slots = (cfg->slot_capacity - cfg->shard_index + cfg->shard_count - 1) / cfg->shard_count;
   if (g.local_slots < 1) g.local_slots = 1;
+  g.cell_shift = cfg->protocol == FPX_VANILLA_MENCIUS ? 1 : 0;
   g.ovf_cap = cfg->overflow_capacity;
   g.ovf_mask = g.ovf_cap ? (uint32_t)g.ovf_cap - 1u : 0u;
   g.m_groups = ~0ull / (unsigned long long)g.groups + 1ull;
@@ -285,11 +288,10 @@ int fpx_create(fpx_engine** out, const fpx_config* cfg) {
     CKC(cudaMalloc(&e->ovf_keys, (size_t)g.ovf_cap * 8));
     CKC(cudaMalloc(&e->ovf_rows, (size_t)g.ovf_cap * g.row_words * 4));
   }
-  CKC(cudaMalloc(&e->votes, (size_t)g.local_slots * g.voters * 8));
+  CKC(cudaMalloc(&e->votes, ((size_t)g.local_slots * g.voters * 8) << g.cell_shift));
   CKC(cudaMalloc(&e->acc_round, kMaxKeys * 4));
   CKC(cudaMalloc(&e->acc_max_voted, kMaxKeys * 4));
   CKC(cudaMalloc(&e->rlog, (size_t)g.local_slots * 8));
-  if (cfg->protocol == FPX_VANILLA_MENCIUS) CKC(cudaMalloc(&e->vm_claim, (size_t)g.local_slots * g.voters * 8));
   if (cfg->protocol == FPX_MENCIUS) {
     e->rng_cap = std::max(1024, g.ovf_cap);
     CKC(cudaMalloc(&e->rng_tab, (size_t)e->rng_cap * kRangeWords * 4));
@@ -354,7 +356,7 @@ void fpx_destroy(fpx_engine* e) {
   cudaSetDevice(e->cfg.device);
   if (e->stream) cudaStreamSynchronize(e->stream);
   cudaFree(e->rows); cudaFree(e->ovf_keys); cudaFree(e->ovf_rows); cudaFree(e->votes);
-  cudaFree(e->acc_round); cudaFree(e->acc_max_voted); cudaFree(e->rlog); cudaFree(e->vm_claim); cudaFree(e->st);
+  cudaFree(e->acc_round); cudaFree(e->acc_max_voted); cudaFree(e->rlog); cudaFree(e->st);
   cudaFree(e->rng_tab); cudaFree(e->rng_dec);
   for (auto& ln : e->lane) {
     cudaFree(ln.d_p2a); cudaFree(ln.d_p2b); cudaFree(ln.d_arm); cudaFree(ln.d_out_p2b); cudaFree(ln.d_out_nack); cudaFree(ln.d_out_chosen);
@@ -962,10 +964,10 @@ static int vm_launch(fpx_engine* e, const void* d_in, int32_t n, fpx_p2b* d_repl
   if (which == 0 && !d_reply) return FPX_ERR_INVALID_ARG;
   VmParams P;
   P.g = e->g; P.in = (const int4*)d_in; P.out = (int4*)d_reply; P.n = n; P.votes = e->votes;
-  P.claim = e->vm_claim; P.rows = e->rows; P.st = e->st;
+  P.rows = e->rows; P.st = e->st;
   P.tag = e->vm_tag++;
   if (e->vm_tag == 0xffffffffu) e->vm_tag = 1;
-  if (which == 0) vm_phase2a_kernel<<<(n + 255) / 256, 256, 0, e->stream>>>(P);
+  if (which == 0) vm_phase2a_kernel<<<std::min((n + 256 * kVmUnroll - 1) / (256 * kVmUnroll), e->num_sms * 8), 256, 0, e->stream>>>(P);
   else vm_learn_chosen_kernel<<<(n + 255) / 256, 256, 0, e->stream>>>(P);
   e->launches++;
   CK(e, cudaGetLastError());

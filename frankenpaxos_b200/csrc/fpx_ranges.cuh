@@ -240,7 +240,7 @@ __global__ void __launch_bounds__(256) range_fill_kernel(RangeFillParams P) {
   const unsigned long long cell = ((unsigned long long)(uint32_t)(rec.z + 1) << 32) | (uint32_t)FPX_VALUE_NOOP;
   for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < count; t += (long long)gridDim.x * blockDim.x) {
     int l = local_slot(g, (int)(first + t * stride));
-    if (l >= 0) atomicMax(&P.votes[(size_t)l * g.voters + a], cell);   // states(slot) = State(round, Noop)
+    if (l >= 0) atomicMax(&P.votes[cell_index(g, l, a)], cell);   // states(slot) = State(round, Noop)
   }
 }
 
@@ -432,7 +432,7 @@ __global__ void __launch_bounds__(256) vm_skip_kernel(VmSkipParams P) {
     const int slot = (int)(rec.y + t * n);
     const int l = local_slot(g, slot);
     if (l < 0) continue;
-    unsigned long long* cell = &P.votes[(size_t)l * g.voters + server];
+    unsigned long long* cell = &P.votes[cell_index(g, l, server)];
     uint32_t* row = P.rows + (size_t)l * g.row_words;
     if (rec.w) {
       unsigned long long old = atomicCAS(cell, 0ull, chosen);                      // log.put(nextSlot, ChosenEntry(Noop)) (:615-618)

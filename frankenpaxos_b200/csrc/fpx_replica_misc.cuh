@@ -178,7 +178,7 @@ __global__ void snapshot_votes_kernel(Geometry g, const unsigned long long* vote
   if (!g.flexible && v >= 0 && group != expected_group(g, slot)) v = -1;  // this acceptor never sees that slot
   int vr = -1, vv = -1;
   if (v >= 0) {
-    unsigned long long c = votes[(size_t)l * g.voters + v];
+    unsigned long long c = votes[cell_index(g, l, v)];
     if ((c >> 32) != 0) { vr = (int)(c >> 32) - 1; vv = (int)(uint32_t)c; }
   }
   vote_round[i] = vr;
@@ -201,7 +201,7 @@ __global__ void __launch_bounds__(256) safe_values_kernel(Geometry g, const unsi
       for (int v = 0; v < g.voters; ++v) {
         int gid = g.flexible ? v : grp * g.per_group + v;   // global acceptor id of voter v of this slot
         if (!((responders >> gid) & 1u)) continue;
-        unsigned long long c = __ldcg(&votes[(size_t)l * g.voters + v]);
+        unsigned long long c = __ldcg(&votes[cell_index(g, l, v)]);
         if (c & kCellChosen) continue;
         m = max(m, c);
       }

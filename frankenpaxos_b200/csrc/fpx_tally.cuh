@@ -112,10 +112,16 @@ __device__ __forceinline__ bool row_completion(const TallyParams& P, const uint3
 #pragma unroll
   for (int v = 0; v < ROWW - 2; ++v)
     if (v < g.voters) touched |= (w[2 + v] - P.seq_base) < (uint32_t)P.n;
-  if (hw == kUnarmed) return !touched;                 // a vote for a key that was never armed (:220-225)
-  if (hw == kPoison || hw == kBusy) return false;      // several live rounds: its keys live in the table
-  if ((int)(hw & ~kDoneBit) != R) return false;        // a vote of round R could hide behind an older stamp
-  if (!touched) return true;
+  if (g.protocol == FPX_VANILLA_MENCIUS) {
+    // the checked phase A only stamped votes the reference counts (right round, Phase 2 running, :1088-1116):
+    // every stamp is a vote; a chosen slot emits nothing more
+    if (hw == kUnarmed || (hw & kDoneBit) || !touched) return true;
+  } else {
+    if (hw == kUnarmed) return !touched;                 // a vote for a key that was never armed (:220-225)
+    if (hw == kPoison || hw == kBusy) return false;      // several live rounds: its keys live in the table
+    if ((int)(hw & ~kDoneBit) != R) return false;        // a vote of round R could hide behind an older stamp
+    if (!touched) return true;
+  }
   uint32_t c = kStampEmpty;
   if (!g.flexible) {
     // phase2bs.size >= f+1 (:238): the (f+1)-th smallest first-delivery stamp
@@ -193,6 +199,12 @@ __device__ __forceinline__ void tally_sweep(const TallyParams& P, int w_lo, int 
       if (!kEmit) {
         if (i != kNoVote) {
           red_or_u32(&P.bw[i >> 5].x, 1u << (i & 31));
+          if (g.protocol == FPX_VANILLA_MENCIUS) {
+            // choose(): the coordinator's own entry becomes ChosenEntry, phase2s.remove (Server.scala:622-625)
+            const int slot = (int)(w_lo + r) * g.shard_count + g.shard_index;
+            red_max_u64(&P.votes[cell_index(g, (int)(w_lo + r), slot % g.per_group)], kCellChosen | w[u][1]);
+            red_or_u32(P.pl.rows + (size_t)(w_lo + r) * ROWW, kDoneBit);
+          }
           if (P.rlog != nullptr) {
             // co-located replica (Replica.scala:580-588), here rather than at emission: consecutive threads
             // hold consecutive log entries.  Sound in a sweep: one round per batch = at most one Chosen per
@@ -303,7 +315,7 @@ __device__ __forceinline__ void tally_exact(const TallyParams& P, int wlo, int w
                 if (vanilla) {
                   // choose(): the coordinator's own entry becomes ChosenEntry, phase2s.remove (:622-625)
                   int owner = rec[u].z % g.per_group;
-                  red_max_u64(&P.votes[(size_t)local_slot(g, rec[u].z) * g.voters + owner], kCellChosen | w[u][1]);
+                  red_max_u64(&P.votes[cell_index(g, local_slot(g, rec[u].z), owner)], kCellChosen | w[u][1]);
                   red_or_u32(r, kDoneBit);
                 }
               }
@@ -413,10 +425,13 @@ __global__ void __launch_bounds__(kTT, 1) tally_kernel(TallyParams P) {
         int v = voter_index(g, rec[u].x, rec[u].y, rec[u].z);
         if (v < 0) continue;
         red_min_u32(&row[u][2 + v], P.seq_base + (uint32_t)i);
+        const int local = (int)((row[u] - P.pl.rows) / g.row_words);
+        lo = min(lo, local); hi = max(hi, local);
+        rmin = min(rmin, rec[u].w); rmax = max(rmax, rec[u].w);
       }
     }
   }
-  if (!vanilla) {
+  {
     lo = __reduce_min_sync(full, lo); hi = __reduce_max_sync(full, hi);
     rmin = __reduce_min_sync(full, rmin); rmax = __reduce_max_sync(full, rmax);
     flags = __reduce_or_sync(full, flags);
@@ -444,8 +459,9 @@ __global__ void __launch_bounds__(kTT, 1) tally_kernel(TallyParams P) {
   // ---- phase B: which votes complete their key
   const int w_lo = __ldcg(&P.st->ts_min_local), w_hi = __ldcg(&P.st->ts_max_local);
   const int R = __ldcg(&P.st->ts_min_round);
-  bool sweep = !(P.path & 2) && !vanilla && __ldcg(&P.st->ts_flags) == 0 && w_hi >= w_lo &&
-               R == __ldcg(&P.st->ts_max_round) && (long long)w_hi - w_lo <= 4ll * P.n + 4096;
+  // (vanilla Mencius: the checked phase A stamped only votes the reference counts, so the rows alone decide)
+  bool sweep = !(P.path & 2) && w_hi >= w_lo && (long long)w_hi - w_lo <= 4ll * P.n + 4096 &&
+               (vanilla || (__ldcg(&P.st->ts_flags) == 0 && R == __ldcg(&P.st->ts_max_round)));
   // every CTA sweeps a contiguous run of the window's rows (a multiple of the CTA size)
   const int rows_per_cta = sweep ? (int)((((long long)w_hi - w_lo + gridDim.x) / gridDim.x + kTT - 1) / kTT) * kTT : 0;
   const bool keep = rows_per_cta <= P.keep_cap;

@@ -66,7 +66,7 @@ def cfg3():
     return {"config": "cfg3: flexible 2x3 grid, f=1, thrifty quorum = one column (Q=2), 2^22 slots per step, Phase2b "
                       "shuffled within 10 proxy-leader partitions (slot % 10)", "slots_per_step": n, "ms_per_step": ms,
             "slots_per_s": n / (ms * 1e-3), "algorithmic_GB/s": (56 * q + 24) * n / (ms * 1e-3) / 1e9,
-            "calls": "arm + acceptor_phase2a + proxyleader_phase2b (two tally launches) + replica_chosen + watermark"}
+            "calls": "arm + acceptor_phase2a + proxyleader_phase2b + replica_chosen + watermark"}
 
 
 def cfg5():
@@ -95,8 +95,20 @@ def cfg5():
     ms = timed(eng, step)
     r = eng.sync()
     assert r.status == 0 and r.n_chosen == n, (r.status, r.n_chosen)
+    # per-kernel split of one more step (CUDA events between the calls)
+    ext = torch.cuda.ExternalStream(eng.stream, device=dev)
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+    eng.reset()
+    dr, dp, db = ins[0]
+    ev[0].record(ext); eng.vm_client_request_dev(dr.data_ptr(), n)
+    ev[1].record(ext); eng.vm_phase2a_dev(dp.data_ptr(), nrec, o_rep.data_ptr())
+    ev[2].record(ext); eng.proxyleader_phase2b_dev(db.data_ptr(), nrec, o_ch.data_ptr())
+    ev[3].record(ext)
+    eng.sync()
+    split = {"vm_client_request_us": ev[0].elapsed_time(ev[1]) * 1e3, "vm_phase2a_us": ev[1].elapsed_time(ev[2]) * 1e3,
+             "tally_us": ev[2].elapsed_time(ev[3]) * 1e3}
     eng.close()
-    return {"config": "cfg5: vanilla Mencius n=7 f=3, owner = slot % 7, 2^20 slots per step, 6 Phase2a + 6 Phase2b per "
+    return {"split": split, "config": "cfg5: vanilla Mencius n=7 f=3, owner = slot % 7, 2^20 slots per step, 6 Phase2a + 6 Phase2b per "
                       "slot, both shuffled", "slots_per_step": n, "ms_per_step": ms, "slots_per_s": n / (ms * 1e-3),
             "messages_per_s": (1 + 2 * (srv - 1)) * n / (ms * 1e-3),
             "calls": "vm_client_request (arm + own vote) + vm_phase2a + proxyleader_phase2b"}
