@@ -222,6 +222,12 @@ class Backend {
   // Acceptor state read-back (Phase1b's `states.iteratorFrom`, Acceptor.scala:171-179)
   virtual void snapshot(int group, int acceptor, int* round, int* max_voted_slot, int first_slot, int n_slots,
                         int32_t* vote_round, int32_t* vote_value) = 0;
+  // Phase 1 reads on the same vote cells (control path; batch boundaries by SURVEY 8(g) rule 2):
+  // Acceptor.handlePhase1a (Acceptor.scala:148-182) -> -1 = round adopted, else the Nack's round;
+  // Leader.safeValue over a set of responders (Leader.scala:318-329), bit g * per_group + a of `responders`
+  virtual int phase1a(int group, int acceptor, int round) = 0;
+  virtual void safe_values(uint32_t responders, int first_slot, int n_slots, int32_t* vote_round, int32_t* value_id,
+                           int* max_slot) = 0;
   // Optional: the backend parses / serialises the hot messages itself (fpx_wire_*), so the actors
   // hand it the transport's raw bytes for Phase2b and get reply bytes back.
   virtual bool has_wire() const { return false; }
@@ -256,6 +262,20 @@ class GpuBackend : public Backend {
                 int32_t* vote_round, int32_t* vote_value) override {
     fpx_snapshot_acceptor(e_, group, acceptor, round, max_voted_slot, first_slot, n_slots, vote_round, vote_value);
   }
+  int phase1a(int group, int acceptor, int round) override {
+    int32_t nack = -1;
+    int st = fpx_acceptor_phase1a(e_, group, acceptor, round, &nack);
+    if (st != FPX_OK) throw std::runtime_error(std::string("fpx_acceptor_phase1a: ") + fpx_strerror(st));
+    return nack;
+  }
+  void safe_values(uint32_t responders, int first_slot, int n_slots, int32_t* vote_round, int32_t* value_id,
+                   int* max_slot) override {
+    int32_t mx = -1;
+    int st = fpx_leader_safe_values(e_, responders, first_slot, n_slots, vote_round, value_id, &mx);
+    if (st != FPX_OK) throw std::runtime_error(std::string("fpx_leader_safe_values: ") + fpx_strerror(st));
+    *max_slot = mx;
+  }
+  int reset() { return fpx_reset(e_); }
   bool has_wire() const override { return true; }
   int wire_decode_proxyleader(const uint8_t* bytes, const int32_t* offs, int n, int32_t* kind, fpx_wire_rec* out,
                               int64_t* err) override {

@@ -24,6 +24,8 @@ int fpo_mp_arm(void* p, const fpx_p2a* in, int n, int64_t* err);
 int fpo_mp_acceptor_phase2a(void* p, const fpx_p2a* in, int n, fpx_p2b* out, int* n_out, fpx_nack* nack, int* n_nack, int64_t* err);
 int fpo_mp_proxyleader_phase2b(void* p, const fpx_p2b* in, int n, fpx_chosen* out, int* n_out, int64_t* err);
 void fpo_mp_snapshot_acceptor(void* p, int g, int a, int* round, int* max_voted_slot, int first_slot, int n_slots, int* vote_round, int* vote_value);
+int fpo_mp_phase1a(void* p, int g, int a, int round);
+void fpo_mp_safe_values(void* p, unsigned responders, int first_slot, int n_slots, int* vote_round, int* value, int* max_slot);
 }
 
 using namespace frankenpaxos;
@@ -37,6 +39,8 @@ class OracleBackend : public Backend {
   int phase2a(const fpx_p2a* in, int n, fpx_p2b* out, int* n_out, fpx_nack* nack, int* n_nack, int64_t* err) override { return fpo_mp_acceptor_phase2a(h_, in, n, out, n_out, nack, n_nack, err); }
   int phase2b(const fpx_p2b* in, int n, fpx_chosen* out, int* n_out, int64_t* err) override { return fpo_mp_proxyleader_phase2b(h_, in, n, out, n_out, err); }
   void snapshot(int g, int a, int* round, int* mvs, int first, int n, int32_t* vr, int32_t* vv) override { fpo_mp_snapshot_acceptor(h_, g, a, round, mvs, first, n, vr, vv); }
+  int phase1a(int g, int a, int round) override { return fpo_mp_phase1a(h_, g, a, round); }
+  void safe_values(uint32_t responders, int first, int n, int32_t* vr, int32_t* vv, int* mx) override { fpo_mp_safe_values(h_, responders, first, n, vr, vv, mx); }
  private:
   void* h_;
 };
