@@ -63,10 +63,28 @@ def test_config_validation_is_checked_before_device():
 
 
 def test_jni_symbols_exported():
-    """frankenpaxos_b200/csrc/fpx_jni.c: every Native method of INTEGRATION.md is an
-    exported Java_frankenpaxos_gpu_Native_* symbol."""
+    """Every `@native def` of INTEGRATION.md's Native.scala is an exported Java_frankenpaxos_gpu_Native_* symbol
+    (frankenpaxos_b200/csrc/fpx_jni.c by hand, fpx_jni_gen.c generated from include/fpx.h), and every entry
+    point of include/fpx.h is reachable from the JVM side."""
     from frankenpaxos_b200 import build
     L = ctypes.CDLL(build.build())
-    for m in ["create", "destroy", "proxyLeaderArm", "acceptorPhase2a", "proxyLeaderPhase2b", "replicaChosen",
-              "chosenWatermark", "snapshotAcceptor"]:
-        assert hasattr(L, "Java_frankenpaxos_gpu_Native_" + m), m
+    md = open(os.path.join(ROOT, "INTEGRATION.md")).read()
+    methods = re.findall(r"@native def ([A-Za-z0-9_]+)\(", md)
+    assert len(methods) >= 80 and len(set(methods)) == len(methods)
+    missing = [m for m in methods if not hasattr(L, "Java_frankenpaxos_gpu_Native_" + m)]
+    assert not missing, missing
+    # coverage of the C ABI: every fpx_* function is called by some JNI stub
+    jni = open(os.path.join(ROOT, "frankenpaxos_b200", "csrc", "fpx_jni.c")).read() + \
+        open(os.path.join(ROOT, "frankenpaxos_b200", "csrc", "fpx_jni_gen.c")).read()
+    called = set(re.findall(r"\b(fpx_[a-z0-9_]+)\s*\(", jni))
+    assert not [s for s in declared_symbols() if s not in called]
+
+
+def test_generated_jni_is_up_to_date():
+    """fpx_jni_gen.c and the GENERATED block of INTEGRATION.md are what gen_jni.py produces from the header."""
+    import subprocess
+    import sys
+    gen = os.path.join(ROOT, "frankenpaxos_b200", "csrc", "fpx_jni_gen.c")
+    before_c, before_md = open(gen).read(), open(os.path.join(ROOT, "INTEGRATION.md")).read()
+    subprocess.check_call([sys.executable, os.path.join(ROOT, "frankenpaxos_b200", "csrc", "gen_jni.py")])
+    assert open(gen).read() == before_c and open(os.path.join(ROOT, "INTEGRATION.md")).read() == before_md
