@@ -24,7 +24,7 @@ SYMBOLS = [
     "fpx_mencius_replica_chosen_range",
     "fpx_wire_decode_inbound", "fpx_wire_decode_inbound_dev", "fpx_wire_encode_phase2b", "fpx_wire_encode_phase2b_dev",
     "fpx_wire_encode_nack", "fpx_wire_encode_chosen",
-    "fpx_step_submit", "fpx_step_wait", "fpx_exchange_export", "fpx_exchange_attach", "fpx_exchange_attach_local", "fpx_exchange_epoch",
+    "fpx_step_submit", "fpx_step_wait", "fpx_retire_below", "fpx_exchange_export", "fpx_exchange_attach", "fpx_exchange_attach_local", "fpx_exchange_epoch",
     "fpx_global_watermark", "fpx_global_watermark_dev",
     "fpx_conflict_index_create", "fpx_conflict_index_destroy", "fpx_conflict_index_put_snapshot", "fpx_conflict_index_batch",
     "fpx_depgraph_create", "fpx_depgraph_destroy", "fpx_depgraph_commit", "fpx_depgraph_update_executed", "fpx_depgraph_execute",
@@ -114,6 +114,7 @@ def lib():
     L.fpx_set_coop_ctas_per_sm.argtypes = [vp, i32]; L.fpx_set_coop_ctas_per_sm.restype = i32
     L.fpx_stream.argtypes = [vp]; L.fpx_stream.restype = vp
     L.fpx_launch_count.argtypes = [vp]; L.fpx_launch_count.restype = i64
+    L.fpx_retire_below.argtypes = [vp, i32]; L.fpx_retire_below.restype = i32
     L.fpx_step_submit.argtypes = [vp, vp, i32, vp, i32, vp, i32, vp, vp, vp]; L.fpx_step_submit.restype = i32
     L.fpx_step_wait.argtypes = [vp, p(i32), p(i32), p(i32), p(i32), p(i64)]; L.fpx_step_wait.restype = i32
     L.fpx_exchange_export.argtypes = [vp, vp]; L.fpx_exchange_export.restype = i32

@@ -61,7 +61,7 @@ __device__ __forceinline__ int decode_p2a(const Geometry& g, const int4& rec, in
   if ((uint32_t)grp >= (uint32_t)g.groups || acc >= g.per_group) return FPX_ERR_BAD_ACCEPTOR;
   if ((uint32_t)rec.y > (uint32_t)FPX_MAX_ROUND) return FPX_ERR_ROUND_RANGE;
   int l = local_slot(g, rec.x);
-  if (l < 0) return FPX_ERR_SLOT_RANGE;
+  if (l < 0 && l != kLocalRetired) return FPX_ERR_SLOT_RANGE;   // retired: round compare and reply as usual, the vote cell is gone
   int v = voter_index(g, grp, acc, rec.x);
   if (v < 0 || (g.protocol == FPX_MENCIUS && grp != expected_group(g, rec.x))) return FPX_ERR_BAD_ACCEPTOR;
   key = grp * g.per_group + acc; loc = l; vix = v;
@@ -150,8 +150,10 @@ __device__ __forceinline__ void acceptor_apply(const AcceptorParams& P, int4* ou
           // Phase2b(groupIndex, acceptorIndex, slot, round) (:211-219)
           st_evict_first(out_p2b + i, make_int4(rec[u].w >> 16, rec[u].w & 0xffff, rec[u].x, r), pol_out);
           // states(slot) = State(voteRound = round, voteValue) (:205-208)
-          cell[u] = ((unsigned long long)(uint32_t)(r + 1) << 32) | (uint32_t)rec[u].z;
-          old[u] = atomicMax(&P.votes[cell_index(g, loc, vix)], cell[u]);
+          if (loc >= 0) {   // (a retired slot's vote is never read again: Phase1b starts at the chosen watermark, :171-179)
+            cell[u] = ((unsigned long long)(uint32_t)(r + 1) << 32) | (uint32_t)rec[u].z;
+            old[u] = atomicMax(&P.votes[cell_index(g, loc, vix)], cell[u]);
+          }
           // maxVotedSlot = max(maxVotedSlot, slot) (:209): thread-private column
           atomicMax(&s_mv[key * kAT + threadIdx.x], rec[u].x);
         }

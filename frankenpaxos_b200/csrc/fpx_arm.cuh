@@ -145,7 +145,7 @@ __device__ __forceinline__ int arm_chunks(const ArmParams& P, int gwarp, int tot
         if (c0 + u < n_chunks && i < P.n) {
           int l = local_slot(g, rec[u].x);
           if (l < 0) {
-            report_error(P.st, FPX_ERR_SLOT_RANGE, i);
+            if (l != kLocalRetired) report_error(P.st, FPX_ERR_SLOT_RANGE, i);   // retired: the key is Done, `case Some(_)` (:177-183)
           } else if ((uint32_t)rec[u].y > (uint32_t)FPX_MAX_ROUND) {
             report_error(P.st, FPX_ERR_ROUND_RANGE, i);
           } else if (P.vanilla && rec[u].y != 0) {

@@ -95,8 +95,10 @@ struct Geometry {
   int32_t num_keys;        // total acceptors = groups * per_group
   int32_t quorum;          // f + 1 (count predicate)
   int32_t row_words;       // 8 / 16 / 32 uint32 per proxy-leader row
-  int32_t slot_capacity;   // global
-  int32_t local_slots;     // rows held by this shard
+  int32_t slot_capacity;   // global: one past the last slot of the live window (grows with fpx_retire_below)
+  int32_t local_slots;     // rows held by this shard = size of the ring
+  int32_t base_local;      // ordinal (slot / shard_count) of the first LIVE local slot; lower ones are retired
+  int32_t base_ring;       // base_local % local_slots: where the live window starts in the ring
   int32_t shard_index, shard_count;
   uint32_t ovf_mask;       // overflow_capacity - 1, or 0 with ovf_cap == 0
   int32_t ovf_cap;
@@ -197,13 +199,36 @@ __device__ __forceinline__ void report_error(DevStatus* st, int code, long long 
   atomicMin(&st->err_word, w);
 }
 
-// global slot -> local row index of this shard, or -1
+// State is a RING of local_slots rows over the shard's residue class: ordinal u = slot / shard_count lives at
+// ring index u % local_slots while base_local <= u < base_local + local_slots.  fpx_retire_below advances
+// base_local behind the chosen watermark and recycles the rows, so a long-lived engine never runs out of slots.
+// Three coordinates: ring (addresses), rel = u - base_local (the live window, contiguous), slot (global).
+constexpr int kLocalRetired = -2;   // below the live window: chosen and executed long ago
+// global slot -> ring index of this shard; -1 out of range / other shard, kLocalRetired
 __device__ __forceinline__ int local_slot(const Geometry& g, int slot) {
   if ((uint32_t)slot >= (uint32_t)g.slot_capacity) return -1;
-  if (g.shard_count == 1) return slot;
-  uint32_t q = fastdiv_u32((uint32_t)slot, g.m_shards);
-  if ((int)((uint32_t)slot - q * (uint32_t)g.shard_count) != g.shard_index) return -1;
-  return (int)q;
+  int u = slot;
+  if (g.shard_count != 1) {
+    uint32_t q = fastdiv_u32((uint32_t)slot, g.m_shards);
+    if ((int)((uint32_t)slot - q * (uint32_t)g.shard_count) != g.shard_index) return -1;
+    u = (int)q;
+  }
+  const int rel = u - g.base_local;
+  if (rel < 0) return kLocalRetired;
+  if (rel >= g.local_slots) return -1;
+  const int ring = rel + g.base_ring;
+  return ring >= g.local_slots ? ring - g.local_slots : ring;
+}
+__device__ __forceinline__ int ring_to_rel(const Geometry& g, int ring) {
+  const int rel = ring - g.base_ring;
+  return rel < 0 ? rel + g.local_slots : rel;
+}
+__device__ __forceinline__ int rel_to_ring(const Geometry& g, long long rel) {
+  const long long r = rel + g.base_ring;
+  return (int)(r >= g.local_slots ? r - g.local_slots : r);
+}
+__device__ __forceinline__ int rel_to_slot(const Geometry& g, long long rel) {
+  return (int)((g.base_local + rel) * g.shard_count + g.shard_index);
 }
 
 // index of the vote cell of voter v of local slot `local` in the flat slot x voter array

@@ -195,6 +195,9 @@ static int reset_state(fpx_engine* e) {
   e->xch_epoch = 0;
   CK(e, cudaMemcpyAsync(e->xch, &e->h_xch, sizeof(DevExchange), cudaMemcpyHostToDevice, e->stream));
   CK(e, cudaStreamSynchronize(e->stream));
+  e->g.base_local = 0;
+  e->g.base_ring = 0;
+  e->g.slot_capacity = e->cfg.slot_capacity;
   e->parity = 0;
   e->seq_base = 1;
   e->rseq_base = 1;
@@ -260,6 +263,8 @@ int fpx_create(fpx_engine** out, const fpx_config* cfg) {
   g.shard_count = cfg->shard_count;
   g.local_slots = (cfg->slot_capacity - cfg->shard_index + cfg->shard_count - 1) / cfg->shard_count;
   if (g.local_slots < 1) g.local_slots = 1;
+  g.base_local = 0;
+  g.base_ring = 0;
   g.cell_shift = cfg->protocol == FPX_VANILLA_MENCIUS ? 1 : 0;
   g.ovf_cap = cfg->overflow_capacity;
   g.ovf_mask = g.ovf_cap ? (uint32_t)g.ovf_cap - 1u : 0u;
@@ -389,6 +394,35 @@ int fpx_reset(fpx_engine* e) {
 }
 
 void* fpx_stream(fpx_engine* e) { return e ? (void*)e->stream : nullptr; }
+
+// Slide the live window: every slot below `slot` is chosen and executed (slot <= the watermark this engine last
+// published) and will not be needed again -- its row, vote cells and log entry are recycled for the slots
+// slot_capacity ahead.  Messages for retired slots afterwards behave as the reference's would on a key that is
+// Done / a log entry that exists: arms, votes and Chosen records are ignored, a Phase2a is still answered
+// (round compare, Phase2b / Nack) but not recorded.
+int fpx_retire_below(fpx_engine* e, int32_t slot) {
+  if (!e || slot < 0) return FPX_ERR_INVALID_ARG;
+  if (e->g.protocol == FPX_VANILLA_MENCIUS) return FPX_ERR_UNSUPPORTED;   // a retired ChosenEntry must still answer Chosen(value)
+  CK(e, cudaSetDevice(e->cfg.device));
+  fpx_sync_result r;
+  int c = fpx_sync(e, &r);
+  if (c != FPX_OK) return c;
+  if (slot > r.watermark) return FPX_ERR_INVALID_ARG;                    // only the executed prefix may go
+  Geometry& g = e->g;
+  // first ordinal of this shard whose slot is >= `slot`
+  long long new_base = ((long long)slot - g.shard_index + g.shard_count - 1) / g.shard_count;
+  if (new_base < g.base_local) new_base = g.base_local;
+  const int count = (int)std::min<long long>(new_base - g.base_local, g.local_slots);
+  if (count == 0) return FPX_OK;
+  recycle_kernel<<<std::min(count * 8 + 255, 148 * 2048) / 256 + 1, 256, 0, e->stream>>>(g, e->rows, e->votes, e->rlog, 0, count);
+  e->launches++;
+  CK(e, cudaGetLastError());
+  g.base_local = (int32_t)new_base;
+  g.base_ring = (int32_t)(new_base % g.local_slots);
+  long long cap = (long long)e->cfg.slot_capacity + (long long)g.base_local * g.shard_count;
+  g.slot_capacity = (int32_t)std::min<long long>(cap, 0x7fffffffll);
+  return FPX_OK;
+}
 
 int fpx_set_coop_ctas_per_sm(fpx_engine* e, int32_t ctas_per_sm) {
   if (!e || ctas_per_sm < 0) return FPX_ERR_INVALID_ARG;

@@ -51,10 +51,13 @@ __global__ void __launch_bounds__(256) replica_chosen_kernel(ReplicaParams P) {
       int i = i0 + u * stride;
       if (i >= n) break;
       int local = local_slot(g, rec[u].x);
-      if (local < 0) { report_error(P.st, FPX_ERR_SLOT_RANGE, i); continue; }
+      if (local < 0) {   // a retired slot is in the log (and executed) already: redundantly chosen (:580-586)
+        if (local != kLocalRetired) report_error(P.st, FPX_ERR_SLOT_RANGE, i);
+        continue;
+      }
       // first Chosen per slot wins (Replica.scala:580-588): min over (delivery seq : value)
       red_min_u64(&P.rlog[local], ((unsigned long long)(P.seq_base + (uint32_t)i) << 32) | (uint32_t)rec[u].y);
-      mx = max(mx, local);
+      mx = max(mx, g.base_local + ring_to_rel(g, local));   // ordinal
     }
   }
   mx = __reduce_max_sync(0xffffffffu, mx);
@@ -74,15 +77,15 @@ __global__ void __launch_bounds__(256) watermark_scan_kernel(Geometry g, const u
                                                             DevStatus* st, int32_t* d_out, DevExchange* xch) {
   __shared__ int s_found[8];
   __shared__ bool s_last;
-  const int lo = __ldcg(&st->wm_local);
-  const int hi = min(__ldcg(&st->max_chosen_local) + 2, g.local_slots);  // one past the last candidate hole
+  const int lo = __ldcg(&st->wm_local);                                                    // ordinals
+  const int hi = min(__ldcg(&st->max_chosen_local) + 2, g.base_local + g.local_slots);      // one past the last candidate hole
   int found = INT_MAX;
   // four independent loads per round trip (the early exit makes consecutive iterations dependent)
   const long long stride = (long long)gridDim.x * blockDim.x;
   for (long long i = lo + (long long)blockIdx.x * blockDim.x + threadIdx.x; i < hi && found == INT_MAX; i += 4 * stride) {
     unsigned long long v[4];
 #pragma unroll
-    for (int u = 0; u < 4; ++u) v[u] = (i + u * stride < hi) ? __ldcg(&rlog[i + u * stride]) : 0ull;
+    for (int u = 0; u < 4; ++u) v[u] = (i + u * stride < hi) ? __ldcg(&rlog[rel_to_ring(g, i + u * stride - g.base_local)]) : 0ull;
 #pragma unroll
     for (int u = 3; u >= 0; --u)
       if (i + u * stride < hi && v[u] == kU64Empty) found = (int)(i + u * stride);   // ascending: the smallest one last
@@ -102,7 +105,7 @@ __global__ void __launch_bounds__(256) watermark_scan_kernel(Geometry g, const u
   __threadfence();
   int f = min(*(volatile int*)&st->wm_found, hi);
   f = max(f, lo);
-  if (f > g.local_slots) f = g.local_slots;
+  if (f > g.base_local + g.local_slots) f = g.base_local + g.local_slots;
   st->wm_local = f;
   st->wm_found = INT_MAX;
   st->ticket = 0;
@@ -184,6 +187,27 @@ __global__ void snapshot_votes_kernel(Geometry g, const unsigned long long* vote
   vote_round[i] = vr;
   vote_value[i] = vv;
 }
+// fpx_retire_below: the ring positions of the ordinals [first, first + count) go back to their initial state
+// (row unarmed, no votes, no log entry) so that they can serve the slots one window ahead.
+__global__ void recycle_kernel(Geometry g, uint32_t* rows, unsigned long long* votes, unsigned long long* rlog,
+                               int first_rel, int count) {
+  const int per_row = g.row_words + 2 * (g.voters << g.cell_shift) + 2;   // 32-bit words of state per slot
+  const long long total = (long long)count * per_row;
+  for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+    const int k = (int)(t / per_row), w = (int)(t % per_row);
+    const int ring = rel_to_ring(g, first_rel + k);
+    if (w < g.row_words) {
+      rows[(size_t)ring * g.row_words + w] = 0xffffffffu;
+    } else if (w < g.row_words + 2 * (g.voters << g.cell_shift)) {
+      const int c = w - g.row_words;                       // 32-bit half of a 64-bit cell / claim word
+      const bool claim = g.cell_shift && ((c >> 1) & 1);   // vanilla: odd 64-bit words are the batch claims (~0)
+      ((uint32_t*)(votes + ((size_t)ring * g.voters << g.cell_shift)))[c] = claim ? 0xffffffffu : 0u;
+    } else {
+      ((uint32_t*)(rlog + ring))[w - g.row_words - 2 * (g.voters << g.cell_shift)] = 0xffffffffu;
+    }
+  }
+}
+
 // Leader.safeValue over a Phase-1 quorum (S/multipaxos/Leader.scala:318-329): coalesced
 // sweep of the flat slot x voter cell array, arg-max of voteRound per slot over the
 // responders' cells (64-bit max of {voteRound+1, value}); warp redux for maxPhase1bSlot.

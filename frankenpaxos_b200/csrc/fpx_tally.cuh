@@ -161,7 +161,7 @@ __device__ __forceinline__ void emit_chosen(const TallyParams& P, uint32_t pos, 
   st_stream2(P.out_chosen + pos, make_int2(slot, value));
   if (kReplica && P.rlog != nullptr) {
     red_min_u64(&P.rlog[local], ((unsigned long long)(P.rseq_base + pos) << 32) | (uint32_t)value);
-    mx = max(mx, local);
+    mx = max(mx, P.g.base_local + ring_to_rel(P.g, local));
   }
 }
 
@@ -188,7 +188,7 @@ __device__ __forceinline__ void tally_sweep(const TallyParams& P, int w_lo, int 
 #pragma unroll
     for (int u = 0; u < U; ++u) {
       const long long r = r0 + u * kTT;
-      if (r < r_end) load_row<ROWW>(P.pl.rows + (size_t)(w_lo + r) * ROWW, w[u]);
+      if (r < r_end) load_row<ROWW>(P.pl.rows + (size_t)rel_to_ring(g, w_lo + r) * ROWW, w[u]);
     }
 #pragma unroll
     for (int u = 0; u < U; ++u) {
@@ -201,23 +201,23 @@ __device__ __forceinline__ void tally_sweep(const TallyParams& P, int w_lo, int 
           red_or_u32(&P.bw[i >> 5].x, 1u << (i & 31));
           if (g.protocol == FPX_VANILLA_MENCIUS) {
             // choose(): the coordinator's own entry becomes ChosenEntry, phase2s.remove (Server.scala:622-625)
-            const int slot = (int)(w_lo + r) * g.shard_count + g.shard_index;
-            red_max_u64(&P.votes[cell_index(g, (int)(w_lo + r), slot % g.per_group)], kCellChosen | w[u][1]);
-            red_or_u32(P.pl.rows + (size_t)(w_lo + r) * ROWW, kDoneBit);
+            const int slot = rel_to_slot(g, w_lo + r), ring = rel_to_ring(g, w_lo + r);
+            red_max_u64(&P.votes[cell_index(g, ring, slot % g.per_group)], kCellChosen | w[u][1]);
+            red_or_u32(P.pl.rows + (size_t)ring * ROWW, kDoneBit);
           }
           if (P.rlog != nullptr) {
             // co-located replica (Replica.scala:580-588), here rather than at emission: consecutive threads
             // hold consecutive log entries.  Sound in a sweep: one round per batch = at most one Chosen per
             // slot in this call, so only earlier calls can have the slot, and their numbers are smaller.
-            red_min_u64(&P.rlog[w_lo + r], ((unsigned long long)(P.rseq_base + i) << 32) | w[u][1]);
-            mx = max(mx, (int)(w_lo + r));
+            red_min_u64(&P.rlog[rel_to_ring(g, w_lo + r)], ((unsigned long long)(P.rseq_base + i) << 32) | w[u][1]);
+            mx = max(mx, g.base_local + (int)(w_lo + r));
           }
         }
         if (keep) s_keep[r - r_begin] = make_uint2(i, w[u][1]);
       } else if (i != kNoVote) {
         // Chosen(slot, pending.phase2a.value) (:249-251) at its place in the order of the completing votes
-        emit_chosen<false>(P, out_base + vote_rank(P, s_ccx, i), (int)(w_lo + r) * g.shard_count + g.shard_index,
-                           (int)(w_lo + r), (int)w[u][1], mx);
+        emit_chosen<false>(P, out_base + vote_rank(P, s_ccx, i), rel_to_slot(g, w_lo + r), rel_to_ring(g, w_lo + r),
+                           (int)w[u][1], mx);
       }
     }
   }
@@ -380,8 +380,12 @@ __global__ void __launch_bounds__(kTT, 1) tally_kernel(TallyParams P) {
         int i = base + u * 32 + lane;
         if (i >= whi) continue;
         int local = local_slot(g, rec[u].z);
-        if (local < 0) { report_error(P.st, FPX_ERR_SLOT_RANGE, i); continue; }
-        lo = min(lo, local); hi = max(hi, local);
+        if (local < 0) {   // a retired slot was chosen long ago: the vote finds `Done` (:227-232)
+          if (local != kLocalRetired) report_error(P.st, FPX_ERR_SLOT_RANGE, i);
+          continue;
+        }
+        const int rel = ring_to_rel(g, local);
+        lo = min(lo, rel); hi = max(hi, rel);
         rmin = min(rmin, rec[u].w); rmax = max(rmax, rec[u].w);
         int v = voter_index(g, rec[u].x, rec[u].y, rec[u].z);
         if (v < 0) { flags |= kTsBadVoter; continue; }               // judged by the exact path (needs Done-ness at i)
@@ -406,7 +410,7 @@ __global__ void __launch_bounds__(kTT, 1) tally_kernel(TallyParams P) {
         if (i < whi) {
           int local = local_slot(g, rec[u].z);
           if (local < 0) {
-            report_error(P.st, FPX_ERR_SLOT_RANGE, i);
+            if (local != kLocalRetired) report_error(P.st, FPX_ERR_SLOT_RANGE, i);
           } else {
             row[u] = P.pl.rows + (size_t)local * g.row_words;
             rw[u] = __ldcg(row[u]);
@@ -425,8 +429,8 @@ __global__ void __launch_bounds__(kTT, 1) tally_kernel(TallyParams P) {
         int v = voter_index(g, rec[u].x, rec[u].y, rec[u].z);
         if (v < 0) continue;
         red_min_u32(&row[u][2 + v], P.seq_base + (uint32_t)i);
-        const int local = (int)((row[u] - P.pl.rows) / g.row_words);
-        lo = min(lo, local); hi = max(hi, local);
+        const int rel = ring_to_rel(g, (int)((row[u] - P.pl.rows) / g.row_words));
+        lo = min(lo, rel); hi = max(hi, rel);
         rmin = min(rmin, rec[u].w); rmax = max(rmax, rec[u].w);
       }
     }
@@ -457,7 +461,7 @@ __global__ void __launch_bounds__(kTT, 1) tally_kernel(TallyParams P) {
   FPX_MARK(P.st->t_tally, 2);
 
   // ---- phase B: which votes complete their key
-  const int w_lo = __ldcg(&P.st->ts_min_local), w_hi = __ldcg(&P.st->ts_max_local);
+  const int w_lo = __ldcg(&P.st->ts_min_local), w_hi = __ldcg(&P.st->ts_max_local);   // rel coordinates (live window)
   const int R = __ldcg(&P.st->ts_min_round);
   // (vanilla Mencius: the checked phase A stamped only votes the reference counts, so the rows alone decide)
   bool sweep = !(P.path & 2) && w_hi >= w_lo && (long long)w_hi - w_lo <= 4ll * P.n + 4096 &&
@@ -553,8 +557,8 @@ __global__ void __launch_bounds__(kTT, 1) tally_kernel(TallyParams P) {
           const uint32_t i = ent[u].x;
           const uint32_t rank = s_ccx[i >> 10] + wd[u].y + __popc(wd[u].x & ((1u << (i & 31)) - 1u));
           const int e = e0 + u * kTT;
-          const int local = (int)(w_lo + r_begin + e);
-          emit_chosen<false>(P, out_base + rank, local * g.shard_count + g.shard_index, local, (int)ent[u].y, mx_local);
+          const long long rel = w_lo + r_begin + e;
+          emit_chosen<false>(P, out_base + rank, rel_to_slot(g, rel), rel_to_ring(g, rel), (int)ent[u].y, mx_local);
         }
       }
     } else if (sweep) {
@@ -606,13 +610,13 @@ __global__ void __launch_bounds__(kTT, 1) tally_kernel(TallyParams P) {
   grid_sync(P.st);
   {
     const int lo_w = __ldcg(&P.st->wm_local);
-    const int hi_w = min(__ldcg(&P.st->max_chosen_local) + 2, g.local_slots);  // one past the last candidate hole
+    const int hi_w = min(__ldcg(&P.st->max_chosen_local) + 2, g.base_local + g.local_slots);  // ordinals; one past the last candidate hole
     int found = INT_MAX;
     const long long stride = (long long)gridDim.x * kTT;
     for (long long i = lo_w + (long long)blockIdx.x * kTT + tid; i < hi_w && found == INT_MAX; i += 4 * stride) {
       unsigned long long v[4];
 #pragma unroll
-      for (int u = 0; u < 4; ++u) v[u] = (i + u * stride < hi_w) ? __ldcg(&P.rlog[i + u * stride]) : 0ull;
+      for (int u = 0; u < 4; ++u) v[u] = (i + u * stride < hi_w) ? __ldcg(&P.rlog[rel_to_ring(g, i + u * stride - g.base_local)]) : 0ull;
 #pragma unroll
       for (int u = 3; u >= 0; --u)
         if (i + u * stride < hi_w && v[u] == kU64Empty) found = (int)(i + u * stride);   // ascending: the smallest one last
@@ -629,7 +633,7 @@ __global__ void __launch_bounds__(kTT, 1) tally_kernel(TallyParams P) {
     if (blockIdx.x == 0 && tid == 0) {
       int f = min(__ldcg(&P.st->wm_found), hi_w);
       f = max(f, lo_w);
-      if (f > g.local_slots) f = g.local_slots;
+      if (f > g.base_local + g.local_slots) f = g.base_local + g.local_slots;
       P.st->wm_local = f;
       P.st->wm_found = INT_MAX;
       const int global = f * g.shard_count + g.shard_index;

@@ -96,6 +96,10 @@ class Engine:
     def reset(self):
         self._check(self._L.fpx_reset(self.h))
 
+    def retire_below(self, slot):
+        """Slide the live window: slots below `slot` (all executed) are recycled for the slots slot_capacity ahead."""
+        self._check(self._L.fpx_retire_below(self.h, slot))
+
     def _check(self, st, idx=-1):
         if st != OK:
             detail = self._L.fpx_last_error(self.h).decode() if st == ERR_CUDA else ""

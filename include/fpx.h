@@ -607,6 +607,19 @@ uint32_t fpx_exchange_epoch(const fpx_engine* e);
 int fpx_global_watermark_dev(fpx_engine* e, uint32_t epoch, int32_t timeout_ms, int32_t* d_out, int32_t* d_frontiers);
 int fpx_global_watermark(fpx_engine* e, uint32_t epoch, int32_t timeout_ms, int32_t* out, int32_t* frontiers);
 
+/* State is a ring of slot_capacity slots (per shard: its residue class).  fpx_retire_below slides the live
+ * window [base, base + slot_capacity): every slot below `slot` must be chosen and executed (slot <= the last
+ * published watermark, else FPX_ERR_INVALID_ARG); its proxy-leader row, vote cells and log entry are recycled
+ * for the slots slot_capacity ahead, so a long-lived engine is bounded by the number of slots IN FLIGHT, not
+ * by the length of the log (the reference's maps grow with the log; Replica's BufferMap.garbageCollect,
+ * S/util/BufferMap.scala:94-115, is the same idea).  Afterwards a message for a retired slot meets what the
+ * reference's would: an arm / vote / Chosen finds the key Done or the entry present and is ignored; a Phase2a
+ * is answered (round compare, Phase2b or Nack) but the vote is not recorded -- Phase1b never reads below the
+ * chosen watermark (Acceptor.scala:171-179).  Slots at or beyond base + slot_capacity are FPX_ERR_SLOT_RANGE.
+ * Secondary (slot, round) keys of retired slots stay in the overflow table until fpx_reset.  Not offered for
+ * FPX_VANILLA_MENCIUS (a retired ChosenEntry would have to answer with its value). */
+int fpx_retire_below(fpx_engine* e, int32_t slot);
+
 /* The engine's CUDA stream (a cudaStream_t) so a caller can order its own work
  * (events, NCCL collectives) with the engine's. */
 void* fpx_stream(fpx_engine* e);

@@ -905,3 +905,60 @@ def test_async_host_step_matches_oracle(tally_path):
     H.compare_acceptors(eng, ora, cfg, 0, n_steps * W_)
     H.compare_log(eng, ora, 0, n_steps * W_)
     eng.close()
+
+
+@pytest.mark.parametrize("shards", [1, 3])
+def test_ring_window_slides_past_slot_capacity(tally_path, shards):
+    """fpx_retire_below: a log ten times longer than slot_capacity runs through one engine (per shard), the
+    executed prefix retired as it goes; every stream equals the oracle's, which keeps everything.  Late
+    messages for retired slots meet Done / an existing entry: duplicate arms, votes and Chosen are ignored, a
+    Phase2a is still answered.  A slot beyond the live window is FPX_ERR_SLOT_RANGE."""
+    cfg, _ = T.config_by_name("cfg2")
+    cap, step, total = 4096, 1000, 40000
+    g = T.rng(2024)
+    engs = [Engine(slot_capacity=cap, max_batch=1 << 14, overflow_capacity=1 << 8, shard_index=s, shard_count=shards, **cfg)
+            for s in range(shards)]
+    ora = O.MultiPaxos(2, 1, 5, False, 3, 3)
+    mine = lambda recs, s: recs[recs["slot"] % shards == s]
+    old_votes = None
+    for w in range(total // step):
+        a, p, b = T.workload(300 + w, cfg, step, slot0=w * step)
+        extra_a, extra_p, extra_b = a[:0], p[:0], b[:0]
+        if old_votes is not None and w % 3 == 0:        # stragglers of a window that is retired by now
+            oa, op, ob_ = old_votes
+            extra_a, extra_p, extra_b = oa[:20], op[:30], ob_[:40]
+        A, Pm, B = np.concatenate([extra_a, a]), np.concatenate([extra_p, p]), np.concatenate([b[:500], extra_b, b[500:]])
+        ora.arm(A)
+        _, _, ob, on = ora.acceptor_phase2a(Pm)
+        _, _, oc = ora.proxyleader_phase2b(B)
+        ora.replica_chosen(oc)
+        got_b, got_c = [], []
+        for s, e in enumerate(engs):
+            e.proxyleader_arm(mine(A, s))
+            eb, en = e.acceptor_phase2a(mine(Pm, s))
+            assert len(en) == 0
+            got_b.append(eb)
+            ec = e.proxyleader_phase2b(mine(B, s))
+            e.replica_chosen(ec)
+            got_c.append(ec)
+            wm = e.chosen_watermark()
+            assert wm >= (w + 1) * step
+        for s in range(shards):
+            H.same(got_b[s], mine(ob, s), f"Phase2b stream, window {w}, shard {s}")
+            H.same(got_c[s], mine(oc, s), f"Chosen stream, window {w}, shard {s}")
+        if w >= 2:
+            for e in engs:
+                e.retire_below((w - 1) * step)          # keep the last two windows
+            old_votes = T.workload(300 + w - 2, cfg, step, slot0=(w - 2) * step)
+    assert ora.executed_watermark() == total
+    # live part of the acceptors' state and of the log
+    lo = total - step
+    if shards == 1:
+        H.compare_acceptors(engs[0], ora, cfg, lo, step)
+        H.compare_log(engs[0], ora, lo, step)
+    with pytest.raises(FpxError) as ei:                  # beyond the window: base + capacity
+        engs[0].proxyleader_arm(T.arms(np.array([total + 2 * cap * shards], dtype=np.int32), 0))
+    assert ei.value.status == -6
+    with pytest.raises(FpxError):                        # only the executed prefix may be retired
+        engs[0].retire_below(total + 10)
+    [e.close() for e in engs]
