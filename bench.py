@@ -422,6 +422,8 @@ def main():
     extra = {}
     if not args.no_extra:
         extra["cfg5"] = cfg5_extra(torch, dist, dev, rank, N, local_rank)
+        if rank == 0:
+            extra["cfg4"] = cfg4_extra(torch, dev, local_rank)
 
     cpu = None
     if rank == 0 and N == 1:
@@ -467,6 +469,45 @@ def main():
         print(json.dumps(line), flush=True)
     if N > 1:
         dist.destroy_process_group()
+
+
+def cfg4_extra(torch, dev, local_rank, n_instances=1 << 20, f=2, reps=3):
+    """BASELINE configs[3]: EPaxos, 5 replicas, 20 % key-conflict rate, 2^20 instances, as replica 0 sees them:
+    device time of each handler batch on device-resident rows (fpx_epaxos_*_dev, CUDA events on the handle's
+    stream, best of `reps` fresh replicas) with its algorithmic bytes per message."""
+    from frankenpaxos_b200 import traces as T
+    from frankenpaxos_b200.epaxos import EpaxosReplica
+    n = 2 * f + 1
+    lead, pa, ok = T.epaxos_cfg4(0, f=f, n_instances=n_instances, me=0)
+    td = lambda x: torch.from_numpy(np.ascontiguousarray(x, dtype=np.int32)).to(dev)
+    d_lead, d_pa, d_ok = td(lead), td(pa), td(ok)
+    d_rep = torch.zeros((len(pa), 4 + n), dtype=torch.int32, device=dev)
+    d_ev = torch.zeros((len(ok), 2 + n), dtype=torch.int32, device=dev)
+    best, counts = {}, None
+    for _ in range(reps):
+        eng = EpaxosReplica(f, 0, n_instances // n + 2, max_batch=1 << 20, device=local_rank)
+        ext = torch.cuda.ExternalStream(eng.stream, device=dev)
+        e = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+        e[0].record(ext); eng.lead_dev(d_lead.data_ptr(), len(lead))
+        e[1].record(ext); eng.preaccept_dev(d_pa.data_ptr(), len(pa), d_rep.data_ptr())
+        e[2].record(ext); eng.preacceptok_dev(d_ok.data_ptr(), len(ok), d_ev.data_ptr())
+        e[3].record(ext)
+        eng.sync()
+        for name, j in (("lead", 0), ("preaccept", 1), ("preacceptok", 2)):
+            best[name] = min(best.get(name, 1e9), e[j].elapsed_time(e[j + 1]))
+        ev = d_ev.cpu().numpy()
+        counts = (int((ev[:, 0] == 1).sum()), int((ev[:, 0] == 2).sum()))
+        eng.close()
+    msgs = {"lead": len(lead), "preaccept": len(pa), "preacceptok": len(ok)}
+    # input row + reply row + cmdLog row read+write (+ the 512-byte leader row for lead, one response entry for an Ok)
+    alg = {"lead": 4 * (8 + n) + 64 + 512, "preaccept": 4 * (6 + 2 * n) + 4 * (4 + n) + 2 * 64,
+           "preacceptok": 4 * (6 + n) + 4 * (2 + n) + 4 * 10 + 64}
+    peak, _ = peaks()
+    return {"config": "cfg4: EPaxos n=5 f=2, 2^20 instances, BernoulliSingleKeyWorkload(0.2), replica 0's view, "
+                      "device-resident rows", "fast_commits": counts[0], "slow_paths": counts[1],
+            "calls": {k: {"messages": msgs[k], "kernel_ms": best[k], "messages_per_s": msgs[k] / (best[k] * 1e-3),
+                          "algorithmic_bytes_per_message": alg[k], "GB/s": alg[k] * msgs[k] / (best[k] * 1e-3) / 1e9,
+                          "frac": alg[k] * msgs[k] / (best[k] * 1e-3) / 1e9 / peak} for k in best}}
 
 
 def cfg5_extra(torch, dist, dev, rank, N, local_rank, K5=4, W5=2):

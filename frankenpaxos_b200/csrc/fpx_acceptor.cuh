@@ -43,7 +43,6 @@ struct AcceptorParams {
   uint32_t* g_wacc;                // [grid*kAW] accepted records per warp range
   uint32_t parity;                 // which nack counter this launch uses
   int32_t append;                  // 1: continue the reply streams of the previous launch (chunked host call)
-  int32_t demote;                  // pass 2 re-reads the stream with evict_first: it is dead afterwards
   DevStatus* st;
   VoteConflict* conflicts;
 };
@@ -96,7 +95,7 @@ __device__ __forceinline__ void acceptor_apply(const AcceptorParams& P, int4* ou
 #pragma unroll
     for (int u = 0; u < kAccUnroll; ++u) {
       int i = base + u * 32 + lane;
-      rec[u] = (i < whi) ? (P.demote && !kExact ? ld_hint(P.in + i, pol_out) : ld_cg(P.in + i)) : make_int4(0, -1, 0, -1);
+      rec[u] = (i < whi) ? ld_cg(P.in + i) : make_int4(0, -1, 0, -1);
       cell[u] = 0; old[u] = 0;
     }
 #pragma unroll

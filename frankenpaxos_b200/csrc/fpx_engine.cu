@@ -446,7 +446,7 @@ int64_t fpx_launch_count(const fpx_engine* e) { return e ? e->launches : 0; }
 // Undocumented test/profiling aids: force the tally's exact per-vote path (path = 2; 0 = automatic), and
 // which path the last tally launch took (1 sweep, 2 exact).
 int fpx_debug_set_tally_path(fpx_engine* e, int32_t path) {
-  if (!e || (path & ~0x7e)) return FPX_ERR_INVALID_ARG;
+  if (!e || (path & ~6)) return FPX_ERR_INVALID_ARG;
   e->tally_path = path;
   return FPX_OK;
 }
@@ -532,7 +532,6 @@ static int acceptor_launch(fpx_engine* e, const fpx_p2a* d_in, int32_t n, fpx_p2
   int grid = std::max(1, std::min(e->grid_acceptor, (n + kAT - 1) / kAT));
   P.parity = e->parity;
   P.append = append;
-  P.demote = (e->tally_path & 64) ? 1 : 0;
   e->parity ^= 1u;
   void* args[] = {&P};
   CK(e, cudaLaunchCooperativeKernel((const void*)acceptor_phase2a_kernel, dim3(grid), dim3(kAT), args,

@@ -48,8 +48,7 @@ for variant in args.variants.split(","):
     L.fpx_debug_phase_times.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]
     ext = torch.cuda.ExternalStream(eng.stream, device=dev)
     if not args.old_lib:
-        eng._check(L.fpx_debug_set_tally_path(eng.h, sum(bit for tok, bit in (("exact", 2), ("nored", 4), ("ef", 8), ("el", 16), ("dem", 64))
-                                                        if tok in variant.split("_"))))
+        eng._check(L.fpx_debug_set_tally_path(eng.h, sum(bit for tok, bit in (("exact", 2), ("nored", 4)) if tok in variant.split("_"))))
     flush = torch.empty(1 << 28, dtype=torch.uint8, device=dev) if "flush" in variant else None
     ins = []
     for s in range(S):
