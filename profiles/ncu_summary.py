@@ -1,13 +1,13 @@
 #!/usr/bin/env python3
 """Summarise an .ncu-rep (read here, no GPU needed): per-kernel duration, DRAM /
 L2 bytes and throughput, occupancy, top stall reasons.
-usage: python profiles/ncu_summary.py gpurun_out/prof.ncu-rep"""
+usage: python profiles/ncu_summary.py gpurun_out/prof.ncu-rep | prof_raw.csv"""
 import csv
 import subprocess
 import sys
 
 WANT = [
-    "gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum", "lts__t_bytes.sum",
+    "gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum", "lts__t_sectors.sum",
     "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "lts__throughput.avg.pct_of_peak_sustained_elapsed",
     "sm__throughput.avg.pct_of_peak_sustained_elapsed", "sm__warps_active.avg.pct_of_peak_sustained_active",
     "launch__registers_per_thread", "launch__grid_size", "launch__waves_per_multiprocessor",
@@ -18,7 +18,9 @@ WANT = [
 
 
 def main(path):
-    out = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    # an .ncu-rep, or its `ncu -i rep --page raw --csv` export (the reports of a whole pass exceed gpurun's 64 MiB)
+    out = open(path).read() if path.endswith(".csv") else \
+        subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(out.splitlines()))
     hdr, units = rows[0], rows[1]
     ki = hdr.index("Kernel Name")
