@@ -58,6 +58,7 @@ struct DevStatus {
   uint32_t ts_flags;                    // kTsBadVoter | kTsAnomaly
   uint32_t ts_path;                     // path the LAST tally launch took: 1 sweep, 2 exact (diagnostic)
   uint32_t n_arm_conflicts;             // entries in the arm kernel's conflict list
+  uint32_t wm_need_scan;                // fused tally: the sweep could not settle the watermark, run the first-hole scan
   unsigned long long t_acceptor[8];  // %globaltimer at the phase boundaries of CTA 0 (profiling aid)
   unsigned long long t_tally[8];
 };

@@ -183,6 +183,10 @@ __device__ __forceinline__ void tally_sweep(const TallyParams& P, int w_lo, int 
   const long long r_begin = (long long)blockIdx.x * rows_per_cta;
   const long long r_end = min(nrows, r_begin + rows_per_cta);
   bool ok = true;
+  // co-located replica with the watermark riding along: the first row of my run that is NOT in the log after
+  // this batch (neither there before nor completed now)
+  const bool track_holes = !kEmit && P.rlog != nullptr && P.fuse_watermark;
+  long long hole = LLONG_MAX;
   for (long long r0 = r_begin + threadIdx.x; r0 < r_end; r0 += (long long)kTT * U) {
     uint32_t w[U][ROWW];
 #pragma unroll
@@ -197,6 +201,7 @@ __device__ __forceinline__ void tally_sweep(const TallyParams& P, int w_lo, int 
       uint32_t i;
       ok &= row_completion<ROWW>(P, w[u], R, &i);
       if (!kEmit) {
+        if (track_holes && i == kNoVote && __ldcg(&P.rlog[rel_to_ring(g, w_lo + r)]) == kU64Empty) hole = min(hole, w_lo + r);
         if (i != kNoVote) {
           red_or_u32(&P.bw[i >> 5].x, 1u << (i & 31));
           if (g.protocol == FPX_VANILLA_MENCIUS) {
@@ -222,6 +227,11 @@ __device__ __forceinline__ void tally_sweep(const TallyParams& P, int w_lo, int 
     }
   }
   if (!kEmit && __any_sync(0xffffffffu, !ok) && (threadIdx.x & 31) == 0) atomicOr(&P.st->ts_flags, kTsAnomaly);
+  if (track_holes) {
+    int h = hole == LLONG_MAX ? INT_MAX : g.base_local + (int)hole;      // ordinal
+    h = __reduce_min_sync(0xffffffffu, h);
+    if ((threadIdx.x & 31) == 0 && h != INT_MAX) atomicMin(&P.st->wm_found, h);
+  }
 }
 
 // ---------------------------------------------------------------------------
@@ -354,6 +364,7 @@ __global__ void __launch_bounds__(kTT, 1) tally_kernel(TallyParams P) {
 
   // ---- phase A: clear the bitmap, first-delivery stamps, batch statistics
   FPX_MARK(P.st->t_tally, 0);
+  if (blockIdx.x == 0 && tid == 0) P.st->wm_need_scan = 0;     // read by every CTA only after the third barrier
   for (int wd = blockIdx.x * kTT + tid; wd < nchunks * 32; wd += gridDim.x * kTT)
     __stcg(&P.bw[wd], make_uint2(0u, 0u));
   int lo = INT_MAX, hi = -1, rmin = INT_MAX, rmax = INT_MIN;
@@ -473,6 +484,34 @@ __global__ void __launch_bounds__(kTT, 1) tally_kernel(TallyParams P) {
     tally_sweep<ROWW, false>(P, w_lo, w_hi, R, rows_per_cta, keep, s_keep, s_ccx, out_base, mx_local);
     FPX_MARK(P.st->t_tally, 3);
     grid_sync(P.st);
+    if (P.rlog != nullptr && P.fuse_watermark && blockIdx.x == 0 && tid == 0 && !(__ldcg(&P.st->ts_flags) & kTsAnomaly)) {
+      // executeLog's prefix rule (Replica.scala:394-402) from what the sweep saw: every log put of this batch
+      // is done (barrier).  Old watermark outside the window: nothing of this batch can move it.  Inside: the
+      // first hole the sweep found, else the slot right after the window if that one is empty; anything else
+      // is left to the first-hole scan.
+      const int lo_w = __ldcg(&P.st->wm_local), W0 = g.base_local + w_lo, W1 = g.base_local + w_hi;
+      int f = lo_w;
+      bool settled = P.first != 0;       // a call split into several launches: earlier launches moved the log too
+      if (settled && lo_w >= W0 && lo_w <= W1) {
+        f = __ldcg(&P.st->wm_found);
+        if (f == INT_MAX) {
+          const int nxt = W1 + 1;
+          if (nxt >= g.base_local + g.local_slots) f = g.base_local + g.local_slots;
+          else if (__ldcg(&P.rlog[rel_to_ring(g, nxt - g.base_local)]) == kU64Empty) f = nxt;
+          else settled = false;
+        }
+      }
+      P.st->wm_found = INT_MAX;
+      if (settled) {
+        P.st->wm_local = f;
+        const int global = f * g.shard_count + g.shard_index;
+        P.st->watermark = global;
+        if (P.d_watermark) *P.d_watermark = global;
+        exchange_publish(P.xch, global);
+      } else {
+        P.st->wm_need_scan = 1;
+      }
+    }
     if (__ldcg(&P.st->ts_flags) & kTsAnomaly) {
       // not a steady-state batch after all: forget the sweep's marks, evaluate every vote
       sweep = false;
@@ -482,6 +521,7 @@ __global__ void __launch_bounds__(kTT, 1) tally_kernel(TallyParams P) {
     }
   }
   if (!sweep) {
+    if (blockIdx.x == 0 && tid == 0) { P.st->wm_need_scan = 1; P.st->wm_found = INT_MAX; }
     tally_exact<ROWW, false>(P, wlo, whi, lane);
     FPX_MARK(P.st->t_tally, 3);
     grid_sync(P.st);
@@ -508,6 +548,7 @@ __global__ void __launch_bounds__(kTT, 1) tally_kernel(TallyParams P) {
   }
   FPX_MARK(P.st->t_tally, 5);
   grid_sync(P.st);
+  const bool need_scan = __ldcg(&P.st->wm_need_scan) != 0;
   FPX_MARK(P.st->t_tally, 6);
 
   // ---- phase D: exclusive scan of the chunk counts (every CTA, in shared memory), then the
@@ -606,7 +647,7 @@ __global__ void __launch_bounds__(kTT, 1) tally_kernel(TallyParams P) {
     int m = __reduce_max_sync(full, s_red[0][lane]);
     if (lane == 0 && m != INT_MIN) atomicMax(&P.st->max_chosen_local, m);
   }
-  if (!P.fuse_watermark) return;
+  if (!P.fuse_watermark || !need_scan) return;
   grid_sync(P.st);
   {
     const int lo_w = __ldcg(&P.st->wm_local);
