@@ -49,7 +49,10 @@ struct AcceptorParams {
 
 constexpr int kAccUnroll = 4;
 // one CTA of 32 warps per SM (see fpx_tally.cuh: several CTAs per SM spread up to 2x, and both passes end at a grid barrier)
-constexpr int kAT = 1024;
+#ifndef FPX_AT
+#define FPX_AT 1024
+#endif
+constexpr int kAT = FPX_AT;
 constexpr int kAW = kAT / 32;
 __device__ __forceinline__ int grp_of(int dst) { return dst >> 16; }
 
@@ -184,7 +187,7 @@ __device__ __forceinline__ void acceptor_apply(const AcceptorParams& P, int4* ou
   }
 }
 
-__global__ void __launch_bounds__(kAT, 1) acceptor_phase2a_kernel(AcceptorParams P) {
+__global__ void __launch_bounds__(kAT, 1024 / kAT) acceptor_phase2a_kernel(AcceptorParams P) {
   const Geometry& g = P.g;
   extern __shared__ int s_mv[];  // [num_keys][kAT] private maxVotedSlot columns
   __shared__ int s_wagg[kAW][kMaxKeys];

@@ -31,7 +31,7 @@
 using namespace fpx;
 
 constexpr int kMaxEvents = 16;
-constexpr int kTallySmem = 200 * 1024;  // dynamic shared memory of a tally CTA (one CTA of 1024 threads per SM)
+constexpr int kTallySmem = 200 * 1024 / (1024 / kTT);  // dynamic shared memory of a tally CTA (one CTA of 1024 threads per SM)
 constexpr int kStepRing = 1024;
 
 struct fpx_engine {

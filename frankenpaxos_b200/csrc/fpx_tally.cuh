@@ -79,12 +79,18 @@ struct TallyParams {
   DevStatus* st;
 };
 
-constexpr int kTallyUnroll = 4;   // chunks of 32 votes per warp per pipeline stage in phase A
+#ifndef FPX_TALLY_UNROLL
+#define FPX_TALLY_UNROLL 4
+#endif
+#ifndef FPX_TT
+#define FPX_TT 1024
+#endif
+constexpr int kTallyUnroll = FPX_TALLY_UNROLL;   // chunks of 32 votes per warp per pipeline stage in phase A
 constexpr int kChunkVotes = 1024; // votes per rank chunk (one bitmap word per lane)
 constexpr uint32_t kNoVote = 0xffffffffu;
 // One CTA of 32 warps per SM: several CTAs per SM spread up to 2x in duration (their loads queue behind
 // each other in the SM's L1TEX, B300_MICROARCH "Multi-CTA spread"), and every phase ends at a grid barrier.
-constexpr int kTT = 1024;
+constexpr int kTT = FPX_TT;
 constexpr int kTW = kTT / 32;
 
 // One proxy-leader row from L2 with a single 256-bit load per 8 words (LDG.E.256, sm_100+).
@@ -341,7 +347,7 @@ __device__ __forceinline__ void tally_exact(const TallyParams& P, int wlo, int w
 }
 
 template <int ROWW>
-__global__ void __launch_bounds__(kTT, 1) tally_kernel(TallyParams P) {
+__global__ void __launch_bounds__(kTT, 1024 / kTT) tally_kernel(TallyParams P) {
   const Geometry& g = P.g;
   extern __shared__ uint32_t s_dyn[];  // [nchunks] exclusive scan of the chunk counts, then [keep_cap] kept {vote, value}
   __shared__ int s_red[4][kTW];
@@ -644,7 +650,7 @@ __global__ void __launch_bounds__(kTT, 1) tally_kernel(TallyParams P) {
   if (lane == 0) s_red[0][warp] = mx_local;
   __syncthreads();
   if (warp == 0) {
-    int m = __reduce_max_sync(full, s_red[0][lane]);
+    int m = __reduce_max_sync(full, lane < kTW ? s_red[0][lane] : INT_MIN);
     if (lane == 0 && m != INT_MIN) atomicMax(&P.st->max_chosen_local, m);
   }
   if (!P.fuse_watermark || !need_scan) return;
@@ -667,7 +673,7 @@ __global__ void __launch_bounds__(kTT, 1) tally_kernel(TallyParams P) {
     if (lane == 0) s_red[1][warp] = found;
     __syncthreads();
     if (warp == 0) {
-      found = __reduce_min_sync(full, s_red[1][lane]);
+      found = __reduce_min_sync(full, lane < kTW ? s_red[1][lane] : INT_MAX);
       if (lane == 0 && found != INT_MAX) atomicMin(&P.st->wm_found, found);
     }
     grid_sync(P.st);

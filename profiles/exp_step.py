@@ -19,9 +19,12 @@ ap.add_argument("--steps", type=int, default=12)
 ap.add_argument("--variants", default="default,acc_first,exact,default,acc_first")
 ap.add_argument("--out", default="")
 ap.add_argument("--old-lib", action="store_true", help="time the round-1 build (profiles/_r1/libfpx.so) instead")
+ap.add_argument("--lib", default="", help="time another build of libfpx.so (tuning variants under profiles/_var/)")
 args = ap.parse_args()
 if args.old_lib:
     os.environ["FPX_LIB_OVERRIDE"] = os.path.join(ROOT, "profiles", "_r1", "libfpx.so")
+if args.lib:
+    os.environ["FPX_LIB_OVERRIDE"] = os.path.join(ROOT, args.lib)
 
 import bench  # noqa: E402
 from frankenpaxos_b200 import Engine, traces as T  # noqa: E402
