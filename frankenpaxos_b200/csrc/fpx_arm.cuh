@@ -181,10 +181,12 @@ __device__ __forceinline__ int arm_chunks(const ArmParams& P, int gwarp, int tot
         if (won && P.vanilla) {
           // Server.handleClientRequest: log.put(slot, PendingEntry(0, 0, value)) (:779) and
           // phase2s(slot).phase2bs = {index -> Phase2b} (:818-825): own vote, stamped "before everything"
+          // a NEW Phase 2 entry: stamps of stray votes that arrived before it existed (ignored by the
+          // reference, stamped blindly by the tally) go
           int self = rec.w & 0xffff;
-          P.pl.rows[(size_t)local[u] * g.row_words + 2 + self] = 0;
-          atomicMax(&P.votes[cell_index(g, local[u], self)],
-                    ((unsigned long long)(uint32_t)(rec.y + 1) << 32) | (uint32_t)rec.z);
+          for (int v = 0; v < g.voters; ++v) P.pl.rows[(size_t)local[u] * g.row_words + 2 + v] = v == self ? 0u : kStampEmpty;
+          red_max_u64(&P.votes[cell_index(g, local[u], self)],
+                      ((unsigned long long)(uint32_t)(rec.y + 1) << 32) | (uint32_t)rec.z);
         }
       }
       unsigned wb = __ballot_sync(0xffffffffu, won);

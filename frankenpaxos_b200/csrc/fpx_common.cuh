@@ -36,7 +36,7 @@ constexpr int kWarps = kThreads / 32;
 constexpr int kMaxKeys = FPX_MAX_ACCEPTORS;       // acceptors tracked by the round scan (lane = key)
 constexpr int kMaxConflicts = 1024;
 constexpr int kMaxGrid = 148 * 8;                 // upper bound on CTAs of a cooperative launch
-constexpr uint32_t kTsBadVoter = 1u, kTsAnomaly = 2u, kTsPoison = 4u;  // DevStatus::ts_flags
+constexpr uint32_t kTsBadVoter = 1u, kTsAnomaly = 2u, kTsPoison = 4u, kTsVanillaRound = 8u;  // DevStatus::ts_flags
 
 // Device-resident status block (one per engine).
 struct DevStatus {

@@ -240,7 +240,7 @@ __global__ void __launch_bounds__(256) range_fill_kernel(RangeFillParams P) {
   const unsigned long long cell = ((unsigned long long)(uint32_t)(rec.z + 1) << 32) | (uint32_t)FPX_VALUE_NOOP;
   for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < count; t += (long long)gridDim.x * blockDim.x) {
     int l = local_slot(g, (int)(first + t * stride));
-    if (l >= 0) atomicMax(&P.votes[cell_index(g, l, a)], cell);   // states(slot) = State(round, Noop)
+    if (l >= 0) red_max_u64(&P.votes[cell_index(g, l, a)], cell);   // states(slot) = State(round, Noop)
   }
 }
 
@@ -438,8 +438,8 @@ __global__ void __launch_bounds__(256) vm_skip_kernel(VmSkipParams P) {
       unsigned long long old = atomicCAS(cell, 0ull, chosen);                      // log.put(nextSlot, ChosenEntry(Noop)) (:615-618)
       if (old != 0ull || __ldcg(row) != kUnarmed) report_error(P.st, FPX_ERR_CHECK_FAILED, j);   // :613-614
     } else {
-      atomicMax(cell, chosen);                                                      // choose: log.put (:624)
-      if (slot % n == server && __ldcg(row) != kUnarmed) atomicOr(row, kDoneBit);   // phase2s.remove(slot) (:625)
+      red_max_u64(cell, chosen);                                                      // choose: log.put (:624)
+      if (slot % n == server && __ldcg(row) != kUnarmed) red_or_u32(row, kDoneBit);   // phase2s.remove(slot) (:625)
     }
   }
 }

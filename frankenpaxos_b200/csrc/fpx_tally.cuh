@@ -346,71 +346,12 @@ __device__ __forceinline__ void tally_exact(const TallyParams& P, int wlo, int w
   }
 }
 
-template <int ROWW>
-__global__ void __launch_bounds__(kTT, 1024 / kTT) tally_kernel(TallyParams P) {
+// Vanilla Mencius, checked stamping (fallback when a batch carries a vote of a round other than 0):
+// Server.handlePhase2b ignores a vote when there is no Phase 2 for the slot or it is already chosen
+// (:1088-1106) or its round is stale (:1109-1112); a larger round fails checkEq (:1116).
+__device__ __forceinline__ void tally_stamp_checked(const TallyParams& P, int wlo, int whi, int lane) {
   const Geometry& g = P.g;
-  extern __shared__ uint32_t s_dyn[];  // [nchunks] exclusive scan of the chunk counts, then [keep_cap] kept {vote, value}
-  __shared__ int s_red[4][kTW];
-  __shared__ uint32_t s_flags;
-  __shared__ uint32_t s_scan[kTW];
-
-  const unsigned full = 0xffffffffu;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int total_warps = gridDim.x * kTW;
-  const int per = (((P.n + total_warps - 1) / total_warps) + 31) & ~31;   // votes per warp: contiguous ranges
-  const int gw = blockIdx.x * kTW + warp;
-  const int wlo = (int)min((long long)P.n, (long long)gw * per);
-  const int whi = (int)min((long long)P.n, (long long)wlo + per);
-  const bool vanilla = g.protocol == FPX_VANILLA_MENCIUS;
-  const int nchunks = (P.n + kChunkVotes - 1) / kChunkVotes;
-  uint32_t* const s_ccx = s_dyn;
-  uint2* const s_keep = (uint2*)(s_dyn + ((nchunks + 1) & ~1));
-  const uint32_t out_base = P.first ? 0u : (uint32_t)__ldcg(&P.st->n_chosen);   // rewritten only after the last barrier
-  int mx_local = INT_MIN;   // co-located replica: largest local slot this thread put into the log
-
-  // ---- phase A: clear the bitmap, first-delivery stamps, batch statistics
-  FPX_MARK(P.st->t_tally, 0);
-  if (blockIdx.x == 0 && tid == 0) P.st->wm_need_scan = 0;     // read by every CTA only after the third barrier
-  for (int wd = blockIdx.x * kTT + tid; wd < nchunks * 32; wd += gridDim.x * kTT)
-    __stcg(&P.bw[wd], make_uint2(0u, 0u));
-  int lo = INT_MAX, hi = -1, rmin = INT_MAX, rmax = INT_MIN;
-  uint32_t flags = 0;
-  if (!vanilla) {
-    // blind: no row header load (see the file comment); phase2bs((g,a)) = msg (:237).
-    // Software-pipelined: the records of stage k+1 are in flight while stage k's REDs issue.
-    int4 rec[kTallyUnroll], nxt[kTallyUnroll];
-#pragma unroll
-    for (int u = 0; u < kTallyUnroll; ++u) {
-      int i = wlo + u * 32 + lane;
-      nxt[u] = (i < whi) ? ld_stream(P.in + i) : make_int4(-1, -1, -1, -1);  // {group, acceptor, slot, round}
-    }
-    for (int base = wlo; base < whi; base += 32 * kTallyUnroll) {
-#pragma unroll
-      for (int u = 0; u < kTallyUnroll; ++u) rec[u] = nxt[u];
-#pragma unroll
-      for (int u = 0; u < kTallyUnroll; ++u) {
-        int i = base + 32 * kTallyUnroll + u * 32 + lane;
-        nxt[u] = (i < whi) ? ld_stream(P.in + i) : make_int4(-1, -1, -1, -1);
-      }
-#pragma unroll
-      for (int u = 0; u < kTallyUnroll; ++u) {
-        int i = base + u * 32 + lane;
-        if (i >= whi) continue;
-        int local = local_slot(g, rec[u].z);
-        if (local < 0) {   // a retired slot was chosen long ago: the vote finds `Done` (:227-232)
-          if (local != kLocalRetired) report_error(P.st, FPX_ERR_SLOT_RANGE, i);
-          continue;
-        }
-        const int rel = ring_to_rel(g, local);
-        lo = min(lo, rel); hi = max(hi, rel);
-        rmin = min(rmin, rec[u].w); rmax = max(rmax, rec[u].w);
-        int v = voter_index(g, rec[u].x, rec[u].y, rec[u].z);
-        if (v < 0) { flags |= kTsBadVoter; continue; }               // judged by the exact path (needs Done-ness at i)
-        if (!(P.path & 4)) red_min_u32(P.pl.rows + (size_t)local * g.row_words + 2 + v, P.seq_base + (uint32_t)i);
-      }
-    }
-  } else {
-    for (int base = wlo; base < whi; base += 32 * kTallyUnroll) {
+  for (int base = wlo; base < whi; base += 32 * kTallyUnroll) {
       int4 rec[kTallyUnroll];
       uint32_t* row[kTallyUnroll];
       uint32_t rw[kTallyUnroll];
@@ -446,9 +387,77 @@ __global__ void __launch_bounds__(kTT, 1024 / kTT) tally_kernel(TallyParams P) {
         int v = voter_index(g, rec[u].x, rec[u].y, rec[u].z);
         if (v < 0) continue;
         red_min_u32(&row[u][2 + v], P.seq_base + (uint32_t)i);
-        const int rel = ring_to_rel(g, (int)((row[u] - P.pl.rows) / g.row_words));
+      }
+    }
+}
+
+template <int ROWW>
+__global__ void __launch_bounds__(kTT, 1024 / kTT) tally_kernel(TallyParams P) {
+  const Geometry& g = P.g;
+  extern __shared__ uint32_t s_dyn[];  // [nchunks] exclusive scan of the chunk counts, then [keep_cap] kept {vote, value}
+  __shared__ int s_red[4][kTW];
+  __shared__ uint32_t s_flags;
+  __shared__ uint32_t s_scan[kTW];
+
+  const unsigned full = 0xffffffffu;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int total_warps = gridDim.x * kTW;
+  const int per = (((P.n + total_warps - 1) / total_warps) + 31) & ~31;   // votes per warp: contiguous ranges
+  const int gw = blockIdx.x * kTW + warp;
+  const int wlo = (int)min((long long)P.n, (long long)gw * per);
+  const int whi = (int)min((long long)P.n, (long long)wlo + per);
+  const bool vanilla = g.protocol == FPX_VANILLA_MENCIUS;
+  const int nchunks = (P.n + kChunkVotes - 1) / kChunkVotes;
+  uint32_t* const s_ccx = s_dyn;
+  uint2* const s_keep = (uint2*)(s_dyn + ((nchunks + 1) & ~1));
+  const uint32_t out_base = P.first ? 0u : (uint32_t)__ldcg(&P.st->n_chosen);   // rewritten only after the last barrier
+  int mx_local = INT_MIN;   // co-located replica: largest local slot this thread put into the log
+
+  // ---- phase A: clear the bitmap, first-delivery stamps, batch statistics
+  FPX_MARK(P.st->t_tally, 0);
+  if (blockIdx.x == 0 && tid == 0) P.st->wm_need_scan = 0;     // read by every CTA only after the third barrier
+  for (int wd = blockIdx.x * kTT + tid; wd < nchunks * 32; wd += gridDim.x * kTT)
+    __stcg(&P.bw[wd], make_uint2(0u, 0u));
+  int lo = INT_MAX, hi = -1, rmin = INT_MAX, rmax = INT_MIN;
+  uint32_t flags = 0;
+  {
+    // blind: no row header load (see the file comment); phase2bs((g,a)) = msg (:237).
+    // Vanilla Mencius too: a coordinator's Phase 2 entries are always in round 0 (Server.handleClientRequest,
+    // :779, enforced by fpx_vm_client_request), so a round-0 vote is right for every entry that exists; votes
+    // for slots without an entry or with a chosen one are ignored by the reference (:1088-1106) and harmless
+    // here (the sweep skips such rows, arming resets the stamps).  A vote of another round raises
+    // kTsVanillaRound: nothing is stamped for it and the batch falls back to the checked pass below.
+    // Software-pipelined: the records of stage k+1 are in flight while stage k's REDs issue.
+    int4 rec[kTallyUnroll], nxt[kTallyUnroll];
+#pragma unroll
+    for (int u = 0; u < kTallyUnroll; ++u) {
+      int i = wlo + u * 32 + lane;
+      nxt[u] = (i < whi) ? ld_stream(P.in + i) : make_int4(-1, -1, -1, -1);  // {group, acceptor, slot, round}
+    }
+    for (int base = wlo; base < whi; base += 32 * kTallyUnroll) {
+#pragma unroll
+      for (int u = 0; u < kTallyUnroll; ++u) rec[u] = nxt[u];
+#pragma unroll
+      for (int u = 0; u < kTallyUnroll; ++u) {
+        int i = base + 32 * kTallyUnroll + u * 32 + lane;
+        nxt[u] = (i < whi) ? ld_stream(P.in + i) : make_int4(-1, -1, -1, -1);
+      }
+#pragma unroll
+      for (int u = 0; u < kTallyUnroll; ++u) {
+        int i = base + u * 32 + lane;
+        if (i >= whi) continue;
+        int local = local_slot(g, rec[u].z);
+        if (local < 0) {   // a retired slot was chosen long ago: the vote finds `Done` (:227-232)
+          if (local != kLocalRetired) report_error(P.st, FPX_ERR_SLOT_RANGE, i);
+          continue;
+        }
+        const int rel = ring_to_rel(g, local);
         lo = min(lo, rel); hi = max(hi, rel);
         rmin = min(rmin, rec[u].w); rmax = max(rmax, rec[u].w);
+        if (vanilla && rec[u].w != 0) { flags |= kTsVanillaRound; continue; }
+        int v = voter_index(g, rec[u].x, rec[u].y, rec[u].z);
+        if (v < 0) { if (!vanilla) flags |= kTsBadVoter; continue; }   // judged by the exact path (needs Done-ness at i)
+        if (!(P.path & 4)) red_min_u32(P.pl.rows + (size_t)local * g.row_words + 2 + v, P.seq_base + (uint32_t)i);
       }
     }
   }
@@ -481,8 +490,9 @@ __global__ void __launch_bounds__(kTT, 1024 / kTT) tally_kernel(TallyParams P) {
   const int w_lo = __ldcg(&P.st->ts_min_local), w_hi = __ldcg(&P.st->ts_max_local);   // rel coordinates (live window)
   const int R = __ldcg(&P.st->ts_min_round);
   // (vanilla Mencius: the checked phase A stamped only votes the reference counts, so the rows alone decide)
+  const uint32_t flags_a = __ldcg(&P.st->ts_flags);
   bool sweep = !(P.path & 2) && w_hi >= w_lo && (long long)w_hi - w_lo <= 4ll * P.n + 4096 &&
-               (vanilla || (__ldcg(&P.st->ts_flags) == 0 && R == __ldcg(&P.st->ts_max_round)));
+               (vanilla ? !(flags_a & kTsVanillaRound) : (flags_a == 0 && R == __ldcg(&P.st->ts_max_round)));
   // every CTA sweeps a contiguous run of the window's rows (a multiple of the CTA size)
   const int rows_per_cta = sweep ? (int)((((long long)w_hi - w_lo + gridDim.x) / gridDim.x + kTT - 1) / kTT) * kTT : 0;
   const bool keep = rows_per_cta <= P.keep_cap;
@@ -528,6 +538,10 @@ __global__ void __launch_bounds__(kTT, 1024 / kTT) tally_kernel(TallyParams P) {
   }
   if (!sweep) {
     if (blockIdx.x == 0 && tid == 0) { P.st->wm_need_scan = 1; P.st->wm_found = INT_MAX; }
+    if (vanilla && (flags_a & kTsVanillaRound)) {   // a vote of another round: judge every vote against its row
+      tally_stamp_checked(P, wlo, whi, lane);
+      grid_sync(P.st);
+    }
     tally_exact<ROWW, false>(P, wlo, whi, lane);
     FPX_MARK(P.st->t_tally, 3);
     grid_sync(P.st);

@@ -113,10 +113,10 @@ __global__ void __launch_bounds__(256) vm_learn_chosen_kernel(VmParams P) {
   int local = local_slot(g, slot);
   if (local < 0) { report_error(P.st, FPX_ERR_SLOT_RANGE, i); return; }
   if ((uint32_t)server >= (uint32_t)g.per_group) { report_error(P.st, FPX_ERR_BAD_ACCEPTOR, i); return; }
-  atomicMax(&P.votes[cell_index(g, local, server)], kCellChosen | (uint32_t)rec.w);   // ChosenEntry (:624)
+  red_max_u64(&P.votes[cell_index(g, local, server)], kCellChosen | (uint32_t)rec.w);   // ChosenEntry (:624)
   if (slot % g.per_group == server) {                                                       // phase2s.remove(slot) (:625)
     uint32_t* row = P.rows + (size_t)local * g.row_words;
-    if (row[0] != kUnarmed) atomicOr(row, kDoneBit);
+    if (row[0] != kUnarmed) red_or_u32(row, kDoneBit);
   }
 }
 
