@@ -175,19 +175,25 @@ __device__ __forceinline__ int arm_chunks(const ArmParams& P, int gwarp, int tot
       if (c0 + u >= n_chunks) break;
       int i = (c0 + u) * 32 + lane;
       bool won = local[u] >= 0 && old[u] == kU64Empty;       // Pending(phase2a, {}) created (:213)
-      if (local[u] >= 0 && (old[u] != kU64Empty || P.vanilla)) {
+      int self = -1;
+      if (local[u] >= 0 && old[u] != kU64Empty) {            // rare: the key exists, or a second round of the slot
         const int4 rec = __ldcg(P.in + i);
         won = arm_finish(P, rec, old[u], i);
-        if (won && P.vanilla) {
-          // Server.handleClientRequest: log.put(slot, PendingEntry(0, 0, value)) (:779) and
-          // phase2s(slot).phase2bs = {index -> Phase2b} (:818-825): own vote, stamped "before everything"
-          // a NEW Phase 2 entry: stamps of stray votes that arrived before it existed (ignored by the
-          // reference, stamped blindly by the tally) go
-          int self = rec.w & 0xffff;
-          for (int v = 0; v < g.voters; ++v) P.pl.rows[(size_t)local[u] * g.row_words + 2 + v] = v == self ? 0u : kStampEmpty;
-          red_max_u64(&P.votes[cell_index(g, local[u], self)],
-                      ((unsigned long long)(uint32_t)(rec.y + 1) << 32) | (uint32_t)rec.z);
-        }
+        self = rec.w & 0xffff;
+      } else if (won && P.vanilla) {
+        self = rel_to_slot(g, ring_to_rel(g, local[u])) % g.per_group;   // the owner coordinates its slot (checked above)
+      }
+      if (won && P.vanilla) {
+        // Server.handleClientRequest: log.put(slot, PendingEntry(0, 0, value)) (:779) and
+        // phase2s(slot).phase2bs = {index -> Phase2b} (:818-825): own vote, stamped "before everything".
+        // A NEW Phase 2 entry: stamps of stray votes that arrived before it existed (ignored by the
+        // reference, stamped blindly by the tally) go -- the rest of the row is rewritten with wide stores.
+        uint32_t* row = P.pl.rows + (size_t)local[u] * g.row_words;
+        auto stamp = [&](int w) { return w - 2 == self ? 0u : kStampEmpty; };
+        *(uint2*)(row + 2) = make_uint2(stamp(2), stamp(3));
+        for (int w = 4; w < g.row_words; w += 4) *(uint4*)(row + w) = make_uint4(stamp(w), stamp(w + 1), stamp(w + 2), stamp(w + 3));
+        // vote cell {round + 1 : value}; want = {value : round}
+        red_max_u64(&P.votes[cell_index(g, local[u], self)], (((want[u] & 0xffffffffull) + 1ull) << 32) | (want[u] >> 32));
       }
       unsigned wb = __ballot_sync(0xffffffffu, won);
       if (lane == 0) P.win_bits[c0 + u] = wb;
