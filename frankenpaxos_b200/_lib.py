@@ -21,7 +21,7 @@ SYMBOLS = [
     "fpx_acceptor_phase1a", "fpx_leader_safe_values",
     "fpx_vm_client_request", "fpx_vm_phase2a", "fpx_vm_learn_chosen", "fpx_vm_skip", "fpx_vm_client_request_dev", "fpx_vm_phase2a_dev",
     "fpx_mencius_arm_range", "fpx_mencius_acceptor_noop_range", "fpx_mencius_range_phase2b",
-    "fpx_mencius_replica_chosen_range",
+    "fpx_mencius_replica_chosen_range", "fpx_mencius_replica_range_first", "fpx_mencius_replica_range_fill",
     "fpx_wire_decode_inbound", "fpx_wire_decode_inbound_dev", "fpx_wire_encode_phase2b", "fpx_wire_encode_phase2b_dev",
     "fpx_wire_encode_nack", "fpx_wire_encode_chosen",
     "fpx_step_submit", "fpx_step_wait", "fpx_retire_below", "fpx_exchange_export", "fpx_exchange_attach", "fpx_exchange_attach_local", "fpx_exchange_epoch",
@@ -100,6 +100,8 @@ def lib():
     L.fpx_mencius_range_phase2b.argtypes = [vp, vp, i32, vp, p(i32), p(i64)]; L.fpx_mencius_range_phase2b.restype = i32
     L.fpx_mencius_replica_chosen_range.argtypes = [vp, vp, i32, p(i64)]
     L.fpx_mencius_replica_chosen_range.restype = i32
+    L.fpx_mencius_replica_range_first.argtypes = [vp, vp, i32, vp, p(i64)]; L.fpx_mencius_replica_range_first.restype = i32
+    L.fpx_mencius_replica_range_fill.argtypes = [vp, vp, i32, vp, p(i64)]; L.fpx_mencius_replica_range_fill.restype = i32
     L.fpx_wire_decode_inbound.argtypes = [vp, i32, vp, vp, i32, vp, vp, p(i64)]; L.fpx_wire_decode_inbound.restype = i32
     L.fpx_wire_decode_inbound_dev.argtypes = [vp, i32, vp, vp, i32, vp, vp]; L.fpx_wire_decode_inbound_dev.restype = i32
     L.fpx_wire_encode_phase2b.argtypes = [vp, vp, i32, vp, i32, vp, p(i64)]; L.fpx_wire_encode_phase2b.restype = i32

@@ -286,6 +286,26 @@ class Engine:
         self._check(self._L.fpx_mencius_replica_chosen_range(self.h, recs.ctypes.data, len(recs), C.byref(err)),
                     err.value)
 
+    RANGE_NO_HIT = 0x7f7f7f7f
+
+    def mencius_replica_range_first(self, recs):
+        """Per record: this shard's first slot of the range that is already in its log (RANGE_NO_HIT if none)."""
+        recs = np.ascontiguousarray(recs, dtype=CHOSEN_RANGE)
+        first = np.full(max(len(recs), 1), self.RANGE_NO_HIT, dtype=np.int32)
+        err = C.c_int64(-1)
+        self._check(self._L.fpx_mencius_replica_range_first(self.h, recs.ctypes.data, len(recs), first.ctypes.data,
+                                                            C.byref(err)), err.value)
+        return first[:len(recs)]
+
+    def mencius_replica_range_fill(self, recs, first):
+        """Noop into this shard's slots of [start, min(end, first[i])): `first` = the minimum over the shards."""
+        recs = np.ascontiguousarray(recs, dtype=CHOSEN_RANGE)
+        first = np.ascontiguousarray(first, dtype=np.int32)
+        assert len(first) == len(recs)
+        err = C.c_int64(-1)
+        self._check(self._L.fpx_mencius_replica_range_fill(self.h, recs.ctypes.data, len(recs), first.ctypes.data,
+                                                           C.byref(err)), err.value)
+
     # -- wire codec: protobuf bytes of a batch of messages <-> records (include/fpx.h)
     def wire_decode_inbound(self, inbound, buf, offsets):
         """buf: uint8 array with the messages back to back, offsets[n+1].  Returns (kind[n], rec[n])."""

@@ -62,6 +62,27 @@ def connect(engine, group=None):
     return handles
 
 
+def min_over_shards(values, group=None):
+    """Element-wise minimum of an int32 numpy vector over the ranks (MIN all-reduce; identity on one rank)."""
+    import torch
+    import torch.distributed as dist
+    values = np.ascontiguousarray(values, dtype=np.int32)
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return values
+    dev = "cuda" if dist.get_backend(group) == "nccl" else "cpu"
+    t = torch.from_numpy(values.copy()).to(dev)
+    dist.all_reduce(t, op=dist.ReduceOp.MIN, group=group)
+    return t.cpu().numpy()
+
+
+def replica_chosen_range(engine, recs, group=None):
+    """Replica.handleChosenNoopRange (mencius/Replica.scala:464-486) on a sharded log: the handler stops at the
+    first slot of the range that is already in the log, and that slot may belong to another shard -- every rank
+    reports its first hit per record, the minimum over the ranks bounds every rank's fill."""
+    first = engine.mencius_replica_range_first(recs)
+    engine.mencius_replica_range_fill(recs, min_over_shards(first, group))
+
+
 def merge_chosen_in_slot_order(per_rank_chosen):
     """A replica's view of the sharded log: Chosen records of all ranks by slot."""
     allc = np.concatenate(per_rank_chosen)

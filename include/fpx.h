@@ -341,9 +341,20 @@ int fpx_mencius_range_phase2b(fpx_engine* e, const fpx_p2b_range* in, int32_t n,
  * ... < end are put as Noop UNTIL THE FIRST ONE ALREADY IN THE LOG, where the reference's
  * handler returns (:476-480).  Batch contract (FPX_ERR_BATCH_ORDER): two records of one
  * call must not cover a common slot.  With shard_count > 1 "already in the log" is judged
- * on this shard's slots only.  fpx_chosen_watermark afterwards is the first hole, i.e.
+ * on this shard's slots only (use the _first / _fill pair below for the reference's result).  fpx_chosen_watermark afterwards is the first hole, i.e.
  * where executeLog stops when it next runs. */
 int fpx_mencius_replica_chosen_range(fpx_engine* e, const fpx_chosen_range* in, int32_t n, int64_t* err_index);
+/* The two halves of the call above for a log sharded by slot residue, where "the first slot already in the log"
+ * (:476-480) may live on another shard: _first reports, per record, this shard's first slot of the range that is
+ * in its log (FPX_RANGE_NO_HIT if none) and changes nothing; the caller takes the minimum over the shards (one
+ * integer per record: sharding.replica_chosen_range all-reduces it) and hands it to _fill, which puts Noop into
+ * this shard's slots of [start, min(end, first[i])).  With the minimum over all shards the union of the shards'
+ * logs is the reference's log. */
+#define FPX_RANGE_NO_HIT 0x7f7f7f7f
+int fpx_mencius_replica_range_first(fpx_engine* e, const fpx_chosen_range* in, int32_t n, int32_t* first_out,
+                                    int64_t* err_index);
+int fpx_mencius_replica_range_fill(fpx_engine* e, const fpx_chosen_range* in, int32_t n, const int32_t* first,
+                                   int64_t* err_index);
 
 /* ---- Wire codec: the reference's protobuf bytes <-> the records above ---------------
  * Every actor's inbound serializer is ProtoSerializer (S/ProtoSerializer.scala:3-11:

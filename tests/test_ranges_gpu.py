@@ -250,6 +250,40 @@ def test_ranges_on_slot_residue_shards():
         e.close()
 
 
+def test_sharded_range_stops_at_a_slot_held_by_another_shard():
+    """handleChosenNoopRange returns at the first slot already in the log (mencius/Replica.scala:476-480); on a
+    log sharded by slot residue that slot may belong to another shard.  _first / min over shards / _fill gives
+    the reference's log; each shard on its own would fill past the hit."""
+    f, LG, AG, per, cap, P = 1, 2, 1, 3, 6000, 3
+    _, ora = make(f, LG, AG, per, cap)
+    engs = [Engine(f, AG, per, num_leaders=2, num_replicas=2, slot_capacity=cap, max_batch=1 << 12, protocol=MENCIUS,
+                   num_leader_groups=LG, shard_index=i, shard_count=P) for i in range(P)]
+    # slots 1000 (shard 1), 2501 (shard 2) and 4000 (shard 1) are chosen before the ranges arrive
+    pre = np.array([(1000, 7), (2501, 8), (4000, 9)], dtype=CHOSEN)
+    ora.replica_chosen(pre)
+    for i, e in enumerate(engs):
+        mine = pre[pre["slot"] % P == i]
+        if len(mine):
+            e.replica_chosen(mine)
+    RC = CHOSEN_RANGE
+    ranges = np.array([(0, 2000), (2001, 3001), (3000, 3800), (3800, 5000)], dtype=RC)
+    ora.replica_chosen_range(ranges, cap)
+    firsts = np.stack([e.mencius_replica_range_first(ranges) for e in engs])
+    assert firsts[1, 0] == 1000 and firsts[0, 0] == Engine.RANGE_NO_HIT and firsts[2, 1] == 2501
+    assert (firsts[:, 2] == Engine.RANGE_NO_HIT).all() and firsts[:, 3].min() == 4000
+    bound = firsts.min(axis=0)
+    for e in engs:
+        e.mencius_replica_range_fill(ranges, bound)
+    merged = np.full(cap, -1, dtype=np.int32)
+    for i, e in enumerate(engs):
+        merged[i::P] = e.snapshot_log(0, cap)[i::P]
+    want = ora.snapshot_log(0, cap)
+    H.same(merged, want, "union of the shards' logs")
+    assert want[998] == VALUE_NOOP and want[1002] == -1 and want[3002] == VALUE_NOOP and want[4002] == -1
+    for e in engs:
+        e.close()
+
+
 # --------------------------------------------------------------------------- vanilla Mencius skips
 def vm_logs(eng, ora, n, cap):
     for s in range(n):

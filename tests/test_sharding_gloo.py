@@ -103,3 +103,64 @@ def test_connect_routes_every_peer_handle():
     for rank, attached, first_bytes, ok in res:
         assert attached == [g for g in range(world) if g != rank]
         assert first_bytes == [1, 2, 3] and ok
+
+
+class _FakeRangeEngine:
+    """Stands in for Engine in sharding.replica_chosen_range: a numpy log of this rank's residue class, with the
+    semantics of fpx_mencius_replica_range_first / _fill (include/fpx.h)."""
+    NO_HIT = 0x7f7f7f7f
+    def __init__(self, rank, world, cap, lgroups):
+        self.rank, self.world, self.lg = rank, world, lgroups
+        self.log = np.full(cap, -1, dtype=np.int64)
+    def mencius_replica_range_first(self, recs):
+        out = []
+        for s, e in recs:
+            hits = [x for x in range(s, e, self.lg) if x % self.world == self.rank and self.log[x] != -1]
+            out.append(hits[0] if hits else self.NO_HIT)
+        return np.array(out, dtype=np.int32)
+    def mencius_replica_range_fill(self, recs, first):
+        for (s, e), f in zip(recs, first):
+            for x in range(s, min(e, int(f)), self.lg):
+                if x % self.world == self.rank:
+                    self.log[x] = 0
+
+
+def _range_worker(rank, world, port, q):
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from frankenpaxos_b200 import sharding as S
+    cap, lg = 400, 2
+    e = _FakeRangeEngine(rank, world, cap, lg)
+    for slot, v in [(100, 7), (251, 8)]:
+        if slot % world == rank:
+            e.log[slot] = v
+    S.replica_chosen_range(e, [(0, 200), (201, 301), (300, 380)])
+    q.put((rank, e.log.tolist()))
+    dist.destroy_process_group()
+
+
+def test_sharded_noop_range_stops_at_the_global_first_hit():
+    """sharding.replica_chosen_range: the MIN all-reduce of the per-record first hits makes every rank stop where
+    the reference's handleChosenNoopRange returns (mencius/Replica.scala:476-480), whoever owns that slot."""
+    world, cap, lg = 3, 400, 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_range_worker, args=(r, world, port, q)) for r in range(world)]
+    [p.start() for p in procs]
+    res = sorted(q.get(timeout=120) for _ in range(world))
+    [p.join(timeout=60) for p in procs]
+    assert all(p.exitcode == 0 for p in procs)
+    merged = np.full(cap, -1, dtype=np.int64)
+    for rank, log in res:
+        merged[rank::world] = np.array(log)[rank::world]
+    want = np.full(cap, -1, dtype=np.int64)
+    want[100], want[251] = 7, 8
+    for s, e in [(0, 200), (201, 301), (300, 380)]:        # the reference's loop
+        for x in range(s, e, lg):
+            if want[x] != -1:
+                break
+            want[x] = 0
+    assert np.array_equal(merged, want)
