@@ -499,9 +499,10 @@ def cfg4_extra(torch, dev, local_rank, n_instances=1 << 20, f=2, reps=3):
         counts = (int((ev[:, 0] == 1).sum()), int((ev[:, 0] == 2).sum()))
         eng.close()
     msgs = {"lead": len(lead), "preaccept": len(pa), "preacceptok": len(ok)}
-    # input row + reply row + cmdLog row read+write (+ the 512-byte leader row for lead, one response entry for an Ok)
-    alg = {"lead": 4 * (8 + n) + 64 + 512, "preaccept": 4 * (6 + 2 * n) + 4 * (4 + n) + 2 * 64,
-           "preacceptok": 4 * (6 + n) + 4 * (2 + n) + 4 * 10 + 64}
+    # input row + reply row + cmdLog row read+write (+ the 384-byte leader row for lead; for an Ok the leader
+    # row's header, stamp and answer sectors, 32 bytes each)
+    alg = {"lead": 4 * (8 + n) + 64 + 384, "preaccept": 4 * (6 + 2 * n) + 4 * (4 + n) + 2 * 64,
+           "preacceptok": 4 * (6 + n) + 4 * (2 + n) + 3 * 32}
     peak, _ = peaks()
     return {"config": "cfg4: EPaxos n=5 f=2, 2^20 instances, BernoulliSingleKeyWorkload(0.2), replica 0's view, "
                       "device-resident rows", "fast_commits": counts[0], "slow_paths": counts[1],
@@ -537,11 +538,8 @@ def cfg5_extra(torch, dist, dev, rank, N, local_rank, K5=4, W5=2):
 
     def step(s):
         dr, dp, db = ins[s]
-        eng.vm_client_request_dev(dr.data_ptr(), n)
-        eng.vm_phase2a_dev(dp.data_ptr(), nrec, o_rep.data_ptr())
-        eng.proxyleader_phase2b_dev(db.data_ptr(), nrec, o_ch.data_ptr())
-        eng.replica_chosen_last_dev(o_ch.data_ptr())
-        eng.chosen_watermark_dev(wm.data_ptr())
+        # one C call per step: client requests, Phase2a batch, tally + log put + watermark (+ exchange) in one kernel
+        eng.vm_step_dev(dr.data_ptr(), n, dp.data_ptr(), nrec, o_rep.data_ptr(), db.data_ptr(), nrec, o_ch.data_ptr(), wm.data_ptr())
     for s in range(W5):
         step(s)
     eng.sync()
@@ -571,7 +569,7 @@ def cfg5_extra(torch, dist, dev, rank, N, local_rank, K5=4, W5=2):
                       "step, 6 Phase2a + 6 Phase2b per slot, both shuffled", "n_gpus": N, "steps": K5, "warmup": W5,
             "ms_per_step": ms, "value": N * n / (ms * 1e-3), "unit": "slots/s",
             "messages_per_s": N * (1 + 2 * (srv - 1)) * n / (ms * 1e-3), "global_prefix": gp,
-            "calls": "vm_client_request + vm_phase2a + proxyleader_phase2b + replica_chosen + chosen_watermark (device pointers)"}
+            "calls": "fpx_vm_step_dev: vm_client_request + vm_phase2a + tally with the log put and the watermark fused (3 launches, device pointers)"}
 
 
 if __name__ == "__main__":

@@ -19,7 +19,7 @@ SYMBOLS = [
     "fpx_replica_chosen_dev", "fpx_replica_chosen_last_dev", "fpx_chosen_watermark_dev", "fpx_sync",
     "fpx_stream", "fpx_launch_count", "fpx_set_coop_ctas_per_sm", "fpx_step_dev", "fpx_step_kernel_ms", "fpx_step_arm_ms",
     "fpx_acceptor_phase1a", "fpx_leader_safe_values",
-    "fpx_vm_client_request", "fpx_vm_phase2a", "fpx_vm_learn_chosen", "fpx_vm_skip", "fpx_vm_client_request_dev", "fpx_vm_phase2a_dev",
+    "fpx_vm_client_request", "fpx_vm_phase2a", "fpx_vm_learn_chosen", "fpx_vm_skip", "fpx_vm_client_request_dev", "fpx_vm_phase2a_dev", "fpx_vm_step_dev",
     "fpx_mencius_arm_range", "fpx_mencius_acceptor_noop_range", "fpx_mencius_range_phase2b",
     "fpx_mencius_replica_chosen_range", "fpx_mencius_replica_range_first", "fpx_mencius_replica_range_fill",
     "fpx_wire_decode_inbound", "fpx_wire_decode_inbound_dev", "fpx_wire_encode_phase2b", "fpx_wire_encode_phase2b_dev",
@@ -110,6 +110,7 @@ def lib():
     L.fpx_wire_encode_chosen.argtypes = [vp, vp, i32, vp, vp, i32, vp, i32, vp, p(i64)]
     L.fpx_wire_encode_chosen.restype = i32
     L.fpx_step_dev.argtypes = [vp, vp, i32, vp, i32, vp, vp, vp, i32, vp, vp, i32]; L.fpx_step_dev.restype = i32
+    L.fpx_vm_step_dev.argtypes = [vp, vp, i32, vp, i32, vp, vp, i32, vp, vp]; L.fpx_vm_step_dev.restype = i32
     L.fpx_step_kernel_ms.argtypes = [vp, i32, p(C.c_float), p(C.c_float)]; L.fpx_step_kernel_ms.restype = i32
     L.fpx_step_arm_ms.argtypes = [vp, i32, p(C.c_float)]; L.fpx_step_arm_ms.restype = i32
     L.fpx_sync.argtypes = [vp, p(SyncResult)]; L.fpx_sync.restype = i32

@@ -1035,6 +1035,19 @@ int fpx_vm_learn_chosen(fpx_engine* e, const fpx_p2b* in, int32_t n, int64_t* er
   return vm_call(e, in, n, nullptr, err_index, 1);
 }
 
+int fpx_vm_step_dev(fpx_engine* e, const fpx_p2a* d_req, int32_t n_req, const fpx_p2a* d_p2a, int32_t n_p2a,
+                    fpx_p2b* d_reply, const fpx_p2b* d_p2b, int32_t n_p2b, fpx_chosen* d_out_chosen, int32_t* d_watermark) {
+  if (!e) return FPX_ERR_INVALID_ARG;
+  if (e->g.protocol != FPX_VANILLA_MENCIUS) return FPX_ERR_UNSUPPORTED;
+  // the client requests open the Phase 2 entries the votes of this step are tallied against, so they go first;
+  // the Phase2a batch touches the other servers' cells only
+  int c = fpx_vm_client_request_dev(e, d_req, n_req);
+  if (c != FPX_OK) return c;
+  c = vm_launch(e, d_p2a, n_p2a, d_reply, 0);
+  if (c != FPX_OK) return c;
+  return tally_launch(e, d_p2b, n_p2b, d_out_chosen, 1, d_watermark);
+}
+
 #include "fpx_engine_ranges.inc"
 #include "fpx_engine_wire.inc"
 

@@ -24,14 +24,16 @@ namespace fpx {
 
 constexpr int kEpMaxN = 8;          // replicas (n = 2f+1 <= 7)
 constexpr int kEpCmdWords = 16;     // cmdLog row: 8 header + 8 deps
-constexpr int kEpLeadWords = 128;   // leader row
+constexpr int kEpLeadWords = 96;    // leader row: twelve 32-byte sectors, every field group sector-aligned
 // cmdLog row words
 enum { C_KIND = 0, C_VALUE, C_BORD, C_BREP, C_VBORD, C_VBREP, C_SEQ, C_PAD, C_DEPS = 8 };
 enum { EK_NONE = 0, EK_NOCOMMAND = 1, EK_PREACCEPTED = 2, EK_ACCEPTED = 3, EK_COMMITTED = 4 };
-// leader row words
-enum { L_KIND = 0, L_VALUE, L_BORD, L_BREP, L_FLAGS, L_ASEQ, L_PAD0, L_PAD1, L_ADEPS = 8, L_ASTAMP = 16, L_RESP = 24 };
+// leader row words: header | accept-phase deps | AcceptOk stamps | PreAcceptOk stamps | one 32-byte answer
+// {seq, deps[7]} per replica.  A response touches the header sector, one stamp word and one answer sector;
+// counting a quorum reads one stamp sector.
+enum { L_KIND = 0, L_VALUE, L_BORD, L_BREP, L_FLAGS, L_ASEQ, L_PAD0, L_PAD1, L_ADEPS = 8, L_ASTAMP = 16, L_RSTAMP = 24, L_RESP = 32 };
 enum { LK_NONE = 0, LK_PREACCEPTING = 1, LK_ACCEPTING = 2 };
-constexpr int kEpRespWords = 10;    // {stamp, seq, deps[8]}
+constexpr int kEpRespWords = 8;     // {seq, deps[7]} (n <= 7)
 enum { LF_AVOID = 1, LF_TIMER = 2 };
 enum { REPLY_NONE = 0, REPLY_OK = 1, REPLY_NACK = 2, REPLY_COMMIT = 3 };
 enum { EV_NONE = 0, EV_FAST_COMMIT = 1, EV_SLOW_ACCEPT = 2, EV_TIMER = 3, EV_COMMIT = 4 };
@@ -95,38 +97,97 @@ struct EpParams {
   uint32_t seq_base;   // response stamps
 };
 
+// A CTA's tile of kEpTile fixed-width int32 rows staged in shared memory with coalesced 128-bit loads; row
+// stride Wp = W | 1 words (odd: conflict-free when thread t reads row t).  256 * W * 4 bytes per tile: the
+// tile starts 16-byte aligned.
+constexpr int kEpTile = 256;
+__device__ __forceinline__ void ep_stage_rows(const int32_t* in, long long tile0, int rows, int W, int Wp, int32_t* s_in) {
+  const int words = rows * W;
+  const int4* src = (const int4*)(in + tile0 * W);
+  const uint32_t mW = 0xffffffffu / (uint32_t)W + 1u;           // e / W for e < 2^16
+  for (int v = threadIdx.x; v < words / 4; v += kEpTile) {
+    const int4 x = ld_stream(src + v);
+    const int vals[4] = {x.x, x.y, x.z, x.w};
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const uint32_t e = 4u * v + q, row = __umulhi(e, mW);
+      s_in[row * Wp + (e - row * W)] = vals[q];
+    }
+  }
+  for (int e = (words & ~3) + threadIdx.x; e < words; e += kEpTile) s_in[(e / W) * Wp + e % W] = in[tile0 * W + e];
+}
+
+// word w of a fresh leader row (transitionToPreAcceptPhase, :695-724): PreAccepting in the message's ballot, no
+// AcceptOk / PreAcceptOk stamps except the leader's own PreAcceptOk, which is "before everything" (:716-724)
+__device__ __forceinline__ int32_t ep_lead_word(const EpGeometry& g, const int32_t* r, int w) {
+  if (w < L_ADEPS)
+    return w == L_KIND ? LK_PREACCEPTING : w == L_VALUE ? r[4] : w == L_BORD ? r[2] : w == L_BREP ? r[3]
+         : w == L_FLAGS ? (r[6] ? LF_AVOID : 0) : 0;
+  if (w < L_ASTAMP) return 0;
+  if (w < L_RSTAMP) return (int32_t)kStampEmpty;
+  if (w < L_RESP) return w - L_RSTAMP == g.index ? 0 : (int32_t)kStampEmpty;
+  const int k = (w - L_RESP) / kEpRespWords, j = (w - L_RESP) % kEpRespWords;
+  if (k != g.index) return 0;
+  return j == 0 ? r[5] : (j - 1 < g.n ? r[8 + j - 1] : 0);
+}
+
 // ---- transitionToPreAcceptPhase (:633-729).  in row: {rep, num, b_ord, b_rep, value, seq, avoid, pad, deps[n]}
-__global__ void ep_lead_kernel(EpParams P) {
+// Thread t judges message t of the tile (claim, cmdLog header as two 128-bit loads, cmdLog row written as four
+// 128-bit words); the 384-byte leader rows are then written by whole warps, lane L the 16 bytes at word 4L:
+// one fully coalesced store instruction per row instead of ~40 scalar ones.
+__global__ void __launch_bounds__(kEpTile) ep_lead_kernel(EpParams P) {
   const EpGeometry& g = P.g;
-  const int W = 8 + g.n;
-  int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= P.n_rec) return;
-  const int32_t* r = P.in + (size_t)i * W;
-  long long inst = ep_instance(g, r[0], r[1]);
-  if (inst < 0) { report_error(P.s.st, FPX_ERR_SLOT_RANGE, i); return; }
-  if (ep_claim(P.s, inst, P.tag, i)) return;
-  int32_t* c = P.s.cmd + inst * kEpCmdWords;
-  unsigned long long b = ballot_key(r[2], r[3]);
-  int kind = c[C_KIND];
-  if (kind == EK_COMMITTED) { report_error(P.s.st, FPX_ERR_EPAXOS_STATE, i); return; }   // logger.fatal :663-667
-  if (kind != EK_NONE) {
-    if (b < ballot_key(c[C_BORD], c[C_BREP])) { report_error(P.s.st, FPX_ERR_EPAXOS_STATE, i); return; }  // checkLe
-    if (kind != EK_NOCOMMAND && b < ballot_key(c[C_VBORD], c[C_VBREP])) { report_error(P.s.st, FPX_ERR_EPAXOS_STATE, i); return; }
+  extern __shared__ int32_t s_ep[];
+  __shared__ long long s_inst[kEpTile];
+  const int W = 8 + g.n, Wp = W | 1;
+  const int tid = threadIdx.x;
+  const long long tile0 = (long long)blockIdx.x * kEpTile;
+  const int rows = (int)min((long long)kEpTile, P.n_rec - tile0);
+  ep_stage_rows(P.in, tile0, rows, W, Wp, s_ep);
+  __syncthreads();
+  long long armed = -1;
+  if (tid < rows) {
+    const int32_t* r = s_ep + tid * Wp;
+    const int i = (int)tile0 + tid;
+    const long long inst = ep_instance(g, r[0], r[1]);
+    if (inst < 0) {
+      report_error(P.s.st, FPX_ERR_SLOT_RANGE, i);
+    } else if (!ep_claim(P.s, inst, P.tag, i)) {
+      int4* c4 = (int4*)(P.s.cmd + inst * kEpCmdWords);
+      const int4 h0 = __ldcg(c4), h1 = __ldcg(c4 + 1);          // {kind, value, bord, brep} {vbord, vbrep, seq, pad}
+      const unsigned long long b = ballot_key(r[2], r[3]);
+      const int kind = h0.x;
+      bool bad = kind == EK_COMMITTED;                           // logger.fatal :663-667
+      if (!bad && kind != EK_NONE) {
+        bad = b < ballot_key(h0.z, h0.w);                        // checkLe
+        if (!bad && kind != EK_NOCOMMAND) bad = b < ballot_key(h1.x, h1.y);
+      }
+      if (bad) {
+        report_error(P.s.st, FPX_ERR_EPAXOS_STATE, i);
+      } else {
+        int dd[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) dd[k] = k < g.n ? r[8 + k] : 0;           // :684-693
+        __stcg(c4, make_int4(EK_PREACCEPTED, r[4], r[2], r[3]));
+        __stcg(c4 + 1, make_int4(r[2], r[3], r[5], 0));
+        __stcg(c4 + 2, make_int4(dd[0], dd[1], dd[2], dd[3]));
+        __stcg(c4 + 3, make_int4(dd[4], dd[5], dd[6], dd[7]));
+        armed = inst;
+      }
+    }
   }
-  c[C_KIND] = EK_PREACCEPTED; c[C_VALUE] = r[4]; c[C_BORD] = r[2]; c[C_BREP] = r[3];
-  c[C_VBORD] = r[2]; c[C_VBREP] = r[3]; c[C_SEQ] = r[5];
-  for (int k = 0; k < g.n; ++k) c[C_DEPS + k] = r[8 + k];                       // :684-693
-  int32_t* l = P.s.lead + inst * kEpLeadWords;
-  l[L_KIND] = LK_PREACCEPTING; l[L_VALUE] = r[4]; l[L_BORD] = r[2]; l[L_BREP] = r[3];
-  l[L_FLAGS] = r[6] ? LF_AVOID : 0;
-  for (int k = 0; k < kEpMaxN; ++k) {
-    l[L_ASTAMP + k] = (int32_t)kStampEmpty;
-    l[L_RESP + k * kEpRespWords] = (int32_t)kStampEmpty;
+  s_inst[tid] = armed;
+  __syncthreads();
+  const int lane = tid & 31, warp = tid >> 5;
+  for (int m = 0; m < 32; ++m) {
+    const int t = warp * 32 + m;
+    const long long inst = s_inst[t];
+    if (inst < 0 || lane >= kEpLeadWords / 4) continue;
+    const int32_t* r = s_ep + t * Wp;
+    const int w = 4 * lane;
+    __stcg((int4*)(P.s.lead + inst * kEpLeadWords) + lane,
+           make_int4(ep_lead_word(g, r, w), ep_lead_word(g, r, w + 1), ep_lead_word(g, r, w + 2), ep_lead_word(g, r, w + 3)));
   }
-  int32_t* self = l + L_RESP + g.index * kEpRespWords;                          // :716-724 own PreAcceptOk
-  self[0] = 0;
-  self[1] = r[5];
-  for (int k = 0; k < g.n; ++k) self[2 + k] = r[8 + k];
 }
 
 // ---- handlePreAccept (:1159-1289) / handleAccept (:1421-1512)
@@ -137,7 +198,6 @@ __global__ void ep_lead_kernel(EpParams P) {
 // memory with coalesced 128-bit loads (row stride padded to an odd word count: conflict-free reads), the
 // replies are staged the same way and leave with coalesced stores; the cmdLog row is one 64-byte line
 // read and written as four 128-bit words; largestBallot is reduced per CTA before it touches memory.
-constexpr int kEpTile = 256;
 __host__ __device__ __forceinline__ int ep_in_words(const EpGeometry& g, bool accept) { return accept ? 6 + g.n : 6 + 2 * g.n; }
 
 template <bool kAccept>
@@ -326,154 +386,220 @@ __global__ void ep_renormalize_kernel(EpState s, size_t n_inst) {
   if (l[L_KIND] == LK_NONE) return;
   for (int k = 0; k < kEpMaxN; ++k) {
     if ((uint32_t)l[L_ASTAMP + k] != kStampEmpty) l[L_ASTAMP + k] = 0;
-    if ((uint32_t)l[L_RESP + k * kEpRespWords] != kStampEmpty) l[L_RESP + k * kEpRespWords] = 0;
+    if ((uint32_t)l[L_RSTAMP + k] != kStampEmpty) l[L_RSTAMP + k] = 0;
   }
 }
 
 // ---- handlePreAcceptOk (:1291-1419) / handleAcceptOk (:1514-1565), stamp pass
 // in row preacceptok: {rep, num, b_ord, b_rep, from, seq, deps[n]};  acceptok: {rep, num, b_ord, b_rep, from, pad}
-// scratch out row word 0: 0 inactive, 1 first delivery of its replica, 2 replacing response
-template <bool kAccept>
-__global__ void ep_response_stamp_kernel(EpParams P) {
-  const EpGeometry& g = P.g;
-  const int W = kAccept ? 6 : 6 + g.n;
-  const int WO = 2 + g.n;
-  int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= P.n_rec) return;
-  const int32_t* r = P.in + (size_t)i * W;
-  int32_t* o = P.out + (size_t)i * WO;
-  o[0] = 0; o[1] = 0;
-  for (int k = 0; k < g.n; ++k) o[2 + k] = 0;
-  long long inst = ep_instance(g, r[0], r[1]);
-  if (inst < 0 || (uint32_t)r[4] >= (uint32_t)g.n) { report_error(P.s.st, FPX_ERR_SLOT_RANGE, i); return; }
-  int32_t* l = P.s.lead + inst * kEpLeadWords;
-  if (l[L_KIND] != (kAccept ? LK_ACCEPTING : LK_PREACCEPTING)) return;          // :1295-1315 / :1518-1535
-  if (ballot_key(r[2], r[3]) != ballot_key(l[L_BORD], l[L_BREP])) return;       // :1325-1335 / :1543-1552
-  ep_count(P.s, inst, P.tag);
-  const uint32_t seq = P.seq_base + (uint32_t)i;
-  if (kAccept) {
-    uint32_t old = atomicMin((uint32_t*)&l[L_ASTAMP + r[4]], seq);
-    if (old == kStampEmpty) o[0] = 1;
-    else if (old >= P.seq_base) report_error(P.s.st, FPX_ERR_BATCH_ORDER, max((uint32_t)i, old - P.seq_base));
-    return;
-  }
-  int32_t* resp = l + L_RESP + r[4] * kEpRespWords;
-  uint32_t old = atomicMin((uint32_t*)&resp[0], seq);
-  if (old == kStampEmpty) {                                     // responses(replicaIndex) = ok (:1340), new key
-    resp[1] = r[5];
-    for (int k = 0; k < g.n; ++k) resp[2 + k] = r[6 + k];
-    o[0] = 1;
-  } else if (old >= P.seq_base) {                               // two responses of one replica in one batch (E2)
-    report_error(P.s.st, FPX_ERR_BATCH_ORDER, max((uint32_t)i, old - P.seq_base));
-  } else {
-    bool same = resp[1] == r[5];
-    for (int k = 0; k < g.n; ++k) same = same && resp[2 + k] == r[6 + k];
-    if (!same) o[0] = 2;                                        // replaces content; judged in the decide pass
-  }
+// mode[i] (scratch): 0 inactive, 1 first delivery of its replica, 2 replacing response.
+// The tile's input rows are staged coalesced; per message: one 128-bit load of the leader header, the batch
+// count, one atomicMin on the replica's stamp word, and the answer {seq, deps} as two 128-bit words (one sector).
+__device__ __forceinline__ void ep_load8(const int32_t* p, int (&v)[8]) {
+  const int4 a = __ldcg((const int4*)p), b = __ldcg((const int4*)p + 1);
+  v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+}
+__device__ __forceinline__ void ep_store8(int32_t* p, const int (&v)[8]) {
+  __stcg((int4*)p, make_int4(v[0], v[1], v[2], v[3]));
+  __stcg((int4*)p + 1, make_int4(v[4], v[5], v[6], v[7]));
+}
+// the answer {seq, deps[n], 0...} carried by PreAcceptOk row r
+__device__ __forceinline__ void ep_answer_of(const EpGeometry& g, const int32_t* r, int (&v)[8]) {
+  v[0] = r[5];
+#pragma unroll
+  for (int k = 0; k < 7; ++k) v[1 + k] = k < g.n ? r[6 + k] : 0;
 }
 
-// decide pass: events at the first crossing of the quorum thresholds
 template <bool kAccept>
-__global__ void ep_response_decide_kernel(EpParams P) {
+__global__ void __launch_bounds__(kEpTile) ep_response_stamp_kernel(EpParams P, int32_t* mode) {
   const EpGeometry& g = P.g;
-  const int W = kAccept ? 6 : 6 + g.n;
-  const int WO = 2 + g.n;
-  int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= P.n_rec) return;
-  const int32_t* r = P.in + (size_t)i * W;
-  int32_t* o = P.out + (size_t)i * WO;
-  const int mode = o[0];
-  o[0] = EV_NONE;
-  if (mode == 0) return;
-  long long inst = ep_instance(g, r[0], r[1]);
-  int32_t* l = P.s.lead + inst * kEpLeadWords;
-  int32_t* c = P.s.cmd + inst * kEpCmdWords;
-  const uint32_t seq = P.seq_base + (uint32_t)i;
-  if (mode == 2) {
-    // a replacing response must be alone for its instance in the batch (E2)
-    unsigned long long cnt = P.s.count[inst];
-    if ((uint32_t)(cnt >> 32) == P.tag && (uint32_t)cnt > 1) { report_error(P.s.st, FPX_ERR_BATCH_ORDER, i); return; }
-    int32_t* resp = l + L_RESP + r[4] * kEpRespWords;
-    resp[1] = r[5];
-    for (int k = 0; k < g.n; ++k) resp[2 + k] = r[6 + k];
-    return;                                                     // size unchanged: no threshold can be crossed
-  }
-  int before = 0;
-  for (int k = 0; k < g.n; ++k) {
-    uint32_t st = (uint32_t)(kAccept ? l[L_ASTAMP + k] : l[L_RESP + k * kEpRespWords]);
-    if (st < seq) ++before;
-  }
-  const int after = before + 1;
-  if (kAccept) {
-    if (!(before < g.slow_quorum && after >= g.slow_quorum)) return;           // :1558-1560
-    o[0] = EV_COMMIT; o[1] = l[L_ASEQ];
-    c[C_KIND] = EK_COMMITTED; c[C_VALUE] = l[L_VALUE]; c[C_SEQ] = l[L_ASEQ];    // commit (:815-829)
-    for (int k = 0; k < g.n; ++k) { o[2 + k] = l[L_ADEPS + k]; c[C_DEPS + k] = l[L_ADEPS + k]; }
-    l[L_KIND] = LK_NONE;
-    return;
-  }
-  const bool avoid = l[L_FLAGS] & LF_AVOID;
-  if (after < g.slow_quorum) return;                                           // :1345-1347
-  bool slow = false, decide = false;
-  if (!avoid && before < g.slow_quorum && after >= g.slow_quorum && g.slow_quorum < g.fast_quorum) {
-    atomicOr((int*)&l[L_FLAGS], LF_TIMER);                                     // :1353-1364
-    o[0] = EV_TIMER;
-    return;
-  }
-  if (avoid) { if (before < g.slow_quorum) slow = true; else return; }         // :1369-1372
-  else if (after >= g.fast_quorum && before < g.fast_quorum) decide = true;    // :1376
-  else return;
-  int fseq = 0, fdeps[kEpMaxN];
-  bool fast = false;
-  if (decide) {
-    // popularItems over the non-leader (seq, deps) pairs, threshold fastQuorumSize - 1 (:1382-1396)
-    for (int a = 0; a < g.n && !fast; ++a) {
-      if (a == g.index) continue;
-      const int32_t* ra = l + L_RESP + a * kEpRespWords;
-      if ((uint32_t)ra[0] > seq) continue;
-      int cnt = 0;
-      for (int b2 = 0; b2 < g.n; ++b2) {
-        if (b2 == g.index) continue;
-        const int32_t* rb = l + L_RESP + b2 * kEpRespWords;
-        if ((uint32_t)rb[0] > seq) continue;
-        bool eq = ra[1] == rb[1];
-        for (int k = 0; k < g.n; ++k) eq = eq && ra[2 + k] == rb[2 + k];
-        cnt += eq;
-      }
-      if (cnt >= g.fast_quorum - 1) {
-        fast = true; fseq = ra[1];
-        for (int k = 0; k < g.n; ++k) fdeps[k] = ra[2 + k];
+  extern __shared__ int32_t s_ep[];
+  const int W = kAccept ? 6 : 6 + g.n, Wp = W | 1;
+  const int tid = threadIdx.x;
+  const long long tile0 = (long long)blockIdx.x * kEpTile;
+  const int rows = (int)min((long long)kEpTile, P.n_rec - tile0);
+  ep_stage_rows(P.in, tile0, rows, W, Wp, s_ep);
+  __syncthreads();
+  if (tid >= rows) return;
+  const int i = (int)tile0 + tid;
+  const int32_t* r = s_ep + tid * Wp;
+  int md = 0;
+  const long long inst = ep_instance(g, r[0], r[1]);
+  if (inst < 0 || (uint32_t)r[4] >= (uint32_t)g.n) {
+    report_error(P.s.st, FPX_ERR_SLOT_RANGE, i);
+  } else {
+    int32_t* l = P.s.lead + inst * kEpLeadWords;
+    const int4 h = __ldcg((const int4*)l);                                      // {kind, value, bord, brep}
+    if (h.x == (kAccept ? LK_ACCEPTING : LK_PREACCEPTING) &&                    // :1295-1315 / :1518-1535
+        ballot_key(r[2], r[3]) == ballot_key(h.z, h.w)) {                       // :1325-1335 / :1543-1552
+      ep_count(P.s, inst, P.tag);
+      const uint32_t seq = P.seq_base + (uint32_t)i;
+      const uint32_t old = atomicMin((uint32_t*)&l[(kAccept ? L_ASTAMP : L_RSTAMP) + r[4]], seq);
+      if (old == kStampEmpty) {                                 // responses(replicaIndex) = ok (:1340), new key
+        md = 1;
+        if (!kAccept) {
+          int v[8];
+          ep_answer_of(g, r, v);
+          ep_store8(l + L_RESP + r[4] * kEpRespWords, v);
+        }
+      } else if (old >= P.seq_base) {                           // two responses of one replica in one batch (E2)
+        report_error(P.s.st, FPX_ERR_BATCH_ORDER, max((uint32_t)i, old - P.seq_base));
+      } else if (!kAccept) {
+        int v[8], have[8];
+        ep_answer_of(g, r, v);
+        ep_load8(l + L_RESP + r[4] * kEpRespWords, have);
+        bool same = true;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) same = same && (k > g.n || have[k] == v[k]);
+        if (!same) md = 2;                                      // replaces content; judged in the decide pass
       }
     }
-    if (!fast) slow = true;
   }
-  if (fast) {                                                                  // :1401-1410 commit
-    o[0] = EV_FAST_COMMIT; o[1] = fseq;
-    c[C_KIND] = EK_COMMITTED; c[C_VALUE] = l[L_VALUE]; c[C_SEQ] = fseq;
-    for (int k = 0; k < g.n; ++k) { o[2 + k] = fdeps[k]; c[C_DEPS + k] = fdeps[k]; }
-    l[L_KIND] = LK_NONE;
-    return;
-  }
-  if (slow) {                                                                  // preAcceptingSlowPath :796-813
-    int sseq = INT_MIN;
-    int sdeps[kEpMaxN];
-    for (int k = 0; k < g.n; ++k) sdeps[k] = 0;
-    for (int a = 0; a < g.n; ++a) {
-      const int32_t* ra = l + L_RESP + a * kEpRespWords;
-      if ((uint32_t)ra[0] > seq) continue;
-      sseq = max(sseq, ra[1]);
-      for (int k = 0; k < g.n; ++k) sdeps[k] = max(sdeps[k], ra[2 + k]);       // dependencies.addAll (:804-807)
+  mode[i] = md;
+}
+
+// decide pass: events at the first crossing of the quorum thresholds.  out row: {event, seq, deps[n]}, staged
+// in shared memory and stored coalesced.
+template <bool kAccept>
+__global__ void __launch_bounds__(kEpTile) ep_response_decide_kernel(EpParams P, const int32_t* mode) {
+  const EpGeometry& g = P.g;
+  extern __shared__ int32_t s_ep[];
+  const int W = kAccept ? 6 : 6 + g.n, Wp = W | 1;
+  const int WO = 2 + g.n;                                       // odd: conflict-free as it is
+  int32_t* s_out = s_ep + kEpTile * Wp;
+  const int tid = threadIdx.x;
+  const long long tile0 = (long long)blockIdx.x * kEpTile;
+  const int rows = (int)min((long long)kEpTile, P.n_rec - tile0);
+  ep_stage_rows(P.in, tile0, rows, W, Wp, s_ep);
+  __syncthreads();
+  if (tid < rows) {
+    const int i = (int)tile0 + tid;
+    const int32_t* r = s_ep + tid * Wp;
+    int32_t* o = s_out + tid * WO;
+    for (int k = 0; k < WO; ++k) o[k] = 0;                      // o[0] = EV_NONE
+    const int md = __ldcg(mode + i);
+    if (md != 0) {
+      const long long inst = ep_instance(g, r[0], r[1]);
+      int32_t* l = P.s.lead + inst * kEpLeadWords;
+      int32_t* c = P.s.cmd + inst * kEpCmdWords;
+      const uint32_t seq = P.seq_base + (uint32_t)i;
+      if (md == 2) {
+        // a replacing response must be alone for its instance in the batch (E2); size unchanged: no
+        // threshold can be crossed
+        const unsigned long long cnt = __ldcg(&P.s.count[inst]);
+        if ((uint32_t)(cnt >> 32) == P.tag && (uint32_t)cnt > 1) {
+          report_error(P.s.st, FPX_ERR_BATCH_ORDER, i);
+        } else {
+          int v[8];
+          ep_answer_of(g, r, v);
+          ep_store8(l + L_RESP + r[4] * kEpRespWords, v);
+        }
+      } else {
+        int st[8];
+        ep_load8(l + (kAccept ? L_ASTAMP : L_RSTAMP), st);
+        int before = 0;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) before += (k < g.n && (uint32_t)st[k] < seq);
+        const int after = before + 1;
+        const int4 h0 = __ldcg((const int4*)l);                 // {kind, value, bord, brep}
+        if (kAccept) {
+          if (before < g.slow_quorum && after >= g.slow_quorum) {                 // :1558-1560
+            int ad[8];
+            ep_load8(l + L_ADEPS, ad);
+            const int aseq = __ldcg(&l[L_ASEQ]);
+            o[0] = EV_COMMIT; o[1] = aseq;
+            #pragma unroll
+            for (int k = 0; k < 7; ++k) if (k < g.n) o[2 + k] = ad[k];
+            c[C_KIND] = EK_COMMITTED; c[C_VALUE] = h0.y; c[C_SEQ] = aseq;        // commit (:815-829)
+#pragma unroll
+            for (int k = 0; k < 8; ++k) if (k >= g.n) ad[k] = 0;
+            ep_store8(c + C_DEPS, ad);
+            l[L_KIND] = LK_NONE;
+          }
+        } else if (after >= g.slow_quorum) {                                      // :1345-1347
+          const bool avoid = __ldcg(&l[L_FLAGS]) & LF_AVOID;
+          bool slow = false, decide = false;
+          if (!avoid && before < g.slow_quorum && g.slow_quorum < g.fast_quorum) {
+            atomicOr((int*)&l[L_FLAGS], LF_TIMER);                               // :1353-1364
+            o[0] = EV_TIMER;
+          } else if (avoid) {
+            slow = before < g.slow_quorum;                                       // :1369-1372
+          } else {
+            decide = after >= g.fast_quorum && before < g.fast_quorum;           // :1376
+          }
+          if (slow || decide) {
+            // the answers delivered up to this one: {seq, deps} of every replica whose stamp is <= seq
+            int ans[kEpMaxN - 1][8];
+            bool in[kEpMaxN - 1];
+#pragma unroll
+            for (int a = 0; a < kEpMaxN - 1; ++a) {
+              in[a] = a < g.n && (uint32_t)st[a] <= seq;
+              if (in[a]) ep_load8(l + L_RESP + a * kEpRespWords, ans[a]);
+            }
+            int fseq = 0, fdeps[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+            bool fast = false;
+            if (decide) {
+              // popularItems over the non-leader (seq, deps) pairs, threshold fastQuorumSize - 1 (:1382-1396)
+#pragma unroll
+              for (int a = 0; a < kEpMaxN - 1; ++a) {
+                if (fast || !in[a] || a == g.index) continue;
+                int cnt = 0;
+#pragma unroll
+                for (int b2 = 0; b2 < kEpMaxN - 1; ++b2) {
+                  if (!in[b2] || b2 == g.index) continue;
+                  bool eq = true;
+#pragma unroll
+                  for (int k = 0; k < 8; ++k) eq = eq && (k > g.n || ans[a][k] == ans[b2][k]);
+                  cnt += eq;
+                }
+                if (cnt >= g.fast_quorum - 1) {
+                  fast = true; fseq = ans[a][0];
+#pragma unroll
+                  for (int k = 0; k < 7; ++k) fdeps[k] = k < g.n ? ans[a][1 + k] : 0;
+                }
+              }
+              if (!fast) slow = true;
+            }
+            if (fast) {                                                          // :1401-1410 commit
+              o[0] = EV_FAST_COMMIT; o[1] = fseq;
+              #pragma unroll
+              for (int k = 0; k < 7; ++k) if (k < g.n) o[2 + k] = fdeps[k];
+              c[C_KIND] = EK_COMMITTED; c[C_VALUE] = h0.y; c[C_SEQ] = fseq;
+              ep_store8(c + C_DEPS, fdeps);
+              l[L_KIND] = LK_NONE;
+            } else if (slow) {                                                   // preAcceptingSlowPath :796-813
+              int sseq = INT_MIN;
+              int sdeps[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+#pragma unroll
+              for (int a = 0; a < kEpMaxN - 1; ++a) {
+                if (!in[a]) continue;
+                sseq = max(sseq, ans[a][0]);
+#pragma unroll
+                for (int k = 0; k < 7; ++k) if (k < g.n) sdeps[k] = max(sdeps[k], ans[a][1 + k]);   // dependencies.addAll (:804-807)
+              }
+              o[0] = EV_SLOW_ACCEPT; o[1] = sseq;
+              #pragma unroll
+              for (int k = 0; k < 7; ++k) if (k < g.n) o[2 + k] = sdeps[k];
+              // transitionToAcceptPhase (:732-793)
+              __stcg((int4*)c, make_int4(EK_ACCEPTED, h0.y, h0.z, h0.w));
+              __stcg((int4*)c + 1, make_int4(h0.z, h0.w, sseq, 0));
+              ep_store8(c + C_DEPS, sdeps);
+              l[L_ASEQ] = sseq;
+              ep_store8(l + L_ADEPS, sdeps);
+              int as[8];
+#pragma unroll
+              for (int k = 0; k < 8; ++k) as[k] = k == g.index ? 0 : (int)kStampEmpty;   // own AcceptOk (:781-789)
+              ep_store8(l + L_ASTAMP, as);
+              l[L_KIND] = LK_ACCEPTING;
+            }
+          }
+        }
+      }
     }
-    o[0] = EV_SLOW_ACCEPT; o[1] = sseq;
-    // transitionToAcceptPhase (:732-793)
-    c[C_KIND] = EK_ACCEPTED; c[C_VALUE] = l[L_VALUE]; c[C_BORD] = l[L_BORD]; c[C_BREP] = l[L_BREP];
-    c[C_VBORD] = l[L_BORD]; c[C_VBREP] = l[L_BREP]; c[C_SEQ] = sseq;
-    l[L_ASEQ] = sseq;
-    for (int k = 0; k < g.n; ++k) { o[2 + k] = sdeps[k]; c[C_DEPS + k] = sdeps[k]; l[L_ADEPS + k] = sdeps[k]; }
-    for (int k = 0; k < kEpMaxN; ++k) l[L_ASTAMP + k] = (int32_t)kStampEmpty;
-    l[L_ASTAMP + g.index] = 0;                                                 // own AcceptOk (:781-789)
-    l[L_KIND] = LK_ACCEPTING;
   }
+  __syncthreads();
+  int32_t* dst = P.out + tile0 * WO;
+  for (int e = tid; e < rows * WO; e += kEpTile) __stcs(dst + e, s_out[e]);
 }
 
 // ---- dense dep-set union (all `values` empty): elementwise max over the R sets of a group.

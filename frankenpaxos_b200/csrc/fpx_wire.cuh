@@ -112,6 +112,9 @@ __device__ __forceinline__ int wire_member(int inbound, int which) {
   return which == 2 ? kWmP2a : which == 3 ? kWmRange3 : kWmOpaque;
 }
 
+// members of the inbound's oneof, numbered 1..count (MultiPaxos.proto:541-561, Mencius.proto:339-361)
+__device__ __forceinline__ int wire_member_count(int inbound) { return inbound == 0 ? 2 : inbound == 1 ? 4 : inbound == 2 ? 5 : 3; }
+
 // Reader positions in, reader positions out (*value_pos: out->z is a position the caller rebases).
 template <bool kShared>
 __device__ __forceinline__ bool wire_decode_one(int inbound, int lgroups, int agroups, WireReader<kShared> r, int* kind,
@@ -125,8 +128,10 @@ __device__ __forceinline__ bool wire_decode_one(int inbound, int lgroups, int ag
     if (wt == 2) {
       const uint32_t n = r.small();
       if (!r.ok || r.end - r.p < n) return false;
-      which = (int)(tag >> 3); blo = r.p; bhi = r.p + n;       // oneof: last member wins
-      r.p = bhi;
+      // oneof: the last member wins; a field number the message does not declare is an unknown field: skipped,
+      // the earlier member stays (scalapb parseFrom)
+      if ((tag >> 3) <= (uint32_t)wire_member_count(inbound)) { which = (int)(tag >> 3); blo = r.p; bhi = r.p + n; }
+      r.p += n;
     } else if (!r.skip(wt)) {
       return false;
     }

@@ -385,6 +385,11 @@ class Engine:
         self._check(self._L.fpx_step_dev(self.h, d_arm, n_arm, d_p2a, n_p2a, d_out_p2b, d_out_nack, d_p2b, n_p2b,
                                          d_out_chosen, d_wm, ring_slot))
 
+    def vm_step_dev(self, d_req, n_req, d_p2a, n_p2a, d_reply, d_p2b, n_p2b, d_out_chosen, d_wm):
+        """One step of the co-located vanilla Mencius servers in one C call: client requests, Phase2a batch,
+        then the tally with the log put and the watermark fused into it."""
+        self._check(self._L.fpx_vm_step_dev(self.h, d_req, n_req, d_p2a, n_p2a, d_reply, d_p2b, n_p2b, d_out_chosen, d_wm))
+
     def step_submit(self, arm, n_arm, p2a, n_p2a, p2b, n_p2b, out_p2b, out_nack, out_chosen):
         """Asynchronous step from HOST pointers (ints; pinned memory recommended), at most two in flight;
         arm = None arms from the Phase2a batch itself.  Pair with step_wait()."""

@@ -541,6 +541,14 @@ int fpx_sync(fpx_engine* e, fpx_sync_result* out);
 int fpx_step_dev(fpx_engine* e, const fpx_p2a* d_arm, int32_t n_arm, const fpx_p2a* d_p2a, int32_t n_p2a,
                  fpx_p2b* d_out_p2b, fpx_nack* d_out_nack, const fpx_p2b* d_p2b, int32_t n_p2b, fpx_chosen* d_out_chosen,
                  int32_t* d_watermark, int32_t ring_slot);
+/* The vanilla Mencius form (protocol FPX_VANILLA_MENCIUS; S/vanillamencius/Server.scala): one step of the n
+ * co-located servers on device-resident buffers, with the same results as fpx_vm_client_request_dev (:767-829),
+ * fpx_vm_phase2a_dev (:1001-1082), fpx_proxyleader_phase2b_dev (:1084-1142), fpx_replica_chosen_last_dev and
+ * fpx_chosen_watermark_dev in that order -- in three launches: the client requests at the owners (arm + own
+ * vote), the Phase2a batch at the other servers (dense replies), and the tally with the servers' shared log
+ * (executeLog's prefix, :641-690) and the watermark (+ the exchange store) riding in the same kernel. */
+int fpx_vm_step_dev(fpx_engine* e, const fpx_p2a* d_req, int32_t n_req, const fpx_p2a* d_p2a, int32_t n_p2a,
+                    fpx_p2b* d_reply, const fpx_p2b* d_p2b, int32_t n_p2b, fpx_chosen* d_out_chosen, int32_t* d_watermark);
 int fpx_step_kernel_ms(fpx_engine* e, int32_t ring_slot, float* acceptor_ms, float* tally_ms);
 int fpx_step_arm_ms(fpx_engine* e, int32_t ring_slot, float* arm_ms);   /* the arm kernel of the same step */
 

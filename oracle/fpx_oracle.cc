@@ -1179,6 +1179,8 @@ inline MemberKind member_kind(int inbound, int which) {
     default: return kOpaque;
   }
 }
+// members of the inbound's oneof, numbered 1..count (MultiPaxos.proto:541-561, Mencius.proto:339-361)
+inline int member_count(int inbound) { return inbound == 0 ? 2 : inbound == 1 ? 4 : inbound == 2 ? 5 : inbound == 3 ? 3 : 0; }
 // lgroups / agroups: the mencius geometry, only used to turn Phase2bNoopRange's (acceptor_group_index,
 // acceptor_index) into the engine's dst = (leader_group * agroups + acceptor_group) << 16 | acceptor
 inline int decode_one(int inbound, const uint8_t* base, int64_t lo, int64_t hi, int lgroups, int agroups, int32_t* kind,
@@ -1192,7 +1194,9 @@ inline int decode_one(int inbound, const uint8_t* base, int64_t lo, int64_t hi, 
     if (wt == 2) {
       uint64_t n = r.varint();
       if (!r.ok || (uint64_t)(r.end - r.p) < n) return kWireError;
-      which = (int)(tag >> 3); blo = r.p; bhi = r.p + n;   // a oneof: the last member on the wire wins
+      // a oneof: the last member on the wire wins; a field number the message does not declare is an unknown
+      // field and is skipped (the earlier member stays)
+      if ((tag >> 3) <= (uint64_t)member_count(inbound)) { which = (int)(tag >> 3); blo = r.p; bhi = r.p + n; }
       r.p += n;
     } else if (!r.skip(wt)) {
       return kWireError;

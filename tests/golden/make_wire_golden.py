@@ -207,6 +207,9 @@ def main():
         "oneof set twice: last member wins": good + cls("ProxyLeaderInbound")(phase2a=cls("Phase2a")(
             slot=5, round=6, command_batch_or_noop=payload(g, -1, 0))).SerializeToString(),
         "empty message": b"",
+        "unknown length-delimited field after the member: the member stays": good + bytes([0x3a, 3]) + b"abc",
+        "unknown length-delimited field before the member": bytes([0x3a, 3]) + b"abc" + good,
+        "only an unknown length-delimited field": bytes([0x3a, 3]) + b"abc",
     }
     for name, raw in odd.items():
         m = cls("ProxyLeaderInbound")()

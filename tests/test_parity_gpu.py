@@ -810,6 +810,52 @@ def test_full_size_bit_exact_cfg5_vanilla_mencius(tally_path):
     eng.close()
 
 
+def test_vanilla_step_in_one_call_matches_the_separate_calls_and_the_oracle(tally_path):
+    """fpx_vm_step_dev (client requests, Phase2a batch, tally with the log put and the watermark riding in it:
+    three launches) against the five separate device calls on a second engine and against the oracle, over
+    several windows of one log; the second window carries a stale duplicate of every earlier vote."""
+    import torch
+    from frankenpaxos_b200 import VANILLA_MENCIUS
+    cfg, _ = T.config_by_name("cfg5")
+    f, n, W, wins = cfg["f"], cfg["acceptors_per_group"], 1 << 15, 3
+    mk = lambda: Engine(slot_capacity=wins * W, max_batch=2 * (n - 1) * W, protocol=VANILLA_MENCIUS, **cfg)
+    one, sep, ora = mk(), mk(), O.VanillaMencius(f)
+    dev = torch.device("cuda", 0)
+    td = lambda x: torch.from_numpy(x.view(np.int32).reshape(len(x), -1).copy()).to(dev)
+    outs = [[torch.zeros((2 * (n - 1) * W, k), dtype=torch.int32, device=dev) for k in (4, 2)] + [torch.zeros(1, dtype=torch.int32, device=dev)]
+            for _ in range(2)]
+    prev_b = None
+    for w in range(wins):
+        req, p, b = T.vanilla_cfg5(70 + w, f, W, slot_offset=w * W)
+        if prev_b is not None:
+            b = np.concatenate([prev_b[: len(prev_b) // 2], b])     # votes for chosen entries: ignored (:1090-1093)
+        prev_b = b
+        assert ora.client_request(req) == (0, -1)
+        _, _, orep = ora.phase2a(p)
+        st, _, oc = ora.proxyleader_phase2b(b)
+        assert st == 0
+        d_req, d_p, d_b = td(req), td(p), td(b)
+        (r1, c1, w1), (r2, c2, w2) = outs
+        one.vm_step_dev(d_req.data_ptr(), len(req), d_p.data_ptr(), len(p), r1.data_ptr(), d_b.data_ptr(), len(b), c1.data_ptr(), w1.data_ptr())
+        sep.vm_client_request_dev(d_req.data_ptr(), len(req))
+        sep.vm_phase2a_dev(d_p.data_ptr(), len(p), r2.data_ptr())
+        sep.proxyleader_phase2b_dev(d_b.data_ptr(), len(b), c2.data_ptr())
+        sep.replica_chosen_last_dev(c2.data_ptr())
+        sep.chosen_watermark_dev(w2.data_ptr())
+        ra, rb = one.sync(), sep.sync()
+        assert (ra.status, ra.n_chosen, ra.watermark) == (rb.status, rb.n_chosen, rb.watermark) == (0, len(oc), (w + 1) * W)
+        assert int(w1.item()) == int(w2.item()) == (w + 1) * W
+        H.same(r1[: len(p)].cpu().numpy().view(P2B).reshape(-1), orep, f"Phase2a replies, window {w}")
+        H.same(c1[: ra.n_chosen].cpu().numpy().view(CHOSEN).reshape(-1), oc, f"Chosen stream, window {w}")
+        H.same(c2[: rb.n_chosen].cpu().numpy().view(CHOSEN).reshape(-1), oc, f"Chosen stream (separate calls), window {w}")
+    H.same(one.snapshot_log(0, wins * W), sep.snapshot_log(0, wins * W), "log")
+    for a in range(n):
+        x, y = one.snapshot_acceptor(0, a, 0, wins * W), sep.snapshot_acceptor(0, a, 0, wins * W)
+        assert x[:2] == y[:2]
+        H.same(x[2], y[2], f"server {a} voteRound"); H.same(x[3], y[3], f"server {a} voteValue")
+    one.close(); sep.close()
+
+
 def test_bench_shaped_step_on_a_rebased_window_matches_the_oracle(tally_path):
     """What bench.py times: the device-pointer path on window w != 0 of a long log (slots
     w*2^20 .. (w+1)*2^20, earlier windows already committed), compared with the oracle."""
