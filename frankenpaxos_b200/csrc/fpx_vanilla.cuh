@@ -41,27 +41,49 @@ __device__ __forceinline__ bool cas128(unsigned long long* p, unsigned long long
 // times slower than loads that do) and ONE 128-bit compare-and-swap that installs the new cell and the claim
 // together.  The swap can only fail when another message of this call took the cell in between, which is the
 // contract violation itself.  kVmUnroll messages per thread are in flight through every stage.
-__global__ void __launch_bounds__(256) vm_phase2a_kernel(VmParams P) {
+#ifndef FPX_VM_PREFETCH
+#define FPX_VM_PREFETCH 1   // the records of round k+1 are in flight while round k's cell loads and swaps run
+#endif
+__global__ void __launch_bounds__(256, 3) vm_phase2a_kernel(VmParams P) {
   const Geometry& g = P.g;
   const int stride = gridDim.x * blockDim.x;
   const int t0 = blockIdx.x * blockDim.x + threadIdx.x;
+#if FPX_VM_PREFETCH
+  int4 nxt[kVmUnroll];
+#pragma unroll
+  for (int u = 0; u < kVmUnroll; ++u) {
+    const int i = t0 + u * stride;
+    nxt[u] = i < P.n ? ld_stream(P.in + i) : make_int4(0, 0, 0, 0);
+  }
+#endif
   for (int i0 = t0; i0 < P.n; i0 += stride * kVmUnroll) {
-    int4 rec[kVmUnroll], rep[kVmUnroll];
+    int4 rec[kVmUnroll];
+    int rk[kVmUnroll], rw[kVmUnroll];     // reply kind (-1: none) and its last word
     unsigned long long* cellp[kVmUnroll];
-    unsigned long long pre0[kVmUnroll], pre1[kVmUnroll], nw[kVmUnroll];
+    unsigned long long pre0[kVmUnroll], pre1[kVmUnroll];
     bool okc[kVmUnroll];
+#if FPX_VM_PREFETCH
+#pragma unroll
+    for (int u = 0; u < kVmUnroll; ++u) rec[u] = nxt[u];
+#pragma unroll
+    for (int u = 0; u < kVmUnroll; ++u) {
+      const long long i = (long long)i0 + (long long)stride * kVmUnroll + (long long)u * stride;
+      nxt[u] = i < P.n ? ld_stream(P.in + i) : make_int4(0, 0, 0, 0);
+    }
+#else
 #pragma unroll
     for (int u = 0; u < kVmUnroll; ++u) {
       const int i = i0 + u * stride;
       rec[u] = i < P.n ? ld_stream(P.in + i) : make_int4(0, 0, 0, 0);
     }
+#endif
 #pragma unroll
     for (int u = 0; u < kVmUnroll; ++u) {
       const int i = i0 + u * stride;
       cellp[u] = nullptr;
+      rk[u] = -1; rw[u] = 0;
       if (i >= P.n) continue;
       const int server = rec[u].w & 0xffff;
-      rep[u] = make_int4(-1, server, rec[u].x, 0);
       const int local = local_slot(g, rec[u].x);
       if (local < 0) { report_error(P.st, FPX_ERR_SLOT_RANGE, i); continue; }
       if ((rec[u].w >> 16) != 0 || server >= g.per_group) { report_error(P.st, FPX_ERR_BAD_ACCEPTOR, i); continue; }
@@ -76,17 +98,17 @@ __global__ void __launch_bounds__(256) vm_phase2a_kernel(VmParams P) {
       const int i = i0 + u * stride;
       const unsigned long long old = pre0[u];
       const unsigned long long mine = ((unsigned long long)(uint32_t)(rec[u].y + 1) << 32) | (uint32_t)rec[u].z;
-      nw[u] = old;
+      unsigned long long nw = old;
       if (old & kCellChosen) {
-        rep[u].x = 2; rep[u].w = (int)(uint32_t)old;                     // Chosen(slot, chosen.value) (:1018-1027)
+        rk[u] = 2; rw[u] = (int)(uint32_t)old;                           // Chosen(slot, chosen.value) (:1018-1027)
       } else if ((uint32_t)(old >> 32) > (uint32_t)(mine >> 32)) {
-        rep[u].x = 1; rep[u].w = (int)(uint32_t)(old >> 32) - 1;         // Phase2Nack(slot, round) (:1044-1051)
+        rk[u] = 1; rw[u] = (int)(uint32_t)(old >> 32) - 1;               // Phase2Nack(slot, round) (:1044-1051)
       } else {
-        nw[u] = mine;                                                    // log.put(slot, PendingEntry(round, round, value)) (:1054-1058)
-        rep[u].x = 0; rep[u].w = rec[u].y;                               // Phase2b(serverIndex, slot, round) (:1077-1081)
+        nw = mine;                                                       // log.put(slot, PendingEntry(round, round, value)) (:1054-1058)
+        rk[u] = 0; rw[u] = rec[u].y;                                     // Phase2b(serverIndex, slot, round) (:1077-1081)
       }
       if ((uint32_t)(pre1[u] >> 32) != ~P.tag)                           // nobody of this call has the cell yet
-        okc[u] = cas128(cellp[u], pre0[u], pre1[u], nw[u], ((unsigned long long)(~P.tag) << 32) | (uint32_t)i);
+        okc[u] = cas128(cellp[u], pre0[u], pre1[u], nw, ((unsigned long long)(~P.tag) << 32) | (uint32_t)i);
     }
 #pragma unroll
     for (int u = 0; u < kVmUnroll; ++u) {
@@ -96,9 +118,9 @@ __global__ void __launch_bounds__(256) vm_phase2a_kernel(VmParams P) {
         // a second Phase2a for this cell in one call (pre1 = the claim that beat this one): the engine cannot
         // order the two
         report_error(P.st, FPX_ERR_BATCH_ORDER, max((long long)i, (long long)(uint32_t)pre1[u]));
-        rep[u] = make_int4(-1, rec[u].w & 0xffff, rec[u].x, 0);
+        rk[u] = -1; rw[u] = 0;
       }
-      st_stream(P.out + i, rep[u]);
+      st_stream(P.out + i, make_int4(rk[u], rec[u].w & 0xffff, rec[u].x, rw[u]));
     }
   }
 }

@@ -227,6 +227,26 @@ def test_tally_takes_the_sweep_in_steady_state_and_falls_back_otherwise(tally_pa
     eng.close()
 
 
+@pytest.mark.parametrize("order", ["by_slot", "reversed", "by_acceptor"])
+def test_skewed_delivery_orders(tally_path, order):
+    """Votes delivered in slot order, reversed, or one acceptor after the other (the last acceptor's votes
+    complete every key: all completing votes in the last third of the batch) give the oracle's stream."""
+    cfg, _ = T.config_by_name("cfg2")
+    n_slots = 150000
+    eng, ora = H.make_pair(cfg, n_slots, max_batch=3 * n_slots, overflow_capacity=1 << 10)
+    a, p, b = T.workload(17, cfg, n_slots)
+    H.arm(eng, ora, a)
+    if order == "by_slot":
+        b = b[np.argsort(b["slot"], kind="stable")]
+    elif order == "reversed":
+        b = b[np.argsort(b["slot"], kind="stable")][::-1].copy()
+    else:
+        b = b[np.lexsort((b["slot"], b["acceptor"]))]
+    st, c = H.phase2b(eng, ora, b)
+    assert st == 0 and len(c) == n_slots
+    eng.close()
+
+
 def test_sweep_error_paths_report_the_reference_index(tally_path):
     cfg, _ = T.config_by_name("cfg2")
     n_slots = 4000
