@@ -70,9 +70,9 @@ def parse():
 
 def ncu_traffic(kernel):
     """dram__bytes_read.sum + dram__bytes_write.sum per launch of `kernel`, from the
-    committed ncu --set full capture (profiles/r2_traffic.json); None if absent."""
+    committed ncu --set full capture (profiles/r2b_traffic.json); None if absent."""
     try:
-        with open(os.path.join(ROOT, "profiles", "r2_traffic.json")) as f:
+        with open(os.path.join(ROOT, "profiles", "r2b_traffic.json")) as f:
             k = json.load(f)[kernel]
         return int(k["dram_bytes_read"] + k["dram_bytes_write"])
     except Exception:
@@ -421,9 +421,17 @@ def main():
 
     extra = {}
     if not args.no_extra:
-        extra["cfg5"] = cfg5_extra(torch, dist, dev, rank, N, local_rank)
+        # the extra keys never cost the headline line: a failure is reported in place (every rank runs the same
+        # deterministic code, so they fail or pass together)
+        try:
+            extra["cfg5"] = cfg5_extra(torch, dist, dev, rank, N, local_rank)
+        except Exception as e:   # noqa: BLE001
+            extra["cfg5"] = {"error": f"{type(e).__name__}: {e}"}
         if rank == 0:
-            extra["cfg4"] = cfg4_extra(torch, dev, local_rank)
+            try:
+                extra["cfg4"] = cfg4_extra(torch, dev, local_rank)
+            except Exception as e:   # noqa: BLE001
+                extra["cfg4"] = {"error": f"{type(e).__name__}: {e}"}
 
     cpu = None
     if rank == 0 and N == 1:

@@ -1000,7 +1000,7 @@ static int vm_launch(fpx_engine* e, const void* d_in, int32_t n, fpx_p2b* d_repl
   P.rows = e->rows; P.st = e->st;
   P.tag = e->vm_tag++;
   if (e->vm_tag == 0xffffffffu) e->vm_tag = 1;
-  if (which == 0) vm_phase2a_kernel<<<std::min((n + 256 * kVmUnroll - 1) / (256 * kVmUnroll), e->num_sms * 8), 256, 0, e->stream>>>(P);
+  if (which == 0) vm_phase2a_kernel<<<std::min((n + 256 * kVmUnroll - 1) / (256 * kVmUnroll), e->num_sms * FPX_VM_CTAS_PER_SM), 256, 0, e->stream>>>(P);
   else vm_learn_chosen_kernel<<<(n + 255) / 256, 256, 0, e->stream>>>(P);
   e->launches++;
   CK(e, cudaGetLastError());

@@ -20,7 +20,13 @@ struct VmParams {
   DevStatus* st;
 };
 
-constexpr int kVmUnroll = 4;
+#ifndef FPX_VM_UNROLL
+#define FPX_VM_UNROLL 4
+#endif
+#ifndef FPX_VM_CTAS_PER_SM
+#define FPX_VM_CTAS_PER_SM 8      // CTAs of the grid-stride launch per SM
+#endif
+constexpr int kVmUnroll = FPX_VM_UNROLL;
 
 // 128-bit compare-and-swap (ATOMG.E.CAS.128, sm_90+): {e0, e1} is the expected value on entry and the
 // value found on return

@@ -114,5 +114,10 @@ def cfg5():
             "calls": "vm_client_request (arm + own vote) + vm_phase2a + proxyleader_phase2b"}
 
 
-res = {"cfg3": cfg3(), "cfg5": cfg5(), "method": f"{W} warm-up + {K} timed steps, CUDA events on the engine's stream"}
+only = sys.argv[sys.argv.index("--only") + 1] if "--only" in sys.argv else ""     # (FPX_LIB_OVERRIDE=... --only cfg5: A/B of a tuning variant)
+res = {"method": f"{W} warm-up + {K} timed steps, CUDA events on the engine's stream", "lib": os.environ.get("FPX_LIB_OVERRIDE", "default")}
+if only in ("", "cfg3"):
+    res["cfg3"] = cfg3()
+if only in ("", "cfg5"):
+    res["cfg5"] = cfg5()
 print(json.dumps(res))
