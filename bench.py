@@ -248,6 +248,11 @@ def main():
 
     if not torch.cuda.is_available():
         sys.exit("bench.py: no CUDA device; the product has no CPU path")
+    # stdout carries ONE line, the JSON record: whatever native libraries write to fd 1 meanwhile (NCCL prints its
+    # version there at any NCCL_DEBUG level >= VERSION) goes to stderr; the record is written to the real stdout
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
     N = world
     if args.gpus != N and world == 1 and args.gpus > 1:
         sys.exit("bench.py: launch N>1 with torch.distributed.run (one rank per GPU)")
@@ -474,7 +479,8 @@ def main():
                                              "global_prefix_after_timed_region": global_prefix},
             "extra": extra,
         }
-        print(json.dumps(line), flush=True)
+        sys.stdout.flush()
+        os.write(real_stdout, (json.dumps(line) + "\n").encode())
     if N > 1:
         dist.destroy_process_group()
 

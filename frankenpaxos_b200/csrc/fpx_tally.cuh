@@ -48,8 +48,9 @@
 //   much larger than the batch.  Any violation flips the WHOLE batch to the exact
 //   path, which also produces the reference's error index.  Blind stamping is sound
 //   for the same reason as before: a primary row in normal state has exactly ONE
-//   armed round.  Vanilla Mencius (stale votes are ignored, not fatal) always takes
-//   the exact path with the checked phase A.
+//   armed round.  Vanilla Mencius ignores stale votes instead of failing: its entries are
+//   always proposed in round 0, so round-0 votes are stamped blindly too and the sweep runs
+//   unconditionally; a vote of another round sends the batch through the checked stamping pass.
 #pragma once
 #include "fpx_common.cuh"
 
