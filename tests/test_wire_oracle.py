@@ -207,3 +207,50 @@ def test_oracle_against_the_protobuf_runtime_on_random_messages():
     nacks = [r32() for _ in range(100)]
     out, eoffs = O.wire_encode_nack(np.array([(0, r) for r in nacks], dtype=O.NACK))
     assert bytes(out) == b"".join(G.cls("LeaderInbound")(nack=G.cls("Nack")(round=r)).SerializeToString() for r in nacks)
+
+
+def test_undeclared_top_level_fields_are_skipped_like_the_protobuf_runtime_does():
+    """scalapb's parseFrom (like every proto2 parser) skips a field number the message does not declare and keeps
+    the oneof member it has: random undeclared fields of every skippable wire type, before / after / between, do
+    not change what the oracle decodes -- checked against Google's Python runtime on the same bytes."""
+    pytest.importorskip("google.protobuf")
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("make_wire_golden",
+                                                  os.path.join(os.path.dirname(__file__), "golden", "make_wire_golden.py"))
+    G = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(G)
+    g = np.random.Generator(np.random.PCG64(77))
+
+    def varint(v):
+        out = bytearray()
+        while v >= 0x80:
+            out.append((v & 0x7f) | 0x80); v >>= 7
+        out.append(v)
+        return bytes(out)
+
+    def junk():
+        f = int(g.integers(3, 200))                       # ProxyLeaderInbound declares 1 and 2 only
+        wt = int(g.choice([0, 1, 2, 5]))
+        tag = varint(f << 3 | wt)
+        if wt == 0:
+            return tag + varint(int(g.integers(0, 1 << 40)))
+        if wt == 1:
+            return tag + bytes(g.integers(0, 256, 8, dtype=np.uint8))
+        if wt == 5:
+            return tag + bytes(g.integers(0, 256, 4, dtype=np.uint8))
+        n = int(g.integers(0, 20))
+        return tag + varint(n) + bytes(g.integers(0, 256, n, dtype=np.uint8))
+    msgs, exp = [], []
+    for _ in range(400):
+        f = [int(g.integers(-(1 << 31), 1 << 31) >> int(g.integers(0, 32))) for _ in range(4)]
+        core = G.cls("ProxyLeaderInbound")(phase2b=G.cls("Phase2b")(group_index=f[0], acceptor_index=f[1], slot=f[2],
+                                                                      round=f[3])).SerializeToString()
+        raw = b"".join(junk() for _ in range(int(g.integers(0, 3)))) + core + b"".join(junk() for _ in range(int(g.integers(0, 3))))
+        m = G.cls("ProxyLeaderInbound")()
+        m.ParseFromString(raw)
+        assert m.WhichOneof("request") == "phase2b"
+        msgs.append(raw)
+        exp.append((m.phase2b.group_index, m.phase2b.acceptor_index, m.phase2b.slot, m.phase2b.round))
+    buf, offs = O.pack_messages(msgs)
+    st, err, kind, rec = O.wire_decode_inbound(0, buf, offs)
+    assert st == 0 and (kind == 2).all() and rec.tolist() == exp
