@@ -247,3 +247,237 @@ class MenciusReplica:  # S/mencius/Replica.scala:325-370, 400-486
                 return                                            # leaves the handler
             self.log[slot] = NOOP                                 # :481-483
         self._execute_log()                                       # :487
+
+
+# =========================================================================== vanilla Mencius
+# S/vanillamencius/Server.scala, the normal-case handlers, transcribed from the Scala (not from the C++ oracle).
+# nextSlot / skipSlots / advanceWithSkips / executeLog / revocation / Phase 1 are the control path the drop-in
+# leaves in Scala: a client request names its slot (the caller's nextSlot).
+class VanillaServer:
+    def __init__(self, index, f):
+        self.index, self.f, self.n = index, f, 2 * f + 1
+        self.log = {}        # slot -> ("pending", round, voteRound, value) | ("chosen", value)        (:208-226)
+        self.phase2s = {}    # slot -> {"round", "value", "phase2bs": {serverIndex}}                   (:198-204)
+
+    def leader(self, slot):  # slotSystem = ClassicRoundRobin(numServers) (:252-257)
+        return slot % self.n
+
+    def handle_client_request(self, slot, value):  # :767-829 with nextSlot = slot
+        # logger.check(!phase2s.contains(nextSlot)); logger.check(!log.contains(nextSlot)) (:773-774).  nextSlot
+        # always points at a vacant slot in the reference; the drop-in ignores a repeated request for a slot
+        if slot in self.phase2s or slot in self.log:
+            return
+        self.log[slot] = ("pending", 0, 0, value)                                         # :779
+        self.phase2s[slot] = {"round": 0, "value": value, "phase2bs": {self.index}}        # :818-825
+
+    def handle_phase2a(self, slot, round_, value):  # :1001-1082, state part; returns the reply
+        entry = self.log.get(slot)                                                         # :1016
+        if entry is not None and entry[0] == "chosen":                                     # :1017-1027
+            return ("chosen", slot, entry[1])
+        rnd = -1 if entry is None else entry[1]                                            # :1029-1034
+        if round_ < rnd:                                                                   # :1037-1045
+            return ("nack", slot, rnd)
+        self.log[slot] = ("pending", round_, round_, value)                                # :1048-1052
+        return ("phase2b", slot, round_)                                                   # :1077-1081
+
+    def handle_phase2b(self, server_index, slot, round_):  # :1084-1142; returns Chosen (slot, value) or None
+        entry = self.log.get(slot)
+        if entry is not None and entry[0] == "chosen":                                     # :1090-1093
+            return None
+        phase2 = self.phase2s.get(slot)                                                    # :1099-1106
+        if phase2 is None:
+            return None
+        if round_ < phase2["round"]:                                                       # :1109-1112
+            return None
+        if round_ != phase2["round"]:                                                      # logger.checkEq (:1116)
+            raise Fatal("Phase2b from the future")
+        phase2["phase2bs"].add(server_index)                                               # :1119
+        if len(phase2["phase2bs"]) < self.f + 1:                                           # :1120-1122
+            return None
+        value = phase2["value"]
+        self.choose(slot, value)                                                           # :1138
+        return (slot, value)                                                               # Chosen to the others (:1127-1136)
+
+    def choose(self, slot, value):  # :622-625 (largestChosenPrefixSlots is execution bookkeeping)
+        self.log[slot] = ("chosen", value)
+        self.phase2s.pop(slot, None)
+
+    def handle_chosen(self, slot, value):  # :1170-1197 without advanceWithSkips / executeLog
+        self.choose(slot, value)
+
+
+class VanillaSystem:
+    """n co-located servers driven with the record shapes of fpx_vm_* (include/fpx.h)."""
+
+    def __init__(self, f):
+        self.f, self.n = f, 2 * f + 1
+        self.servers = [VanillaServer(i, f) for i in range(self.n)]
+
+    def client_requests(self, recs):  # (slot, round, value, dst = owner)
+        for slot, _round, value, dst in recs:
+            self.servers[dst].handle_client_request(slot, value)
+
+    def phase2a_batch(self, recs):  # (slot, round, value, dst) -> dense replies (kind, server, slot, round | value)
+        out = []
+        for slot, round_, value, dst in recs:
+            kind, s, x = self.servers[dst].handle_phase2a(slot, round_, value)
+            out.append(({"phase2b": 0, "nack": 1, "chosen": 2}[kind], dst, s, x))
+        return out
+
+    def phase2b_batch(self, recs):  # (group, serverIndex, slot, round) -> (status, index, [(slot, value)])
+        chosen = []
+        for i, (_g, server_index, slot, round_) in enumerate(recs):
+            try:
+                c = self.servers[slot % self.n].handle_phase2b(server_index, slot, round_)   # the coordinator tallies
+            except Fatal:
+                return -4, i, chosen
+            if c is not None:
+                chosen.append(c)
+        return 0, -1, chosen
+
+    def learn_chosen(self, recs):  # (_, server, slot, value)
+        for _g, server, slot, value in recs:
+            self.servers[server].handle_chosen(slot, value)
+
+
+# =========================================================================== EPaxos
+# S/epaxos/Replica.scala, one replica's handlers on the path, transcribed from the Scala.  Dependency sets are
+# dense watermark vectors (InstancePrefixSet with empty `values`, topKDependencies = 1): addAll is the elementwise
+# max (S/compact/IntPrefixSet.scala:317-321).  computeSequenceNumberAndDependencies' answer (the conflict index) is
+# an input.  Ballots are (ordering, replicaIndex) pairs compared as tuples (BallotHelpers.Ordering); the null
+# ballot is (-1, -1).
+NULL_BALLOT = (-1, -1)
+
+
+class EpaxosReplica:
+    def __init__(self, f, index):
+        self.f, self.n, self.index = f, 2 * f + 1, index
+        self.fast_quorum, self.slow_quorum = self.n - 1, f + 1       # S/epaxos/Config.scala:8-9
+        self.cmd_log = {}          # instance -> ("preaccepted" | "accepted", ballot, voteBallot, value, seq, deps) | ("committed", value, seq, deps)
+        self.leader_states = {}    # instance -> dict
+        self.largest_ballot = NULL_BALLOT
+
+    @staticmethod
+    def _union(a, b):
+        return tuple(max(x, y) for x, y in zip(a, b))
+
+    def _check_can_lead(self, instance, ballot):  # the match of :662-681 / :744-764
+        e = self.cmd_log.get(instance)
+        if e is None:
+            return
+        if e[0] == "committed":
+            raise Fatal("already committed")
+        if not (e[1] <= ballot and e[2] <= ballot):                  # checkLe(ballot), checkLe(voteBallot)
+            raise Fatal("checkLe")
+
+    def transition_to_pre_accept_phase(self, instance, ballot, value, seq, deps, avoid_fast_path):  # :633-729
+        self._check_can_lead(instance, ballot)
+        self.cmd_log[instance] = ("preaccepted", ballot, ballot, value, seq, deps)           # :683-693
+        self.leader_states[instance] = {"kind": "preaccepting", "ballot": ballot, "value": value,
+                                        "responses": {self.index: (seq, deps)},               # :716-724
+                                        "avoid": avoid_fast_path, "timer": False}
+
+    def transition_to_accept_phase(self, instance, ballot, value, seq, deps):  # :732-793
+        self._check_can_lead(instance, ballot)
+        self.cmd_log[instance] = ("accepted", ballot, ballot, value, seq, deps)              # :766-768
+        self.leader_states[instance] = {"kind": "accepting", "ballot": ballot, "value": value, "seq": seq, "deps": deps,
+                                        "responses": {self.index}}                             # :781-789
+
+    def commit(self, instance, value, seq, deps):  # :815-831
+        self.cmd_log[instance] = ("committed", value, seq, deps)
+        self.leader_states.pop(instance, None)
+
+    def handle_pre_accept(self, instance, ballot, value, seq, local_deps, msg_deps):  # :1159-1289
+        nack = ("nack", self.largest_ballot)                                                  # :1166-1167
+        e = self.cmd_log.get(instance)
+        if e is not None:
+            if e[0] == "preaccepted":
+                if ballot < e[1]:                                                             # :1188-1191
+                    return nack
+                if ballot == e[2]:                                                            # :1195-1208
+                    return ("ok", ballot, e[4], e[5])
+            elif e[0] == "accepted":
+                if ballot < e[1]:                                                             # :1212-1215
+                    return nack
+                if ballot == e[2]:                                                            # :1219-1221
+                    return ("none", ballot)
+            elif e[0] == "committed":                                                         # :1223-1234
+                return ("commit", e[2], e[3])
+        ls = self.leader_states.get(instance)                                                 # :1240-1244
+        if ls is not None and ballot > ls["ballot"]:
+            del self.leader_states[instance]
+        self.largest_ballot = max(self.largest_ballot, ballot)                                # :1246
+        seq = max(0, seq)                                                                     # (0, deps) :599, :1256
+        deps = self._union(local_deps, msg_deps)                                              # :1257
+        self.cmd_log[instance] = ("preaccepted", ballot, ballot, value, seq, deps)            # :1260-1271
+        return ("ok", ballot, seq, deps)                                                      # :1278-1288
+
+    def handle_accept(self, instance, ballot, value, seq, deps):  # :1421-1512
+        nack = ("nack", self.largest_ballot)
+        e = self.cmd_log.get(instance)
+        if e is not None:
+            if e[0] == "preaccepted":
+                if ballot < e[1]:                                                             # :1439-1444
+                    return nack
+            elif e[0] == "accepted":
+                if ballot < e[1]:                                                             # :1448-1451
+                    return nack
+                if ballot == e[2]:                                                            # :1455-1464
+                    return ("ok", ballot, 0, None)
+            elif e[0] == "committed":                                                         # :1466-1477
+                return ("commit", e[2], e[3])
+        ls = self.leader_states.get(instance)                                                 # :1482-1486
+        if ls is not None and ballot > ls["ballot"]:
+            del self.leader_states[instance]
+        self.largest_ballot = max(self.largest_ballot, ballot)                                # :1489
+        self.cmd_log[instance] = ("accepted", ballot, ballot, value, seq, deps)               # :1495-1504
+        return ("ok", ballot, 0, None)                                                        # :1506-1511
+
+    def pre_accepting_slow_path(self, instance, ls):  # :796-813
+        answers = set(ls["responses"].values())
+        seq = max(a[0] for a in answers)
+        deps = (0,) * self.n
+        for a in answers:
+            deps = self._union(deps, a[1])
+        self.transition_to_accept_phase(instance, ls["ballot"], ls["value"], seq, deps)
+        return ("slow", seq, deps)
+
+    def handle_pre_accept_ok(self, instance, ballot, replica_index, seq, deps):  # :1291-1419
+        ls = self.leader_states.get(instance)
+        if ls is None or ls["kind"] != "preaccepting":                                        # :1295-1315
+            return None
+        if ballot != ls["ballot"]:                                                            # :1325-1335 (a larger one is checkLt-fatal)
+            return None
+        responses = ls["responses"]
+        old = len(responses)
+        responses[replica_index] = (seq, deps)                                                # :1339-1341
+        new = len(responses)
+        if new < self.slow_quorum:                                                            # :1345-1347
+            return None
+        if (not ls["avoid"] and old < self.slow_quorum <= new and self.slow_quorum < self.fast_quorum):   # :1353-1364
+            ls["timer"] = True
+            return ("timer",)
+        if ls["avoid"] and new >= self.slow_quorum:                                           # :1369-1372
+            return self.pre_accepting_slow_path(instance, ls)
+        if new >= self.fast_quorum:                                                           # :1376-1417
+            seq_deps = [v for k, v in responses.items() if k != self.index]                   # :1382-1393
+            candidates = {x for x in seq_deps if seq_deps.count(x) >= self.fast_quorum - 1}   # Util.popularItems
+            if candidates:
+                (s, d), = candidates                                                          # checkEq(size, 1)
+                self.commit(instance, ls["value"], s, d)                                      # :1401-1410
+                return ("fast", s, d)
+            return self.pre_accepting_slow_path(instance, ls)                                 # :1412-1415
+        return None
+
+    def handle_accept_ok(self, instance, ballot, replica_index):  # :1514-1565
+        ls = self.leader_states.get(instance)
+        if ls is None or ls["kind"] != "accepting":
+            return None
+        if ballot != ls["ballot"]:                                                            # :1543-1552
+            return None
+        ls["responses"].add(replica_index)                                                    # :1554-1555
+        if len(ls["responses"]) < self.slow_quorum:                                           # :1558-1560
+            return None
+        seq, deps = ls["seq"], ls["deps"]
+        self.commit(instance, ls["value"], seq, deps)                                         # :1563
+        return ("commit", seq, deps)
