@@ -305,6 +305,22 @@ class VanillaServer:
     def handle_chosen(self, slot, value):  # :1170-1197 without advanceWithSkips / executeLog
         self.choose(slot, value)
 
+    NOOP = -(1 << 31)   # value id of CommandOrNoop().withNoop(Noop())
+
+    def fill_own_skips(self, next_slot, new_stop):  # the log fill of advanceWithSkips (:607-620); returns nextSlot
+        while next_slot < new_stop:
+            if next_slot in self.log or next_slot in self.phase2s:                         # logger.check (:613-614)
+                raise Fatal("skipping a slot that is not vacant")
+            self.log[next_slot] = ("chosen", self.NOOP)                                    # :615-618
+            next_slot += self.n                                                            # nextClassicRound(index, nextSlot)
+        return next_slot
+
+    def handle_skip(self, start, stop):  # :1144-1168 without executeLog
+        slot = start
+        while slot < stop:
+            self.choose(slot, self.NOOP)
+            slot += self.n                                                                 # nextClassicRound(coordinator, slot)
+
 
 class VanillaSystem:
     """n co-located servers driven with the record shapes of fpx_vm_* (include/fpx.h)."""

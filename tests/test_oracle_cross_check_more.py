@@ -15,6 +15,8 @@ vm_step = st.one_of(
     st.tuples(st.just("p2a"), st.lists(st.tuples(slot, st.integers(0, 3), st.integers(0, 50), st.integers(0, 6)), min_size=1, max_size=24)),
     st.tuples(st.just("p2b"), st.lists(st.tuples(st.integers(0, 6), slot, st.integers(0, 3)), min_size=1, max_size=24)),
     st.tuples(st.just("learn"), st.lists(st.tuples(st.integers(0, 6), slot, st.integers(0, 50)), min_size=1, max_size=4)),
+    # (server, start, length, own): own = the skipping server's log fill, else handleSkip at another server
+    st.tuples(st.just("skip"), st.lists(st.tuples(st.integers(0, 6), slot, st.integers(0, 9), st.booleans()), min_size=1, max_size=3)),
 )
 
 
@@ -39,10 +41,30 @@ def test_vanilla_mencius_oracle_agrees_with_the_transcription(f, script):
             assert (st_, idx) == (rst, ridx) and c.tolist() == rc
             if st_ != 0:
                 return
-        else:
+        elif kind == "learn":
             b = np.array([(0, srv % n, s, v) for srv, s, v in recs], dtype=P2B)
             ora.learn_chosen(b)
             ref.learn_chosen(b.tolist())
+        else:
+            for srv, start, length, own in recs:
+                srv, stop = srv % n, min(NSLOTS, start + length)
+                if own:
+                    start += (srv - start) % n                      # the skipping server's own slots (slot % n == server)
+                    if start > NSLOTS:
+                        continue                                    # outside the log: a precondition of the call
+                    if start > stop:
+                        stop = start
+                want = (0, -1)
+                try:
+                    if own:
+                        ref.servers[srv].fill_own_skips(start, stop)
+                    else:
+                        ref.servers[srv].handle_skip(start, stop)
+                except S.Fatal:
+                    want = (-14, 0)
+                assert ora.skip(np.array([(srv, start, stop, int(own))], dtype=O.VM_SKIP), NSLOTS) == want
+                if want[0] != 0:
+                    return
     for srv in range(n):
         k, r, v = ora.snapshot(srv, 0, NSLOTS)
         for s in range(NSLOTS):
