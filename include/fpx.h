@@ -257,7 +257,11 @@ int fpx_acceptor_phase1a(fpx_engine* e, int32_t group, int32_t acceptor, int32_t
  * acceptors that answered Phase 1 (responders: bit group*acceptors_per_group+index)
  * and may vote on the slot -- safeValue -- or vote_round = -1 / value_id = -1 where
  * none voted (Noop is safe).  *max_slot = the largest slot with a vote among the
- * responders (maxPhase1bSlot, :303-312), -1 if none. */
+ * responders (maxPhase1bSlot, :303-312), -1 if none.
+ * Flexible grids: the reference's fill-in literally reads phase1bs(slot % numAcceptorGroups)
+ * (:553), i.e. ONE grid row per slot, although every acceptor of the grid may hold a vote
+ * for the slot; this call takes the maximum over ALL responders (never a lower round than
+ * the reference's answer; identical whenever that row holds the responders' highest vote). */
 int fpx_leader_safe_values(fpx_engine* e, uint32_t responders, int32_t first_slot, int32_t n_slots,
                            int32_t* vote_round, int32_t* value_id, int32_t* max_slot);
 

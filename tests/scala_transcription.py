@@ -57,6 +57,27 @@ class Acceptor:  # S/multipaxos/Acceptor.scala:59-104
         self.round = round_
         return -1
 
+    def phase1b_info(self, chosen_watermark):  # states.iteratorFrom(phase1a.chosenWatermark) (:171-179)
+        return [(slot, vr, vv) for slot, (vr, vv) in sorted(self.states.items()) if slot >= chosen_watermark]
+
+
+def leader_fill_in(phase1bs, num_groups, chosen_watermark):
+    """Leader.handlePhase1b once the quorum is there (S/multipaxos/Leader.scala:536-562): phase1bs[group] =
+    {acceptorIndex: info}.  Returns (maxSlot, [(slot, voteRound or -1, value or None)]) for chosenWatermark..maxSlot:
+    safeValue (:318-329) = the vote with the highest voteRound among the Phase1bs of group slot % numAcceptorGroups
+    (:553), Noop when none.  NB the literal reference consults that ONE group also on a flexible grid."""
+    max_slot = max([max([i[0] for i in info], default=-1) for group in phase1bs for info in group.values()], default=-1)   # :303-312, :541-546
+    out = []
+    for slot in range(chosen_watermark, max_slot + 1):
+        group = phase1bs[slot % num_groups]                                                  # :553
+        infos = [i for info in group.values() for i in info if i[0] == slot]                  # info.find(_.slot == slot)
+        if not infos:
+            out.append((slot, -1, None))                                                      # Noop (:324-325)
+        else:
+            best = max(infos, key=lambda i: i[1])                                             # maxBy(_.voteRound) (:327)
+            out.append((slot, best[1], best[2]))
+    return max_slot, out
+
 
 class ProxyLeader:  # S/multipaxos/ProxyLeader.scala:67-258
     DONE = "Done"

@@ -216,3 +216,51 @@ def test_epaxos_directed_rounds_reach_every_decision():
             e = ref.cmd_log[inst]
             assert out[0] == {"preaccepted": 2, "accepted": 3, "committed": 4}[e[0]]
     assert seen == {0, 1, 2, 3, 4}
+
+
+# --------------------------------------------------------------------------- Phase 1 reads
+@settings(max_examples=300, deadline=None)
+@given(shape=st.sampled_from(["majority3", "majority5", "groups2x3", "grid2x3"]),
+       votes=st.lists(st.tuples(st.integers(0, 14), st.integers(0, 3), st.integers(0, 1), st.integers(0, 4)), min_size=0, max_size=40),
+       responders=st.integers(1, (1 << 6) - 1), watermark=st.integers(0, 6))
+def test_phase1_reads_agree_with_the_transcription(shape, votes, responders, watermark):
+    """Acceptor.handlePhase1a's Phase1b info + Leader.handlePhase1b's fill-in (safeValue per slot, maxSlot) from the
+    Scala against fpo_mp_safe_values.  Votes are made consistent the way correct acceptors' are: one value per
+    (slot, round).  On a flexible grid the reference literally consults only the Phase1bs of grid row
+    slot % numAcceptorGroups (Leader.scala:553); the engine's contract (include/fpx.h) is the maximum over ALL
+    responders, so there the check is the documented relation: same answer whenever the reference's row holds the
+    highest-round vote among the responders, never a lower round."""
+    f, G, A, flexible, L = {"majority3": (1, 1, 3, False, 2), "majority5": (2, 1, 5, False, 3), "groups2x3": (1, 2, 3, False, 2),
+                            "grid2x3": (1, 2, 3, True, 2)}[shape]
+    ora = O.MultiPaxos(f, G, A, flexible, L, f + 1)
+    accs = [[S.Acceptor(g, a, L) for a in range(A)] for g in range(G)]
+    recs = []
+    for slot_, rnd, g, a in sorted(votes, key=lambda v: v[1]):          # rounds never decrease at an acceptor
+        g, a = (g % G, a % A) if flexible else (slot_ % G, a % A)
+        recs.append((slot_, rnd, 100 * slot_ + rnd, (g << 16) | a))
+    if recs:
+        arr = np.array(recs, dtype=P2A)
+        st_, _, ob, on = ora.acceptor_phase2a(arr)
+        assert st_ == 0
+        for slot_, rnd, val, dst in recs:
+            accs[dst >> 16][dst & 0xffff].handle_phase2a(slot_, rnd, val)
+    responders &= (1 << (G * A)) - 1
+    if responders == 0:
+        responders = 1
+    phase1bs = [{a: accs[g][a].phase1b_info(watermark) for a in range(A) if (responders >> (g * A + a)) & 1} for g in range(G)]
+    max_slot, fill = S.leader_fill_in(phase1bs, G, watermark)
+    n_slots = 16 - watermark
+    vr, vv, mx = ora.safe_values(responders, watermark, n_slots)
+    if not flexible:
+        assert mx == max_slot
+        want = {s: (r, v) for s, r, v in fill}
+        for i in range(n_slots):
+            r, v = want.get(watermark + i, (-1, None))
+            assert (vr[i], vv[i]) == (r, -1 if v is None else v)
+    else:
+        assert mx == max_slot                      # maxPhase1bSlot ranges over every Phase1b (:541-546)
+        for s, r, v in fill:
+            i = s - watermark
+            assert vr[i] >= r
+            if vr[i] == r and r >= 0:
+                assert vv[i] == v
