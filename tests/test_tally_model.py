@@ -53,3 +53,41 @@ def test_closed_form_completing_vote_matches_the_sequential_handlers(name, seed)
         assert oc.tolist() == want
         seq += len(chunk)
     assert (np.sort(stamps, axis=1)[:, f] != EMPTY).all() if not flexible else True
+
+
+@pytest.mark.parametrize("seed", [0, 1, 2, 3])
+def test_keyed_prefix_max_rule_of_the_acceptor_kernel_matches_the_sequential_handler(seed):
+    """fpx_acceptor.cuh: `round` is one scalar per acceptor (Acceptor.scala:95), so record i to acceptor k is accepted
+    iff round_i >= max(round_k at batch start, max over earlier records j to k of round_j) -- rejected records are
+    below the running max, so including them changes nothing -- and a Nack carries that running max.  numpy's
+    keyed exclusive prefix-max against the oracle's sequential handler, rounds going up and down."""
+    cfg, _ = T.config_by_name("cfg2")
+    f, G, A = cfg["f"], cfg["num_acceptor_groups"], cfg["acceptors_per_group"]
+    g = T.rng(900 + seed)
+    ora = O.MultiPaxos(f, G, A, False, cfg["num_leaders"], cfg["num_replicas"])
+    start = np.full(A, -1, dtype=np.int64)
+    for batch in range(4):
+        n = 5000
+        recs = np.zeros(n, dtype=T.P2A)
+        recs["slot"] = g.integers(0, 4000, n)
+        # mostly one round, sprinkled with higher and lower ones (leader changes, stale leaders)
+        recs["round"] = batch + g.choice([0, 0, 0, 0, 0, 0, 1, 2, -1], n).clip(-batch, None)
+        recs["value_id"] = g.integers(0, 1 << 20, n)
+        acc = g.integers(0, A, n)
+        recs["dst"] = acc
+        st, _, ob, on = ora.acceptor_phase2a(recs)
+        assert st == 0
+        run = np.empty(n, dtype=np.int64)                     # exclusive prefix max per acceptor, seeded with `start`
+        for k in range(A):
+            idx = np.nonzero(acc == k)[0]
+            r = recs["round"][idx].astype(np.int64)
+            incl = np.maximum.accumulate(np.concatenate([[start[k]], r]))
+            run[idx] = incl[:-1]
+            start[k] = incl[-1]
+        accept = recs["round"] >= run
+        assert ob["slot"].tolist() == recs["slot"][accept].tolist() and ob["round"].tolist() == recs["round"][accept].tolist()
+        assert ob["acceptor"].tolist() == acc[accept].tolist()
+        assert on["round"].tolist() == run[~accept].tolist()                     # Nack(round) (:197-198)
+        assert on["leader"].tolist() == (recs["round"][~accept] % cfg["num_leaders"]).tolist()
+        for k in range(A):
+            assert ora.snapshot_acceptor(0, k, 0, 1)[0] == start[k]
